@@ -1,0 +1,118 @@
+"""ctypes loader for libqsim_b200.so (the C ABI declared in include/qsim_b200.h).
+
+There is deliberately no fallback: if the shared library is missing, or a call needs a GPU and none
+is present, the error propagates.  Nothing in this package imports the CPU oracle under oracle/.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_uint, c_uint64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqsim_b200.so")
+
+#: numpy mirror of qsim_gate_t (== GateOp of the reference, include/Circuit.hpp:64-84)
+GATE_DTYPE = np.dtype([("type", "<i4"), ("q0", "<i4"), ("q1", "<i4"), ("q2", "<i4"), ("param", "<f8")], align=True)
+assert GATE_DTYPE.itemsize == 24
+
+
+class QsimError(RuntimeError):
+    """std::runtime_error of the C++ API (CUDA failures, unknown gate, zero-probability outcome)."""
+
+
+class InvalidArgument(ValueError):
+    """std::invalid_argument of the C++ API."""
+
+
+class OutOfRange(IndexError):
+    """std::out_of_range of the C++ API."""
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise QsimError(
+                f"{LIB_PATH} not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        _lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_LOCAL)
+        _declare(_lib)
+    return _lib
+
+
+def check(status: int) -> None:
+    if status == 0:
+        return
+    msg = lib().qsim_last_error().decode("utf-8", "replace")
+    if status == 1:
+        raise InvalidArgument(msg)
+    if status == 2:
+        raise OutOfRange(msg)
+    raise QsimError(msg)
+
+
+def _declare(L: ctypes.CDLL) -> None:
+    P = c_void_p
+    PP = POINTER(c_void_p)
+    sig = {
+        "qsim_last_error": (c_char_p, []),
+        "qsim_version": (c_char_p, []),
+        "qsim_max_qubits": (c_int, []),
+        "qsim_circuit_validate": (c_int, [c_int, P, c_int64]),
+        "qsim_circuit_random": (c_int, [c_int, c_int, c_uint, P]),
+        "qsim_circuit_ghz": (c_int, [c_int, P]),
+        "qsim_circuit_depth": (c_int, [c_int, P, c_int64, POINTER(c_int64)]),
+        "qsim_program_compile": (c_int, [c_int, c_int, P, c_int64, PP]),
+        "qsim_program_destroy": (None, [P]),
+        "qsim_program_info": (c_int, [P, POINTER(c_int64)]),
+        "qsim_program_describe": (c_size_t, [P, c_char_p, c_size_t]),
+        "qsim_sim_create": (c_int, [c_int, PP]),
+        "qsim_sim_create_external": (c_int, [c_int, P, PP]),
+        "qsim_sim_destroy": (None, [P]),
+        "qsim_sim_set_stream": (c_int, [P, P]),
+        "qsim_sim_reset": (c_int, [P]),
+        "qsim_sim_init_basis": (c_int, [P, c_uint64]),
+        "qsim_sim_set_state": (c_int, [P, P]),
+        "qsim_sim_run": (c_int, [P, c_int, P, c_int64]),
+        "qsim_sim_apply_gate": (c_int, [P, P]),
+        "qsim_sim_execute": (c_int, [P, P]),
+        "qsim_sim_synchronize": (c_int, [P]),
+        "qsim_sim_get_state": (c_int, [P, P]),
+        "qsim_sim_get_probabilities": (c_int, [P, P]),
+        "qsim_sim_get_probability_range": (c_int, [P, c_uint64, c_uint64, P]),
+        "qsim_sim_total_probability": (c_int, [P, POINTER(c_double)]),
+        "qsim_sim_sample_uniforms": (c_int, [P, P, c_int64, P]),
+        "qsim_sim_sample_seeded": (c_int, [P, c_uint, c_int64, P]),
+        "qsim_sim_measure": (c_int, [P, c_int, c_double, POINTER(c_int)]),
+        "qsim_sim_measure_bit": (c_int, [P, c_int, c_double, POINTER(c_int), POINTER(c_double)]),
+        "qsim_sim_num_qubits": (c_int, [P]),
+        "qsim_sim_device_ptr": (c_void_p, [P]),
+        "qsim_sim_launch_count": (c_int64, [P]),
+        "qsim_sim_set_timing": (c_int, [P, c_int]),
+        "qsim_sim_pass_time_ms": (c_int, [P, POINTER(c_double), POINTER(c_int64)]),
+        "qsim_shard_create": (c_int, [c_int, c_int, c_int, P, PP]),
+        "qsim_shard_swap_p2p": (c_int, [P, P, c_int, c_int]),
+        "qsim_shard_pack_half": (c_int, [P, c_int, c_int, c_int64, c_int64, P]),
+        "qsim_shard_unpack_half": (c_int, [P, c_int, c_int, c_int64, c_int64, P]),
+        "qsim_ipc_get_handle": (c_int, [P, P, POINTER(c_uint64)]),
+        "qsim_ipc_open_handle": (c_int, [P, PP]),
+        "qsim_ipc_close_handle": (c_int, [P]),
+        "qsim_shard_partial_probability": (c_int, [P, c_int, POINTER(c_double)]),
+        "qsim_shard_collapse": (c_int, [P, c_int, c_int, c_double]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)   # AttributeError here == the library does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    L._qsim_declared = tuple(sig)
+
+
+def gates_ptr(gates: np.ndarray) -> c_void_p:
+    assert gates.dtype == GATE_DTYPE and gates.flags["C_CONTIGUOUS"]
+    return gates.ctypes.data_as(c_void_p)

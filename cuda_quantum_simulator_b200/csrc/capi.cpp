@@ -1,0 +1,480 @@
+// C ABI (include/qsim_b200.h) over the qsim C++ classes.  Exceptions become status codes:
+// invalid_argument -> 1, out_of_range -> 2, anything else -> 3; the message is kept per thread.
+#include "qsim_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "engine.hpp"
+#include "program.hpp"
+#include "qsim/circuit.hpp"
+#include "qsim/constants.hpp"
+#include "qsim/simulator.hpp"
+#include "shard.cuh"
+
+using namespace qsim;
+
+namespace {
+
+thread_local std::string g_error;
+
+template <class F>
+qsim_status_t guarded(F&& body) {
+    try {
+        body();
+        return QSIM_OK;
+    } catch (const std::invalid_argument& e) {
+        g_error = e.what();
+        return QSIM_ERR_INVALID_ARGUMENT;
+    } catch (const std::out_of_range& e) {
+        g_error = e.what();
+        return QSIM_ERR_OUT_OF_RANGE;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return QSIM_ERR_RUNTIME;
+    } catch (...) {
+        g_error = "unknown error";
+        return QSIM_ERR_RUNTIME;
+    }
+}
+
+void require(bool cond, const char* what) {
+    if (!cond) throw std::invalid_argument(what);
+}
+
+// Replays a gate record through the fluent builder so that validation is the builder's own.
+void append(Circuit& c, const qsim_gate_t& g) {
+    switch (g.type) {
+        case QSIM_GATE_X: c.x(g.q0); break;
+        case QSIM_GATE_Y: c.y(g.q0); break;
+        case QSIM_GATE_Z: c.z(g.q0); break;
+        case QSIM_GATE_H: c.h(g.q0); break;
+        case QSIM_GATE_S: c.s(g.q0); break;
+        case QSIM_GATE_T: c.t(g.q0); break;
+        case QSIM_GATE_SDAG: c.sdag(g.q0); break;
+        case QSIM_GATE_TDAG: c.tdag(g.q0); break;
+        case QSIM_GATE_RX: c.rx(g.q0, g.param); break;
+        case QSIM_GATE_RY: c.ry(g.q0, g.param); break;
+        case QSIM_GATE_RZ: c.rz(g.q0, g.param); break;
+        case QSIM_GATE_CNOT: c.cnot(g.q0, g.q1); break;
+        case QSIM_GATE_CZ: c.cz(g.q0, g.q1); break;
+        case QSIM_GATE_CRY: c.cry(g.q0, g.q1, g.param); break;
+        case QSIM_GATE_CRZ: c.crz(g.q0, g.q1, g.param); break;
+        case QSIM_GATE_SWAP: c.swap(g.q0, g.q1); break;
+        case QSIM_GATE_TOFFOLI: c.toffoli(g.q0, g.q1, g.q2); break;
+        default: throw std::runtime_error("Unknown gate type");
+    }
+}
+
+Circuit build(int n, const qsim_gate_t* gates, int64_t ng) {
+    Circuit c(n);
+    for (int64_t i = 0; i < ng; ++i) append(c, gates[i]);
+    return c;
+}
+
+void emit(const Circuit& c, qsim_gate_t* out) {
+    size_t i = 0;
+    for (const GateOp& g : c.getGates()) {
+        qsim_gate_t r{static_cast<int32_t>(g.type), -1, -1, -1, g.parameter};
+        if (g.qubits.size() > 0) r.q0 = g.qubits[0];
+        if (g.qubits.size() > 1) r.q1 = g.qubits[1];
+        if (g.qubits.size() > 2) r.q2 = g.qubits[2];
+        out[i++] = r;
+    }
+}
+
+}  // namespace
+
+struct qsim_program {
+    b200::DeviceProgram dev;
+    int n_global = 0;
+};
+
+struct qsim_sim {
+    std::unique_ptr<Simulator> sim;
+    int n_total = 0;
+    int n_global = 0;
+    int rank = 0;
+    uint64_t hi_bits() const { return (uint64_t)rank << (n_total - n_global); }
+};
+
+extern "C" {
+
+const char* qsim_last_error(void) { return g_error.c_str(); }
+const char* qsim_version(void) { return "qsim_b200 0.1 (sm_100a fused-pass engine)"; }
+int qsim_max_qubits(void) { return cuda_config::MAX_QUBITS; }
+
+// ---- circuits ---------------------------------------------------------------------------------
+
+qsim_status_t qsim_circuit_validate(int n, const qsim_gate_t* gates, int64_t ng) {
+    return guarded([&] { build(n, gates, ng); });
+}
+
+qsim_status_t qsim_circuit_random(int n, int depth, unsigned seed, qsim_gate_t* out) {
+    return guarded([&] { emit(createRandomCircuit(n, depth, seed), out); });
+}
+
+qsim_status_t qsim_circuit_ghz(int n, qsim_gate_t* out) {
+    return guarded([&] { emit(createGHZCircuit(n), out); });
+}
+
+qsim_status_t qsim_circuit_depth(int n, const qsim_gate_t* gates, int64_t ng, int64_t* depth) {
+    return guarded([&] { *depth = (int64_t)build(n, gates, ng).getDepth(); });
+}
+
+// ---- programs ---------------------------------------------------------------------------------
+
+qsim_status_t qsim_program_compile(int n, int n_global, const qsim_gate_t* gates, int64_t ng, qsim_program_t** out) {
+    return guarded([&] {
+        require(out != nullptr, "null output");
+        require(n_global >= 0 && n_global < n, "n_global out of range");
+        build(n, gates, ng);   // validation only
+        auto p = std::make_unique<qsim_program>();
+        p->n_global = n_global;
+        b200::CompileOptions opt;
+        opt.n_global = n_global;
+        std::string err;
+        if (!b200::compile(n, gates, ng, opt, p->dev.host, &err)) throw std::runtime_error(err);
+        p->dev.upload();
+        *out = p.release();
+    });
+}
+
+void qsim_program_destroy(qsim_program_t* p) { delete p; }
+
+qsim_status_t qsim_program_info(const qsim_program_t* p, int64_t info[8]) {
+    return guarded([&] {
+        require(p != nullptr, "null program");
+        const b200::Program& h = p->dev.host;
+        int64_t sweeps = 0;
+        for (auto& ps : h.passes) sweeps += ps.n_sweeps;
+        info[0] = (int64_t)h.passes.size();
+        info[1] = (int64_t)h.lops.size();
+        info[2] = h.n_gates;
+        info[3] = sweeps;
+        info[4] = h.passes.empty() ? 0 : h.passes[0].t;
+        info[5] = h.n_local;
+        info[6] = info[7] = 0;
+    });
+}
+
+size_t qsim_program_describe(const qsim_program_t* p, char* buf, size_t cap) {
+    if (!p) return 0;
+    const std::string d = p->dev.host.describe();
+    if (buf && cap) {
+        const size_t k = d.size() < cap - 1 ? d.size() : cap - 1;
+        std::memcpy(buf, d.data(), k);
+        buf[k] = 0;
+    }
+    return d.size() + 1;
+}
+
+// ---- simulator --------------------------------------------------------------------------------
+
+qsim_status_t qsim_sim_create(int n, qsim_sim_t** out) {
+    return guarded([&] {
+        require(out != nullptr, "null output");
+        auto s = std::make_unique<qsim_sim>();
+        s->sim = std::make_unique<Simulator>(n);
+        s->n_total = n;
+        *out = s.release();
+    });
+}
+
+qsim_status_t qsim_sim_create_external(int n, void* device_state, qsim_sim_t** out) {
+    return guarded([&] {
+        require(out != nullptr, "null output");
+        auto s = std::make_unique<qsim_sim>();
+        s->sim = std::make_unique<Simulator>(n, static_cast<cuDoubleComplex*>(device_state));
+        s->n_total = n;
+        *out = s.release();
+    });
+}
+
+qsim_status_t qsim_shard_create(int n, int n_global, int rank, void* device_state, qsim_sim_t** out) {
+    return guarded([&] {
+        require(out != nullptr, "null output");
+        require(isValidQubitCount(n), "Number of qubits out of range");
+        require(n_global >= 0 && n_global < n, "n_global out of range");
+        require(rank >= 0 && rank < (1 << n_global), "rank out of range");
+        auto s = std::make_unique<qsim_sim>();
+        const int nl = n - n_global;
+        if (device_state) s->sim = std::make_unique<Simulator>(nl, static_cast<cuDoubleComplex*>(device_state));
+        else s->sim = std::make_unique<Simulator>(nl);
+        s->n_total = n;
+        s->n_global = n_global;
+        s->rank = rank;
+        // |0...0> lives on rank 0 only
+        if (rank != 0) {
+            CUDA_CHECK(cudaMemsetAsync(s->sim->state().devicePtr(), 0, s->sim->getStateSize() * sizeof(cuDoubleComplex),
+                                       s->sim->state().engine().stream()));
+            s->sim->synchronize();
+        } else if (device_state) {
+            s->sim->reset();
+        }
+        *out = s.release();
+    });
+}
+
+void qsim_sim_destroy(qsim_sim_t* s) { delete s; }
+
+qsim_status_t qsim_sim_set_stream(qsim_sim_t* s, void* stream) {
+    return guarded([&] {
+        require(s != nullptr, "null simulator");
+        s->sim->state().engine().setStream(static_cast<cudaStream_t>(stream));
+    });
+}
+
+qsim_status_t qsim_sim_reset(qsim_sim_t* s) {
+    return guarded([&] {
+        require(s != nullptr, "null simulator");
+        if (s->n_global && s->rank != 0) {
+            CUDA_CHECK(cudaMemsetAsync(s->sim->state().devicePtr(), 0, s->sim->getStateSize() * sizeof(cuDoubleComplex),
+                                       s->sim->state().engine().stream()));
+            s->sim->synchronize();
+        } else s->sim->reset();
+    });
+}
+
+qsim_status_t qsim_sim_init_basis(qsim_sim_t* s, uint64_t idx) {
+    return guarded([&] { require(s != nullptr, "null simulator"); s->sim->state().initializeBasis(idx); });
+}
+
+qsim_status_t qsim_sim_set_state(qsim_sim_t* s, const double* amps) {
+    return guarded([&] {
+        require(s != nullptr && amps != nullptr, "null argument");
+        s->sim->state().setFromHost(reinterpret_cast<const std::complex<double>*>(amps));
+    });
+}
+
+qsim_status_t qsim_sim_run(qsim_sim_t* s, int circuit_qubits, const qsim_gate_t* gates, int64_t ng) {
+    return guarded([&] {
+        require(s != nullptr, "null simulator");
+        Circuit c = build(circuit_qubits, gates, ng);
+        if (s->n_global == 0) { s->sim->run(c); return; }
+        if (circuit_qubits != s->n_total) throw std::invalid_argument("Circuit qubit count doesn't match simulator");
+        b200::Program prog;
+        b200::CompileOptions opt;
+        opt.n_global = s->n_global;
+        std::string err;
+        if (!b200::compile(s->n_total, gates, ng, opt, prog, &err)) throw std::runtime_error(err);
+        s->sim->state().engine().execute(prog, s->sim->state().devicePtr(), s->hi_bits());
+    });
+}
+
+qsim_status_t qsim_sim_apply_gate(qsim_sim_t* s, const qsim_gate_t* g) {
+    return guarded([&] {
+        require(s != nullptr && g != nullptr, "null argument");
+        Circuit c = build(s->n_total, g, 1);
+        if (s->n_global == 0) s->sim->applyGate(c.getGates()[0]);
+        else {
+            b200::Program prog;
+            b200::CompileOptions opt;
+            opt.n_global = s->n_global;
+            std::string err;
+            if (!b200::compile(s->n_total, g, 1, opt, prog, &err)) throw std::runtime_error(err);
+            s->sim->state().engine().execute(prog, s->sim->state().devicePtr(), s->hi_bits());
+        }
+    });
+}
+
+qsim_status_t qsim_sim_execute(qsim_sim_t* s, const qsim_program_t* p) {
+    return guarded([&] {
+        require(s != nullptr && p != nullptr, "null argument");
+        if (p->dev.host.n != s->n_total || p->n_global != s->n_global)
+            throw std::invalid_argument("Circuit qubit count doesn't match simulator");
+        s->sim->state().engine().execute(p->dev, s->sim->state().devicePtr(), s->hi_bits());
+    });
+}
+
+qsim_status_t qsim_sim_synchronize(qsim_sim_t* s) {
+    return guarded([&] { require(s != nullptr, "null simulator"); s->sim->synchronize(); });
+}
+
+qsim_status_t qsim_sim_get_state(const qsim_sim_t* s, double* out) {
+    return guarded([&] {
+        require(s != nullptr && out != nullptr, "null argument");
+        s->sim->state().toHost(reinterpret_cast<std::complex<double>*>(out));
+    });
+}
+
+qsim_status_t qsim_sim_get_probabilities(const qsim_sim_t* s, double* out) {
+    return guarded([&] {
+        require(s != nullptr && out != nullptr, "null argument");
+        s->sim->state().getProbabilities(out, 0, s->sim->getStateSize());
+    });
+}
+
+qsim_status_t qsim_sim_get_probability_range(const qsim_sim_t* s, uint64_t first, uint64_t count, double* out) {
+    return guarded([&] {
+        require(s != nullptr && out != nullptr, "null argument");
+        s->sim->state().getProbabilities(out, first, count);
+    });
+}
+
+qsim_status_t qsim_sim_total_probability(const qsim_sim_t* s, double* out) {
+    return guarded([&] {
+        require(s != nullptr && out != nullptr, "null argument");
+        *out = s->sim->state().getTotalProbability();
+    });
+}
+
+qsim_status_t qsim_sim_sample_uniforms(qsim_sim_t* s, const double* u, int64_t shots, int64_t* out) {
+    return guarded([&] {
+        require(s != nullptr && u != nullptr && out != nullptr, "null argument");
+        auto v = s->sim->state().sampleWithUniforms(u, shots);
+        std::memcpy(out, v.data(), v.size() * sizeof(int64_t));
+    });
+}
+
+qsim_status_t qsim_sim_sample_seeded(qsim_sim_t* s, unsigned seed, int64_t shots, int64_t* out) {
+    return guarded([&] {
+        require(s != nullptr && out != nullptr, "null argument");
+        auto v = s->sim->state().sampleSeeded(seed, shots);
+        std::memcpy(out, v.data(), v.size() * sizeof(int64_t));
+    });
+}
+
+qsim_status_t qsim_sim_measure(qsim_sim_t* s, int qubit, double r, int* outcome) {
+    return guarded([&] {
+        require(s != nullptr && outcome != nullptr, "null argument");
+        *outcome = s->sim->state().measure(qubit, r);
+    });
+}
+
+qsim_status_t qsim_sim_measure_bit(qsim_sim_t* s, int bit, double r, int* outcome, double* p0) {
+    return guarded([&] {
+        require(s != nullptr && outcome != nullptr, "null argument");
+        *outcome = s->sim->state().measureBit(bit, r, p0);
+    });
+}
+
+int qsim_sim_num_qubits(const qsim_sim_t* s) { return s ? s->n_total : 0; }
+void* qsim_sim_device_ptr(qsim_sim_t* s) { return s ? s->sim->state().devicePtr() : nullptr; }
+int64_t qsim_sim_launch_count(const qsim_sim_t* s) { return s ? s->sim->state().engine().launches() : 0; }
+
+qsim_status_t qsim_sim_set_timing(qsim_sim_t* s, int enabled) {
+    return guarded([&] { require(s != nullptr, "null simulator"); s->sim->state().engine().setTiming(enabled != 0); });
+}
+
+qsim_status_t qsim_sim_pass_time_ms(qsim_sim_t* s, double* total_ms, int64_t* n_passes) {
+    return guarded([&] {
+        require(s != nullptr, "null simulator");
+        s->sim->state().engine().drainTiming(total_ms, n_passes);
+    });
+}
+
+// ---- shards -----------------------------------------------------------------------------------
+
+qsim_status_t qsim_shard_swap_p2p(qsim_sim_t* s, void* peer_state, int global_qubit, int local_qubit) {
+    return guarded([&] {
+        require(s != nullptr && peer_state != nullptr, "null argument");
+        const int nl = s->n_total - s->n_global;
+        require(global_qubit >= nl && global_qubit < s->n_total, "global_qubit is not a global qubit");
+        require(local_qubit >= 0 && local_qubit < nl, "local_qubit is not a local qubit");
+        const int my_bit = (s->rank >> (global_qubit - nl)) & 1;
+        auto& eng = s->sim->state().engine();
+        b200::launch_swap_p2p(s->sim->state().devicePtr(), static_cast<cuDoubleComplex*>(peer_state), nl, local_qubit,
+                              my_bit, eng.numSMs(), eng.stream());
+        eng.countLaunch();
+    });
+}
+
+static void chunk_range(int nl, int64_t chunk, int64_t n_chunks, uint64_t* jb, uint64_t* cnt) {
+    const uint64_t pairs = 1ULL << (nl - 1);
+    const uint64_t per = (pairs + (uint64_t)n_chunks - 1) / (uint64_t)n_chunks;
+    *jb = per * (uint64_t)chunk;
+    *cnt = *jb >= pairs ? 0 : (pairs - *jb < per ? pairs - *jb : per);
+}
+
+qsim_status_t qsim_shard_pack_half(qsim_sim_t* s, int local_qubit, int keep_bit, int64_t chunk, int64_t n_chunks,
+                                   void* buf) {
+    return guarded([&] {
+        require(s != nullptr && buf != nullptr, "null argument");
+        const int nl = s->n_total - s->n_global;
+        require(local_qubit >= 0 && local_qubit < nl && n_chunks > 0 && chunk >= 0 && chunk < n_chunks, "bad argument");
+        uint64_t jb, cnt;
+        chunk_range(nl, chunk, n_chunks, &jb, &cnt);
+        auto& eng = s->sim->state().engine();
+        if (cnt) {
+            b200::launch_pack_half(s->sim->state().devicePtr(), static_cast<cuDoubleComplex*>(buf), local_qubit,
+                                   keep_bit ^ 1, jb, cnt, eng.numSMs(), eng.stream());
+            eng.countLaunch();
+        }
+    });
+}
+
+qsim_status_t qsim_shard_unpack_half(qsim_sim_t* s, int local_qubit, int keep_bit, int64_t chunk, int64_t n_chunks,
+                                     const void* buf) {
+    return guarded([&] {
+        require(s != nullptr && buf != nullptr, "null argument");
+        const int nl = s->n_total - s->n_global;
+        require(local_qubit >= 0 && local_qubit < nl && n_chunks > 0 && chunk >= 0 && chunk < n_chunks, "bad argument");
+        uint64_t jb, cnt;
+        chunk_range(nl, chunk, n_chunks, &jb, &cnt);
+        auto& eng = s->sim->state().engine();
+        if (cnt) {
+            b200::launch_unpack_half(s->sim->state().devicePtr(), static_cast<const cuDoubleComplex*>(buf), local_qubit,
+                                     keep_bit ^ 1, jb, cnt, eng.numSMs(), eng.stream());
+            eng.countLaunch();
+        }
+    });
+}
+
+qsim_status_t qsim_ipc_get_handle(void* device_ptr, unsigned char handle_out[64], uint64_t* offset_out) {
+    return guarded([&] {
+        require(device_ptr != nullptr && handle_out != nullptr, "null argument");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+        b200::require_device();
+        // The driver API is reached through the runtime (no link-time dependency on libcuda.so.1, so the
+        // library still loads on a GPU-less build box).
+        using range_fn = CUresult (*)(CUdeviceptr*, size_t*, CUdeviceptr);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) throw std::runtime_error("cuMemGetAddressRange unavailable");
+        CUdeviceptr base = 0;
+        size_t size = 0;
+        if (reinterpret_cast<range_fn>(fn)(&base, &size, reinterpret_cast<CUdeviceptr>(device_ptr)) != CUDA_SUCCESS)
+            throw std::runtime_error("cuMemGetAddressRange failed");
+        cudaIpcMemHandle_t h;
+        CUDA_CHECK(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+        std::memcpy(handle_out, &h, 64);
+        if (offset_out) *offset_out = (uint64_t)(reinterpret_cast<CUdeviceptr>(device_ptr) - base);
+    });
+}
+
+qsim_status_t qsim_ipc_open_handle(const unsigned char handle[64], void** base_ptr_out) {
+    return guarded([&] {
+        require(handle != nullptr && base_ptr_out != nullptr, "null argument");
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle, 64);
+        CUDA_CHECK(cudaIpcOpenMemHandle(base_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    });
+}
+
+qsim_status_t qsim_ipc_close_handle(void* base_ptr) {
+    return guarded([&] { CUDA_CHECK(cudaIpcCloseMemHandle(base_ptr)); });
+}
+
+qsim_status_t qsim_shard_partial_probability(const qsim_sim_t* s, int bit, double* out) {
+    return guarded([&] {
+        require(s != nullptr && out != nullptr, "null argument");
+        *out = s->sim->state().partialProbability(bit);
+    });
+}
+
+qsim_status_t qsim_shard_collapse(qsim_sim_t* s, int bit, int outcome, double scale) {
+    return guarded([&] {
+        require(s != nullptr, "null simulator");
+        s->sim->state().collapse(bit, outcome, scale);
+    });
+}
+
+}  // extern "C"

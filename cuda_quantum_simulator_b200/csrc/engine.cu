@@ -1,0 +1,148 @@
+#include "engine.hpp"
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "kernels.cuh"
+#include "qsim/constants.hpp"
+
+namespace qsim {
+namespace b200 {
+
+void require_device() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        throw std::runtime_error(
+            "qsim_b200: no CUDA device available - this engine has no CPU fallback (the fused-pass kernels "
+            "require an sm_100a GPU)");
+    }
+}
+
+DeviceProgram::~DeviceProgram() {
+    if (d_ops) cudaFree(d_ops);
+}
+
+void DeviceProgram::upload() {
+    require_device();
+    if (d_ops) { cudaFree(d_ops); d_ops = nullptr; }
+    if (host.ops.empty()) return;
+    CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_ops), host.ops.size() * sizeof(DevOp)));
+    CUDA_CHECK(cudaMemcpy(d_ops, host.ops.data(), host.ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice));
+}
+
+Engine::Engine() {
+    require_device();
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev));
+    int major = 0;
+    CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10)
+        throw std::runtime_error("qsim_b200: kernels are built for sm_100a only (found compute capability " +
+                                 std::to_string(major) + ".x)");
+    CUDA_CHECK(cudaEventCreateWithFlags(&staged_, cudaEventDisableTiming));
+}
+
+Engine::~Engine() {
+    if (d_ops_) cudaFree(d_ops_);
+    if (h_ops_) cudaFreeHost(h_ops_);
+    if (staged_) cudaEventDestroy(staged_);
+    for (auto& e : events_) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto& e : pool_) cudaEventDestroy(e);
+}
+
+void Engine::synchronize() const { CUDA_CHECK(cudaStreamSynchronize(stream_)); }
+
+cudaEvent_t Engine::getEvent() {
+    if (!pool_.empty()) { cudaEvent_t e = pool_.back(); pool_.pop_back(); return e; }
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreate(&e));
+    return e;
+}
+
+void Engine::setTiming(bool on) {
+    timing_ = on;
+    if (!on) {
+        for (auto& e : events_) { pool_.push_back(e.first); pool_.push_back(e.second); }
+        events_.clear();
+    }
+}
+
+void Engine::drainTiming(double* total_ms, int64_t* n_passes) {
+    double tot = 0;
+    for (auto& e : events_) {
+        CUDA_CHECK(cudaEventSynchronize(e.second));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e.first, e.second));
+        tot += ms;
+        pool_.push_back(e.first);
+        pool_.push_back(e.second);
+    }
+    if (total_ms) *total_ms = tot;
+    if (n_passes) *n_passes = (int64_t)events_.size();
+    events_.clear();
+}
+
+void Engine::launchAll(const Program& p, const DevOp* d_ops, cuDoubleComplex* state, uint64_t hi_bits) {
+    for (const PassDesc& pd : p.passes) {
+        PassParams prm;
+        prm.state = state;
+        prm.ops = d_ops + pd.op_offset;
+        prm.hi_bits = hi_bits;
+        prm.n_tiles = 1ULL << (pd.n - pd.t);
+        prm.pd = pd;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (timing_) {
+            e0 = getEvent();
+            e1 = getEvent();
+            CUDA_CHECK(cudaEventRecord(e0, stream_));
+        }
+        CUDA_CHECK(launch_pass(prm, num_sms_, stream_));
+        ++launches_;
+        if (timing_) {
+            CUDA_CHECK(cudaEventRecord(e1, stream_));
+            events_.emplace_back(e0, e1);
+        }
+    }
+}
+
+void Engine::execute(const Program& p, cuDoubleComplex* state, uint64_t hi_bits) {
+    const size_t n = p.ops.size();
+    if (n == 0) return;
+    if (staged_pending_) {           // the pinned buffer may still be in flight from the previous run
+        CUDA_CHECK(cudaEventSynchronize(staged_));
+        staged_pending_ = false;
+    }
+    if (n > h_cap_) {
+        if (h_ops_) cudaFreeHost(h_ops_);
+        h_ops_ = nullptr;
+        size_t cap = n + n / 2 + 64;
+        CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h_ops_), cap * sizeof(DevOp), cudaHostAllocDefault));
+        h_cap_ = cap;
+    }
+    if (n > d_cap_) {
+        // Earlier launches on stream_ may still read the old buffer: free is stream-ordered.
+        if (d_ops_) { CUDA_CHECK(cudaStreamSynchronize(stream_)); cudaFree(d_ops_); }
+        d_ops_ = nullptr;
+        size_t cap = n + n / 2 + 64;
+        CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_ops_), cap * sizeof(DevOp)));
+        d_cap_ = cap;
+    }
+    std::memcpy(h_ops_, p.ops.data(), n * sizeof(DevOp));
+    CUDA_CHECK(cudaMemcpyAsync(d_ops_, h_ops_, n * sizeof(DevOp), cudaMemcpyHostToDevice, stream_));
+    CUDA_CHECK(cudaEventRecord(staged_, stream_));
+    staged_pending_ = true;
+    launchAll(p, d_ops_, state, hi_bits);
+}
+
+void Engine::execute(const DeviceProgram& p, cuDoubleComplex* state, uint64_t hi_bits) {
+    if (p.host.ops.empty()) return;
+    if (!p.d_ops) throw std::runtime_error("qsim_b200: program was not uploaded");
+    launchAll(p.host, p.d_ops, state, hi_bits);
+}
+
+}  // namespace b200
+}  // namespace qsim

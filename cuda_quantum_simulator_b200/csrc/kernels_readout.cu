@@ -1,0 +1,359 @@
+// Read-out kernels: probabilities, reductions, measurement collapse and *bit-exact* sampling.
+//
+// The reference computes its CDF on the host with a sequential fp64 std::partial_sum over 2^n
+// probabilities and answers each shot with std::lower_bound (src/Simulator.cu:164-185,
+// src/StateVector.cu:316-342); measurement sums the masked probabilities sequentially on the host
+// too (src/StateVector.cu:280-287).  A parallel scan rounds differently, so shots that land within
+// rounding distance of a CDF step would come out different.  SequentialCdf reproduces the
+// *sequential* rounding exactly, in parallel, without ever materialising 2^n probabilities:
+//
+//   While the running sum c stays inside one binade [2^e, 2^(e+1)) it is a multiple of
+//   u = 2^(e-52), and fl(c + p) = c + rn_u(p), where rn_u(p) (p rounded to a multiple of u) does
+//   not depend on c — except for exact ties.  So for a chunk of 4096 probabilities known (from an
+//   approximate prefix sum with a rigorous margin) to stay inside binade e, every thread can add
+//   its 16 probabilities to the surrogate start 2^e instead of the unknown c: the increment
+//   comes out identical, and increments are multiples of u that add exactly.  Chunks that may
+//   cross a binade boundary, start at zero, or contain a tie are flagged and replayed
+//   sequentially from the exact start by one warp (a few dozen chunks per sweep).
+//
+// p_i is computed as fl(fl(re*re) + fl(im*im)) — std::norm's rounding on the reference CPU path
+// (src/Simulator.cu:319-325) — with explicit __dmul_rn/__dadd_rn so nvcc cannot contract it.
+#include "readout.cuh"
+
+#include <stdexcept>
+
+#include "qsim/constants.hpp"
+
+namespace qsim {
+namespace b200 {
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr double kMargin = 1.9073486328125e-06;  // 2^-19: twice the (N-1)*2^-53 bound (N <= 2^33) on |sequential - exact| / sum
+
+__device__ __forceinline__ double prob_of(const cuDoubleComplex a) {
+    return __dadd_rn(__dmul_rn(a.x, a.x), __dmul_rn(a.y, a.y));
+}
+
+__device__ __forceinline__ double masked_prob(const cuDoubleComplex* __restrict__ state, uint64_t i, int mask_bit) {
+    if (mask_bit >= 0 && ((i >> mask_bit) & 1)) return 0.0;
+    return prob_of(state[i]);
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = (threadIdx.x < blockDim.x / 32) ? red[threadIdx.x] : 0.0;
+    if (warp == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = __dadd_rn(t, __shfl_xor_sync(0xffffffffu, t, o));
+        if (lane == 0) red[0] = t;
+    }
+    __syncthreads();
+    return red[0];
+}
+
+// ---- plain read-out ----------------------------------------------------------------------------
+
+__global__ void probabilities_range_kernel(const cuDoubleComplex* __restrict__ state, double* __restrict__ out,
+                                           uint64_t first, uint64_t count) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        out[i] = prob_of(state[first + i]);
+}
+
+__global__ void set_basis_kernel(cuDoubleComplex* state, uint64_t idx) { state[idx] = make_cuDoubleComplex(1.0, 0.0); }
+
+// Deterministic two-level reduction of sum |a_i|^2 over indices with bit `mask_bit` == 0.
+__global__ void partial_prob_kernel(const cuDoubleComplex* __restrict__ state, uint64_t n, int mask_bit,
+                                    double* __restrict__ partial) {
+    __shared__ double red[32];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        acc = __dadd_rn(acc, masked_prob(state, i, mask_bit));
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void final_sum_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc = __dadd_rn(acc, partial[i]);
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) *out = s;
+}
+
+__global__ void collapse_kernel(cuDoubleComplex* __restrict__ state, uint64_t n, int bit, int outcome, double scale) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        cuDoubleComplex a = state[i];
+        if ((int)((i >> bit) & 1) != outcome) a = make_cuDoubleComplex(0.0, 0.0);
+        else a = make_cuDoubleComplex(__dmul_rn(a.x, scale), __dmul_rn(a.y, scale));
+        state[i] = a;
+    }
+}
+
+// ---- exact sequential CDF ------------------------------------------------------------------------
+
+// K1: approximate (tree-order) sum of each chunk.
+__global__ void chunk_approx_kernel(const cuDoubleComplex* __restrict__ state, int mask_bit, int chunk,
+                                    double* __restrict__ approx) {
+    __shared__ double red[32];
+    const uint64_t base = (uint64_t)blockIdx.x * chunk;
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < chunk; j += blockDim.x) acc = __dadd_rn(acc, masked_prob(state, base + j, mask_bit));
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) approx[blockIdx.x] = s;
+}
+
+// K2: single-block exclusive scan of the approximate chunk sums: lo[k] = approx start of chunk k.
+__global__ void chunk_scan_kernel(const double* __restrict__ approx, uint64_t m, double* __restrict__ lo) {
+    __shared__ double part[1024];
+    const uint64_t per = (m + blockDim.x - 1) / blockDim.x;
+    const uint64_t b = (uint64_t)threadIdx.x * per, e = (b + per < m) ? b + per : m;
+    double acc = 0.0;
+    for (uint64_t i = b; i < e; ++i) acc += approx[i];
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double run = 0.0;
+        for (int i = 0; i < (int)blockDim.x; ++i) { double v = part[i]; part[i] = run; run += v; }
+    }
+    __syncthreads();
+    double run = part[threadIdx.x];
+    for (uint64_t i = b; i < e; ++i) { lo[i] = run; run += approx[i]; }
+}
+
+enum : uint8_t { CH_ZERO = 0, CH_FAST = 1, CH_SLOW = 2 };
+
+// K3: per chunk, the sequential-order increment computed from the surrogate start 2^e.
+__global__ void chunk_surrogate_kernel(const cuDoubleComplex* __restrict__ state, int mask_bit, int chunk,
+                                       const double* __restrict__ approx, const double* __restrict__ lo,
+                                       double* __restrict__ delta, double* __restrict__ bin_base,
+                                       uint8_t* __restrict__ flag) {
+    __shared__ double ps[4096 + 256];
+    __shared__ double red[32];
+    __shared__ int tie_any;
+    const uint64_t k = blockIdx.x;
+    const double a_lo = lo[k], a_sum = approx[k], a_hi = a_lo + a_sum;
+    // classification (uniform across the block)
+    uint8_t f = CH_SLOW;
+    double base = 0.0;
+    if (a_sum == 0.0) f = CH_ZERO;  // a tree sum of non-negative terms is 0 only if every term is 0: c unchanged
+    else if (chunk == 4096 && a_lo > 1e-290) {
+        int ex;
+        frexp(a_lo, &ex);           // a_lo = m * 2^ex, m in [0.5, 1)
+        base = ldexp(1.0, ex - 1);  // 2^e with 2^e <= a_lo < 2^(e+1)
+        if (a_lo * (1.0 - kMargin) >= base && a_hi * (1.0 + kMargin) < 2.0 * base) f = CH_FAST;
+    }
+    if (f != CH_FAST) {
+        if (threadIdx.x == 0) { flag[k] = f; delta[k] = 0.0; bin_base[k] = 0.0; }
+        return;
+    }
+    if (threadIdx.x == 0) tie_any = 0;
+    const uint64_t g0 = k * (uint64_t)chunk;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int i = threadIdx.x + j * kBlock;
+        ps[i + (i >> 4)] = masked_prob(state, g0 + i, mask_bit);
+    }
+    __syncthreads();
+    const double half_u = ldexp(base, -53);   // u/2 with u = 2^(e-52)
+    double s = base;
+    bool tie = false;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const double x = ps[17 * threadIdx.x + j];
+        const double t = __dadd_rn(s, x);
+        const double err = __dsub_rn(x, __dsub_rn(t, s));   // exact: s >= x (Fast2Sum)
+        tie |= (fabs(err) == half_u);
+        s = t;
+    }
+    if (tie) atomicOr(&tie_any, 1);
+    const double d = block_sum(__dsub_rn(s, base), red);   // multiples of u below 2^(e+1): exact adds
+    if (threadIdx.x == 0) {
+        flag[k] = tie_any ? CH_SLOW : CH_FAST;
+        delta[k] = d;
+        bin_base[k] = base;
+    }
+}
+
+// Sequential replay of one chunk by a full warp (all lanes carry the same running sum).
+__device__ __forceinline__ double replay_chunk(const cuDoubleComplex* __restrict__ state, int mask_bit, uint64_t g0,
+                                               int chunk, double c) {
+    const int lane = threadIdx.x & 31;
+    for (int g = 0; g < chunk; g += 32) {
+        const double p = (g + lane < chunk) ? masked_prob(state, g0 + g + lane, mask_bit) : 0.0;
+        const int lim = (chunk - g) < 32 ? (chunk - g) : 32;
+        for (int j = 0; j < lim; ++j) c = __dadd_rn(c, __shfl_sync(0xffffffffu, p, j));
+    }
+    return c;
+}
+
+// K4: one warp walks the chunks in order and records the exact running sum at every chunk start.
+__global__ void chunk_walk_kernel(const cuDoubleComplex* __restrict__ state, int mask_bit, int chunk, uint64_t m,
+                                  const double* __restrict__ delta, const double* __restrict__ bin_base,
+                                  const uint8_t* __restrict__ flag, double* __restrict__ start,
+                                  unsigned long long* __restrict__ n_slow) {
+    const int lane = threadIdx.x & 31;
+    double c = 0.0;
+    unsigned long long slow = 0;
+    for (uint64_t k0 = 0; k0 < m; k0 += 32) {
+        const uint64_t kk = k0 + lane;
+        const double d = kk < m ? delta[kk] : 0.0;
+        const double b = kk < m ? bin_base[kk] : 0.0;
+        const int f = kk < m ? (int)flag[kk] : (int)CH_ZERO;
+        const int lim = (m - k0) < 32 ? (int)(m - k0) : 32;
+        for (int j = 0; j < lim; ++j) {
+            const double dj = __shfl_sync(0xffffffffu, d, j), bj = __shfl_sync(0xffffffffu, b, j);
+            const int fj = __shfl_sync(0xffffffffu, f, j);
+            if (lane == 0) start[k0 + j] = c;
+            if (fj == CH_ZERO) continue;
+            const double cc = __dadd_rn(c, dj);
+            if (fj == CH_FAST && c >= bj && cc < 2.0 * bj) c = cc;   // exact binade check on the true values
+            else { c = replay_chunk(state, mask_bit, (k0 + j) * (uint64_t)chunk, chunk, c); ++slow; }
+        }
+    }
+    if (lane == 0) { start[m] = c; *n_slow = slow; }
+}
+
+// K5: one warp per shot: binary search over the exact chunk ends, then replay inside the chunk.
+__global__ void sample_kernel(const cuDoubleComplex* __restrict__ state, int mask_bit, int chunk, uint64_t m,
+                              const double* __restrict__ start, const double* __restrict__ uniforms, int64_t n_shots,
+                              int64_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t shot = warp; shot < n_shots; shot += n_warps) {
+        const double r = uniforms[shot];
+        // smallest k in [0, m) with start[k+1] >= r
+        uint64_t lo_k = 0, hi_k = m;
+        while (lo_k < hi_k) {
+            const uint64_t mid = (lo_k + hi_k) >> 1;
+            if (start[mid + 1] >= r) hi_k = mid; else lo_k = mid + 1;
+        }
+        int64_t result = (int64_t)(m * (uint64_t)chunk);   // past the end: the reference returns 2^n here
+        if (lo_k < m) {
+            double c = start[lo_k];
+            const uint64_t g0 = lo_k * (uint64_t)chunk;
+            bool found = false;
+            for (int g = 0; g < chunk && !found; g += 32) {
+                const double p = (g + lane < chunk) ? masked_prob(state, g0 + g + lane, mask_bit) : 0.0;
+                const int lim = (chunk - g) < 32 ? (chunk - g) : 32;
+                for (int j = 0; j < lim; ++j) {
+                    c = __dadd_rn(c, __shfl_sync(0xffffffffu, p, j));
+                    if (c >= r) { result = (int64_t)(g0 + g + j); found = true; break; }
+                }
+            }
+        }
+        if (lane == 0) out[shot] = result;
+    }
+}
+
+int grid_for(uint64_t n, int num_sms) {
+    uint64_t blocks = (n + kBlock - 1) / kBlock;
+    uint64_t cap = (uint64_t)num_sms * 8;
+    return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+// ---- host wrappers -------------------------------------------------------------------------------
+
+void launch_probabilities(const cuDoubleComplex* state, double* out, uint64_t first, uint64_t count, int num_sms,
+                          cudaStream_t stream) {
+    if (!count) return;
+    probabilities_range_kernel<<<grid_for(count, num_sms), kBlock, 0, stream>>>(state, out, first, count);
+    CUDA_CHECK_LAST_ERROR();
+}
+
+void launch_init_basis(cuDoubleComplex* state, uint64_t n, uint64_t idx, cudaStream_t stream) {
+    CUDA_CHECK(cudaMemsetAsync(state, 0, n * sizeof(cuDoubleComplex), stream));
+    set_basis_kernel<<<1, 1, 0, stream>>>(state, idx);
+    CUDA_CHECK_LAST_ERROR();
+}
+
+double reduce_probability(const cuDoubleComplex* state, uint64_t n, int mask_bit, int num_sms, cudaStream_t stream) {
+    const int grid = grid_for(n, num_sms);
+    CudaMemory<double> partial((size_t)grid + 1);
+    partial_prob_kernel<<<grid, kBlock, 0, stream>>>(state, n, mask_bit, partial.get());
+    CUDA_CHECK_LAST_ERROR();
+    final_sum_kernel<<<1, kBlock, 0, stream>>>(partial.get(), grid, partial.get() + grid);
+    CUDA_CHECK_LAST_ERROR();
+    double out = 0.0;
+    CUDA_CHECK(cudaMemcpyAsync(&out, partial.get() + grid, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    return out;
+}
+
+void launch_collapse(cuDoubleComplex* state, uint64_t n, int bit, int outcome, double scale, int num_sms,
+                     cudaStream_t stream) {
+    collapse_kernel<<<grid_for(n, num_sms), kBlock, 0, stream>>>(state, n, bit, outcome, scale);
+    CUDA_CHECK_LAST_ERROR();
+}
+
+SequentialCdf::SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, cudaStream_t stream)
+    : state_(state), n_(n), mask_bit_(mask_bit), stream_(stream) {
+    chunk_ = n >= 4096 ? 4096 : (int)n;
+    m_ = n / (uint64_t)chunk_;
+    approx_ = CudaMemory<double>(m_);
+    lo_ = CudaMemory<double>(m_);
+    delta_ = CudaMemory<double>(m_);
+    base_ = CudaMemory<double>(m_);
+    flag_ = CudaMemory<uint8_t>(m_);
+    start_ = CudaMemory<double>(m_ + 1);
+    slow_ = CudaMemory<unsigned long long>(1);
+    chunk_approx_kernel<<<(unsigned)m_, kBlock, 0, stream>>>(state, mask_bit, chunk_, approx_.get());
+    CUDA_CHECK_LAST_ERROR();
+    chunk_scan_kernel<<<1, 1024, 0, stream>>>(approx_.get(), m_, lo_.get());
+    CUDA_CHECK_LAST_ERROR();
+    chunk_surrogate_kernel<<<(unsigned)m_, kBlock, 0, stream>>>(state, mask_bit, chunk_, approx_.get(), lo_.get(),
+                                                                delta_.get(), base_.get(), flag_.get());
+    CUDA_CHECK_LAST_ERROR();
+    chunk_walk_kernel<<<1, 32, 0, stream>>>(state, mask_bit, chunk_, m_, delta_.get(), base_.get(), flag_.get(),
+                                            start_.get(), slow_.get());
+    CUDA_CHECK_LAST_ERROR();
+    launches_ = 4;
+}
+
+double SequentialCdf::total() const {
+    double t = 0.0;
+    CUDA_CHECK(cudaMemcpyAsync(&t, start_.get() + m_, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    return t;
+}
+
+uint64_t SequentialCdf::slowChunks() const {
+    unsigned long long s = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&s, slow_.get(), sizeof(s), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    return s;
+}
+
+void SequentialCdf::sample(const double* uniforms_host, int64_t n_shots, int64_t* out_host, int num_sms) {
+    if (n_shots <= 0) return;
+    CudaMemory<double> d_u((size_t)n_shots);
+    CudaMemory<int64_t> d_out((size_t)n_shots);
+    CUDA_CHECK(cudaMemcpyAsync(d_u.get(), uniforms_host, (size_t)n_shots * sizeof(double), cudaMemcpyHostToDevice,
+                               stream_));
+    const int64_t warps_needed = n_shots;
+    int64_t blocks = (warps_needed * 32 + kBlock - 1) / kBlock;
+    const int64_t cap = (int64_t)num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    sample_kernel<<<(unsigned)blocks, kBlock, 0, stream_>>>(state_, mask_bit_, chunk_, m_, start_.get(), d_u.get(),
+                                                            n_shots, d_out.get());
+    CUDA_CHECK_LAST_ERROR();
+    ++launches_;
+    CUDA_CHECK(cudaMemcpyAsync(out_host, d_out.get(), (size_t)n_shots * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                               stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+}  // namespace b200
+}  // namespace qsim

@@ -1,0 +1,421 @@
+// Circuit compiler: gate list -> merged ops -> passes -> sweeps -> device records.
+// See program.hpp for the model.  Gate matrices follow SURVEY.md Appendix A, i.e. the
+// reference kernels src/Gates.cu:31-410 and CPU path src/Simulator.cu:222-317.
+#include "program.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <sstream>
+
+namespace qsim {
+namespace b200 {
+
+namespace {
+
+constexpr double kInvSqrt2 = 0.70710678118654752440;  // reference include/Constants.hpp:44
+
+inline void set_m(LogicalOp& o, double a_re, double a_im, double b_re, double b_im, double c_re, double c_im,
+                  double d_re, double d_im) {
+    o.m[0] = a_re; o.m[1] = a_im; o.m[2] = b_re; o.m[3] = b_im;
+    o.m[4] = c_re; o.m[5] = c_im; o.m[6] = d_re; o.m[7] = d_im;
+}
+
+LogicalOp make_op(int target, uint64_t cmask, int gate_index) {
+    LogicalOp o{};
+    o.kind = OP_MAT;
+    o.target = target;
+    o.cmask = cmask;
+    o.cval = cmask;
+    o.first_gate = gate_index;
+    o.n_gates = 1;
+    return o;
+}
+
+// 2x2 complex product out = b * a (a is applied first).
+void matmul(const double* b, const double* a, double* out) {
+    auto at = [](const double* m, int r, int c, int part) { return m[(r * 2 + c) * 2 + part]; };
+    double tmp[8];
+    for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 2; ++c) {
+            double re = 0, im = 0;
+            for (int k = 0; k < 2; ++k) {
+                double xr = at(b, r, k, 0), xi = at(b, r, k, 1), yr = at(a, k, c, 0), yi = at(a, k, c, 1);
+                re += xr * yr - xi * yi;
+                im += xr * yi + xi * yr;
+            }
+            tmp[(r * 2 + c) * 2] = re;
+            tmp[(r * 2 + c) * 2 + 1] = im;
+        }
+    std::memcpy(out, tmp, sizeof(tmp));
+}
+
+inline bool is_diag_kind(uint8_t k) { return k == OP_DIAG; }
+
+inline uint64_t qubits_of(const LogicalOp& o) { return o.cmask | (1ULL << o.target); }
+
+// Two controlled one-qubit operators commute when each non-diagonal target is untouched by the
+// other operator (diagonal operators and control projectors are all diagonal in the same basis).
+bool commutes(const LogicalOp& a, const LogicalOp& b) {
+    if (!is_diag_kind(a.kind) && (qubits_of(b) >> a.target) & 1) return false;
+    if (!is_diag_kind(b.kind) && (qubits_of(a) >> b.target) & 1) return false;
+    return true;
+}
+
+bool is_identity(const LogicalOp& o) {
+    return o.m[0] == 1.0 && o.m[1] == 0.0 && o.m[2] == 0.0 && o.m[3] == 0.0 && o.m[4] == 0.0 && o.m[5] == 0.0 &&
+           o.m[6] == 1.0 && o.m[7] == 0.0;
+}
+
+}  // namespace
+
+void classify(LogicalOp& o) {
+    const double* m = o.m;
+    const bool off_zero = m[2] == 0 && m[3] == 0 && m[4] == 0 && m[5] == 0;
+    const bool on_zero = m[0] == 0 && m[1] == 0 && m[6] == 0 && m[7] == 0;
+    const bool real = m[1] == 0 && m[3] == 0 && m[5] == 0 && m[7] == 0;
+    if (off_zero) o.kind = OP_DIAG;
+    else if (on_zero && real && m[2] == 1.0 && m[4] == 1.0) o.kind = OP_FLIP;
+    else if (on_zero) o.kind = OP_ADIAG;
+    else if (real) o.kind = OP_MATREAL;
+    else o.kind = OP_MAT;
+}
+
+bool lower_gate(const qsim_gate_t& g, std::vector<LogicalOp>& out, int gi) {
+    const double k = kInvSqrt2;
+    const double c = std::cos(g.param / 2.0), s = std::sin(g.param / 2.0);
+    auto one = [&](int target, uint64_t cmask) -> LogicalOp& {
+        out.push_back(make_op(target, cmask, gi));
+        return out.back();
+    };
+    auto flip = [&](int target, uint64_t cmask) { set_m(one(target, cmask), 0, 0, 1, 0, 1, 0, 0, 0); };
+    switch (g.type) {
+        case QSIM_GATE_X: flip(g.q0, 0); break;
+        case QSIM_GATE_Y: set_m(one(g.q0, 0), 0, 0, 0, -1, 0, 1, 0, 0); break;
+        case QSIM_GATE_Z: set_m(one(g.q0, 0), 1, 0, 0, 0, 0, 0, -1, 0); break;
+        case QSIM_GATE_H: set_m(one(g.q0, 0), k, 0, k, 0, k, 0, -k, 0); break;
+        case QSIM_GATE_S: set_m(one(g.q0, 0), 1, 0, 0, 0, 0, 0, 0, 1); break;
+        case QSIM_GATE_T: set_m(one(g.q0, 0), 1, 0, 0, 0, 0, 0, k, k); break;
+        case QSIM_GATE_SDAG: set_m(one(g.q0, 0), 1, 0, 0, 0, 0, 0, 0, -1); break;
+        case QSIM_GATE_TDAG: set_m(one(g.q0, 0), 1, 0, 0, 0, 0, 0, k, -k); break;
+        case QSIM_GATE_RX: set_m(one(g.q0, 0), c, 0, 0, -s, 0, -s, c, 0); break;
+        case QSIM_GATE_RY: set_m(one(g.q0, 0), c, 0, -s, 0, s, 0, c, 0); break;
+        case QSIM_GATE_RZ: set_m(one(g.q0, 0), c, -s, 0, 0, 0, 0, c, s); break;
+        case QSIM_GATE_CNOT: flip(g.q1, 1ULL << g.q0); break;
+        case QSIM_GATE_CZ: set_m(one(g.q1, 1ULL << g.q0), 1, 0, 0, 0, 0, 0, -1, 0); break;
+        case QSIM_GATE_CRY: set_m(one(g.q1, 1ULL << g.q0), c, 0, -s, 0, s, 0, c, 0); break;
+        case QSIM_GATE_CRZ: set_m(one(g.q1, 1ULL << g.q0), c, -s, 0, 0, 0, 0, c, s); break;
+        case QSIM_GATE_SWAP:  // swap(a,b) = CX(a,b) CX(b,a) CX(a,b): three index permutations
+            flip(g.q1, 1ULL << g.q0);
+            flip(g.q0, 1ULL << g.q1);
+            flip(g.q1, 1ULL << g.q0);
+            break;
+        case QSIM_GATE_TOFFOLI: flip(g.q2, (1ULL << g.q0) | (1ULL << g.q1)); break;
+        default: return false;
+    }
+    for (size_t i = out.size(); i-- > 0 && out[i].first_gate == gi;) classify(out[i]);
+    return true;
+}
+
+namespace {
+
+// Merge `b` into an earlier op on the same (target, controls) when everything in between
+// commutes with it; otherwise append.
+void append_merged(std::vector<LogicalOp>& out, const LogicalOp& b, bool merge) {
+    if (merge) {
+        const size_t window = 96;
+        for (size_t back = 0; back < window && back < out.size(); ++back) {
+            LogicalOp& a = out[out.size() - 1 - back];
+            if (a.target == b.target && a.cmask == b.cmask && a.cval == b.cval) {
+                matmul(b.m, a.m, a.m);
+                a.n_gates += b.n_gates;
+                classify(a);
+                return;
+            }
+            if (!commutes(a, b)) break;
+        }
+    }
+    out.push_back(b);
+}
+
+struct PassPlan {
+    std::vector<int> op_idx;   // indices into the logical op list, execution order
+    uint64_t need = 0;         // qubits that must be tile bits (non-diagonal targets)
+};
+
+// Can a pass whose required qubit set is `need` be tiled with t tile bits, keeping lmin low bits?
+bool tile_feasible(uint64_t need, int n_local, int t, int lmin) {
+    if (t >= n_local) return true;
+    int high = __builtin_popcountll(need >> lmin);
+    return lmin + high <= t;
+}
+
+void choose_tile_bits(uint64_t need, int n_local, int t, int lmin, PassDesc& pd) {
+    // Largest L with L + |need ∩ [L, n)| <= t (f is non-decreasing in L).
+    int L = std::min(t, n_local);
+    if (t < n_local) {
+        L = lmin;
+        while (L + 1 <= t && (L + 1) + __builtin_popcountll(need >> (L + 1)) <= t) ++L;
+    }
+    std::vector<int> bits;
+    for (int q = 0; q < L; ++q) bits.push_back(q);
+    for (int q = L; q < n_local; ++q)
+        if ((need >> q) & 1) bits.push_back(q);
+    // pad with the lowest unused qubits (keeps runs long and the tile count a power of two)
+    for (int q = L; q < n_local && (int)bits.size() < t; ++q)
+        if (!((need >> q) & 1)) bits.push_back(q);
+    std::sort(bits.begin(), bits.end());
+    int LL = 0;
+    while (LL < (int)bits.size() && bits[LL] == LL) ++LL;
+    pd.t = (int)bits.size();
+    pd.L = LL;
+    pd.n_high = pd.t - pd.L;
+    for (int i = 0; i < pd.t && i < kMaxTileBits; ++i) pd.tile_bits[i] = (uint8_t)bits[i];
+    // segments of outer (non-tile) bits
+    pd.n_segments = 0;
+    uint64_t tmask = 0;
+    for (int b : bits) tmask |= 1ULL << b;
+    int src = 0;
+    for (int q = 0; q < n_local;) {
+        if ((tmask >> q) & 1) { ++q; continue; }
+        int q0 = q;
+        while (q < n_local && !((tmask >> q) & 1)) ++q;
+        Segment& sg = pd.seg[pd.n_segments++];
+        int len = q - q0;
+        sg.mask = (len >= 64) ? ~0ULL : ((1ULL << len) - 1);
+        sg.src_shift = (uint8_t)src;
+        sg.dst_shift = (uint8_t)q0;
+        src += len;
+    }
+}
+
+}  // namespace
+
+bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& opt, Program& out, std::string* error) {
+    auto fail = [&](const std::string& s) { if (error) *error = s; return false; };
+    out = Program();
+    out.n = n;
+    out.n_local = n - opt.n_global;
+    const int nl = out.n_local;
+    if (nl < 1) return fail("no local qubits");
+    const int t = std::min(opt.max_tile_bits, nl);
+    const int lmin = std::min(std::max(opt.min_low_bits, 3), t);
+
+    // 1. merge
+    for (auto& op : lops_in) {
+        if (!is_diag_kind(op.kind) && op.target >= nl)
+            return fail("non-diagonal gate on a global qubit must be remapped before compilation");
+        append_merged(out.lops, op, opt.merge);
+    }
+    {
+        std::vector<LogicalOp> kept;
+        for (auto& op : out.lops)
+            if (!(is_diag_kind(op.kind) && is_identity(op))) kept.push_back(op);
+        out.lops.swap(kept);
+    }
+
+    // 2. passes: list scheduling — an op joins the open pass if its target fits the tile and it
+    //    commutes with every op already deferred to a later pass.
+    std::vector<int> pending(out.lops.size());
+    for (size_t i = 0; i < pending.size(); ++i) pending[i] = (int)i;
+    std::vector<PassPlan> plans;
+    while (!pending.empty()) {
+        PassPlan plan;
+        std::vector<int> deferred;
+        for (int idx : pending) {
+            const LogicalOp& op = out.lops[idx];
+            uint64_t need = plan.need | (is_diag_kind(op.kind) ? 0ULL : (1ULL << op.target));
+            bool ok = tile_feasible(need, nl, t, lmin) && (int)plan.op_idx.size() < kMaxOpsPerPass;
+            if (ok && !deferred.empty()) {
+                if (!opt.reorder) ok = false;
+                else
+                    for (int d : deferred)
+                        if (!commutes(out.lops[d], op)) { ok = false; break; }
+            }
+            if (ok) { plan.op_idx.push_back(idx); plan.need = need; }
+            else deferred.push_back(idx);
+        }
+        if (plan.op_idx.empty()) return fail("scheduler made no progress");
+        plans.push_back(std::move(plan));
+        pending.swap(deferred);
+    }
+
+    // 3. per pass: tile bits, sweeps, device records
+    for (auto& plan : plans) {
+        PassDesc pd{};
+        pd.n = nl;
+        choose_tile_bits(plan.need, nl, t, lmin, pd);
+        int local_of[64];
+        for (int q = 0; q < 64; ++q) local_of[q] = -1;
+        for (int i = 0; i < pd.t; ++i) local_of[pd.tile_bits[i]] = i;
+
+        const int r = pd.t > 9 ? kMaxRegBits : std::max(0, pd.t - 5);
+        const int nthr = pd.t - r;
+        const int n_lane = std::min(5, nthr);
+        const int cap = n_lane + r;  // targetable positions per sweep
+
+        pd.op_offset = (int)out.ops.size();
+        pd.n_ops = 0;
+        pd.n_sweeps = 0;
+
+        std::vector<int> todo = plan.op_idx;
+        while (!todo.empty()) {
+            if (pd.n_sweeps >= kMaxSweeps) return fail("too many sweeps in one pass");
+            // choose the targetable set greedily in order (commutation-aware deferral as above)
+            uint32_t S = 0;
+            for (int p = 0; p < std::min(3, pd.t); ++p) S |= 1u << p;
+            std::vector<int> chosen, deferred;
+            std::vector<int> uses(pd.t, 0);
+            for (int idx : todo) {
+                const LogicalOp& op = out.lops[idx];
+                bool ok = true;
+                uint32_t S2 = S;
+                if (!is_diag_kind(op.kind)) {
+                    S2 |= 1u << local_of[op.target];
+                    ok = __builtin_popcount(S2) <= cap;
+                }
+                if (ok && !deferred.empty()) {
+                    if (!opt.reorder) ok = false;
+                    else
+                        for (int d : deferred)
+                            if (!commutes(out.lops[d], op)) { ok = false; break; }
+                }
+                if (ok) {
+                    S = S2;
+                    chosen.push_back(idx);
+                    if (!is_diag_kind(op.kind)) uses[local_of[op.target]]++;
+                } else deferred.push_back(idx);
+            }
+            if (chosen.empty()) return fail("sweep scheduler made no progress");
+
+            // role assignment: tid bits 0..2 = tile bits 0..2; busiest other targets -> registers;
+            // remaining targets -> lane bits 3,4; everything else -> leftover lane/warp bits.
+            SweepDesc sd{};
+            sd.r = (uint8_t)r;
+            sd.nthr = (uint8_t)nthr;
+            std::vector<int> cand;  // targetable positions beyond the fixed low lanes
+            for (int p = std::min(3, pd.t); p < pd.t; ++p)
+                if ((S >> p) & 1) cand.push_back(p);
+            std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return uses[a] > uses[b]; });
+            std::vector<int> regs, lanes_extra, rest;
+            for (int p : cand) {
+                if ((int)regs.size() < r) regs.push_back(p);
+                else lanes_extra.push_back(p);
+            }
+            std::vector<char> taken(pd.t, 0);
+            for (int p = 0; p < std::min(3, pd.t); ++p) taken[p] = 1;
+            for (int p : regs) taken[p] = 1;
+            for (int p : lanes_extra) taken[p] = 1;
+            // registers prefer high tile bits when free (keeps lane bits low => coalesced smem rows)
+            for (int p = pd.t - 1; p >= 0 && (int)regs.size() < r; --p)
+                if (!taken[p]) { regs.push_back(p); taken[p] = 1; }
+            std::sort(regs.begin(), regs.end());
+            for (int p = 0; p < pd.t; ++p)
+                if (!taken[p]) rest.push_back(p);
+            int ti = 0;
+            for (int p = 0; p < std::min(3, pd.t); ++p) sd.thr_pos[ti++] = (uint8_t)p;
+            for (int p : lanes_extra) sd.thr_pos[ti++] = (uint8_t)p;
+            for (int p : rest) sd.thr_pos[ti++] = (uint8_t)p;
+            if (ti != nthr) return fail("internal: thread-bit assignment");
+            for (int j = 0; j < r; ++j) sd.reg_pos[j] = (uint8_t)regs[j];
+            for (int k = 0; k < 16; ++k) {
+                unsigned off = 0;
+                for (int j = 0; j < r; ++j)
+                    if ((k >> j) & 1) off |= 1u << regs[j];
+                sd.slot_off[k] = (uint16_t)off;
+            }
+            int role_tid[kMaxTileBits], role_reg[kMaxTileBits];
+            for (int p = 0; p < pd.t; ++p) role_tid[p] = role_reg[p] = -1;
+            for (int i = 0; i < nthr; ++i) role_tid[sd.thr_pos[i]] = i;
+            for (int j = 0; j < r; ++j) role_reg[sd.reg_pos[j]] = j;
+
+            sd.op_begin = (uint16_t)pd.n_ops;
+            for (int idx : chosen) {
+                const LogicalOp& op = out.lops[idx];
+                DevOp d{};
+                d.kind = op.kind;
+                std::memcpy(d.m, op.m, sizeof(op.m));
+                uint32_t reg_cmask = 0, reg_cval = 0;
+                for (int q = 0; q < 64; ++q) {
+                    if (!((op.cmask >> q) & 1)) continue;
+                    uint64_t v = (op.cval >> q) & 1;
+                    int p = q < nl ? local_of[q] : -1;
+                    if (p < 0) { d.cmask_out |= 1ULL << q; d.cval_out |= v << q; }
+                    else if (role_reg[p] >= 0) { reg_cmask |= 1u << role_reg[p]; reg_cval |= (uint32_t)v << role_reg[p]; }
+                    else { d.cmask_thr |= 1u << role_tid[p]; d.cval_thr |= (uint32_t)v << role_tid[p]; }
+                }
+                for (int k = 0; k < 16; ++k)
+                    if (((uint32_t)k & reg_cmask) == reg_cval) d.slotmask |= (uint16_t)(1u << k);
+                int p = op.target < nl ? local_of[op.target] : -1;
+                if (p < 0) {
+                    if (!is_diag_kind(op.kind)) return fail("internal: non-diagonal target outside tile");
+                    d.thome = T_OUTSIDE;
+                    d.tmask_out = 1ULL << op.target;
+                } else if (role_reg[p] >= 0) {
+                    d.thome = T_REG;
+                    d.tbit = (uint8_t)role_reg[p];
+                    for (int k = 0; k < 16; ++k)
+                        if ((k >> role_reg[p]) & 1) d.tslots |= (uint16_t)(1u << k);
+                } else {
+                    int tb = role_tid[p];
+                    if (is_diag_kind(op.kind)) { d.thome = T_THREAD; d.tbit = (uint8_t)tb; d.tmask_thr = 1u << tb; }
+                    else {
+                        if (tb >= 5) return fail("internal: non-diagonal target on a warp bit");
+                        d.thome = T_LANE;
+                        d.tbit = (uint8_t)tb;
+                    }
+                }
+                out.ops.push_back(d);
+                pd.n_ops++;
+            }
+            sd.op_end = (uint16_t)pd.n_ops;
+            pd.sweep[pd.n_sweeps++] = sd;
+            todo.swap(deferred);
+        }
+        out.passes.push_back(pd);
+    }
+    return true;
+}
+
+bool compile(int n, const qsim_gate_t* gates, int64_t n_gates, const CompileOptions& opt, Program& out,
+             std::string* error) {
+    std::vector<LogicalOp> lops;
+    lops.reserve((size_t)n_gates + 8);
+    for (int64_t i = 0; i < n_gates; ++i)
+        if (!lower_gate(gates[i], lops, (int)i)) {
+            if (error) *error = "Unknown gate type";
+            return false;
+        }
+    bool ok = compile_ops(n, std::move(lops), opt, out, error);
+    out.n_gates = n_gates;
+    return ok;
+}
+
+std::string Program::describe() const {
+    std::ostringstream os;
+    size_t sweeps = 0;
+    for (auto& p : passes) sweeps += p.n_sweeps;
+    os << "program: " << n << " qubits (" << n_local << " local), " << n_gates << " gates -> " << lops.size()
+       << " ops, " << passes.size() << " passes, " << sweeps << " sweeps\n";
+    static const char* kn[] = {"MAT", "MATREAL", "ADIAG", "FLIP", "DIAG"};
+    for (size_t i = 0; i < passes.size(); ++i) {
+        const PassDesc& p = passes[i];
+        os << "  pass " << i << ": t=" << p.t << " L=" << p.L << " tile_bits=[";
+        for (int b = 0; b < p.t; ++b) os << (b ? "," : "") << (int)p.tile_bits[b];
+        os << "] ops=" << p.n_ops << " sweeps=" << p.n_sweeps << "\n";
+        for (int s = 0; s < p.n_sweeps; ++s) {
+            const SweepDesc& sd = p.sweep[s];
+            os << "    sweep " << s << ": regs=[";
+            for (int j = 0; j < sd.r; ++j) os << (j ? "," : "") << (int)p.tile_bits[sd.reg_pos[j]];
+            os << "] lanes=[";
+            for (int j = 0; j < std::min<int>(5, sd.nthr); ++j) os << (j ? "," : "") << (int)p.tile_bits[sd.thr_pos[j]];
+            os << "] ops:";
+            for (int o = sd.op_begin; o < sd.op_end; ++o) os << " " << kn[ops[p.op_offset + o].kind];
+            os << "\n";
+        }
+    }
+    return os.str();
+}
+
+}  // namespace b200
+}  // namespace qsim

@@ -1,0 +1,144 @@
+// Circuit compiler for the fused-pass engine (host only, no CUDA).
+//
+// A circuit (the reference's gate list, include/Circuit.hpp:64-84 of the reference) is lowered to
+//   ops    : controlled one-qubit operators (dense 2x2, real 2x2, anti-diagonal, bit-flip, diagonal),
+//            after merging runs of gates that act on the same (target, controls);
+//   passes : groups of consecutive ops whose non-diagonal targets all live inside one set of
+//            `t` "tile qubits".  One pass = one kernel launch = one read + one write of the state
+//            (2 * 16 * 2^n bytes), however many gates it carries;
+//   sweeps : within a pass, the assignment of tile bits to lane / register / warp bits.  A sweep
+//            can hit any target held in a lane bit (warp shuffle) or register bit (in-thread).
+//
+// The reference executes one kernel and one full sweep of HBM per gate
+// (src/Simulator.cu:28-154 of the reference); this compiler is what replaces that loop.
+#pragma once
+
+#include <array>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "qsim_b200.h"
+
+namespace qsim {
+namespace b200 {
+
+constexpr int kMaxTileBits = 12;         // 2^12 amplitudes * 16 B = 64 KiB per pipeline stage
+constexpr int kStages = 3;               // TMA ring depth (3 * 64 KiB of 227 KiB shared memory)
+constexpr int kComputeWarps = 8;
+constexpr int kComputeThreads = kComputeWarps * 32;
+constexpr int kMaxRegBits = 4;           // 16 amplitudes (32 doubles) per thread
+constexpr int kMaxSweeps = 12;
+constexpr int kMaxSegments = 14;
+constexpr int kMaxOpsPerPass = 192;      // ops of one pass are staged in shared memory
+
+enum OpKind : uint8_t {
+    OP_MAT = 0,      // dense complex 2x2
+    OP_MATREAL = 1,  // real 2x2 (H, Ry, ...): half the flops
+    OP_ADIAG = 2,    // anti-diagonal [[0,b],[c,0]] (Y, X*diag)
+    OP_FLIP = 3,     // bit flip (X / CNOT / Toffoli): pure data movement
+    OP_DIAG = 4,     // diagonal diag(d0, d1): phase by target bit, target may live anywhere
+};
+
+enum TargetHome : uint8_t {
+    T_LANE = 0,      // target is tid bit `tbit` < 5: partner amplitude comes by __shfl_xor
+    T_REG = 1,       // target is register bit `tbit`: partner is another slot of the same thread
+    T_THREAD = 2,    // (diagonal only) target is a tid bit, no partner needed
+    T_OUTSIDE = 3,   // (diagonal only) target is not a tile bit: uniform for the whole tile
+};
+
+// Device-visible op record (128 bytes, read as broadcast from shared memory).
+struct alignas(16) DevOp {
+    uint8_t kind;
+    uint8_t thome;
+    uint8_t tbit;
+    uint8_t pad0;
+    uint16_t slotmask;    // register slots whose register-resident control bits are satisfied
+    uint16_t tslots;      // OP_DIAG with T_REG: slots whose target bit is 1
+    uint32_t cmask_thr;   // controls held in tid bits
+    uint32_t cval_thr;
+    uint32_t tmask_thr;   // OP_DIAG with T_THREAD: the tid bit of the target
+    uint32_t pad1;
+    uint64_t cmask_out;   // controls outside the tile, as a mask over the global amplitude index
+    uint64_t cval_out;
+    uint64_t tmask_out;   // OP_DIAG with T_OUTSIDE: global-index bit of the target
+    double m[8];          // m00.re m00.im m01.re m01.im m10.re m10.im m11.re m11.im
+    double pad3[2];
+};
+static_assert(sizeof(DevOp) == 128, "DevOp layout");
+
+struct SweepDesc {
+    uint16_t op_begin, op_end;   // indices into the pass's op array
+    uint8_t r;                   // register bits in use (slots = 1 << r)
+    uint8_t nthr;                // tid bits in use (active threads = 1 << nthr)
+    uint8_t thr_pos[8];          // tile-local bit position held by tid bit i
+    uint8_t reg_pos[4];          // tile-local bit position held by register bit j
+    uint16_t slot_off[16];       // tile-local index offset of register slot k
+    uint16_t pad;
+};
+
+struct Segment {                 // tile number -> global base index, one contiguous run of outer bits
+    uint64_t mask;               // applied after the shift
+    uint8_t src_shift, dst_shift;
+    uint8_t pad[6];
+};
+
+struct PassDesc {
+    int32_t n;                   // qubits held in this buffer (local qubits when sharded)
+    int32_t t;                   // tile bits
+    int32_t L;                   // low contiguous tile bits: runs of 16 << L bytes
+    int32_t n_sweeps;
+    int32_t n_ops;
+    int32_t op_offset;           // into Program::ops
+    int32_t n_segments;
+    int32_t n_high;              // t - L
+    uint8_t tile_bits[kMaxTileBits];   // global bit of tile-local bit i (ascending)
+    uint8_t pad[4];
+    Segment seg[kMaxSegments];
+    SweepDesc sweep[kMaxSweeps];
+};
+
+// Host-side logical op: controlled one-qubit operator on global qubits.
+struct LogicalOp {
+    uint8_t kind;
+    int target;
+    uint64_t cmask, cval;        // controls over global qubits (cval allows control-on-zero)
+    double m[8];
+    int first_gate, n_gates;     // provenance (for statistics)
+};
+
+struct CompileOptions {
+    int min_low_bits = 5;        // every pass keeps at least this many low bits contiguous (512 B runs)
+    int max_tile_bits = kMaxTileBits;
+    bool merge = true;           // merge runs of gates on the same (target, controls)
+    bool reorder = true;         // commute ops across passes when legal (fewer passes)
+    int n_global = 0;            // qubits >= n - n_global live in the rank id (sharded state)
+};
+
+struct Program {
+    int n = 0;                   // total qubits (local + global)
+    int n_local = 0;
+    std::vector<LogicalOp> lops; // after merging
+    std::vector<DevOp> ops;      // encoded, pass-major
+    std::vector<PassDesc> passes;
+    int64_t n_gates = 0;
+    std::string describe() const;
+};
+
+// Gate list -> matrices.  Returns false for an unknown gate type.
+bool lower_gate(const qsim_gate_t& g, std::vector<LogicalOp>& out, int gate_index);
+
+// Full compile.  Ops whose non-diagonal target is a global qubit (>= n_local) are rejected
+// (return false): the sharded driver must remap those qubits before compiling a segment.
+bool compile(int n, const qsim_gate_t* gates, int64_t n_gates, const CompileOptions& opt, Program& out,
+             std::string* error = nullptr);
+
+// Compile an explicit op list (used by the density-matrix and noise paths, which build
+// non-unitary / conjugated operators directly).
+bool compile_ops(int n, std::vector<LogicalOp> lops, const CompileOptions& opt, Program& out,
+                 std::string* error = nullptr);
+
+void classify(LogicalOp& op);    // picks the cheapest OpKind for op.m
+
+}  // namespace b200
+}  // namespace qsim

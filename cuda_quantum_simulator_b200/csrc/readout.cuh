@@ -1,0 +1,47 @@
+// Read-out entry points (internal header).  See kernels_readout.cu.
+#pragma once
+
+#include <cuComplex.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "qsim/cuda_memory.cuh"
+
+namespace qsim {
+namespace b200 {
+
+void launch_probabilities(const cuDoubleComplex* state, double* out, uint64_t first, uint64_t count, int num_sms,
+                          cudaStream_t stream);
+void launch_init_basis(cuDoubleComplex* state, uint64_t n, uint64_t idx, cudaStream_t stream);
+// sum of |a_i|^2 over indices whose bit `mask_bit` is 0 (mask_bit < 0: all); deterministic tree order
+double reduce_probability(const cuDoubleComplex* state, uint64_t n, int mask_bit, int num_sms, cudaStream_t stream);
+void launch_collapse(cuDoubleComplex* state, uint64_t n, int bit, int outcome, double scale, int num_sms,
+                     cudaStream_t stream);
+
+// Exact sequential-order fp64 prefix sums of the (optionally masked) probabilities, kept as the
+// running sum at every 4096-element chunk boundary.
+class SequentialCdf {
+public:
+    SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, cudaStream_t stream);
+    double total() const;           // == the reference's index-order host sum, bit for bit
+    uint64_t slowChunks() const;    // chunks that had to be replayed sequentially (diagnostics)
+    // out[i] = smallest index whose CDF value >= uniforms[i] (n if none), host in / host out
+    void sample(const double* uniforms_host, int64_t n_shots, int64_t* out_host, int num_sms);
+    int launches() const { return launches_; }
+
+private:
+    const cuDoubleComplex* state_;
+    uint64_t n_;
+    int mask_bit_;
+    cudaStream_t stream_;
+    int chunk_ = 0;
+    uint64_t m_ = 0;
+    CudaMemory<double> approx_, lo_, delta_, base_, start_;
+    CudaMemory<uint8_t> flag_;
+    CudaMemory<unsigned long long> slow_;
+    int launches_ = 0;
+};
+
+}  // namespace b200
+}  // namespace qsim

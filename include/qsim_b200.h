@@ -1,0 +1,181 @@
+/* qsim_b200.h — C ABI of the B200-native state-vector engine.
+ *
+ * This is the drop-in boundary for the gate-application hot path of
+ * rylanmalarchick/cuda-quantum-simulator.  The reference has no FFI layer: its boundary is the
+ * C++ class surface of static library `quantum_sim_lib` (reference CMakeLists.txt:48-61).  The
+ * same C++ surface is provided by include/qsim/ *.hpp (namespace qsim) on top of this library;
+ * the functions below are what a foreign-language binding (ctypes / cgo / JNI) of that surface
+ * would call.  Each entry cites the reference interface it stands in for (paths relative to the
+ * reference repository).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all buffers are caller-owned unless stated otherwise;
+ *   - amplitudes are interleaved (re, im) IEEE doubles == cuDoubleComplex == std::complex<double>;
+ *   - qubit q <-> bit q of the amplitude index (reference src/Gates.cu:19-25);
+ *   - every function returns a qsim_status_t; the text of the last error of the calling thread
+ *     is available from qsim_last_error().  The codes mirror the C++ exception the reference
+ *     throws in the same situation (reference include/Constants.hpp:83-100, src/Circuit.cpp:16-56);
+ *   - there is NO CPU fallback: functions that need the GPU return QSIM_ERR_RUNTIME when no
+ *     device is present.
+ */
+#ifndef QSIM_B200_H
+#define QSIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define QSIM_API __attribute__((visibility("default")))
+#else
+#define QSIM_API
+#endif
+
+typedef enum {
+    QSIM_OK = 0,
+    QSIM_ERR_INVALID_ARGUMENT = 1, /* std::invalid_argument */
+    QSIM_ERR_OUT_OF_RANGE = 2,     /* std::out_of_range     */
+    QSIM_ERR_RUNTIME = 3           /* std::runtime_error (CUDA errors, unknown gate, zero-probability outcome) */
+} qsim_status_t;
+
+/* Gate types, same order and integer values as `enum class GateType`
+ * (reference include/Circuit.hpp:42-59). */
+enum {
+    QSIM_GATE_X = 0, QSIM_GATE_Y, QSIM_GATE_Z, QSIM_GATE_H, QSIM_GATE_S, QSIM_GATE_T,
+    QSIM_GATE_SDAG, QSIM_GATE_TDAG, QSIM_GATE_RX, QSIM_GATE_RY, QSIM_GATE_RZ,
+    QSIM_GATE_CNOT, QSIM_GATE_CZ, QSIM_GATE_CRY, QSIM_GATE_CRZ, QSIM_GATE_SWAP, QSIM_GATE_TOFFOLI
+};
+
+/* One gate == `struct GateOp` (reference include/Circuit.hpp:64-84):
+ * qubits are [target], [control, target] / [q1, q2], or [c1, c2, target]; unused slots are -1. */
+typedef struct {
+    int32_t type;
+    int32_t q0, q1, q2;
+    double param;
+} qsim_gate_t;
+
+/* Noise types, same order as `enum class NoiseType` (reference include/NoiseModel.cuh:46-53). */
+enum {
+    QSIM_NOISE_DEPOLARIZING = 0, QSIM_NOISE_AMPLITUDE_DAMPING, QSIM_NOISE_PHASE_DAMPING,
+    QSIM_NOISE_BIT_FLIP, QSIM_NOISE_PHASE_FLIP, QSIM_NOISE_BIT_PHASE_FLIP
+};
+
+/* One noise channel == `struct NoiseChannel` (reference include/NoiseModel.cuh:58-66) flattened:
+ * n_qubits == 0 means "all qubits" (reference include/NoiseModel.cuh:118-122). */
+typedef struct {
+    int32_t type;
+    int32_t n_qubits;
+    const int32_t* qubits;
+    double probability;
+} qsim_noise_channel_t;
+
+typedef struct qsim_sim qsim_sim_t;           /* Simulator / StateVector      */
+typedef struct qsim_program qsim_program_t;   /* a compiled (fused) circuit   */
+typedef struct qsim_batched qsim_batched_t;   /* BatchedSimulator             */
+typedef struct qsim_noisy qsim_noisy_t;       /* NoisySimulator               */
+typedef struct qsim_dm qsim_dm_t;             /* DensityMatrixSimulator       */
+
+QSIM_API const char* qsim_last_error(void);
+QSIM_API const char* qsim_version(void);
+QSIM_API int qsim_max_qubits(void);           /* cuda_config::MAX_QUBITS, raised from 30 */
+
+/* ---- Circuit (reference include/Circuit.hpp:89-144, src/Circuit.cpp) -------------------------- */
+/* Validation exactly as the fluent builder does it, gate by gate: out_of_range for a bad qubit
+ * index (src/Circuit.cpp:26-31), invalid_argument for duplicate qubits (:33-48), non-finite angle
+ * (:50-56) or a qubit count outside [1, MAX] (:16-24). */
+QSIM_API qsim_status_t qsim_circuit_validate(int num_qubits, const qsim_gate_t* gates, int64_t n_gates);
+/* createRandomCircuit(n, depth, seed) (src/Circuit.cpp:252-282): writes `depth` gates. */
+QSIM_API qsim_status_t qsim_circuit_random(int num_qubits, int depth, unsigned seed, qsim_gate_t* out);
+/* createGHZCircuit(n) (src/Circuit.cpp:240-250): writes n gates. */
+QSIM_API qsim_status_t qsim_circuit_ghz(int num_qubits, qsim_gate_t* out);
+/* Circuit::getDepth (src/Circuit.cpp:165-182). */
+QSIM_API qsim_status_t qsim_circuit_depth(int num_qubits, const qsim_gate_t* gates, int64_t n_gates, int64_t* depth);
+
+/* ---- Compiled circuits (new: the fusion pass; no reference counterpart) ----------------------- */
+/* n_global > 0 compiles for one shard of a state whose top n_global qubits are the rank id.    */
+QSIM_API qsim_status_t qsim_program_compile(int num_qubits, int n_global, const qsim_gate_t* gates,
+                                            int64_t n_gates, qsim_program_t** out);
+QSIM_API void qsim_program_destroy(qsim_program_t* p);
+/* info[0]=passes, [1]=ops after merging, [2]=gates, [3]=sweeps (total), [4]=tile bits of pass 0 */
+QSIM_API qsim_status_t qsim_program_info(const qsim_program_t* p, int64_t info[8]);
+/* Human-readable plan (passes, tile qubits, sweeps).  Returns bytes needed incl. NUL. */
+QSIM_API size_t qsim_program_describe(const qsim_program_t* p, char* buf, size_t cap);
+
+/* ---- Simulator / StateVector (reference include/Simulator.hpp:53-85, include/StateVector.cuh:66-124) */
+QSIM_API qsim_status_t qsim_sim_create(int num_qubits, qsim_sim_t** out);            /* Simulator(int) */
+/* Same, on caller-owned device memory of 16 << num_qubits bytes (e.g. a torch tensor). */
+QSIM_API qsim_status_t qsim_sim_create_external(int num_qubits, void* device_state, qsim_sim_t** out);
+QSIM_API void qsim_sim_destroy(qsim_sim_t* s);
+QSIM_API qsim_status_t qsim_sim_set_stream(qsim_sim_t* s, void* cuda_stream);
+QSIM_API qsim_status_t qsim_sim_reset(qsim_sim_t* s);                                /* Simulator::reset */
+QSIM_API qsim_status_t qsim_sim_init_basis(qsim_sim_t* s, uint64_t basis_index);     /* StateVector::initializeBasis */
+QSIM_API qsim_status_t qsim_sim_set_state(qsim_sim_t* s, const double* host_amplitudes);
+QSIM_API qsim_status_t qsim_sim_run(qsim_sim_t* s, int circuit_qubits, const qsim_gate_t* gates,
+                                    int64_t n_gates);                                /* Simulator::run */
+QSIM_API qsim_status_t qsim_sim_apply_gate(qsim_sim_t* s, const qsim_gate_t* gate);  /* Simulator::applyGate */
+QSIM_API qsim_status_t qsim_sim_execute(qsim_sim_t* s, const qsim_program_t* p);     /* pre-compiled run */
+QSIM_API qsim_status_t qsim_sim_synchronize(qsim_sim_t* s);
+QSIM_API qsim_status_t qsim_sim_get_state(const qsim_sim_t* s, double* host_out);    /* getStateVector */
+QSIM_API qsim_status_t qsim_sim_get_probabilities(const qsim_sim_t* s, double* host_out); /* getProbabilities */
+/* Device-side read-out that never materialises 2^n values: probabilities of
+ * `count` indices starting at `first`. */
+QSIM_API qsim_status_t qsim_sim_get_probability_range(const qsim_sim_t* s, uint64_t first, uint64_t count,
+                                                      double* host_out);
+QSIM_API qsim_status_t qsim_sim_total_probability(const qsim_sim_t* s, double* out); /* getTotalProbability */
+/* Simulator::sample with caller-supplied uniforms in [0,1): out[i] = smallest index
+ * whose sequential fp64 CDF value is >= uniforms[i] — bit-identical to std::partial_sum +
+ * std::lower_bound (reference src/Simulator.cu:164-185).  64-bit indices. */
+QSIM_API qsim_status_t qsim_sim_sample_uniforms(qsim_sim_t* s, const double* uniforms, int64_t n_shots,
+                                                int64_t* out);
+/* Same with uniforms drawn as the reference does: std::mt19937(seed) +
+ * std::uniform_real_distribution<double>(0,1), one draw per shot. */
+QSIM_API qsim_status_t qsim_sim_sample_seeded(qsim_sim_t* s, unsigned seed, int64_t n_shots, int64_t* out);
+/* Simulator::measureQubit(q) with the uniform draw r supplied: measures index bit n-1-q exactly as
+ * StateVector::measure does (reference src/StateVector.cu:87-89, 260-314). */
+QSIM_API qsim_status_t qsim_sim_measure(qsim_sim_t* s, int qubit, double r, int* outcome);
+/* Measurement of index bit `bit` (the NoisySimulator convention, reference src/NoiseModel.cu:615-651). */
+QSIM_API qsim_status_t qsim_sim_measure_bit(qsim_sim_t* s, int bit, double r, int* outcome, double* p0);
+QSIM_API int qsim_sim_num_qubits(const qsim_sim_t* s);
+QSIM_API void* qsim_sim_device_ptr(qsim_sim_t* s);                                   /* StateVector::devicePtr */
+/* Kernel launches issued by this simulator so far (bench.py's gpu_launches). */
+QSIM_API int64_t qsim_sim_launch_count(const qsim_sim_t* s);
+/* Average device time of the fused-pass kernel since the last call (CUDA events on the
+ * simulator's stream), and how many passes were timed.  Enable with qsim_sim_set_timing. */
+QSIM_API qsim_status_t qsim_sim_set_timing(qsim_sim_t* s, int enabled);
+QSIM_API qsim_status_t qsim_sim_pass_time_ms(qsim_sim_t* s, double* total_ms, int64_t* n_passes);
+
+/* ---- Sharded state: one process per GPU, top n_global qubits = rank -------------- */
+/* The shard holds 2^(num_qubits - n_global) amplitudes; `rank` supplies the values of the global
+ * qubits.  device_state may be NULL (library allocates). */
+QSIM_API qsim_status_t qsim_shard_create(int num_qubits, int n_global, int rank, void* device_state,
+                                         qsim_sim_t** out);
+/* In-place half-shard exchange with the peer rank (rank ^ (1 << (global_qubit - n_local))):
+ * swaps global qubit `global_qubit` with local qubit `local_qubit`.  `peer_state` is the peer's
+ * shard mapped into this process (CUDA IPC / peer access).  Both ranks call it; each moves half of
+ * the pairs.  Callers synchronise ranks before and after. */
+QSIM_API qsim_status_t qsim_shard_swap_p2p(qsim_sim_t* s, void* peer_state, int global_qubit, int local_qubit);
+/* Bounce-buffer variant for NCCL send/recv: pack the half shard that must leave into `buf`
+ * (chunk `chunk` of `n_chunks`), and unpack a received chunk. */
+QSIM_API qsim_status_t qsim_shard_pack_half(qsim_sim_t* s, int local_qubit, int keep_bit, int64_t chunk,
+                                            int64_t n_chunks, void* buf);
+QSIM_API qsim_status_t qsim_shard_unpack_half(qsim_sim_t* s, int local_qubit, int keep_bit, int64_t chunk,
+                                              int64_t n_chunks, const void* buf);
+/* CUDA IPC plumbing so Python can exchange handles over torch.distributed. */
+/* handle_out identifies the allocation that contains device_ptr; *offset_out is device_ptr's byte
+ * offset inside it (a torch tensor need not start its cudaMalloc block). */
+QSIM_API qsim_status_t qsim_ipc_get_handle(void* device_ptr, unsigned char handle_out[64], uint64_t* offset_out);
+/* Maps the peer allocation; returns its BASE pointer (add the peer's offset yourself). */
+QSIM_API qsim_status_t qsim_ipc_open_handle(const unsigned char handle[64], void** base_ptr_out);
+QSIM_API qsim_status_t qsim_ipc_close_handle(void* base_ptr);
+/* Partial sums for distributed read-out: this shard's sum of |a|^2 (optionally restricted to
+ * index bit `bit` == 0; bit < 0 means no restriction). */
+QSIM_API qsim_status_t qsim_shard_partial_probability(const qsim_sim_t* s, int bit, double* out);
+QSIM_API qsim_status_t qsim_shard_collapse(qsim_sim_t* s, int bit, int outcome, double scale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSIM_B200_H */

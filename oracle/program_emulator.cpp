@@ -1,0 +1,141 @@
+// TEST INFRASTRUCTURE ONLY.  A thread-by-thread CPU emulation of what the fused-pass CUDA kernel
+// (cuda_quantum_simulator_b200/csrc/kernels_pass.cu) does with a compiled Program: tiles, sweeps,
+// register slots, lane shuffles, control masks.  It exists so that the circuit compiler
+// (csrc/program.cpp — host code, linked here unchanged) can be validated against the oracle in the
+// GPU-less container.  The product never loads this library.
+#include <complex>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../cuda_quantum_simulator_b200/csrc/program.hpp"
+
+using namespace qsim::b200;
+using cplx = std::complex<double>;
+
+namespace {
+
+void run_pass(const Program& prog, const PassDesc& pd, uint64_t hi_bits, cplx* state) {
+    const DevOp* ops = prog.ops.data() + pd.op_offset;
+    const uint64_t n_tiles = 1ULL << (pd.n - pd.t);
+    const uint32_t tile_amps = 1u << pd.t;
+    std::vector<cplx> tile(tile_amps);
+    std::vector<uint64_t> gidx(tile_amps);
+    for (uint64_t tau = 0; tau < n_tiles; ++tau) {
+        uint64_t base = 0;
+        for (int s = 0; s < pd.n_segments; ++s)
+            base |= ((tau >> pd.seg[s].src_shift) & pd.seg[s].mask) << pd.seg[s].dst_shift;
+        const uint64_t gbase = base | hi_bits;
+        for (uint32_t l = 0; l < tile_amps; ++l) {
+            uint64_t g = base;
+            for (int i = 0; i < pd.t; ++i)
+                if ((l >> i) & 1) g |= 1ULL << pd.tile_bits[i];
+            gidx[l] = g;
+            tile[l] = state[g];
+        }
+        for (int sw = 0; sw < pd.n_sweeps; ++sw) {
+            const SweepDesc& sd = pd.sweep[sw];
+            const int slots = 1 << sd.r;
+            const uint32_t n_active = 1u << sd.nthr;
+            for (uint32_t warp0 = 0; warp0 < n_active; warp0 += 32) {
+                cplx reg[32][16];
+                uint32_t base_local[32];
+                bool active[32];
+                for (int lane = 0; lane < 32; ++lane) {
+                    uint32_t tid = warp0 + lane;
+                    active[lane] = tid < n_active;
+                    uint32_t bl = 0;
+                    for (int i = 0; i < sd.nthr; ++i)
+                        if ((tid >> i) & 1) bl |= 1u << sd.thr_pos[i];
+                    base_local[lane] = bl;
+                    for (int k = 0; k < 16; ++k)
+                        reg[lane][k] = (active[lane] && k < slots) ? tile[bl + sd.slot_off[k]] : cplx(0, 0);
+                }
+                for (int o = sd.op_begin; o < sd.op_end; ++o) {
+                    const DevOp& op = ops[o];
+                    if ((gbase & op.cmask_out) != op.cval_out) continue;
+                    const cplx m00(op.m[0], op.m[1]), m01(op.m[2], op.m[3]), m10(op.m[4], op.m[5]), m11(op.m[6], op.m[7]);
+                    cplx nxt[32][16];
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const uint32_t tid = warp0 + lane;
+                        const bool thr_ok = (tid & op.cmask_thr) == op.cval_thr;
+                        const uint32_t sm = thr_ok ? op.slotmask : 0;
+                        for (int k = 0; k < 16; ++k) {
+                            cplx own = reg[lane][k], res = own;
+                            if ((sm >> k) & 1) {
+                                if (op.kind == OP_DIAG) {
+                                    bool b;
+                                    if (op.thome == T_REG) b = (op.tslots >> k) & 1;
+                                    else if (op.thome == T_THREAD) b = (tid & op.tmask_thr) != 0;
+                                    else b = (gbase & op.tmask_out) != 0;
+                                    res = (b ? m11 : m00) * own;
+                                } else {
+                                    bool b;
+                                    cplx partner;
+                                    if (op.thome == T_REG) { b = (k >> op.tbit) & 1; partner = reg[lane][k ^ (1 << op.tbit)]; }
+                                    else { b = (tid >> op.tbit) & 1; partner = reg[lane ^ (1 << op.tbit)][k]; }
+                                    cplx c_own = b ? m11 : m00, c_par = b ? m10 : m01;
+                                    if (op.kind == OP_FLIP) res = partner;
+                                    else if (op.kind == OP_ADIAG) res = c_par * partner;
+                                    else res = c_own * own + c_par * partner;
+                                }
+                            }
+                            nxt[lane][k] = res;
+                        }
+                    }
+                    std::memcpy(reg, nxt, sizeof(reg));
+                }
+                for (int lane = 0; lane < 32; ++lane)
+                    if (active[lane])
+                        for (int k = 0; k < slots; ++k) tile[base_local[lane] + sd.slot_off[k]] = reg[lane][k];
+            }
+        }
+        for (uint32_t l = 0; l < tile_amps; ++l) state[gidx[l]] = tile[l];
+    }
+}
+
+}  // namespace
+
+// Compile `gates` and run the emulated kernel on `state` (2^(n - n_global) amplitudes of shard `rank`).
+// info_out: [0]=passes [1]=ops [2]=sweeps.  Returns 0, or -1 with the compiler's message in err.
+extern "C" __attribute__((visibility("default")))
+int emu_run(int n, int n_global, int rank, const qsim_gate_t* gates, int64_t ng, double* state,
+            int min_low_bits, int max_tile_bits, int merge, int reorder, int64_t* info_out, char* err, int errcap) {
+    CompileOptions opt;
+    opt.n_global = n_global;
+    if (min_low_bits > 0) opt.min_low_bits = min_low_bits;
+    if (max_tile_bits > 0) opt.max_tile_bits = max_tile_bits;
+    opt.merge = merge != 0;
+    opt.reorder = reorder != 0;
+    Program prog;
+    std::string e;
+    if (!compile(n, gates, ng, opt, prog, &e)) {
+        if (err && errcap > 0) { std::strncpy(err, e.c_str(), errcap - 1); err[errcap - 1] = 0; }
+        return -1;
+    }
+    const uint64_t hi = (uint64_t)rank << prog.n_local;
+    for (const PassDesc& pd : prog.passes) run_pass(prog, pd, hi, reinterpret_cast<cplx*>(state));
+    if (info_out) {
+        info_out[0] = (int64_t)prog.passes.size();
+        info_out[1] = (int64_t)prog.lops.size();
+        int64_t sw = 0;
+        for (auto& p : prog.passes) sw += p.n_sweeps;
+        info_out[2] = sw;
+    }
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default")))
+int emu_describe(int n, int n_global, const qsim_gate_t* gates, int64_t ng, int min_low_bits, char* buf, int cap) {
+    CompileOptions opt;
+    opt.n_global = n_global;
+    if (min_low_bits > 0) opt.min_low_bits = min_low_bits;
+    Program prog;
+    std::string e;
+    if (!compile(n, gates, ng, opt, prog, &e)) { std::strncpy(buf, e.c_str(), cap - 1); buf[cap - 1] = 0; return -1; }
+    std::string d = prog.describe();
+    std::strncpy(buf, d.c_str(), cap - 1);
+    buf[cap - 1] = 0;
+    return 0;
+}
