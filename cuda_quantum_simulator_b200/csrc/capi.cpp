@@ -137,7 +137,7 @@ qsim_status_t qsim_program_compile(int n, int n_global, const qsim_gate_t* gates
         build(n, gates, ng);   // validation only
         auto p = std::make_unique<qsim_program>();
         p->n_global = n_global;
-        b200::CompileOptions opt;
+        b200::CompileOptions opt = b200::default_options();
         opt.n_global = n_global;
         std::string err;
         if (!b200::compile(n, gates, ng, opt, p->dev.host, &err)) throw std::runtime_error(err);
@@ -260,7 +260,7 @@ qsim_status_t qsim_sim_run(qsim_sim_t* s, int circuit_qubits, const qsim_gate_t*
         if (s->n_global == 0) { s->sim->run(c); return; }
         if (circuit_qubits != s->n_total) throw std::invalid_argument("Circuit qubit count doesn't match simulator");
         b200::Program prog;
-        b200::CompileOptions opt;
+        b200::CompileOptions opt = b200::default_options();
         opt.n_global = s->n_global;
         std::string err;
         if (!b200::compile(s->n_total, gates, ng, opt, prog, &err)) throw std::runtime_error(err);
@@ -275,7 +275,7 @@ qsim_status_t qsim_sim_apply_gate(qsim_sim_t* s, const qsim_gate_t* g) {
         if (s->n_global == 0) s->sim->applyGate(c.getGates()[0]);
         else {
             b200::Program prog;
-            b200::CompileOptions opt;
+            b200::CompileOptions opt = b200::default_options();
             opt.n_global = s->n_global;
             std::string err;
             if (!b200::compile(s->n_total, g, 1, opt, prog, &err)) throw std::runtime_error(err);
@@ -367,6 +367,16 @@ qsim_status_t qsim_sim_pass_time_ms(qsim_sim_t* s, double* total_ms, int64_t* n_
     return guarded([&] {
         require(s != nullptr, "null simulator");
         s->sim->state().engine().drainTiming(total_ms, n_passes);
+    });
+}
+
+qsim_status_t qsim_sim_pass_times(qsim_sim_t* s, double* out_ms, int64_t cap, int64_t* n_out) {
+    return guarded([&] {
+        require(s != nullptr && n_out != nullptr, "null argument");
+        std::vector<double> each;
+        s->sim->state().engine().drainTiming(nullptr, nullptr, &each);
+        *n_out = (int64_t)each.size();
+        for (int64_t i = 0; i < (int64_t)each.size() && i < cap; ++i) out_ms[i] = each[i];
     });
 }
 

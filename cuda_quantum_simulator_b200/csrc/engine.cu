@@ -1,5 +1,6 @@
 #include "engine.hpp"
 
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -44,6 +45,8 @@ Engine::Engine() {
         throw std::runtime_error("qsim_b200: kernels are built for sm_100a only (found compute capability " +
                                  std::to_string(major) + ".x)");
     CUDA_CHECK(cudaEventCreateWithFlags(&staged_, cudaEventDisableTiming));
+    if (const char* e = std::getenv("QSIM_STAGES")) stages_wanted_ = std::atoi(e);
+    if (std::getenv("QSIM_TMA_1D")) use_tensor_map_ = false;
 }
 
 Engine::~Engine() {
@@ -71,13 +74,14 @@ void Engine::setTiming(bool on) {
     }
 }
 
-void Engine::drainTiming(double* total_ms, int64_t* n_passes) {
+void Engine::drainTiming(double* total_ms, int64_t* n_passes, std::vector<double>* each) {
     double tot = 0;
     for (auto& e : events_) {
         CUDA_CHECK(cudaEventSynchronize(e.second));
         float ms = 0;
         CUDA_CHECK(cudaEventElapsedTime(&ms, e.first, e.second));
         tot += ms;
+        if (each) each->push_back(ms);
         pool_.push_back(e.first);
         pool_.push_back(e.second);
     }
@@ -94,6 +98,8 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, cuDoubleComplex* st
         prm.hi_bits = hi_bits;
         prm.n_tiles = 1ULL << (pd.n - pd.t);
         prm.pd = pd;
+        prm.stages = pick_stages(pd, stages_wanted_);
+        prm.use_tensor_map = use_tensor_map_ ? 1 : 0;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (timing_) {
             e0 = getEvent();
@@ -111,7 +117,11 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, cuDoubleComplex* st
 
 void Engine::execute(const Program& p, cuDoubleComplex* state, uint64_t hi_bits) {
     const size_t n = p.ops.size();
-    if (n == 0) return;
+    if (p.passes.empty()) return;
+    if (n == 0) {   // passes without ops exist: a pure index permutation (deferred X gates)
+        launchAll(p, nullptr, state, hi_bits);
+        return;
+    }
     if (staged_pending_) {           // the pinned buffer may still be in flight from the previous run
         CUDA_CHECK(cudaEventSynchronize(staged_));
         staged_pending_ = false;
@@ -139,8 +149,8 @@ void Engine::execute(const Program& p, cuDoubleComplex* state, uint64_t hi_bits)
 }
 
 void Engine::execute(const DeviceProgram& p, cuDoubleComplex* state, uint64_t hi_bits) {
-    if (p.host.ops.empty()) return;
-    if (!p.d_ops) throw std::runtime_error("qsim_b200: program was not uploaded");
+    if (p.host.passes.empty()) return;
+    if (!p.d_ops && !p.host.ops.empty()) throw std::runtime_error("qsim_b200: program was not uploaded");
     launchAll(p.host, p.d_ops, state, hi_bits);
 }
 

@@ -48,12 +48,14 @@ public:
 
     void setTiming(bool on);
     // Sum of pass-kernel device times since the last call, and the number of passes timed.
-    void drainTiming(double* total_ms, int64_t* n_passes);
+    void drainTiming(double* total_ms, int64_t* n_passes, std::vector<double>* each = nullptr);
 
 private:
     cudaStream_t stream_ = nullptr;
     int num_sms_ = 0;
     int64_t launches_ = 0;
+    bool use_tensor_map_ = true;
+    int stages_wanted_ = 0;   // 0 = as deep as shared memory allows
     // staging for execute(const Program&)
     DevOp* d_ops_ = nullptr;
     size_t d_cap_ = 0;

@@ -19,11 +19,15 @@ struct PassParams {
     const DevOp* ops;         // device copy of this pass's ops
     uint64_t hi_bits;         // rank << n_local for a sharded state, else 0 (only used by controls)
     uint64_t n_tiles;         // 2^(pd.n - pd.t)
+    int32_t stages;           // depth of the shared-memory ring
+    int32_t use_tensor_map;   // 1: cp.async.bulk.tensor boxes (default); 0: one 1-D bulk copy per contiguous run
     PassDesc pd;
 };
 static_assert(sizeof(PassParams) <= 4000, "kernel parameter space");
 
-size_t pass_smem_bytes(const PassDesc& pd);
+constexpr int kMaxStages = 8;
+size_t pass_smem_bytes(const PassDesc& pd, int stages);
+int pick_stages(const PassDesc& pd, int wanted);
 cudaError_t launch_pass(const PassParams& params, int num_sms, cudaStream_t stream);
 
 }  // namespace b200

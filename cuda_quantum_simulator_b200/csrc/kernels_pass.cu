@@ -17,7 +17,10 @@
 // Algorithmic traffic: 2 * 16 * 2^n bytes per pass.
 #include "kernels.cuh"
 
+#include <cuda.h>
+
 #include <cstdio>
+#include <cstring>
 
 namespace qsim {
 namespace b200 {
@@ -73,6 +76,40 @@ __device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_sr
                  : "memory");
 }
 
+// tensor-map (tiled) variants: one instruction moves a whole 5-D box (SASS UTMALDG / UTMASTG)
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, const int (&c)[5], uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const int (&c)[5], const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(map),
+                 "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(smem_u32(smem_src))
+                 : "memory");
+}
+
+// coordinates of the box that starts at global amplitude index g
+__device__ __forceinline__ void tma_coords(const PassDesc& pd, uint64_t g, int (&c)[5]) {
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+        const uint32_t rb = pd.tma_dim[d].range_bits;
+        const uint64_t v = rb ? ((g >> pd.tma_dim[d].start_bit) & ((1ULL << rb) - 1)) : 0ULL;
+        c[d] = (int)(d == 0 ? v * 2 : v);   // dimension 0 counts doubles
+    }
+}
+
+__device__ __forceinline__ uint64_t instr_offset(const PassDesc& pd, uint32_t q) {
+    uint64_t off = 0;
+    const int box_bits = pd.t - pd.tma_instr_bits;
+#pragma unroll 1
+    for (int b = 0; b < pd.tma_instr_bits; ++b)
+        if ((q >> b) & 1) off |= 1ULL << pd.tile_bits[box_bits + b];
+    return off;
+}
+
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -105,44 +142,54 @@ __device__ __forceinline__ uint64_t run_offset(const PassDesc& pd, uint32_t run)
 }
 
 // ---- op application on the thread's register file -------------------------------------------------
+// Everything below is straight-line code over the 16 register slots: no per-slot branches, so the
+// 16 independent dependency chains interleave (controls become selects, and ops without controls —
+// the common case — carry no predicate at all).
 
-template <int J, int KIND>
-__device__ __forceinline__ void reg_pairs_k(const DevOp& op, uint32_t sm, double (&ar)[16], double (&ai)[16]) {
+template <int J, int KIND, bool CTRL>
+__device__ __forceinline__ void reg_pairs(const DevOp& op, uint32_t sm, double (&ar)[16], double (&ai)[16]) {
     const double m00r = op.m[0], m00i = op.m[1], m01r = op.m[2], m01i = op.m[3];
     const double m10r = op.m[4], m10i = op.m[5], m11r = op.m[6], m11i = op.m[7];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        if (k & (1 << J)) continue;   // k enumerates the slots whose target bit is 0
+        if (k & (1 << J)) continue;   // compile-time: k enumerates the slots whose target bit is 0
         const int k1 = k | (1 << J);
-        if (!((sm >> k) & 1)) continue;
         const double xr = ar[k], xi = ai[k], yr = ar[k1], yi = ai[k1];
+        double n0r, n0i, n1r, n1i;
         if (KIND == OP_FLIP) {
-            ar[k] = yr; ai[k] = yi; ar[k1] = xr; ai[k1] = xi;
+            n0r = yr; n0i = yi; n1r = xr; n1i = xi;
         } else if (KIND == OP_ADIAG) {
-            ar[k] = m01r * yr - m01i * yi; ai[k] = m01r * yi + m01i * yr;
-            ar[k1] = m10r * xr - m10i * xi; ai[k1] = m10r * xi + m10i * xr;
+            n0r = m01r * yr - m01i * yi; n0i = m01r * yi + m01i * yr;
+            n1r = m10r * xr - m10i * xi; n1i = m10r * xi + m10i * xr;
         } else if (KIND == OP_MATREAL) {
-            ar[k] = m00r * xr + m01r * yr; ai[k] = m00r * xi + m01r * yi;
-            ar[k1] = m10r * xr + m11r * yr; ai[k1] = m10r * xi + m11r * yi;
+            n0r = m00r * xr + m01r * yr; n0i = m00r * xi + m01r * yi;
+            n1r = m10r * xr + m11r * yr; n1i = m10r * xi + m11r * yi;
         } else {
-            ar[k] = m00r * xr - m00i * xi + m01r * yr - m01i * yi;
-            ai[k] = m00r * xi + m00i * xr + m01r * yi + m01i * yr;
-            ar[k1] = m10r * xr - m10i * xi + m11r * yr - m11i * yi;
-            ai[k1] = m10r * xi + m10i * xr + m11r * yi + m11i * yr;
+            n0r = m00r * xr - m00i * xi + m01r * yr - m01i * yi;
+            n0i = m00r * xi + m00i * xr + m01r * yi + m01i * yr;
+            n1r = m10r * xr - m10i * xi + m11r * yr - m11i * yi;
+            n1i = m10r * xi + m10i * xr + m11r * yi + m11i * yr;
+        }
+        if (CTRL) {
+            const bool on = (sm >> k) & 1;
+            ar[k] = on ? n0r : xr; ai[k] = on ? n0i : xi; ar[k1] = on ? n1r : yr; ai[k1] = on ? n1i : yi;
+        } else {
+            ar[k] = n0r; ai[k] = n0i; ar[k1] = n1r; ai[k1] = n1i;
         }
     }
 }
 
-template <int J>
-__device__ __forceinline__ void reg_pairs(const DevOp& op, uint32_t sm, double (&ar)[16], double (&ai)[16]) {
-    switch (op.kind) {
-        case OP_FLIP: reg_pairs_k<J, OP_FLIP>(op, sm, ar, ai); break;
-        case OP_ADIAG: reg_pairs_k<J, OP_ADIAG>(op, sm, ar, ai); break;
-        case OP_MATREAL: reg_pairs_k<J, OP_MATREAL>(op, sm, ar, ai); break;
-        default: reg_pairs_k<J, OP_MAT>(op, sm, ar, ai); break;
+template <int KIND, bool CTRL>
+__device__ __forceinline__ void reg_target(const DevOp& op, uint32_t sm, double (&ar)[16], double (&ai)[16]) {
+    switch (op.tbit) {
+        case 0: reg_pairs<0, KIND, CTRL>(op, sm, ar, ai); break;
+        case 1: reg_pairs<1, KIND, CTRL>(op, sm, ar, ai); break;
+        case 2: reg_pairs<2, KIND, CTRL>(op, sm, ar, ai); break;
+        default: reg_pairs<3, KIND, CTRL>(op, sm, ar, ai); break;
     }
 }
 
+template <int KIND, bool CTRL>
 __device__ __forceinline__ void lane_target(const DevOp& op, uint32_t sm, uint32_t tid, double (&ar)[16],
                                             double (&ai)[16]) {
     const int lm = 1 << op.tbit;
@@ -150,52 +197,88 @@ __device__ __forceinline__ void lane_target(const DevOp& op, uint32_t sm, uint32
     // coefficient of my own amplitude and of my partner's
     const double cor = b ? op.m[6] : op.m[0], coi = b ? op.m[7] : op.m[1];
     const double cpr = b ? op.m[4] : op.m[2], cpi = b ? op.m[5] : op.m[3];
-    const uint8_t kind = op.kind;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const double pr = shfl_xor_f64(ar[k], lm), pi = shfl_xor_f64(ai[k], lm);
-        if (!((sm >> k) & 1)) continue;
         const double xr = ar[k], xi = ai[k];
-        if (kind == OP_FLIP) { ar[k] = pr; ai[k] = pi; }
-        else if (kind == OP_ADIAG) { ar[k] = cpr * pr - cpi * pi; ai[k] = cpr * pi + cpi * pr; }
-        else if (kind == OP_MATREAL) { ar[k] = cor * xr + cpr * pr; ai[k] = cor * xi + cpr * pi; }
+        double nr, ni;
+        if (KIND == OP_FLIP) { nr = pr; ni = pi; }
+        else if (KIND == OP_ADIAG) { nr = cpr * pr - cpi * pi; ni = cpr * pi + cpi * pr; }
+        else if (KIND == OP_MATREAL) { nr = cor * xr + cpr * pr; ni = cor * xi + cpr * pi; }
         else {
-            ar[k] = cor * xr - coi * xi + cpr * pr - cpi * pi;
-            ai[k] = cor * xi + coi * xr + cpr * pi + cpi * pr;
+            nr = cor * xr - coi * xi + cpr * pr - cpi * pi;
+            ni = cor * xi + coi * xr + cpr * pi + cpi * pr;
+        }
+        if (CTRL) {
+            const bool on = (sm >> k) & 1;
+            ar[k] = on ? nr : xr; ai[k] = on ? ni : xi;
+        } else {
+            ar[k] = nr; ai[k] = ni;
         }
     }
 }
 
+template <bool CTRL>
 __device__ __forceinline__ void diagonal(const DevOp& op, uint32_t sm, uint32_t tid, uint64_t gbase, double (&ar)[16],
                                          double (&ai)[16]) {
-    uint32_t tsl;
-    if (op.thome == T_REG) tsl = op.tslots;
-    else {
-        const bool b = (op.thome == T_THREAD) ? ((tid & op.tmask_thr) != 0) : ((gbase & op.tmask_out) != 0);
-        tsl = b ? 0xffffu : 0u;
-    }
     const double d0r = op.m[0], d0i = op.m[1], d1r = op.m[6], d1i = op.m[7];
+    if (op.thome == T_REG) {
+        const uint32_t tsl = op.tslots;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        if (!((sm >> k) & 1)) continue;
-        const bool b = (tsl >> k) & 1;
+        for (int k = 0; k < 16; ++k) {
+            const bool b = (tsl >> k) & 1;
+            const double pr = b ? d1r : d0r, pi = b ? d1i : d0i;
+            const double xr = ar[k], xi = ai[k];
+            const double nr = xr * pr - xi * pi, ni = xr * pi + xi * pr;
+            if (CTRL) { const bool on = (sm >> k) & 1; ar[k] = on ? nr : xr; ai[k] = on ? ni : xi; }
+            else { ar[k] = nr; ai[k] = ni; }
+        }
+    } else {
+        const bool b = (op.thome == T_THREAD) ? ((tid & op.tmask_thr) != 0) : ((gbase & op.tmask_out) != 0);
         const double pr = b ? d1r : d0r, pi = b ? d1i : d0i;
-        const double xr = ar[k], xi = ai[k];
-        ar[k] = xr * pr - xi * pi;
-        ai[k] = xr * pi + xi * pr;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const double xr = ar[k], xi = ai[k];
+            const double nr = xr * pr - xi * pi, ni = xr * pi + xi * pr;
+            if (CTRL) { const bool on = (sm >> k) & 1; ar[k] = on ? nr : xr; ai[k] = on ? ni : xi; }
+            else { ar[k] = nr; ai[k] = ni; }
+        }
+    }
+}
+
+template <bool CTRL>
+__device__ __forceinline__ void apply_op(const DevOp& op, uint32_t sm, uint32_t tid, uint64_t gbase, double (&ar)[16],
+                                         double (&ai)[16]) {
+    if (op.kind == OP_DIAG) { diagonal<CTRL>(op, sm, tid, gbase, ar, ai); return; }
+    if (op.thome == T_LANE) {
+        switch (op.kind) {
+            case OP_FLIP: lane_target<OP_FLIP, CTRL>(op, sm, tid, ar, ai); break;
+            case OP_ADIAG: lane_target<OP_ADIAG, CTRL>(op, sm, tid, ar, ai); break;
+            case OP_MATREAL: lane_target<OP_MATREAL, CTRL>(op, sm, tid, ar, ai); break;
+            default: lane_target<OP_MAT, CTRL>(op, sm, tid, ar, ai); break;
+        }
+    } else {
+        switch (op.kind) {
+            case OP_FLIP: reg_target<OP_FLIP, CTRL>(op, sm, ar, ai); break;
+            case OP_ADIAG: reg_target<OP_ADIAG, CTRL>(op, sm, ar, ai); break;
+            case OP_MATREAL: reg_target<OP_MATREAL, CTRL>(op, sm, ar, ai); break;
+            default: reg_target<OP_MAT, CTRL>(op, sm, ar, ai); break;
+        }
     }
 }
 
 }  // namespace
 
-__global__ void __launch_bounds__(kPassThreads, 1) fused_pass_kernel(const __grid_constant__ PassParams P) {
+__global__ void __launch_bounds__(kPassThreads, 1)
+fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const PassDesc& pd = P.pd;
     const uint32_t tile_bytes = 16u << pd.t;
     unsigned char* tiles = smem;
-    DevOp* sops = reinterpret_cast<DevOp*>(smem + kStages * tile_bytes);
-    uint64_t* full = reinterpret_cast<uint64_t*>(sops + pd.n_ops);
-    uint64_t* done = full + kStages;
+    const int n_stages = P.stages;
+    DevOp* sops = reinterpret_cast<DevOp*>(smem + (size_t)n_stages * tile_bytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(sops + pd.n_ops + 1);   // +1: zeroed padding record (prefetch)
+    uint64_t* done = full + n_stages;
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -205,9 +288,11 @@ __global__ void __launch_bounds__(kPassThreads, 1) fused_pass_kernel(const __gri
         uint4* dst = reinterpret_cast<uint4*>(sops);
         const int n16 = pd.n_ops * (int)(sizeof(DevOp) / 16);
         for (int i = tid; i < n16; i += kPassThreads) dst[i] = src[i];
+        if (tid < (int)(sizeof(DevOp) / 16)) dst[n16 + tid] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        if (P.use_tensor_map) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        for (int s = 0; s < n_stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&done[s], kComputeWarps);
         }
@@ -217,48 +302,85 @@ __global__ void __launch_bounds__(kPassThreads, 1) fused_pass_kernel(const __gri
 
     const uint64_t n_tiles = P.n_tiles;
     const uint64_t first = blockIdx.x, stride = gridDim.x;
-    const uint64_t n_my = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+    // Work items of this CTA.  Without a tile XOR item i is tile first + i*stride.  With one, tiles are
+    // handled in partner pairs (tau, tau ^ xor_tau): items 2j and 2j+1 are the two members of pair
+    // first + j*stride, each is written to the other's location, and a tile is only overwritten after its
+    // own contents have been loaded (see the wait before the store below).
+    const uint64_t xor_tau = pd.xor_tau;
+    const int pivot = xor_tau ? 63 - __clzll((long long)xor_tau) : 0;
+    const uint64_t n_units = xor_tau ? n_tiles / 2 : n_tiles;
+    const uint64_t my_units = first < n_units ? (n_units - first + stride - 1) / stride : 0;
+    const uint64_t n_my = xor_tau ? 2 * my_units : my_units;
+    auto tile_of = [&](uint64_t i) -> uint64_t {
+        if (!xor_tau) return first + i * stride;
+        const uint64_t p = first + (i >> 1) * stride;
+        const uint64_t t0 = (p & ((1ULL << pivot) - 1)) | ((p >> pivot) << (pivot + 1));   // pair id with a 0 at the pivot bit
+        return (i & 1) ? (t0 ^ xor_tau) : t0;
+    };
     const uint32_t n_runs = 1u << pd.n_high;
     const uint32_t run_bytes = 16u << pd.L;
+    const uint32_t n_instr = 1u << pd.tma_instr_bits;
+    const uint32_t box_bytes = tile_bytes >> pd.tma_instr_bits;
     unsigned char* const gstate = reinterpret_cast<unsigned char*>(P.state);
 
     if (warp == kComputeWarps) {
         // ===================== TMA warp =====================
         auto issue_load = [&](uint64_t i) {
-            const int s = (int)(i % kStages);
-            const uint64_t base = tile_base(pd, first + i * stride);
+            const int s = (int)(i % n_stages);
+            const uint64_t base = tile_base(pd, tile_of(i));
             if (lane == 0) mbar_expect_tx(&full[s], tile_bytes);
             __syncwarp();
-            for (uint32_t run = lane; run < n_runs; run += 32) {
-                const uint64_t g = base + run_offset(pd, run);
-                tma_load_1d(tiles + (size_t)s * tile_bytes + (size_t)run * run_bytes, gstate + g * 16, run_bytes,
-                            &full[s]);
+            if (P.use_tensor_map) {
+                for (uint32_t q = lane; q < n_instr; q += 32) {
+                    int c[5];
+                    tma_coords(pd, base + instr_offset(pd, q), c);
+                    tma_load_5d(tiles + (size_t)s * tile_bytes + (size_t)q * box_bytes, &tmap, c, &full[s]);
+                }
+            } else {
+                for (uint32_t run = lane; run < n_runs; run += 32) {
+                    const uint64_t g = base + run_offset(pd, run);
+                    tma_load_1d(tiles + (size_t)s * tile_bytes + (size_t)run * run_bytes, gstate + g * 16, run_bytes,
+                                &full[s]);
+                }
             }
         };
-        const uint64_t pre = n_my < (uint64_t)kStages ? n_my : (uint64_t)kStages;
+        const uint64_t pre = n_my < (uint64_t)n_stages ? n_my : (uint64_t)n_stages;
         for (uint64_t i = 0; i < pre; ++i) issue_load(i);
         for (uint64_t i = 0; i < n_my; ++i) {
-            const int s = (int)(i % kStages);
-            const uint32_t parity = (uint32_t)((i / kStages) & 1);
+            const int s = (int)(i % n_stages);
+            const uint32_t parity = (uint32_t)((i / n_stages) & 1);
             mbar_wait(&done[s], parity);
-            const uint64_t base = tile_base(pd, first + i * stride);
-            for (uint32_t run = lane; run < n_runs; run += 32) {
-                const uint64_t g = base + run_offset(pd, run);
-                tma_store_1d(gstate + g * 16, tiles + (size_t)s * tile_bytes + (size_t)run * run_bytes, run_bytes);
+            if (xor_tau && !(i & 1)) {
+                // this tile goes to its partner's location: the partner (item i+1) must have been read first
+                const uint64_t j = i + 1;
+                mbar_wait(&full[(int)(j % n_stages)], (uint32_t)((j / n_stages) & 1));
+            }
+            const uint64_t base = tile_base(pd, tile_of(i) ^ xor_tau);
+            if (P.use_tensor_map) {
+                for (uint32_t q = lane; q < n_instr; q += 32) {
+                    int c[5];
+                    tma_coords(pd, base + instr_offset(pd, q), c);
+                    tma_store_5d(&tmap, c, tiles + (size_t)s * tile_bytes + (size_t)q * box_bytes);
+                }
+            } else {
+                for (uint32_t run = lane; run < n_runs; run += 32) {
+                    const uint64_t g = base + run_offset(pd, run);
+                    tma_store_1d(gstate + g * 16, tiles + (size_t)s * tile_bytes + (size_t)run * run_bytes, run_bytes);
+                }
             }
             tma_store_commit();
             tma_store_wait_read();   // shared memory of this stage may be overwritten now
             __syncwarp();
-            if (i + kStages < n_my) issue_load(i + kStages);
+            if (i + n_stages < n_my) issue_load(i + n_stages);
         }
         tma_store_wait_all();
     } else {
         // ===================== compute warps =====================
         double ar[16], ai[16];
         for (uint64_t i = 0; i < n_my; ++i) {
-            const int s = (int)(i % kStages);
-            const uint32_t parity = (uint32_t)((i / kStages) & 1);
-            const uint64_t gbase = tile_base(pd, first + i * stride) | P.hi_bits;
+            const int s = (int)(i % n_stages);
+            const uint32_t parity = (uint32_t)((i / n_stages) & 1);
+            const uint64_t gbase = tile_base(pd, tile_of(i)) | P.hi_bits;
             unsigned char* tile = tiles + (size_t)s * tile_bytes;
             mbar_wait(&full[s], parity);
 
@@ -268,7 +390,11 @@ __global__ void __launch_bounds__(kPassThreads, 1) fused_pass_kernel(const __gri
                 if (sw > 0) compute_barrier();
                 const uint32_t n_active = 1u << sd.nthr;
                 const bool warp_active = (warp << 5) < n_active;
-                if (!warp_active) continue;
+                const uint32_t xl = (sw + 1 == pd.n_sweeps) ? pd.xor_local : 0u;   // deferred X gates, see the store
+                if (!warp_active) {
+                    if (xl) compute_barrier();   // keep the barrier count equal across warps
+                    continue;
+                }
                 const bool active = tid < n_active;
                 const int slots = 1 << sd.r;
                 uint32_t base_local = 0;
@@ -290,26 +416,24 @@ __global__ void __launch_bounds__(kPassThreads, 1) fused_pass_kernel(const __gri
 #pragma unroll 1
                 for (int o = sd.op_begin; o < sd.op_end; ++o) {
                     const DevOp& op = sops[o];
-                    if ((gbase & op.cmask_out) != op.cval_out) continue;
-                    const bool thr_ok = (tid & op.cmask_thr) == op.cval_thr;
-                    const uint32_t sm = thr_ok ? (uint32_t)op.slotmask : 0u;
-                    if (op.kind == OP_DIAG) {
-                        diagonal(op, sm, tid, gbase, ar, ai);
-                    } else if (op.thome == T_LANE) {
-                        lane_target(op, sm, tid, ar, ai);
+                    if (op.has_out && (gbase & op.cmask_out) != op.cval_out) continue;
+                    // warp-uniform: does any control live in this sweep's thread / register bits?
+                    const bool has_ctrl = (op.cmask_thr != 0u) || (op.slotmask != 0xffffu);
+                    if (!has_ctrl) {
+                        apply_op<false>(op, 0xffffu, tid, gbase, ar, ai);
                     } else {
-                        switch (op.tbit) {
-                            case 0: reg_pairs<0>(op, sm, ar, ai); break;
-                            case 1: reg_pairs<1>(op, sm, ar, ai); break;
-                            case 2: reg_pairs<2>(op, sm, ar, ai); break;
-                            default: reg_pairs<3>(op, sm, ar, ai); break;
-                        }
+                        const bool thr_ok = (tid & op.cmask_thr) == op.cval_thr;
+                        const uint32_t sm = thr_ok ? (uint32_t)op.slotmask : 0u;
+                        apply_op<true>(op, sm, tid, gbase, ar, ai);
                     }
                 }
+                // the pass's deferred X gates: the last sweep stores to the XOR-ed tile-local index (other
+                // threads' slots, hence the barrier: everybody has finished loading)
+                if (xl) compute_barrier();
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     if (active && k < slots)
-                        *reinterpret_cast<double2*>(tile + (size_t)(base_local + sd.slot_off[k]) * 16) =
+                        *reinterpret_cast<double2*>(tile + (size_t)((base_local + sd.slot_off[k]) ^ xl) * 16) =
                             make_double2(ar[k], ai[k]);
                 }
             }
@@ -321,11 +445,61 @@ __global__ void __launch_bounds__(kPassThreads, 1) fused_pass_kernel(const __gri
     }
 }
 
-size_t pass_smem_bytes(const PassDesc& pd) {
-    return (size_t)kStages * ((size_t)16 << pd.t) + (size_t)pd.n_ops * sizeof(DevOp) + 2 * kStages * sizeof(uint64_t);
+size_t pass_smem_bytes(const PassDesc& pd, int stages) {
+    return (size_t)stages * ((size_t)16 << pd.t) + ((size_t)pd.n_ops + 1) * sizeof(DevOp) + 2 * (size_t)stages * sizeof(uint64_t);
 }
 
-cudaError_t launch_pass(const PassParams& params, int num_sms, cudaStream_t stream) {
+// Deepest ring that fits the 227 KiB of shared memory (at most kMaxStages).
+int pick_stages(const PassDesc& pd, int wanted) {
+    int st = wanted > 0 ? wanted : kMaxStages;
+    if (st > kMaxStages) st = kMaxStages;
+    while (st > 1 && pass_smem_bytes(pd, st) > (size_t)kMaxDynamicSmem) --st;
+    return st;
+}
+
+namespace {
+
+using encode_fn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_fn get_encode() {
+    static encode_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<encode_fn>(p);
+    }();
+    return fn;
+}
+
+// The state viewed as a 5-D tensor of doubles whose dimensions are the pass's runs of tile bits.
+bool encode_tensor_map(const PassParams& prm, CUtensorMap* out) {
+    encode_fn enc = get_encode();
+    if (!enc) return false;
+    const PassDesc& pd = prm.pd;
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t box[5], estride[5] = {1, 1, 1, 1, 1};
+    for (int d = 0; d < 5; ++d) {
+        const TmaDim& td = pd.tma_dim[d];
+        gdim[d] = (cuuint64_t)1 << td.range_bits;
+        box[d] = 1u << td.box_bits;
+        if (d == 0) { gdim[d] *= 2; box[d] *= 2; }
+        else gstride[d - 1] = (cuuint64_t)16 << td.start_bit;
+    }
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, prm.state, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t stream) {
+    PassParams params = params_in;
+    alignas(64) CUtensorMap tmap;
+    std::memset(&tmap, 0, sizeof(tmap));
+    if (params.use_tensor_map && !encode_tensor_map(params, &tmap)) return cudaErrorInvalidValue;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e =
@@ -333,10 +507,10 @@ cudaError_t launch_pass(const PassParams& params, int num_sms, cudaStream_t stre
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const size_t smem = pass_smem_bytes(params.pd);
-    if (smem > (size_t)kMaxDynamicSmem) return cudaErrorInvalidValue;
+    const size_t smem = pass_smem_bytes(params.pd, params.stages);
+    if (params.stages < 1 || smem > (size_t)kMaxDynamicSmem) return cudaErrorInvalidValue;
     uint64_t grid = params.n_tiles < (uint64_t)num_sms ? params.n_tiles : (uint64_t)num_sms;
-    fused_pass_kernel<<<(unsigned)grid, kPassThreads, smem, stream>>>(params);
+    fused_pass_kernel<<<(unsigned)grid, kPassThreads, smem, stream>>>(params, tmap);
     return cudaGetLastError();
 }
 

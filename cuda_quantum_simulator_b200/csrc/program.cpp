@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
@@ -68,6 +69,15 @@ bool is_identity(const LogicalOp& o) {
 }
 
 }  // namespace
+
+CompileOptions default_options() {
+    CompileOptions o;
+    if (const char* e = std::getenv("QSIM_TILE_BITS")) { int v = std::atoi(e); if (v >= 3 && v <= kMaxTileBits) o.max_tile_bits = v; }
+    if (const char* e = std::getenv("QSIM_MIN_LOW_BITS")) { int v = std::atoi(e); if (v >= 3 && v <= kMaxTileBits) o.min_low_bits = v; }
+    if (std::getenv("QSIM_NO_MERGE")) o.merge = false;
+    if (std::getenv("QSIM_NO_REORDER")) o.reorder = false;
+    return o;
+}
 
 void classify(LogicalOp& o) {
     const double* m = o.m;
@@ -171,6 +181,38 @@ void choose_tile_bits(uint64_t need, int n_local, int t, int lmin, PassDesc& pd)
     pd.L = LL;
     pd.n_high = pd.t - pd.L;
     for (int i = 0; i < pd.t && i < kMaxTileBits; ++i) pd.tile_bits[i] = (uint8_t)bits[i];
+    // Tensor-map geometry: contiguous runs of tile bits become box dimensions (dim 0 at most 7 bits =
+    // 256 doubles, the others at most 8 bits); each dimension's coordinate range reaches up to the next
+    // one.  Runs beyond the fifth dimension are enumerated by separate instructions.
+    {
+        std::vector<std::pair<int, int>> chunks;   // (first bit, length)
+        for (size_t i = 0; i < bits.size();) {
+            size_t j = i;
+            const int cap = chunks.empty() ? 7 : 8;
+            while (j + 1 < bits.size() && bits[j + 1] == bits[j] + 1 && (int)(j + 1 - i) < cap) ++j;
+            chunks.emplace_back(bits[i], (int)(j - i + 1));
+            i = j + 1;
+        }
+        const int nd = std::min<int>(5, (int)chunks.size());
+        int instr_bits = 0;
+        for (size_t c = nd; c < chunks.size(); ++c) instr_bits += chunks[c].second;
+        pd.tma_instr_bits = (uint8_t)instr_bits;
+        for (int d = 0; d < 5; ++d) {
+            TmaDim& td = pd.tma_dim[d];
+            if (d < nd) {
+                const int start = d == 0 ? 0 : chunks[d].first;
+                const int end = (d + 1 < nd) ? chunks[d + 1].first : n_local;
+                td.start_bit = (uint8_t)start;
+                td.range_bits = (uint8_t)(end - start);
+                td.box_bits = (uint8_t)chunks[d].second;
+            } else {
+                td.start_bit = (uint8_t)n_local;   // degenerate dimension of extent 1
+                td.range_bits = 0;
+                td.box_bits = 0;
+            }
+            td.pad = 0;
+        }
+    }
     // segments of outer (non-tile) bits
     pd.n_segments = 0;
     uint64_t tmask = 0;
@@ -201,12 +243,28 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
     const int t = std::min(opt.max_tile_bits, nl);
     const int lmin = std::min(std::max(opt.min_low_bits, 3), t);
 
+    // 0. X frame: an uncontrolled X is not executed; it toggles a pending index-XOR mask through which
+    //    later ops are conjugated (X on their target: swap the matrix's rows and columns; X on a control:
+    //    the control fires on 0).  What is left at the end is applied by the last pass's addressing.
+    uint64_t xf = opt.initial_xor;
     // 1. merge
-    for (auto& op : lops_in) {
+    for (auto& op_in : lops_in) {
+        LogicalOp op = op_in;
+        if (opt.defer_x) {
+            if (op.kind == OP_FLIP && op.cmask == 0) { xf ^= 1ULL << op.target; continue; }
+            if ((xf >> op.target) & 1) {
+                std::swap(op.m[0], op.m[6]); std::swap(op.m[1], op.m[7]);
+                std::swap(op.m[2], op.m[4]); std::swap(op.m[3], op.m[5]);
+                classify(op);
+            }
+            op.cval ^= (xf & op.cmask);
+        }
         if (!is_diag_kind(op.kind) && op.target >= nl)
             return fail("non-diagonal gate on a global qubit must be remapped before compilation");
         append_merged(out.lops, op, opt.merge);
     }
+    out.global_xor = nl < 64 ? (xf >> nl) : 0;
+    const uint64_t xf_local = nl < 64 ? (xf & ((1ULL << nl) - 1)) : xf;
     {
         std::vector<LogicalOp> kept;
         for (auto& op : out.lops)
@@ -240,8 +298,11 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
         pending.swap(deferred);
     }
 
+    if (plans.empty() && xf_local) plans.emplace_back();   // nothing but a deferred X: one pure permutation pass
+
     // 3. per pass: tile bits, sweeps, device records
-    for (auto& plan : plans) {
+    for (size_t plan_i = 0; plan_i < plans.size(); ++plan_i) {
+        PassPlan& plan = plans[plan_i];
         PassDesc pd{};
         pd.n = nl;
         choose_tile_bits(plan.need, nl, t, lmin, pd);
@@ -258,8 +319,22 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
         pd.n_ops = 0;
         pd.n_sweeps = 0;
 
+        if (plan_i + 1 == plans.size() && xf_local) {
+            // the deferred X frame rides on the last pass: tile bits -> XOR of the tile-local store index,
+            // other bits -> the tile is written to the partner tile's location
+            uint64_t tau_bit = 0;
+            int src = 0;
+            for (int q = 0; q < nl; ++q) {
+                if (local_of[q] >= 0) { if ((xf_local >> q) & 1) pd.xor_local |= 1u << local_of[q]; }
+                else { if ((xf_local >> q) & 1) tau_bit |= 1ULL << src; ++src; }
+            }
+            pd.xor_tau = tau_bit;
+        }
+
         std::vector<int> todo = plan.op_idx;
-        while (!todo.empty()) {
+        bool need_empty_sweep = todo.empty();
+        while (!todo.empty() || need_empty_sweep) {
+            need_empty_sweep = false;
             if (pd.n_sweeps >= kMaxSweeps) return fail("too many sweeps in one pass");
             // choose the targetable set greedily in order (commutation-aware deferral as above)
             uint32_t S = 0;
@@ -286,7 +361,7 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
                     if (!is_diag_kind(op.kind)) uses[local_of[op.target]]++;
                 } else deferred.push_back(idx);
             }
-            if (chosen.empty()) return fail("sweep scheduler made no progress");
+            if (chosen.empty() && !plan.op_idx.empty()) return fail("sweep scheduler made no progress");
 
             // role assignment: tid bits 0..2 = tile bits 0..2; busiest other targets -> registers;
             // remaining targets -> lane bits 3,4; everything else -> leftover lane/warp bits.
@@ -365,6 +440,8 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
                         d.tbit = (uint8_t)tb;
                     }
                 }
+                d.has_out = (d.cmask_out != 0 || d.tmask_out != 0) ? 1u : 0u;
+                d.opcode = op_code(d.kind, d.thome, d.tbit, d.cmask_thr != 0 || d.slotmask != 0xffffu);
                 out.ops.push_back(d);
                 pd.n_ops++;
             }

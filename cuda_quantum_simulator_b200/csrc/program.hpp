@@ -24,7 +24,6 @@ namespace qsim {
 namespace b200 {
 
 constexpr int kMaxTileBits = 12;         // 2^12 amplitudes * 16 B = 64 KiB per pipeline stage
-constexpr int kStages = 3;               // TMA ring depth (3 * 64 KiB of 227 KiB shared memory)
 constexpr int kComputeWarps = 8;
 constexpr int kComputeThreads = kComputeWarps * 32;
 constexpr int kMaxRegBits = 4;           // 16 amplitudes (32 doubles) per thread
@@ -52,13 +51,13 @@ struct alignas(16) DevOp {
     uint8_t kind;
     uint8_t thome;
     uint8_t tbit;
-    uint8_t pad0;
+    uint8_t opcode;       // dense dispatch code, see op_code(): (kind, where the target lives, has in-tile controls)
     uint16_t slotmask;    // register slots whose register-resident control bits are satisfied
     uint16_t tslots;      // OP_DIAG with T_REG: slots whose target bit is 1
     uint32_t cmask_thr;   // controls held in tid bits
     uint32_t cval_thr;
     uint32_t tmask_thr;   // OP_DIAG with T_THREAD: the tid bit of the target
-    uint32_t pad1;
+    uint32_t has_out;     // 1 if the op depends on index bits outside the tile (cmask_out / tmask_out)
     uint64_t cmask_out;   // controls outside the tile, as a mask over the global amplitude index
     uint64_t cval_out;
     uint64_t tmask_out;   // OP_DIAG with T_OUTSIDE: global-index bit of the target
@@ -66,6 +65,15 @@ struct alignas(16) DevOp {
     double pad3[2];
 };
 static_assert(sizeof(DevOp) == 128, "DevOp layout");
+
+// opcode = kind * 10 + home * 2 + ctrl for the pair-wise kinds (home: 0 = lane, 1 + j = register bit j),
+//          40 + home * 2 + ctrl for OP_DIAG (home: 0 = register-resident target, 1 = thread/outside target)
+constexpr int kNumOpcodes = 44;
+inline uint8_t op_code(uint8_t kind, uint8_t thome, uint8_t tbit, bool ctrl) {
+    if (kind == OP_DIAG) return (uint8_t)(40 + (thome == T_REG ? 0 : 2) + (ctrl ? 1 : 0));
+    const int home = thome == T_LANE ? 0 : 1 + tbit;
+    return (uint8_t)(kind * 10 + home * 2 + (ctrl ? 1 : 0));
+}
 
 struct SweepDesc {
     uint16_t op_begin, op_end;   // indices into the pass's op array
@@ -83,6 +91,13 @@ struct Segment {                 // tile number -> global base index, one contig
     uint8_t pad[6];
 };
 
+// One dimension of the pass's tensor map (cp.async.bulk.tensor): index bits [start_bit,
+// start_bit + range_bits); the box covers the lowest box_bits of that range (the tile bits), the
+// remaining bits of the range are coordinate (outer / per-instruction) bits.
+struct TmaDim {
+    uint8_t start_bit, range_bits, box_bits, pad;
+};
+
 struct PassDesc {
     int32_t n;                   // qubits held in this buffer (local qubits when sharded)
     int32_t t;                   // tile bits
@@ -93,7 +108,11 @@ struct PassDesc {
     int32_t n_segments;
     int32_t n_high;              // t - L
     uint8_t tile_bits[kMaxTileBits];   // global bit of tile-local bit i (ascending)
-    uint8_t pad[4];
+    uint32_t xor_local;          // tile-local index XOR applied by the pass's final store (deferred X gates)
+    uint64_t xor_tau;            // tile-number XOR: the tile read from tau is written to tau ^ xor_tau
+    uint8_t tma_instr_bits;      // the top tma_instr_bits tile bits are enumerated by separate TMA instructions
+    uint8_t pad[3];
+    TmaDim tma_dim[5];
     Segment seg[kMaxSegments];
     SweepDesc sweep[kMaxSweeps];
 };
@@ -113,6 +132,8 @@ struct CompileOptions {
     bool merge = true;           // merge runs of gates on the same (target, controls)
     bool reorder = true;         // commute ops across passes when legal (fewer passes)
     int n_global = 0;            // qubits >= n - n_global live in the rank id (sharded state)
+    bool defer_x = true;         // carry uncontrolled X gates as an index-XOR frame, folded into the last pass's addressing
+    uint64_t initial_xor = 0;    // X frame inherited from earlier segments (sharded driver: pending flips of global qubits)
 };
 
 struct Program {
@@ -122,8 +143,12 @@ struct Program {
     std::vector<DevOp> ops;      // encoded, pass-major
     std::vector<PassDesc> passes;
     int64_t n_gates = 0;
+    uint64_t global_xor = 0;     // X frame left on global qubits (bit q - n_local): a rank relabelling the caller owns
     std::string describe() const;
 };
+
+// Defaults, overridable for experiments by QSIM_TILE_BITS / QSIM_MIN_LOW_BITS / QSIM_NO_MERGE / QSIM_NO_REORDER.
+CompileOptions default_options();
 
 // Gate list -> matrices.  Returns false for an unknown gate type.
 bool lower_gate(const qsim_gate_t& g, std::vector<LogicalOp>& out, int gate_index);

@@ -26,7 +26,7 @@ void run_records(StateVector& sv, const std::vector<qsim_gate_t>& recs) {
     if (recs.empty()) return;
     b200::Program prog;
     std::string err;
-    if (!b200::compile(sv.getNumQubits(), recs.data(), (int64_t)recs.size(), b200::CompileOptions{}, prog, &err))
+    if (!b200::compile(sv.getNumQubits(), recs.data(), (int64_t)recs.size(), b200::default_options(), prog, &err))
         throw std::runtime_error(err);
     sv.engine().execute(prog, sv.devicePtr(), 0);
 }

@@ -132,5 +132,11 @@ class Simulator:
         _lib.check(_lib.lib().qsim_sim_pass_time_ms(self._h, byref(t), byref(n)))
         return t.value, n.value
 
+    def pass_times_ms(self):
+        out = np.zeros(4096)
+        n = c_int64()
+        _lib.check(_lib.lib().qsim_sim_pass_times(self._h, out.ctypes.data_as(c_void_p), len(out), byref(n)))
+        return out[:min(n.value, len(out))]
+
     getStateVector, getProbabilities, measureQubit = get_state_vector, get_probabilities, measure_qubit
     getNumQubits, getStateSize, applyGate = get_num_qubits, get_state_size, apply_gate

@@ -146,6 +146,8 @@ QSIM_API int64_t qsim_sim_launch_count(const qsim_sim_t* s);
  * simulator's stream), and how many passes were timed.  Enable with qsim_sim_set_timing. */
 QSIM_API qsim_status_t qsim_sim_set_timing(qsim_sim_t* s, int enabled);
 QSIM_API qsim_status_t qsim_sim_pass_time_ms(qsim_sim_t* s, double* total_ms, int64_t* n_passes);
+/* Same, one duration per timed pass in launch order (at most `cap` written; *n_out = how many there were). */
+QSIM_API qsim_status_t qsim_sim_pass_times(qsim_sim_t* s, double* out_ms, int64_t cap, int64_t* n_out);
 
 /* ---- Sharded state: one process per GPU, top n_global qubits = rank -------------- */
 /* The shard holds 2^(num_qubits - n_global) amplitudes; `rank` supplies the values of the global

@@ -5,6 +5,7 @@
 // GPU-less container.  The product never loads this library.
 #include <complex>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -16,12 +17,19 @@ using cplx = std::complex<double>;
 
 namespace {
 
+long g_tma_errors = 0;
+
 void run_pass(const Program& prog, const PassDesc& pd, uint64_t hi_bits, cplx* state) {
     const DevOp* ops = prog.ops.data() + pd.op_offset;
     const uint64_t n_tiles = 1ULL << (pd.n - pd.t);
     const uint32_t tile_amps = 1u << pd.t;
     std::vector<cplx> tile(tile_amps);
     std::vector<uint64_t> gidx(tile_amps);
+    // the kernel reads tile tau and writes tile tau ^ xor_tau (pairs are ordered so every tile is read before
+    // it is overwritten); emulate with a snapshot of the input
+    std::vector<cplx> snapshot;
+    const cplx* src_state = state;
+    if (pd.xor_tau) { snapshot.assign(state, state + (1ULL << pd.n)); src_state = snapshot.data(); }
     for (uint64_t tau = 0; tau < n_tiles; ++tau) {
         uint64_t base = 0;
         for (int s = 0; s < pd.n_segments; ++s)
@@ -32,7 +40,30 @@ void run_pass(const Program& prog, const PassDesc& pd, uint64_t hi_bits, cplx* s
             for (int i = 0; i < pd.t; ++i)
                 if ((l >> i) & 1) g |= 1ULL << pd.tile_bits[i];
             gidx[l] = g;
-            tile[l] = state[g];
+            tile[l] = src_state[g];
+        }
+        // cross-check the tensor-map geometry: the kernel's TMA boxes must land exactly these elements
+        {
+            const int ib = pd.tma_instr_bits, box_bits = pd.t - ib;
+            for (uint32_t q = 0; q < (1u << ib); ++q) {
+                uint64_t g = base;
+                for (int b = 0; b < ib; ++b)
+                    if ((q >> b) & 1) g |= 1ULL << pd.tile_bits[box_bits + b];
+                uint64_t coord[5];
+                for (int d = 0; d < 5; ++d)
+                    coord[d] = pd.tma_dim[d].range_bits ? (g >> pd.tma_dim[d].start_bit) & ((1ULL << pd.tma_dim[d].range_bits) - 1) : 0;
+                for (uint32_t e = 0; e < (1u << box_bits); ++e) {
+                    uint64_t addr = 0;
+                    uint32_t rem = e;
+                    for (int d = 0; d < 5; ++d) {
+                        const uint32_t in_box = rem & ((1u << pd.tma_dim[d].box_bits) - 1);
+                        rem >>= pd.tma_dim[d].box_bits;
+                        if (coord[d] & ((1ULL << pd.tma_dim[d].box_bits) - 1)) { g_tma_errors++; }
+                        addr += (coord[d] + in_box) << pd.tma_dim[d].start_bit;
+                    }
+                    if (rem != 0 || addr != gidx[(q << box_bits) + e]) g_tma_errors++;
+                }
+            }
         }
         for (int sw = 0; sw < pd.n_sweeps; ++sw) {
             const SweepDesc& sd = pd.sweep[sw];
@@ -91,7 +122,13 @@ void run_pass(const Program& prog, const PassDesc& pd, uint64_t hi_bits, cplx* s
                         for (int k = 0; k < slots; ++k) tile[base_local[lane] + sd.slot_off[k]] = reg[lane][k];
             }
         }
-        for (uint32_t l = 0; l < tile_amps; ++l) state[gidx[l]] = tile[l];
+        {
+            uint64_t sbase = 0;
+            const uint64_t stau = tau ^ pd.xor_tau;
+            for (int s = 0; s < pd.n_segments; ++s)
+                sbase |= ((stau >> pd.seg[s].src_shift) & pd.seg[s].mask) << pd.seg[s].dst_shift;
+            for (uint32_t l = 0; l < tile_amps; ++l) state[(gidx[l] - base) + sbase] = tile[l ^ pd.xor_local];
+        }
     }
 }
 
@@ -115,7 +152,12 @@ int emu_run(int n, int n_global, int rank, const qsim_gate_t* gates, int64_t ng,
         return -1;
     }
     const uint64_t hi = (uint64_t)rank << prog.n_local;
+    g_tma_errors = 0;
     for (const PassDesc& pd : prog.passes) run_pass(prog, pd, hi, reinterpret_cast<cplx*>(state));
+    if (g_tma_errors) {
+        if (err && errcap > 0) std::snprintf(err, errcap, "tensor-map geometry mismatch (%ld)", g_tma_errors);
+        return -2;
+    }
     if (info_out) {
         info_out[0] = (int64_t)prog.passes.size();
         info_out[1] = (int64_t)prog.lops.size();
