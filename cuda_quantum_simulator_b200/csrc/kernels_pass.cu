@@ -118,6 +118,18 @@ __device__ __forceinline__ void compute_barrier() {
     asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory");
 }
 
+__device__ __forceinline__ void lds128(uint32_t addr, double& x, double& y) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ double shfl_xor_f64(double v, int lane_mask) {
     return __shfl_xor_sync(0xffffffffu, v, lane_mask);
 }
@@ -246,26 +258,17 @@ __device__ __forceinline__ void diagonal(const DevOp& op, uint32_t sm, uint32_t 
     }
 }
 
-template <bool CTRL>
-__device__ __forceinline__ void apply_op(const DevOp& op, uint32_t sm, uint32_t tid, uint64_t gbase, double (&ar)[16],
-                                         double (&ai)[16]) {
-    if (op.kind == OP_DIAG) { diagonal<CTRL>(op, sm, tid, gbase, ar, ai); return; }
-    if (op.thome == T_LANE) {
-        switch (op.kind) {
-            case OP_FLIP: lane_target<OP_FLIP, CTRL>(op, sm, tid, ar, ai); break;
-            case OP_ADIAG: lane_target<OP_ADIAG, CTRL>(op, sm, tid, ar, ai); break;
-            case OP_MATREAL: lane_target<OP_MATREAL, CTRL>(op, sm, tid, ar, ai); break;
-            default: lane_target<OP_MAT, CTRL>(op, sm, tid, ar, ai); break;
-        }
-    } else {
-        switch (op.kind) {
-            case OP_FLIP: reg_target<OP_FLIP, CTRL>(op, sm, ar, ai); break;
-            case OP_ADIAG: reg_target<OP_ADIAG, CTRL>(op, sm, ar, ai); break;
-            case OP_MATREAL: reg_target<OP_MATREAL, CTRL>(op, sm, ar, ai); break;
-            default: reg_target<OP_MAT, CTRL>(op, sm, ar, ai); break;
-        }
-    }
-}
+#define QSIM_PAIR_CASES(KIND)                                                          \
+    case (KIND) * 10 + 0: lane_target<KIND, false>(op, 0xffffu, tid, ar, ai); break;   \
+    case (KIND) * 10 + 1: lane_target<KIND, true>(op, sm, tid, ar, ai); break;         \
+    case (KIND) * 10 + 2: reg_pairs<0, KIND, false>(op, 0xffffu, ar, ai); break;       \
+    case (KIND) * 10 + 3: reg_pairs<0, KIND, true>(op, sm, ar, ai); break;             \
+    case (KIND) * 10 + 4: reg_pairs<1, KIND, false>(op, 0xffffu, ar, ai); break;       \
+    case (KIND) * 10 + 5: reg_pairs<1, KIND, true>(op, sm, ar, ai); break;             \
+    case (KIND) * 10 + 6: reg_pairs<2, KIND, false>(op, 0xffffu, ar, ai); break;       \
+    case (KIND) * 10 + 7: reg_pairs<2, KIND, true>(op, sm, ar, ai); break;             \
+    case (KIND) * 10 + 8: reg_pairs<3, KIND, false>(op, 0xffffu, ar, ai); break;       \
+    case (KIND) * 10 + 9: reg_pairs<3, KIND, true>(op, sm, ar, ai); break;
 
 }  // namespace
 
@@ -401,40 +404,53 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
 #pragma unroll
                 for (int b = 0; b < 8; ++b)
                     if (b < sd.nthr && ((tid >> b) & 1)) base_local |= 1u << sd.thr_pos[b];
+                const uint32_t tile_u32 = smem_u32(tile);
+                const uint32_t my_addr = tile_u32 + base_local * 16u;
+                const bool full_sweep = (sd.r == 4) && (sd.nthr == 8);   // the only shape that matters for speed
+                if (full_sweep) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (active && k < slots) {
-                        const double2 v =
-                            *reinterpret_cast<const double2*>(tile + (size_t)(base_local + sd.slot_off[k]) * 16);
-                        ar[k] = v.x;
-                        ai[k] = v.y;
-                    } else {
+                    for (int k = 0; k < 16; ++k) lds128(my_addr + (uint32_t)sd.slot_off[k] * 16u, ar[k], ai[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
                         ar[k] = 0.0;
                         ai[k] = 0.0;
+                        if (active && k < slots) lds128(my_addr + (uint32_t)sd.slot_off[k] * 16u, ar[k], ai[k]);
                     }
                 }
+                const uint32_t ops_u32 = smem_u32(sops);
 #pragma unroll 1
                 for (int o = sd.op_begin; o < sd.op_end; ++o) {
                     const DevOp& op = sops[o];
-                    if (op.has_out && (gbase & op.cmask_out) != op.cval_out) continue;
-                    // warp-uniform: does any control live in this sweep's thread / register bits?
-                    const bool has_ctrl = (op.cmask_thr != 0u) || (op.slotmask != 0xffffu);
-                    if (!has_ctrl) {
-                        apply_op<false>(op, 0xffffu, tid, gbase, ar, ai);
-                    } else {
-                        const bool thr_ok = (tid & op.cmask_thr) == op.cval_thr;
-                        const uint32_t sm = thr_ok ? (uint32_t)op.slotmask : 0u;
-                        apply_op<true>(op, sm, tid, gbase, ar, ai);
+                    // first 16 bytes of the record: kind|thome|tbit|opcode, slotmask|tslots, cmask_thr, cval_thr
+                    const uint4 hdr = lds_u4(ops_u32 + (uint32_t)o * (uint32_t)sizeof(DevOp));
+                    const uint32_t opcode = hdr.x >> 24;
+                    if (opcode & 0x80u) {
+                        if ((gbase & op.cmask_out) != op.cval_out) continue;
+                    }
+                    const bool thr_ok = (tid & hdr.z) == hdr.w;
+                    const uint32_t sm = thr_ok ? (hdr.y & 0xffffu) : 0u;
+                    switch (opcode & 0x7fu) {
+                        QSIM_PAIR_CASES(OP_MAT)
+                        QSIM_PAIR_CASES(OP_MATREAL)
+                        QSIM_PAIR_CASES(OP_ADIAG)
+                        QSIM_PAIR_CASES(OP_FLIP)
+                        case 40: case 42: diagonal<false>(op, 0xffffu, tid, gbase, ar, ai); break;
+                        default: diagonal<true>(op, sm, tid, gbase, ar, ai); break;
                     }
                 }
                 // the pass's deferred X gates: the last sweep stores to the XOR-ed tile-local index (other
                 // threads' slots, hence the barrier: everybody has finished loading)
                 if (xl) compute_barrier();
+                if (full_sweep) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (active && k < slots)
-                        *reinterpret_cast<double2*>(tile + (size_t)((base_local + sd.slot_off[k]) ^ xl) * 16) =
-                            make_double2(ar[k], ai[k]);
+                    for (int k = 0; k < 16; ++k)
+                        sts128(tile_u32 + (((base_local + (uint32_t)sd.slot_off[k]) ^ xl) * 16u), ar[k], ai[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if (active && k < slots)
+                            sts128(tile_u32 + (((base_local + (uint32_t)sd.slot_off[k]) ^ xl) * 16u), ar[k], ai[k]);
                 }
             }
             // make the generic-proxy writes visible to the bulk-copy engine, then hand the stage over

@@ -441,7 +441,8 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
                     }
                 }
                 d.has_out = (d.cmask_out != 0 || d.tmask_out != 0) ? 1u : 0u;
-                d.opcode = op_code(d.kind, d.thome, d.tbit, d.cmask_thr != 0 || d.slotmask != 0xffffu);
+                d.opcode = (uint8_t)(op_code(d.kind, d.thome, d.tbit, d.cmask_thr != 0 || d.slotmask != 0xffffu) |
+                                     (d.has_out ? 0x80u : 0u));   // bit 7: depends on index bits outside the tile
                 out.ops.push_back(d);
                 pd.n_ops++;
             }
