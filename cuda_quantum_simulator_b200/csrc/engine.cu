@@ -50,11 +50,22 @@ Engine::Engine() {
 }
 
 Engine::~Engine() {
+    for (void* p : scratch_) if (p) cudaFree(p);
     if (d_ops_) cudaFree(d_ops_);
     if (h_ops_) cudaFreeHost(h_ops_);
     if (staged_) cudaEventDestroy(staged_);
     for (auto& e : events_) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto& e : pool_) cudaEventDestroy(e);
+}
+
+void* Engine::scratch(int slot, size_t bytes) {
+    if (bytes > scratch_cap_[slot]) {
+        if (scratch_[slot]) { CUDA_CHECK(cudaStreamSynchronize(stream_)); cudaFree(scratch_[slot]); scratch_[slot] = nullptr; }
+        const size_t cap = bytes + bytes / 4 + 4096;
+        CUDA_CHECK(cudaMalloc(&scratch_[slot], cap));
+        scratch_cap_[slot] = cap;
+    }
+    return scratch_[slot];
 }
 
 void Engine::synchronize() const { CUDA_CHECK(cudaStreamSynchronize(stream_)); }

@@ -46,6 +46,10 @@ public:
     int64_t launches() const { return launches_; }
     void countLaunch(int64_t k = 1) { launches_ += k; }
 
+    // Persistent device scratch (grow-only, two independent slots) for read-out temporaries, so the hot
+    // read-out calls never cudaMalloc/cudaFree.
+    void* scratch(int slot, size_t bytes);
+
     void setTiming(bool on);
     // Sum of pass-kernel device times since the last call, and the number of passes timed.
     void drainTiming(double* total_ms, int64_t* n_passes, std::vector<double>* each = nullptr);
@@ -54,6 +58,8 @@ private:
     cudaStream_t stream_ = nullptr;
     int num_sms_ = 0;
     int64_t launches_ = 0;
+    void* scratch_[2] = {nullptr, nullptr};
+    size_t scratch_cap_[2] = {0, 0};
     bool use_tensor_map_ = true;
     int stages_wanted_ = 0;   // 0 = as deep as shared memory allows
     // staging for execute(const Program&)

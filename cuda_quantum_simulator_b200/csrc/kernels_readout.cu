@@ -210,6 +210,36 @@ __global__ void chunk_walk_kernel(const cuDoubleComplex* __restrict__ state, int
         const double b = kk < m ? bin_base[kk] : 0.0;
         const int f = kk < m ? (int)flag[kk] : (int)CH_ZERO;
         const int lim = (m - k0) < 32 ? (int)(m - k0) : 32;
+        // Fast path for a whole group of 32 chunks that stay in one binade: their increments are multiples of
+        // the same ulp and add exactly in any order, so a warp scan replaces 32 dependent additions.
+        {
+            const unsigned fast_mask = __ballot_sync(0xffffffffu, kk < m && f == (int)CH_FAST);
+            const unsigned slow_mask = __ballot_sync(0xffffffffu, kk < m && f == (int)CH_SLOW);
+            if (slow_mask == 0u) {
+                if (fast_mask == 0u) {   // nothing but zeros: the running sum does not move
+                    if (kk < m) start[kk] = c;
+                    continue;
+                }
+                const double bb = __shfl_sync(0xffffffffu, b, __ffs(fast_mask) - 1);
+                const bool is_fast = (fast_mask >> lane) & 1u;
+                if (__all_sync(0xffffffffu, !is_fast || b == bb)) {
+                    const double dd = is_fast ? d : 0.0;
+                    double incl = dd;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl = __dadd_rn(incl, up);
+                    }
+                    const double total = __shfl_sync(0xffffffffu, incl, 31);
+                    const double c_end = __dadd_rn(c, total);
+                    if (c >= bb && c_end < 2.0 * bb) {
+                        if (kk < m) start[kk] = __dadd_rn(c, __dsub_rn(incl, dd));
+                        c = c_end;
+                        continue;
+                    }
+                }
+            }
+        }
         for (int j = 0; j < lim; ++j) {
             const double dj = __shfl_sync(0xffffffffu, d, j), bj = __shfl_sync(0xffffffffu, b, j);
             const int fj = __shfl_sync(0xffffffffu, f, j);
@@ -279,15 +309,16 @@ void launch_init_basis(cuDoubleComplex* state, uint64_t n, uint64_t idx, cudaStr
     CUDA_CHECK_LAST_ERROR();
 }
 
-double reduce_probability(const cuDoubleComplex* state, uint64_t n, int mask_bit, int num_sms, cudaStream_t stream) {
-    const int grid = grid_for(n, num_sms);
-    CudaMemory<double> partial((size_t)grid + 1);
-    partial_prob_kernel<<<grid, kBlock, 0, stream>>>(state, n, mask_bit, partial.get());
+double reduce_probability(const cuDoubleComplex* state, uint64_t n, int mask_bit, Engine& eng) {
+    cudaStream_t stream = eng.stream();
+    const int grid = grid_for(n, eng.numSMs());
+    double* partial = static_cast<double*>(eng.scratch(0, ((size_t)grid + 1) * sizeof(double)));
+    partial_prob_kernel<<<grid, kBlock, 0, stream>>>(state, n, mask_bit, partial);
     CUDA_CHECK_LAST_ERROR();
-    final_sum_kernel<<<1, kBlock, 0, stream>>>(partial.get(), grid, partial.get() + grid);
+    final_sum_kernel<<<1, kBlock, 0, stream>>>(partial, grid, partial + grid);
     CUDA_CHECK_LAST_ERROR();
     double out = 0.0;
-    CUDA_CHECK(cudaMemcpyAsync(&out, partial.get() + grid, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaMemcpyAsync(&out, partial + grid, sizeof(double), cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
     return out;
 }
@@ -298,60 +329,58 @@ void launch_collapse(cuDoubleComplex* state, uint64_t n, int bit, int outcome, d
     CUDA_CHECK_LAST_ERROR();
 }
 
-SequentialCdf::SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, cudaStream_t stream)
-    : state_(state), n_(n), mask_bit_(mask_bit), stream_(stream) {
+SequentialCdf::SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, Engine& eng)
+    : state_(state), n_(n), mask_bit_(mask_bit), stream_(eng.stream()), eng_(eng) {
     chunk_ = n >= 4096 ? 4096 : (int)n;
     m_ = n / (uint64_t)chunk_;
-    approx_ = CudaMemory<double>(m_);
-    lo_ = CudaMemory<double>(m_);
-    delta_ = CudaMemory<double>(m_);
-    base_ = CudaMemory<double>(m_);
-    flag_ = CudaMemory<uint8_t>(m_);
-    start_ = CudaMemory<double>(m_ + 1);
-    slow_ = CudaMemory<unsigned long long>(1);
-    chunk_approx_kernel<<<(unsigned)m_, kBlock, 0, stream>>>(state, mask_bit, chunk_, approx_.get());
+    const size_t m8 = (m_ + 2) * sizeof(double);
+    unsigned char* arena = static_cast<unsigned char*>(eng.scratch(0, 5 * m8 + 16 + m_ + 64));
+    approx_ = reinterpret_cast<double*>(arena);
+    lo_ = reinterpret_cast<double*>(arena + m8);
+    delta_ = reinterpret_cast<double*>(arena + 2 * m8);
+    base_ = reinterpret_cast<double*>(arena + 3 * m8);
+    start_ = reinterpret_cast<double*>(arena + 4 * m8);
+    slow_ = reinterpret_cast<unsigned long long*>(arena + 5 * m8);
+    flag_ = arena + 5 * m8 + 16;
+    cudaStream_t stream = stream_;
+    chunk_approx_kernel<<<(unsigned)m_, kBlock, 0, stream>>>(state, mask_bit, chunk_, approx_);
     CUDA_CHECK_LAST_ERROR();
-    chunk_scan_kernel<<<1, 1024, 0, stream>>>(approx_.get(), m_, lo_.get());
+    chunk_scan_kernel<<<1, 1024, 0, stream>>>(approx_, m_, lo_);
     CUDA_CHECK_LAST_ERROR();
-    chunk_surrogate_kernel<<<(unsigned)m_, kBlock, 0, stream>>>(state, mask_bit, chunk_, approx_.get(), lo_.get(),
-                                                                delta_.get(), base_.get(), flag_.get());
+    chunk_surrogate_kernel<<<(unsigned)m_, kBlock, 0, stream>>>(state, mask_bit, chunk_, approx_, lo_, delta_, base_, flag_);
     CUDA_CHECK_LAST_ERROR();
-    chunk_walk_kernel<<<1, 32, 0, stream>>>(state, mask_bit, chunk_, m_, delta_.get(), base_.get(), flag_.get(),
-                                            start_.get(), slow_.get());
+    chunk_walk_kernel<<<1, 32, 0, stream>>>(state, mask_bit, chunk_, m_, delta_, base_, flag_, start_, slow_);
     CUDA_CHECK_LAST_ERROR();
     launches_ = 4;
 }
 
 double SequentialCdf::total() const {
     double t = 0.0;
-    CUDA_CHECK(cudaMemcpyAsync(&t, start_.get() + m_, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(&t, start_ + m_, sizeof(double), cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     return t;
 }
 
 uint64_t SequentialCdf::slowChunks() const {
     unsigned long long s = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&s, slow_.get(), sizeof(s), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(&s, slow_, sizeof(s), cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     return s;
 }
 
-void SequentialCdf::sample(const double* uniforms_host, int64_t n_shots, int64_t* out_host, int num_sms) {
+void SequentialCdf::sample(const double* uniforms_host, int64_t n_shots, int64_t* out_host) {
     if (n_shots <= 0) return;
-    CudaMemory<double> d_u((size_t)n_shots);
-    CudaMemory<int64_t> d_out((size_t)n_shots);
-    CUDA_CHECK(cudaMemcpyAsync(d_u.get(), uniforms_host, (size_t)n_shots * sizeof(double), cudaMemcpyHostToDevice,
-                               stream_));
-    const int64_t warps_needed = n_shots;
-    int64_t blocks = (warps_needed * 32 + kBlock - 1) / kBlock;
-    const int64_t cap = (int64_t)num_sms * 8;
+    unsigned char* arena = static_cast<unsigned char*>(eng_.scratch(1, (size_t)n_shots * 16));
+    double* d_u = reinterpret_cast<double*>(arena);
+    int64_t* d_out = reinterpret_cast<int64_t*>(arena + (size_t)n_shots * 8);
+    CUDA_CHECK(cudaMemcpyAsync(d_u, uniforms_host, (size_t)n_shots * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    int64_t blocks = (n_shots * 32 + kBlock - 1) / kBlock;
+    const int64_t cap = (int64_t)eng_.numSMs() * 8;
     if (blocks > cap) blocks = cap;
-    sample_kernel<<<(unsigned)blocks, kBlock, 0, stream_>>>(state_, mask_bit_, chunk_, m_, start_.get(), d_u.get(),
-                                                            n_shots, d_out.get());
+    sample_kernel<<<(unsigned)blocks, kBlock, 0, stream_>>>(state_, mask_bit_, chunk_, m_, start_, d_u, n_shots, d_out);
     CUDA_CHECK_LAST_ERROR();
     ++launches_;
-    CUDA_CHECK(cudaMemcpyAsync(out_host, d_out.get(), (size_t)n_shots * sizeof(int64_t), cudaMemcpyDeviceToHost,
-                               stream_));
+    CUDA_CHECK(cudaMemcpyAsync(out_host, d_out, (size_t)n_shots * sizeof(int64_t), cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
 

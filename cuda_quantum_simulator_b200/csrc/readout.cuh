@@ -6,6 +6,7 @@
 
 #include <cstdint>
 
+#include "engine.hpp"
 #include "qsim/cuda_memory.cuh"
 
 namespace qsim {
@@ -15,7 +16,7 @@ void launch_probabilities(const cuDoubleComplex* state, double* out, uint64_t fi
                           cudaStream_t stream);
 void launch_init_basis(cuDoubleComplex* state, uint64_t n, uint64_t idx, cudaStream_t stream);
 // sum of |a_i|^2 over indices whose bit `mask_bit` is 0 (mask_bit < 0: all); deterministic tree order
-double reduce_probability(const cuDoubleComplex* state, uint64_t n, int mask_bit, int num_sms, cudaStream_t stream);
+double reduce_probability(const cuDoubleComplex* state, uint64_t n, int mask_bit, Engine& eng);
 void launch_collapse(cuDoubleComplex* state, uint64_t n, int bit, int outcome, double scale, int num_sms,
                      cudaStream_t stream);
 
@@ -23,11 +24,11 @@ void launch_collapse(cuDoubleComplex* state, uint64_t n, int bit, int outcome, d
 // running sum at every 4096-element chunk boundary.
 class SequentialCdf {
 public:
-    SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, cudaStream_t stream);
+    SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, Engine& eng);
     double total() const;           // == the reference's index-order host sum, bit for bit
     uint64_t slowChunks() const;    // chunks that had to be replayed sequentially (diagnostics)
     // out[i] = smallest index whose CDF value >= uniforms[i] (n if none), host in / host out
-    void sample(const double* uniforms_host, int64_t n_shots, int64_t* out_host, int num_sms);
+    void sample(const double* uniforms_host, int64_t n_shots, int64_t* out_host);
     int launches() const { return launches_; }
 
 private:
@@ -37,9 +38,11 @@ private:
     cudaStream_t stream_;
     int chunk_ = 0;
     uint64_t m_ = 0;
-    CudaMemory<double> approx_, lo_, delta_, base_, start_;
-    CudaMemory<uint8_t> flag_;
-    CudaMemory<unsigned long long> slow_;
+    Engine& eng_;
+    // slices of the engine's scratch slot 0
+    double *approx_ = nullptr, *lo_ = nullptr, *delta_ = nullptr, *base_ = nullptr, *start_ = nullptr;
+    unsigned long long* slow_ = nullptr;
+    uint8_t* flag_ = nullptr;
     int launches_ = 0;
 };
 

@@ -111,12 +111,12 @@ void StateVector::getProbabilities(double* out, uint64_t first, uint64_t count) 
     if (first > size_ || count > size_ - first) throw std::invalid_argument("Probability range out of bounds");
     // stream the range through a bounded device buffer: never a second 2^n allocation
     const uint64_t cap = std::min<uint64_t>(count, uint64_t(1) << 24);
-    CudaMemory<double> buf(cap);
+    double* buf = static_cast<double*>(engine_->scratch(1, cap * sizeof(double)));
     for (uint64_t done = 0; done < count; done += cap) {
         const uint64_t n = std::min<uint64_t>(cap, count - done);
-        b200::launch_probabilities(d_state_, buf.get(), first + done, n, engine_->numSMs(), engine_->stream());
+        b200::launch_probabilities(d_state_, buf, first + done, n, engine_->numSMs(), engine_->stream());
         engine_->countLaunch();
-        CUDA_CHECK(cudaMemcpyAsync(out + done, buf.get(), n * sizeof(double), cudaMemcpyDeviceToHost, engine_->stream()));
+        CUDA_CHECK(cudaMemcpyAsync(out + done, buf, n * sizeof(double), cudaMemcpyDeviceToHost, engine_->stream()));
         engine_->synchronize();
     }
 }
@@ -130,7 +130,7 @@ std::vector<double> StateVector::getProbabilities() const {
 // Same value as the reference's index-order host loop (src/StateVector.cu:235-242), computed on
 // the device by SequentialCdf.
 double StateVector::getTotalProbability() const {
-    b200::SequentialCdf cdf(d_state_, size_, -1, engine_->stream());
+    b200::SequentialCdf cdf(d_state_, size_, -1, *engine_);
     engine_->countLaunch(cdf.launches());
     return cdf.total();
 }
@@ -146,7 +146,7 @@ void StateVector::assertNormalized(double tolerance) const {
 
 double StateVector::partialProbability(int bit) const {
     engine_->countLaunch(2);
-    return b200::reduce_probability(d_state_, size_, bit, engine_->numSMs(), engine_->stream());
+    return b200::reduce_probability(d_state_, size_, bit, *engine_);
 }
 
 void StateVector::collapse(int bit, int outcome, double scale) {
@@ -159,7 +159,7 @@ int StateVector::measureBit(int bit, double r, double* p0_out) {
         throw std::invalid_argument("Qubit index " + std::to_string(bit) + " out of range [0, " +
                                     std::to_string(num_qubits_ - 1) + "]");
     // p0 = index-order sum of the masked probabilities, exactly as the reference's host loop
-    b200::SequentialCdf cdf(d_state_, size_, bit, engine_->stream());
+    b200::SequentialCdf cdf(d_state_, size_, bit, *engine_);
     engine_->countLaunch(cdf.launches());
     const double p0 = cdf.total();
     if (p0_out) *p0_out = p0;
@@ -191,9 +191,9 @@ int StateVector::measure(int qubit) {
 
 std::vector<int64_t> StateVector::sampleWithUniforms(const double* uniforms, int64_t n_shots) {
     if (n_shots <= 0) throw std::invalid_argument("n_shots must be positive");
-    b200::SequentialCdf cdf(d_state_, size_, -1, engine_->stream());
+    b200::SequentialCdf cdf(d_state_, size_, -1, *engine_);
     std::vector<int64_t> out((size_t)n_shots);
-    cdf.sample(uniforms, n_shots, out.data(), engine_->numSMs());
+    cdf.sample(uniforms, n_shots, out.data());
     engine_->countLaunch(cdf.launches());
     return out;
 }
