@@ -69,6 +69,7 @@ def _declare(L: ctypes.CDLL) -> None:
         "qsim_circuit_ghz": (c_int, [c_int, P]),
         "qsim_circuit_depth": (c_int, [c_int, P, c_int64, POINTER(c_int64)]),
         "qsim_program_compile": (c_int, [c_int, c_int, P, c_int64, PP]),
+        "qsim_program_compile_ex": (c_int, [c_int, c_int, P, c_int64, c_uint64, PP]),
         "qsim_program_destroy": (None, [P]),
         "qsim_program_info": (c_int, [P, POINTER(c_int64)]),
         "qsim_program_describe": (c_size_t, [P, c_char_p, c_size_t]),
@@ -106,6 +107,7 @@ def _declare(L: ctypes.CDLL) -> None:
         "qsim_ipc_close_handle": (c_int, [P]),
         "qsim_shard_partial_probability": (c_int, [P, c_int, POINTER(c_double)]),
         "qsim_shard_collapse": (c_int, [P, c_int, c_int, c_double]),
+        "qsim_shard_sample": (c_int, [P, c_double, c_int, P, c_int64, P, POINTER(c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)   # AttributeError here == the library does not export what the header declares

@@ -131,6 +131,11 @@ qsim_status_t qsim_circuit_depth(int n, const qsim_gate_t* gates, int64_t ng, in
 // ---- programs ---------------------------------------------------------------------------------
 
 qsim_status_t qsim_program_compile(int n, int n_global, const qsim_gate_t* gates, int64_t ng, qsim_program_t** out) {
+    return qsim_program_compile_ex(n, n_global, gates, ng, 0, out);
+}
+
+qsim_status_t qsim_program_compile_ex(int n, int n_global, const qsim_gate_t* gates, int64_t ng, uint64_t initial_xor,
+                                      qsim_program_t** out) {
     return guarded([&] {
         require(out != nullptr, "null output");
         require(n_global >= 0 && n_global < n, "n_global out of range");
@@ -139,6 +144,7 @@ qsim_status_t qsim_program_compile(int n, int n_global, const qsim_gate_t* gates
         p->n_global = n_global;
         b200::CompileOptions opt = b200::default_options();
         opt.n_global = n_global;
+        opt.initial_xor = initial_xor;
         std::string err;
         if (!b200::compile(n, gates, ng, opt, p->dev.host, &err)) throw std::runtime_error(err);
         p->dev.upload();
@@ -160,7 +166,8 @@ qsim_status_t qsim_program_info(const qsim_program_t* p, int64_t info[8]) {
         info[3] = sweeps;
         info[4] = h.passes.empty() ? 0 : h.passes[0].t;
         info[5] = h.n_local;
-        info[6] = info[7] = 0;
+        info[6] = (int64_t)h.global_xor;
+        info[7] = 0;
     });
 }
 
@@ -484,6 +491,14 @@ qsim_status_t qsim_shard_collapse(qsim_sim_t* s, int bit, int outcome, double sc
     return guarded([&] {
         require(s != nullptr, "null simulator");
         s->sim->state().collapse(bit, outcome, scale);
+    });
+}
+
+qsim_status_t qsim_shard_sample(qsim_sim_t* s, double c_init, int first_shard, const double* uniforms, int64_t n_shots,
+                                int64_t* out, double* c_end) {
+    return guarded([&] {
+        require(s != nullptr && uniforms != nullptr && out != nullptr && c_end != nullptr, "null argument");
+        *c_end = s->sim->state().sampleShard(c_init, first_shard != 0, uniforms, n_shots, out);
     });
 }
 

@@ -113,7 +113,7 @@ __global__ void chunk_approx_kernel(const cuDoubleComplex* __restrict__ state, i
 }
 
 // K2: single-block exclusive scan of the approximate chunk sums: lo[k] = approx start of chunk k.
-__global__ void chunk_scan_kernel(const double* __restrict__ approx, uint64_t m, double* __restrict__ lo) {
+__global__ void chunk_scan_kernel(const double* __restrict__ approx, uint64_t m, double* __restrict__ lo, double c_init) {
     __shared__ double part[1024];
     const uint64_t per = (m + blockDim.x - 1) / blockDim.x;
     const uint64_t b = (uint64_t)threadIdx.x * per, e = (b + per < m) ? b + per : m;
@@ -122,7 +122,7 @@ __global__ void chunk_scan_kernel(const double* __restrict__ approx, uint64_t m,
     part[threadIdx.x] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double run = 0.0;
+        double run = c_init;
         for (int i = 0; i < (int)blockDim.x; ++i) { double v = part[i]; part[i] = run; run += v; }
     }
     __syncthreads();
@@ -200,9 +200,9 @@ __device__ __forceinline__ double replay_chunk(const cuDoubleComplex* __restrict
 __global__ void chunk_walk_kernel(const cuDoubleComplex* __restrict__ state, int mask_bit, int chunk, uint64_t m,
                                   const double* __restrict__ delta, const double* __restrict__ bin_base,
                                   const uint8_t* __restrict__ flag, double* __restrict__ start,
-                                  unsigned long long* __restrict__ n_slow) {
+                                  unsigned long long* __restrict__ n_slow, double c_init) {
     const int lane = threadIdx.x & 31;
-    double c = 0.0;
+    double c = c_init;
     unsigned long long slow = 0;
     for (uint64_t k0 = 0; k0 < m; k0 += 32) {
         const uint64_t kk = k0 + lane;
@@ -329,7 +329,7 @@ void launch_collapse(cuDoubleComplex* state, uint64_t n, int bit, int outcome, d
     CUDA_CHECK_LAST_ERROR();
 }
 
-SequentialCdf::SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, Engine& eng)
+SequentialCdf::SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, Engine& eng, double c_init)
     : state_(state), n_(n), mask_bit_(mask_bit), stream_(eng.stream()), eng_(eng) {
     chunk_ = n >= 4096 ? 4096 : (int)n;
     m_ = n / (uint64_t)chunk_;
@@ -345,11 +345,11 @@ SequentialCdf::SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_
     cudaStream_t stream = stream_;
     chunk_approx_kernel<<<(unsigned)m_, kBlock, 0, stream>>>(state, mask_bit, chunk_, approx_);
     CUDA_CHECK_LAST_ERROR();
-    chunk_scan_kernel<<<1, 1024, 0, stream>>>(approx_, m_, lo_);
+    chunk_scan_kernel<<<1, 1024, 0, stream>>>(approx_, m_, lo_, c_init);
     CUDA_CHECK_LAST_ERROR();
     chunk_surrogate_kernel<<<(unsigned)m_, kBlock, 0, stream>>>(state, mask_bit, chunk_, approx_, lo_, delta_, base_, flag_);
     CUDA_CHECK_LAST_ERROR();
-    chunk_walk_kernel<<<1, 32, 0, stream>>>(state, mask_bit, chunk_, m_, delta_, base_, flag_, start_, slow_);
+    chunk_walk_kernel<<<1, 32, 0, stream>>>(state, mask_bit, chunk_, m_, delta_, base_, flag_, start_, slow_, c_init);
     CUDA_CHECK_LAST_ERROR();
     launches_ = 4;
 }

@@ -24,7 +24,9 @@ void launch_collapse(cuDoubleComplex* state, uint64_t n, int bit, int outcome, d
 // running sum at every 4096-element chunk boundary.
 class SequentialCdf {
 public:
-    SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, Engine& eng);
+    // c_init: value the running sum starts from (0 for a whole state; the exact sum of the preceding shards
+    // for one shard of a distributed state)
+    SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, Engine& eng, double c_init = 0.0);
     double total() const;           // == the reference's index-order host sum, bit for bit
     uint64_t slowChunks() const;    // chunks that had to be replayed sequentially (diagnostics)
     // out[i] = smallest index whose CDF value >= uniforms[i] (n if none), host in / host out

@@ -198,6 +198,21 @@ std::vector<int64_t> StateVector::sampleWithUniforms(const double* uniforms, int
     return out;
 }
 
+double StateVector::sampleShard(double c_init, bool first_shard, const double* uniforms, int64_t n_shots, int64_t* out) {
+    b200::SequentialCdf cdf(d_state_, size_, -1, *engine_, c_init);
+    const double c_end = cdf.total();
+    if (n_shots > 0) {
+        cdf.sample(uniforms, n_shots, out);
+        for (int64_t i = 0; i < n_shots; ++i) {
+            const double r = uniforms[i];
+            const bool mine = (c_end >= r) && (c_init < r || first_shard);
+            if (!mine) out[i] = -1;
+        }
+    }
+    engine_->countLaunch(cdf.launches());
+    return c_end;
+}
+
 std::vector<int64_t> StateVector::sampleSeeded(unsigned seed, int64_t n_shots) {
     if (n_shots <= 0) throw std::invalid_argument("n_shots must be positive");
     std::mt19937 rng(seed);

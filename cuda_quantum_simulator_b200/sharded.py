@@ -1,0 +1,443 @@
+"""Multi-GPU state vector: one process per GPU, the top log2(P) qubits are the rank id.
+
+The reference is single-GPU only (its README lists multi-GPU as future work), so this module has no
+reference counterpart; its contract is "same amplitudes as the single-device run".
+
+  * gates whose non-diagonal target is a local qubit run in the fused-pass engine on every shard;
+    controls and diagonal gates on global qubits need no data movement (the rank supplies the bit);
+  * an uncontrolled X on a global qubit is a rank relabelling, carried as an X frame;
+  * any other non-diagonal gate on a global qubit g first swaps g with a local qubit l: rank r and
+    r ^ (1 << (g - n_local)) exchange the half of their shards whose bit l differs from their own
+    value of g (16 * 2^(n_local - 1) bytes each way: the NVLink roofline of the step).  The swap is
+    never undone: the logical -> physical qubit permutation is carried and resolved at read-out.
+
+`plan_circuit` (pure host logic) decides where the swaps go; an *engine* executes the steps.  The
+product engine is `CudaShardEngine` (C ABI + CUDA IPC peer memory, or NCCL send/recv through
+torch.distributed).  Tests inject their own engine to exercise the planning / exchange choreography
+on CPU with the gloo backend; the product never falls back to anything but CUDA.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_double, c_int64, c_uint64, c_void_p
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import GATE_DTYPE
+from .circuit import Circuit
+
+_DIAGONAL = {2, 4, 5, 6, 7, 10, 12, 14}      # Z S T Sdag Tdag Rz CZ CRZ
+_X = 0
+
+
+def _target_positions(g) -> Tuple[int, ...]:
+    """Qubit slots (q0/q1/q2) of a gate record that are non-diagonal targets."""
+    t = int(g["type"])
+    if t in _DIAGONAL:
+        return ()
+    if t <= 10:
+        return (0,)
+    if t == 15:                # SWAP: both are targets
+        return (0, 1)
+    if t == 16:
+        return (2,)
+    return (1,)                # CNOT, CRY
+
+
+@dataclass
+class Step:
+    kind: str                              # "gates" | "swap"
+    gates: Optional[np.ndarray] = None     # physical-qubit gate records
+    global_qubit: int = -1
+    local_qubit: int = -1
+
+
+@dataclass
+class Plan:
+    num_qubits: int
+    n_global: int
+    steps: List[Step] = field(default_factory=list)
+    perm: List[int] = field(default_factory=list)      # logical qubit -> physical position after the plan
+    n_gates: int = 0
+
+    @property
+    def n_swaps(self) -> int:
+        return sum(1 for s in self.steps if s.kind == "swap")
+
+
+def plan_circuit(num_qubits: int, n_global: int, gates: np.ndarray, perm: Optional[Sequence[int]] = None) -> Plan:
+    """Split a circuit into local segments separated by global<->local qubit swaps.
+
+    `perm[q]` is the physical bit position currently holding logical qubit q.  The swap partner is the
+    local position whose next use as a non-diagonal target lies farthest in the future (Belady), with a
+    preference for high positions (long contiguous runs in the exchange).
+    """
+    n, nl = num_qubits, num_qubits - n_global
+    perm = list(range(n)) if perm is None else list(perm)
+    plan = Plan(n, n_global, n_gates=len(gates))
+    cur: List[tuple] = []
+
+    def flush():
+        if cur:
+            plan.steps.append(Step("gates", gates=np.array(cur, dtype=GATE_DTYPE)))
+            cur.clear()
+
+    qcols = ("q0", "q1", "q2")
+    for idx, g in enumerate(gates):
+        t = int(g["type"])
+        if t != _X:   # an uncontrolled X on a global qubit is a frame toggle, handled by the compiler
+            for slot in _target_positions(g):
+                lq = int(g[qcols[slot]])
+                if perm[lq] >= nl:
+                    flush()
+                    # choose the local position to evict
+                    next_use = {p: 1 << 60 for p in range(nl)}
+                    inv = {perm[q]: q for q in range(n)}
+                    busy = {perm[int(g[c])] for c in qcols if int(g[c]) >= 0}
+                    for j in range(idx, len(gates)):
+                        h = gates[j]
+                        for s2 in _target_positions(h):
+                            p = perm[int(h[qcols[s2]])]
+                            if p < nl and next_use[p] == 1 << 60:
+                                next_use[p] = j
+                    cand = [p for p in range(nl) if p not in busy]
+                    victim = max(cand, key=lambda p: (next_use[p], p))
+                    gpos = perm[lq]
+                    plan.steps.append(Step("swap", global_qubit=gpos, local_qubit=victim))
+                    other = inv[victim]
+                    perm[lq], perm[other] = victim, gpos
+        rec = (t, perm[int(g["q0"])] if int(g["q0"]) >= 0 else -1, perm[int(g["q1"])] if int(g["q1"]) >= 0 else -1,
+               perm[int(g["q2"])] if int(g["q2"]) >= 0 else -1, float(g["param"]))
+        cur.append(rec)
+    flush()
+    plan.perm = perm
+    return plan
+
+
+# ---------------------------------------------------------------------------------------------------
+
+
+class CudaShardEngine:
+    """Executes plan steps on this rank's GPU shard through the C ABI."""
+
+    def __init__(self, num_qubits: int, n_global: int, rank: int, world: int, exchange: str = "auto"):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.n, self.ng, self.nl = num_qubits, n_global, num_qubits - n_global
+        self.rank, self.world = rank, world
+        self.state = torch.empty(1 << self.nl, dtype=torch.complex128, device="cuda")
+        self._h = c_void_p()
+        _lib.check(_lib.lib().qsim_shard_create(self.n, self.ng, rank, c_void_p(self.state.data_ptr()), byref(self._h)))
+        self.stream = torch.cuda.current_stream()
+        _lib.check(_lib.lib().qsim_sim_set_stream(self._h, c_void_p(self.stream.cuda_stream)))
+        self._flag = torch.zeros(1, device="cuda")
+        self._peer_ptr = {}
+        self._peer_base = []
+        self.exchange = exchange
+        self._bounce = None
+        if world > 1 and exchange in ("auto", "p2p"):
+            try:
+                self._open_peers()
+                self.exchange = "p2p"
+            except Exception:
+                if exchange == "p2p":
+                    raise
+                self.exchange = "nccl"
+        elif world > 1:
+            self.exchange = "nccl"
+
+    # -- peer memory ----------------------------------------------------------------------------
+    def _open_peers(self):
+        handle = (ctypes.c_ubyte * 64)()
+        off = c_uint64()
+        _lib.check(_lib.lib().qsim_ipc_get_handle(c_void_p(self.state.data_ptr()), handle, byref(off)))
+        mine = (bytes(handle), int(off.value))
+        everyone = [None] * self.world
+        self.dist.all_gather_object(everyone, mine)
+        for b in range(self.ng):
+            peer = self.rank ^ (1 << b)
+            hbytes, poff = everyone[peer]
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(hbytes)
+            base = c_void_p()
+            _lib.check(_lib.lib().qsim_ipc_open_handle(buf, byref(base)))
+            self._peer_base.append(base)
+            self._peer_ptr[peer] = base.value + poff
+
+    def device_barrier(self):
+        """Stream-ordered barrier across ranks: nobody's later kernels start before everybody's earlier ones ended."""
+        if self.world > 1:
+            self.dist.all_reduce(self._flag)
+
+    # -- steps ----------------------------------------------------------------------------------
+    def compile_gates(self, gates: np.ndarray, initial_xor: int):
+        h = c_void_p()
+        g = np.ascontiguousarray(gates, dtype=GATE_DTYPE)
+        _lib.check(_lib.lib().qsim_program_compile_ex(self.n, self.ng, _lib.gates_ptr(g) if len(g) else None, len(g),
+                                                      c_uint64(initial_xor), byref(h)))
+        info = (c_int64 * 8)()
+        _lib.check(_lib.lib().qsim_program_info(h, info))
+        return h, {"passes": info[0], "ops": info[1], "global_xor": int(info[6])}
+
+    def run_program(self, handle):
+        _lib.check(_lib.lib().qsim_sim_execute(self._h, handle))
+
+    def free_program(self, handle):
+        _lib.lib().qsim_program_destroy(handle)
+
+    def swap(self, global_qubit: int, local_qubit: int):
+        peer = self.rank ^ (1 << (global_qubit - self.nl))
+        self.device_barrier()
+        if self.exchange == "p2p":
+            _lib.check(_lib.lib().qsim_shard_swap_p2p(self._h, c_void_p(self._peer_ptr[peer]), global_qubit, local_qubit))
+        else:
+            self._swap_nccl(peer, global_qubit, local_qubit)
+        self.device_barrier()
+
+    def _swap_nccl(self, peer: int, global_qubit: int, local_qubit: int):
+        torch, dist = self.torch, self.dist
+        my_bit = (self.rank >> (global_qubit - self.nl)) & 1
+        pairs = 1 << (self.nl - 1)
+        chunk_amps = min(pairs, 1 << 24)                      # 256 MiB bounce buffers
+        n_chunks = pairs // chunk_amps
+        if self._bounce is None or self._bounce[0].numel() < chunk_amps:
+            self._bounce = (torch.empty(chunk_amps, dtype=torch.complex128, device="cuda"),
+                            torch.empty(chunk_amps, dtype=torch.complex128, device="cuda"))
+        send, recv = self._bounce
+        for c in range(n_chunks):
+            # the half that leaves has bit `local_qubit` != my value of the global qubit
+            _lib.check(_lib.lib().qsim_shard_pack_half(self._h, local_qubit, my_bit, c, n_chunks, c_void_p(send.data_ptr())))
+            ops = [dist.P2POp(dist.isend, send[:chunk_amps], peer), dist.P2POp(dist.irecv, recv[:chunk_amps], peer)]
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            _lib.check(_lib.lib().qsim_shard_unpack_half(self._h, local_qubit, my_bit, c, n_chunks, c_void_p(recv.data_ptr())))
+
+    # -- state ------------------------------------------------------------------------------------
+    def reset(self):
+        _lib.check(_lib.lib().qsim_sim_reset(self._h))
+
+    def synchronize(self):
+        _lib.check(_lib.lib().qsim_sim_synchronize(self._h))
+
+    def local_state(self) -> np.ndarray:
+        out = np.empty(1 << self.nl, np.complex128)
+        _lib.check(_lib.lib().qsim_sim_get_state(self._h, out.ctypes.data_as(c_void_p)))
+        return out
+
+    def set_local_state(self, amps: np.ndarray):
+        a = np.ascontiguousarray(amps, dtype=np.complex128)
+        _lib.check(_lib.lib().qsim_sim_set_state(self._h, a.ctypes.data_as(c_void_p)))
+
+    def partial_probability(self, bit: int = -1) -> float:
+        v = c_double()
+        _lib.check(_lib.lib().qsim_shard_partial_probability(self._h, bit, byref(v)))
+        return v.value
+
+    def shard_sample(self, c_init: float, first: bool, uniforms: np.ndarray):
+        u = np.ascontiguousarray(uniforms, np.float64)
+        out = np.empty(len(u), np.int64)
+        c_end = c_double()
+        _lib.check(_lib.lib().qsim_shard_sample(self._h, c_init, int(first), u.ctypes.data_as(c_void_p), len(u),
+                                                out.ctypes.data_as(c_void_p), byref(c_end)))
+        return out, c_end.value
+
+    def launch_count(self) -> int:
+        return int(_lib.lib().qsim_sim_launch_count(self._h))
+
+    def set_timing(self, on: bool):
+        _lib.check(_lib.lib().qsim_sim_set_timing(self._h, int(bool(on))))
+
+    def pass_time_ms(self):
+        t, n = c_double(), c_int64()
+        _lib.check(_lib.lib().qsim_sim_pass_time_ms(self._h, byref(t), byref(n)))
+        return t.value, n.value
+
+    def close(self):
+        if self._h and self._h.value:
+            _lib.lib().qsim_sim_destroy(self._h)
+            self._h = c_void_p()
+        for b in self._peer_base:
+            _lib.lib().qsim_ipc_close_handle(b)
+        self._peer_base = []
+
+
+@dataclass
+class CompiledPlan:
+    plan: Plan
+    programs: list                 # per step: program handle or None
+    frame_after: int               # X frame (over physical positions) once the plan has run
+    n_passes: int
+    n_ops: int
+    n_swaps: int
+
+
+class ShardedSimulator:
+    """Simulator over a state sharded across torch.distributed ranks (one GPU each)."""
+
+    def __init__(self, num_qubits: int, exchange: str = "auto", engine=None, rank: Optional[int] = None,
+                 world: Optional[int] = None):
+        if engine is None or rank is None:
+            import torch.distributed as dist
+            world = dist.get_world_size() if dist.is_initialized() else 1
+            rank = dist.get_rank() if dist.is_initialized() else 0
+        assert world & (world - 1) == 0, "world size must be a power of two"
+        self.n = int(num_qubits)
+        self.ng = world.bit_length() - 1
+        self.nl = self.n - self.ng
+        self.rank, self.world = rank, world
+        self.engine = engine if engine is not None else CudaShardEngine(self.n, self.ng, rank, world, exchange)
+        self.perm = list(range(self.n))      # logical qubit -> physical position
+        self.frame = 0                       # pending X mask over physical positions (global bits only, between runs)
+
+    @property
+    def local(self):
+        return self.engine
+
+    # -- execution ----------------------------------------------------------------------------
+    def reset(self):
+        self.engine.reset()
+        self.perm = list(range(self.n))
+        self.frame = 0
+
+    def compile(self, circuit: Circuit) -> CompiledPlan:
+        """Plan + compile against the CURRENT qubit permutation and X frame."""
+        if circuit.get_num_qubits() != self.n:
+            raise _lib.InvalidArgument("Circuit qubit count doesn't match simulator")
+        plan = plan_circuit(self.n, self.ng, circuit.gates, self.perm)
+        frame = self.frame
+        programs, n_passes, n_ops = [], 0, 0
+        for st in plan.steps:
+            if st.kind == "gates":
+                h, info = self.engine.compile_gates(st.gates, frame)
+                programs.append(h)
+                n_passes += info["passes"]
+                n_ops += info["ops"]
+                frame = info["global_xor"] << self.nl       # local part was applied by the program itself
+            else:
+                programs.append(None)
+                g, l = st.global_qubit, st.local_qubit      # the pending X (if any) travels with the qubit
+                bg, bl = (frame >> g) & 1, (frame >> l) & 1
+                frame = (frame & ~((1 << g) | (1 << l))) | (bl << g) | (bg << l)
+        return CompiledPlan(plan, programs, frame, n_passes, n_ops, plan.n_swaps)
+
+    def execute(self, cp: CompiledPlan):
+        for st, h in zip(cp.plan.steps, cp.programs):
+            if st.kind == "gates":
+                self.engine.run_program(h)
+            else:
+                self.engine.swap(st.global_qubit, st.local_qubit)
+        self.perm = list(cp.plan.perm)
+        self.frame = cp.frame_after
+
+    def release(self, cp: CompiledPlan):
+        for h in cp.programs:
+            if h is not None:
+                self.engine.free_program(h)
+        cp.programs = []
+
+    def run(self, circuit: Circuit):
+        cp = self.compile(circuit)
+        try:
+            self.execute(cp)
+        finally:
+            self.release(cp)
+
+    def synchronize(self):
+        self.engine.synchronize()
+
+    # -- index bookkeeping ----------------------------------------------------------------------
+    def _logical_rank_order(self) -> List[int]:
+        """Physical ranks in the order their shards appear in the *stored* index space with the frame resolved:
+        stored rank r holds frame-resolved rank r ^ (frame >> nl)."""
+        fx = self.frame >> self.nl
+        return [r ^ fx for r in range(self.world)]
+
+    def physical_to_logical_index(self, phys: np.ndarray) -> np.ndarray:
+        """Map amplitude indices of the stored layout (frame already resolved) to logical basis-state indices."""
+        phys = np.asarray(phys, dtype=np.uint64)
+        out = np.zeros_like(phys)
+        for q in range(self.n):
+            out |= ((phys >> np.uint64(self.perm[q])) & np.uint64(1)) << np.uint64(q)
+        return out
+
+    # -- read-out -------------------------------------------------------------------------------
+    def _allgather(self, value: float) -> List[float]:
+        if self.world == 1:
+            return [value]
+        return self.engine.allgather_float(value) if hasattr(self.engine, "allgather_float") else self._torch_allgather(value)
+
+    def _torch_allgather(self, value: float) -> List[float]:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([value], dtype=torch.float64, device="cuda")
+        out = [torch.zeros_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t)
+        return [float(x.item()) for x in out]
+
+    def _allreduce_max(self, arr: np.ndarray) -> np.ndarray:
+        if self.world == 1:
+            return arr
+        if hasattr(self.engine, "allreduce_max"):
+            return self.engine.allreduce_max(arr)
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(arr).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+
+    def get_total_probability(self) -> float:
+        return float(sum(self._allgather(self.engine.partial_probability(-1))))
+
+    def sample(self, n_shots: int = 0, uniforms: Optional[np.ndarray] = None, seed: Optional[int] = None) -> np.ndarray:
+        """Bit-exact distributed sampling: the sequential CDF runs through the shards in stored-index order (the
+        order a single device holding the same stored layout would use); returns LOGICAL basis-state indices."""
+        if uniforms is None:
+            rs = np.random.RandomState(seed)
+            uniforms = rs.random_sample(n_shots)
+        u = np.ascontiguousarray(uniforms, np.float64)
+        fx = self.frame >> self.nl
+        my_pos = self.rank ^ fx                       # position of my shard in the frame-resolved order
+        c = 0.0
+        result = np.full(len(u), -1, np.int64)
+        for pos in range(self.world):                 # chain: shard `pos` continues from the exact sum so far
+            if pos == my_pos:
+                local, c_end = self.engine.shard_sample(c, pos == 0, u)
+                hit = local >= 0
+                result[hit] = (np.int64(pos) << np.int64(self.nl)) | local[hit]
+            else:
+                c_end = 0.0
+            ends = self._allgather(c_end if pos == my_pos else -1.0)
+            c = max(ends)
+        result = self._allreduce_max(result)
+        missing = result < 0
+        out = self.physical_to_logical_index(np.where(missing, 0, result).astype(np.uint64)).astype(np.int64)
+        out[missing] = 1 << self.n                    # past the end, as the reference's lower_bound
+        return out
+
+    def get_state_vector(self) -> np.ndarray:
+        """Full logical state on every rank (small states only: tests)."""
+        import torch
+        local = self.engine.local_state()
+        if self.world > 1:
+            if hasattr(self.engine, "allgather_array"):
+                shards = self.engine.allgather_array(local)
+            else:
+                import torch.distributed as dist
+                t = torch.from_numpy(local).cuda()
+                outs = [torch.empty_like(t) for _ in range(self.world)]
+                dist.all_gather(outs, t)
+                shards = [o.cpu().numpy() for o in outs]
+        else:
+            shards = [local]
+        fx = self.frame >> self.nl
+        stored = np.concatenate([shards[p ^ fx] for p in range(self.world)])   # frame-resolved physical order
+        idx = self.physical_to_logical_index(np.arange(1 << self.n, dtype=np.uint64))
+        out = np.empty(1 << self.n, np.complex128)
+        out[idx.astype(np.int64)] = stored
+        return out
+
+    def close(self):
+        self.engine.close()

@@ -60,6 +60,8 @@ public:
     int measureBit(int bit, double uniform_draw, double* p0_out = nullptr);
     std::vector<int64_t> sampleWithUniforms(const double* uniforms, int64_t n_shots);
     std::vector<int64_t> sampleSeeded(unsigned seed, int64_t n_shots);   // mt19937(seed) draws
+    // one shard of a distributed CDF: continues the sequential sum from c_init; returns the running sum at the end
+    double sampleShard(double c_init, bool first_shard, const double* uniforms, int64_t n_shots, int64_t* out);
     double partialProbability(int bit) const;                            // sum |a|^2 with index bit == 0 (bit<0: all)
     void collapse(int bit, int outcome, double scale);
 

@@ -98,8 +98,13 @@ QSIM_API qsim_status_t qsim_circuit_depth(int num_qubits, const qsim_gate_t* gat
 /* n_global > 0 compiles for one shard of a state whose top n_global qubits are the rank id.    */
 QSIM_API qsim_status_t qsim_program_compile(int num_qubits, int n_global, const qsim_gate_t* gates,
                                             int64_t n_gates, qsim_program_t** out);
+/* Same with an inherited X frame: bit q of initial_xor set means "an X on physical qubit q is still
+ * pending" (the sharded driver threads the frame of the global qubits from one segment to the next). */
+QSIM_API qsim_status_t qsim_program_compile_ex(int num_qubits, int n_global, const qsim_gate_t* gates,
+                                               int64_t n_gates, uint64_t initial_xor, qsim_program_t** out);
 QSIM_API void qsim_program_destroy(qsim_program_t* p);
-/* info[0]=passes, [1]=ops after merging, [2]=gates, [3]=sweeps (total), [4]=tile bits of pass 0 */
+/* info[0]=passes, [1]=ops after merging, [2]=gates, [3]=sweeps (total), [4]=tile bits of pass 0,
+ * [5]=local qubits, [6]=X frame left on the global qubits (bit q - n_local): the caller owns it */
 QSIM_API qsim_status_t qsim_program_info(const qsim_program_t* p, int64_t info[8]);
 /* Human-readable plan (passes, tile qubits, sweeps).  Returns bytes needed incl. NUL. */
 QSIM_API size_t qsim_program_describe(const qsim_program_t* p, char* buf, size_t cap);
@@ -176,6 +181,13 @@ QSIM_API qsim_status_t qsim_ipc_close_handle(void* base_ptr);
  * index bit `bit` == 0; bit < 0 means no restriction). */
 QSIM_API qsim_status_t qsim_shard_partial_probability(const qsim_sim_t* s, int bit, double* out);
 QSIM_API qsim_status_t qsim_shard_collapse(qsim_sim_t* s, int bit, int outcome, double scale);
+/* Distributed bit-exact sampling: the sequential CDF of this shard continued from c_init (the exact
+ * running sum at the end of the previous shard, in logical rank order).  out[i] = local index of the
+ * first amplitude whose CDF value is >= uniforms[i] if that index lies in this shard, else -1;
+ * *c_end = exact running sum at the end of this shard.  `first_shard` != 0 makes r <= c_init (r == 0)
+ * resolve to local index 0 as std::lower_bound does. */
+QSIM_API qsim_status_t qsim_shard_sample(qsim_sim_t* s, double c_init, int first_shard, const double* uniforms,
+                                         int64_t n_shots, int64_t* out, double* c_end);
 
 #ifdef __cplusplus
 }

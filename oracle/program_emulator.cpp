@@ -134,13 +134,26 @@ void run_pass(const Program& prog, const PassDesc& pd, uint64_t hi_bits, cplx* s
 
 }  // namespace
 
+extern "C" int emu_run_ex(int n, int n_global, int rank, const qsim_gate_t* gates, int64_t ng, double* state,
+                          int min_low_bits, int max_tile_bits, int merge, int reorder, uint64_t initial_xor,
+                          int64_t* info_out, char* err, int errcap);
+
 // Compile `gates` and run the emulated kernel on `state` (2^(n - n_global) amplitudes of shard `rank`).
 // info_out: [0]=passes [1]=ops [2]=sweeps.  Returns 0, or -1 with the compiler's message in err.
 extern "C" __attribute__((visibility("default")))
 int emu_run(int n, int n_global, int rank, const qsim_gate_t* gates, int64_t ng, double* state,
             int min_low_bits, int max_tile_bits, int merge, int reorder, int64_t* info_out, char* err, int errcap) {
+    return emu_run_ex(n, n_global, rank, gates, ng, state, min_low_bits, max_tile_bits, merge, reorder, 0, info_out, err,
+                      errcap);
+}
+
+// Same with an inherited X frame (see CompileOptions::initial_xor); info_out[3] = frame left on the global qubits.
+extern "C" __attribute__((visibility("default")))
+int emu_run_ex(int n, int n_global, int rank, const qsim_gate_t* gates, int64_t ng, double* state, int min_low_bits,
+               int max_tile_bits, int merge, int reorder, uint64_t initial_xor, int64_t* info_out, char* err, int errcap) {
     CompileOptions opt;
     opt.n_global = n_global;
+    opt.initial_xor = initial_xor;
     if (min_low_bits > 0) opt.min_low_bits = min_low_bits;
     if (max_tile_bits > 0) opt.max_tile_bits = max_tile_bits;
     opt.merge = merge != 0;
@@ -164,6 +177,7 @@ int emu_run(int n, int n_global, int rank, const qsim_gate_t* gates, int64_t ng,
         int64_t sw = 0;
         for (auto& p : prog.passes) sw += p.n_sweeps;
         info_out[2] = sw;
+        info_out[3] = (int64_t)prog.global_xor;
     }
     return 0;
 }

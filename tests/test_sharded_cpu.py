@@ -1,0 +1,168 @@
+"""Multi-rank path on CPU (gloo, world_size 2 and 4): the planner, the X-frame / permutation bookkeeping
+and the exchange choreography of cuda_quantum_simulator_b200.sharded, with a TEST engine that executes
+local segments through the kernel emulator and exchanges half shards over gloo.  The product engine
+(CudaShardEngine) is exercised on GPUs by tests/test_sharded_gpu.py."""
+import ctypes
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import helpers as H
+from cuda_quantum_simulator_b200 import Circuit
+from cuda_quantum_simulator_b200.sharded import ShardedSimulator, plan_circuit
+
+
+class EmulatorShardEngine:
+    """TEST ONLY: local segments run in oracle/program_emulator (CPU), exchanges go over gloo."""
+
+    def __init__(self, n, ng, rank, world):
+        self.n, self.ng, self.nl, self.rank, self.world = n, ng, n - ng, rank, world
+        self.shard = np.zeros(1 << self.nl, np.complex128)
+        self.reset()
+
+    def reset(self):
+        self.shard[:] = 0
+        if self.rank == 0:
+            self.shard[0] = 1
+
+    def _emu(self, gates, initial_xor, state):
+        info = np.zeros(8, np.int64)
+        err = ctypes.create_string_buffer(256)
+        g = np.ascontiguousarray(gates, H.GATE_DTYPE)
+        rc = H.emulator().emu_run_ex(self.n, self.ng, self.rank, g.ctypes.data_as(H.P) if len(g) else None,
+                                     H.c_int64(len(g)), state.ctypes.data_as(H.P), 3, 6, 1, 1,
+                                     ctypes.c_uint64(initial_xor), info.ctypes.data_as(H.P), err, 256)
+        assert rc == 0, err.value
+        return info
+
+    def compile_gates(self, gates, initial_xor):
+        info = self._emu(gates, initial_xor, self.shard.copy())       # dry run for the bookkeeping outputs
+        return (np.array(gates), initial_xor), {"passes": int(info[0]), "ops": int(info[1]), "global_xor": int(info[3])}
+
+    def run_program(self, handle):
+        self._emu(handle[0], handle[1], self.shard)
+
+    def free_program(self, handle):
+        pass
+
+    def swap(self, g, l):
+        peer = self.rank ^ (1 << (g - self.nl))
+        my_bit = (self.rank >> (g - self.nl)) & 1
+        idx = np.arange(1 << self.nl)
+        leaving = ((idx >> l) & 1) != my_bit
+        send = torch.from_numpy(self.shard[leaving].copy().view(np.float64))
+        recv = torch.empty_like(send)
+        reqs = [dist.isend(send, peer), dist.irecv(recv, peer)]
+        for r in reqs:
+            r.wait()
+        self.shard[leaving] = recv.numpy().view(np.complex128)
+
+    def synchronize(self): pass
+    def local_state(self): return self.shard.copy()
+    def partial_probability(self, bit=-1): return float(np.sum(np.abs(self.shard) ** 2))
+
+    def shard_sample(self, c_init, first, u):
+        probs = H.oracle_probs(self.shard)
+        cum = np.empty(len(probs))
+        c = c_init
+        for i, p in enumerate(probs):         # sequential fp64, continuing from c_init
+            c = c + p
+            cum[i] = c
+        out = np.searchsorted(cum, u, side="left").astype(np.int64)
+        mine = (cum[-1] >= u) & ((c_init < u) | first)
+        out[~mine] = -1
+        return out, float(cum[-1])
+
+    def allgather_float(self, v):
+        t = torch.tensor([v], dtype=torch.float64)
+        outs = [torch.zeros_like(t) for _ in range(self.world)]
+        dist.all_gather(outs, t)
+        return [float(x.item()) for x in outs]
+
+    def allreduce_max(self, arr):
+        t = torch.from_numpy(arr.copy())
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.numpy()
+
+    def allgather_array(self, a):
+        t = torch.from_numpy(a.view(np.float64).copy())
+        outs = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(outs, t)
+        return [o.numpy().view(np.complex128) for o in outs]
+
+    def close(self): pass
+
+
+def _worker(rank, world, port, n, seeds, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ng = world.bit_length() - 1
+    try:
+        worst = 0.0
+        for seed in seeds:
+            rng = np.random.default_rng(seed)
+            g = H.random_gates(n, 60, rng)
+            sim = ShardedSimulator(n, engine=EmulatorShardEngine(n, ng, rank, world), rank=rank, world=world)
+            c = Circuit(n).extend(g)
+            sim.run(c)
+            got = sim.get_state_vector()
+            want = H.oracle_run(n, g)
+            worst = max(worst, float(np.max(np.abs(got - want))))
+            # run() composes across calls with the carried permutation / frame
+            sim.run(c)
+            got2 = sim.get_state_vector()
+            want2 = H.oracle_run(n, g, want)
+            worst = max(worst, float(np.max(np.abs(got2 - want2))))
+            assert abs(sim.get_total_probability() - 1) < 1e-10
+            # sampling: identical on every rank, right distribution support
+            u = np.random.default_rng(1).random(64)
+            s = sim.sample(uniforms=u)
+            pr = np.abs(want2) ** 2
+            assert np.all(pr[s] > 0)
+        if rank == 0:
+            q.put(worst)
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_matches_oracle_over_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 8, [1, 2, 3], q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) < 1e-12
+
+
+def test_planner_c4_needs_one_swap():
+    """Config C4 (36 qubits over 8 GPUs): only H(35) needs an exchange; X(35) is a frame toggle."""
+    import cuda_quantum_simulator_b200 as qs
+    c = qs.create_random_circuit(36, 20, 42)
+    plan = plan_circuit(36, 3, c.gates)
+    assert plan.n_swaps == 1
+    sw = [s for s in plan.steps if s.kind == "swap"][0]
+    assert sw.global_qubit == 35 and sw.local_qubit < 33
+    # diagonal gates and controls on global qubits never force a swap
+    c2 = qs.Circuit(6).h(0).cz(5, 0).rz(5, 0.3).cnot(5, 1).crz(4, 5, 0.2).x(5).z(4)
+    assert plan_circuit(6, 2, c2.gates).n_swaps == 0
+    c3 = qs.Circuit(6).h(5).h(5).cnot(0, 5).ry(4, 0.3)
+    p3 = plan_circuit(6, 2, c3.gates)
+    assert p3.n_swaps == 2 and sorted(p3.perm) == list(range(6))
