@@ -262,6 +262,27 @@ def main():
         dist.all_reduce(e2e_sec, op=dist.ReduceOp.MAX)
     e2e_value = n_gates * 2.0 ** (n - 30) / float(e2e_sec.item())
 
+    # ---- NVLink leg of a global-qubit swap, timed on its own (two swaps = there and back) ---------------
+    nvlink = None
+    if world > 1:
+        eng = runner.engine
+        g, l = n - 1, n_local - 1
+        eng.swap(g, l); eng.swap(g, l)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(4):
+            eng.swap(g, l)
+        e1.record(stream)
+        sync_all()
+        sw_ms = torch.tensor([e0.elapsed_time(e1) / 4], dtype=torch.float64, device="cuda")
+        dist.all_reduce(sw_ms, op=dist.ReduceOp.MAX)
+        half_bytes = 16 * (1 << (n_local - 1))
+        nvlink = {"exchange": eng.exchange, "bytes_per_direction_per_gpu": half_bytes, "ms": float(sw_ms.item()),
+                  "achieved": half_bytes / float(sw_ms.item()) / 1e6, "peak": 770.0, "unit": "GB/s",
+                  "frac": half_bytes / float(sw_ms.item()) / 1e6 / 770.0,
+                  "peak_source": "measured peer copy per direction per GPU (B200_PROFILING.md)"}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -299,6 +320,8 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if nvlink:
+        line["nvlink"] = nvlink
     if not args.no_cpu_baseline:
         n_cpu = min(args.cpu_qubits, n)
         sec, kind, ng = cpu_reference_run(n_cpu, args.depth, args.seed)
