@@ -3,9 +3,11 @@ rylanmalarchick/cuda-quantum-simulator.  Python mirror of the C++ classes; all c
 libqsim_b200.so (hand-written CUDA).  There is no CPU fallback."""
 from ._lib import GATE_DTYPE, InvalidArgument, OutOfRange, QsimError, LIB_PATH
 from .circuit import Circuit, GateType, create_bell_circuit, create_ghz_circuit, create_random_circuit
+from .noise import (BatchedSimulator, DensityMatrixSimulator, NoiseChannel, NoiseModel, NoiseType, NoisySimulator)
 from .simulator import CompiledCircuit, Simulator
 
 __all__ = [
     "GATE_DTYPE", "InvalidArgument", "OutOfRange", "QsimError", "LIB_PATH", "Circuit", "GateType",
     "create_bell_circuit", "create_ghz_circuit", "create_random_circuit", "CompiledCircuit", "Simulator",
+    "BatchedSimulator", "DensityMatrixSimulator", "NoiseChannel", "NoiseModel", "NoiseType", "NoisySimulator",
 ]

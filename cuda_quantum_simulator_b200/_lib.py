@@ -107,6 +107,44 @@ def _declare(L: ctypes.CDLL) -> None:
         "qsim_ipc_close_handle": (c_int, [P]),
         "qsim_shard_partial_probability": (c_int, [P, c_int, POINTER(c_double)]),
         "qsim_shard_collapse": (c_int, [P, c_int, c_int, c_double]),
+        "qsim_noisy_create": (c_int, [c_int, P, c_int, PP]),
+        "qsim_noisy_destroy": (None, [P]),
+        "qsim_noisy_set_noise": (c_int, [P, P, c_int]),
+        "qsim_noisy_set_seed": (c_int, [P, c_uint]),
+        "qsim_noisy_reset": (c_int, [P]),
+        "qsim_noisy_run": (c_int, [P, c_int, P, c_int64]),
+        "qsim_noisy_apply_gate": (c_int, [P, P]),
+        "qsim_noisy_apply_noise": (c_int, [P, P]),
+        "qsim_noisy_get_state": (c_int, [P, P]),
+        "qsim_noisy_get_probabilities": (c_int, [P, P]),
+        "qsim_noisy_sample": (c_int, [P, c_int, P]),
+        "qsim_noisy_measure": (c_int, [P, c_int, POINTER(c_int)]),
+        "qsim_batched_create": (c_int, [c_int, c_int, P, c_int, PP]),
+        "qsim_batched_destroy": (None, [P]),
+        "qsim_batched_set_noise": (c_int, [P, P, c_int]),
+        "qsim_batched_set_seed": (c_int, [P, c_uint]),
+        "qsim_batched_reset": (c_int, [P]),
+        "qsim_batched_run": (c_int, [P, c_int, P, c_int64]),
+        "qsim_batched_average_probabilities": (c_int, [P, P]),
+        "qsim_batched_get_probabilities": (c_int, [P, c_int, P]),
+        "qsim_batched_get_state": (c_int, [P, c_int, P]),
+        "qsim_batched_sample": (c_int, [P, c_int, P]),
+        "qsim_batched_histogram": (c_int, [P, c_int, P]),
+        "qsim_batched_total_memory_bytes": (c_size_t, [P]),
+        "qsim_dm_create": (c_int, [c_int, P, c_int, PP]),
+        "qsim_dm_destroy": (None, [P]),
+        "qsim_dm_reset": (c_int, [P]),
+        "qsim_dm_run": (c_int, [P, c_int, P, c_int64]),
+        "qsim_dm_apply_gate": (c_int, [P, P]),
+        "qsim_dm_apply_channel": (c_int, [P, c_int, c_int, c_double]),
+        "qsim_dm_init_pure": (c_int, [P, P]),
+        "qsim_dm_init_maximally_mixed": (c_int, [P]),
+        "qsim_dm_get_probabilities": (c_int, [P, P]),
+        "qsim_dm_get_matrix": (c_int, [P, P]),
+        "qsim_dm_purity": (c_int, [P, POINTER(c_double)]),
+        "qsim_dm_trace": (c_int, [P, POINTER(c_double)]),
+        "qsim_dm_is_valid": (c_int, [P, c_double, POINTER(c_int)]),
+        "qsim_dm_measure": (c_int, [P, c_int, c_double, POINTER(c_int)]),
         "qsim_shard_sample": (c_int, [P, c_double, c_int, P, c_int64, P, POINTER(c_double)]),
     }
     for name, (res, args) in sig.items():

@@ -15,6 +15,8 @@
 #include "program.hpp"
 #include "qsim/circuit.hpp"
 #include "qsim/constants.hpp"
+#include "qsim/density_matrix.cuh"
+#include "qsim/noise_model.cuh"
 #include "qsim/simulator.hpp"
 #include "shard.cuh"
 
@@ -87,6 +89,38 @@ void emit(const Circuit& c, qsim_gate_t* out) {
         if (g.qubits.size() > 2) r.q2 = g.qubits[2];
         out[i++] = r;
     }
+}
+
+}  // namespace
+
+struct qsim_noisy { std::unique_ptr<NoisySimulator> sim; };
+struct qsim_batched { std::unique_ptr<BatchedSimulator> sim; };
+struct qsim_dm { std::unique_ptr<DensityMatrixSimulator> sim; };
+
+namespace {
+
+NoiseModel to_model(const qsim_noise_channel_t* ch, int n) {
+    NoiseModel m;
+    for (int i = 0; i < n; ++i) {
+        const qsim_noise_channel_t& c = ch[i];
+        require(c.type >= 0 && c.type <= QSIM_NOISE_BIT_PHASE_FLIP, "unknown noise type");
+        const std::vector<int> q(c.qubits, c.qubits + (c.n_qubits > 0 ? c.n_qubits : 0));
+        const bool all = c.n_qubits <= 0;
+        switch (c.type) {
+            case QSIM_NOISE_DEPOLARIZING: all ? m.addDepolarizing(c.probability) : m.addDepolarizing(q, c.probability); break;
+            case QSIM_NOISE_AMPLITUDE_DAMPING: all ? m.addAmplitudeDamping(c.probability) : m.addAmplitudeDamping(q, c.probability); break;
+            case QSIM_NOISE_PHASE_DAMPING: all ? m.addPhaseDamping(c.probability) : m.addPhaseDamping(q, c.probability); break;
+            case QSIM_NOISE_BIT_FLIP: all ? m.addBitFlip(c.probability) : m.addBitFlip(q, c.probability); break;
+            case QSIM_NOISE_PHASE_FLIP: all ? m.addPhaseFlip(c.probability) : m.addPhaseFlip(q, c.probability); break;
+            default: all ? m.addBitPhaseFlip(c.probability) : m.addBitPhaseFlip(q, c.probability); break;
+        }
+    }
+    return m;
+}
+
+template <class T>
+void copy_out(const std::vector<T>& v, T* out) {
+    std::memcpy(out, v.data(), v.size() * sizeof(T));
 }
 
 }  // namespace
@@ -500,6 +534,170 @@ qsim_status_t qsim_shard_sample(qsim_sim_t* s, double c_init, int first_shard, c
         require(s != nullptr && uniforms != nullptr && out != nullptr && c_end != nullptr, "null argument");
         *c_end = s->sim->state().sampleShard(c_init, first_shard != 0, uniforms, n_shots, out);
     });
+}
+
+// ---- noisy ------------------------------------------------------------------------------------
+
+qsim_status_t qsim_noisy_create(int n, const qsim_noise_channel_t* ch, int nch, qsim_noisy_t** out) {
+    return guarded([&] {
+        require(out != nullptr, "null output");
+        auto h = std::make_unique<qsim_noisy>();
+        h->sim = std::make_unique<NoisySimulator>(n, to_model(ch, nch));
+        *out = h.release();
+    });
+}
+void qsim_noisy_destroy(qsim_noisy_t* s) { delete s; }
+qsim_status_t qsim_noisy_set_noise(qsim_noisy_t* s, const qsim_noise_channel_t* ch, int nch) {
+    return guarded([&] { require(s != nullptr, "null simulator"); s->sim->setNoiseModel(to_model(ch, nch)); });
+}
+qsim_status_t qsim_noisy_set_seed(qsim_noisy_t* s, unsigned seed) {
+    return guarded([&] { require(s != nullptr, "null simulator"); s->sim->setSeed(seed); });
+}
+qsim_status_t qsim_noisy_reset(qsim_noisy_t* s) {
+    return guarded([&] { require(s != nullptr, "null simulator"); s->sim->reset(); });
+}
+qsim_status_t qsim_noisy_run(qsim_noisy_t* s, int cq, const qsim_gate_t* gates, int64_t ng) {
+    return guarded([&] { require(s != nullptr, "null simulator"); s->sim->run(build(cq, gates, ng)); });
+}
+qsim_status_t qsim_noisy_apply_gate(qsim_noisy_t* s, const qsim_gate_t* g) {
+    return guarded([&] {
+        require(s != nullptr && g != nullptr, "null argument");
+        s->sim->applyGate(build(s->sim->getNumQubits(), g, 1).getGates()[0]);
+    });
+}
+qsim_status_t qsim_noisy_apply_noise(qsim_noisy_t* s, const qsim_noise_channel_t* ch) {
+    return guarded([&] {
+        require(s != nullptr && ch != nullptr, "null argument");
+        for (const NoiseChannel& c : to_model(ch, 1).getChannels()) s->sim->applyNoise(c);
+    });
+}
+qsim_status_t qsim_noisy_get_state(const qsim_noisy_t* s, double* out) {
+    return guarded([&] {
+        require(s != nullptr && out != nullptr, "null argument");
+        copy_out(s->sim->getStateVector(), reinterpret_cast<std::complex<double>*>(out));
+    });
+}
+qsim_status_t qsim_noisy_get_probabilities(const qsim_noisy_t* s, double* out) {
+    return guarded([&] { require(s != nullptr && out != nullptr, "null argument"); copy_out(s->sim->getProbabilities(), out); });
+}
+qsim_status_t qsim_noisy_sample(qsim_noisy_t* s, int n_shots, int32_t* out) {
+    return guarded([&] { require(s != nullptr && out != nullptr, "null argument"); copy_out(s->sim->sample(n_shots), out); });
+}
+qsim_status_t qsim_noisy_measure(qsim_noisy_t* s, int qubit, int* outcome) {
+    return guarded([&] { require(s != nullptr && outcome != nullptr, "null argument"); *outcome = s->sim->measureQubit(qubit); });
+}
+
+// ---- batched ----------------------------------------------------------------------------------
+
+qsim_status_t qsim_batched_create(int n, int batch, const qsim_noise_channel_t* ch, int nch, qsim_batched_t** out) {
+    return guarded([&] {
+        require(out != nullptr, "null output");
+        auto h = std::make_unique<qsim_batched>();
+        h->sim = std::make_unique<BatchedSimulator>(n, batch, to_model(ch, nch));
+        *out = h.release();
+    });
+}
+void qsim_batched_destroy(qsim_batched_t* s) { delete s; }
+qsim_status_t qsim_batched_set_noise(qsim_batched_t* s, const qsim_noise_channel_t* ch, int nch) {
+    return guarded([&] { require(s != nullptr, "null simulator"); s->sim->setNoiseModel(to_model(ch, nch)); });
+}
+qsim_status_t qsim_batched_set_seed(qsim_batched_t* s, unsigned seed) {
+    return guarded([&] { require(s != nullptr, "null simulator"); s->sim->setSeed(seed); });
+}
+qsim_status_t qsim_batched_reset(qsim_batched_t* s) {
+    return guarded([&] { require(s != nullptr, "null simulator"); s->sim->reset(); });
+}
+qsim_status_t qsim_batched_run(qsim_batched_t* s, int cq, const qsim_gate_t* gates, int64_t ng) {
+    return guarded([&] { require(s != nullptr, "null simulator"); s->sim->run(build(cq, gates, ng)); });
+}
+qsim_status_t qsim_batched_average_probabilities(const qsim_batched_t* s, double* out) {
+    return guarded([&] { require(s != nullptr && out != nullptr, "null argument"); copy_out(s->sim->getAverageProbabilities(), out); });
+}
+qsim_status_t qsim_batched_get_probabilities(const qsim_batched_t* s, int traj, double* out) {
+    return guarded([&] { require(s != nullptr && out != nullptr, "null argument"); copy_out(s->sim->getProbabilities(traj), out); });
+}
+qsim_status_t qsim_batched_get_state(const qsim_batched_t* s, int traj, double* out) {
+    return guarded([&] {
+        require(s != nullptr && out != nullptr, "null argument");
+        copy_out(s->sim->getTrajectoryState(traj), reinterpret_cast<std::complex<double>*>(out));
+    });
+}
+qsim_status_t qsim_batched_sample(qsim_batched_t* s, int n_shots, int32_t* out) {
+    return guarded([&] {
+        require(s != nullptr && out != nullptr, "null argument");
+        const auto v = s->sim->sample(n_shots);
+        const size_t b = (size_t)s->sim->getBatchSize();
+        for (size_t i = 0; i < v.size(); ++i) std::memcpy(out + i * b, v[i].data(), b * sizeof(int32_t));
+    });
+}
+qsim_status_t qsim_batched_histogram(qsim_batched_t* s, int n_shots, int32_t* out) {
+    return guarded([&] { require(s != nullptr && out != nullptr, "null argument"); copy_out(s->sim->getHistogram(n_shots), out); });
+}
+size_t qsim_batched_total_memory_bytes(const qsim_batched_t* s) { return s ? s->sim->getTotalMemoryBytes() : 0; }
+
+// ---- density matrix -----------------------------------------------------------------------------
+
+qsim_status_t qsim_dm_create(int n, const qsim_noise_channel_t* ch, int nch, qsim_dm_t** out) {
+    return guarded([&] {
+        require(out != nullptr, "null output");
+        auto h = std::make_unique<qsim_dm>();
+        h->sim = std::make_unique<DensityMatrixSimulator>(n, to_model(ch, nch));
+        *out = h.release();
+    });
+}
+void qsim_dm_destroy(qsim_dm_t* s) { delete s; }
+qsim_status_t qsim_dm_reset(qsim_dm_t* s) {
+    return guarded([&] { require(s != nullptr, "null simulator"); s->sim->reset(); });
+}
+qsim_status_t qsim_dm_run(qsim_dm_t* s, int cq, const qsim_gate_t* gates, int64_t ng) {
+    return guarded([&] { require(s != nullptr, "null simulator"); s->sim->run(build(cq, gates, ng)); });
+}
+qsim_status_t qsim_dm_apply_gate(qsim_dm_t* s, const qsim_gate_t* g) {
+    return guarded([&] {
+        require(s != nullptr && g != nullptr, "null argument");
+        s->sim->applyGate(build(s->sim->getNumQubits(), g, 1).getGates()[0]);
+    });
+}
+qsim_status_t qsim_dm_apply_channel(qsim_dm_t* s, int type, int qubit, double p) {
+    return guarded([&] {
+        require(s != nullptr, "null simulator");
+        require(type >= 0 && type <= QSIM_NOISE_BIT_PHASE_FLIP, "unknown noise type");
+        s->sim->applyChannel(static_cast<NoiseType>(type), qubit, p);
+    });
+}
+qsim_status_t qsim_dm_init_pure(qsim_dm_t* s, const double* st) {
+    return guarded([&] {
+        require(s != nullptr && st != nullptr, "null argument");
+        const auto* c = reinterpret_cast<const std::complex<double>*>(st);
+        s->sim->densityMatrix().initFromPureState(std::vector<std::complex<double>>(c, c + s->sim->densityMatrix().getDimension()));
+    });
+}
+qsim_status_t qsim_dm_init_maximally_mixed(qsim_dm_t* s) {
+    return guarded([&] { require(s != nullptr, "null simulator"); s->sim->densityMatrix().initMaximallyMixed(); });
+}
+qsim_status_t qsim_dm_get_probabilities(const qsim_dm_t* s, double* out) {
+    return guarded([&] { require(s != nullptr && out != nullptr, "null argument"); copy_out(s->sim->getProbabilities(), out); });
+}
+qsim_status_t qsim_dm_get_matrix(const qsim_dm_t* s, double* out) {
+    return guarded([&] {
+        require(s != nullptr && out != nullptr, "null argument");
+        copy_out(s->sim->getDensityMatrix(), reinterpret_cast<std::complex<double>*>(out));
+    });
+}
+qsim_status_t qsim_dm_purity(const qsim_dm_t* s, double* out) {
+    return guarded([&] { require(s != nullptr && out != nullptr, "null argument"); *out = s->sim->getPurity(); });
+}
+qsim_status_t qsim_dm_trace(const qsim_dm_t* s, double* out) {
+    return guarded([&] { require(s != nullptr && out != nullptr, "null argument"); *out = s->sim->getTrace(); });
+}
+qsim_status_t qsim_dm_is_valid(const qsim_dm_t* s, double tol, int* out) {
+    return guarded([&] {
+        require(s != nullptr && out != nullptr, "null argument");
+        *out = const_cast<qsim_dm_t*>(s)->sim->densityMatrix().isValid(tol) ? 1 : 0;
+    });
+}
+qsim_status_t qsim_dm_measure(qsim_dm_t* s, int qubit, double u, int* outcome) {
+    return guarded([&] { require(s != nullptr && outcome != nullptr, "null argument"); *outcome = s->sim->measureQubit(qubit, u); });
 }
 
 }  // extern "C"

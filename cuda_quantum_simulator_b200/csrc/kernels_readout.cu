@@ -36,8 +36,10 @@ __device__ __forceinline__ double prob_of(const cuDoubleComplex a) {
     return __dadd_rn(__dmul_rn(a.x, a.x), __dmul_rn(a.y, a.y));
 }
 
+// mask_bit < 0: every index counts.  Otherwise bits 0-7 hold an index bit position and bit 8 the value that
+// bit must have for the amplitude to count (0: "qubit reads 0", the measurement sums of the reference).
 __device__ __forceinline__ double masked_prob(const cuDoubleComplex* __restrict__ state, uint64_t i, int mask_bit) {
-    if (mask_bit >= 0 && ((i >> mask_bit) & 1)) return 0.0;
+    if (mask_bit >= 0 && (int)((i >> (mask_bit & 0xff)) & 1) != ((mask_bit >> 8) & 1)) return 0.0;
     return prob_of(state[i]);
 }
 

@@ -189,6 +189,56 @@ QSIM_API qsim_status_t qsim_shard_collapse(qsim_sim_t* s, int bit, int outcome, 
 QSIM_API qsim_status_t qsim_shard_sample(qsim_sim_t* s, double c_init, int first_shard, const double* uniforms,
                                          int64_t n_shots, int64_t* out, double* c_end);
 
+/* ---- NoisySimulator (reference include/NoiseModel.cuh:141-225) ---------------------------------- */
+QSIM_API qsim_status_t qsim_noisy_create(int num_qubits, const qsim_noise_channel_t* channels, int n_channels,
+                                         qsim_noisy_t** out);
+QSIM_API void qsim_noisy_destroy(qsim_noisy_t* s);
+QSIM_API qsim_status_t qsim_noisy_set_noise(qsim_noisy_t* s, const qsim_noise_channel_t* channels, int n_channels);
+QSIM_API qsim_status_t qsim_noisy_set_seed(qsim_noisy_t* s, unsigned seed);                 /* setSeed */
+QSIM_API qsim_status_t qsim_noisy_reset(qsim_noisy_t* s);
+QSIM_API qsim_status_t qsim_noisy_run(qsim_noisy_t* s, int circuit_qubits, const qsim_gate_t* gates, int64_t n_gates);
+QSIM_API qsim_status_t qsim_noisy_apply_gate(qsim_noisy_t* s, const qsim_gate_t* gate);
+QSIM_API qsim_status_t qsim_noisy_apply_noise(qsim_noisy_t* s, const qsim_noise_channel_t* channel); /* applyNoise */
+QSIM_API qsim_status_t qsim_noisy_get_state(const qsim_noisy_t* s, double* host_out);
+QSIM_API qsim_status_t qsim_noisy_get_probabilities(const qsim_noisy_t* s, double* host_out);
+/* sample(n_shots): one mt19937 draw per shot from the simulator's own engine (seeded by set_seed). */
+QSIM_API qsim_status_t qsim_noisy_sample(qsim_noisy_t* s, int n_shots, int32_t* out);
+/* measureQubit(q): index bit q, one draw (reference src/NoiseModel.cu:615-651). */
+QSIM_API qsim_status_t qsim_noisy_measure(qsim_noisy_t* s, int qubit, int* outcome);
+
+/* ---- BatchedSimulator (reference include/NoiseModel.cuh:236-297) --------------------------------- */
+QSIM_API qsim_status_t qsim_batched_create(int num_qubits, int batch_size, const qsim_noise_channel_t* channels,
+                                           int n_channels, qsim_batched_t** out);
+QSIM_API void qsim_batched_destroy(qsim_batched_t* s);
+QSIM_API qsim_status_t qsim_batched_set_noise(qsim_batched_t* s, const qsim_noise_channel_t* channels, int n_channels);
+QSIM_API qsim_status_t qsim_batched_set_seed(qsim_batched_t* s, unsigned seed);
+QSIM_API qsim_status_t qsim_batched_reset(qsim_batched_t* s);
+QSIM_API qsim_status_t qsim_batched_run(qsim_batched_t* s, int circuit_qubits, const qsim_gate_t* gates, int64_t n_gates);
+QSIM_API qsim_status_t qsim_batched_average_probabilities(const qsim_batched_t* s, double* host_out);   /* 2^n */
+QSIM_API qsim_status_t qsim_batched_get_probabilities(const qsim_batched_t* s, int trajectory, double* host_out);
+QSIM_API qsim_status_t qsim_batched_get_state(const qsim_batched_t* s, int trajectory, double* host_out);
+/* sample(n_shots): out[shot * batch + trajectory]; draws are trajectory-major (src/NoiseModel.cu:938-957). */
+QSIM_API qsim_status_t qsim_batched_sample(qsim_batched_t* s, int n_shots, int32_t* out);
+QSIM_API qsim_status_t qsim_batched_histogram(qsim_batched_t* s, int n_shots, int32_t* out);             /* 2^n */
+QSIM_API size_t qsim_batched_total_memory_bytes(const qsim_batched_t* s);
+
+/* ---- DensityMatrixSimulator (reference include/DensityMatrix.cuh:63-224) -------------------------- */
+QSIM_API qsim_status_t qsim_dm_create(int num_qubits, const qsim_noise_channel_t* channels, int n_channels, qsim_dm_t** out);
+QSIM_API void qsim_dm_destroy(qsim_dm_t* s);
+QSIM_API qsim_status_t qsim_dm_reset(qsim_dm_t* s);
+QSIM_API qsim_status_t qsim_dm_run(qsim_dm_t* s, int circuit_qubits, const qsim_gate_t* gates, int64_t n_gates);
+QSIM_API qsim_status_t qsim_dm_apply_gate(qsim_dm_t* s, const qsim_gate_t* gate);
+QSIM_API qsim_status_t qsim_dm_apply_channel(qsim_dm_t* s, int noise_type, int qubit, double probability);
+QSIM_API qsim_status_t qsim_dm_init_pure(qsim_dm_t* s, const double* host_state);        /* DensityMatrix::initFromPureState */
+QSIM_API qsim_status_t qsim_dm_init_maximally_mixed(qsim_dm_t* s);
+QSIM_API qsim_status_t qsim_dm_get_probabilities(const qsim_dm_t* s, double* host_out);  /* 2^n */
+QSIM_API qsim_status_t qsim_dm_get_matrix(const qsim_dm_t* s, double* host_out);         /* 4^n complex, row-major */
+QSIM_API qsim_status_t qsim_dm_purity(const qsim_dm_t* s, double* out);
+QSIM_API qsim_status_t qsim_dm_trace(const qsim_dm_t* s, double* out);
+QSIM_API qsim_status_t qsim_dm_is_valid(const qsim_dm_t* s, double tolerance, int* out);
+/* measureQubit with the uniform supplied: outcome = (u < p1) ? 1 : 0 (src/DensityMatrix.cu:374-406). */
+QSIM_API qsim_status_t qsim_dm_measure(qsim_dm_t* s, int qubit, double uniform, int* outcome);
+
 #ifdef __cplusplus
 }
 #endif
