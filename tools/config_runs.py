@@ -1,0 +1,114 @@
+"""Runs the BASELINE.json configurations that are not the bench headline and prints one JSON line each
+(evidence for profiles/): c1 (20 q, 120 gates), c3 (33 q GHZ + QFT-style), c5 (12 q x 65536 noisy trajectories).
+usage: config_runs.py c1|c3|c5 [...]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cuda_quantum_simulator_b200 as q
+import helpers as H
+
+
+def timed(sim, fn, reps):
+    fn(); sim.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    sim.synchronize()
+    return (time.perf_counter() - t0) / reps
+
+
+def qft_style(n, window=None):
+    """GHZ followed by H / CRZ(j, q, pi/2^(j-q)) layers and a seeded Rz layer."""
+    c = q.create_ghz_circuit(n)
+    for qb in range(n):
+        c.h(qb)
+        hi = n if window is None else min(n, qb + 1 + window)
+        for j in range(qb + 1, hi):
+            c.crz(j, qb, float(np.pi / 2 ** (j - qb)))
+    theta = H.mt19937_uniforms(42, n) * 2 * np.pi
+    for qb in range(n):
+        c.rz(qb, float(theta[qb]))
+    return c
+
+
+def c1():
+    n = 20
+    g = H.bench_c1_gates(n)
+    c = q.Circuit(n).extend(g)
+    sim = q.Simulator(n)
+    prog = q.CompiledCircuit(c)
+    sim.execute(prog)
+    err = float(np.max(np.abs(sim.get_state_vector() - H.oracle_run(n, g))))
+    sim.reset()
+    sec = timed(sim, lambda: sim.execute(prog), 200)
+    sec_api = timed(sim, lambda: sim.run(c), 50)
+    ref = H.reference()
+    cpu = ref.ref_cpu_run(n, g.ctypes.data_as(H.P), H.c_int64(len(g)), None) if ref else None
+    ref_gpu = ref.ref_gpu_run(n, g.ctypes.data_as(H.P), H.c_int64(len(g)), None, 20) if ref else None
+    print(json.dumps({"config": "C1 20q 100H+20CNOT (benchmark_scaling.cu:68-75)", "gates": len(g), "passes": prog.n_passes,
+                      "max_abs_err_vs_oracle": err, "ms_compiled": sec * 1e3, "gates_per_s_compiled": len(g) / sec,
+                      "ms_run_api": sec_api * 1e3, "gates_per_s_run_api": len(g) / sec_api,
+                      "reference_cpu_ms": cpu * 1e3 if cpu else None,
+                      "reference_gpu_kernels_sm100a_ms": ref_gpu * 1e3 if ref_gpu else None}), flush=True)
+
+
+def c3(n=33, window=None):
+    c = qft_style(n, window)
+    t0 = time.perf_counter()
+    prog = q.CompiledCircuit(c)
+    compile_s = time.perf_counter() - t0
+    sim = q.Simulator(n)
+    sec = timed(sim, lambda: (sim.reset(), sim.execute(prog)), 2)
+    total = sim.get_total_probability()
+    byt = 2 * 16 * (1 << n)
+    # parity of the same generator at a size the oracle can do
+    m = 22
+    cs = qft_style(m, window)
+    s2 = q.Simulator(m)
+    s2.run(cs)
+    err = float(np.max(np.abs(s2.get_state_vector() - H.oracle_run(m, cs.gates))))
+    print(json.dumps({"config": f"C3 {n}q GHZ + QFT-style H/CRZ/Rz (window={window})", "gates": c.get_gate_count(), "passes": prog.n_passes,
+                      "ops": prog.n_ops, "ms": sec * 1e3, "gates_per_s": c.get_gate_count() / sec, "compile_ms": compile_s * 1e3,
+                      "achieved_gbs_circuit_level": prog.n_passes * byt / sec / 1e9, "total_probability": total,
+                      f"max_abs_err_vs_oracle_at_{m}q": err}), flush=True)
+
+
+def c5():
+    n, batch = 12, 65536
+    c = q.create_ghz_circuit(n)
+    m = q.NoiseModel().add_depolarizing(0.005).add_amplitude_damping(0.001)
+    sim = q.BatchedSimulator(n, batch, m)
+    sim.set_seed(42)
+    t0 = time.perf_counter(); sim.run(c); run_s = time.perf_counter() - t0      # includes the first-launch setup
+    sim.reset(); sim.set_seed(42)
+    t0 = time.perf_counter(); sim.run(c); run_s = time.perf_counter() - t0
+    t0 = time.perf_counter(); avg = sim.get_average_probabilities(); avg_s = time.perf_counter() - t0
+    t0 = time.perf_counter(); hist = sim.get_histogram(1); hist_s = time.perf_counter() - t0
+    out = {"config": "C5 BatchedSimulator 12q GHZ x 65536 trajectories, depolarizing 0.005 + amplitude damping 0.001 on all qubits after every gate",
+           "run_ms": run_s * 1e3, "trajectories_per_s": batch / run_s, "average_probabilities_ms": avg_s * 1e3,
+           "histogram_ms": hist_s * 1e3, "avg_sum": float(avg.sum()), "hist_total": int(hist.sum()),
+           "p_all_zero": float(avg[0]), "p_all_one": float(avg[-1])}
+    ref = H.reference()
+    if ref is not None:   # the reference's own BatchedSimulator (depolarizing only, per-pair draws) on the same GPU
+        g = c.gates
+        dq = np.arange(n, dtype=np.int32)
+        secs = ref.ref_gpu_batched_run(n, batch, g.ctypes.data_as(H.P), H.c_int64(len(g)), dq.ctypes.data_as(H.P), n,
+                                       H.c_double(0.005), H.c_uint(42), None)
+        out["reference_batched_gpu_ms_depolarizing_only"] = secs * 1e3
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    for name in sys.argv[1:]:
+        if name == "c1": c1()
+        elif name == "c3": c3()
+        elif name == "c3w": c3(33, 8)
+        elif name == "c3small": c3(28)
+        elif name == "c5": c5()
