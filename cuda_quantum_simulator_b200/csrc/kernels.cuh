@@ -11,7 +11,6 @@
 namespace qsim {
 namespace b200 {
 
-constexpr int kPassThreads = kComputeThreads + 32;   // 8 compute warps + 1 TMA warp
 constexpr int kMaxDynamicSmem = 227 * 1024;
 
 struct PassParams {

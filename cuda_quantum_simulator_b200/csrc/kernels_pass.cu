@@ -2,17 +2,18 @@
 // many gates the pass carries (the reference sweeps HBM once per gate, src/Simulator.cu:48-154 and
 // src/Gates.cu:31-410 of the reference).
 //
-// Structure (persistent, one CTA per SM, 9 warps):
-//   warp 8     TMA producer/consumer of global memory.  For its CTA's tiles it issues 1-D bulk
-//              copies (cp.async.bulk, SASS UBLKCP) global -> shared into a 3-stage ring, signalled
-//              through mbarrier complete_tx; after the compute warps release a stage it issues the
-//              bulk copies shared -> global for that stage and immediately refills it.
-//   warps 0-7  compute.  A tile is 2^t amplitudes (t <= 12: 64 KiB): the low L index bits (one
-//              contiguous run of 16 << L bytes) x (t - L) arbitrary high "tile qubits".  Per sweep
-//              every thread pulls 2^r amplitudes (r <= 4) from shared memory into registers with
-//              128-bit conflict-free loads, runs the sweep's op list — register-resident targets
-//              in-thread, lane-resident targets with __shfl_xor butterflies, diagonal gates as a
-//              single complex multiply wherever their qubits live — and writes back.
+// Structure (persistent, one CTA per SM, kComputeWarps warps, every warp computes):
+//   A tile is 2^t amplitudes (t <= 12: 64 KiB): up to five runs of contiguous index bits, moved by ONE
+//   tensor-map TMA instruction per direction (cp.async.bulk.tensor.5d, SASS UTMALDG / UTMASTG) into a
+//   ring of shared-memory stages, completion through mbarrier complete_tx.  Per sweep every thread pulls
+//   kSlots amplitudes from shared memory into registers with 128-bit conflict-free loads, runs the
+//   sweep's op list — register-resident targets in-thread, lane-resident targets with __shfl_xor
+//   butterflies, diagonal gates as a single complex multiply wherever their qubits live — and writes back.
+//   TMA issue is folded into one elected thread: after tile i has been computed it issues the store of
+//   tile i, makes sure the store of tile i-1 has drained its stage and refills that stage with tile
+//   i-1+S, so one or two tile loads are always in flight while the warps compute.  (A dedicated TMA
+//   warp would be the ninth/seventeenth warp and, with the 4-warp register allocation granularity, cost
+//   a quarter of the register file.)
 //
 // Algorithmic traffic: 2 * 16 * 2^n bytes per pass.
 #include "kernels.cuh"
@@ -40,9 +41,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                  : "memory");
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -111,12 +109,9 @@ __device__ __forceinline__ uint64_t instr_offset(const PassDesc& pd, uint32_t q)
 }
 
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void compute_barrier() {
-    asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory");
-}
 
 __device__ __forceinline__ void lds128(uint32_t addr, double& x, double& y) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr) : "memory");
@@ -159,11 +154,11 @@ __device__ __forceinline__ uint64_t run_offset(const PassDesc& pd, uint32_t run)
 // the common case — carry no predicate at all).
 
 template <int J, int KIND, bool CTRL>
-__device__ __forceinline__ void reg_pairs(const DevOp& op, uint32_t sm, double (&ar)[16], double (&ai)[16]) {
+__device__ __forceinline__ void reg_pairs(const DevOp& op, uint32_t sm, double (&ar)[kSlots], double (&ai)[kSlots]) {
     const double m00r = op.m[0], m00i = op.m[1], m01r = op.m[2], m01i = op.m[3];
     const double m10r = op.m[4], m10i = op.m[5], m11r = op.m[6], m11i = op.m[7];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (int k = 0; k < kSlots; ++k) {
         if (k & (1 << J)) continue;   // compile-time: k enumerates the slots whose target bit is 0
         const int k1 = k | (1 << J);
         const double xr = ar[k], xi = ai[k], yr = ar[k1], yi = ai[k1];
@@ -192,25 +187,15 @@ __device__ __forceinline__ void reg_pairs(const DevOp& op, uint32_t sm, double (
 }
 
 template <int KIND, bool CTRL>
-__device__ __forceinline__ void reg_target(const DevOp& op, uint32_t sm, double (&ar)[16], double (&ai)[16]) {
-    switch (op.tbit) {
-        case 0: reg_pairs<0, KIND, CTRL>(op, sm, ar, ai); break;
-        case 1: reg_pairs<1, KIND, CTRL>(op, sm, ar, ai); break;
-        case 2: reg_pairs<2, KIND, CTRL>(op, sm, ar, ai); break;
-        default: reg_pairs<3, KIND, CTRL>(op, sm, ar, ai); break;
-    }
-}
-
-template <int KIND, bool CTRL>
-__device__ __forceinline__ void lane_target(const DevOp& op, uint32_t sm, uint32_t tid, double (&ar)[16],
-                                            double (&ai)[16]) {
+__device__ __forceinline__ void lane_target(const DevOp& op, uint32_t sm, uint32_t tid, double (&ar)[kSlots],
+                                            double (&ai)[kSlots]) {
     const int lm = 1 << op.tbit;
     const bool b = (tid >> op.tbit) & 1;
     // coefficient of my own amplitude and of my partner's
     const double cor = b ? op.m[6] : op.m[0], coi = b ? op.m[7] : op.m[1];
     const double cpr = b ? op.m[4] : op.m[2], cpi = b ? op.m[5] : op.m[3];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (int k = 0; k < kSlots; ++k) {
         const double pr = shfl_xor_f64(ar[k], lm), pi = shfl_xor_f64(ai[k], lm);
         const double xr = ar[k], xi = ai[k];
         double nr, ni;
@@ -231,13 +216,13 @@ __device__ __forceinline__ void lane_target(const DevOp& op, uint32_t sm, uint32
 }
 
 template <bool CTRL>
-__device__ __forceinline__ void diagonal(const DevOp& op, uint32_t sm, uint32_t tid, uint64_t gbase, double (&ar)[16],
-                                         double (&ai)[16]) {
+__device__ __forceinline__ void diagonal(const DevOp& op, uint32_t sm, uint32_t tid, uint64_t gbase, double (&ar)[kSlots],
+                                         double (&ai)[kSlots]) {
     const double d0r = op.m[0], d0i = op.m[1], d1r = op.m[6], d1i = op.m[7];
     if (op.thome == T_REG) {
         const uint32_t tsl = op.tslots;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < kSlots; ++k) {
             const bool b = (tsl >> k) & 1;
             const double pr = b ? d1r : d0r, pi = b ? d1i : d0i;
             const double xr = ar[k], xi = ai[k];
@@ -249,7 +234,7 @@ __device__ __forceinline__ void diagonal(const DevOp& op, uint32_t sm, uint32_t 
         const bool b = (op.thome == T_THREAD) ? ((tid & op.tmask_thr) != 0) : ((gbase & op.tmask_out) != 0);
         const double pr = b ? d1r : d0r, pi = b ? d1i : d0i;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < kSlots; ++k) {
             const double xr = ar[k], xi = ai[k];
             const double nr = xr * pr - xi * pi, ni = xr * pi + xi * pr;
             if (CTRL) { const bool on = (sm >> k) & 1; ar[k] = on ? nr : xr; ai[k] = on ? ni : xi; }
@@ -267,12 +252,12 @@ __device__ __forceinline__ void diagonal(const DevOp& op, uint32_t sm, uint32_t 
     case (KIND) * 10 + 5: reg_pairs<1, KIND, true>(op, sm, ar, ai); break;             \
     case (KIND) * 10 + 6: reg_pairs<2, KIND, false>(op, 0xffffu, ar, ai); break;       \
     case (KIND) * 10 + 7: reg_pairs<2, KIND, true>(op, sm, ar, ai); break;             \
-    case (KIND) * 10 + 8: reg_pairs<3, KIND, false>(op, 0xffffu, ar, ai); break;       \
-    case (KIND) * 10 + 9: reg_pairs<3, KIND, true>(op, sm, ar, ai); break;
+    case (KIND) * 10 + 8: reg_pairs<(kMaxRegBits > 3 ? 3 : 0), KIND, false>(op, 0xffffu, ar, ai); break; \
+    case (KIND) * 10 + 9: reg_pairs<(kMaxRegBits > 3 ? 3 : 0), KIND, true>(op, sm, ar, ai); break;
 
 }  // namespace
 
-__global__ void __launch_bounds__(kPassThreads, 1)
+__global__ void __launch_bounds__(kComputeThreads, 1)
 fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const PassDesc& pd = P.pd;
@@ -281,23 +266,21 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
     const int n_stages = P.stages;
     DevOp* sops = reinterpret_cast<DevOp*>(smem + (size_t)n_stages * tile_bytes);
     uint64_t* full = reinterpret_cast<uint64_t*>(sops + pd.n_ops + 1);   // +1: zeroed padding record (prefetch)
-    uint64_t* done = full + n_stages;
 
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
 
     // stage this pass's op list in shared memory (broadcast reads later)
     {
         const uint4* src = reinterpret_cast<const uint4*>(P.ops);
         uint4* dst = reinterpret_cast<uint4*>(sops);
         const int n16 = pd.n_ops * (int)(sizeof(DevOp) / 16);
-        for (int i = tid; i < n16; i += kPassThreads) dst[i] = src[i];
+        for (int i = tid; i < n16; i += kComputeThreads) dst[i] = src[i];
         if (tid < (int)(sizeof(DevOp) / 16)) dst[n16 + tid] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
         if (P.use_tensor_map) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
         for (int s = 0; s < n_stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&done[s], kComputeWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -326,139 +309,139 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
     const uint32_t box_bytes = tile_bytes >> pd.tma_instr_bits;
     unsigned char* const gstate = reinterpret_cast<unsigned char*>(P.state);
 
-    if (warp == kComputeWarps) {
-        // ===================== TMA warp =====================
-        auto issue_load = [&](uint64_t i) {
-            const int s = (int)(i % n_stages);
-            const uint64_t base = tile_base(pd, tile_of(i));
-            if (lane == 0) mbar_expect_tx(&full[s], tile_bytes);
-            __syncwarp();
-            if (P.use_tensor_map) {
-                for (uint32_t q = lane; q < n_instr; q += 32) {
-                    int c[5];
-                    tma_coords(pd, base + instr_offset(pd, q), c);
-                    tma_load_5d(tiles + (size_t)s * tile_bytes + (size_t)q * box_bytes, &tmap, c, &full[s]);
-                }
-            } else {
-                for (uint32_t run = lane; run < n_runs; run += 32) {
-                    const uint64_t g = base + run_offset(pd, run);
-                    tma_load_1d(tiles + (size_t)s * tile_bytes + (size_t)run * run_bytes, gstate + g * 16, run_bytes,
-                                &full[s]);
-                }
+    // ---- TMA duties of the elected thread --------------------------------------------------------------
+    auto issue_load = [&](uint64_t i) {
+        const int s = (int)(i % n_stages);
+        const uint64_t base = tile_base(pd, tile_of(i));
+        mbar_expect_tx(&full[s], tile_bytes);
+        if (P.use_tensor_map) {
+            for (uint32_t q = 0; q < n_instr; ++q) {
+                int c[5];
+                tma_coords(pd, base + instr_offset(pd, q), c);
+                tma_load_5d(tiles + (size_t)s * tile_bytes + (size_t)q * box_bytes, &tmap, c, &full[s]);
             }
-        };
+        } else {
+            for (uint32_t run = 0; run < n_runs; ++run) {
+                const uint64_t g = base + run_offset(pd, run);
+                tma_load_1d(tiles + (size_t)s * tile_bytes + (size_t)run * run_bytes, gstate + g * 16, run_bytes, &full[s]);
+            }
+        }
+    };
+    auto issue_store = [&](uint64_t i) {
+        const int s = (int)(i % n_stages);
+        if (xor_tau && !(i & 1)) {
+            // this tile goes to its partner's location: the partner (item i+1) must have been read first
+            const uint64_t j = i + 1;
+            mbar_wait(&full[(int)(j % n_stages)], (uint32_t)((j / n_stages) & 1));
+        }
+        const uint64_t base = tile_base(pd, tile_of(i) ^ xor_tau);
+        if (P.use_tensor_map) {
+            for (uint32_t q = 0; q < n_instr; ++q) {
+                int c[5];
+                tma_coords(pd, base + instr_offset(pd, q), c);
+                tma_store_5d(&tmap, c, tiles + (size_t)s * tile_bytes + (size_t)q * box_bytes);
+            }
+        } else {
+            for (uint32_t run = 0; run < n_runs; ++run) {
+                const uint64_t g = base + run_offset(pd, run);
+                tma_store_1d(gstate + g * 16, tiles + (size_t)s * tile_bytes + (size_t)run * run_bytes, run_bytes);
+            }
+        }
+        tma_store_commit();
+    };
+
+    if (tid == 0) {
         const uint64_t pre = n_my < (uint64_t)n_stages ? n_my : (uint64_t)n_stages;
         for (uint64_t i = 0; i < pre; ++i) issue_load(i);
-        for (uint64_t i = 0; i < n_my; ++i) {
-            const int s = (int)(i % n_stages);
-            const uint32_t parity = (uint32_t)((i / n_stages) & 1);
-            mbar_wait(&done[s], parity);
-            if (xor_tau && !(i & 1)) {
-                // this tile goes to its partner's location: the partner (item i+1) must have been read first
-                const uint64_t j = i + 1;
-                mbar_wait(&full[(int)(j % n_stages)], (uint32_t)((j / n_stages) & 1));
-            }
-            const uint64_t base = tile_base(pd, tile_of(i) ^ xor_tau);
-            if (P.use_tensor_map) {
-                for (uint32_t q = lane; q < n_instr; q += 32) {
-                    int c[5];
-                    tma_coords(pd, base + instr_offset(pd, q), c);
-                    tma_store_5d(&tmap, c, tiles + (size_t)s * tile_bytes + (size_t)q * box_bytes);
-                }
-            } else {
-                for (uint32_t run = lane; run < n_runs; run += 32) {
-                    const uint64_t g = base + run_offset(pd, run);
-                    tma_store_1d(gstate + g * 16, tiles + (size_t)s * tile_bytes + (size_t)run * run_bytes, run_bytes);
-                }
-            }
-            tma_store_commit();
-            tma_store_wait_read();   // shared memory of this stage may be overwritten now
-            __syncwarp();
-            if (i + n_stages < n_my) issue_load(i + n_stages);
-        }
-        tma_store_wait_all();
-    } else {
-        // ===================== compute warps =====================
-        double ar[16], ai[16];
-        for (uint64_t i = 0; i < n_my; ++i) {
-            const int s = (int)(i % n_stages);
-            const uint32_t parity = (uint32_t)((i / n_stages) & 1);
-            const uint64_t gbase = tile_base(pd, tile_of(i)) | P.hi_bits;
-            unsigned char* tile = tiles + (size_t)s * tile_bytes;
-            mbar_wait(&full[s], parity);
+    }
+
+    double ar[kSlots], ai[kSlots];
+    for (uint64_t i = 0; i < n_my; ++i) {
+        const int s = (int)(i % n_stages);
+        const uint32_t parity = (uint32_t)((i / n_stages) & 1);
+        const uint64_t gbase = tile_base(pd, tile_of(i)) | P.hi_bits;
+        unsigned char* tile = tiles + (size_t)s * tile_bytes;
+        mbar_wait(&full[s], parity);
 
 #pragma unroll 1
-            for (int sw = 0; sw < pd.n_sweeps; ++sw) {
-                const SweepDesc& sd = pd.sweep[sw];
-                if (sw > 0) compute_barrier();
-                const uint32_t n_active = 1u << sd.nthr;
-                const bool warp_active = (warp << 5) < n_active;
-                const uint32_t xl = (sw + 1 == pd.n_sweeps) ? pd.xor_local : 0u;   // deferred X gates, see the store
-                if (!warp_active) {
-                    if (xl) compute_barrier();   // keep the barrier count equal across warps
-                    continue;
-                }
-                const bool active = tid < n_active;
-                const int slots = 1 << sd.r;
-                uint32_t base_local = 0;
+        for (int sw = 0; sw < pd.n_sweeps; ++sw) {
+            const SweepDesc& sd = pd.sweep[sw];
+            if (sw > 0) __syncthreads();
+            const uint32_t n_active = 1u << sd.nthr;
+            const bool warp_active = (warp << 5) < n_active;
+            const uint32_t xl = (sw + 1 == pd.n_sweeps) ? pd.xor_local : 0u;   // deferred X gates, see the store
+            if (!warp_active) {
+                if (xl) __syncthreads();   // keep the barrier count equal across warps
+                continue;
+            }
+            const bool active = tid < n_active;
+            const int slots = 1 << sd.r;
+            uint32_t base_local = 0;
 #pragma unroll
-                for (int b = 0; b < 8; ++b)
-                    if (b < sd.nthr && ((tid >> b) & 1)) base_local |= 1u << sd.thr_pos[b];
-                const uint32_t tile_u32 = smem_u32(tile);
-                const uint32_t my_addr = tile_u32 + base_local * 16u;
-                const bool full_sweep = (sd.r == 4) && (sd.nthr == 8);   // the only shape that matters for speed
-                if (full_sweep) {
+            for (int b = 0; b < kMaxTileBits - kMaxRegBits; ++b)
+                if (b < sd.nthr && ((tid >> b) & 1)) base_local |= 1u << sd.thr_pos[b];
+            const uint32_t tile_u32 = smem_u32(tile);
+            const uint32_t my_addr = tile_u32 + base_local * 16u;
+            const bool full_sweep = (sd.r == kMaxRegBits) && (sd.nthr == kMaxTileBits - kMaxRegBits);
+            if (full_sweep) {
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) lds128(my_addr + (uint32_t)sd.slot_off[k] * 16u, ar[k], ai[k]);
-                } else {
+                for (int k = 0; k < kSlots; ++k) lds128(my_addr + (uint32_t)sd.slot_off[k] * 16u, ar[k], ai[k]);
+            } else {
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        ar[k] = 0.0;
-                        ai[k] = 0.0;
-                        if (active && k < slots) lds128(my_addr + (uint32_t)sd.slot_off[k] * 16u, ar[k], ai[k]);
-                    }
-                }
-                const uint32_t ops_u32 = smem_u32(sops);
-#pragma unroll 1
-                for (int o = sd.op_begin; o < sd.op_end; ++o) {
-                    const DevOp& op = sops[o];
-                    // first 16 bytes of the record: kind|thome|tbit|opcode, slotmask|tslots, cmask_thr, cval_thr
-                    const uint4 hdr = lds_u4(ops_u32 + (uint32_t)o * (uint32_t)sizeof(DevOp));
-                    const uint32_t opcode = hdr.x >> 24;
-                    if (opcode & 0x80u) {
-                        if ((gbase & op.cmask_out) != op.cval_out) continue;
-                    }
-                    const bool thr_ok = (tid & hdr.z) == hdr.w;
-                    const uint32_t sm = thr_ok ? (hdr.y & 0xffffu) : 0u;
-                    switch (opcode & 0x7fu) {
-                        QSIM_PAIR_CASES(OP_MAT)
-                        QSIM_PAIR_CASES(OP_MATREAL)
-                        QSIM_PAIR_CASES(OP_ADIAG)
-                        QSIM_PAIR_CASES(OP_FLIP)
-                        case 40: case 42: diagonal<false>(op, 0xffffu, tid, gbase, ar, ai); break;
-                        default: diagonal<true>(op, sm, tid, gbase, ar, ai); break;
-                    }
-                }
-                // the pass's deferred X gates: the last sweep stores to the XOR-ed tile-local index (other
-                // threads' slots, hence the barrier: everybody has finished loading)
-                if (xl) compute_barrier();
-                if (full_sweep) {
-#pragma unroll
-                    for (int k = 0; k < 16; ++k)
-                        sts128(tile_u32 + (((base_local + (uint32_t)sd.slot_off[k]) ^ xl) * 16u), ar[k], ai[k]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 16; ++k)
-                        if (active && k < slots)
-                            sts128(tile_u32 + (((base_local + (uint32_t)sd.slot_off[k]) ^ xl) * 16u), ar[k], ai[k]);
+                for (int k = 0; k < kSlots; ++k) {
+                    ar[k] = 0.0;
+                    ai[k] = 0.0;
+                    if (active && k < slots) lds128(my_addr + (uint32_t)sd.slot_off[k] * 16u, ar[k], ai[k]);
                 }
             }
-            // make the generic-proxy writes visible to the bulk-copy engine, then hand the stage over
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&done[s]);
+            const uint32_t ops_u32 = smem_u32(sops);
+#pragma unroll 1
+            for (int o = sd.op_begin; o < sd.op_end; ++o) {
+                const DevOp& op = sops[o];
+                // first 16 bytes of the record: kind|thome|tbit|opcode, slotmask|tslots, cmask_thr, cval_thr
+                const uint4 hdr = lds_u4(ops_u32 + (uint32_t)o * (uint32_t)sizeof(DevOp));
+                const uint32_t opcode = hdr.x >> 24;
+                if (opcode & 0x80u) {
+                    if ((gbase & op.cmask_out) != op.cval_out) continue;
+                }
+                const bool thr_ok = (tid & hdr.z) == hdr.w;
+                const uint32_t sm = thr_ok ? (hdr.y & 0xffffu) : 0u;
+                switch (opcode & 0x7fu) {
+                    QSIM_PAIR_CASES(OP_MAT)
+                    QSIM_PAIR_CASES(OP_MATREAL)
+                    QSIM_PAIR_CASES(OP_ADIAG)
+                    QSIM_PAIR_CASES(OP_FLIP)
+                    case 40: case 42: diagonal<false>(op, 0xffffu, tid, gbase, ar, ai); break;
+                    default: diagonal<true>(op, sm, tid, gbase, ar, ai); break;
+                }
+            }
+            // the pass's deferred X gates: the last sweep stores to the XOR-ed tile-local index (other
+            // threads' slots, hence the barrier: everybody has finished loading)
+            if (xl) __syncthreads();
+            if (full_sweep) {
+#pragma unroll
+                for (int k = 0; k < kSlots; ++k)
+                    sts128(tile_u32 + (((base_local + (uint32_t)sd.slot_off[k]) ^ xl) * 16u), ar[k], ai[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < kSlots; ++k)
+                    if (active && k < slots)
+                        sts128(tile_u32 + (((base_local + (uint32_t)sd.slot_off[k]) ^ xl) * 16u), ar[k], ai[k]);
+            }
+        }
+        // make the generic-proxy writes visible to the bulk-copy engine; then the elected thread stores
+        // this tile and refills the stage whose store (tile i-1) has drained
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            issue_store(i);
+            if (i >= 1 && (i - 1) + (uint64_t)n_stages < n_my) {
+                tma_store_wait_read_1();   // all but the newest store group have finished reading shared memory
+                issue_load((i - 1) + (uint64_t)n_stages);
+            }
         }
     }
+    if (tid == 0) tma_store_wait_all();
 }
 
 size_t pass_smem_bytes(const PassDesc& pd, int stages) {
@@ -469,6 +452,7 @@ size_t pass_smem_bytes(const PassDesc& pd, int stages) {
 int pick_stages(const PassDesc& pd, int wanted) {
     int st = wanted > 0 ? wanted : kMaxStages;
     if (st > kMaxStages) st = kMaxStages;
+    if (st < 3) st = 3;   // the partner-tile store waits for the load of the next item: needs three stages
     while (st > 1 && pass_smem_bytes(pd, st) > (size_t)kMaxDynamicSmem) --st;
     return st;
 }
@@ -526,7 +510,7 @@ cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t s
     const size_t smem = pass_smem_bytes(params.pd, params.stages);
     if (params.stages < 1 || smem > (size_t)kMaxDynamicSmem) return cudaErrorInvalidValue;
     uint64_t grid = params.n_tiles < (uint64_t)num_sms ? params.n_tiles : (uint64_t)num_sms;
-    fused_pass_kernel<<<(unsigned)grid, kPassThreads, smem, stream>>>(params, tmap);
+    fused_pass_kernel<<<(unsigned)grid, kComputeThreads, smem, stream>>>(params, tmap);
     return cudaGetLastError();
 }
 

@@ -310,7 +310,7 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
         for (int q = 0; q < 64; ++q) local_of[q] = -1;
         for (int i = 0; i < pd.t; ++i) local_of[pd.tile_bits[i]] = i;
 
-        const int r = pd.t > 9 ? kMaxRegBits : std::max(0, pd.t - 5);
+        const int r = pd.t > 5 + kMaxRegBits ? kMaxRegBits : std::max(0, pd.t - 5);
         const int nthr = pd.t - r;
         const int n_lane = std::min(5, nthr);
         const int cap = n_lane + r;  // targetable positions per sweep

@@ -24,9 +24,13 @@ namespace qsim {
 namespace b200 {
 
 constexpr int kMaxTileBits = 12;         // 2^12 amplitudes * 16 B = 64 KiB per pipeline stage
-constexpr int kComputeWarps = 8;
+#ifndef QSIM_REG_BITS
+#define QSIM_REG_BITS 3                  // register bits per thread: 3 -> 16 warps x 8 amplitudes, 4 -> 8 warps x 16
+#endif
+constexpr int kMaxRegBits = QSIM_REG_BITS;
+constexpr int kSlots = 1 << kMaxRegBits;                                  // amplitudes per thread
+constexpr int kComputeWarps = 1 << (kMaxTileBits - kMaxRegBits - 5);      // a full tile is one sweep of all warps
 constexpr int kComputeThreads = kComputeWarps * 32;
-constexpr int kMaxRegBits = 4;           // 16 amplitudes (32 doubles) per thread
 constexpr int kMaxSweeps = 12;
 constexpr int kMaxSegments = 14;
 constexpr int kMaxOpsPerPass = 192;      // ops of one pass are staged in shared memory
@@ -66,6 +70,7 @@ struct alignas(16) DevOp {
 };
 static_assert(sizeof(DevOp) == 128, "DevOp layout");
 
+// (the opcode table allows register bits 0..3 whatever kMaxRegBits is)
 // opcode = kind * 10 + home * 2 + ctrl for the pair-wise kinds (home: 0 = lane, 1 + j = register bit j),
 //          40 + home * 2 + ctrl for OP_DIAG (home: 0 = register-resident target, 1 = thread/outside target)
 constexpr int kNumOpcodes = 44;
@@ -79,7 +84,7 @@ struct SweepDesc {
     uint16_t op_begin, op_end;   // indices into the pass's op array
     uint8_t r;                   // register bits in use (slots = 1 << r)
     uint8_t nthr;                // tid bits in use (active threads = 1 << nthr)
-    uint8_t thr_pos[8];          // tile-local bit position held by tid bit i
+    uint8_t thr_pos[12];         // tile-local bit position held by tid bit i
     uint8_t reg_pos[4];          // tile-local bit position held by register bit j
     uint16_t slot_off[16];       // tile-local index offset of register slot k
     uint16_t pad;
