@@ -153,14 +153,50 @@ __device__ __forceinline__ uint64_t run_offset(const PassDesc& pd, uint32_t run)
 // 16 independent dependency chains interleave (controls become selects, and ops without controls —
 // the common case — carry no predicate at all).
 
+// In-place pair updates written as PTX with read-write operands: the amplitudes stay in the registers they
+// live in across the interpreter loop (plain C++ lets the compiler rename results freely, which costs a full
+// copy of the register file per op at the loop header).
+__device__ __forceinline__ void pair_real(double& xr, double& xi, double& yr, double& yi, double m00, double m01, double m10,
+                                          double m11) {
+    asm("{\n\t.reg .f64 t0, t1, t2, t3;\n\t"
+        "mul.f64 t0, %4, %0;\n\tmul.f64 t1, %4, %1;\n\tmul.f64 t2, %6, %0;\n\tmul.f64 t3, %6, %1;\n\t"
+        "fma.rn.f64 %0, %5, %2, t0;\n\tfma.rn.f64 %1, %5, %3, t1;\n\t"
+        "fma.rn.f64 %2, %7, %2, t2;\n\tfma.rn.f64 %3, %7, %3, t3;\n\t}"
+        : "+d"(xr), "+d"(xi), "+d"(yr), "+d"(yi)
+        : "d"(m00), "d"(m01), "d"(m10), "d"(m11));
+}
+
+// x' = a*x + b*y, y' = c*x + d*y with complex a, b, c, d
+__device__ __forceinline__ void pair_complex(double& xr, double& xi, double& yr, double& yi, const DevOp& op) {
+    const double ar_ = op.m[0], ai_ = op.m[1], br_ = op.m[2], bi_ = op.m[3], cr_ = op.m[4], ci_ = op.m[5], dr_ = op.m[6], di_ = op.m[7];
+    asm("{\n\t.reg .f64 p0, p1, q0, q1, n0;\n\t"
+        "mul.f64 p0, %4, %0;\n\tmul.f64 p1, %4, %1;\n\t"          // a.re * x
+        "neg.f64 n0, %5;\n\t"
+        "fma.rn.f64 p0, n0, %1, p0;\n\tfma.rn.f64 p1, %5, %0, p1;\n\t"   // + i a.im * x
+        "fma.rn.f64 p0, %6, %2, p0;\n\tfma.rn.f64 p1, %6, %3, p1;\n\t"   // + b.re * y
+        "neg.f64 n0, %7;\n\t"
+        "fma.rn.f64 p0, n0, %3, p0;\n\tfma.rn.f64 p1, %7, %2, p1;\n\t"   // + i b.im * y
+        "mul.f64 q0, %8, %0;\n\tmul.f64 q1, %8, %1;\n\t"
+        "neg.f64 n0, %9;\n\t"
+        "fma.rn.f64 q0, n0, %1, q0;\n\tfma.rn.f64 q1, %9, %0, q1;\n\t"
+        "fma.rn.f64 q0, %10, %2, q0;\n\tfma.rn.f64 q1, %10, %3, q1;\n\t"
+        "neg.f64 n0, %11;\n\t"
+        "fma.rn.f64 q0, n0, %3, q0;\n\tfma.rn.f64 q1, %11, %2, q1;\n\t"
+        "mov.f64 %0, p0;\n\tmov.f64 %1, p1;\n\tmov.f64 %2, q0;\n\tmov.f64 %3, q1;\n\t}"
+        : "+d"(xr), "+d"(xi), "+d"(yr), "+d"(yi)
+        : "d"(ar_), "d"(ai_), "d"(br_), "d"(bi_), "d"(cr_), "d"(ci_), "d"(dr_), "d"(di_));
+}
+
 template <int J, int KIND, bool CTRL>
 __device__ __forceinline__ void reg_pairs(const DevOp& op, uint32_t sm, double (&ar)[kSlots], double (&ai)[kSlots]) {
-    const double m00r = op.m[0], m00i = op.m[1], m01r = op.m[2], m01i = op.m[3];
-    const double m10r = op.m[4], m10i = op.m[5], m11r = op.m[6], m11i = op.m[7];
+    const double m00r = op.m[0], m01r = op.m[2], m01i = op.m[3];
+    const double m10r = op.m[4], m10i = op.m[5], m11r = op.m[6];
 #pragma unroll
     for (int k = 0; k < kSlots; ++k) {
         if (k & (1 << J)) continue;   // compile-time: k enumerates the slots whose target bit is 0
         const int k1 = k | (1 << J);
+        if (!CTRL && KIND == OP_MATREAL) { pair_real(ar[k], ai[k], ar[k1], ai[k1], m00r, m01r, m10r, m11r); continue; }
+        if (!CTRL && KIND == OP_MAT) { pair_complex(ar[k], ai[k], ar[k1], ai[k1], op); continue; }
         const double xr = ar[k], xi = ai[k], yr = ar[k1], yi = ai[k1];
         double n0r, n0i, n1r, n1i;
         if (KIND == OP_FLIP) {
@@ -172,6 +208,7 @@ __device__ __forceinline__ void reg_pairs(const DevOp& op, uint32_t sm, double (
             n0r = m00r * xr + m01r * yr; n0i = m00r * xi + m01r * yi;
             n1r = m10r * xr + m11r * yr; n1i = m10r * xi + m11r * yi;
         } else {
+            const double m00i = op.m[1], m11i = op.m[7];
             n0r = m00r * xr - m00i * xi + m01r * yr - m01i * yi;
             n0i = m00r * xi + m00i * xr + m01r * yi + m01i * yr;
             n1r = m10r * xr - m10i * xi + m11r * yr - m11i * yi;
@@ -310,18 +347,21 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
     unsigned char* const gstate = reinterpret_cast<unsigned char*>(P.state);
 
     // ---- TMA duties of the elected thread --------------------------------------------------------------
+    // (executed by every lane of warp 0: lane q issues instruction q, q+32, ...)
+    const uint32_t lane = tid & 31u;
     auto issue_load = [&](uint64_t i) {
         const int s = (int)(i % n_stages);
         const uint64_t base = tile_base(pd, tile_of(i));
-        mbar_expect_tx(&full[s], tile_bytes);
+        if (lane == 0) mbar_expect_tx(&full[s], tile_bytes);
+        __syncwarp();
         if (P.use_tensor_map) {
-            for (uint32_t q = 0; q < n_instr; ++q) {
+            for (uint32_t q = lane; q < n_instr; q += 32) {
                 int c[5];
                 tma_coords(pd, base + instr_offset(pd, q), c);
                 tma_load_5d(tiles + (size_t)s * tile_bytes + (size_t)q * box_bytes, &tmap, c, &full[s]);
             }
         } else {
-            for (uint32_t run = 0; run < n_runs; ++run) {
+            for (uint32_t run = lane; run < n_runs; run += 32) {
                 const uint64_t g = base + run_offset(pd, run);
                 tma_load_1d(tiles + (size_t)s * tile_bytes + (size_t)run * run_bytes, gstate + g * 16, run_bytes, &full[s]);
             }
@@ -336,21 +376,21 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
         }
         const uint64_t base = tile_base(pd, tile_of(i) ^ xor_tau);
         if (P.use_tensor_map) {
-            for (uint32_t q = 0; q < n_instr; ++q) {
+            for (uint32_t q = lane; q < n_instr; q += 32) {
                 int c[5];
                 tma_coords(pd, base + instr_offset(pd, q), c);
                 tma_store_5d(&tmap, c, tiles + (size_t)s * tile_bytes + (size_t)q * box_bytes);
             }
         } else {
-            for (uint32_t run = 0; run < n_runs; ++run) {
+            for (uint32_t run = lane; run < n_runs; run += 32) {
                 const uint64_t g = base + run_offset(pd, run);
                 tma_store_1d(gstate + g * 16, tiles + (size_t)s * tile_bytes + (size_t)run * run_bytes, run_bytes);
             }
         }
-        tma_store_commit();
+        tma_store_commit();   // every lane commits its own (possibly empty) bulk group
     };
 
-    if (tid == 0) {
+    if (warp == 0) {
         const uint64_t pre = n_my < (uint64_t)n_stages ? n_my : (uint64_t)n_stages;
         for (uint64_t i = 0; i < pre; ++i) issue_load(i);
     }
@@ -433,15 +473,16 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
         // this tile and refills the stage whose store (tile i-1) has drained
         fence_proxy_async();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             issue_store(i);
             if (i >= 1 && (i - 1) + (uint64_t)n_stages < n_my) {
-                tma_store_wait_read_1();   // all but the newest store group have finished reading shared memory
+                tma_store_wait_read_1();   // all but this lane's newest store group have finished reading shared memory
+                __syncwarp();              // ... for every lane: the stage of tile i-1 is free
                 issue_load((i - 1) + (uint64_t)n_stages);
             }
         }
     }
-    if (tid == 0) tma_store_wait_all();
+    if (warp == 0) tma_store_wait_all();
 }
 
 size_t pass_smem_bytes(const PassDesc& pd, int stages) {
