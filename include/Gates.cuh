@@ -1,0 +1,3 @@
+// Forwarding header: keeps the reference's include name for drop-in callers.
+#pragma once
+#include "qsim/gates.cuh"
