@@ -307,7 +307,7 @@ def main():
                                f"({16 * (1 << n_local) / 2**30:.0f} GiB per GPU)",
                    "gates": n_gates, "passes": n_passes, "global_qubit_swaps": n_swaps, "qubits": n,
                    "local_qubits": n_local, "parallelism": f"shard top {n_global} qubits over {world} GPU(s)",
-                   "l2": "state (16 GiB/GPU) is far larger than the 126 MB L2: no flush needed",
+                   "l2": f"state ({16 * (1 << n_local) / 2**30:.0f} GiB/GPU) is far larger than the 126 MB L2: no flush needed",
                    "gates_per_s_raw": n_gates / (ms_per_step * 1e-3)},
         "roofline": {"bound": "hbm", "kernel": "fused_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,

@@ -24,6 +24,8 @@ void require_device() {
 
 DeviceProgram::~DeviceProgram() {
     if (d_ops) cudaFree(d_ops);
+    if (d_tables) cudaFree(d_tables);
+    if (d_terms) cudaFree(d_terms);
 }
 
 void DeviceProgram::upload() {
@@ -32,6 +34,16 @@ void DeviceProgram::upload() {
     if (host.ops.empty()) return;
     CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_ops), host.ops.size() * sizeof(DevOp)));
     CUDA_CHECK(cudaMemcpy(d_ops, host.ops.data(), host.ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice));
+    if (d_tables) { cudaFree(d_tables); d_tables = nullptr; }
+    if (d_terms) { cudaFree(d_terms); d_terms = nullptr; }
+    if (!host.phase_tables.empty()) {
+        CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_tables), host.phase_tables.size() * sizeof(double)));
+        CUDA_CHECK(cudaMemcpy(d_tables, host.phase_tables.data(), host.phase_tables.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (!host.phase_terms.empty()) {
+        CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_terms), host.phase_terms.size() * sizeof(PhaseTerm)));
+        CUDA_CHECK(cudaMemcpy(d_terms, host.phase_terms.data(), host.phase_terms.size() * sizeof(PhaseTerm), cudaMemcpyHostToDevice));
+    }
 }
 
 Engine::Engine() {
@@ -51,6 +63,7 @@ Engine::Engine() {
 
 Engine::~Engine() {
     for (void* p : scratch_) if (p) cudaFree(p);
+    if (d_aux_) cudaFree(d_aux_);
     if (d_ops_) cudaFree(d_ops_);
     if (h_ops_) cudaFreeHost(h_ops_);
     if (staged_) cudaEventDestroy(staged_);
@@ -101,11 +114,14 @@ void Engine::drainTiming(double* total_ms, int64_t* n_passes, std::vector<double
     events_.clear();
 }
 
-void Engine::launchAll(const Program& p, const DevOp* d_ops, cuDoubleComplex* state, uint64_t hi_bits) {
+void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tables, const PhaseTerm* d_terms,
+                       cuDoubleComplex* state, uint64_t hi_bits) {
     for (const PassDesc& pd : p.passes) {
         PassParams prm;
         prm.state = state;
         prm.ops = d_ops + pd.op_offset;
+        prm.phase_tables = d_tables ? reinterpret_cast<const double2*>(d_tables) + pd.phase_table_offset : nullptr;
+        prm.phase_terms = d_terms ? d_terms + pd.phase_term_offset : nullptr;
         prm.hi_bits = hi_bits;
         prm.n_tiles = 1ULL << (pd.n - pd.t);
         prm.pd = pd;
@@ -130,7 +146,7 @@ void Engine::execute(const Program& p, cuDoubleComplex* state, uint64_t hi_bits)
     const size_t n = p.ops.size();
     if (p.passes.empty()) return;
     if (n == 0) {   // passes without ops exist: a pure index permutation (deferred X gates)
-        launchAll(p, nullptr, state, hi_bits);
+        launchAll(p, nullptr, nullptr, nullptr, state, hi_bits);
         return;
     }
     if (staged_pending_) {           // the pinned buffer may still be in flight from the previous run
@@ -156,13 +172,30 @@ void Engine::execute(const Program& p, cuDoubleComplex* state, uint64_t hi_bits)
     CUDA_CHECK(cudaMemcpyAsync(d_ops_, h_ops_, n * sizeof(DevOp), cudaMemcpyHostToDevice, stream_));
     CUDA_CHECK(cudaEventRecord(staged_, stream_));
     staged_pending_ = true;
-    launchAll(p, d_ops_, state, hi_bits);
+    // fused diagonal runs: tables and terms ride along (synchronous copy from pageable memory: the driver stages
+    // it before returning; these programs are rare and the blob is small next to the state)
+    const double* d_tables = nullptr;
+    const PhaseTerm* d_terms = nullptr;
+    const size_t tb = p.phase_tables.size() * sizeof(double), tt = p.phase_terms.size() * sizeof(PhaseTerm);
+    if (tb + tt > 0) {
+        const size_t tb_pad = (tb + 255) & ~size_t(255);
+        if (tb_pad + tt > d_aux_cap_) {
+            if (d_aux_) { CUDA_CHECK(cudaStreamSynchronize(stream_)); cudaFree(d_aux_); d_aux_ = nullptr; }
+            d_aux_cap_ = (tb_pad + tt) * 2 + 4096;
+            CUDA_CHECK(cudaMalloc(&d_aux_, d_aux_cap_));
+        }
+        if (tb) CUDA_CHECK(cudaMemcpyAsync(d_aux_, p.phase_tables.data(), tb, cudaMemcpyHostToDevice, stream_));
+        if (tt) CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(d_aux_) + tb_pad, p.phase_terms.data(), tt, cudaMemcpyHostToDevice, stream_));
+        d_tables = static_cast<const double*>(d_aux_);
+        d_terms = tt ? reinterpret_cast<const PhaseTerm*>(static_cast<char*>(d_aux_) + tb_pad) : nullptr;
+    }
+    launchAll(p, d_ops_, d_tables, d_terms, state, hi_bits);
 }
 
 void Engine::execute(const DeviceProgram& p, cuDoubleComplex* state, uint64_t hi_bits) {
     if (p.host.passes.empty()) return;
     if (!p.d_ops && !p.host.ops.empty()) throw std::runtime_error("qsim_b200: program was not uploaded");
-    launchAll(p.host, p.d_ops, state, hi_bits);
+    launchAll(p.host, p.d_ops, p.d_tables, p.d_terms, state, hi_bits);
 }
 
 }  // namespace b200

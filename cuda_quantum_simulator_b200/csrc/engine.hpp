@@ -19,6 +19,8 @@ namespace b200 {
 struct DeviceProgram {
     Program host;
     DevOp* d_ops = nullptr;
+    double* d_tables = nullptr;       // OP_PHASE tables
+    PhaseTerm* d_terms = nullptr;     // OP_PHASE terms
     ~DeviceProgram();
     DeviceProgram() = default;
     DeviceProgram(const DeviceProgram&) = delete;
@@ -74,7 +76,11 @@ private:
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events_;
     std::vector<cudaEvent_t> pool_;
 
-    void launchAll(const Program& p, const DevOp* d_ops, cuDoubleComplex* state, uint64_t hi_bits);
+    void launchAll(const Program& p, const DevOp* d_ops, const double* d_tables, const PhaseTerm* d_terms,
+                   cuDoubleComplex* state, uint64_t hi_bits);
+    // staging of the phase tables / terms of execute(const Program&)
+    void* d_aux_ = nullptr;
+    size_t d_aux_cap_ = 0;
     cudaEvent_t getEvent();
 };
 

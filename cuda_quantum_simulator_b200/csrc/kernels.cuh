@@ -16,6 +16,8 @@ constexpr int kMaxDynamicSmem = 227 * 1024;
 struct PassParams {
     cuDoubleComplex* state;   // this GPU's amplitudes (2^pd.n of them)
     const DevOp* ops;         // device copy of this pass's ops
+    const double2* phase_tables;    // this pass's OP_PHASE tables (kPhaseTableSize entries each)
+    const PhaseTerm* phase_terms;   // this pass's OP_PHASE outside-bit terms
     uint64_t hi_bits;         // rank << n_local for a sharded state, else 0 (only used by controls)
     uint64_t n_tiles;         // 2^(pd.n - pd.t)
     int32_t stages;           // depth of the shared-memory ring

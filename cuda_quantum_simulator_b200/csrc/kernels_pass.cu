@@ -280,6 +280,51 @@ __device__ __forceinline__ void diagonal(const DevOp& op, uint32_t sm, uint32_t 
     }
 }
 
+// A fused run of diagonal gates: amplitude(l) *= TABLE[l] * U * prod_{tile bits j of l} E_j.
+__device__ __forceinline__ void phase_op(const DevOp& op, const double2* __restrict__ tables, const double2* eu,
+                                         const SweepDesc& sd, uint32_t tid, uint32_t base_local, double (&ar)[kSlots],
+                                         double (&ai)[kSlots]) {
+    const double2* tb = tables + op.cmask_out;
+    double2 f[kSlots];
+#pragma unroll
+    for (int k = 0; k < kSlots; ++k) f[k] = __ldg(tb + base_local + sd.slot_off[k]);
+    if (op.tslots != 0) {   // some factor depends on bits outside the tile
+        const double2* e = eu + (size_t)op.tmask_out * 13;
+        double pr = e[12].x, pi = e[12].y;   // U, then the thread-resident tile bits
+#pragma unroll
+        for (int b = 0; b < kMaxTileBits - kMaxRegBits; ++b) {
+            if (b < sd.nthr && ((tid >> b) & 1)) {
+                const double2 v = e[sd.thr_pos[b]];
+                const double r = pr * v.x - pi * v.y;
+                pi = pr * v.y + pi * v.x;
+                pr = r;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kSlots; ++k) {
+            double qr = pr, qi = pi;
+#pragma unroll
+            for (int j = 0; j < kMaxRegBits; ++j) {
+                if (j < sd.r && ((k >> j) & 1)) {
+                    const double2 v = e[sd.reg_pos[j]];
+                    const double r = qr * v.x - qi * v.y;
+                    qi = qr * v.y + qi * v.x;
+                    qr = r;
+                }
+            }
+            const double r = f[k].x * qr - f[k].y * qi;
+            f[k].y = f[k].x * qi + f[k].y * qr;
+            f[k].x = r;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kSlots; ++k) {
+        const double xr = ar[k], xi = ai[k];
+        ar[k] = xr * f[k].x - xi * f[k].y;
+        ai[k] = xr * f[k].y + xi * f[k].x;
+    }
+}
+
 #define QSIM_PAIR_CASES(KIND)                                                          \
     case (KIND) * 10 + 0: lane_target<KIND, false>(op, 0xffffu, tid, ar, ai); break;   \
     case (KIND) * 10 + 1: lane_target<KIND, true>(op, sm, tid, ar, ai); break;         \
@@ -302,7 +347,8 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
     unsigned char* tiles = smem;
     const int n_stages = P.stages;
     DevOp* sops = reinterpret_cast<DevOp*>(smem + (size_t)n_stages * tile_bytes);
-    uint64_t* full = reinterpret_cast<uint64_t*>(sops + pd.n_ops + 1);   // +1: zeroed padding record (prefetch)
+    double2* eu = reinterpret_cast<double2*>(sops + pd.n_ops + 1);       // (E_0..E_11, U) of every OP_PHASE, per tile
+    uint64_t* full = reinterpret_cast<uint64_t*>(eu + (size_t)pd.n_phase * 13);
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
 
@@ -401,6 +447,26 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
         const uint32_t parity = (uint32_t)((i / n_stages) & 1);
         const uint64_t gbase = tile_base(pd, tile_of(i)) | P.hi_bits;
         unsigned char* tile = tiles + (size_t)s * tile_bytes;
+        if (pd.n_phase > 0) {
+            // factors of the fused diagonal runs that depend on index bits outside the tile: one (op, factor) per thread
+            __syncthreads();   // the previous tile's readers of eu are done
+            for (int idx = (int)tid; idx < pd.n_ops * 13; idx += kComputeThreads) {
+                const int o = idx / 13, e = idx - o * 13;
+                const DevOp& op = sops[o];
+                if (op.kind != OP_PHASE) continue;
+                const uint16_t* starts = reinterpret_cast<const uint16_t*>(op.m);
+                const PhaseTerm* terms = P.phase_terms + op.cval_out;
+                double fr = 1.0, fi = 0.0;
+                for (int k = starts[e]; k < starts[e + 1]; ++k) {
+                    const PhaseTerm t = terms[k];
+                    bool on = (gbase >> t.o) & 1;
+                    if (t.kind == 2) on = on && ((gbase >> t.j) & 1);
+                    if (on) { const double r = fr * t.fr - fi * t.fi; fi = fr * t.fi + fi * t.fr; fr = r; }
+                }
+                eu[(size_t)op.tmask_out * 13 + e] = make_double2(fr, fi);
+            }
+            __syncthreads();
+        }
         mbar_wait(&full[s], parity);
 
 #pragma unroll 1
@@ -452,6 +518,7 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
                     QSIM_PAIR_CASES(OP_ADIAG)
                     QSIM_PAIR_CASES(OP_FLIP)
                     case 40: case 42: diagonal<false>(op, 0xffffu, tid, gbase, ar, ai); break;
+                    case 44: phase_op(op, P.phase_tables, eu, sd, tid, base_local, ar, ai); break;
                     default: diagonal<true>(op, sm, tid, gbase, ar, ai); break;
                 }
             }
@@ -486,7 +553,8 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
 }
 
 size_t pass_smem_bytes(const PassDesc& pd, int stages) {
-    return (size_t)stages * ((size_t)16 << pd.t) + ((size_t)pd.n_ops + 1) * sizeof(DevOp) + 2 * (size_t)stages * sizeof(uint64_t);
+    return (size_t)stages * ((size_t)16 << pd.t) + ((size_t)pd.n_ops + 1) * sizeof(DevOp) + (size_t)pd.n_phase * 13 * sizeof(double2) +
+           2 * (size_t)stages * sizeof(uint64_t);
 }
 
 // Deepest ring that fits the 227 KiB of shared memory (at most kMaxStages).

@@ -51,7 +51,7 @@ void matmul(const double* b, const double* a, double* out) {
     std::memcpy(out, tmp, sizeof(tmp));
 }
 
-inline bool is_diag_kind(uint8_t k) { return k == OP_DIAG; }
+inline bool is_diag_kind(uint8_t k) { return k == OP_DIAG || k == OP_PHASE; }
 
 inline uint64_t qubits_of(const LogicalOp& o) { return o.cmask | (1ULL << o.target); }
 
@@ -76,6 +76,7 @@ CompileOptions default_options() {
     if (const char* e = std::getenv("QSIM_MIN_LOW_BITS")) { int v = std::atoi(e); if (v >= 3 && v <= kMaxTileBits) o.min_low_bits = v; }
     if (std::getenv("QSIM_NO_MERGE")) o.merge = false;
     if (std::getenv("QSIM_NO_REORDER")) o.reorder = false;
+    if (std::getenv("QSIM_NO_PHASE")) o.fuse_diagonals = false;
     return o;
 }
 
@@ -233,6 +234,108 @@ void choose_tile_bits(uint64_t need, int n_local, int t, int lmin, PassDesc& pd)
 
 }  // namespace
 
+namespace {
+
+struct Cx {
+    double r, i;
+};
+inline Cx cmul(Cx a, Cx b) { return {a.r * b.r - a.i * b.i, a.r * b.i + a.i * b.r}; }
+inline Cx cdiv(Cx a, Cx b) {
+    const double d = b.r * b.r + b.i * b.i;
+    return {(a.r * b.r + a.i * b.i) / d, (a.i * b.r - a.r * b.i) / d};
+}
+
+// Turns a run of diagonal ops into the multiplicative degree-2 polynomial  f = C * prod A_q^{b_q} * prod B_pq^{b_p b_q}
+// and splits it by where the bits live: inside-only terms go to a table over the tile-local index, terms that involve
+// bits outside the tile become PhaseTerm records evaluated once per tile.
+void encode_phase(Program& out, PassDesc& pd, const std::vector<int>& members, const int* local_of, int nl, DevOp& d) {
+    Cx C{1, 0};
+    std::vector<Cx> A(64, Cx{1, 0});
+    std::vector<std::pair<std::pair<int, int>, Cx>> B;   // ((p, q), factor), p < q
+    auto addB = [&](int p, int q, Cx f) {
+        if (p > q) std::swap(p, q);
+        for (auto& e : B)
+            if (e.first.first == p && e.first.second == q) { e.second = cmul(e.second, f); return; }
+        B.push_back({{p, q}, f});
+    };
+    for (int mi : members) {
+        const LogicalOp& op = out.lops[mi];
+        const Cx d0{op.m[0], op.m[1]}, d1{op.m[6], op.m[7]};
+        const int t = op.target;
+        if (op.cmask == 0) {                       // factor d0 * (d1/d0)^{b_t}
+            C = cmul(C, d0);
+            A[t] = cmul(A[t], cdiv(d1, d0));
+        } else {
+            const int c = __builtin_ctzll(op.cmask);
+            if ((op.cval >> c) & 1) {              // active when b_c = 1: [d0 (d1/d0)^{b_t}]^{b_c}
+                A[c] = cmul(A[c], d0);
+                addB(c, t, cdiv(d1, d0));
+            } else {                               // active when b_c = 0: d0 (d1/d0)^{b_t} * [d0^-1 (d0/d1)^{b_t}]^{b_c}
+                C = cmul(C, d0);
+                A[t] = cmul(A[t], cdiv(d1, d0));
+                A[c] = cmul(A[c], cdiv(Cx{1, 0}, d0));
+                addB(c, t, cdiv(d0, d1));
+            }
+        }
+    }
+    auto inside = [&](int q) { return q < nl && local_of[q] >= 0; };
+    // table over the tile-local index: C, inside singles, inside-inside pairs
+    const size_t base = out.phase_tables.size();
+    out.phase_tables.resize(base + 2 * (size_t)kPhaseTableSize);
+    const uint32_t n_entries = 1u << pd.t;
+    for (uint32_t l = 0; l < (uint32_t)kPhaseTableSize; ++l) {
+        Cx f{1, 0};
+        if (l < n_entries) {
+            f = C;
+            for (int q = 0; q < 64; ++q)
+                if (inside(q) && ((l >> local_of[q]) & 1) && (A[q].r != 1.0 || A[q].i != 0.0)) f = cmul(f, A[q]);
+            for (auto& e : B) {
+                const int p = e.first.first, q = e.first.second;
+                if (inside(p) && inside(q) && ((l >> local_of[p]) & 1) && ((l >> local_of[q]) & 1)) f = cmul(f, e.second);
+            }
+        }
+        out.phase_tables[base + 2 * l] = f.r;
+        out.phase_tables[base + 2 * l + 1] = f.i;
+    }
+    // terms with outside bits, grouped by the factor they feed: E_0..E_11, then U
+    std::vector<std::vector<PhaseTerm>> groups(13);
+    auto term = [&](int kind, int o, int j, Cx f) {
+        PhaseTerm t{};
+        t.kind = (uint8_t)kind; t.o = (uint8_t)o; t.j = (uint8_t)j; t.fr = f.r; t.fi = f.i;
+        return t;
+    };
+    for (int q = 0; q < 64; ++q)
+        if (!inside(q) && (A[q].r != 1.0 || A[q].i != 0.0)) groups[12].push_back(term(1, q, 0, A[q]));
+    for (auto& e : B) {
+        const int p = e.first.first, q = e.first.second;
+        const bool ip = inside(p), iq = inside(q);
+        if (ip && iq) continue;
+        if (!ip && !iq) groups[12].push_back(term(2, p, q, e.second));
+        else if (ip) groups[local_of[p]].push_back(term(0, q, local_of[p], e.second));
+        else groups[local_of[q]].push_back(term(0, p, local_of[q], e.second));
+    }
+    const size_t first_term = out.phase_terms.size();
+    uint16_t starts[14];
+    size_t cursor = 0;
+    for (int e = 0; e < 13; ++e) {
+        starts[e] = (uint16_t)cursor;
+        for (auto& t : groups[e]) out.phase_terms.push_back(t);
+        cursor += groups[e].size();
+    }
+    starts[13] = (uint16_t)cursor;
+    d.kind = OP_PHASE;
+    d.opcode = kOpcodePhase;
+    d.slotmask = 0xffff;
+    d.tslots = (uint16_t)cursor;                                              // number of terms
+    d.cmask_out = (uint64_t)(base / 2) - (uint64_t)pd.phase_table_offset;     // table entry offset within the pass
+    d.cval_out = (uint64_t)first_term - (uint64_t)pd.phase_term_offset;      // first term within the pass
+    d.tmask_out = (uint64_t)pd.n_phase;                                       // shared-memory slot of (E, U)
+    std::memcpy(d.m, starts, sizeof(starts));
+    pd.n_phase++;
+}
+
+}  // namespace
+
 bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& opt, Program& out, std::string* error) {
     auto fail = [&](const std::string& s) { if (error) *error = s; return false; };
     out = Program();
@@ -331,6 +434,55 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
             pd.xor_tau = tau_bit;
         }
 
+        // Fuse runs of diagonal gates (each with at most one control and no zero entry) into OP_PHASE ops:
+        // a diagonal op may slide back to the open run as long as nothing emitted since the run started has its
+        // non-diagonal target among the op's qubits.
+        std::vector<std::vector<int>> clusters;   // members (indices into out.lops) of each fused run
+        if (opt.fuse_diagonals) {
+            auto eligible = [&](const LogicalOp& op) {
+                if (op.kind != OP_DIAG || __builtin_popcountll(op.cmask) > 1) return false;
+                return (op.m[0] != 0.0 || op.m[1] != 0.0) && (op.m[6] != 0.0 || op.m[7] != 0.0);
+            };
+            std::vector<int> order;               // >= 0: op index, < 0: -(cluster id) - 1
+            int open = -1;
+            uint64_t blocked = 0;                 // non-diagonal targets emitted since the open run started
+            for (int idx : plan.op_idx) {
+                const LogicalOp& op = out.lops[idx];
+                if (eligible(op)) {
+                    if (open >= 0 && (qubits_of(op) & blocked) == 0) { clusters[open].push_back(idx); continue; }
+                    if ((int)clusters.size() < kMaxPhaseOps) {
+                        open = (int)clusters.size();
+                        clusters.push_back({idx});
+                        blocked = 0;
+                        order.push_back(-open - 1);
+                        continue;
+                    }
+                }
+                order.push_back(idx);
+                if (!is_diag_kind(op.kind)) blocked |= 1ULL << op.target;
+            }
+            std::vector<int> rebuilt;
+            for (int item : order) {
+                if (item >= 0) { rebuilt.push_back(item); continue; }
+                const std::vector<int>& mem = clusters[-item - 1];
+                if (mem.size() < 3) { for (int m : mem) rebuilt.push_back(m); continue; }   // not worth a table
+                LogicalOp ph{};
+                ph.kind = OP_PHASE;
+                uint64_t qs = 0;
+                for (int m : mem) qs |= qubits_of(out.lops[m]);
+                ph.target = __builtin_ctzll(qs);
+                ph.cmask = qs & ~(1ULL << ph.target);   // qubits_of(ph) == every qubit of the run
+                ph.cval = ph.cmask;
+                ph.first_gate = -item - 1;              // cluster id
+                ph.n_gates = (int)mem.size();
+                out.lops.push_back(ph);
+                rebuilt.push_back((int)out.lops.size() - 1);
+            }
+            plan.op_idx.swap(rebuilt);
+        }
+        pd.phase_table_offset = (int)(out.phase_tables.size() / 2);
+        pd.phase_term_offset = (int)out.phase_terms.size();
+
         std::vector<int> todo = plan.op_idx;
         bool need_empty_sweep = todo.empty();
         while (!todo.empty() || need_empty_sweep) {
@@ -409,6 +561,12 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
                 const LogicalOp& op = out.lops[idx];
                 DevOp d{};
                 d.kind = op.kind;
+                if (op.kind == OP_PHASE) {
+                    encode_phase(out, pd, clusters[op.first_gate], local_of, nl, d);
+                    out.ops.push_back(d);
+                    pd.n_ops++;
+                    continue;
+                }
                 std::memcpy(d.m, op.m, sizeof(op.m));
                 uint32_t reg_cmask = 0, reg_cval = 0;
                 for (int q = 0; q < 64; ++q) {
@@ -475,7 +633,7 @@ std::string Program::describe() const {
     for (auto& p : passes) sweeps += p.n_sweeps;
     os << "program: " << n << " qubits (" << n_local << " local), " << n_gates << " gates -> " << lops.size()
        << " ops, " << passes.size() << " passes, " << sweeps << " sweeps\n";
-    static const char* kn[] = {"MAT", "MATREAL", "ADIAG", "FLIP", "DIAG"};
+    static const char* kn[] = {"MAT", "MATREAL", "ADIAG", "FLIP", "DIAG", "PHASE"};
     for (size_t i = 0; i < passes.size(); ++i) {
         const PassDesc& p = passes[i];
         os << "  pass " << i << ": t=" << p.t << " L=" << p.L << " tile_bits=[";

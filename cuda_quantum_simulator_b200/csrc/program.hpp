@@ -33,7 +33,9 @@ constexpr int kComputeWarps = 1 << (kMaxTileBits - kMaxRegBits - 5);      // a f
 constexpr int kComputeThreads = kComputeWarps * 32;
 constexpr int kMaxSweeps = 12;
 constexpr int kMaxSegments = 14;
-constexpr int kMaxOpsPerPass = 192;      // ops of one pass are staged in shared memory
+constexpr int kMaxOpsPerPass = 160;      // ops of one pass are staged in shared memory
+constexpr int kMaxPhaseOps = 24;         // fused diagonal runs per pass (13 complex factors each in shared memory)
+constexpr int kPhaseTableSize = 1 << kMaxTileBits;   // one complex factor per tile-local index
 
 enum OpKind : uint8_t {
     OP_MAT = 0,      // dense complex 2x2
@@ -41,6 +43,8 @@ enum OpKind : uint8_t {
     OP_ADIAG = 2,    // anti-diagonal [[0,b],[c,0]] (Y, X*diag)
     OP_FLIP = 3,     // bit flip (X / CNOT / Toffoli): pure data movement
     OP_DIAG = 4,     // diagonal diag(d0, d1): phase by target bit, target may live anywhere
+    OP_PHASE = 5,    // a fused RUN of diagonal gates (<= 1 control each): one complex factor per amplitude,
+                     //   f(idx) = TABLE[tile-local idx] * U(tile) * prod_{tile bits j set} E_j(tile)
 };
 
 enum TargetHome : uint8_t {
@@ -73,12 +77,26 @@ static_assert(sizeof(DevOp) == 128, "DevOp layout");
 // (the opcode table allows register bits 0..3 whatever kMaxRegBits is)
 // opcode = kind * 10 + home * 2 + ctrl for the pair-wise kinds (home: 0 = lane, 1 + j = register bit j),
 //          40 + home * 2 + ctrl for OP_DIAG (home: 0 = register-resident target, 1 = thread/outside target)
-constexpr int kNumOpcodes = 44;
+constexpr int kNumOpcodes = 45;
+constexpr uint8_t kOpcodePhase = 44;
 inline uint8_t op_code(uint8_t kind, uint8_t thome, uint8_t tbit, bool ctrl) {
     if (kind == OP_DIAG) return (uint8_t)(40 + (thome == T_REG ? 0 : 2) + (ctrl ? 1 : 0));
     const int home = thome == T_LANE ? 0 : 1 + tbit;
     return (uint8_t)(kind * 10 + home * 2 + (ctrl ? 1 : 0));
 }
+
+// OP_PHASE records reuse DevOp fields: cmask_out = first entry of the op's table in the pass's table blob,
+// cval_out = first term in the pass's term array, tmask_out = slot of its (E_0..E_11, U) factors in shared
+// memory, tslots = number of terms; m[] viewed as uint16[14]: term range start of E_0..E_11, U, end.
+// A term multiplies one of those 13 factors when one (kind 0/1) or two (kind 2) index bits OUTSIDE the tile are set.
+struct PhaseTerm {
+    uint8_t kind;     // 0: E_j *= f if bit o;  1: U *= f if bit o;  2: U *= f if bits o and j
+    uint8_t o;        // global index bit (may be a rank bit of a sharded state)
+    uint8_t j;        // kind 0: tile-local bit; kind 2: the second global bit
+    uint8_t pad[5];
+    double fr, fi;
+};
+static_assert(sizeof(PhaseTerm) == 24, "PhaseTerm layout");
 
 struct SweepDesc {
     uint16_t op_begin, op_end;   // indices into the pass's op array
@@ -112,6 +130,10 @@ struct PassDesc {
     int32_t op_offset;           // into Program::ops
     int32_t n_segments;
     int32_t n_high;              // t - L
+    int32_t n_phase;             // OP_PHASE ops in this pass
+    int32_t phase_table_offset;  // into Program::phase_tables (entries)
+    int32_t phase_term_offset;   // into Program::phase_terms
+    int32_t pad2;
     uint8_t tile_bits[kMaxTileBits];   // global bit of tile-local bit i (ascending)
     uint32_t xor_local;          // tile-local index XOR applied by the pass's final store (deferred X gates)
     uint64_t xor_tau;            // tile-number XOR: the tile read from tau is written to tau ^ xor_tau
@@ -137,6 +159,7 @@ struct CompileOptions {
     bool merge = true;           // merge runs of gates on the same (target, controls)
     bool reorder = true;         // commute ops across passes when legal (fewer passes)
     int n_global = 0;            // qubits >= n - n_global live in the rank id (sharded state)
+    bool fuse_diagonals = true;  // runs of >= 3 diagonal gates become one OP_PHASE
     bool defer_x = true;         // carry uncontrolled X gates as an index-XOR frame, folded into the last pass's addressing
     uint64_t initial_xor = 0;    // X frame inherited from earlier segments (sharded driver: pending flips of global qubits)
 };
@@ -147,6 +170,8 @@ struct Program {
     std::vector<LogicalOp> lops; // after merging
     std::vector<DevOp> ops;      // encoded, pass-major
     std::vector<PassDesc> passes;
+    std::vector<double> phase_tables;      // (re, im) pairs, kPhaseTableSize entries per OP_PHASE
+    std::vector<PhaseTerm> phase_terms;
     int64_t n_gates = 0;
     uint64_t global_xor = 0;     // X frame left on global qubits (bit q - n_local): a rank relabelling the caller owns
     std::string describe() const;

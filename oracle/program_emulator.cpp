@@ -65,6 +65,22 @@ void run_pass(const Program& prog, const PassDesc& pd, uint64_t hi_bits, cplx* s
                 }
             }
         }
+        // per-tile factors of the fused diagonal runs (what the kernel's tile prologue computes)
+        std::vector<cplx> eu((size_t)pd.n_phase * 13, cplx(1, 0));
+        for (int o = 0; o < pd.n_ops; ++o) {
+            const DevOp& op = ops[o];
+            if (op.kind != OP_PHASE) continue;
+            uint16_t starts[14];
+            std::memcpy(starts, op.m, sizeof(starts));
+            const PhaseTerm* terms = prog.phase_terms.data() + pd.phase_term_offset + op.cval_out;
+            for (int e = 0; e < 13; ++e)
+                for (int k = starts[e]; k < starts[e + 1]; ++k) {
+                    const PhaseTerm& t = terms[k];
+                    bool on = (gbase >> t.o) & 1;
+                    if (t.kind == 2) on = on && ((gbase >> t.j) & 1);
+                    if (on) eu[op.tmask_out * 13 + e] *= cplx(t.fr, t.fi);
+                }
+        }
         for (int sw = 0; sw < pd.n_sweeps; ++sw) {
             const SweepDesc& sd = pd.sweep[sw];
             const int slots = 1 << sd.r;
@@ -85,7 +101,7 @@ void run_pass(const Program& prog, const PassDesc& pd, uint64_t hi_bits, cplx* s
                 }
                 for (int o = sd.op_begin; o < sd.op_end; ++o) {
                     const DevOp& op = ops[o];
-                    if ((gbase & op.cmask_out) != op.cval_out) continue;
+                    if (op.kind != OP_PHASE && (gbase & op.cmask_out) != op.cval_out) continue;   // (PHASE reuses these fields)
                     const cplx m00(op.m[0], op.m[1]), m01(op.m[2], op.m[3]), m10(op.m[4], op.m[5]), m11(op.m[6], op.m[7]);
                     cplx nxt[32][16];
                     for (int lane = 0; lane < 32; ++lane) {
@@ -94,7 +110,14 @@ void run_pass(const Program& prog, const PassDesc& pd, uint64_t hi_bits, cplx* s
                         const uint32_t sm = thr_ok ? op.slotmask : 0;
                         for (int k = 0; k < 16; ++k) {
                             cplx own = reg[lane][k], res = own;
-                            if ((sm >> k) & 1) {
+                            if (op.kind == OP_PHASE) {
+                                const uint32_t l = base_local[lane] + sd.slot_off[k < slots ? k : 0];
+                                const double* tb = prog.phase_tables.data() + 2 * ((size_t)pd.phase_table_offset + op.cmask_out + l);
+                                cplx f = cplx(tb[0], tb[1]) * eu[op.tmask_out * 13 + 12];
+                                for (int j = 0; j < pd.t; ++j)
+                                    if ((l >> j) & 1) f *= eu[op.tmask_out * 13 + j];
+                                res = f * own;
+                            } else if ((sm >> k) & 1) {
                                 if (op.kind == OP_DIAG) {
                                     bool b;
                                     if (op.thome == T_REG) b = (op.tslots >> k) & 1;
