@@ -153,51 +153,20 @@ __device__ __forceinline__ uint64_t run_offset(const PassDesc& pd, uint32_t run)
 // 16 independent dependency chains interleave (controls become selects, and ops without controls —
 // the common case — carry no predicate at all).
 
-// In-place pair updates written as PTX with read-write operands: the amplitudes stay in the registers they
-// live in across the interpreter loop (plain C++ lets the compiler rename results freely, which costs a full
-// copy of the register file per op at the loop header).
-__device__ __forceinline__ void pair_real(double& xr, double& xi, double& yr, double& yi, double m00, double m01, double m10,
-                                          double m11) {
-    asm("{\n\t.reg .f64 t0, t1, t2, t3;\n\t"
-        "mul.f64 t0, %4, %0;\n\tmul.f64 t1, %4, %1;\n\tmul.f64 t2, %6, %0;\n\tmul.f64 t3, %6, %1;\n\t"
-        "fma.rn.f64 %0, %5, %2, t0;\n\tfma.rn.f64 %1, %5, %3, t1;\n\t"
-        "fma.rn.f64 %2, %7, %2, t2;\n\tfma.rn.f64 %3, %7, %3, t3;\n\t}"
-        : "+d"(xr), "+d"(xi), "+d"(yr), "+d"(yi)
-        : "d"(m00), "d"(m01), "d"(m10), "d"(m11));
-}
-
-// x' = a*x + b*y, y' = c*x + d*y with complex a, b, c, d
-__device__ __forceinline__ void pair_complex(double& xr, double& xi, double& yr, double& yi, const DevOp& op) {
-    const double ar_ = op.m[0], ai_ = op.m[1], br_ = op.m[2], bi_ = op.m[3], cr_ = op.m[4], ci_ = op.m[5], dr_ = op.m[6], di_ = op.m[7];
-    asm("{\n\t.reg .f64 p0, p1, q0, q1, n0;\n\t"
-        "mul.f64 p0, %4, %0;\n\tmul.f64 p1, %4, %1;\n\t"          // a.re * x
-        "neg.f64 n0, %5;\n\t"
-        "fma.rn.f64 p0, n0, %1, p0;\n\tfma.rn.f64 p1, %5, %0, p1;\n\t"   // + i a.im * x
-        "fma.rn.f64 p0, %6, %2, p0;\n\tfma.rn.f64 p1, %6, %3, p1;\n\t"   // + b.re * y
-        "neg.f64 n0, %7;\n\t"
-        "fma.rn.f64 p0, n0, %3, p0;\n\tfma.rn.f64 p1, %7, %2, p1;\n\t"   // + i b.im * y
-        "mul.f64 q0, %8, %0;\n\tmul.f64 q1, %8, %1;\n\t"
-        "neg.f64 n0, %9;\n\t"
-        "fma.rn.f64 q0, n0, %1, q0;\n\tfma.rn.f64 q1, %9, %0, q1;\n\t"
-        "fma.rn.f64 q0, %10, %2, q0;\n\tfma.rn.f64 q1, %10, %3, q1;\n\t"
-        "neg.f64 n0, %11;\n\t"
-        "fma.rn.f64 q0, n0, %3, q0;\n\tfma.rn.f64 q1, %11, %2, q1;\n\t"
-        "mov.f64 %0, p0;\n\tmov.f64 %1, p1;\n\tmov.f64 %2, q0;\n\tmov.f64 %3, q1;\n\t}"
-        : "+d"(xr), "+d"(xi), "+d"(yr), "+d"(yi)
-        : "d"(ar_), "d"(ai_), "d"(br_), "d"(bi_), "d"(cr_), "d"(ci_), "d"(dr_), "d"(di_));
-}
+// Every op is written OUT OF PLACE: it reads the register file x and writes all of y.  The interpreter loop
+// alternates the two files (a -> b, b -> a), so no value has to survive in "its" register across the loop
+// header — an in-place formulation makes the compiler copy the whole file once per op.
 
 template <int J, int KIND, bool CTRL>
-__device__ __forceinline__ void reg_pairs(const DevOp& op, uint32_t sm, double (&ar)[kSlots], double (&ai)[kSlots]) {
-    const double m00r = op.m[0], m01r = op.m[2], m01i = op.m[3];
-    const double m10r = op.m[4], m10i = op.m[5], m11r = op.m[6];
+__device__ __forceinline__ void reg_pairs(const DevOp& op, uint32_t sm, const double (&xr_)[kSlots], const double (&xi_)[kSlots],
+                                          double (&yr_)[kSlots], double (&yi_)[kSlots]) {
+    const double m00r = op.m[0], m00i = op.m[1], m01r = op.m[2], m01i = op.m[3];
+    const double m10r = op.m[4], m10i = op.m[5], m11r = op.m[6], m11i = op.m[7];
 #pragma unroll
     for (int k = 0; k < kSlots; ++k) {
         if (k & (1 << J)) continue;   // compile-time: k enumerates the slots whose target bit is 0
         const int k1 = k | (1 << J);
-        if (!CTRL && KIND == OP_MATREAL) { pair_real(ar[k], ai[k], ar[k1], ai[k1], m00r, m01r, m10r, m11r); continue; }
-        if (!CTRL && KIND == OP_MAT) { pair_complex(ar[k], ai[k], ar[k1], ai[k1], op); continue; }
-        const double xr = ar[k], xi = ai[k], yr = ar[k1], yi = ai[k1];
+        const double xr = xr_[k], xi = xi_[k], yr = xr_[k1], yi = xi_[k1];
         double n0r, n0i, n1r, n1i;
         if (KIND == OP_FLIP) {
             n0r = yr; n0i = yi; n1r = xr; n1i = xi;
@@ -208,7 +177,6 @@ __device__ __forceinline__ void reg_pairs(const DevOp& op, uint32_t sm, double (
             n0r = m00r * xr + m01r * yr; n0i = m00r * xi + m01r * yi;
             n1r = m10r * xr + m11r * yr; n1i = m10r * xi + m11r * yi;
         } else {
-            const double m00i = op.m[1], m11i = op.m[7];
             n0r = m00r * xr - m00i * xi + m01r * yr - m01i * yi;
             n0i = m00r * xi + m00i * xr + m01r * yi + m01i * yr;
             n1r = m10r * xr - m10i * xi + m11r * yr - m11i * yi;
@@ -216,16 +184,16 @@ __device__ __forceinline__ void reg_pairs(const DevOp& op, uint32_t sm, double (
         }
         if (CTRL) {
             const bool on = (sm >> k) & 1;
-            ar[k] = on ? n0r : xr; ai[k] = on ? n0i : xi; ar[k1] = on ? n1r : yr; ai[k1] = on ? n1i : yi;
+            yr_[k] = on ? n0r : xr; yi_[k] = on ? n0i : xi; yr_[k1] = on ? n1r : yr; yi_[k1] = on ? n1i : yi;
         } else {
-            ar[k] = n0r; ai[k] = n0i; ar[k1] = n1r; ai[k1] = n1i;
+            yr_[k] = n0r; yi_[k] = n0i; yr_[k1] = n1r; yi_[k1] = n1i;
         }
     }
 }
 
 template <int KIND, bool CTRL>
-__device__ __forceinline__ void lane_target(const DevOp& op, uint32_t sm, uint32_t tid, double (&ar)[kSlots],
-                                            double (&ai)[kSlots]) {
+__device__ __forceinline__ void lane_target(const DevOp& op, uint32_t sm, uint32_t tid, const double (&xr_)[kSlots],
+                                            const double (&xi_)[kSlots], double (&yr_)[kSlots], double (&yi_)[kSlots]) {
     const int lm = 1 << op.tbit;
     const bool b = (tid >> op.tbit) & 1;
     // coefficient of my own amplitude and of my partner's
@@ -233,8 +201,8 @@ __device__ __forceinline__ void lane_target(const DevOp& op, uint32_t sm, uint32
     const double cpr = b ? op.m[4] : op.m[2], cpi = b ? op.m[5] : op.m[3];
 #pragma unroll
     for (int k = 0; k < kSlots; ++k) {
-        const double pr = shfl_xor_f64(ar[k], lm), pi = shfl_xor_f64(ai[k], lm);
-        const double xr = ar[k], xi = ai[k];
+        const double xr = xr_[k], xi = xi_[k];
+        const double pr = shfl_xor_f64(xr, lm), pi = shfl_xor_f64(xi, lm);
         double nr, ni;
         if (KIND == OP_FLIP) { nr = pr; ni = pi; }
         else if (KIND == OP_ADIAG) { nr = cpr * pr - cpi * pi; ni = cpr * pi + cpi * pr; }
@@ -245,16 +213,16 @@ __device__ __forceinline__ void lane_target(const DevOp& op, uint32_t sm, uint32
         }
         if (CTRL) {
             const bool on = (sm >> k) & 1;
-            ar[k] = on ? nr : xr; ai[k] = on ? ni : xi;
+            yr_[k] = on ? nr : xr; yi_[k] = on ? ni : xi;
         } else {
-            ar[k] = nr; ai[k] = ni;
+            yr_[k] = nr; yi_[k] = ni;
         }
     }
 }
 
 template <bool CTRL>
-__device__ __forceinline__ void diagonal(const DevOp& op, uint32_t sm, uint32_t tid, uint64_t gbase, double (&ar)[kSlots],
-                                         double (&ai)[kSlots]) {
+__device__ __forceinline__ void diagonal(const DevOp& op, uint32_t sm, uint32_t tid, uint64_t gbase, const double (&xr_)[kSlots],
+                                         const double (&xi_)[kSlots], double (&yr_)[kSlots], double (&yi_)[kSlots]) {
     const double d0r = op.m[0], d0i = op.m[1], d1r = op.m[6], d1i = op.m[7];
     if (op.thome == T_REG) {
         const uint32_t tsl = op.tslots;
@@ -262,28 +230,28 @@ __device__ __forceinline__ void diagonal(const DevOp& op, uint32_t sm, uint32_t 
         for (int k = 0; k < kSlots; ++k) {
             const bool b = (tsl >> k) & 1;
             const double pr = b ? d1r : d0r, pi = b ? d1i : d0i;
-            const double xr = ar[k], xi = ai[k];
+            const double xr = xr_[k], xi = xi_[k];
             const double nr = xr * pr - xi * pi, ni = xr * pi + xi * pr;
-            if (CTRL) { const bool on = (sm >> k) & 1; ar[k] = on ? nr : xr; ai[k] = on ? ni : xi; }
-            else { ar[k] = nr; ai[k] = ni; }
+            if (CTRL) { const bool on = (sm >> k) & 1; yr_[k] = on ? nr : xr; yi_[k] = on ? ni : xi; }
+            else { yr_[k] = nr; yi_[k] = ni; }
         }
     } else {
         const bool b = (op.thome == T_THREAD) ? ((tid & op.tmask_thr) != 0) : ((gbase & op.tmask_out) != 0);
         const double pr = b ? d1r : d0r, pi = b ? d1i : d0i;
 #pragma unroll
         for (int k = 0; k < kSlots; ++k) {
-            const double xr = ar[k], xi = ai[k];
+            const double xr = xr_[k], xi = xi_[k];
             const double nr = xr * pr - xi * pi, ni = xr * pi + xi * pr;
-            if (CTRL) { const bool on = (sm >> k) & 1; ar[k] = on ? nr : xr; ai[k] = on ? ni : xi; }
-            else { ar[k] = nr; ai[k] = ni; }
+            if (CTRL) { const bool on = (sm >> k) & 1; yr_[k] = on ? nr : xr; yi_[k] = on ? ni : xi; }
+            else { yr_[k] = nr; yi_[k] = ni; }
         }
     }
 }
 
 // A fused run of diagonal gates: amplitude(l) *= TABLE[l] * U * prod_{tile bits j of l} E_j.
 __device__ __forceinline__ void phase_op(const DevOp& op, const double2* __restrict__ tables, const double2* eu,
-                                         const SweepDesc& sd, uint32_t tid, uint32_t base_local, double (&ar)[kSlots],
-                                         double (&ai)[kSlots]) {
+                                         const SweepDesc& sd, uint32_t tid, uint32_t base_local, const double (&xr_)[kSlots],
+                                         const double (&xi_)[kSlots], double (&yr_)[kSlots], double (&yi_)[kSlots]) {
     const double2* tb = tables + op.cmask_out;
     double2 f[kSlots];
 #pragma unroll
@@ -319,23 +287,45 @@ __device__ __forceinline__ void phase_op(const DevOp& op, const double2* __restr
     }
 #pragma unroll
     for (int k = 0; k < kSlots; ++k) {
-        const double xr = ar[k], xi = ai[k];
-        ar[k] = xr * f[k].x - xi * f[k].y;
-        ai[k] = xr * f[k].y + xi * f[k].x;
+        const double xr = xr_[k], xi = xi_[k];
+        yr_[k] = xr * f[k].x - xi * f[k].y;
+        yi_[k] = xr * f[k].y + xi * f[k].x;
     }
 }
 
-#define QSIM_PAIR_CASES(KIND)                                                          \
-    case (KIND) * 10 + 0: lane_target<KIND, false>(op, 0xffffu, tid, ar, ai); break;   \
-    case (KIND) * 10 + 1: lane_target<KIND, true>(op, sm, tid, ar, ai); break;         \
-    case (KIND) * 10 + 2: reg_pairs<0, KIND, false>(op, 0xffffu, ar, ai); break;       \
-    case (KIND) * 10 + 3: reg_pairs<0, KIND, true>(op, sm, ar, ai); break;             \
-    case (KIND) * 10 + 4: reg_pairs<1, KIND, false>(op, 0xffffu, ar, ai); break;       \
-    case (KIND) * 10 + 5: reg_pairs<1, KIND, true>(op, sm, ar, ai); break;             \
-    case (KIND) * 10 + 6: reg_pairs<2, KIND, false>(op, 0xffffu, ar, ai); break;       \
-    case (KIND) * 10 + 7: reg_pairs<2, KIND, true>(op, sm, ar, ai); break;             \
-    case (KIND) * 10 + 8: reg_pairs<(kMaxRegBits > 3 ? 3 : 0), KIND, false>(op, 0xffffu, ar, ai); break; \
-    case (KIND) * 10 + 9: reg_pairs<(kMaxRegBits > 3 ? 3 : 0), KIND, true>(op, sm, ar, ai); break;
+#define QSIM_PAIR_CASES(KIND)                                                                   \
+    case (KIND) * 10 + 0: lane_target<KIND, false>(op, 0xffffu, tid, xr, xi, yr, yi); break;   \
+    case (KIND) * 10 + 1: lane_target<KIND, true>(op, sm, tid, xr, xi, yr, yi); break;         \
+    case (KIND) * 10 + 2: reg_pairs<0, KIND, false>(op, 0xffffu, xr, xi, yr, yi); break;       \
+    case (KIND) * 10 + 3: reg_pairs<0, KIND, true>(op, sm, xr, xi, yr, yi); break;             \
+    case (KIND) * 10 + 4: reg_pairs<1, KIND, false>(op, 0xffffu, xr, xi, yr, yi); break;       \
+    case (KIND) * 10 + 5: reg_pairs<1, KIND, true>(op, sm, xr, xi, yr, yi); break;             \
+    case (KIND) * 10 + 6: reg_pairs<2, KIND, false>(op, 0xffffu, xr, xi, yr, yi); break;       \
+    case (KIND) * 10 + 7: reg_pairs<2, KIND, true>(op, sm, xr, xi, yr, yi); break;             \
+    case (KIND) * 10 + 8: reg_pairs<(kMaxRegBits > 3 ? 3 : 0), KIND, false>(op, 0xffffu, xr, xi, yr, yi); break; \
+    case (KIND) * 10 + 9: reg_pairs<(kMaxRegBits > 3 ? 3 : 0), KIND, true>(op, sm, xr, xi, yr, yi); break;
+
+constexpr uint32_t kOpcodeCopy = 46;   // not produced by the compiler: stands in for a skipped op
+
+// one op, register file x -> register file y
+__device__ __forceinline__ void apply_op(const DevOp& op, uint32_t opcode, uint32_t sm, uint32_t tid, uint64_t gbase,
+                                         const double2* __restrict__ tables, const double2* eu, const SweepDesc& sd,
+                                         uint32_t base_local, const double (&xr)[kSlots], const double (&xi)[kSlots],
+                                         double (&yr)[kSlots], double (&yi)[kSlots]) {
+    switch (opcode) {
+        QSIM_PAIR_CASES(OP_MAT)
+        QSIM_PAIR_CASES(OP_MATREAL)
+        QSIM_PAIR_CASES(OP_ADIAG)
+        QSIM_PAIR_CASES(OP_FLIP)
+        case 40: case 42: diagonal<false>(op, 0xffffu, tid, gbase, xr, xi, yr, yi); break;
+        case 44: phase_op(op, tables, eu, sd, tid, base_local, xr, xi, yr, yi); break;
+        case kOpcodeCopy:
+#pragma unroll
+            for (int k = 0; k < kSlots; ++k) { yr[k] = xr[k]; yi[k] = xi[k]; }
+            break;
+        default: diagonal<true>(op, sm, tid, gbase, xr, xi, yr, yi); break;
+    }
+}
 
 }  // namespace
 
@@ -441,7 +431,7 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
         for (uint64_t i = 0; i < pre; ++i) issue_load(i);
     }
 
-    double ar[kSlots], ai[kSlots];
+    double ar[kSlots], ai[kSlots], br[kSlots], bi[kSlots];
     for (uint64_t i = 0; i < n_my; ++i) {
         const int s = (int)(i % n_stages);
         const uint32_t parity = (uint32_t)((i / n_stages) & 1);
@@ -475,9 +465,12 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
             if (sw > 0) __syncthreads();
             const uint32_t n_active = 1u << sd.nthr;
             const bool warp_active = (warp << 5) < n_active;
-            const uint32_t xl = (sw + 1 == pd.n_sweeps) ? pd.xor_local : 0u;   // deferred X gates, see the store
+            const bool last_sweep = (sw + 1 == pd.n_sweeps);
+            const uint32_t xl = last_sweep ? pd.xor_local : 0u;                 // deferred X gates, see the store
+            const int n_tail = last_sweep ? pd.n_tail : 0;                      // trailing bit flips, see the store
+            const bool permuted_store = (xl != 0u) || (n_tail > 0);
             if (!warp_active) {
-                if (xl) __syncthreads();   // keep the barrier count equal across warps
+                if (permuted_store) __syncthreads();   // keep the barrier count equal across warps
                 continue;
             }
             const bool active = tid < n_active;
@@ -501,31 +494,58 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
                 }
             }
             const uint32_t ops_u32 = smem_u32(sops);
-#pragma unroll 1
-            for (int o = sd.op_begin; o < sd.op_end; ++o) {
-                const DevOp& op = sops[o];
+            // the interpreter: fetch() finds the next op that applies to this tile (ops whose controls outside the
+            // tile fail are skipped), apply_op() alternates between the two register files
+            int o = sd.op_begin;
+            const int o_end = sd.op_end;
+            uint32_t opcode = 0, sm = 0;
+            auto fetch = [&]() -> bool {
+                if (o >= o_end) return false;
                 // first 16 bytes of the record: kind|thome|tbit|opcode, slotmask|tslots, cmask_thr, cval_thr
                 const uint4 hdr = lds_u4(ops_u32 + (uint32_t)o * (uint32_t)sizeof(DevOp));
-                const uint32_t opcode = hdr.x >> 24;
-                if (opcode & 0x80u) {
-                    if ((gbase & op.cmask_out) != op.cval_out) continue;
-                }
-                const bool thr_ok = (tid & hdr.z) == hdr.w;
-                const uint32_t sm = thr_ok ? (hdr.y & 0xffffu) : 0u;
-                switch (opcode & 0x7fu) {
-                    QSIM_PAIR_CASES(OP_MAT)
-                    QSIM_PAIR_CASES(OP_MATREAL)
-                    QSIM_PAIR_CASES(OP_ADIAG)
-                    QSIM_PAIR_CASES(OP_FLIP)
-                    case 40: case 42: diagonal<false>(op, 0xffffu, tid, gbase, ar, ai); break;
-                    case 44: phase_op(op, P.phase_tables, eu, sd, tid, base_local, ar, ai); break;
-                    default: diagonal<true>(op, sm, tid, gbase, ar, ai); break;
-                }
+                opcode = hdr.x >> 24;
+                // an op whose controls outside the tile fail becomes a register-file copy (no extra control-flow
+                // edge around apply_op: that edge is what made the compiler copy the file at every loop header)
+                const bool skip = (opcode & 0x80u) && (gbase & sops[o].cmask_out) != sops[o].cval_out;
+                opcode = skip ? kOpcodeCopy : (opcode & 0x7fu);
+                sm = ((tid & hdr.z) == hdr.w) ? (hdr.y & 0xffffu) : 0u;
+                return true;
+            };
+            bool in_b = false;
+#pragma unroll 1
+            for (;;) {
+                if (!fetch()) break;
+                apply_op(sops[o], opcode, sm, tid, gbase, P.phase_tables, eu, sd, base_local, ar, ai, br, bi);
+                ++o;
+                if (!fetch()) { in_b = true; break; }
+                apply_op(sops[o], opcode, sm, tid, gbase, P.phase_tables, eu, sd, base_local, br, bi, ar, ai);
+                ++o;
             }
-            // the pass's deferred X gates: the last sweep stores to the XOR-ed tile-local index (other
-            // threads' slots, hence the barrier: everybody has finished loading)
-            if (xl) __syncthreads();
-            if (full_sweep) {
+            if (in_b) {
+#pragma unroll
+                for (int k = 0; k < kSlots; ++k) { ar[k] = br[k]; ai[k] = bi[k]; }
+            }
+            // The pass's index permutations ride on the last sweep's store: trailing controlled bit flips
+            // (l ^= 1 << t where the controls match), then the deferred X gates (l ^= xor_local).  The targets are
+            // other threads' slots, hence the barrier: everybody has finished loading.
+            if (permuted_store) __syncthreads();
+            if (n_tail > 0) {
+                uint32_t l[kSlots];
+#pragma unroll
+                for (int k = 0; k < kSlots; ++k) l[k] = base_local + (uint32_t)sd.slot_off[k];
+#pragma unroll 1
+                for (int f = 0; f < n_tail; ++f) {
+                    const TailFlip tf = pd.tail[f];
+                    // controls outside the tile are the same for the whole tile
+                    if ((gbase & tf.cmask_out) != tf.cval_out) continue;
+                    const uint32_t cm = tf.cmask_local, cv = tf.cval_local, tb = 1u << tf.t_local;
+#pragma unroll
+                    for (int k = 0; k < kSlots; ++k) l[k] ^= ((l[k] & cm) == cv) ? tb : 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < kSlots; ++k)
+                    if (active && k < slots) sts128(tile_u32 + ((l[k] ^ xl) * 16u), ar[k], ai[k]);
+            } else if (full_sweep) {
 #pragma unroll
                 for (int k = 0; k < kSlots; ++k)
                     sts128(tile_u32 + (((base_local + (uint32_t)sd.slot_off[k]) ^ xl) * 16u), ar[k], ai[k]);

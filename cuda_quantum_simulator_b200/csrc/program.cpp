@@ -77,6 +77,7 @@ CompileOptions default_options() {
     if (std::getenv("QSIM_NO_MERGE")) o.merge = false;
     if (std::getenv("QSIM_NO_REORDER")) o.reorder = false;
     if (std::getenv("QSIM_NO_PHASE")) o.fuse_diagonals = false;
+    if (std::getenv("QSIM_NO_TAIL")) o.fold_tail_flips = false;
     return o;
 }
 
@@ -432,6 +433,39 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
                 else { if ((xf_local >> q) & 1) tau_bit |= 1ULL << src; ++src; }
             }
             pd.xor_tau = tau_bit;
+        }
+
+        // Trailing bit flips: walking backwards, a FLIP that commutes with every op that stays behind it can be
+        // moved to the end of the pass, where it costs only an index XOR in the final store.
+        if (opt.fold_tail_flips && pd.t <= 16) {
+            std::vector<int> stay, tail;   // both in reverse order
+            for (size_t k = plan.op_idx.size(); k-- > 0;) {
+                const int idx = plan.op_idx[k];
+                const LogicalOp& op = out.lops[idx];
+                bool movable = op.kind == OP_FLIP && (int)tail.size() < kMaxTailFlips && op.target < nl &&
+                               local_of[op.target] >= 0;
+                if (movable)
+                    for (int s2 : stay)
+                        if (!commutes(op, out.lops[s2])) { movable = false; break; }
+                (movable ? tail : stay).push_back(idx);
+            }
+            if (!tail.empty()) {
+                std::reverse(stay.begin(), stay.end());
+                std::reverse(tail.begin(), tail.end());
+                for (int idx : tail) {
+                    const LogicalOp& op = out.lops[idx];
+                    TailFlip tf{};
+                    tf.t_local = (uint8_t)local_of[op.target];
+                    for (int q = 0; q < 64; ++q) {
+                        if (!((op.cmask >> q) & 1)) continue;
+                        const uint64_t v = (op.cval >> q) & 1;
+                        if (q < nl && local_of[q] >= 0) { tf.cmask_local |= (uint16_t)(1u << local_of[q]); tf.cval_local |= (uint16_t)(v << local_of[q]); }
+                        else { tf.cmask_out |= 1ULL << q; tf.cval_out |= v << q; }
+                    }
+                    pd.tail[pd.n_tail++] = tf;
+                }
+                plan.op_idx.swap(stay);
+            }
         }
 
         // Fuse runs of diagonal gates (each with at most one control and no zero entry) into OP_PHASE ops:

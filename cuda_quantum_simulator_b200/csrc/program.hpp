@@ -121,6 +121,16 @@ struct TmaDim {
     uint8_t start_bit, range_bits, box_bits, pad;
 };
 
+// A controlled bit flip (X / CNOT / Toffoli) that ends a pass is not executed as an op: it is folded into the
+// tile-local index the final store goes to (l ^= 1 << t when the controls match).
+struct TailFlip {
+    uint16_t cmask_local, cval_local;   // controls that are tile bits (tile-local positions)
+    uint8_t t_local;                    // target, tile-local position
+    uint8_t pad[3];
+    uint64_t cmask_out, cval_out;       // controls outside the tile (global index bits)
+};
+constexpr int kMaxTailFlips = 12;
+
 struct PassDesc {
     int32_t n;                   // qubits held in this buffer (local qubits when sharded)
     int32_t t;                   // tile bits
@@ -133,13 +143,14 @@ struct PassDesc {
     int32_t n_phase;             // OP_PHASE ops in this pass
     int32_t phase_table_offset;  // into Program::phase_tables (entries)
     int32_t phase_term_offset;   // into Program::phase_terms
-    int32_t pad2;
+    int32_t n_tail;              // trailing flips folded into the final store
     uint8_t tile_bits[kMaxTileBits];   // global bit of tile-local bit i (ascending)
     uint32_t xor_local;          // tile-local index XOR applied by the pass's final store (deferred X gates)
     uint64_t xor_tau;            // tile-number XOR: the tile read from tau is written to tau ^ xor_tau
     uint8_t tma_instr_bits;      // the top tma_instr_bits tile bits are enumerated by separate TMA instructions
     uint8_t pad[3];
     TmaDim tma_dim[5];
+    TailFlip tail[kMaxTailFlips];
     Segment seg[kMaxSegments];
     SweepDesc sweep[kMaxSweeps];
 };
@@ -159,6 +170,7 @@ struct CompileOptions {
     bool merge = true;           // merge runs of gates on the same (target, controls)
     bool reorder = true;         // commute ops across passes when legal (fewer passes)
     int n_global = 0;            // qubits >= n - n_global live in the rank id (sharded state)
+    bool fold_tail_flips = true; // bit flips that can slide to the end of a pass become store addressing
     bool fuse_diagonals = true;  // runs of >= 3 diagonal gates become one OP_PHASE
     bool defer_x = true;         // carry uncontrolled X gates as an index-XOR frame, folded into the last pass's addressing
     uint64_t initial_xor = 0;    // X frame inherited from earlier segments (sharded driver: pending flips of global qubits)

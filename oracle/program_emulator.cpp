@@ -150,7 +150,17 @@ void run_pass(const Program& prog, const PassDesc& pd, uint64_t hi_bits, cplx* s
             const uint64_t stau = tau ^ pd.xor_tau;
             for (int s = 0; s < pd.n_segments; ++s)
                 sbase |= ((stau >> pd.seg[s].src_shift) & pd.seg[s].mask) << pd.seg[s].dst_shift;
-            for (uint32_t l = 0; l < tile_amps; ++l) state[(gidx[l] - base) + sbase] = tile[l ^ pd.xor_local];
+            // the final store's index permutation: trailing bit flips in order, then the X frame
+            std::vector<cplx> permuted(tile_amps);
+            for (uint32_t l = 0; l < tile_amps; ++l) {
+                uint32_t d = l;
+                for (int f = 0; f < pd.n_tail; ++f) {
+                    const TailFlip& tf = pd.tail[f];
+                    if ((gbase & tf.cmask_out) == tf.cval_out && (d & tf.cmask_local) == tf.cval_local) d ^= 1u << tf.t_local;
+                }
+                permuted[d ^ pd.xor_local] = tile[l];
+            }
+            for (uint32_t l = 0; l < tile_amps; ++l) state[(gidx[l] - base) + sbase] = permuted[l];
         }
     }
 }
