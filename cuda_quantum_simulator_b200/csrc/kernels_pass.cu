@@ -339,6 +339,8 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
     DevOp* sops = reinterpret_cast<DevOp*>(smem + (size_t)n_stages * tile_bytes);
     double2* eu = reinterpret_cast<double2*>(sops + pd.n_ops + 1);       // (E_0..E_11, U) of every OP_PHASE, per tile
     uint64_t* full = reinterpret_cast<uint64_t*>(eu + (size_t)pd.n_phase * 13);
+    // base_tab[sw][tid]: the tile-local index of the thread's slot 0 in sweep sw (tile-invariant)
+    uint16_t* base_tab = reinterpret_cast<uint16_t*>(full + 2 * n_stages);
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
 
@@ -349,6 +351,13 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
         const int n16 = pd.n_ops * (int)(sizeof(DevOp) / 16);
         for (int i = tid; i < n16; i += kComputeThreads) dst[i] = src[i];
         if (tid < (int)(sizeof(DevOp) / 16)) dst[n16 + tid] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int sw = 0; sw < pd.n_sweeps; ++sw) {
+        const SweepDesc& sd = pd.sweep[sw];
+        uint32_t bl = 0;
+        for (int b = 0; b < sd.nthr; ++b)
+            if ((tid >> b) & 1) bl |= 1u << sd.thr_pos[b];
+        base_tab[sw * kComputeThreads + (int)tid] = (uint16_t)bl;
     }
     if (tid == 0) {
         if (P.use_tensor_map) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -363,19 +372,29 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
     const uint64_t first = blockIdx.x, stride = gridDim.x;
     // Work items of this CTA.  Without a tile XOR item i is tile first + i*stride.  With one, tiles are
     // handled in partner pairs (tau, tau ^ xor_tau): items 2j and 2j+1 are the two members of pair
-    // first + j*stride, each is written to the other's location, and a tile is only overwritten after its
-    // own contents have been loaded (see the wait before the store below).
+    // first + j*stride (the pair id is the tile number with the pivot bit of xor_tau squeezed out), each is
+    // written to the other's location, and a tile is only overwritten after its own contents have been loaded
+    // (see the wait before the store below).
     const uint64_t xor_tau = pd.xor_tau;
     const int pivot = xor_tau ? 63 - __clzll((long long)xor_tau) : 0;
     const uint64_t n_units = xor_tau ? n_tiles / 2 : n_tiles;
     const uint64_t my_units = first < n_units ? (n_units - first + stride - 1) / stride : 0;
     const uint64_t n_my = xor_tau ? 2 * my_units : my_units;
-    auto tile_of = [&](uint64_t i) -> uint64_t {
-        if (!xor_tau) return first + i * stride;
-        const uint64_t p = first + (i >> 1) * stride;
-        const uint64_t t0 = (p & ((1ULL << pivot) - 1)) | ((p >> pivot) << (pivot + 1));   // pair id with a 0 at the pivot bit
-        return (i & 1) ? (t0 ^ xor_tau) : t0;
+    // Global base index of a unit = its number deposited into the index bits that are neither tile bits nor the
+    // pivot ("holes").  Stepping to the next unit is an add with the holes filled so carries pass through them.
+    const uint64_t xdep = xor_tau ? tile_base(pd, xor_tau) : 0ULL;   // index XOR between the members of a pair
+    uint64_t holes = xor_tau ? tile_base(pd, 1ULL << pivot) : 0ULL;
+    for (int j = 0; j < pd.t; ++j) holes |= 1ULL << pd.tile_bits[j];
+    const uint64_t keep = ((1ULL << pd.n) - 1ULL) & ~holes;
+    auto deposit = [&](uint64_t x) -> uint64_t {
+        uint64_t r = 0;
+        int j = 0;
+        for (int b = 0; b < pd.n; ++b)
+            if ((keep >> b) & 1ULL) { r |= ((x >> j) & 1ULL) << b; ++j; }
+        return r;
     };
+    const uint64_t ustride = deposit(stride), ufirst = deposit(first);
+    auto next_unit = [&](uint64_t ub) -> uint64_t { return ((ub | holes) + ustride) & keep; };
     const uint32_t n_runs = 1u << pd.n_high;
     const uint32_t run_bytes = 16u << pd.L;
     const uint32_t n_instr = 1u << pd.tma_instr_bits;
@@ -385,9 +404,8 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
     // ---- TMA duties of the elected thread --------------------------------------------------------------
     // (executed by every lane of warp 0: lane q issues instruction q, q+32, ...)
     const uint32_t lane = tid & 31u;
-    auto issue_load = [&](uint64_t i) {
+    auto issue_load = [&](uint64_t i, uint64_t base) {
         const int s = (int)(i % n_stages);
-        const uint64_t base = tile_base(pd, tile_of(i));
         if (lane == 0) mbar_expect_tx(&full[s], tile_bytes);
         __syncwarp();
         if (P.use_tensor_map) {
@@ -403,14 +421,13 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
             }
         }
     };
-    auto issue_store = [&](uint64_t i) {
+    auto issue_store = [&](uint64_t i, uint64_t base) {
         const int s = (int)(i % n_stages);
         if (xor_tau && !(i & 1)) {
             // this tile goes to its partner's location: the partner (item i+1) must have been read first
             const uint64_t j = i + 1;
             mbar_wait(&full[(int)(j % n_stages)], (uint32_t)((j / n_stages) & 1));
         }
-        const uint64_t base = tile_base(pd, tile_of(i) ^ xor_tau);
         if (P.use_tensor_map) {
             for (uint32_t q = lane; q < n_instr; q += 32) {
                 int c[5];
@@ -426,16 +443,28 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
         tma_store_commit();   // every lane commits its own (possibly empty) bulk group
     };
 
+    // bases of the next item to load (warp 0) and of the item being computed
+    uint64_t load_unit = ufirst, cur_unit = ufirst;
+    uint64_t n_loaded = 0;
+    auto load_next = [&]() {
+        const bool odd = xor_tau && (n_loaded & 1);
+        issue_load(n_loaded, odd ? (load_unit ^ xdep) : load_unit);
+        if (!xor_tau || odd) load_unit = next_unit(load_unit);
+        ++n_loaded;
+    };
     if (warp == 0) {
         const uint64_t pre = n_my < (uint64_t)n_stages ? n_my : (uint64_t)n_stages;
-        for (uint64_t i = 0; i < pre; ++i) issue_load(i);
+        for (uint64_t i = 0; i < pre; ++i) load_next();
     }
 
     double ar[kSlots], ai[kSlots], br[kSlots], bi[kSlots];
     for (uint64_t i = 0; i < n_my; ++i) {
         const int s = (int)(i % n_stages);
         const uint32_t parity = (uint32_t)((i / n_stages) & 1);
-        const uint64_t gbase = tile_base(pd, tile_of(i)) | P.hi_bits;
+        const bool odd_item = xor_tau && (i & 1);
+        const uint64_t tbase = odd_item ? (cur_unit ^ xdep) : cur_unit;
+        if (!xor_tau || odd_item) cur_unit = next_unit(cur_unit);
+        const uint64_t gbase = tbase | P.hi_bits;
         unsigned char* tile = tiles + (size_t)s * tile_bytes;
         if (pd.n_phase > 0) {
             // factors of the fused diagonal runs that depend on index bits outside the tile: one (op, factor) per thread
@@ -475,10 +504,7 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
             }
             const bool active = tid < n_active;
             const int slots = 1 << sd.r;
-            uint32_t base_local = 0;
-#pragma unroll
-            for (int b = 0; b < kMaxTileBits - kMaxRegBits; ++b)
-                if (b < sd.nthr && ((tid >> b) & 1)) base_local |= 1u << sd.thr_pos[b];
+            const uint32_t base_local = base_tab[sw * kComputeThreads + (int)tid];
             const uint32_t tile_u32 = smem_u32(tile);
             const uint32_t my_addr = tile_u32 + base_local * 16u;
             const bool full_sweep = (sd.r == kMaxRegBits) && (sd.nthr == kMaxTileBits - kMaxRegBits);
@@ -529,7 +555,7 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
             // (l ^= 1 << t where the controls match), then the deferred X gates (l ^= xor_local).  The targets are
             // other threads' slots, hence the barrier: everybody has finished loading.
             if (permuted_store) __syncthreads();
-            if (n_tail > 0) {
+            {
                 uint32_t l[kSlots];
 #pragma unroll
                 for (int k = 0; k < kSlots; ++k) l[k] = base_local + (uint32_t)sd.slot_off[k];
@@ -542,18 +568,14 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < kSlots; ++k) l[k] ^= ((l[k] & cm) == cv) ? tb : 0u;
                 }
+                if (full_sweep) {
 #pragma unroll
-                for (int k = 0; k < kSlots; ++k)
-                    if (active && k < slots) sts128(tile_u32 + ((l[k] ^ xl) * 16u), ar[k], ai[k]);
-            } else if (full_sweep) {
+                    for (int k = 0; k < kSlots; ++k) sts128(tile_u32 + ((l[k] ^ xl) * 16u), ar[k], ai[k]);
+                } else {
 #pragma unroll
-                for (int k = 0; k < kSlots; ++k)
-                    sts128(tile_u32 + (((base_local + (uint32_t)sd.slot_off[k]) ^ xl) * 16u), ar[k], ai[k]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < kSlots; ++k)
-                    if (active && k < slots)
-                        sts128(tile_u32 + (((base_local + (uint32_t)sd.slot_off[k]) ^ xl) * 16u), ar[k], ai[k]);
+                    for (int k = 0; k < kSlots; ++k)
+                        if (active && k < slots) sts128(tile_u32 + ((l[k] ^ xl) * 16u), ar[k], ai[k]);
+                }
             }
         }
         // make the generic-proxy writes visible to the bulk-copy engine; then the elected thread stores
@@ -561,11 +583,11 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
         fence_proxy_async();
         __syncthreads();
         if (warp == 0) {
-            issue_store(i);
-            if (i >= 1 && (i - 1) + (uint64_t)n_stages < n_my) {
+            issue_store(i, tbase ^ xdep);
+            if (i >= 1 && n_loaded < n_my) {
                 tma_store_wait_read_1();   // all but this lane's newest store group have finished reading shared memory
                 __syncwarp();              // ... for every lane: the stage of tile i-1 is free
-                issue_load((i - 1) + (uint64_t)n_stages);
+                load_next();               // item (i - 1) + n_stages
             }
         }
     }
@@ -574,7 +596,7 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
 
 size_t pass_smem_bytes(const PassDesc& pd, int stages) {
     return (size_t)stages * ((size_t)16 << pd.t) + ((size_t)pd.n_ops + 1) * sizeof(DevOp) + (size_t)pd.n_phase * 13 * sizeof(double2) +
-           2 * (size_t)stages * sizeof(uint64_t);
+           2 * (size_t)stages * sizeof(uint64_t) + (size_t)pd.n_sweeps * kComputeThreads * sizeof(uint16_t);
 }
 
 // Deepest ring that fits the 227 KiB of shared memory (at most kMaxStages).
