@@ -293,6 +293,13 @@ __device__ __forceinline__ void phase_op(const DevOp& op, const double2* __restr
     }
 }
 
+#if QSIM_REG_BITS > 3
+#define QSIM_PAIR_CASES_BIT3(KIND)                                                          \
+    case (KIND) * 10 + 8: reg_pairs<3, KIND, false>(op, 0xffffu, xr, xi, yr, yi); break;   \
+    case (KIND) * 10 + 9: reg_pairs<3, KIND, true>(op, sm, xr, xi, yr, yi); break;
+#else
+#define QSIM_PAIR_CASES_BIT3(KIND)
+#endif
 #define QSIM_PAIR_CASES(KIND)                                                                   \
     case (KIND) * 10 + 0: lane_target<KIND, false>(op, 0xffffu, tid, xr, xi, yr, yi); break;   \
     case (KIND) * 10 + 1: lane_target<KIND, true>(op, sm, tid, xr, xi, yr, yi); break;         \
@@ -302,8 +309,7 @@ __device__ __forceinline__ void phase_op(const DevOp& op, const double2* __restr
     case (KIND) * 10 + 5: reg_pairs<1, KIND, true>(op, sm, xr, xi, yr, yi); break;             \
     case (KIND) * 10 + 6: reg_pairs<2, KIND, false>(op, 0xffffu, xr, xi, yr, yi); break;       \
     case (KIND) * 10 + 7: reg_pairs<2, KIND, true>(op, sm, xr, xi, yr, yi); break;             \
-    case (KIND) * 10 + 8: reg_pairs<(kMaxRegBits > 3 ? 3 : 0), KIND, false>(op, 0xffffu, xr, xi, yr, yi); break; \
-    case (KIND) * 10 + 9: reg_pairs<(kMaxRegBits > 3 ? 3 : 0), KIND, true>(op, sm, xr, xi, yr, yi); break;
+    QSIM_PAIR_CASES_BIT3(KIND)
 
 constexpr uint32_t kOpcodeCopy = 46;   // not produced by the compiler: stands in for a skipped op
 
@@ -358,6 +364,13 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
         for (int b = 0; b < sd.nthr; ++b)
             if ((tid >> b) & 1) bl |= 1u << sd.thr_pos[b];
         base_tab[sw * kComputeThreads + (int)tid] = (uint16_t)bl;
+        if (sw + 1 == pd.n_sweeps) {
+            // extra row: where the final store puts the thread's slot 0 (the folded flips' affine map, see TailDyn)
+            uint32_t sb = pd.tail_const;
+            for (int j = 0; j < pd.t; ++j)
+                if ((bl >> j) & 1) sb ^= pd.tail_lin[j];
+            base_tab[pd.n_sweeps * kComputeThreads + (int)tid] = (uint16_t)sb;
+        }
     }
     if (tid == 0) {
         if (P.use_tensor_map) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -547,35 +560,34 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
                 apply_op(sops[o], opcode, sm, tid, gbase, P.phase_tables, eu, sd, base_local, br, bi, ar, ai);
                 ++o;
             }
-            if (in_b) {
-#pragma unroll
-                for (int k = 0; k < kSlots; ++k) { ar[k] = br[k]; ai[k] = bi[k]; }
-            }
-            // The pass's index permutations ride on the last sweep's store: trailing controlled bit flips
-            // (l ^= 1 << t where the controls match), then the deferred X gates (l ^= xor_local).  The targets are
+            // The pass's index permutations ride on the last sweep's store: the folded trailing bit flips (an affine
+            // map of the tile-local index, see TailDyn), then the deferred X gates (l ^= xor_local).  The targets are
             // other threads' slots, hence the barrier: everybody has finished loading.
             if (permuted_store) __syncthreads();
             {
                 uint32_t l[kSlots];
+                if (last_sweep) {
+                    uint32_t sb = base_tab[pd.n_sweeps * kComputeThreads + (int)tid] ^ xl;
+                    for (int f = 0; f < pd.n_dyn; ++f)   // flips controlled from outside the tile: the same for the whole tile
+                        if ((gbase & pd.dyn[f].cmask_out) == pd.dyn[f].cval_out) sb ^= pd.dyn[f].w;
 #pragma unroll
-                for (int k = 0; k < kSlots; ++k) l[k] = base_local + (uint32_t)sd.slot_off[k];
-#pragma unroll 1
-                for (int f = 0; f < n_tail; ++f) {
-                    const TailFlip tf = pd.tail[f];
-                    // controls outside the tile are the same for the whole tile
-                    if ((gbase & tf.cmask_out) != tf.cval_out) continue;
-                    const uint32_t cm = tf.cmask_local, cv = tf.cval_local, tb = 1u << tf.t_local;
-#pragma unroll
-                    for (int k = 0; k < kSlots; ++k) l[k] ^= ((l[k] & cm) == cv) ? tb : 0u;
-                }
-                if (full_sweep) {
-#pragma unroll
-                    for (int k = 0; k < kSlots; ++k) sts128(tile_u32 + ((l[k] ^ xl) * 16u), ar[k], ai[k]);
+                    for (int k = 0; k < kSlots; ++k) l[k] = tile_u32 + (sb ^ (uint32_t)pd.store_slot_off[k]) * 16u;
                 } else {
 #pragma unroll
-                    for (int k = 0; k < kSlots; ++k)
-                        if (active && k < slots) sts128(tile_u32 + ((l[k] ^ xl) * 16u), ar[k], ai[k]);
+                    for (int k = 0; k < kSlots; ++k) l[k] = tile_u32 + (base_local ^ (uint32_t)sd.slot_off[k]) * 16u;
                 }
+                // (the result sits in whichever register file the last op wrote)
+                auto store = [&](const double (&sr)[kSlots], const double (&si)[kSlots]) {
+                    if (full_sweep) {
+#pragma unroll
+                        for (int k = 0; k < kSlots; ++k) sts128(l[k], sr[k], si[k]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kSlots; ++k)
+                            if (active && k < slots) sts128(l[k], sr[k], si[k]);
+                    }
+                };
+                if (in_b) store(br, bi); else store(ar, ai);
             }
         }
         // make the generic-proxy writes visible to the bulk-copy engine; then the elected thread stores
@@ -596,7 +608,7 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
 
 size_t pass_smem_bytes(const PassDesc& pd, int stages) {
     return (size_t)stages * ((size_t)16 << pd.t) + ((size_t)pd.n_ops + 1) * sizeof(DevOp) + (size_t)pd.n_phase * 13 * sizeof(double2) +
-           2 * (size_t)stages * sizeof(uint64_t) + (size_t)pd.n_sweeps * kComputeThreads * sizeof(uint16_t);
+           2 * (size_t)stages * sizeof(uint64_t) + ((size_t)pd.n_sweeps + 1) * kComputeThreads * sizeof(uint16_t);
 }
 
 // Deepest ring that fits the 227 KiB of shared memory (at most kMaxStages).

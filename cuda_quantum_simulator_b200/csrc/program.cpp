@@ -436,17 +436,29 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
         }
 
         // Trailing bit flips: walking backwards, a FLIP that commutes with every op that stays behind it can be
-        // moved to the end of the pass, where it costs only an index XOR in the final store.
-        if (opt.fold_tail_flips && pd.t <= 16) {
+        // moved to the end of the pass, where it costs only index arithmetic in the final store.  Only flips that
+        // are affine in the tile-local index qualify (see TailDyn).
+        for (int j = 0; j < kMaxTileBits; ++j) pd.tail_lin[j] = (uint16_t)(1u << j);
+        if (opt.fold_tail_flips) {
             std::vector<int> stay, tail;   // both in reverse order
+            int n_dyn = 0;
             for (size_t k = plan.op_idx.size(); k-- > 0;) {
                 const int idx = plan.op_idx[k];
                 const LogicalOp& op = out.lops[idx];
                 bool movable = op.kind == OP_FLIP && (int)tail.size() < kMaxTailFlips && op.target < nl &&
                                local_of[op.target] >= 0;
+                bool dyn = false;
+                if (movable) {
+                    int n_in = 0, n_out = 0;
+                    for (int q = 0; q < 64; ++q)
+                        if ((op.cmask >> q) & 1) ((q < nl && local_of[q] >= 0) ? n_in : n_out)++;
+                    dyn = n_out > 0;
+                    movable = dyn ? (n_in == 0 && n_dyn < kMaxTailDyn) : (n_in <= 1);
+                }
                 if (movable)
                     for (int s2 : stay)
                         if (!commutes(op, out.lops[s2])) { movable = false; break; }
+                if (movable && dyn) ++n_dyn;
                 (movable ? tail : stay).push_back(idx);
             }
             if (!tail.empty()) {
@@ -454,15 +466,28 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
                 std::reverse(tail.begin(), tail.end());
                 for (int idx : tail) {
                     const LogicalOp& op = out.lops[idx];
-                    TailFlip tf{};
-                    tf.t_local = (uint8_t)local_of[op.target];
+                    const uint16_t et = (uint16_t)(1u << local_of[op.target]);
+                    uint64_t cm_out = 0, cv_out = 0;
+                    int cb = -1, cv = 1;
                     for (int q = 0; q < 64; ++q) {
                         if (!((op.cmask >> q) & 1)) continue;
                         const uint64_t v = (op.cval >> q) & 1;
-                        if (q < nl && local_of[q] >= 0) { tf.cmask_local |= (uint16_t)(1u << local_of[q]); tf.cval_local |= (uint16_t)(v << local_of[q]); }
-                        else { tf.cmask_out |= 1ULL << q; tf.cval_out |= v << q; }
+                        if (q < nl && local_of[q] >= 0) { cb = local_of[q]; cv = (int)v; }
+                        else { cm_out |= 1ULL << q; cv_out |= v << q; }
                     }
-                    pd.tail[pd.n_tail++] = tf;
+                    if (cm_out) {
+                        TailDyn& d = pd.dyn[pd.n_dyn++];
+                        d.cmask_out = cm_out; d.cval_out = cv_out; d.w = et;
+                    } else if (cb < 0) {
+                        pd.tail_const ^= et;
+                    } else {
+                        // l_t ^= l_cb (^ 1 for a control on zero), composed after everything folded so far
+                        for (int j = 0; j < kMaxTileBits; ++j) if ((pd.tail_lin[j] >> cb) & 1) pd.tail_lin[j] ^= et;
+                        for (int d = 0; d < pd.n_dyn; ++d) if ((pd.dyn[d].w >> cb) & 1) pd.dyn[d].w ^= et;
+                        if ((pd.tail_const >> cb) & 1) pd.tail_const ^= et;
+                        if (!cv) pd.tail_const ^= et;
+                    }
+                    ++pd.n_tail;
                 }
                 plan.op_idx.swap(stay);
             }
@@ -641,6 +666,14 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
             sd.op_end = (uint16_t)pd.n_ops;
             pd.sweep[pd.n_sweeps++] = sd;
             todo.swap(deferred);
+        }
+        {   // the final store's slot offsets: the folded flips' linear part applied to the last sweep's
+            const SweepDesc& last = pd.sweep[pd.n_sweeps - 1];
+            for (int k = 0; k < 16; ++k) {
+                unsigned v = 0;
+                for (int j = 0; j < kMaxTileBits; ++j) if ((last.slot_off[k] >> j) & 1) v ^= pd.tail_lin[j];
+                pd.store_slot_off[k] = (uint16_t)v;
+            }
         }
         out.passes.push_back(pd);
     }

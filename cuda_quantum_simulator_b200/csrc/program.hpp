@@ -121,15 +121,17 @@ struct TmaDim {
     uint8_t start_bit, range_bits, box_bits, pad;
 };
 
-// A controlled bit flip (X / CNOT / Toffoli) that ends a pass is not executed as an op: it is folded into the
-// tile-local index the final store goes to (l ^= 1 << t when the controls match).
-struct TailFlip {
-    uint16_t cmask_local, cval_local;   // controls that are tile bits (tile-local positions)
-    uint8_t t_local;                    // target, tile-local position
-    uint8_t pad[3];
+// Controlled bit flips (X / CNOT) that can slide to the end of a pass are not executed as ops: together they are
+// an affine map over GF(2) of the tile-local index, l -> A l ^ c, applied by the final store's addressing.  A flip
+// whose control lies outside the tile is a translation that fires per tile (TailDyn); flips with two or more
+// controls inside the tile are not affine and stay ops.
+struct TailDyn {
     uint64_t cmask_out, cval_out;       // controls outside the tile (global index bits)
+    uint16_t w;                         // tile-local index XOR when they match (already pushed through later flips)
+    uint16_t pad[3];
 };
-constexpr int kMaxTailFlips = 12;
+constexpr int kMaxTailFlips = 16;
+constexpr int kMaxTailDyn = 6;
 
 struct PassDesc {
     int32_t n;                   // qubits held in this buffer (local qubits when sharded)
@@ -143,14 +145,19 @@ struct PassDesc {
     int32_t n_phase;             // OP_PHASE ops in this pass
     int32_t phase_table_offset;  // into Program::phase_tables (entries)
     int32_t phase_term_offset;   // into Program::phase_terms
-    int32_t n_tail;              // trailing flips folded into the final store
+    int32_t n_tail;              // trailing flips folded into the final store (0: the map below is the identity)
+    int32_t n_dyn;               // of which translations that depend on the tile
     uint8_t tile_bits[kMaxTileBits];   // global bit of tile-local bit i (ascending)
     uint32_t xor_local;          // tile-local index XOR applied by the pass's final store (deferred X gates)
     uint64_t xor_tau;            // tile-number XOR: the tile read from tau is written to tau ^ xor_tau
     uint8_t tma_instr_bits;      // the top tma_instr_bits tile bits are enumerated by separate TMA instructions
     uint8_t pad[3];
     TmaDim tma_dim[5];
-    TailFlip tail[kMaxTailFlips];
+    uint16_t tail_lin[kMaxTileBits];   // A: image of tile-local bit j
+    uint16_t tail_const;               // c
+    uint16_t pad3;
+    uint16_t store_slot_off[16];       // A applied to the last sweep's slot_off
+    TailDyn dyn[kMaxTailDyn];
     Segment seg[kMaxSegments];
     SweepDesc sweep[kMaxSweeps];
 };

@@ -150,15 +150,15 @@ void run_pass(const Program& prog, const PassDesc& pd, uint64_t hi_bits, cplx* s
             const uint64_t stau = tau ^ pd.xor_tau;
             for (int s = 0; s < pd.n_segments; ++s)
                 sbase |= ((stau >> pd.seg[s].src_shift) & pd.seg[s].mask) << pd.seg[s].dst_shift;
-            // the final store's index permutation: trailing bit flips in order, then the X frame
+            // the final store's index map: the folded flips (affine map, per-tile translations), then the X frame
             std::vector<cplx> permuted(tile_amps);
+            uint32_t shift = pd.tail_const ^ pd.xor_local;
+            for (int f = 0; f < pd.n_dyn; ++f)
+                if ((gbase & pd.dyn[f].cmask_out) == pd.dyn[f].cval_out) shift ^= pd.dyn[f].w;
             for (uint32_t l = 0; l < tile_amps; ++l) {
-                uint32_t d = l;
-                for (int f = 0; f < pd.n_tail; ++f) {
-                    const TailFlip& tf = pd.tail[f];
-                    if ((gbase & tf.cmask_out) == tf.cval_out && (d & tf.cmask_local) == tf.cval_local) d ^= 1u << tf.t_local;
-                }
-                permuted[d ^ pd.xor_local] = tile[l];
+                uint32_t d = 0;
+                for (int j = 0; j < pd.t; ++j) if ((l >> j) & 1) d ^= pd.tail_lin[j];
+                permuted[d ^ shift] = tile[l];
             }
             for (uint32_t l = 0; l < tile_amps; ++l) state[(gidx[l] - base) + sbase] = permuted[l];
         }

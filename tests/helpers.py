@@ -77,6 +77,25 @@ def gates(lst):
     return out
 
 
+def flip_heavy_gates(n, rng, body, tail):
+    """A few dense gates, then a long run of X / CNOT / Toffoli / SWAP: what the compiler folds into store addressing."""
+    lst = []
+    for _ in range(body):
+        lst.append((str(rng.choice(["H", "T", "Ry"])), int(rng.integers(n))) if n else None)
+        if lst[-1][0] == "Ry":
+            lst[-1] = ("Ry", lst[-1][1], float(rng.uniform(-3, 3)))
+    for _ in range(tail):
+        kind = str(rng.choice(["X", "CNOT", "CNOT", "CNOT", "Toffoli", "SWAP"]))
+        qs = [int(q) for q in rng.permutation(n)[:3]]
+        if kind == "X" or n < 2:
+            lst.append(("X", qs[0]))
+        elif kind in ("CNOT", "SWAP") or n < 3:
+            lst.append((kind if kind != "Toffoli" else "CNOT", qs[0], qs[1]))
+        else:
+            lst.append(("Toffoli", qs[0], qs[1], qs[2]))
+    return gates(lst)
+
+
 def random_gates(n, depth, rng, kinds=None):
     """Random circuit over ALL 17 gate types (the reference's generator only draws H/X/CNOT/Rz)."""
     out = np.zeros(depth, GATE_DTYPE)

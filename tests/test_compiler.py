@@ -81,3 +81,16 @@ def test_plans_for_benchmark_circuits():
     assert H.emulator().emu_describe(20, 0, g1.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(g1)), 0, buf, 1 << 16) == 0
     passes = int(buf.value.decode().split(" passes")[0].split()[-1])
     assert passes <= 4
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_trailing_flips_fold_into_the_store(seed):
+    """Controlled flips at the end of a pass become an affine map of the store index (program.hpp TailDyn): controls
+    inside and outside the tile, controls on zero (after the X frame), Toffolis that must stay ops."""
+    rng = np.random.default_rng(500 + seed)
+    for n, tmax in ((3, 0), (7, 5), (13, 0), (14, 8), (15, 12)):
+        g = H.flip_heavy_gates(n, rng, body=int(rng.integers(0, 6)), tail=int(rng.integers(1, 30)))
+        st0 = H.random_state(n, rng)
+        want = H.oracle_run(n, g, st0)
+        got, _ = H.emu_run(n, g, st0, lmin=3, tmax=tmax)
+        assert np.max(np.abs(got - want)) < 1e-12, (n, tmax, seed)

@@ -61,6 +61,18 @@ def test_fuzz_all_gate_types_from_random_state(n):
         assert np.max(np.abs(got - want)) < 1e-12, (n, d, trial)
 
 
+@pytest.mark.parametrize("n", [2, 5, 12, 13, 14, 16, 19])
+def test_trailing_flips_fold_into_the_store(n):
+    """X / CNOT / Toffoli / SWAP runs at the end of a pass are folded into the final store's addressing."""
+    rng = np.random.default_rng(700 + n)
+    for trial in range(4):
+        g = H.flip_heavy_gates(n, rng, body=int(rng.integers(0, 8)), tail=int(rng.integers(1, 40)))
+        st0 = H.random_state(n, rng)
+        got, _ = run_gpu(n, g, st0)
+        want = H.oracle_run(n, g, st0)
+        assert np.max(np.abs(got - want)) < 1e-12, (n, trial)
+
+
 def test_every_gate_on_every_qubit_18q():
     """Each gate type with its target on every bit position class (lane, register, warp, outside-tile)."""
     n = 18

@@ -5,6 +5,9 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cuda_quantum_simulator_b200 as q
 
+if os.environ.get("QSIM_LIB"):   # development: load another build of the library
+    q._lib.LIB_PATH = os.path.abspath(os.environ["QSIM_LIB"])
+
 n = 30
 reps = 5
 sim = q.Simulator(n)

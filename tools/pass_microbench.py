@@ -9,6 +9,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import cuda_quantum_simulator_b200 as q
 
+if os.environ.get("QSIM_LIB"):   # development: load another build of the library
+    q._lib.LIB_PATH = os.path.abspath(os.environ["QSIM_LIB"])
+
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 reps = 5
 sim = q.Simulator(n)
