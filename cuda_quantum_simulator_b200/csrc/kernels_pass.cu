@@ -294,24 +294,28 @@ __device__ __forceinline__ void phase_op(const DevOp& op, const double2* __restr
 }
 
 #if QSIM_REG_BITS > 3
-#define QSIM_PAIR_CASES_BIT3(KIND)                                                          \
-    case (KIND) * 10 + 8: reg_pairs<3, KIND, false>(op, 0xffffu, xr, xi, yr, yi); break;   \
-    case (KIND) * 10 + 9: reg_pairs<3, KIND, true>(op, sm, xr, xi, yr, yi); break;
+#define QSIM_PAIR_CASES_BIT3(KIND)                                                                          \
+    case (KIND) * kOpcodesPerKind + 8: reg_pairs<3, KIND, false>(op, 0xffffu, xr, xi, yr, yi); break;      \
+    case (KIND) * kOpcodesPerKind + 9: reg_pairs<3, KIND, true>(op, sm, xr, xi, yr, yi); break;
 #else
 #define QSIM_PAIR_CASES_BIT3(KIND)
 #endif
-#define QSIM_PAIR_CASES(KIND)                                                                   \
-    case (KIND) * 10 + 0: lane_target<KIND, false>(op, 0xffffu, tid, xr, xi, yr, yi); break;   \
-    case (KIND) * 10 + 1: lane_target<KIND, true>(op, sm, tid, xr, xi, yr, yi); break;         \
-    case (KIND) * 10 + 2: reg_pairs<0, KIND, false>(op, 0xffffu, xr, xi, yr, yi); break;       \
-    case (KIND) * 10 + 3: reg_pairs<0, KIND, true>(op, sm, xr, xi, yr, yi); break;             \
-    case (KIND) * 10 + 4: reg_pairs<1, KIND, false>(op, 0xffffu, xr, xi, yr, yi); break;       \
-    case (KIND) * 10 + 5: reg_pairs<1, KIND, true>(op, sm, xr, xi, yr, yi); break;             \
-    case (KIND) * 10 + 6: reg_pairs<2, KIND, false>(op, 0xffffu, xr, xi, yr, yi); break;       \
-    case (KIND) * 10 + 7: reg_pairs<2, KIND, true>(op, sm, xr, xi, yr, yi); break;             \
+#if QSIM_REG_BITS > 2
+#define QSIM_PAIR_CASES_BIT2(KIND)                                                                          \
+    case (KIND) * kOpcodesPerKind + 6: reg_pairs<2, KIND, false>(op, 0xffffu, xr, xi, yr, yi); break;      \
+    case (KIND) * kOpcodesPerKind + 7: reg_pairs<2, KIND, true>(op, sm, xr, xi, yr, yi); break;
+#else
+#define QSIM_PAIR_CASES_BIT2(KIND)
+#endif
+#define QSIM_PAIR_CASES(KIND)                                                                                \
+    case (KIND) * kOpcodesPerKind + 0: lane_target<KIND, false>(op, 0xffffu, tid, xr, xi, yr, yi); break;   \
+    case (KIND) * kOpcodesPerKind + 1: lane_target<KIND, true>(op, sm, tid, xr, xi, yr, yi); break;         \
+    case (KIND) * kOpcodesPerKind + 2: reg_pairs<0, KIND, false>(op, 0xffffu, xr, xi, yr, yi); break;       \
+    case (KIND) * kOpcodesPerKind + 3: reg_pairs<0, KIND, true>(op, sm, xr, xi, yr, yi); break;             \
+    case (KIND) * kOpcodesPerKind + 4: reg_pairs<1, KIND, false>(op, 0xffffu, xr, xi, yr, yi); break;       \
+    case (KIND) * kOpcodesPerKind + 5: reg_pairs<1, KIND, true>(op, sm, xr, xi, yr, yi); break;             \
+    QSIM_PAIR_CASES_BIT2(KIND)                                                                               \
     QSIM_PAIR_CASES_BIT3(KIND)
-
-constexpr uint32_t kOpcodeCopy = 46;   // not produced by the compiler: stands in for a skipped op
 
 // one op, register file x -> register file y
 __device__ __forceinline__ void apply_op(const DevOp& op, uint32_t opcode, uint32_t sm, uint32_t tid, uint64_t gbase,
@@ -323,13 +327,14 @@ __device__ __forceinline__ void apply_op(const DevOp& op, uint32_t opcode, uint3
         QSIM_PAIR_CASES(OP_MATREAL)
         QSIM_PAIR_CASES(OP_ADIAG)
         QSIM_PAIR_CASES(OP_FLIP)
-        case 40: case 42: diagonal<false>(op, 0xffffu, tid, gbase, xr, xi, yr, yi); break;
-        case 44: phase_op(op, tables, eu, sd, tid, base_local, xr, xi, yr, yi); break;
+        case kOpcodeDiag + 0: case kOpcodeDiag + 2: diagonal<false>(op, 0xffffu, tid, gbase, xr, xi, yr, yi); break;
+        case kOpcodeDiag + 1: case kOpcodeDiag + 3: diagonal<true>(op, sm, tid, gbase, xr, xi, yr, yi); break;
+        case kOpcodePhase: phase_op(op, tables, eu, sd, tid, base_local, xr, xi, yr, yi); break;
         case kOpcodeCopy:
 #pragma unroll
             for (int k = 0; k < kSlots; ++k) { yr[k] = xr[k]; yi[k] = xi[k]; }
             break;
-        default: diagonal<true>(op, sm, tid, gbase, xr, xi, yr, yi); break;
+        default: __builtin_unreachable();
     }
 }
 

@@ -74,15 +74,18 @@ struct alignas(16) DevOp {
 };
 static_assert(sizeof(DevOp) == 128, "DevOp layout");
 
-// (the opcode table allows register bits 0..3 whatever kMaxRegBits is)
-// opcode = kind * 10 + home * 2 + ctrl for the pair-wise kinds (home: 0 = lane, 1 + j = register bit j),
-//          40 + home * 2 + ctrl for OP_DIAG (home: 0 = register-resident target, 1 = thread/outside target)
-constexpr int kNumOpcodes = 45;
-constexpr uint8_t kOpcodePhase = 44;
+// Dense dispatch codes (the interpreter's switch is one jump table):
+// opcode = kind * kOpcodesPerKind + home * 2 + ctrl for the pair-wise kinds (home: 0 = lane, 1 + j = register bit j),
+//          kOpcodeDiag + home * 2 + ctrl for OP_DIAG (home: 0 = register-resident target, 1 = thread/outside target)
+constexpr int kOpcodesPerKind = 2 * (1 + kMaxRegBits);
+constexpr uint8_t kOpcodeDiag = 4 * kOpcodesPerKind;
+constexpr uint8_t kOpcodePhase = kOpcodeDiag + 4;
+constexpr uint8_t kOpcodeCopy = kOpcodeDiag + 5;   // not produced by the compiler: the kernel's stand-in for a skipped op
+constexpr int kNumOpcodes = kOpcodeDiag + 6;
 inline uint8_t op_code(uint8_t kind, uint8_t thome, uint8_t tbit, bool ctrl) {
-    if (kind == OP_DIAG) return (uint8_t)(40 + (thome == T_REG ? 0 : 2) + (ctrl ? 1 : 0));
+    if (kind == OP_DIAG) return (uint8_t)(kOpcodeDiag + (thome == T_REG ? 0 : 2) + (ctrl ? 1 : 0));
     const int home = thome == T_LANE ? 0 : 1 + tbit;
-    return (uint8_t)(kind * 10 + home * 2 + (ctrl ? 1 : 0));
+    return (uint8_t)(kind * kOpcodesPerKind + home * 2 + (ctrl ? 1 : 0));
 }
 
 // OP_PHASE records reuse DevOp fields: cmask_out = first entry of the op's table in the pass's table blob,
