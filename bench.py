@@ -179,8 +179,7 @@ def main():
     stream = torch.cuda.current_stream()
 
     if world == 1:
-        state = torch.empty(1 << n_local, dtype=torch.complex128, device="cuda")
-        sim = q.Simulator(n, device_ptr=state.data_ptr())
+        sim = q.Simulator(n)   # library-owned state (what a user of the public API gets)
         sim.set_stream(stream.cuda_stream)
         sim.reset()
         prog = q.CompiledCircuit(circuit)
@@ -316,7 +315,9 @@ def main():
                      "circuit_level_gbs": n_passes * bytes_per_pass / (ms_per_step * 1e-3) / 1e9},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(e2e_sec.item()) * 1e3,
-                "what": "reset + run(host gate records: compile, upload, launch) + sample(1024 host uniforms) + indices to host"},
+                "what": "reset + run(host gate records: compile, upload, launch) + sample(1024 host uniforms) + indices to host; "
+                        "reset is lazy: the first pass after it generates |0..0> on chip (zero-fill + one tile) instead of "
+                        "a memset sweep followed by a load sweep; `value` is measured on the dense evolved state"},
         "gpu_launches": launches,
         "clocks": clocks,
     }

@@ -115,7 +115,8 @@ void Engine::drainTiming(double* total_ms, int64_t* n_passes, std::vector<double
 }
 
 void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tables, const PhaseTerm* d_terms,
-                       cuDoubleComplex* state, uint64_t hi_bits) {
+                       cuDoubleComplex* state, uint64_t hi_bits, int64_t init_basis) {
+    bool first = true;
     for (const PassDesc& pd : p.passes) {
         PassParams prm;
         prm.state = state;
@@ -127,6 +128,10 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
         prm.pd = pd;
         prm.stages = pick_stages(pd, stages_wanted_);
         prm.use_tensor_map = use_tensor_map_ ? 1 : 0;
+        prm.init_basis = (first && init_basis >= 0) ? 1 : 0;
+        prm.pad = 0;
+        prm.init_index = init_basis >= 0 ? (uint64_t)init_basis : 0;
+        first = false;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (timing_) {
             e0 = getEvent();
@@ -142,11 +147,11 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
     }
 }
 
-void Engine::execute(const Program& p, cuDoubleComplex* state, uint64_t hi_bits) {
+void Engine::execute(const Program& p, cuDoubleComplex* state, uint64_t hi_bits, int64_t init_basis) {
     const size_t n = p.ops.size();
     if (p.passes.empty()) return;
     if (n == 0) {   // passes without ops exist: a pure index permutation (deferred X gates)
-        launchAll(p, nullptr, nullptr, nullptr, state, hi_bits);
+        launchAll(p, nullptr, nullptr, nullptr, state, hi_bits, init_basis);
         return;
     }
     if (staged_pending_) {           // the pinned buffer may still be in flight from the previous run
@@ -189,13 +194,13 @@ void Engine::execute(const Program& p, cuDoubleComplex* state, uint64_t hi_bits)
         d_tables = static_cast<const double*>(d_aux_);
         d_terms = tt ? reinterpret_cast<const PhaseTerm*>(static_cast<char*>(d_aux_) + tb_pad) : nullptr;
     }
-    launchAll(p, d_ops_, d_tables, d_terms, state, hi_bits);
+    launchAll(p, d_ops_, d_tables, d_terms, state, hi_bits, init_basis);
 }
 
-void Engine::execute(const DeviceProgram& p, cuDoubleComplex* state, uint64_t hi_bits) {
+void Engine::execute(const DeviceProgram& p, cuDoubleComplex* state, uint64_t hi_bits, int64_t init_basis) {
     if (p.host.passes.empty()) return;
     if (!p.d_ops && !p.host.ops.empty()) throw std::runtime_error("qsim_b200: program was not uploaded");
-    launchAll(p.host, p.d_ops, p.d_tables, p.d_terms, state, hi_bits);
+    launchAll(p.host, p.d_ops, p.d_tables, p.d_terms, state, hi_bits, init_basis);
 }
 
 }  // namespace b200

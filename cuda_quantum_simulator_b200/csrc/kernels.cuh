@@ -22,6 +22,9 @@ struct PassParams {
     uint64_t n_tiles;         // 2^(pd.n - pd.t)
     int32_t stages;           // depth of the shared-memory ring
     int32_t use_tensor_map;   // 1: cp.async.bulk.tensor boxes (default); 0: one 1-D bulk copy per contiguous run
+    int32_t init_basis;       // 1: the memory holds nothing yet, the input state is the basis state |init_index>:
+    int32_t pad;              //    tiles are generated on chip, all-zero tiles are stored without interpretation
+    uint64_t init_index;
     PassDesc pd;
 };
 static_assert(sizeof(PassParams) <= 4000, "kernel parameter space");

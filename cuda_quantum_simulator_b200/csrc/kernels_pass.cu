@@ -441,7 +441,7 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
     };
     auto issue_store = [&](uint64_t i, uint64_t base) {
         const int s = (int)(i % n_stages);
-        if (xor_tau && !(i & 1)) {
+        if (xor_tau && !(i & 1) && !P.init_basis) {
             // this tile goes to its partner's location: the partner (item i+1) must have been read first
             const uint64_t j = i + 1;
             mbar_wait(&full[(int)(j % n_stages)], (uint32_t)((j / n_stages) & 1));
@@ -470,11 +470,26 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
         if (!xor_tau || odd) load_unit = next_unit(load_unit);
         ++n_loaded;
     };
-    if (warp == 0) {
+    if (warp == 0 && !P.init_basis) {
         const uint64_t pre = n_my < (uint64_t)n_stages ? n_my : (uint64_t)n_stages;
         for (uint64_t i = 0; i < pre; ++i) load_next();
     }
-
+    // Basis-state input (P.init_basis): nothing is loaded.  A tile that does not contain |init_index> is all zero
+    // before and after any op: those locations are zero-filled linearly by the whole grid (the memset this pass
+    // replaces, minus the one tile below); the tile that does contain it is generated in shared memory and takes the
+    // normal path.
+    uint64_t tile_mask = 0;
+    for (int j = 0; j < pd.t; ++j) tile_mask |= 1ULL << pd.tile_bits[j];
+    const uint64_t init_tile = P.init_index & ~tile_mask;
+    uint32_t init_local = 0;
+    for (int j = 0; j < pd.t; ++j) init_local |= (uint32_t)((P.init_index >> pd.tile_bits[j]) & 1ULL) << j;
+    if (P.init_basis) {
+        const uint64_t dest_tile = init_tile ^ xdep;   // where that tile is written (deferred X gates on outer bits)
+        const uint64_t n_amps = 1ULL << pd.n;
+        uint4* out = reinterpret_cast<uint4*>(P.state);
+        for (uint64_t idx = (uint64_t)blockIdx.x * kComputeThreads + tid; idx < n_amps; idx += (uint64_t)gridDim.x * kComputeThreads)
+            if ((idx & ~tile_mask) != dest_tile) out[idx] = make_uint4(0u, 0u, 0u, 0u);
+    }
     double ar[kSlots], ai[kSlots], br[kSlots], bi[kSlots];
     for (uint64_t i = 0; i < n_my; ++i) {
         const int s = (int)(i % n_stages);
@@ -484,6 +499,14 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
         if (!xor_tau || odd_item) cur_unit = next_unit(cur_unit);
         const uint64_t gbase = tbase | P.hi_bits;
         unsigned char* tile = tiles + (size_t)s * tile_bytes;
+        if (P.init_basis) {
+            if (tbase != init_tile) continue;   // (uniform over the CTA) zero-filled above
+            uint4* z = reinterpret_cast<uint4*>(tile);
+            for (uint32_t e = tid; e < tile_bytes / 16; e += kComputeThreads) z[e] = make_uint4(0u, 0u, 0u, 0u);
+            __syncthreads();
+            if (tid == 0) reinterpret_cast<double2*>(z)[init_local] = make_double2(1.0, 0.0);
+            __syncthreads();
+        }
         if (pd.n_phase > 0) {
             // factors of the fused diagonal runs that depend on index bits outside the tile: one (op, factor) per thread
             __syncthreads();   // the previous tile's readers of eu are done
@@ -504,7 +527,7 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
             }
             __syncthreads();
         }
-        mbar_wait(&full[s], parity);
+        if (!P.init_basis) mbar_wait(&full[s], parity);
 
 #pragma unroll 1
         for (int sw = 0; sw < pd.n_sweeps; ++sw) {
@@ -601,7 +624,7 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
         __syncthreads();
         if (warp == 0) {
             issue_store(i, tbase ^ xdep);
-            if (i >= 1 && n_loaded < n_my) {
+            if (!P.init_basis && i >= 1 && n_loaded < n_my) {
                 tma_store_wait_read_1();   // all but this lane's newest store group have finished reading shared memory
                 __syncwarp();              // ... for every lane: the stage of tile i-1 is free
                 load_next();               // item (i - 1) + n_stages

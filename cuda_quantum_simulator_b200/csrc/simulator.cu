@@ -22,13 +22,25 @@ qsim_gate_t to_record(const GateOp& g) {
     return r;
 }
 
+// A state that was reset and not touched since is still only a recorded basis index (StateVector::takePendingBasis):
+// the first pass then generates its tiles on chip instead of loading them.
+template <class ProgramT>
+void run_program(StateVector& sv, const ProgramT& prog, const b200::Program& host) {
+    uint64_t basis = 0;
+    if (!host.passes.empty() && sv.takePendingBasis(&basis))
+        sv.engine().execute(prog, sv.rawDevicePtr(), 0, (int64_t)basis);
+    else
+        sv.engine().execute(prog, sv.devicePtr(), 0);
+}
+void run_program(StateVector& sv, const b200::Program& prog) { run_program(sv, prog, prog); }
+
 void run_records(StateVector& sv, const std::vector<qsim_gate_t>& recs) {
     if (recs.empty()) return;
     b200::Program prog;
     std::string err;
     if (!b200::compile(sv.getNumQubits(), recs.data(), (int64_t)recs.size(), b200::default_options(), prog, &err))
         throw std::runtime_error(err);
-    sv.engine().execute(prog, sv.devicePtr(), 0);
+    run_program(sv, prog);
 }
 
 }  // namespace
@@ -62,7 +74,7 @@ void Simulator::applyGate(const GateOp& gate) {
 void Simulator::execute(const b200::DeviceProgram& program) {
     if (program.host.n != state_.getNumQubits())
         throw std::invalid_argument("Circuit qubit count doesn't match simulator");
-    state_.engine().execute(program, state_.devicePtr(), 0);
+    run_program(state_, program, program.host);
 }
 
 void Simulator::synchronize() const { state_.engine().synchronize(); }

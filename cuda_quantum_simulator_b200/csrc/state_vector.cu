@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstring>
 #include <random>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -45,8 +46,10 @@ StateVector::StateVector(int num_qubits, cuDoubleComplex* external) : num_qubits
 StateVector::~StateVector() { deallocate(); }
 
 StateVector::StateVector(StateVector&& o) noexcept
-    : num_qubits_(o.num_qubits_), size_(o.size_), d_state_(o.d_state_), owns_(o.owns_), engine_(std::move(o.engine_)) {
+    : num_qubits_(o.num_qubits_), size_(o.size_), d_state_(o.d_state_), owns_(o.owns_), pending_basis_(o.pending_basis_),
+      pending_idx_(o.pending_idx_), engine_(std::move(o.engine_)) {
     o.d_state_ = nullptr;
+    o.pending_basis_ = false;
     o.size_ = 0;
     o.num_qubits_ = 0;
 }
@@ -58,8 +61,11 @@ StateVector& StateVector::operator=(StateVector&& o) noexcept {
         size_ = o.size_;
         d_state_ = o.d_state_;
         owns_ = o.owns_;
+        pending_basis_ = o.pending_basis_;
+        pending_idx_ = o.pending_idx_;
         engine_ = std::move(o.engine_);
         o.d_state_ = nullptr;
+        o.pending_basis_ = false;
         o.size_ = 0;
         o.num_qubits_ = 0;
     }
@@ -83,12 +89,34 @@ void StateVector::initializeZero() { initializeBasis(0); }
 
 void StateVector::initializeBasis(size_t basis_idx) {
     if (basis_idx >= size_) throw std::invalid_argument("Basis index out of range");
+    if (owns_ && !std::getenv("QSIM_EAGER_INIT")) {
+        // nobody else can see this memory: defer the write (devicePtr() and every read-out materialise it)
+        pending_basis_ = true;
+        pending_idx_ = basis_idx;
+        return;
+    }
+    pending_basis_ = false;
     b200::launch_init_basis(d_state_, size_, basis_idx, engine_->stream());
     engine_->countLaunch(2);
     engine_->synchronize();   // the reference synchronises here too (src/StateVector.cu:188-190)
 }
 
+void StateVector::materialize() const {
+    if (!pending_basis_) return;
+    pending_basis_ = false;
+    b200::launch_init_basis(d_state_, size_, pending_idx_, engine_->stream());
+    engine_->countLaunch(2);
+}
+
+bool StateVector::takePendingBasis(uint64_t* basis_idx) {
+    if (!pending_basis_) return false;
+    pending_basis_ = false;
+    *basis_idx = pending_idx_;
+    return true;
+}
+
 void StateVector::setFromHost(const std::complex<double>* amplitudes) {
+    pending_basis_ = false;   // everything is overwritten
     CUDA_CHECK(cudaMemcpyAsync(d_state_, amplitudes, size_ * sizeof(cuDoubleComplex), cudaMemcpyHostToDevice,
                                engine_->stream()));
     engine_->synchronize();
@@ -96,7 +124,7 @@ void StateVector::setFromHost(const std::complex<double>* amplitudes) {
 
 void StateVector::toHost(std::complex<double>* out) const {
     static_assert(sizeof(std::complex<double>) == sizeof(cuDoubleComplex), "layout");
-    CUDA_CHECK(cudaMemcpyAsync(out, d_state_, size_ * sizeof(cuDoubleComplex), cudaMemcpyDeviceToHost,
+    CUDA_CHECK(cudaMemcpyAsync(out, devicePtr(), size_ * sizeof(cuDoubleComplex), cudaMemcpyDeviceToHost,
                                engine_->stream()));
     engine_->synchronize();
 }
@@ -114,7 +142,7 @@ void StateVector::getProbabilities(double* out, uint64_t first, uint64_t count) 
     double* buf = static_cast<double*>(engine_->scratch(1, cap * sizeof(double)));
     for (uint64_t done = 0; done < count; done += cap) {
         const uint64_t n = std::min<uint64_t>(cap, count - done);
-        b200::launch_probabilities(d_state_, buf, first + done, n, engine_->numSMs(), engine_->stream());
+        b200::launch_probabilities(devicePtr(), buf, first + done, n, engine_->numSMs(), engine_->stream());
         engine_->countLaunch();
         CUDA_CHECK(cudaMemcpyAsync(out + done, buf, n * sizeof(double), cudaMemcpyDeviceToHost, engine_->stream()));
         engine_->synchronize();
@@ -130,7 +158,7 @@ std::vector<double> StateVector::getProbabilities() const {
 // Same value as the reference's index-order host loop (src/StateVector.cu:235-242), computed on
 // the device by SequentialCdf.
 double StateVector::getTotalProbability() const {
-    b200::SequentialCdf cdf(d_state_, size_, -1, *engine_);
+    b200::SequentialCdf cdf(devicePtr(), size_, -1, *engine_);
     engine_->countLaunch(cdf.launches());
     return cdf.total();
 }
@@ -146,11 +174,11 @@ void StateVector::assertNormalized(double tolerance) const {
 
 double StateVector::partialProbability(int bit) const {
     engine_->countLaunch(2);
-    return b200::reduce_probability(d_state_, size_, bit, *engine_);
+    return b200::reduce_probability(devicePtr(), size_, bit, *engine_);
 }
 
 void StateVector::collapse(int bit, int outcome, double scale) {
-    b200::launch_collapse(d_state_, size_, bit, outcome, scale, engine_->numSMs(), engine_->stream());
+    b200::launch_collapse(devicePtr(), size_, bit, outcome, scale, engine_->numSMs(), engine_->stream());
     engine_->countLaunch();
 }
 
@@ -159,7 +187,7 @@ int StateVector::measureBit(int bit, double r, double* p0_out) {
         throw std::invalid_argument("Qubit index " + std::to_string(bit) + " out of range [0, " +
                                     std::to_string(num_qubits_ - 1) + "]");
     // p0 = index-order sum of the masked probabilities, exactly as the reference's host loop
-    b200::SequentialCdf cdf(d_state_, size_, bit, *engine_);
+    b200::SequentialCdf cdf(devicePtr(), size_, bit, *engine_);
     engine_->countLaunch(cdf.launches());
     const double p0 = cdf.total();
     if (p0_out) *p0_out = p0;
@@ -191,7 +219,7 @@ int StateVector::measure(int qubit) {
 
 std::vector<int64_t> StateVector::sampleWithUniforms(const double* uniforms, int64_t n_shots) {
     if (n_shots <= 0) throw std::invalid_argument("n_shots must be positive");
-    b200::SequentialCdf cdf(d_state_, size_, -1, *engine_);
+    b200::SequentialCdf cdf(devicePtr(), size_, -1, *engine_);
     std::vector<int64_t> out((size_t)n_shots);
     cdf.sample(uniforms, n_shots, out.data());
     engine_->countLaunch(cdf.launches());
@@ -199,7 +227,7 @@ std::vector<int64_t> StateVector::sampleWithUniforms(const double* uniforms, int
 }
 
 double StateVector::sampleShard(double c_init, bool first_shard, const double* uniforms, int64_t n_shots, int64_t* out) {
-    b200::SequentialCdf cdf(d_state_, size_, -1, *engine_, c_init);
+    b200::SequentialCdf cdf(devicePtr(), size_, -1, *engine_, c_init);
     const double c_end = cdf.total();
     if (n_shots > 0) {
         cdf.sample(uniforms, n_shots, out);

@@ -40,8 +40,9 @@ public:
 
     int getNumQubits() const { return num_qubits_; }
     size_t getSize() const { return size_; }
-    cuDoubleComplex* devicePtr() { return d_state_; }
-    const cuDoubleComplex* devicePtr() const { return d_state_; }
+    // (a pending lazy basis state, see takePendingBasis, is written out first)
+    cuDoubleComplex* devicePtr() { materialize(); return d_state_; }
+    const cuDoubleComplex* devicePtr() const { materialize(); return d_state_; }
 
     std::vector<std::complex<double>> toHost() const;
     std::vector<double> getProbabilities() const;
@@ -67,12 +68,21 @@ public:
 
     b200::Engine& engine() const { return *engine_; }
 
+    // initializeZero / initializeBasis on memory this object owns only RECORD the basis state; it is written by
+    // whoever needs the amplitudes first.  Simulator::run takes it over: its first pass generates the tiles on chip
+    // instead of loading them (no memset sweep, no load sweep).  Returns false when the memory is already valid.
+    bool takePendingBasis(uint64_t* basis_idx);
+    cuDoubleComplex* rawDevicePtr() { return d_state_; }   // no materialisation: only with takePendingBasis
+
 private:
     int num_qubits_ = 0;
     size_t size_ = 0;
     cuDoubleComplex* d_state_ = nullptr;
     bool owns_ = true;
+    mutable bool pending_basis_ = false;      // the memory does not hold the state yet: it is |pending_idx_>
+    mutable uint64_t pending_idx_ = 0;
     std::unique_ptr<b200::Engine> engine_;
+    void materialize() const;
 
     void allocate();
     void deallocate();
