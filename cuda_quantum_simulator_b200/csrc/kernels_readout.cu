@@ -198,61 +198,124 @@ __device__ __forceinline__ double replay_chunk(const cuDoubleComplex* __restrict
     return c;
 }
 
-// K4: one warp walks the chunks in order and records the exact running sum at every chunk start.
-__global__ void chunk_walk_kernel(const cuDoubleComplex* __restrict__ state, int mask_bit, int chunk, uint64_t m,
-                                  const double* __restrict__ delta, const double* __restrict__ bin_base,
-                                  const uint8_t* __restrict__ flag, double* __restrict__ start,
-                                  unsigned long long* __restrict__ n_slow, double c_init) {
+// K4: the exact running sum at every chunk start, in three launches.  The chunks are taken in groups of 32.
+//  (a) one warp per group, whole grid: a group whose non-zero chunks are all FAST in one binade has increments that are
+//      multiples of one ulp — they add exactly in any order, so a warp scan gives the group's total;
+//  (b) one warp stitches the group totals in order — one exact addition and one binade check per group — and replays,
+//      chunk by chunk, the few groups that need it;
+//  (c) one warp per group, whole grid: per-chunk starts = group start + exact in-group prefix.
+enum : uint8_t { G_ZERO = 0, G_SIMPLE = 1, G_COMPLEX = 2, G_DONE = 3 };
+
+// in-group scan shared by (a) and (c): returns the group's kind, its total and the lane's exclusive prefix
+__device__ __forceinline__ uint8_t group_scan(const double* __restrict__ delta, const double* __restrict__ bin_base,
+                                              const uint8_t* __restrict__ flag, uint64_t m, uint64_t group, double& total,
+                                              double& bb, double& excl) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t kk = group * 32 + lane;
+    const double d = kk < m ? delta[kk] : 0.0;
+    const double b = kk < m ? bin_base[kk] : 0.0;
+    const int f = kk < m ? (int)flag[kk] : (int)CH_ZERO;
+    const unsigned fast_mask = __ballot_sync(0xffffffffu, f == (int)CH_FAST);
+    const unsigned slow_mask = __ballot_sync(0xffffffffu, f == (int)CH_SLOW);
+    total = 0.0; bb = 0.0; excl = 0.0;
+    if (slow_mask != 0u) return G_COMPLEX;
+    if (fast_mask == 0u) return G_ZERO;
+    bb = __shfl_sync(0xffffffffu, b, __ffs(fast_mask) - 1);
+    const bool is_fast = (fast_mask >> lane) & 1u;
+    if (!__all_sync(0xffffffffu, !is_fast || b == bb)) return G_COMPLEX;
+    const double dd = is_fast ? d : 0.0;
+    double incl = dd;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl = __dadd_rn(incl, up);
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    excl = __dsub_rn(incl, dd);
+    return G_SIMPLE;
+}
+
+__global__ void group_summary_kernel(const double* __restrict__ delta, const double* __restrict__ bin_base,
+                                     const uint8_t* __restrict__ flag, uint64_t m, uint64_t n_groups,
+                                     double* __restrict__ g_total, double* __restrict__ g_bb, uint8_t* __restrict__ g_kind) {
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t g = warp; g < n_groups; g += n_warps) {
+        double total, bb, excl;
+        const uint8_t kind = group_scan(delta, bin_base, flag, m, g, total, bb, excl);
+        if ((threadIdx.x & 31) == 0) { g_kind[g] = kind; g_total[g] = total; g_bb[g] = bb; }
+    }
+}
+
+__global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, int mask_bit, int chunk, uint64_t m,
+                                    uint64_t n_groups, const double* __restrict__ delta,
+                                    const double* __restrict__ bin_base, const uint8_t* __restrict__ flag,
+                                    const double* __restrict__ g_total, const double* __restrict__ g_bb,
+                                    uint8_t* __restrict__ g_kind, double* __restrict__ g_start,
+                                    double* __restrict__ start, unsigned long long* __restrict__ n_slow, double c_init) {
     const int lane = threadIdx.x & 31;
     double c = c_init;
     unsigned long long slow = 0;
-    for (uint64_t k0 = 0; k0 < m; k0 += 32) {
-        const uint64_t kk = k0 + lane;
-        const double d = kk < m ? delta[kk] : 0.0;
-        const double b = kk < m ? bin_base[kk] : 0.0;
-        const int f = kk < m ? (int)flag[kk] : (int)CH_ZERO;
-        const int lim = (m - k0) < 32 ? (int)(m - k0) : 32;
-        // Fast path for a whole group of 32 chunks that stay in one binade: their increments are multiples of
-        // the same ulp and add exactly in any order, so a warp scan replaces 32 dependent additions.
-        {
-            const unsigned fast_mask = __ballot_sync(0xffffffffu, kk < m && f == (int)CH_FAST);
-            const unsigned slow_mask = __ballot_sync(0xffffffffu, kk < m && f == (int)CH_SLOW);
-            if (slow_mask == 0u) {
-                if (fast_mask == 0u) {   // nothing but zeros: the running sum does not move
-                    if (kk < m) start[kk] = c;
-                    continue;
-                }
-                const double bb = __shfl_sync(0xffffffffu, b, __ffs(fast_mask) - 1);
-                const bool is_fast = (fast_mask >> lane) & 1u;
-                if (__all_sync(0xffffffffu, !is_fast || b == bb)) {
-                    const double dd = is_fast ? d : 0.0;
-                    double incl = dd;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const double up = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl = __dadd_rn(incl, up);
-                    }
-                    const double total = __shfl_sync(0xffffffffu, incl, 31);
-                    const double c_end = __dadd_rn(c, total);
-                    if (c >= bb && c_end < 2.0 * bb) {
-                        if (kk < m) start[kk] = __dadd_rn(c, __dsub_rn(incl, dd));
-                        c = c_end;
-                        continue;
-                    }
-                }
+    // lane l holds the summary of group g0 + l; the next 32 are fetched while these are stitched
+    uint64_t gl = lane;
+    double t_nxt = gl < n_groups ? g_total[gl] : 0.0, b_nxt = gl < n_groups ? g_bb[gl] : 0.0;
+    int k_nxt = gl < n_groups ? (int)g_kind[gl] : (int)G_ZERO;
+    for (uint64_t g0 = 0; g0 < n_groups; g0 += 32) {
+        const double t_cur = t_nxt, b_cur = b_nxt;
+        const int k_cur = k_nxt;
+        gl = g0 + 32 + lane;
+        t_nxt = gl < n_groups ? g_total[gl] : 0.0;
+        b_nxt = gl < n_groups ? g_bb[gl] : 0.0;
+        k_nxt = gl < n_groups ? (int)g_kind[gl] : (int)G_ZERO;
+        const int cnt = (n_groups - g0) < 32 ? (int)(n_groups - g0) : 32;
+        double my_start = 0.0;
+        bool my_done = false;
+        for (int i = 0; i < cnt; ++i) {
+            const int kind = __shfl_sync(0xffffffffu, k_cur, i);
+            if (kind == G_ZERO) { if (lane == i) my_start = c; continue; }
+            if (kind == G_SIMPLE) {
+                const double bb = __shfl_sync(0xffffffffu, b_cur, i);
+                const double c_end = __dadd_rn(c, __shfl_sync(0xffffffffu, t_cur, i));
+                if (c >= bb && c_end < 2.0 * bb) { if (lane == i) my_start = c; c = c_end; continue; }   // exact binade check
             }
+            // chunk by chunk
+            const uint64_t k0 = (g0 + i) * 32, kk = k0 + lane;
+            const double d = kk < m ? delta[kk] : 0.0;
+            const double b = kk < m ? bin_base[kk] : 0.0;
+            const int f = kk < m ? (int)flag[kk] : (int)CH_ZERO;
+            const int lim = (m - k0) < 32 ? (int)(m - k0) : 32;
+            for (int j = 0; j < lim; ++j) {
+                const double dj = __shfl_sync(0xffffffffu, d, j), bj = __shfl_sync(0xffffffffu, b, j);
+                const int fj = __shfl_sync(0xffffffffu, f, j);
+                if (lane == 0) start[k0 + j] = c;
+                if (fj == CH_ZERO) continue;
+                const double cc = __dadd_rn(c, dj);
+                if (fj == CH_FAST && c >= bj && cc < 2.0 * bj) c = cc;   // exact binade check on the true values
+                else { c = replay_chunk(state, mask_bit, (k0 + j) * (uint64_t)chunk, chunk, c); ++slow; }
+            }
+            if (lane == i) my_done = true;
         }
-        for (int j = 0; j < lim; ++j) {
-            const double dj = __shfl_sync(0xffffffffu, d, j), bj = __shfl_sync(0xffffffffu, b, j);
-            const int fj = __shfl_sync(0xffffffffu, f, j);
-            if (lane == 0) start[k0 + j] = c;
-            if (fj == CH_ZERO) continue;
-            const double cc = __dadd_rn(c, dj);
-            if (fj == CH_FAST && c >= bj && cc < 2.0 * bj) c = cc;   // exact binade check on the true values
-            else { c = replay_chunk(state, mask_bit, (k0 + j) * (uint64_t)chunk, chunk, c); ++slow; }
+        if (lane < cnt) {
+            g_start[g0 + lane] = my_start;
+            if (my_done) g_kind[g0 + lane] = G_DONE;
         }
     }
     if (lane == 0) { start[m] = c; *n_slow = slow; }
+}
+
+__global__ void group_write_kernel(const double* __restrict__ delta, const double* __restrict__ bin_base,
+                                   const uint8_t* __restrict__ flag, uint64_t m, uint64_t n_groups,
+                                   const uint8_t* __restrict__ g_kind, const double* __restrict__ g_start,
+                                   double* __restrict__ start) {
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t g = warp; g < n_groups; g += n_warps) {
+        if (g_kind[g] == G_DONE) continue;
+        double total, bb, excl;
+        group_scan(delta, bin_base, flag, m, g, total, bb, excl);
+        const uint64_t kk = g * 32 + (threadIdx.x & 31);
+        if (kk < m) start[kk] = __dadd_rn(g_start[g], excl);
+    }
 }
 
 // K5: one warp per shot: binary search over the exact chunk ends, then replay inside the chunk.
@@ -351,9 +414,19 @@ SequentialCdf::SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_
     CUDA_CHECK_LAST_ERROR();
     chunk_surrogate_kernel<<<(unsigned)m_, kBlock, 0, stream>>>(state, mask_bit, chunk_, approx_, lo_, delta_, base_, flag_);
     CUDA_CHECK_LAST_ERROR();
-    chunk_walk_kernel<<<1, 32, 0, stream>>>(state, mask_bit, chunk_, m_, delta_, base_, flag_, start_, slow_, c_init);
+    // the approximate sums and lower bounds are dead now: their storage holds the group summaries
+    const uint64_t n_groups = (m_ + 31) / 32;
+    double *g_total = approx_, *g_bb = approx_ + n_groups, *g_start = approx_ + 2 * n_groups;
+    uint8_t* g_kind = reinterpret_cast<uint8_t*>(lo_);
+    const int g_grid = (int)std::min<uint64_t>((n_groups * 32 + kBlock - 1) / kBlock, (uint64_t)eng.numSMs() * 8);
+    group_summary_kernel<<<g_grid, kBlock, 0, stream>>>(delta_, base_, flag_, m_, n_groups, g_total, g_bb, g_kind);
     CUDA_CHECK_LAST_ERROR();
-    launches_ = 4;
+    group_stitch_kernel<<<1, 32, 0, stream>>>(state, mask_bit, chunk_, m_, n_groups, delta_, base_, flag_, g_total, g_bb,
+                                             g_kind, g_start, start_, slow_, c_init);
+    CUDA_CHECK_LAST_ERROR();
+    group_write_kernel<<<g_grid, kBlock, 0, stream>>>(delta_, base_, flag_, m_, n_groups, g_kind, g_start, start_);
+    CUDA_CHECK_LAST_ERROR();
+    launches_ = 6;
 }
 
 double SequentialCdf::total() const {
