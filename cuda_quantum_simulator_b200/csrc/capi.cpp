@@ -330,7 +330,8 @@ qsim_status_t qsim_sim_execute(qsim_sim_t* s, const qsim_program_t* p) {
         require(s != nullptr && p != nullptr, "null argument");
         if (p->dev.host.n != s->n_total || p->n_global != s->n_global)
             throw std::invalid_argument("Circuit qubit count doesn't match simulator");
-        s->sim->state().engine().execute(p->dev, s->sim->state().devicePtr(), s->hi_bits());
+        if (s->n_global == 0) s->sim->execute(p->dev);
+        else s->sim->state().engine().execute(p->dev, s->sim->state().devicePtr(), s->hi_bits());
     });
 }
 
@@ -434,6 +435,42 @@ qsim_status_t qsim_shard_swap_p2p(qsim_sim_t* s, void* peer_state, int global_qu
         b200::launch_swap_p2p(s->sim->state().devicePtr(), static_cast<cuDoubleComplex*>(peer_state), nl, local_qubit,
                               my_bit, eng.numSMs(), eng.stream());
         eng.countLaunch();
+    });
+}
+
+qsim_status_t qsim_program_last_tile_mask(const qsim_program_t* p, uint64_t* mask_out) {
+    return guarded([&] {
+        require(p != nullptr && mask_out != nullptr, "null argument");
+        uint64_t m = 0;
+        if (!p->dev.host.passes.empty()) {
+            const b200::PassDesc& pd = p->dev.host.passes.back();
+            for (int j = 0; j < pd.t; ++j) m |= 1ULL << pd.tile_bits[j];
+        }
+        *mask_out = m;
+    });
+}
+
+qsim_status_t qsim_shard_execute_exchange(qsim_sim_t* s, const qsim_program_t* p, void* alt_state, void* peer_alt_state,
+                                          int global_qubit, int local_qubit) {
+    return guarded([&] {
+        require(s != nullptr && p != nullptr && alt_state != nullptr && peer_alt_state != nullptr, "null argument");
+        if (p->dev.host.n != s->n_total || p->n_global != s->n_global)
+            throw std::invalid_argument("Circuit qubit count doesn't match simulator");
+        const int nl = s->n_total - s->n_global;
+        require(global_qubit >= nl && global_qubit < s->n_total, "global_qubit is not a global qubit");
+        require(local_qubit >= 0 && local_qubit < nl, "local_qubit is not a local qubit");
+        require(!p->dev.host.passes.empty(), "the program has no pass to fuse the exchange into");
+        const b200::PassDesc& pd = p->dev.host.passes.back();
+        for (int j = 0; j < pd.t; ++j)
+            require(pd.tile_bits[j] != local_qubit, "local_qubit is a tile qubit of the program's last pass");
+        b200::StoreRedirect rd;
+        rd.keep = static_cast<cuDoubleComplex*>(alt_state);
+        rd.send = static_cast<cuDoubleComplex*>(peer_alt_state);
+        rd.bit = local_qubit;
+        rd.keep_value = (s->rank >> (global_qubit - nl)) & 1;
+        StateVector& sv = s->sim->state();
+        sv.engine().execute(p->dev, sv.devicePtr(), s->hi_bits(), -1, &rd);
+        sv.rebindExternal(rd.keep);
     });
 }
 

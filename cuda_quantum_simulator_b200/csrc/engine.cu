@@ -115,9 +115,10 @@ void Engine::drainTiming(double* total_ms, int64_t* n_passes, std::vector<double
 }
 
 void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tables, const PhaseTerm* d_terms,
-                       cuDoubleComplex* state, uint64_t hi_bits, int64_t init_basis) {
+                       cuDoubleComplex* state, uint64_t hi_bits, int64_t init_basis, const StoreRedirect* redirect) {
     bool first = true;
     for (const PassDesc& pd : p.passes) {
+        const bool last = (&pd == &p.passes.back());
         PassParams prm;
         prm.state = state;
         prm.ops = d_ops + pd.op_offset;
@@ -132,6 +133,12 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
         prm.pad = 0;
         prm.init_index = init_basis >= 0 ? (uint64_t)init_basis : 0;
         first = false;
+        prm.redirect = (last && redirect) ? 1 : 0;
+        prm.redirect_bit = redirect ? redirect->bit : 0;
+        prm.redirect_keep = redirect ? redirect->keep_value : 0;
+        prm.send_ctas = 0;   // chosen by launch_pass
+        prm.dst_keep = (last && redirect) ? redirect->keep : nullptr;
+        prm.dst_send = (last && redirect) ? redirect->send : nullptr;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (timing_) {
             e0 = getEvent();
@@ -197,10 +204,11 @@ void Engine::execute(const Program& p, cuDoubleComplex* state, uint64_t hi_bits,
     launchAll(p, d_ops_, d_tables, d_terms, state, hi_bits, init_basis);
 }
 
-void Engine::execute(const DeviceProgram& p, cuDoubleComplex* state, uint64_t hi_bits, int64_t init_basis) {
+void Engine::execute(const DeviceProgram& p, cuDoubleComplex* state, uint64_t hi_bits, int64_t init_basis,
+                     const StoreRedirect* redirect) {
     if (p.host.passes.empty()) return;
     if (!p.d_ops && !p.host.ops.empty()) throw std::runtime_error("qsim_b200: program was not uploaded");
-    launchAll(p.host, p.d_ops, p.d_tables, p.d_terms, state, hi_bits, init_basis);
+    launchAll(p.host, p.d_ops, p.d_tables, p.d_terms, state, hi_bits, init_basis, redirect);
 }
 
 }  // namespace b200

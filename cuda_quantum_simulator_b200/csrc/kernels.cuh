@@ -25,6 +25,15 @@ struct PassParams {
     int32_t init_basis;       // 1: the memory holds nothing yet, the input state is the basis state |init_index>:
     int32_t pad;              //    tiles are generated on chip, all-zero tiles are stored without interpretation
     uint64_t init_index;
+    // Fused qubit exchange (sharded states): this pass stores OUT OF PLACE.  Tiles whose index bit `redirect_bit`
+    // equals `redirect_keep` go to dst_keep at the same index, the others to dst_send (the partner GPU's buffer,
+    // peer-mapped) at index ^ (1 << redirect_bit).  redirect_bit is never a tile bit of such a pass.
+    int32_t redirect;
+    int32_t redirect_bit;
+    int32_t redirect_keep;
+    int32_t send_ctas;        // > 0: CTAs [0, send_ctas) take the tiles that leave, the others the tiles that stay
+    cuDoubleComplex* dst_keep;
+    cuDoubleComplex* dst_send;
     PassDesc pd;
 };
 static_assert(sizeof(PassParams) <= 4000, "kernel parameter space");

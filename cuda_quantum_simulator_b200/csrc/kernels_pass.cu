@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace qsim {
@@ -341,7 +342,8 @@ __device__ __forceinline__ void apply_op(const DevOp& op, uint32_t opcode, uint3
 }  // namespace
 
 __global__ void __launch_bounds__(kComputeThreads, 1)
-fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ CUtensorMap tmap) {
+fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ CUtensorMap tmap,
+                  const __grid_constant__ CUtensorMap tmap_keep, const __grid_constant__ CUtensorMap tmap_send) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const PassDesc& pd = P.pd;
     const uint32_t tile_bytes = 16u << pd.t;
@@ -387,7 +389,7 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
     __syncthreads();
 
     const uint64_t n_tiles = P.n_tiles;
-    const uint64_t first = blockIdx.x, stride = gridDim.x;
+    uint64_t first = blockIdx.x, stride = gridDim.x;
     // Work items of this CTA.  Without a tile XOR item i is tile first + i*stride.  With one, tiles are
     // handled in partner pairs (tau, tau ^ xor_tau): items 2j and 2j+1 are the two members of pair
     // first + j*stride (the pair id is the tile number with the pivot bit of xor_tau squeezed out), each is
@@ -395,14 +397,26 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
     // (see the wait before the store below).
     const uint64_t xor_tau = pd.xor_tau;
     const int pivot = xor_tau ? 63 - __clzll((long long)xor_tau) : 0;
-    const uint64_t n_units = xor_tau ? n_tiles / 2 : n_tiles;
-    const uint64_t my_units = first < n_units ? (n_units - first + stride - 1) / stride : 0;
-    const uint64_t n_my = xor_tau ? 2 * my_units : my_units;
+    uint64_t n_units = xor_tau ? n_tiles / 2 : n_tiles;
     // Global base index of a unit = its number deposited into the index bits that are neither tile bits nor the
     // pivot ("holes").  Stepping to the next unit is an add with the holes filled so carries pass through them.
     const uint64_t xdep = xor_tau ? tile_base(pd, xor_tau) : 0ULL;   // index XOR between the members of a pair
     uint64_t holes = xor_tau ? tile_base(pd, 1ULL << pivot) : 0ULL;
     for (int j = 0; j < pd.t; ++j) holes |= 1ULL << pd.tile_bits[j];
+    // Fused exchange: the tiles that leave drain at NVLink speed, the ones that stay at HBM speed; mixing them in one
+    // CTA's three-stage ring makes every third stage wait for a slow drain.  So the grid is split: CTAs [0, send_ctas)
+    // take the leaving tiles, the rest the staying ones (the exchanged bit becomes one more hole with a fixed value).
+    uint64_t class_bits = 0;
+    if (P.redirect && P.send_ctas > 0 && P.send_ctas < (int)gridDim.x && !((xdep >> P.redirect_bit) & 1ULL)) {
+        const bool sender = (int)blockIdx.x < P.send_ctas;
+        first = sender ? blockIdx.x : blockIdx.x - P.send_ctas;
+        stride = sender ? P.send_ctas : gridDim.x - P.send_ctas;
+        n_units /= 2;
+        holes |= 1ULL << P.redirect_bit;
+        class_bits = (uint64_t)(sender ? (P.redirect_keep ^ 1) : P.redirect_keep) << P.redirect_bit;
+    }
+    const uint64_t my_units = first < n_units ? (n_units - first + stride - 1) / stride : 0;
+    const uint64_t n_my = xor_tau ? 2 * my_units : my_units;
     const uint64_t keep = ((1ULL << pd.n) - 1ULL) & ~holes;
     auto deposit = [&](uint64_t x) -> uint64_t {
         uint64_t r = 0;
@@ -411,8 +425,8 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
             if ((keep >> b) & 1ULL) { r |= ((x >> j) & 1ULL) << b; ++j; }
         return r;
     };
-    const uint64_t ustride = deposit(stride), ufirst = deposit(first);
-    auto next_unit = [&](uint64_t ub) -> uint64_t { return ((ub | holes) + ustride) & keep; };
+    const uint64_t ustride = deposit(stride), ufirst = deposit(first) | class_bits;
+    auto next_unit = [&](uint64_t ub) -> uint64_t { return (((ub | holes) + ustride) & keep) | class_bits; };
     const uint32_t n_runs = 1u << pd.n_high;
     const uint32_t run_bytes = 16u << pd.L;
     const uint32_t n_instr = 1u << pd.tma_instr_bits;
@@ -446,16 +460,25 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
             const uint64_t j = i + 1;
             mbar_wait(&full[(int)(j % n_stages)], (uint32_t)((j / n_stages) & 1));
         }
+        // fused qubit exchange: the whole tile stays (other buffer, same index) or leaves (partner GPU, bit flipped)
+        const CUtensorMap* smap = &tmap;
+        unsigned char* sdst = gstate;
+        if (P.redirect) {
+            const bool keep = (int)((base >> P.redirect_bit) & 1ULL) == P.redirect_keep;
+            smap = keep ? &tmap_keep : &tmap_send;
+            sdst = reinterpret_cast<unsigned char*>(keep ? P.dst_keep : P.dst_send);
+            if (!keep) base ^= 1ULL << P.redirect_bit;
+        }
         if (P.use_tensor_map) {
             for (uint32_t q = lane; q < n_instr; q += 32) {
                 int c[5];
                 tma_coords(pd, base + instr_offset(pd, q), c);
-                tma_store_5d(&tmap, c, tiles + (size_t)s * tile_bytes + (size_t)q * box_bytes);
+                tma_store_5d(smap, c, tiles + (size_t)s * tile_bytes + (size_t)q * box_bytes);
             }
         } else {
             for (uint32_t run = lane; run < n_runs; run += 32) {
                 const uint64_t g = base + run_offset(pd, run);
-                tma_store_1d(gstate + g * 16, tiles + (size_t)s * tile_bytes + (size_t)run * run_bytes, run_bytes);
+                tma_store_1d(sdst + g * 16, tiles + (size_t)s * tile_bytes + (size_t)run * run_bytes, run_bytes);
             }
         }
         tma_store_commit();   // every lane commits its own (possibly empty) bulk group
@@ -667,7 +690,7 @@ encode_fn get_encode() {
 }
 
 // The state viewed as a 5-D tensor of doubles whose dimensions are the pass's runs of tile bits.
-bool encode_tensor_map(const PassParams& prm, CUtensorMap* out) {
+bool encode_tensor_map(const PassParams& prm, void* base, CUtensorMap* out) {
     encode_fn enc = get_encode();
     if (!enc) return false;
     const PassDesc& pd = prm.pd;
@@ -680,7 +703,7 @@ bool encode_tensor_map(const PassParams& prm, CUtensorMap* out) {
         if (d == 0) { gdim[d] *= 2; box[d] *= 2; }
         else gstride[d - 1] = (cuuint64_t)16 << td.start_bit;
     }
-    return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, prm.state, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -688,9 +711,19 @@ bool encode_tensor_map(const PassParams& prm, CUtensorMap* out) {
 
 cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t stream) {
     PassParams params = params_in;
-    alignas(64) CUtensorMap tmap;
+    alignas(64) CUtensorMap tmap, tmap_keep, tmap_send;
     std::memset(&tmap, 0, sizeof(tmap));
-    if (params.use_tensor_map && !encode_tensor_map(params, &tmap)) return cudaErrorInvalidValue;
+    if (params.use_tensor_map && !encode_tensor_map(params, params.state, &tmap)) return cudaErrorInvalidValue;
+    tmap_keep = tmap;
+    tmap_send = tmap;
+    if (params.redirect) {
+        if (!params.dst_keep || !params.dst_send || params.init_basis) return cudaErrorInvalidValue;
+        for (int j = 0; j < params.pd.t; ++j)
+            if (params.pd.tile_bits[j] == params.redirect_bit) return cudaErrorInvalidValue;
+        if (params.use_tensor_map && (!encode_tensor_map(params, params.dst_keep, &tmap_keep) ||
+                                      !encode_tensor_map(params, params.dst_send, &tmap_send)))
+            return cudaErrorInvalidValue;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e =
@@ -701,7 +734,16 @@ cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t s
     const size_t smem = pass_smem_bytes(params.pd, params.stages);
     if (params.stages < 1 || smem > (size_t)kMaxDynamicSmem) return cudaErrorInvalidValue;
     uint64_t grid = params.n_tiles < (uint64_t)num_sms ? params.n_tiles : (uint64_t)num_sms;
-    fused_pass_kernel<<<(unsigned)grid, kComputeThreads, smem, stream>>>(params, tmap);
+    params.send_ctas = 0;
+    if (params.redirect && grid >= 16) {
+        // enough senders that their compute on the leaving half keeps up with NVLink, few enough that each sender's share
+        // of the link drains a stage about as fast as it computes one (measured on C2 at 31 q, 2 GPUs: 16 senders 43.8 ms
+        // per circuit, 32: 24.9, 48: 18.6, 63: 19.6, 100: 19.2, no split: 22.4)
+        int send = (int)(grid / 3);
+        if (const char* e = std::getenv("QSIM_SEND_CTAS")) send = std::atoi(e);
+        if (send > 0 && send < (int)grid) params.send_ctas = send;
+    }
+    fused_pass_kernel<<<(unsigned)grid, kComputeThreads, smem, stream>>>(params, tmap, tmap_keep, tmap_send);
     return cudaGetLastError();
 }
 

@@ -108,6 +108,12 @@ void StateVector::materialize() const {
     engine_->countLaunch(2);
 }
 
+void StateVector::rebindExternal(cuDoubleComplex* external) {
+    if (owns_) throw std::invalid_argument("rebindExternal needs a non-owning StateVector");
+    if (!external) throw std::invalid_argument("external device memory must not be null");
+    d_state_ = external;
+}
+
 bool StateVector::takePendingBasis(uint64_t* basis_idx) {
     if (!pending_basis_) return false;
     pending_basis_ = false;

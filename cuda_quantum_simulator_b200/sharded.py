@@ -19,6 +19,7 @@ on CPU with the gloo backend; the product never falls back to anything but CUDA.
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import byref, c_double, c_int64, c_uint64, c_void_p
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
@@ -135,37 +136,54 @@ class CudaShardEngine:
         self.stream = torch.cuda.current_stream()
         _lib.check(_lib.lib().qsim_sim_set_stream(self._h, c_void_p(self.stream.cuda_stream)))
         self._flag = torch.zeros(1, device="cuda")
-        self._peer_ptr = {}
+        self._peer_ptr = {}          # peer rank -> [pointer to its buffer 0, pointer to its buffer 1]
         self._peer_base = []
         self.exchange = exchange
         self._bounce = None
+        # Second shard buffer for the fused exchange (the last pass before a swap stores out of place, partly into the
+        # partner's second buffer).  Every rank flips buffers at the same steps, so `_cur` is the same number everywhere.
+        self._bufs = [self.state]
+        self._cur = 0
+        self.fused_exchanges = 0
         if world > 1 and exchange in ("auto", "p2p"):
             try:
+                free, _total = torch.cuda.mem_get_info()
+                shard_bytes = 16 << self.nl
+                want_alt = os.environ.get("QSIM_NO_FUSED_EXCHANGE") is None and free > shard_bytes + (4 << 30)
+                flags = [None] * world
+                dist.all_gather_object(flags, bool(want_alt))
+                if all(flags):
+                    self._bufs.append(torch.empty(1 << self.nl, dtype=torch.complex128, device="cuda"))
                 self._open_peers()
                 self.exchange = "p2p"
             except Exception:
                 if exchange == "p2p":
                     raise
                 self.exchange = "nccl"
+                self._bufs = [self.state]
         elif world > 1:
             self.exchange = "nccl"
 
     # -- peer memory ----------------------------------------------------------------------------
     def _open_peers(self):
-        handle = (ctypes.c_ubyte * 64)()
-        off = c_uint64()
-        _lib.check(_lib.lib().qsim_ipc_get_handle(c_void_p(self.state.data_ptr()), handle, byref(off)))
-        mine = (bytes(handle), int(off.value))
+        mine = []
+        for t in self._bufs:
+            handle = (ctypes.c_ubyte * 64)()
+            off = c_uint64()
+            _lib.check(_lib.lib().qsim_ipc_get_handle(c_void_p(t.data_ptr()), handle, byref(off)))
+            mine.append((bytes(handle), int(off.value)))
         everyone = [None] * self.world
         self.dist.all_gather_object(everyone, mine)
         for b in range(self.ng):
             peer = self.rank ^ (1 << b)
-            hbytes, poff = everyone[peer]
-            buf = (ctypes.c_ubyte * 64).from_buffer_copy(hbytes)
-            base = c_void_p()
-            _lib.check(_lib.lib().qsim_ipc_open_handle(buf, byref(base)))
-            self._peer_base.append(base)
-            self._peer_ptr[peer] = base.value + poff
+            ptrs = []
+            for hbytes, poff in everyone[peer]:
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(hbytes)
+                base = c_void_p()
+                _lib.check(_lib.lib().qsim_ipc_open_handle(buf, byref(base)))
+                self._peer_base.append(base)
+                ptrs.append(base.value + poff)
+            self._peer_ptr[peer] = ptrs
 
     def device_barrier(self):
         """Stream-ordered barrier across ranks: nobody's later kernels start before everybody's earlier ones ended."""
@@ -192,10 +210,31 @@ class CudaShardEngine:
         peer = self.rank ^ (1 << (global_qubit - self.nl))
         self.device_barrier()
         if self.exchange == "p2p":
-            _lib.check(_lib.lib().qsim_shard_swap_p2p(self._h, c_void_p(self._peer_ptr[peer]), global_qubit, local_qubit))
+            _lib.check(_lib.lib().qsim_shard_swap_p2p(self._h, c_void_p(self._peer_ptr[peer][self._cur]), global_qubit,
+                                                      local_qubit))
         else:
             self._swap_nccl(peer, global_qubit, local_qubit)
         self.device_barrier()
+
+    def run_program_then_swap(self, handle, global_qubit: int, local_qubit: int) -> bool:
+        """The program followed by the swap as ONE step: the program's last pass stores out of place, the half that
+        leaves going straight into the partner's other buffer over NVLink (qsim_shard_execute_exchange).  Returns
+        False, having done nothing, when that is not possible here (the caller then runs the two steps)."""
+        if self.exchange != "p2p" or len(self._bufs) < 2:
+            return False
+        mask = c_uint64()
+        _lib.check(_lib.lib().qsim_program_last_tile_mask(handle, byref(mask)))
+        if mask.value == 0 or (mask.value >> local_qubit) & 1:
+            return False
+        peer = self.rank ^ (1 << (global_qubit - self.nl))
+        alt = 1 - self._cur
+        _lib.check(_lib.lib().qsim_shard_execute_exchange(self._h, handle, c_void_p(self._bufs[alt].data_ptr()),
+                                                         c_void_p(self._peer_ptr[peer][alt]), global_qubit, local_qubit))
+        self._cur = alt
+        self.state = self._bufs[alt]
+        self.fused_exchanges += 1
+        self.device_barrier()
+        return True
 
     def _swap_nccl(self, peer: int, global_qubit: int, local_qubit: int):
         torch, dist = self.torch, self.dist
@@ -324,11 +363,21 @@ class ShardedSimulator:
         return CompiledPlan(plan, programs, frame, n_passes, n_ops, plan.n_swaps)
 
     def execute(self, cp: CompiledPlan):
-        for st, h in zip(cp.plan.steps, cp.programs):
+        steps, progs = cp.plan.steps, cp.programs
+        fuse = getattr(self.engine, "run_program_then_swap", None)
+        i = 0
+        while i < len(steps):
+            st = steps[i]
             if st.kind == "gates":
-                self.engine.run_program(h)
+                nxt = steps[i + 1] if i + 1 < len(steps) else None
+                if fuse is not None and nxt is not None and nxt.kind == "swap" and \
+                        fuse(progs[i], nxt.global_qubit, nxt.local_qubit):
+                    i += 2          # the program's last pass carried the exchange
+                    continue
+                self.engine.run_program(progs[i])
             else:
                 self.engine.swap(st.global_qubit, st.local_qubit)
+            i += 1
         self.perm = list(cp.plan.perm)
         self.frame = cp.frame_after
 

@@ -72,7 +72,9 @@ public:
     // whoever needs the amplitudes first.  Simulator::run takes it over: its first pass generates the tiles on chip
     // instead of loading them (no memset sweep, no load sweep).  Returns false when the memory is already valid.
     bool takePendingBasis(uint64_t* basis_idx);
-    cuDoubleComplex* rawDevicePtr() { return d_state_; }   // no materialisation: only with takePendingBasis
+    cuDoubleComplex* rawDevicePtr() { return d_state_; }
+    // non-owning views only: continue on other caller memory of the same size (double-buffered qubit exchange)
+    void rebindExternal(cuDoubleComplex* external_device_memory);   // no materialisation: only with takePendingBasis
 
 private:
     int num_qubits_ = 0;

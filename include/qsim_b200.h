@@ -164,6 +164,17 @@ QSIM_API qsim_status_t qsim_shard_create(int num_qubits, int n_global, int rank,
  * shard mapped into this process (CUDA IPC / peer access).  Both ranks call it; each moves half of
  * the pairs.  Callers synchronise ranks before and after. */
 QSIM_API qsim_status_t qsim_shard_swap_p2p(qsim_sim_t* s, void* peer_state, int global_qubit, int local_qubit);
+/* The same exchange FUSED into the last pass of program `p` (one kernel does the gate pass and the NVLink transfer,
+ * tile by tile): the pass stores out of place — amplitudes that stay go to `alt_state` (a second buffer of this
+ * rank, same size as the shard), amplitudes that leave go straight into `peer_alt_state` (the partner's second
+ * buffer, peer-mapped) — and the simulator continues on `alt_state`.  Nothing is written to the buffers any rank is
+ * still reading, so no rank synchronisation is needed BEFORE the call; synchronise ranks after it.  Fails with
+ * QSIM_ERR_INVALID_ARGUMENT, having done nothing, when the program has no pass or `local_qubit` is a tile qubit of
+ * its last pass (qsim_program_last_tile_mask): run qsim_sim_execute + qsim_shard_swap_p2p instead. */
+QSIM_API qsim_status_t qsim_shard_execute_exchange(qsim_sim_t* s, const qsim_program_t* p, void* alt_state,
+                                                   void* peer_alt_state, int global_qubit, int local_qubit);
+/* Bit q set: local qubit q is a tile qubit of the program's last pass (0 when the program has no pass). */
+QSIM_API qsim_status_t qsim_program_last_tile_mask(const qsim_program_t* p, uint64_t* mask_out);
 /* Bounce-buffer variant for NCCL send/recv: pack the half shard that must leave into `buf`
  * (chunk `chunk` of `n_chunks`), and unpack a received chunk. */
 QSIM_API qsim_status_t qsim_shard_pack_half(qsim_sim_t* s, int local_qubit, int keep_bit, int64_t chunk,

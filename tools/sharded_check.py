@@ -40,7 +40,8 @@ for seed, n in [(1, 12), (2, 16), (3, 18)]:
     assert np.all(np.abs(want[s]) ** 2 > 0)
     assert abs(sim.get_total_probability() - 1) < 1e-10
     if rank == 0:
-        print(f"n={n} seed={seed} exchange={sim.engine.exchange} swaps={sim.compile(c).n_swaps} max|err|={err:.2e}", flush=True)
+        print(f"n={n} seed={seed} exchange={sim.engine.exchange} swaps={sim.compile(c).n_swaps} "
+              f"fused={sim.engine.fused_exchanges} max|err|={err:.2e}", flush=True)
     sim.close()
 assert worst < 1e-10, worst
 
@@ -53,7 +54,8 @@ got = sim.get_state_vector()
 want = H.oracle_run(n, c.gates)
 err = float(np.max(np.abs(got - want)))
 if rank == 0:
-    print(f"createRandomCircuit({n},40,7): swaps={sim.compile(c).n_swaps} max|err|={err:.2e}", flush=True)
+    print(f"createRandomCircuit({n},40,7): swaps={sim.compile(c).n_swaps} fused={sim.engine.fused_exchanges} "
+          f"max|err|={err:.2e}", flush=True)
 assert err < 1e-10
 sim.close()
 
