@@ -25,3 +25,68 @@ def test_two_gpu_parity(exchange):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "sharded check ok" in out.stdout
+
+
+@pytest.mark.parametrize("nl,g_local,tail_x", [(14, 13, False), (16, 3, False), (20, 17, True), (21, 0, False)])
+def test_fused_exchange_on_one_gpu(nl, g_local, tail_x):
+    """qsim_shard_execute_exchange with both 'ranks' of a 2-shard state living on this one GPU: the program's last pass
+    stores the staying half into the rank's second buffer and the leaving half into the other rank's second buffer.
+    Checked against the oracle: gates on the full state, then the global<->local qubit swap as an index permutation."""
+    import ctypes
+    from ctypes import byref, c_uint64, c_void_p
+
+    import numpy as np
+    import torch
+
+    from cuda_quantum_simulator_b200 import _lib
+
+    L = _lib.lib()
+    n = nl + 1
+    rng = np.random.default_rng(900 + nl)
+    # gates on local qubits only, none on the victim at the end (so it is not a tile qubit of the last pass)
+    others = [q for q in range(nl) if q != g_local]
+    lst = []
+    for _ in range(30):
+        k = str(rng.choice(["H", "T", "CNOT", "Rz", "X"]))
+        a, b = (int(x) for x in rng.choice(others, 2, replace=False))
+        lst.append((k, a, b) if k == "CNOT" else (k, a, float(rng.uniform(-3, 3))) if k == "Rz" else (k, a))
+    if tail_x:
+        lst.append(("X", others[-1]))   # a deferred X on a high local qubit: the partner-tile store path
+    g = H.gates(lst)
+    full = H.random_state(n, rng)
+    want_gates = H.oracle_run(n, g, full)
+    idx = np.arange(1 << n, dtype=np.uint64)
+    bg, bl = (idx >> np.uint64(nl)) & np.uint64(1), (idx >> np.uint64(g_local)) & np.uint64(1)
+    src = (idx & ~((np.uint64(1) << np.uint64(nl)) | (np.uint64(1) << np.uint64(g_local)))) | (bl << np.uint64(nl)) | (bg << np.uint64(g_local))
+    want = want_gates[src.astype(np.int64)]
+
+    bufs = [[torch.empty(1 << nl, dtype=torch.complex128, device="cuda") for _ in range(2)] for _ in range(2)]
+    sims = []
+    for r in range(2):
+        h = c_void_p()
+        _lib.check(L.qsim_shard_create(n, 1, r, c_void_p(bufs[r][0].data_ptr()), byref(h)))
+        shard = np.ascontiguousarray(full[r << nl:(r + 1) << nl])
+        _lib.check(L.qsim_sim_set_state(h, shard.ctypes.data_as(c_void_p)))
+        sims.append(h)
+    prog = c_void_p()
+    _lib.check(L.qsim_program_compile_ex(n, 1, _lib.gates_ptr(g), len(g), c_uint64(0), byref(prog)))
+    mask = c_uint64()
+    _lib.check(L.qsim_program_last_tile_mask(prog, byref(mask)))
+    if (mask.value >> g_local) & 1:
+        # the victim is a tile qubit of the last pass: the call must refuse and leave everything untouched
+        rc = L.qsim_shard_execute_exchange(sims[0], prog, c_void_p(bufs[0][1].data_ptr()), c_void_p(bufs[1][1].data_ptr()), nl, g_local)
+        assert rc != 0
+    else:
+        for r in range(2):
+            _lib.check(L.qsim_shard_execute_exchange(sims[r], prog, c_void_p(bufs[r][1].data_ptr()),
+                                                     c_void_p(bufs[1 - r][1].data_ptr()), nl, g_local))
+        torch.cuda.synchronize()
+        got = np.concatenate([bufs[r][1].cpu().numpy() for r in range(2)])
+        assert np.max(np.abs(got - want)) < 1e-12
+        # the simulators continue on their second buffers
+        out = np.empty(1 << nl, np.complex128)
+        _lib.check(L.qsim_sim_get_state(sims[1], out.ctypes.data_as(c_void_p)))
+        assert np.array_equal(out, got[1 << nl:])
+    L.qsim_program_destroy(prog)
+    for h in sims:
+        L.qsim_sim_destroy(h)
