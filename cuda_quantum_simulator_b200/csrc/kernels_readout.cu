@@ -20,7 +20,10 @@
 // (src/Simulator.cu:319-325) — with explicit __dmul_rn/__dadd_rn so nvcc cannot contract it.
 #include "readout.cuh"
 
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
+#include <vector>
 
 #include "qsim/constants.hpp"
 
@@ -30,7 +33,6 @@ namespace b200 {
 namespace {
 
 constexpr int kBlock = 256;
-constexpr double kMargin = 1.9073486328125e-06;  // 2^-19: twice the (N-1)*2^-53 bound (N <= 2^33) on |sequential - exact| / sum
 
 __device__ __forceinline__ double prob_of(const cuDoubleComplex a) {
     return __dadd_rn(__dmul_rn(a.x, a.x), __dmul_rn(a.y, a.y));
@@ -103,15 +105,49 @@ __global__ void collapse_kernel(cuDoubleComplex* __restrict__ state, uint64_t n,
 
 // ---- exact sequential CDF ------------------------------------------------------------------------
 
-// K1: approximate (tree-order) sum of each chunk.
+// K1: approximate (tree-order) sum of each chunk and, in the same sweep, the chunk's exact sequential-order increment
+// under each of kCand CANDIDATE binades [2^-j, 2^(1-j)), j = 0..kCand-1, of the running sum (see K2b for why that is a
+// sum of independently rounded terms): almost every chunk of a normalised state starts in one of them, so the second
+// sweep over the state (K3) only revisits the rest.
+constexpr int kCand = 4;
+
 __global__ void chunk_approx_kernel(const cuDoubleComplex* __restrict__ state, int mask_bit, int chunk,
-                                    double* __restrict__ approx) {
+                                    double* __restrict__ approx, double* __restrict__ cand_delta,
+                                    uint8_t* __restrict__ cand_tie, uint64_t m) {
     __shared__ double red[32];
+    __shared__ int tie_bits;
     const uint64_t base = (uint64_t)blockIdx.x * chunk;
+    const bool cands = (chunk == 4096);
+    if (threadIdx.x == 0) tie_bits = 0;
     double acc = 0.0;
-    for (int j = threadIdx.x; j < chunk; j += blockDim.x) acc = __dadd_rn(acc, masked_prob(state, base + j, mask_bit));
-    const double s = block_sum(acc, red);
-    if (threadIdx.x == 0) approx[blockIdx.x] = s;
+    double s[kCand];
+    int tie = 0;
+#pragma unroll
+    for (int c = 0; c < kCand; ++c) s[c] = ldexp(1.0, -c);
+    for (int j = threadIdx.x; j < chunk; j += blockDim.x) {
+        const double x = masked_prob(state, base + j, mask_bit);
+        acc = __dadd_rn(acc, x);
+        if (cands && x != 0.0) {   // (adding zero changes nothing and cannot tie)
+#pragma unroll
+            for (int c = 0; c < kCand; ++c) {
+                const double t = __dadd_rn(s[c], x);
+                const double err = __dsub_rn(x, __dsub_rn(t, s[c]));   // exact while s >= x (Fast2Sum); else unused
+                if (fabs(err) == ldexp(1.0, -c - 53)) tie |= 1 << c;
+                s[c] = t;
+            }
+        }
+    }
+    const double total = block_sum(acc, red);
+    if (threadIdx.x == 0) approx[blockIdx.x] = total;
+    if (cands) {
+        if (tie) atomicOr(&tie_bits, tie);
+#pragma unroll
+        for (int c = 0; c < kCand; ++c) {
+            const double d = block_sum(__dsub_rn(s[c], ldexp(1.0, -c)), red);   // multiples of u: exact adds
+            if (threadIdx.x == 0) cand_delta[(uint64_t)c * m + blockIdx.x] = d;
+        }
+        if (threadIdx.x == 0) cand_tie[blockIdx.x] = (uint8_t)tie_bits;
+    }
 }
 
 // K2: single-block exclusive scan of the approximate chunk sums: lo[k] = approx start of chunk k.
@@ -132,68 +168,98 @@ __global__ void chunk_scan_kernel(const double* __restrict__ approx, uint64_t m,
     for (uint64_t i = b; i < e; ++i) { lo[i] = run; run += approx[i]; }
 }
 
-enum : uint8_t { CH_ZERO = 0, CH_FAST = 1, CH_SLOW = 2 };
+enum : uint8_t { CH_ZERO = 0, CH_FAST = 1, CH_SLOW = 2, CH_PENDING = 3 };
 
-// K3: per chunk, the sequential-order increment computed from the surrogate start 2^e.
-__global__ void chunk_surrogate_kernel(const cuDoubleComplex* __restrict__ state, int mask_bit, int chunk,
-                                       const double* __restrict__ approx, const double* __restrict__ lo,
-                                       double* __restrict__ delta, double* __restrict__ bin_base,
-                                       uint8_t* __restrict__ flag) {
-    __shared__ double ps[4096 + 256];
-    __shared__ double red[32];
-    __shared__ int tie_any;
-    const uint64_t k = blockIdx.x;
-    const double a_lo = lo[k], a_sum = approx[k], a_hi = a_lo + a_sum;
-    // classification (uniform across the block)
-    uint8_t f = CH_SLOW;
-    double base = 0.0;
-    if (a_sum == 0.0) f = CH_ZERO;  // a tree sum of non-negative terms is 0 only if every term is 0: c unchanged
-    else if (chunk == 4096 && a_lo > 1e-290) {
-        int ex;
-        frexp(a_lo, &ex);           // a_lo = m * 2^ex, m in [0.5, 1)
-        base = ldexp(1.0, ex - 1);  // 2^e with 2^e <= a_lo < 2^(e+1)
-        if (a_lo * (1.0 - kMargin) >= base && a_hi * (1.0 + kMargin) < 2.0 * base) f = CH_FAST;
-    }
-    if (f != CH_FAST) {
-        if (threadIdx.x == 0) { flag[k] = f; delta[k] = 0.0; bin_base[k] = 0.0; }
-        return;
-    }
-    if (threadIdx.x == 0) tie_any = 0;
-    const uint64_t g0 = k * (uint64_t)chunk;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int i = threadIdx.x + j * kBlock;
-        ps[i + (i >> 4)] = masked_prob(state, g0 + i, mask_bit);
-    }
-    __syncthreads();
-    const double half_u = ldexp(base, -53);   // u/2 with u = 2^(e-52)
-    double s = base;
-    bool tie = false;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const double x = ps[17 * threadIdx.x + j];
-        const double t = __dadd_rn(s, x);
-        const double err = __dsub_rn(x, __dsub_rn(t, s));   // exact: s >= x (Fast2Sum)
-        tie |= (fabs(err) == half_u);
-        s = t;
-    }
-    if (tie) atomicOr(&tie_any, 1);
-    const double d = block_sum(__dsub_rn(s, base), red);   // multiples of u below 2^(e+1): exact adds
-    if (threadIdx.x == 0) {
-        flag[k] = tie_any ? CH_SLOW : CH_FAST;
+// K2b: classify every chunk from the approximate running sum.  ZERO: all terms are zero.  Otherwise TENTATIVELY FAST
+// in the binade [2^e, 2^(e+1)) of the approximate start: while the running sum c stays inside one binade,
+// fl(c + p) = c + rn_u(p) with u = 2^(e-52) whatever c is, so the chunk's increment is a sum of independently rounded
+// terms — taken from K1's candidates when 2^e is one of them, else left PENDING for K3; a term that rounds on an exact
+// tie depends on c's parity and makes the chunk SLOW.  Whether c really stays inside the binade is decided later, by
+// the stitch, on the EXACT running sum (c >= 2^e and c + increment < 2^(e+1)); chunks that fail are replayed.
+__global__ void chunk_classify_kernel(int chunk, uint64_t m, const double* __restrict__ approx,
+                                      const double* __restrict__ lo, const double* __restrict__ cand_delta,
+                                      const uint8_t* __restrict__ cand_tie, double* __restrict__ delta,
+                                      double* __restrict__ bin_base, uint8_t* __restrict__ flag,
+                                      unsigned int* __restrict__ n_pending, unsigned int* __restrict__ pending) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += stride) {
+        const double a_lo = lo[k], a_sum = approx[k];
+        uint8_t f = CH_SLOW;
+        double base = 0.0, d = 0.0;
+        if (a_sum == 0.0) f = CH_ZERO;  // a tree sum of non-negative terms is 0 only if every term is 0: c unchanged
+        else if (chunk == 4096 && a_lo > 1e-290 && a_sum < a_lo) {
+            int ex;
+            frexp(a_lo, &ex);           // a_lo = m * 2^ex, m in [0.5, 1)
+            base = ldexp(1.0, ex - 1);  // 2^e with 2^e <= a_lo < 2^(e+1)
+            const int c = 1 - ex;       // candidate index of the binade starting at 2^-c
+            if (c >= 0 && c < kCand) {
+                d = cand_delta[(uint64_t)c * m + k];
+                f = ((cand_tie[k] >> c) & 1) ? CH_SLOW : CH_FAST;
+            } else {
+                f = CH_PENDING;
+                pending[atomicAdd(n_pending, 1u)] = (unsigned int)k;
+            }
+        }
+        flag[k] = f;
         delta[k] = d;
-        bin_base[k] = base;
+        bin_base[k] = (f == CH_SLOW) ? 0.0 : base;
     }
 }
 
-// Sequential replay of one chunk by a full warp (all lanes carry the same running sum).
+// K3: the pending chunks' sequential-order increments, computed from the surrogate start 2^e (a second read of those
+// chunks only).  Each thread adds 16 probabilities to 2^e; a term that rounds on an exact tie makes the chunk SLOW.
+__global__ void chunk_surrogate_kernel(const cuDoubleComplex* __restrict__ state, int mask_bit, int chunk,
+                                       const unsigned int* __restrict__ n_pending, const unsigned int* __restrict__ pending,
+                                       double* __restrict__ delta, const double* __restrict__ bin_base,
+                                       uint8_t* __restrict__ flag) {
+    __shared__ double red[32];
+    __shared__ int tie_any;
+    const unsigned int n = *n_pending;
+    for (unsigned int w = blockIdx.x; w < n; w += gridDim.x) {
+        const uint64_t k = pending[w];
+        const double base = bin_base[k];
+        if (threadIdx.x == 0) tie_any = 0;
+        __syncthreads();
+        const uint64_t g0 = k * (uint64_t)chunk;
+        const double half_u = ldexp(base, -53);   // u/2 with u = 2^(e-52)
+        double s = base;
+        bool tie = false;
+        for (int j = threadIdx.x; j < chunk; j += blockDim.x) {
+            const double x = masked_prob(state, g0 + j, mask_bit);
+            const double t = __dadd_rn(s, x);
+            const double err = __dsub_rn(x, __dsub_rn(t, s));   // exact: s >= x (Fast2Sum)
+            tie |= (fabs(err) == half_u);
+            s = t;
+        }
+        if (tie) atomicOr(&tie_any, 1);
+        const double d = block_sum(__dsub_rn(s, base), red);   // multiples of u below 2^(e+1): exact adds
+        if (threadIdx.x == 0) {
+            flag[k] = tie_any ? CH_SLOW : CH_FAST;
+            delta[k] = d;
+        }
+        __syncthreads();
+    }
+}
+
+// Sequential replay of one chunk by a full warp (all lanes carry the same running sum).  Only the additions form a
+// dependent chain: the next 32 probabilities are loaded and the 32 broadcasts issued ahead of it.
 __device__ __forceinline__ double replay_chunk(const cuDoubleComplex* __restrict__ state, int mask_bit, uint64_t g0,
                                                int chunk, double c) {
     const int lane = threadIdx.x & 31;
+    double p_next = (lane < chunk) ? masked_prob(state, g0 + lane, mask_bit) : 0.0;
     for (int g = 0; g < chunk; g += 32) {
-        const double p = (g + lane < chunk) ? masked_prob(state, g0 + g + lane, mask_bit) : 0.0;
-        const int lim = (chunk - g) < 32 ? (chunk - g) : 32;
-        for (int j = 0; j < lim; ++j) c = __dadd_rn(c, __shfl_sync(0xffffffffu, p, j));
+        const double p = p_next;
+        const int gn = g + 32 + lane;
+        p_next = (gn < chunk) ? masked_prob(state, g0 + gn, mask_bit) : 0.0;
+        if (chunk - g >= 32) {
+            double v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __shfl_sync(0xffffffffu, p, j);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) c = __dadd_rn(c, v[j]);
+        } else {
+            for (int j = 0; j < chunk - g; ++j) c = __dadd_rn(c, __shfl_sync(0xffffffffu, p, j));
+        }
     }
     return c;
 }
@@ -235,15 +301,43 @@ __device__ __forceinline__ uint8_t group_scan(const double* __restrict__ delta, 
     return G_SIMPLE;
 }
 
+// inclusive warp scan of exact addends (multiples of one ulp, or garbage that the caller's range check rejects)
+__device__ __forceinline__ double warp_incl_scan(double v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = __dadd_rn(v, up);
+    }
+    return v;
+}
+
 __global__ void group_summary_kernel(const double* __restrict__ delta, const double* __restrict__ bin_base,
-                                     const uint8_t* __restrict__ flag, uint64_t m, uint64_t n_groups,
-                                     double* __restrict__ g_total, double* __restrict__ g_bb, uint8_t* __restrict__ g_kind) {
+                                     const uint8_t* __restrict__ flag, int chunk, uint64_t m, uint64_t n_groups,
+                                     const double* __restrict__ cand_delta, const uint8_t* __restrict__ cand_tie,
+                                     double* __restrict__ g_total, double* __restrict__ g_bb, uint8_t* __restrict__ g_kind,
+                                     double* __restrict__ g_cand, uint8_t* __restrict__ g_tie) {
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
     for (uint64_t g = warp; g < n_groups; g += n_warps) {
         double total, bb, excl;
         const uint8_t kind = group_scan(delta, bin_base, flag, m, g, total, bb, excl);
-        if ((threadIdx.x & 31) == 0) { g_kind[g] = kind; g_total[g] = total; g_bb[g] = bb; }
+        if (lane == 0) { g_kind[g] = kind; g_total[g] = total; g_bb[g] = bb; }
+        // the group's total and tie flags under each candidate binade of K1 (the stitch picks by the exact sum)
+        const uint64_t kk = g * 32 + lane;
+        unsigned tie = (chunk == 4096 && kk < m) ? cand_tie[kk] : 0xffu;
+        if (kk >= m) tie = 0;
+        if (chunk != 4096) tie = 0xffu;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tie |= __shfl_xor_sync(0xffffffffu, tie, o);
+#pragma unroll
+        for (int c = 0; c < kCand; ++c) {
+            const double d = (chunk == 4096 && kk < m) ? cand_delta[(uint64_t)c * m + kk] : 0.0;
+            const double t = __shfl_sync(0xffffffffu, warp_incl_scan(d), 31);
+            if (lane == 0) g_cand[(uint64_t)c * n_groups + g] = t;
+        }
+        if (lane == 0) g_tie[g] = (uint8_t)tie;
     }
 }
 
@@ -252,6 +346,9 @@ __global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, i
                                     const double* __restrict__ bin_base, const uint8_t* __restrict__ flag,
                                     const double* __restrict__ g_total, const double* __restrict__ g_bb,
                                     uint8_t* __restrict__ g_kind, double* __restrict__ g_start,
+                                    const double* __restrict__ cand_delta, const uint8_t* __restrict__ cand_tie,
+                                    const double* __restrict__ g_cand, const uint8_t* __restrict__ g_tie,
+                                    uint8_t* __restrict__ g_choice,
                                     double* __restrict__ start, unsigned long long* __restrict__ n_slow, double c_init) {
     const int lane = threadIdx.x & 31;
     double c = c_init;
@@ -260,19 +357,50 @@ __global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, i
     uint64_t gl = lane;
     double t_nxt = gl < n_groups ? g_total[gl] : 0.0, b_nxt = gl < n_groups ? g_bb[gl] : 0.0;
     int k_nxt = gl < n_groups ? (int)g_kind[gl] : (int)G_ZERO;
+    double ct_nxt[kCand];
+    int tie_nxt = gl < n_groups ? (int)g_tie[gl] : 0xff;
+#pragma unroll
+    for (int cd = 0; cd < kCand; ++cd) ct_nxt[cd] = gl < n_groups ? g_cand[(uint64_t)cd * n_groups + gl] : 0.0;
     for (uint64_t g0 = 0; g0 < n_groups; g0 += 32) {
         const double t_cur = t_nxt, b_cur = b_nxt;
-        const int k_cur = k_nxt;
+        const int k_cur = k_nxt, tie_cur = tie_nxt;
+        double ct_cur[kCand];
+#pragma unroll
+        for (int cd = 0; cd < kCand; ++cd) ct_cur[cd] = ct_nxt[cd];
         gl = g0 + 32 + lane;
         t_nxt = gl < n_groups ? g_total[gl] : 0.0;
         b_nxt = gl < n_groups ? g_bb[gl] : 0.0;
         k_nxt = gl < n_groups ? (int)g_kind[gl] : (int)G_ZERO;
+        tie_nxt = gl < n_groups ? (int)g_tie[gl] : 0xff;
+#pragma unroll
+        for (int cd = 0; cd < kCand; ++cd) ct_nxt[cd] = gl < n_groups ? g_cand[(uint64_t)cd * n_groups + gl] : 0.0;
+        int my_choice = 0xff;
         const int cnt = (n_groups - g0) < 32 ? (int)(n_groups - g0) : 32;
         double my_start = 0.0;
         bool my_done = false;
         for (int i = 0; i < cnt; ++i) {
             const int kind = __shfl_sync(0xffffffffu, k_cur, i);
             if (kind == G_ZERO) { if (lane == i) my_start = c; continue; }
+            // the whole group under the candidate binade the EXACT running sum is in
+            if (c > 0.0) {
+                int ex;
+                frexp(c, &ex);
+                const int cd = 1 - ex;   // c in [2^-cd, 2^(1-cd))
+                if (cd >= 0 && cd < kCand && !((__shfl_sync(0xffffffffu, tie_cur, i) >> cd) & 1)) {
+                    double tot = 0.0;
+#pragma unroll
+                    for (int q = 0; q < kCand; ++q) {
+                        const double v = __shfl_sync(0xffffffffu, ct_cur[q], i);
+                        if (q == cd) tot = v;
+                    }
+                    const double c_end = __dadd_rn(c, tot);
+                    if (c_end < ldexp(1.0, ex)) {
+                        if (lane == i) { my_start = c; my_choice = cd; }
+                        c = c_end;
+                        continue;
+                    }
+                }
+            }
             if (kind == G_SIMPLE) {
                 const double bb = __shfl_sync(0xffffffffu, b_cur, i);
                 const double c_end = __dadd_rn(c, __shfl_sync(0xffffffffu, t_cur, i));
@@ -290,13 +418,26 @@ __global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, i
                 if (lane == 0) start[k0 + j] = c;
                 if (fj == CH_ZERO) continue;
                 const double cc = __dadd_rn(c, dj);
-                if (fj == CH_FAST && c >= bj && cc < 2.0 * bj) c = cc;   // exact binade check on the true values
-                else { c = replay_chunk(state, mask_bit, (k0 + j) * (uint64_t)chunk, chunk, c); ++slow; }
+                if (fj == CH_FAST && c >= bj && cc < 2.0 * bj) { c = cc; continue; }   // exact binade check on the true values
+                // the approximate start picked the wrong binade (c sits next to a power of two): try K1's candidate
+                // for the binade the exact c is in
+                if (chunk == 4096 && c > 0.0) {
+                    int ex;
+                    frexp(c, &ex);
+                    const int cd = 1 - ex;
+                    if (cd >= 0 && cd < kCand && !((cand_tie[k0 + j] >> cd) & 1)) {
+                        const double c2 = __dadd_rn(c, cand_delta[(uint64_t)cd * m + k0 + j]);
+                        if (c2 < ldexp(1.0, ex)) { c = c2; continue; }
+                    }
+                }
+                c = replay_chunk(state, mask_bit, (k0 + j) * (uint64_t)chunk, chunk, c);
+                ++slow;
             }
             if (lane == i) my_done = true;
         }
         if (lane < cnt) {
             g_start[g0 + lane] = my_start;
+            g_choice[g0 + lane] = (uint8_t)my_choice;
             if (my_done) g_kind[g0 + lane] = G_DONE;
         }
     }
@@ -306,14 +447,22 @@ __global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, i
 __global__ void group_write_kernel(const double* __restrict__ delta, const double* __restrict__ bin_base,
                                    const uint8_t* __restrict__ flag, uint64_t m, uint64_t n_groups,
                                    const uint8_t* __restrict__ g_kind, const double* __restrict__ g_start,
+                                   const double* __restrict__ cand_delta, const uint8_t* __restrict__ g_choice,
                                    double* __restrict__ start) {
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t g = warp; g < n_groups; g += n_warps) {
         if (g_kind[g] == G_DONE) continue;
-        double total, bb, excl;
-        group_scan(delta, bin_base, flag, m, g, total, bb, excl);
         const uint64_t kk = g * 32 + (threadIdx.x & 31);
+        const int choice = g_choice[g];
+        double excl;
+        if (choice < kCand) {   // stitched under a candidate binade
+            const double d = kk < m ? cand_delta[(uint64_t)choice * m + kk] : 0.0;
+            excl = __dsub_rn(warp_incl_scan(d), d);
+        } else {
+            double total, bb;
+            group_scan(delta, bin_base, flag, m, g, total, bb, excl);
+        }
         if (kk < m) start[kk] = __dadd_rn(g_start[g], excl);
     }
 }
@@ -399,34 +548,59 @@ SequentialCdf::SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_
     chunk_ = n >= 4096 ? 4096 : (int)n;
     m_ = n / (uint64_t)chunk_;
     const size_t m8 = (m_ + 2) * sizeof(double);
-    unsigned char* arena = static_cast<unsigned char*>(eng.scratch(0, 5 * m8 + 16 + m_ + 64));
+    const size_t m4 = ((m_ + 2) * sizeof(unsigned int) + 7) & ~(size_t)7;
+    const size_t m1 = (m_ + 8) & ~(size_t)7;
+    const uint64_t n_groups = (m_ + 31) / 32;
+    const size_t g8 = (n_groups + 1) * sizeof(double), g1 = (n_groups + 8) & ~(size_t)7;
+    unsigned char* arena = static_cast<unsigned char*>(
+        eng.scratch(0, (5 + kCand) * m8 + 16 + 2 * m1 + m4 + (3 + kCand) * g8 + 3 * g1 + 64));
     approx_ = reinterpret_cast<double*>(arena);
     lo_ = reinterpret_cast<double*>(arena + m8);
     delta_ = reinterpret_cast<double*>(arena + 2 * m8);
     base_ = reinterpret_cast<double*>(arena + 3 * m8);
     start_ = reinterpret_cast<double*>(arena + 4 * m8);
-    slow_ = reinterpret_cast<unsigned long long*>(arena + 5 * m8);
-    flag_ = arena + 5 * m8 + 16;
+    double* cand_delta = reinterpret_cast<double*>(arena + 5 * m8);
+    slow_ = reinterpret_cast<unsigned long long*>(arena + (5 + kCand) * m8);
+    unsigned int* n_pending = reinterpret_cast<unsigned int*>(arena + (5 + kCand) * m8 + 8);
+    flag_ = arena + (5 + kCand) * m8 + 16;
+    uint8_t* cand_tie = flag_ + m1;
+    unsigned int* pending = reinterpret_cast<unsigned int*>(cand_tie + m1);
     cudaStream_t stream = stream_;
-    chunk_approx_kernel<<<(unsigned)m_, kBlock, 0, stream>>>(state, mask_bit, chunk_, approx_);
+    CUDA_CHECK(cudaMemsetAsync(n_pending, 0, sizeof(unsigned int), stream));
+    chunk_approx_kernel<<<(unsigned)m_, kBlock, 0, stream>>>(state, mask_bit, chunk_, approx_, cand_delta, cand_tie, m_);
     CUDA_CHECK_LAST_ERROR();
     chunk_scan_kernel<<<1, 1024, 0, stream>>>(approx_, m_, lo_, c_init);
     CUDA_CHECK_LAST_ERROR();
-    chunk_surrogate_kernel<<<(unsigned)m_, kBlock, 0, stream>>>(state, mask_bit, chunk_, approx_, lo_, delta_, base_, flag_);
+    const int c_grid = (int)std::min<uint64_t>((m_ + kBlock - 1) / kBlock, (uint64_t)eng.numSMs() * 8);
+    chunk_classify_kernel<<<c_grid, kBlock, 0, stream>>>(chunk_, m_, approx_, lo_, cand_delta, cand_tie, delta_, base_, flag_,
+                                                        n_pending, pending);
     CUDA_CHECK_LAST_ERROR();
-    // the approximate sums and lower bounds are dead now: their storage holds the group summaries
-    const uint64_t n_groups = (m_ + 31) / 32;
-    double *g_total = approx_, *g_bb = approx_ + n_groups, *g_start = approx_ + 2 * n_groups;
-    uint8_t* g_kind = reinterpret_cast<uint8_t*>(lo_);
+    chunk_surrogate_kernel<<<eng.numSMs() * 8, kBlock, 0, stream>>>(state, mask_bit, chunk_, n_pending, pending, delta_,
+                                                                   base_, flag_);
+    CUDA_CHECK_LAST_ERROR();
+    if (std::getenv("QSIM_DEBUG_CDF")) {
+        std::vector<uint8_t> hf(m_);
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        cudaMemcpy(hf.data(), flag_, m_, cudaMemcpyDeviceToHost);
+        uint64_t cnt[4] = {0, 0, 0, 0};
+        for (uint64_t k = 0; k < m_; ++k) cnt[hf[k] & 3]++;
+        fprintf(stderr, "[cdf] zero %llu fast %llu slow %llu pending %llu\n", (unsigned long long)cnt[0], (unsigned long long)cnt[1], (unsigned long long)cnt[2], (unsigned long long)cnt[3]);
+    }
+    unsigned char* garena = reinterpret_cast<unsigned char*>(pending) + m4;
+    double* g_total = reinterpret_cast<double*>(garena);
+    double *g_bb = g_total + (n_groups + 1), *g_start = g_bb + (n_groups + 1), *g_cand = g_start + (n_groups + 1);
+    uint8_t* g_kind = garena + (3 + kCand) * g8;
+    uint8_t *g_tie = g_kind + g1, *g_choice = g_tie + g1;
     const int g_grid = (int)std::min<uint64_t>((n_groups * 32 + kBlock - 1) / kBlock, (uint64_t)eng.numSMs() * 8);
-    group_summary_kernel<<<g_grid, kBlock, 0, stream>>>(delta_, base_, flag_, m_, n_groups, g_total, g_bb, g_kind);
+    group_summary_kernel<<<g_grid, kBlock, 0, stream>>>(delta_, base_, flag_, chunk_, m_, n_groups, cand_delta, cand_tie, g_total, g_bb,
+                                                       g_kind, g_cand, g_tie);
     CUDA_CHECK_LAST_ERROR();
     group_stitch_kernel<<<1, 32, 0, stream>>>(state, mask_bit, chunk_, m_, n_groups, delta_, base_, flag_, g_total, g_bb,
-                                             g_kind, g_start, start_, slow_, c_init);
+                                             g_kind, g_start, cand_delta, cand_tie, g_cand, g_tie, g_choice, start_, slow_, c_init);
     CUDA_CHECK_LAST_ERROR();
-    group_write_kernel<<<g_grid, kBlock, 0, stream>>>(delta_, base_, flag_, m_, n_groups, g_kind, g_start, start_);
+    group_write_kernel<<<g_grid, kBlock, 0, stream>>>(delta_, base_, flag_, m_, n_groups, g_kind, g_start, cand_delta, g_choice, start_);
     CUDA_CHECK_LAST_ERROR();
-    launches_ = 6;
+    launches_ = 7;
 }
 
 double SequentialCdf::total() const {
@@ -445,6 +619,7 @@ uint64_t SequentialCdf::slowChunks() const {
 
 void SequentialCdf::sample(const double* uniforms_host, int64_t n_shots, int64_t* out_host) {
     if (n_shots <= 0) return;
+    if (std::getenv("QSIM_DEBUG_CDF")) fprintf(stderr, "[cdf] chunks %llu, replayed sequentially %llu\n", (unsigned long long)m_, (unsigned long long)slowChunks());
     unsigned char* arena = static_cast<unsigned char*>(eng_.scratch(1, (size_t)n_shots * 16));
     double* d_u = reinterpret_cast<double*>(arena);
     int64_t* d_out = reinterpret_cast<int64_t*>(arena + (size_t)n_shots * 8);

@@ -72,6 +72,43 @@ def test_sampling_flat_and_sparse_states():
     assert set(out.tolist()) <= {0, (1 << n) - 1}
 
 
+@pytest.mark.parametrize("shape", ["plateau_half", "noise_tail", "ties", "tiny_head", "over_one"])
+def test_sampling_hard_cdf_shapes(shape):
+    """States that stress the exact parallel CDF (csrc/kernels_readout.cu): the running sum parked on a power of two
+    over many chunks, a long tail of ~1e-34 probabilities after the sum has reached ~1, terms that round on exact ties,
+    a head of tiny probabilities (many binades per chunk), and a sum that passes 1.0.  All must equal the host's
+    sequential algorithm bit for bit — and stay fast (the replay path is sequential)."""
+    n = 20
+    N = 1 << n
+    rng = np.random.default_rng(77)
+    amp = np.zeros(N, np.complex128)
+    if shape == "plateau_half":
+        amp[: N // 4] = np.sqrt(0.5 / (N // 4))                  # c reaches 0.5 (up to rounding) at N/4
+        amp[N // 4: 3 * N // 4] = 1e-40 * rng.random(N // 2)     # ... and sits there for half the state
+        amp[3 * N // 4:] = np.sqrt(0.5 / (N // 4))
+    elif shape == "noise_tail":
+        amp[: N // 2] = rng.normal(size=N // 2) + 1j * rng.normal(size=N // 2)
+        amp[: N // 2] /= np.linalg.norm(amp[: N // 2])
+        amp[N // 2:] = 1e-17 * (rng.normal(size=N // 2) + 1j * rng.normal(size=N // 2))
+    elif shape == "ties":
+        # p = 3 * 2^-54 style terms: half an ulp of the running sum once it is in [0.5, 1)
+        amp[:] = np.sqrt(1.0 / N)
+        amp[N // 2 + 5:: 97] = np.sqrt(3.0 * 2.0 ** -54)
+    elif shape == "tiny_head":
+        amp[: N // 2] = 10.0 ** rng.uniform(-160, -20, N // 2)
+        amp[N // 2:] = np.sqrt(1.0 / (N // 2))
+    else:
+        amp[:] = np.sqrt(1.0000001 / N)                            # unnormalised on purpose: the sum crosses 1.0
+    sim = prepared(n, [], amp)
+    probs = H.oracle_probs(amp)
+    cum = np.cumsum(probs)
+    picks = cum[rng.integers(0, N, 256)]
+    u = np.concatenate([rng.random(1024), picks, np.nextafter(picks, 0), np.nextafter(picks, 2), [0.0, 0.5, 0.25]])
+    u = u[u < 1.0]
+    assert np.array_equal(sim.sample(0, uniforms=u), H.oracle_sample(probs, u))
+    assert sim.get_total_probability() == H.oracle().orc_total_probability(probs.ctypes.data_as(H.P), H.c_int64(len(probs)))
+
+
 def test_measure_matches_reference_semantics():
     """StateVector::measure: bit n-1-q, r < p0 ? 0 : 1, collapse by 1/sqrt(p) (src/StateVector.cu:260-314)."""
     rng = np.random.default_rng(9)
