@@ -18,6 +18,7 @@ using cplx = std::complex<double>;
 namespace {
 
 long g_tma_errors = 0;
+long g_bank_conflicts = 0;
 
 void run_pass(const Program& prog, const PassDesc& pd, uint64_t hi_bits, cplx* state) {
     const DevOp* ops = prog.ops.data() + pd.op_offset;
@@ -99,6 +100,15 @@ void run_pass(const Program& prog, const PassDesc& pd, uint64_t hi_bits, cplx* s
                     for (int k = 0; k < 16; ++k)
                         reg[lane][k] = (active[lane] && k < slots) ? tile[bl + sd.slot_off[k]] : cplx(0, 0);
                 }
+                // shared-memory rows: the 8 lanes of a quarter warp must touch 8 different 16-byte columns
+                if (sd.nthr >= 5 && pd.t >= 3)
+                    for (int k = 0; k < slots; ++k)
+                        for (int q = 0; q < 32; q += 8) {
+                            unsigned cols = 0;
+                            for (int lane = q; lane < q + 8; ++lane)
+                                if (active[lane]) cols |= 1u << ((base_local[lane] + sd.slot_off[k]) & 7u);
+                            if (active[q + 7] && cols != 0xffu) g_bank_conflicts++;
+                        }
                 for (int o = sd.op_begin; o < sd.op_end; ++o) {
                     const DevOp& op = ops[o];
                     if (op.kind != OP_PHASE && (gbase & op.cmask_out) != op.cval_out) continue;   // (PHASE reuses these fields)
@@ -199,7 +209,12 @@ int emu_run_ex(int n, int n_global, int rank, const qsim_gate_t* gates, int64_t 
     }
     const uint64_t hi = (uint64_t)rank << prog.n_local;
     g_tma_errors = 0;
+    g_bank_conflicts = 0;
     for (const PassDesc& pd : prog.passes) run_pass(prog, pd, hi, reinterpret_cast<cplx*>(state));
+    if (g_bank_conflicts) {
+        if (err && errcap > 0) std::snprintf(err, errcap, "shared-memory bank conflicts in a sweep's rows (%ld)", g_bank_conflicts);
+        return -3;
+    }
     if (g_tma_errors) {
         if (err && errcap > 0) std::snprintf(err, errcap, "tensor-map geometry mismatch (%ld)", g_tma_errors);
         return -2;
