@@ -384,10 +384,23 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
     while (!pending.empty()) {
         PassPlan plan;
         std::vector<int> deferred;
+        // Sweep budget: a sweep can target five tile bits besides the lowest three, so every time a sixth distinct
+        // target shows up among the ops taken in order, another sweep starts (the sweep scheduler below reorders with
+        // commutation and only does better).  The pass is closed before that estimate exceeds what PassDesc holds.
+        uint64_t sweep_targets = 0;
+        int sweeps_est = 1;
+        bool closed = false;
         for (int idx : pending) {
             const LogicalOp& op = out.lops[idx];
             uint64_t need = plan.need | (is_diag_kind(op.kind) ? 0ULL : (1ULL << op.target));
-            bool ok = tile_feasible(need, nl, t, lmin) && (int)plan.op_idx.size() < kMaxOpsPerPass;
+            bool ok = !closed && tile_feasible(need, nl, t, lmin) && (int)plan.op_idx.size() < kMaxOpsPerPass;
+            if (ok && !is_diag_kind(op.kind) && !((sweep_targets >> op.target) & 1ULL)) {
+                if (__builtin_popcountll(sweep_targets) >= 5) {
+                    if (sweeps_est + 1 >= kMaxSweeps) { ok = false; closed = true; }
+                    else { ++sweeps_est; sweep_targets = 0; }
+                }
+                if (ok) sweep_targets |= 1ULL << op.target;
+            }
             if (ok && !deferred.empty()) {
                 if (!opt.reorder) ok = false;
                 else

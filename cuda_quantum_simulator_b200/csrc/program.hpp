@@ -33,7 +33,8 @@ constexpr int kComputeWarps = 1 << (kMaxTileBits - kMaxRegBits - 5);      // a f
 constexpr int kComputeThreads = kComputeWarps * 32;
 constexpr int kMaxSweeps = 12;
 constexpr int kMaxSegments = 14;
-constexpr int kMaxOpsPerPass = 160;      // ops of one pass are staged in shared memory
+constexpr int kMaxOpsPerPass = 128;      // ops of one pass are staged in shared memory (with kMaxSweeps and kMaxPhaseOps this
+                                         // keeps three 64 KiB stages + tables within the 227 KiB of shared memory)
 constexpr int kMaxPhaseOps = 24;         // fused diagonal runs per pass (13 complex factors each in shared memory)
 constexpr int kPhaseTableSize = 1 << kMaxTileBits;   // one complex factor per tile-local index
 
