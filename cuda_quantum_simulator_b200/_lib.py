@@ -100,6 +100,8 @@ def _declare(L: ctypes.CDLL) -> None:
         "qsim_sim_pass_times": (c_int, [P, P, c_int64, POINTER(c_int64)]),
         "qsim_shard_create": (c_int, [c_int, c_int, c_int, P, PP]),
         "qsim_shard_swap_p2p": (c_int, [P, P, c_int, c_int]),
+        "qsim_shard_cdf_prepare": (c_int, [P, P]),
+        "qsim_shard_cdf_classify": (c_int, [P, c_double]),
         "qsim_shard_execute_exchange": (c_int, [P, P, P, P, c_int, c_int]),
         "qsim_program_last_tile_mask": (c_int, [P, P]),
         "qsim_shard_pack_half": (c_int, [P, c_int, c_int, c_int64, c_int64, P]),

@@ -573,6 +573,20 @@ qsim_status_t qsim_shard_sample(qsim_sim_t* s, double c_init, int first_shard, c
     });
 }
 
+qsim_status_t qsim_shard_cdf_prepare(qsim_sim_t* s, double* approx_total) {
+    return guarded([&] {
+        require(s != nullptr && approx_total != nullptr, "null argument");
+        *approx_total = s->sim->state().sampleShardPrepare();
+    });
+}
+
+qsim_status_t qsim_shard_cdf_classify(qsim_sim_t* s, double approx_c_init) {
+    return guarded([&] {
+        require(s != nullptr, "null simulator");
+        s->sim->state().sampleShardClassify(approx_c_init);
+    });
+}
+
 // ---- noisy ------------------------------------------------------------------------------------
 
 qsim_status_t qsim_noisy_create(int n, const qsim_noise_channel_t* ch, int nch, qsim_noisy_t** out) {

@@ -545,38 +545,77 @@ void launch_collapse(cuDoubleComplex* state, uint64_t n, int bit, int outcome, d
 
 SequentialCdf::SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, Engine& eng, double c_init)
     : state_(state), n_(n), mask_bit_(mask_bit), stream_(eng.stream()), eng_(eng) {
-    chunk_ = n >= 4096 ? 4096 : (int)n;
-    m_ = n / (uint64_t)chunk_;
+    setup();
+    prepare();
+    classify(c_init);
+    stitch(c_init);
+}
+
+SequentialCdf::SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, Engine& eng, Deferred)
+    : state_(state), n_(n), mask_bit_(mask_bit), stream_(eng.stream()), eng_(eng) {
+    setup();
+    prepare();
+}
+
+void SequentialCdf::setup() {
+    chunk_ = n_ >= 4096 ? 4096 : (int)n_;
+    m_ = n_ / (uint64_t)chunk_;
+    n_groups_ = (m_ + 31) / 32;
     const size_t m8 = (m_ + 2) * sizeof(double);
     const size_t m4 = ((m_ + 2) * sizeof(unsigned int) + 7) & ~(size_t)7;
     const size_t m1 = (m_ + 8) & ~(size_t)7;
-    const uint64_t n_groups = (m_ + 31) / 32;
-    const size_t g8 = (n_groups + 1) * sizeof(double), g1 = (n_groups + 8) & ~(size_t)7;
+    const size_t g8 = (n_groups_ + 1) * sizeof(double), g1 = (n_groups_ + 8) & ~(size_t)7;
     unsigned char* arena = static_cast<unsigned char*>(
-        eng.scratch(0, (5 + kCand) * m8 + 16 + 2 * m1 + m4 + (3 + kCand) * g8 + 3 * g1 + 64));
+        eng_.scratch(0, (5 + kCand) * m8 + 16 + 2 * m1 + m4 + (3 + kCand) * g8 + 3 * g1 + 64));
     approx_ = reinterpret_cast<double*>(arena);
     lo_ = reinterpret_cast<double*>(arena + m8);
     delta_ = reinterpret_cast<double*>(arena + 2 * m8);
     base_ = reinterpret_cast<double*>(arena + 3 * m8);
     start_ = reinterpret_cast<double*>(arena + 4 * m8);
-    double* cand_delta = reinterpret_cast<double*>(arena + 5 * m8);
+    cand_delta_ = reinterpret_cast<double*>(arena + 5 * m8);
     slow_ = reinterpret_cast<unsigned long long*>(arena + (5 + kCand) * m8);
-    unsigned int* n_pending = reinterpret_cast<unsigned int*>(arena + (5 + kCand) * m8 + 8);
+    n_pending_ = reinterpret_cast<unsigned int*>(arena + (5 + kCand) * m8 + 8);
     flag_ = arena + (5 + kCand) * m8 + 16;
-    uint8_t* cand_tie = flag_ + m1;
-    unsigned int* pending = reinterpret_cast<unsigned int*>(cand_tie + m1);
+    cand_tie_ = flag_ + m1;
+    pending_ = reinterpret_cast<unsigned int*>(cand_tie_ + m1);
+    unsigned char* garena = reinterpret_cast<unsigned char*>(pending_) + m4;
+    g_total_ = reinterpret_cast<double*>(garena);
+    g_bb_ = g_total_ + (n_groups_ + 1);
+    g_start_ = g_bb_ + (n_groups_ + 1);
+    g_cand_ = g_start_ + (n_groups_ + 1);
+    g_kind_ = garena + (3 + kCand) * g8;
+    g_tie_ = g_kind_ + g1;
+    g_choice_ = g_tie_ + g1;
+}
+
+void SequentialCdf::prepare() {
+    CUDA_CHECK(cudaMemsetAsync(n_pending_, 0, sizeof(unsigned int), stream_));
+    chunk_approx_kernel<<<(unsigned)m_, kBlock, 0, stream_>>>(state_, mask_bit_, chunk_, approx_, cand_delta_, cand_tie_, m_);
+    CUDA_CHECK_LAST_ERROR();
+    launches_ = 1;
+}
+
+double SequentialCdf::approxTotal() {
+    // (g_start_ is not in use yet: one double of it receives the sum)
+    final_sum_kernel<<<1, kBlock, 0, stream_>>>(approx_, (int)m_, g_start_);
+    CUDA_CHECK_LAST_ERROR();
+    ++launches_;
+    double t = 0.0;
+    CUDA_CHECK(cudaMemcpyAsync(&t, g_start_, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    return t;
+}
+
+void SequentialCdf::classify(double approx_c_init) {
     cudaStream_t stream = stream_;
-    CUDA_CHECK(cudaMemsetAsync(n_pending, 0, sizeof(unsigned int), stream));
-    chunk_approx_kernel<<<(unsigned)m_, kBlock, 0, stream>>>(state, mask_bit, chunk_, approx_, cand_delta, cand_tie, m_);
+    chunk_scan_kernel<<<1, 1024, 0, stream>>>(approx_, m_, lo_, approx_c_init);
     CUDA_CHECK_LAST_ERROR();
-    chunk_scan_kernel<<<1, 1024, 0, stream>>>(approx_, m_, lo_, c_init);
+    const int c_grid = (int)std::min<uint64_t>((m_ + kBlock - 1) / kBlock, (uint64_t)eng_.numSMs() * 8);
+    chunk_classify_kernel<<<c_grid, kBlock, 0, stream>>>(chunk_, m_, approx_, lo_, cand_delta_, cand_tie_, delta_, base_, flag_,
+                                                        n_pending_, pending_);
     CUDA_CHECK_LAST_ERROR();
-    const int c_grid = (int)std::min<uint64_t>((m_ + kBlock - 1) / kBlock, (uint64_t)eng.numSMs() * 8);
-    chunk_classify_kernel<<<c_grid, kBlock, 0, stream>>>(chunk_, m_, approx_, lo_, cand_delta, cand_tie, delta_, base_, flag_,
-                                                        n_pending, pending);
-    CUDA_CHECK_LAST_ERROR();
-    chunk_surrogate_kernel<<<eng.numSMs() * 8, kBlock, 0, stream>>>(state, mask_bit, chunk_, n_pending, pending, delta_,
-                                                                   base_, flag_);
+    chunk_surrogate_kernel<<<eng_.numSMs() * 8, kBlock, 0, stream>>>(state_, mask_bit_, chunk_, n_pending_, pending_, delta_,
+                                                                    base_, flag_);
     CUDA_CHECK_LAST_ERROR();
     if (std::getenv("QSIM_DEBUG_CDF")) {
         std::vector<uint8_t> hf(m_);
@@ -586,21 +625,24 @@ SequentialCdf::SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_
         for (uint64_t k = 0; k < m_; ++k) cnt[hf[k] & 3]++;
         fprintf(stderr, "[cdf] zero %llu fast %llu slow %llu pending %llu\n", (unsigned long long)cnt[0], (unsigned long long)cnt[1], (unsigned long long)cnt[2], (unsigned long long)cnt[3]);
     }
-    unsigned char* garena = reinterpret_cast<unsigned char*>(pending) + m4;
-    double* g_total = reinterpret_cast<double*>(garena);
-    double *g_bb = g_total + (n_groups + 1), *g_start = g_bb + (n_groups + 1), *g_cand = g_start + (n_groups + 1);
-    uint8_t* g_kind = garena + (3 + kCand) * g8;
-    uint8_t *g_tie = g_kind + g1, *g_choice = g_tie + g1;
-    const int g_grid = (int)std::min<uint64_t>((n_groups * 32 + kBlock - 1) / kBlock, (uint64_t)eng.numSMs() * 8);
-    group_summary_kernel<<<g_grid, kBlock, 0, stream>>>(delta_, base_, flag_, chunk_, m_, n_groups, cand_delta, cand_tie, g_total, g_bb,
-                                                       g_kind, g_cand, g_tie);
+    const int g_grid = (int)std::min<uint64_t>((n_groups_ * 32 + kBlock - 1) / kBlock, (uint64_t)eng_.numSMs() * 8);
+    group_summary_kernel<<<g_grid, kBlock, 0, stream>>>(delta_, base_, flag_, chunk_, m_, n_groups_, cand_delta_, cand_tie_, g_total_,
+                                                       g_bb_, g_kind_, g_cand_, g_tie_);
     CUDA_CHECK_LAST_ERROR();
-    group_stitch_kernel<<<1, 32, 0, stream>>>(state, mask_bit, chunk_, m_, n_groups, delta_, base_, flag_, g_total, g_bb,
-                                             g_kind, g_start, cand_delta, cand_tie, g_cand, g_tie, g_choice, start_, slow_, c_init);
+    launches_ += 4;
+}
+
+void SequentialCdf::stitch(double c_init) {
+    cudaStream_t stream = stream_;
+    const int g_grid = (int)std::min<uint64_t>((n_groups_ * 32 + kBlock - 1) / kBlock, (uint64_t)eng_.numSMs() * 8);
+    group_stitch_kernel<<<1, 32, 0, stream>>>(state_, mask_bit_, chunk_, m_, n_groups_, delta_, base_, flag_, g_total_, g_bb_,
+                                             g_kind_, g_start_, cand_delta_, cand_tie_, g_cand_, g_tie_, g_choice_, start_, slow_,
+                                             c_init);
     CUDA_CHECK_LAST_ERROR();
-    group_write_kernel<<<g_grid, kBlock, 0, stream>>>(delta_, base_, flag_, m_, n_groups, g_kind, g_start, cand_delta, g_choice, start_);
+    group_write_kernel<<<g_grid, kBlock, 0, stream>>>(delta_, base_, flag_, m_, n_groups_, g_kind_, g_start_, cand_delta_, g_choice_,
+                                                     start_);
     CUDA_CHECK_LAST_ERROR();
-    launches_ = 7;
+    launches_ += 2;
 }
 
 double SequentialCdf::total() const {

@@ -27,6 +27,15 @@ public:
     // c_init: value the running sum starts from (0 for a whole state; the exact sum of the preceding shards
     // for one shard of a distributed state)
     SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, Engine& eng, double c_init = 0.0);
+    // The same in three steps, for a state sharded over several GPUs: every shard runs the sweep over its amplitudes
+    // (prepare) and its classification (classify, from the APPROXIMATE sum of the shards before it) at the same time;
+    // only stitch(c_init), which needs the EXACT sum of the shards before it, runs one shard after the other.
+    // Nothing else may use the engine's scratch slot 0 between prepare and stitch.
+    struct Deferred {};
+    SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, Engine& eng, Deferred);
+    double approxTotal();           // after prepare (the constructor above): tree-order sum of this shard
+    void classify(double approx_c_init);
+    void stitch(double c_init);
     double total() const;           // == the reference's index-order host sum, bit for bit
     uint64_t slowChunks() const;    // chunks that had to be replayed sequentially (diagnostics)
     // out[i] = smallest index whose CDF value >= uniforms[i] (n if none), host in / host out
@@ -45,6 +54,12 @@ private:
     double *approx_ = nullptr, *lo_ = nullptr, *delta_ = nullptr, *base_ = nullptr, *start_ = nullptr;
     unsigned long long* slow_ = nullptr;
     uint8_t* flag_ = nullptr;
+    double *cand_delta_ = nullptr, *g_total_ = nullptr, *g_bb_ = nullptr, *g_start_ = nullptr, *g_cand_ = nullptr;
+    uint8_t *cand_tie_ = nullptr, *g_kind_ = nullptr, *g_tie_ = nullptr, *g_choice_ = nullptr;
+    unsigned int *n_pending_ = nullptr, *pending_ = nullptr;
+    uint64_t n_groups_ = 0;
+    void setup();
+    void prepare();
     int launches_ = 0;
 };
 

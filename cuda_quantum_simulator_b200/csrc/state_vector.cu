@@ -232,8 +232,21 @@ std::vector<int64_t> StateVector::sampleWithUniforms(const double* uniforms, int
     return out;
 }
 
+double StateVector::sampleShardPrepare() {
+    prepared_cdf_ = std::make_unique<b200::SequentialCdf>(devicePtr(), size_, -1, *engine_, b200::SequentialCdf::Deferred{});
+    return prepared_cdf_->approxTotal();
+}
+
+void StateVector::sampleShardClassify(double approx_c_init) {
+    if (!prepared_cdf_) throw std::runtime_error("sampleShardClassify without sampleShardPrepare");
+    prepared_cdf_->classify(approx_c_init);
+}
+
 double StateVector::sampleShard(double c_init, bool first_shard, const double* uniforms, int64_t n_shots, int64_t* out) {
-    b200::SequentialCdf cdf(devicePtr(), size_, -1, *engine_, c_init);
+    std::unique_ptr<b200::SequentialCdf> own = std::move(prepared_cdf_);
+    if (own) own->stitch(c_init);
+    else own = std::make_unique<b200::SequentialCdf>(devicePtr(), size_, -1, *engine_, c_init);
+    b200::SequentialCdf& cdf = *own;
     const double c_end = cdf.total();
     if (n_shots > 0) {
         cdf.sample(uniforms, n_shots, out);

@@ -283,6 +283,14 @@ class CudaShardEngine:
                                                 out.ctypes.data_as(c_void_p), byref(c_end)))
         return out, c_end.value
 
+    def cdf_prepare(self) -> float:
+        v = c_double()
+        _lib.check(_lib.lib().qsim_shard_cdf_prepare(self._h, byref(v)))
+        return v.value
+
+    def cdf_classify(self, approx_c_init: float):
+        _lib.check(_lib.lib().qsim_shard_cdf_classify(self._h, c_double(approx_c_init)))
+
     def launch_count(self) -> int:
         return int(_lib.lib().qsim_sim_launch_count(self._h))
 
@@ -449,6 +457,10 @@ class ShardedSimulator:
         u = np.ascontiguousarray(uniforms, np.float64)
         fx = self.frame >> self.nl
         my_pos = self.rank ^ fx                       # position of my shard in the frame-resolved order
+        if self.world > 1 and hasattr(self.engine, "cdf_prepare"):
+            # every shard sweeps its amplitudes now, at the same time; the chain below only stitches and samples
+            totals = self._allgather(self.engine.cdf_prepare())           # indexed by physical rank
+            self.engine.cdf_classify(float(sum(totals[p ^ fx] for p in range(my_pos))))
         c = 0.0
         result = np.full(len(u), -1, np.int64)
         for pos in range(self.world):                 # chain: shard `pos` continues from the exact sum so far

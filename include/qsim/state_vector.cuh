@@ -63,6 +63,11 @@ public:
     std::vector<int64_t> sampleSeeded(unsigned seed, int64_t n_shots);   // mt19937(seed) draws
     // one shard of a distributed CDF: continues the sequential sum from c_init; returns the running sum at the end
     double sampleShard(double c_init, bool first_shard, const double* uniforms, int64_t n_shots, int64_t* out);
+    // the same in steps, so that all shards sweep their amplitudes at the same time (see b200::SequentialCdf):
+    // sampleShardPrepare() -> this shard's approximate total; sampleShardClassify(approximate sum of the shards before);
+    // then sampleShard(exact sum of the shards before, ...) finishes.  No other read-out in between.
+    double sampleShardPrepare();
+    void sampleShardClassify(double approx_c_init);
     double partialProbability(int bit) const;                            // sum |a|^2 with index bit == 0 (bit<0: all)
     void collapse(int bit, int outcome, double scale);
 
@@ -84,6 +89,7 @@ private:
     mutable bool pending_basis_ = false;      // the memory does not hold the state yet: it is |pending_idx_>
     mutable uint64_t pending_idx_ = 0;
     std::unique_ptr<b200::Engine> engine_;
+    std::unique_ptr<b200::SequentialCdf> prepared_cdf_;
     void materialize() const;
 
     void allocate();

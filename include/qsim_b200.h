@@ -199,6 +199,12 @@ QSIM_API qsim_status_t qsim_shard_collapse(qsim_sim_t* s, int bit, int outcome, 
  * resolve to local index 0 as std::lower_bound does. */
 QSIM_API qsim_status_t qsim_shard_sample(qsim_sim_t* s, double c_init, int first_shard, const double* uniforms,
                                          int64_t n_shots, int64_t* out, double* c_end);
+/* Optional two-step preamble that lets all shards do the expensive part at the same time: qsim_shard_cdf_prepare sweeps
+ * this shard's amplitudes (chunk sums and candidate increments) and returns its approximate total;
+ * qsim_shard_cdf_classify takes the approximate sum of the shards before this one; the following qsim_shard_sample then
+ * only stitches the chunk starts from the exact c_init and samples.  No other read-out call in between. */
+QSIM_API qsim_status_t qsim_shard_cdf_prepare(qsim_sim_t* s, double* approx_total);
+QSIM_API qsim_status_t qsim_shard_cdf_classify(qsim_sim_t* s, double approx_c_init);
 
 /* ---- NoisySimulator (reference include/NoiseModel.cuh:141-225) ---------------------------------- */
 QSIM_API qsim_status_t qsim_noisy_create(int num_qubits, const qsim_noise_channel_t* channels, int n_channels,

@@ -90,3 +90,52 @@ def test_fused_exchange_on_one_gpu(nl, g_local, tail_x):
     L.qsim_program_destroy(prog)
     for h in sims:
         L.qsim_sim_destroy(h)
+
+
+def test_staged_shard_sampling_on_one_gpu():
+    """qsim_shard_cdf_prepare / _classify / qsim_shard_sample with both shards of a 2-shard state on this GPU: the chained
+    result must equal the host's sequential CDF over the whole state, bit for bit."""
+    from ctypes import byref, c_double, c_void_p
+
+    import numpy as np
+
+    from cuda_quantum_simulator_b200 import _lib
+
+    L = _lib.lib()
+    nl, n = 15, 16
+    rng = np.random.default_rng(321)
+    full = H.random_state(n, rng)
+    full[: 1 << 13] *= 1e-9          # a tiny head, so the second shard starts far from where its own sum would
+    full /= np.linalg.norm(full)
+    probs = H.oracle_probs(full)
+    u = np.concatenate([rng.random(2000), [0.0, 0.5]])
+    want = H.oracle_sample(probs, u)
+    sims = []
+    for r in range(2):
+        h = c_void_p()
+        _lib.check(L.qsim_shard_create(n, 1, r, None, byref(h)))
+        shard = np.ascontiguousarray(full[r << nl:(r + 1) << nl])
+        _lib.check(L.qsim_sim_set_state(h, shard.ctypes.data_as(c_void_p)))
+        sims.append(h)
+    approx = []
+    for h in sims:
+        v = c_double()
+        _lib.check(L.qsim_shard_cdf_prepare(h, byref(v)))
+        approx.append(v.value)
+    assert abs(sum(approx) - 1.0) < 1e-9
+    _lib.check(L.qsim_shard_cdf_classify(sims[0], c_double(0.0)))
+    _lib.check(L.qsim_shard_cdf_classify(sims[1], c_double(approx[0])))
+    got = np.full(len(u), -1, np.int64)
+    c = 0.0
+    for r, h in enumerate(sims):
+        out = np.empty(len(u), np.int64)
+        c_end = c_double()
+        _lib.check(L.qsim_shard_sample(h, c_double(c), int(r == 0), u.ctypes.data_as(c_void_p), len(u),
+                                       out.ctypes.data_as(c_void_p), byref(c_end)))
+        hit = out >= 0
+        got[hit] = (r << nl) | out[hit]
+        c = c_end.value
+    assert np.array_equal(got, want)
+    assert c == H.oracle().orc_total_probability(probs.ctypes.data_as(H.P), H.c_int64(len(probs)))
+    for h in sims:
+        L.qsim_sim_destroy(h)
