@@ -48,6 +48,35 @@ def _target_positions(g) -> Tuple[int, ...]:
     return (1,)                # CNOT, CRY
 
 
+def choose_initial_layout(num_qubits: int, n_global: int, gates: np.ndarray) -> List[int]:
+    """Logical qubit -> physical position for a circuit that starts from |0...0> (which is the same state under any
+    relabelling of the qubits): the qubits that are never a non-diagonal target — uncontrolled X is an index relabel,
+    diagonal gates and controls need no data — go to the global positions, where they cost no exchange at all; if there
+    are not enough of those, the ones targeted last.  Everything else keeps its relative order."""
+    n, nl = num_qubits, num_qubits - n_global
+    first_use = [1 << 60] * n
+    qcols = ("q0", "q1", "q2")
+    for j, g in enumerate(gates):
+        if int(g["type"]) == _X:
+            continue
+        for slot in _target_positions(g):
+            q = int(g[qcols[slot]])
+            if first_use[q] == 1 << 60:
+                first_use[q] = j
+    # best candidates for the global positions: latest first non-diagonal use, ties -> highest qubit (identity if possible)
+    order = sorted(range(n), key=lambda q: (first_use[q], q), reverse=True)
+    glob = sorted(order[:n_global])
+    perm = [0] * n
+    pos = 0
+    for q in range(n):
+        if q not in glob:
+            perm[q] = pos
+            pos += 1
+    for i, q in enumerate(glob):
+        perm[q] = nl + i
+    return perm
+
+
 @dataclass
 class Step:
     kind: str                              # "gates" | "swap"
@@ -338,6 +367,7 @@ class ShardedSimulator:
         self.engine = engine if engine is not None else CudaShardEngine(self.n, self.ng, rank, world, exchange)
         self.perm = list(range(self.n))      # logical qubit -> physical position
         self.frame = 0                       # pending X mask over physical positions (global bits only, between runs)
+        self._pristine = True                # the state is |0...0>: the qubit layout is still free to choose
 
     @property
     def local(self):
@@ -348,11 +378,19 @@ class ShardedSimulator:
         self.engine.reset()
         self.perm = list(range(self.n))
         self.frame = 0
+        self._pristine = True
+
+    def set_local_state(self, amps: np.ndarray):
+        """Overwrite this rank's shard (stored layout); the qubit layout is fixed from here on."""
+        self.engine.set_local_state(amps)
+        self._pristine = False
 
     def compile(self, circuit: Circuit) -> CompiledPlan:
         """Plan + compile against the CURRENT qubit permutation and X frame."""
         if circuit.get_num_qubits() != self.n:
             raise _lib.InvalidArgument("Circuit qubit count doesn't match simulator")
+        if self._pristine and self.ng > 0 and os.environ.get("QSIM_NO_LAYOUT") is None:
+            self.perm = choose_initial_layout(self.n, self.ng, circuit.gates)
         plan = plan_circuit(self.n, self.ng, circuit.gates, self.perm)
         frame = self.frame
         programs, n_passes, n_ops = [], 0, 0
@@ -388,6 +426,7 @@ class ShardedSimulator:
             i += 1
         self.perm = list(cp.plan.perm)
         self.frame = cp.frame_after
+        self._pristine = False
 
     def release(self, cp: CompiledPlan):
         for h in cp.programs:

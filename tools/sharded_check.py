@@ -59,6 +59,24 @@ if rank == 0:
 assert err < 1e-10
 sim.close()
 
+# the same with the identity qubit layout forced (the free initial layout above avoids the exchange altogether), and a
+# circuit that targets every qubit many times: global<->local swaps, fused into the preceding pass where possible
+for label, n, depth, seed, free_layout in (("identity layout", 24, 40, 7, False), ("dense", 22, 300, 11, True)):
+    c = q.create_random_circuit(n, depth, seed)
+    sim = ShardedSimulator(n, exchange=exchange)
+    sim._pristine = free_layout
+    cp = sim.compile(c)
+    sim.execute(cp)
+    got = sim.get_state_vector()
+    want = H.oracle_run(n, c.gates)
+    err = float(np.max(np.abs(got - want)))
+    if rank == 0:
+        print(f"createRandomCircuit({n},{depth},{seed}) {label}: swaps={cp.n_swaps} fused={sim.engine.fused_exchanges} "
+              f"max|err|={err:.2e}", flush=True)
+    assert err < 1e-10
+    sim.release(cp)
+    sim.close()
+
 # exchange bandwidth: swap the top global qubit with the top local qubit on 2^big-amplitude shards
 n = big + ng
 sim = ShardedSimulator(n, exchange=exchange)
