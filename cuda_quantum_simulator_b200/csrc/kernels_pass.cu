@@ -510,9 +510,35 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
         const uint64_t dest_tile = init_tile ^ xdep;   // where that tile is written (deferred X gates on outer bits)
         const uint64_t n_amps = 1ULL << pd.n;
         uint4* out = reinterpret_cast<uint4*>(P.state);
-        for (uint64_t idx = (uint64_t)blockIdx.x * kComputeThreads + tid; idx < n_amps; idx += (uint64_t)gridDim.x * kComputeThreads)
-            if ((idx & ~tile_mask) != dest_tile) out[idx] = make_uint4(0u, 0u, 0u, 0u);
+        if (n_amps >= 4096 && pd.t == kMaxTileBits) {
+            // 64 KiB at a time, as 1-D bulk copies from an all-zero stage (one instruction per chunk); the few chunks
+            // that contain rows of the special tile are written element by element around them
+            uint4* z = reinterpret_cast<uint4*>(tiles);
+            for (uint32_t e = tid; e < 65536 / 16; e += kComputeThreads) z[e] = make_uint4(0u, 0u, 0u, 0u);
+            fence_proxy_async();
+            __syncthreads();
+            const uint64_t n_chunks = n_amps >> 12;
+            for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+                const bool has_special = ((((c << 12) ^ dest_tile) & ~tile_mask) >> 12) == 0;   // (uniform)
+                if (has_special) {
+                    for (uint32_t e = tid; e < 4096; e += kComputeThreads) {
+                        const uint64_t idx = (c << 12) + e;
+                        if ((idx & ~tile_mask) != dest_tile) out[idx] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                } else if (tid == 0) {
+                    tma_store_1d(gstate + (c << 16), tiles, 65536);
+                    tma_store_commit();
+                }
+            }
+            if (tid == 0) tma_store_wait_all();   // the stage is reused below
+            __syncthreads();
+        } else {
+            const uint64_t step = (uint64_t)gridDim.x * kComputeThreads;
+            for (uint64_t idx = (uint64_t)blockIdx.x * kComputeThreads + tid; idx < n_amps; idx += step)
+                if ((idx & ~tile_mask) != dest_tile) out[idx] = make_uint4(0u, 0u, 0u, 0u);
+        }
     }
+
     double ar[kSlots], ai[kSlots], br[kSlots], bi[kSlots];
     for (uint64_t i = 0; i < n_my; ++i) {
         const int s = (int)(i % n_stages);

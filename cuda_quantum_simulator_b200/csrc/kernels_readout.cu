@@ -150,22 +150,51 @@ __global__ void chunk_approx_kernel(const cuDoubleComplex* __restrict__ state, i
     }
 }
 
-// K2: single-block exclusive scan of the approximate chunk sums: lo[k] = approx start of chunk k.
-__global__ void chunk_scan_kernel(const double* __restrict__ approx, uint64_t m, double* __restrict__ lo, double c_init) {
-    __shared__ double part[1024];
-    const uint64_t per = (m + blockDim.x - 1) / blockDim.x;
-    const uint64_t b = (uint64_t)threadIdx.x * per, e = (b + per < m) ? b + per : m;
-    double acc = 0.0;
-    for (uint64_t i = b; i < e; ++i) acc += approx[i];
-    part[threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
+// K2: exclusive scan of the approximate chunk sums, lo[k] = approximate start of chunk k (any summation order will do:
+// it only picks the tentative binade).  Three small launches: per-block totals, scan of the block totals, per-block scan.
+constexpr int kScanBlock = 1024;
+
+__global__ void scan_block_totals_kernel(const double* __restrict__ approx, uint64_t m, double* __restrict__ block_tot) {
+    __shared__ double red[32];
+    const uint64_t i = (uint64_t)blockIdx.x * kScanBlock + threadIdx.x;
+    const double t = block_sum(i < m ? approx[i] : 0.0, red);
+    if (threadIdx.x == 0) block_tot[blockIdx.x] = t;
+}
+
+__global__ void scan_totals_kernel(double* __restrict__ block_tot, int n_blocks, double c_init) {
+    // n_blocks <= 2^21 / 1024 = 2048 for the largest state: one thread walks them
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
         double run = c_init;
-        for (int i = 0; i < (int)blockDim.x; ++i) { double v = part[i]; part[i] = run; run += v; }
+        for (int b = 0; b < n_blocks; ++b) { const double v = block_tot[b]; block_tot[b] = run; run += v; }
+    }
+}
+
+__global__ void scan_blocks_kernel(const double* __restrict__ approx, uint64_t m, const double* __restrict__ block_tot,
+                                   double* __restrict__ lo) {
+    __shared__ double wsum[32];
+    const uint64_t i = (uint64_t)blockIdx.x * kScanBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double v = i < m ? approx[i] : 0.0;
+    double incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        double w = wsum[lane];
+        double wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += up;
+        }
+        wsum[lane] = wi - w;   // exclusive prefix of the warp totals
     }
     __syncthreads();
-    double run = part[threadIdx.x];
-    for (uint64_t i = b; i < e; ++i) { lo[i] = run; run += approx[i]; }
+    if (i < m) lo[i] = block_tot[blockIdx.x] + wsum[warp] + (incl - v);
 }
 
 enum : uint8_t { CH_ZERO = 0, CH_FAST = 1, CH_SLOW = 2, CH_PENDING = 3 };
@@ -608,8 +637,15 @@ double SequentialCdf::approxTotal() {
 
 void SequentialCdf::classify(double approx_c_init) {
     cudaStream_t stream = stream_;
-    chunk_scan_kernel<<<1, 1024, 0, stream>>>(approx_, m_, lo_, approx_c_init);
-    CUDA_CHECK_LAST_ERROR();
+    {   // (start_ is only written by the stitch: until then its head holds the per-block totals)
+        const int n_blocks = (int)((m_ + kScanBlock - 1) / kScanBlock);
+        scan_block_totals_kernel<<<n_blocks, kScanBlock, 0, stream>>>(approx_, m_, start_);
+        CUDA_CHECK_LAST_ERROR();
+        scan_totals_kernel<<<1, 32, 0, stream>>>(start_, n_blocks, approx_c_init);
+        CUDA_CHECK_LAST_ERROR();
+        scan_blocks_kernel<<<n_blocks, kScanBlock, 0, stream>>>(approx_, m_, start_, lo_);
+        CUDA_CHECK_LAST_ERROR();
+    }
     const int c_grid = (int)std::min<uint64_t>((m_ + kBlock - 1) / kBlock, (uint64_t)eng_.numSMs() * 8);
     chunk_classify_kernel<<<c_grid, kBlock, 0, stream>>>(chunk_, m_, approx_, lo_, cand_delta_, cand_tie_, delta_, base_, flag_,
                                                         n_pending_, pending_);
@@ -629,7 +665,7 @@ void SequentialCdf::classify(double approx_c_init) {
     group_summary_kernel<<<g_grid, kBlock, 0, stream>>>(delta_, base_, flag_, chunk_, m_, n_groups_, cand_delta_, cand_tie_, g_total_,
                                                        g_bb_, g_kind_, g_cand_, g_tie_);
     CUDA_CHECK_LAST_ERROR();
-    launches_ += 4;
+    launches_ += 6;
 }
 
 void SequentialCdf::stitch(double c_init) {
