@@ -217,6 +217,8 @@ def main():
         return float(ms.item())
 
     # ---- kernel-resident throughput -------------------------------------------------------------
+    step()   # untimed and not a warm-up step: the first pass after reset() generates |0..0> on chip; everything timed
+             # below runs on the dense evolved state, loaded from and stored to HBM in full
     for _ in range(args.warmup):
         step()
     sync_all()
