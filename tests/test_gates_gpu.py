@@ -73,6 +73,37 @@ def test_trailing_flips_fold_into_the_store(n):
         assert np.max(np.abs(got - want)) < 1e-12, (n, trial)
 
 
+@pytest.mark.parametrize("n", [1, 4, 12, 13, 15, 18, 21])
+def test_run_from_a_recorded_basis_state(n):
+    """reset() / init_basis() only record the basis state; the first pass of the next run generates its tiles on chip
+    (fused_pass_kernel, PassParams::init_basis) — with deferred X gates on tile and non-tile qubits, folded flips,
+    several passes, and a compiled program as well as run()."""
+    rng = np.random.default_rng(4000 + n)
+    for trial in range(4):
+        idx = int(rng.integers(0, 1 << n))
+        g = H.random_gates(n, int(rng.integers(1, 60)), rng)
+        if n > 1:
+            extra = H.flip_heavy_gates(n, rng, body=2, tail=int(rng.integers(1, 12)))
+            g = np.concatenate([g, extra])
+        st0 = np.zeros(1 << n, np.complex128)
+        st0[idx] = 1.0
+        want = H.oracle_run(n, g, st0)
+        sim = q.Simulator(n)
+        sim.init_basis(idx)
+        c = q.Circuit(n).extend(g)
+        if trial % 2:
+            sim.execute(q.CompiledCircuit(c))
+        else:
+            sim.run(c)
+        assert np.max(np.abs(sim.get_state_vector() - want)) < 1e-12, (n, trial, idx)
+        # and again after a plain reset, sampling without ever touching the amplitudes from the host
+        sim.reset()
+        sim.run(c)
+        u = rng.random(64)
+        want0 = H.oracle_run(n, g)
+        assert np.array_equal(sim.sample(0, uniforms=u), H.oracle_sample(H.oracle_probs(want0), u)), (n, trial)
+
+
 def test_every_gate_on_every_qubit_18q():
     """Each gate type with its target on every bit position class (lane, register, warp, outside-tile)."""
     n = 18
