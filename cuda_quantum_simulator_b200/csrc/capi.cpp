@@ -251,14 +251,11 @@ qsim_status_t qsim_shard_create(int n, int n_global, int rank, void* device_stat
         s->n_total = n;
         s->n_global = n_global;
         s->rank = rank;
-        // |0...0> lives on rank 0 only
-        if (rank != 0) {
-            CUDA_CHECK(cudaMemsetAsync(s->sim->state().devicePtr(), 0, s->sim->getStateSize() * sizeof(cuDoubleComplex),
-                                       s->sim->state().engine().stream()));
-            s->sim->synchronize();
-        } else if (device_state) {
-            s->sim->reset();
-        }
+        // |0...0> lives on rank 0 only.  Shards defer the write even on caller memory: every access goes through this
+        // object, and ranks that are about to be read by a peer materialise first (qsim_sim_device_ptr).
+        if (n_global > 0) s->sim->state().allowLazyExternal(true);
+        if (rank != 0) s->sim->state().initializeAllZero();
+        else if (device_state) s->sim->reset();
         *out = s.release();
     });
 }
@@ -275,11 +272,8 @@ qsim_status_t qsim_sim_set_stream(qsim_sim_t* s, void* stream) {
 qsim_status_t qsim_sim_reset(qsim_sim_t* s) {
     return guarded([&] {
         require(s != nullptr, "null simulator");
-        if (s->n_global && s->rank != 0) {
-            CUDA_CHECK(cudaMemsetAsync(s->sim->state().devicePtr(), 0, s->sim->getStateSize() * sizeof(cuDoubleComplex),
-                                       s->sim->state().engine().stream()));
-            s->sim->synchronize();
-        } else s->sim->reset();
+        if (s->n_global && s->rank != 0) s->sim->state().initializeAllZero();
+        else s->sim->reset();
     });
 }
 
@@ -331,7 +325,14 @@ qsim_status_t qsim_sim_execute(qsim_sim_t* s, const qsim_program_t* p) {
         if (p->dev.host.n != s->n_total || p->n_global != s->n_global)
             throw std::invalid_argument("Circuit qubit count doesn't match simulator");
         if (s->n_global == 0) s->sim->execute(p->dev);
-        else s->sim->state().engine().execute(p->dev, s->sim->state().devicePtr(), s->hi_bits());
+        else {
+            StateVector& sv = s->sim->state();
+            uint64_t basis = 0;
+            if (!p->dev.host.passes.empty() && sv.takePendingBasis(&basis))   // first pass generates the shard on chip
+                sv.engine().execute(p->dev, sv.rawDevicePtr(), s->hi_bits(), (int64_t)basis);
+            else
+                sv.engine().execute(p->dev, sv.devicePtr(), s->hi_bits());
+        }
     });
 }
 

@@ -89,7 +89,7 @@ void StateVector::initializeZero() { initializeBasis(0); }
 
 void StateVector::initializeBasis(size_t basis_idx) {
     if (basis_idx >= size_) throw std::invalid_argument("Basis index out of range");
-    if (owns_ && !std::getenv("QSIM_EAGER_INIT")) {
+    if ((owns_ || lazy_external_) && !std::getenv("QSIM_EAGER_INIT")) {
         // nobody else can see this memory: defer the write (devicePtr() and every read-out materialise it)
         pending_basis_ = true;
         pending_idx_ = basis_idx;
@@ -101,9 +101,25 @@ void StateVector::initializeBasis(size_t basis_idx) {
     engine_->synchronize();   // the reference synchronises here too (src/StateVector.cu:188-190)
 }
 
+void StateVector::initializeAllZero() {
+    if ((owns_ || lazy_external_) && !std::getenv("QSIM_EAGER_INIT")) {
+        pending_basis_ = true;
+        pending_idx_ = kAllZero;
+        return;
+    }
+    pending_basis_ = false;
+    CUDA_CHECK(cudaMemsetAsync(d_state_, 0, size_ * sizeof(cuDoubleComplex), engine_->stream()));
+    engine_->synchronize();
+}
+
 void StateVector::materialize() const {
     if (!pending_basis_) return;
     pending_basis_ = false;
+    if (pending_idx_ == kAllZero) {
+        CUDA_CHECK(cudaMemsetAsync(d_state_, 0, size_ * sizeof(cuDoubleComplex), engine_->stream()));
+        engine_->countLaunch(1);
+        return;
+    }
     b200::launch_init_basis(d_state_, size_, pending_idx_, engine_->stream());
     engine_->countLaunch(2);
 }

@@ -237,6 +237,7 @@ class CudaShardEngine:
 
     def swap(self, global_qubit: int, local_qubit: int):
         peer = self.rank ^ (1 << (global_qubit - self.nl))
+        _lib.lib().qsim_sim_device_ptr(self._h)   # a lazily reset shard is written out now: the peer is about to read it
         self.device_barrier()
         if self.exchange == "p2p":
             _lib.check(_lib.lib().qsim_shard_swap_p2p(self._h, c_void_p(self._peer_ptr[peer][self._cur]), global_qubit,

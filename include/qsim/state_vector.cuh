@@ -37,6 +37,10 @@ public:
 
     void initializeZero();
     void initializeBasis(size_t basis_idx);
+    void initializeAllZero();                 // additive: the zero vector (a shard that does not hold |0...0>)
+    // additive: let a non-owning view defer its initialisation like an owning one does (the caller promises to reach
+    // the memory only through this object until devicePtr() has been called)
+    void allowLazyExternal(bool on) { lazy_external_ = on; }
 
     int getNumQubits() const { return num_qubits_; }
     size_t getSize() const { return size_; }
@@ -76,7 +80,8 @@ public:
     // initializeZero / initializeBasis on memory this object owns only RECORD the basis state; it is written by
     // whoever needs the amplitudes first.  Simulator::run takes it over: its first pass generates the tiles on chip
     // instead of loading them (no memset sweep, no load sweep).  Returns false when the memory is already valid.
-    bool takePendingBasis(uint64_t* basis_idx);
+    bool takePendingBasis(uint64_t* basis_idx);   // kAllZero: the zero vector
+    static constexpr uint64_t kAllZero = 0x7fffffffffffffffULL;
     cuDoubleComplex* rawDevicePtr() { return d_state_; }
     // non-owning views only: continue on other caller memory of the same size (double-buffered qubit exchange)
     void rebindExternal(cuDoubleComplex* external_device_memory);   // no materialisation: only with takePendingBasis
@@ -87,6 +92,7 @@ private:
     cuDoubleComplex* d_state_ = nullptr;
     bool owns_ = true;
     mutable bool pending_basis_ = false;      // the memory does not hold the state yet: it is |pending_idx_>
+    bool lazy_external_ = false;
     mutable uint64_t pending_idx_ = 0;
     std::unique_ptr<b200::Engine> engine_;
     std::unique_ptr<b200::SequentialCdf> prepared_cdf_;
