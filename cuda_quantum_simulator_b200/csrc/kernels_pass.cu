@@ -225,65 +225,78 @@ template <bool CTRL>
 __device__ __forceinline__ void diagonal(const DevOp& op, uint32_t sm, uint32_t tid, uint64_t gbase, const double (&xr_)[kSlots],
                                          const double (&xi_)[kSlots], double (&yr_)[kSlots], double (&yi_)[kSlots]) {
     const double d0r = op.m[0], d0i = op.m[1], d1r = op.m[6], d1i = op.m[7];
-    if (op.thome == T_REG) {
-        const uint32_t tsl = op.tslots;
+    // which diagonal entry a slot takes: by the slot (register-resident target) or the same for the whole thread
+    // (target on a tid bit or outside the tile) — folded into ONE mask so there is a single multiply loop
+    const bool bt = (op.thome == T_THREAD) ? ((tid & op.tmask_thr) != 0) : ((gbase & op.tmask_out) != 0);
+    const uint32_t tsl = (op.thome == T_REG) ? (uint32_t)op.tslots : (bt ? 0xffffu : 0u);
 #pragma unroll
-        for (int k = 0; k < kSlots; ++k) {
-            const bool b = (tsl >> k) & 1;
-            const double pr = b ? d1r : d0r, pi = b ? d1i : d0i;
-            const double xr = xr_[k], xi = xi_[k];
-            const double nr = xr * pr - xi * pi, ni = xr * pi + xi * pr;
-            if (CTRL) { const bool on = (sm >> k) & 1; yr_[k] = on ? nr : xr; yi_[k] = on ? ni : xi; }
-            else { yr_[k] = nr; yi_[k] = ni; }
-        }
-    } else {
-        const bool b = (op.thome == T_THREAD) ? ((tid & op.tmask_thr) != 0) : ((gbase & op.tmask_out) != 0);
+    for (int k = 0; k < kSlots; ++k) {
+        const bool b = (tsl >> k) & 1;
         const double pr = b ? d1r : d0r, pi = b ? d1i : d0i;
-#pragma unroll
-        for (int k = 0; k < kSlots; ++k) {
-            const double xr = xr_[k], xi = xi_[k];
-            const double nr = xr * pr - xi * pi, ni = xr * pi + xi * pr;
-            if (CTRL) { const bool on = (sm >> k) & 1; yr_[k] = on ? nr : xr; yi_[k] = on ? ni : xi; }
-            else { yr_[k] = nr; yi_[k] = ni; }
-        }
+        const double xr = xr_[k], xi = xi_[k];
+        const double nr = xr * pr - xi * pi, ni = xr * pi + xi * pr;
+        if (CTRL) { const bool on = (sm >> k) & 1; yr_[k] = on ? nr : xr; yi_[k] = on ? ni : xi; }
+        else { yr_[k] = nr; yi_[k] = ni; }
     }
 }
 
-// A fused run of diagonal gates: amplitude(l) *= TABLE[l] * U * prod_{tile bits j of l} E_j.
+// A fused run of diagonal gates: amplitude(l) *= TABLE[l] * U * prod_{tile bits j of l} E_j.  op.cmask_thr says which of
+// those factors exist at all (uniform), so a run whose qubits all lie outside the tile costs one complex multiply per
+// amplitude and a run without outside partners only the table look-up.
 __device__ __forceinline__ void phase_op(const DevOp& op, const double2* __restrict__ tables, const double2* eu,
                                          const SweepDesc& sd, uint32_t tid, uint32_t base_local, const double (&xr_)[kSlots],
                                          const double (&xi_)[kSlots], double (&yr_)[kSlots], double (&yi_)[kSlots]) {
-    const double2* tb = tables + op.cmask_out;
-    double2 f[kSlots];
+    const uint32_t present = op.cmask_thr;
+    const double2* e = eu + (size_t)op.tmask_out * 13;
+    // thread-wide factor: U and the E_j of the tile bits held by tid bits
+    double pr = 1.0, pi = 0.0;
+    if (present & (1u << 12)) { pr = e[12].x; pi = e[12].y; }
+    uint32_t reg_present = 0;
 #pragma unroll
-    for (int k = 0; k < kSlots; ++k) f[k] = __ldg(tb + base_local + sd.slot_off[k]);
-    if (op.tslots != 0) {   // some factor depends on bits outside the tile
-        const double2* e = eu + (size_t)op.tmask_out * 13;
-        double pr = e[12].x, pi = e[12].y;   // U, then the thread-resident tile bits
+    for (int j = 0; j < kMaxRegBits; ++j)
+        if (j < sd.r && ((present >> sd.reg_pos[j]) & 1u)) reg_present |= 1u << j;
+    if (present & 0xfffu) {
 #pragma unroll
         for (int b = 0; b < kMaxTileBits - kMaxRegBits; ++b) {
-            if (b < sd.nthr && ((tid >> b) & 1)) {
+            if (b < sd.nthr && ((present >> sd.thr_pos[b]) & 1u) && ((tid >> b) & 1)) {   // (first two tests are uniform)
                 const double2 v = e[sd.thr_pos[b]];
                 const double r = pr * v.x - pi * v.y;
                 pi = pr * v.y + pi * v.x;
                 pr = r;
             }
         }
+    }
+    double2 f[kSlots];
+    if (present & (1u << 13)) {
+        const double2* tb = tables + op.cmask_out;
 #pragma unroll
         for (int k = 0; k < kSlots; ++k) {
-            double qr = pr, qi = pi;
+            const double2 t = __ldg(tb + (base_local ^ (uint32_t)sd.slot_off[k]));
+            f[k].x = t.x * pr - t.y * pi;
+            f[k].y = t.x * pi + t.y * pr;
+        }
+    } else {
+        if (present & (1u << 14)) {   // constant table: fold it into the thread-wide factor
+            const double2 t = __ldg(tables + op.cmask_out);
+            const double r = t.x * pr - t.y * pi;
+            pi = t.x * pi + t.y * pr;
+            pr = r;
+        }
 #pragma unroll
-            for (int j = 0; j < kMaxRegBits; ++j) {
-                if (j < sd.r && ((k >> j) & 1)) {
-                    const double2 v = e[sd.reg_pos[j]];
-                    const double r = qr * v.x - qi * v.y;
-                    qi = qr * v.y + qi * v.x;
-                    qr = r;
-                }
+        for (int k = 0; k < kSlots; ++k) { f[k].x = pr; f[k].y = pi; }
+    }
+    if (reg_present) {   // E_j of register-resident tile bits
+#pragma unroll
+        for (int j = 0; j < kMaxRegBits; ++j) {
+            if (!((reg_present >> j) & 1u)) continue;
+            const double2 v = e[sd.reg_pos[j]];
+#pragma unroll
+            for (int k = 0; k < kSlots; ++k) {
+                if (!((k >> j) & 1)) continue;
+                const double r = f[k].x * v.x - f[k].y * v.y;
+                f[k].y = f[k].x * v.y + f[k].y * v.x;
+                f[k].x = r;
             }
-            const double r = f[k].x * qr - f[k].y * qi;
-            f[k].y = f[k].x * qi + f[k].y * qr;
-            f[k].x = r;
         }
     }
 #pragma unroll

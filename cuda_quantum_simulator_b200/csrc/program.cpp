@@ -331,6 +331,19 @@ void encode_phase(Program& out, PassDesc& pd, const std::vector<int>& members, c
     d.cmask_out = (uint64_t)(base / 2) - (uint64_t)pd.phase_table_offset;     // table entry offset within the pass
     d.cval_out = (uint64_t)first_term - (uint64_t)pd.phase_term_offset;      // first term within the pass
     d.tmask_out = (uint64_t)pd.n_phase;                                       // shared-memory slot of (E, U)
+    // which factors are not identically 1: bit j (j < 12) = E_j has terms, bit 12 = U has terms, bit 13 = the table is
+    // not constant (bit 14 = not even the constant 1)
+    uint32_t present = 0;
+    for (int e = 0; e < 13; ++e)
+        if (!groups[e].empty()) present |= 1u << e;
+    {
+        const double* tb = out.phase_tables.data() + base;
+        bool constant = true;
+        for (uint32_t l = 1; l < n_entries && constant; ++l) constant = (tb[2 * l] == tb[0] && tb[2 * l + 1] == tb[1]);
+        if (!constant) present |= 1u << 13;
+        if (!constant || tb[0] != 1.0 || tb[1] != 0.0) present |= 1u << 14;
+    }
+    d.cmask_thr = present;
     std::memcpy(d.m, starts, sizeof(starts));
     pd.n_phase++;
 }
