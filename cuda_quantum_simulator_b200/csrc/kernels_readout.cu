@@ -114,11 +114,11 @@ constexpr int kCand = 4;
 __global__ void chunk_approx_kernel(const cuDoubleComplex* __restrict__ state, int mask_bit, int chunk,
                                     double* __restrict__ approx, double* __restrict__ cand_delta,
                                     uint8_t* __restrict__ cand_tie, uint64_t m) {
-    __shared__ double red[32];
     __shared__ int tie_bits;
     const uint64_t base = (uint64_t)blockIdx.x * chunk;
     const bool cands = (chunk == 4096);
     if (threadIdx.x == 0) tie_bits = 0;
+    __syncthreads();
     double acc = 0.0;
     double s[kCand];
     int tie = 0;
@@ -137,17 +137,33 @@ __global__ void chunk_approx_kernel(const cuDoubleComplex* __restrict__ state, i
             }
         }
     }
-    const double total = block_sum(acc, red);
-    if (threadIdx.x == 0) approx[blockIdx.x] = total;
-    if (cands) {
-        if (tie) atomicOr(&tie_bits, tie);
+    // one reduction for the approximate sum and the candidate increments together (order inside a warp, then over
+    // the warps: any order is fine for the approximate sum, and the increments add exactly)
+    double v[kCand + 1];
+    v[0] = acc;
 #pragma unroll
-        for (int c = 0; c < kCand; ++c) {
-            const double d = block_sum(__dsub_rn(s[c], ldexp(1.0, -c)), red);   // multiples of u: exact adds
-            if (threadIdx.x == 0) cand_delta[(uint64_t)c * m + blockIdx.x] = d;
-        }
-        if (threadIdx.x == 0) cand_tie[blockIdx.x] = (uint8_t)tie_bits;
+    for (int c = 0; c < kCand; ++c) v[c + 1] = cands ? __dsub_rn(s[c], ldexp(1.0, -c)) : 0.0;
+#pragma unroll
+    for (int q = 0; q <= kCand; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] = __dadd_rn(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
     }
+    __shared__ double part[kBlock / 32][kCand + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (tie) atomicOr(&tie_bits, tie);
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q <= kCand; ++q) part[warp][q] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x <= kCand) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; ++w) t = __dadd_rn(t, part[w][threadIdx.x]);
+        if (threadIdx.x == 0) approx[blockIdx.x] = t;
+        else if (cands) cand_delta[(uint64_t)(threadIdx.x - 1) * m + blockIdx.x] = t;
+    }
+    if (cands && threadIdx.x == 0) cand_tie[blockIdx.x] = (uint8_t)tie_bits;
 }
 
 // K2: exclusive scan of the approximate chunk sums, lo[k] = approximate start of chunk k (any summation order will do:
