@@ -27,7 +27,8 @@ def test_two_gpu_parity(exchange):
     assert "sharded check ok" in out.stdout
 
 
-@pytest.mark.parametrize("nl,g_local,tail_x", [(14, 13, False), (16, 3, False), (20, 17, True), (21, 0, False)])
+@pytest.mark.parametrize("nl,g_local,tail_x", [(14, 13, False), (16, 3, False), (20, 17, True), (21, 0, False), (20, 18, "victim"),
+                                               (22, 19, "victim")])
 def test_fused_exchange_on_one_gpu(nl, g_local, tail_x):
     """qsim_shard_execute_exchange with both 'ranks' of a 2-shard state living on this one GPU: the program's last pass
     stores the staying half into the rank's second buffer and the leaving half into the other rank's second buffer.
@@ -50,7 +51,10 @@ def test_fused_exchange_on_one_gpu(nl, g_local, tail_x):
         k = str(rng.choice(["H", "T", "CNOT", "Rz", "X"]))
         a, b = (int(x) for x in rng.choice(others, 2, replace=False))
         lst.append((k, a, b) if k == "CNOT" else (k, a, float(rng.uniform(-3, 3))) if k == "Rz" else (k, a))
-    if tail_x:
+    if tail_x == "victim":
+        lst.append(("X", g_local))      # a deferred X on the exchanged qubit itself: partner tiles differ in that very bit
+        lst.append(("X", others[-2]))
+    elif tail_x:
         lst.append(("X", others[-1]))   # a deferred X on a high local qubit: the partner-tile store path
     g = H.gates(lst)
     full = H.random_state(n, rng)
