@@ -126,6 +126,36 @@ def _worker(rank, world, port, n, seeds, q):
             s = sim.sample(uniforms=u)
             pr = np.abs(want2) ** 2
             assert np.all(pr[s] > 0)
+        # A circuit that leaves enough qubits without a non-diagonal target: from |0...0> the layout parks those in the
+        # rank bits, no exchange happens, and — those bits being the same for every non-zero amplitude — sampling is
+        # bit-identical to the single-device sequential CDF in LOGICAL index order.
+        rng = np.random.default_rng(77)
+        lst = []
+        busy = [q_ for q_ in range(n) if q_ not in (2, n - 2)][: n - ng]
+        for _ in range(50):
+            k = str(rng.choice(["H", "Ry", "CNOT", "T", "X", "CZ"]))
+            a, b = (int(x) for x in rng.choice(busy, 2, replace=False))
+            if k == "CNOT":
+                lst.append(("CNOT", int(rng.choice([2, n - 2, a])), b))       # parked qubits may control
+            elif k == "CZ":
+                lst.append(("CZ", 2, b))
+            elif k == "Ry":
+                lst.append(("Ry", a, float(rng.uniform(-3, 3))))
+            elif k == "X":
+                lst.append(("X", int(rng.choice([2, n - 2, a]))))              # ... and be flipped
+            else:
+                lst.append((k, a))
+        g = H.gates(lst)
+        sim = ShardedSimulator(n, engine=EmulatorShardEngine(n, ng, rank, world), rank=rank, world=world)
+        cp = sim.compile(Circuit(n).extend(g))
+        if ng <= 2:
+            assert cp.n_swaps == 0
+        sim.execute(cp)
+        want = H.oracle_run(n, g)
+        worst = max(worst, float(np.max(np.abs(sim.get_state_vector() - want))))
+        u = np.concatenate([np.random.default_rng(3).random(200), [0.5, 0.25, 0.999]])
+        if cp.n_swaps == 0:
+            assert np.array_equal(sim.sample(uniforms=u), H.oracle_sample(H.oracle_probs(want), u))
         if rank == 0:
             q.put(worst)
     finally:
@@ -150,6 +180,22 @@ def test_sharded_matches_oracle_over_gloo(world):
         p.join(180)
         assert p.exitcode == 0
     assert q.get(timeout=5) < 1e-12
+
+
+def test_initial_layout_parks_untargeted_qubits_in_the_rank_bits():
+    import cuda_quantum_simulator_b200 as qs
+    from cuda_quantum_simulator_b200.sharded import choose_initial_layout
+    for n, ng in ((31, 1), (33, 3), (36, 3)):
+        c = qs.create_random_circuit(n, 20, 42)
+        perm = choose_initial_layout(n, ng, c.gates)
+        assert sorted(perm) == list(range(n))
+        assert plan_circuit(n, ng, c.gates, perm).n_swaps == 0          # identity layout: one swap (next test)
+        kept = [q for q in range(n) if perm[q] < n - ng]
+        assert [perm[q] for q in kept] == list(range(n - ng))           # the others keep their relative order
+    # nothing to gain: every qubit is a target early on -> the ones targeted last go global, layout still a permutation
+    c = qs.Circuit(4).h(0).h(1).h(2).h(3).h(3)
+    perm = choose_initial_layout(4, 1, c.gates)
+    assert sorted(perm) == [0, 1, 2, 3] and perm[3] == 3
 
 
 def test_planner_c4_needs_one_swap():
