@@ -196,6 +196,18 @@ template <int KIND, bool CTRL>
 __device__ __forceinline__ void lane_target(const DevOp& op, uint32_t sm, uint32_t tid, const double (&xr_)[kSlots],
                                             const double (&xi_)[kSlots], double (&yr_)[kSlots], double (&yi_)[kSlots]) {
     const int lm = 1 << op.tbit;
+    if (KIND == OP_FLIP) {
+        // pure data movement: every slot is fetched from the partner lane, or (controls not satisfied) from the
+        // thread's own lane — the select is on the source lane, not on the data
+        const int lane = (int)(tid & 31u);
+#pragma unroll
+        for (int k = 0; k < kSlots; ++k) {
+            const int src = (!CTRL || ((sm >> k) & 1)) ? (lane ^ lm) : lane;
+            yr_[k] = __shfl_sync(0xffffffffu, xr_[k], src);
+            yi_[k] = __shfl_sync(0xffffffffu, xi_[k], src);
+        }
+        return;
+    }
     const bool b = (tid >> op.tbit) & 1;
     // coefficient of my own amplitude and of my partner's
     const double cor = b ? op.m[6] : op.m[0], coi = b ? op.m[7] : op.m[1];
@@ -205,8 +217,7 @@ __device__ __forceinline__ void lane_target(const DevOp& op, uint32_t sm, uint32
         const double xr = xr_[k], xi = xi_[k];
         const double pr = shfl_xor_f64(xr, lm), pi = shfl_xor_f64(xi, lm);
         double nr, ni;
-        if (KIND == OP_FLIP) { nr = pr; ni = pi; }
-        else if (KIND == OP_ADIAG) { nr = cpr * pr - cpi * pi; ni = cpr * pi + cpi * pr; }
+        if (KIND == OP_ADIAG) { nr = cpr * pr - cpi * pi; ni = cpr * pi + cpi * pr; }
         else if (KIND == OP_MATREAL) { nr = cor * xr + cpr * pr; ni = cor * xi + cpr * pi; }
         else {
             nr = cor * xr - coi * xi + cpr * pr - cpi * pi;
