@@ -9,11 +9,14 @@
 //   kSlots amplitudes from shared memory into registers with 128-bit conflict-free loads, runs the
 //   sweep's op list — register-resident targets in-thread, lane-resident targets with __shfl_xor
 //   butterflies, diagonal gates as a single complex multiply wherever their qubits live — and writes back.
-//   TMA issue is folded into one elected thread: after tile i has been computed it issues the store of
-//   tile i, makes sure the store of tile i-1 has drained its stage and refills that stage with tile
+//   TMA issue is folded into warp 0 (lane q issues box q): after tile i has been computed it issues the
+//   store of tile i, makes sure the store of tile i-1 has drained its stage and refills that stage with tile
 //   i-1+S, so one or two tile loads are always in flight while the warps compute.  (A dedicated TMA
-//   warp would be the ninth/seventeenth warp and, with the 4-warp register allocation granularity, cost
+//   warp would be the seventeenth warp and, with the 4-warp register allocation granularity, cost
 //   a quarter of the register file.)
+//   Variants of the same kernel: basis-state input (PassParams::init_basis: no loads, zero fill + one generated
+//   tile), out-of-place store for a fused qubit exchange between GPUs (PassParams::redirect), store-side index
+//   maps (deferred X gates, folded trailing CNOTs).
 //
 // Algorithmic traffic: 2 * 16 * 2^n bytes per pass.
 #include "kernels.cuh"
@@ -150,8 +153,8 @@ __device__ __forceinline__ uint64_t run_offset(const PassDesc& pd, uint32_t run)
 }
 
 // ---- op application on the thread's register file -------------------------------------------------
-// Everything below is straight-line code over the 16 register slots: no per-slot branches, so the
-// 16 independent dependency chains interleave (controls become selects, and ops without controls —
+// Everything below is straight-line code over the kSlots register slots: no per-slot branches, so the
+// independent dependency chains interleave (controls become selects, and ops without controls —
 // the common case — carry no predicate at all).
 
 // Every op is written OUT OF PLACE: it reads the register file x and writes all of y.  The interpreter loop
