@@ -405,6 +405,13 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
                 if ((bl >> j) & 1) sb ^= pd.tail_lin[j];
             base_tab[pd.n_sweeps * kComputeThreads + (int)tid] = (uint16_t)sb;
         }
+        if (sw == 0) {
+            // and where the first load finds it (leading flips, inverse map)
+            uint32_t lb = pd.head_const;
+            for (int j = 0; j < pd.t; ++j)
+                if ((bl >> j) & 1) lb ^= pd.head_lin[j];
+            base_tab[(pd.n_sweeps + 1) * kComputeThreads + (int)tid] = (uint16_t)lb;
+        }
     }
     if (tid == 0) {
         if (P.use_tensor_map) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -623,17 +630,31 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
             const int slots = 1 << sd.r;
             const uint32_t base_local = base_tab[sw * kComputeThreads + (int)tid];
             const uint32_t tile_u32 = smem_u32(tile);
-            const uint32_t my_addr = tile_u32 + base_local * 16u;
             const bool full_sweep = (sd.r == kMaxRegBits) && (sd.nthr == kMaxTileBits - kMaxRegBits);
-            if (full_sweep) {
+            {
+                // where each slot is read from: its own index, or (first sweep of a pass with folded leading flips)
+                // the pre-image of that index under the flips
+                uint32_t la[kSlots];
+                if (sw == 0 && pd.n_head > 0) {
+                    uint32_t lb = base_tab[(pd.n_sweeps + 1) * kComputeThreads + (int)tid];
+                    for (int f = 0; f < pd.n_head_dyn; ++f)
+                        if ((gbase & pd.head_dyn[f].cmask_out) == pd.head_dyn[f].cval_out) lb ^= pd.head_dyn[f].w;
 #pragma unroll
-                for (int k = 0; k < kSlots; ++k) lds128(my_addr + (uint32_t)sd.slot_off[k] * 16u, ar[k], ai[k]);
-            } else {
+                    for (int k = 0; k < kSlots; ++k) la[k] = tile_u32 + (lb ^ (uint32_t)pd.load_slot_off[k]) * 16u;
+                } else {
 #pragma unroll
-                for (int k = 0; k < kSlots; ++k) {
-                    ar[k] = 0.0;
-                    ai[k] = 0.0;
-                    if (active && k < slots) lds128(my_addr + (uint32_t)sd.slot_off[k] * 16u, ar[k], ai[k]);
+                    for (int k = 0; k < kSlots; ++k) la[k] = tile_u32 + (base_local + (uint32_t)sd.slot_off[k]) * 16u;
+                }
+                if (full_sweep) {
+#pragma unroll
+                    for (int k = 0; k < kSlots; ++k) lds128(la[k], ar[k], ai[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kSlots; ++k) {
+                        ar[k] = 0.0;
+                        ai[k] = 0.0;
+                        if (active && k < slots) lds128(la[k], ar[k], ai[k]);
+                    }
                 }
             }
             const uint32_t ops_u32 = smem_u32(sops);
@@ -712,13 +733,13 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
 
 // worst case with three full stages must fit (pick_stages never has to go below the three the partner-tile store needs)
 static_assert(3 * (16 << kMaxTileBits) + (kMaxOpsPerPass + 1) * sizeof(DevOp) + kMaxPhaseOps * 13 * sizeof(double2) +
-                      2 * 3 * sizeof(uint64_t) + (kMaxSweeps + 1) * kComputeThreads * sizeof(uint16_t) <=
+                      2 * 3 * sizeof(uint64_t) + (kMaxSweeps + 2) * kComputeThreads * sizeof(uint16_t) <=
                   (size_t)kMaxDynamicSmem,
               "shared-memory budget of a pass");
 
 size_t pass_smem_bytes(const PassDesc& pd, int stages) {
     return (size_t)stages * ((size_t)16 << pd.t) + ((size_t)pd.n_ops + 1) * sizeof(DevOp) + (size_t)pd.n_phase * 13 * sizeof(double2) +
-           2 * (size_t)stages * sizeof(uint64_t) + ((size_t)pd.n_sweeps + 1) * kComputeThreads * sizeof(uint16_t);
+           2 * (size_t)stages * sizeof(uint64_t) + ((size_t)pd.n_sweeps + 2) * kComputeThreads * sizeof(uint16_t);
 }
 
 // Deepest ring that fits the 227 KiB of shared memory (at most kMaxStages).

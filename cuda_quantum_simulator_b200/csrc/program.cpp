@@ -461,26 +461,67 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
             pd.xor_tau = tau_bit;
         }
 
-        // Trailing bit flips: walking backwards, a FLIP that commutes with every op that stays behind it can be
-        // moved to the end of the pass, where it costs only index arithmetic in the final store.  Only flips that
-        // are affine in the tile-local index qualify (see TailDyn).
-        for (int j = 0; j < kMaxTileBits; ++j) pd.tail_lin[j] = (uint16_t)(1u << j);
+        // Trailing / leading bit flips.  Walking backwards, a FLIP that commutes with every op that stays behind it can
+        // be moved to the end of the pass, where it costs only index arithmetic in the final store; walking forwards,
+        // one that commutes with every op that stays in front of it can be moved to the start, into the first sweep's
+        // load.  Only flips that are affine in the tile-local index qualify (see TailDyn).
+        struct AffineMap {
+            uint16_t lin[kMaxTileBits];
+            uint16_t cst = 0;
+            TailDyn dyn[kMaxTailDyn];
+            int n_dyn = 0, n = 0;
+        };
+        auto affine_ok = [&](const LogicalOp& op, int n_dyn_so_far, bool* is_dyn) {
+            if (op.kind != OP_FLIP || op.target >= nl || local_of[op.target] < 0) return false;
+            int n_in = 0, n_out = 0;
+            for (int q = 0; q < 64; ++q)
+                if ((op.cmask >> q) & 1) ((q < nl && local_of[q] >= 0) ? n_in : n_out)++;
+            *is_dyn = n_out > 0;
+            return *is_dyn ? (n_in == 0 && n_dyn_so_far < kMaxTailDyn) : (n_in <= 1);
+        };
+        // F = f_m o ... o f_1 for the flips in execution order: F(x) = lin x ^ cst ^ (fired translations)
+        auto compose = [&](const std::vector<int>& flips, AffineMap& M) {
+            for (int j = 0; j < kMaxTileBits; ++j) M.lin[j] = (uint16_t)(1u << j);
+            for (int idx : flips) {
+                const LogicalOp& op = out.lops[idx];
+                const uint16_t et = (uint16_t)(1u << local_of[op.target]);
+                uint64_t cm_out = 0, cv_out = 0;
+                int cb = -1, cv = 1;
+                for (int q = 0; q < 64; ++q) {
+                    if (!((op.cmask >> q) & 1)) continue;
+                    const uint64_t v = (op.cval >> q) & 1;
+                    if (q < nl && local_of[q] >= 0) { cb = local_of[q]; cv = (int)v; }
+                    else { cm_out |= 1ULL << q; cv_out |= v << q; }
+                }
+                if (cm_out) {
+                    TailDyn& d = M.dyn[M.n_dyn++];
+                    d.cmask_out = cm_out; d.cval_out = cv_out; d.w = et;
+                } else if (cb < 0) {
+                    M.cst ^= et;
+                } else {
+                    // l_t ^= l_cb (^ 1 for a control on zero), composed after everything folded so far
+                    for (int j = 0; j < kMaxTileBits; ++j) if ((M.lin[j] >> cb) & 1) M.lin[j] ^= et;
+                    for (int d = 0; d < M.n_dyn; ++d) if ((M.dyn[d].w >> cb) & 1) M.dyn[d].w ^= et;
+                    if ((M.cst >> cb) & 1) M.cst ^= et;
+                    if (!cv) M.cst ^= et;
+                }
+                ++M.n;
+            }
+        };
+        auto apply_lin = [](const uint16_t (&lin)[kMaxTileBits], unsigned x) {
+            unsigned v = 0;
+            for (int j = 0; j < kMaxTileBits; ++j) if ((x >> j) & 1) v ^= lin[j];
+            return v;
+        };
+        for (int j = 0; j < kMaxTileBits; ++j) pd.tail_lin[j] = pd.head_lin[j] = (uint16_t)(1u << j);
         if (opt.fold_tail_flips) {
             std::vector<int> stay, tail;   // both in reverse order
             int n_dyn = 0;
             for (size_t k = plan.op_idx.size(); k-- > 0;) {
                 const int idx = plan.op_idx[k];
                 const LogicalOp& op = out.lops[idx];
-                bool movable = op.kind == OP_FLIP && (int)tail.size() < kMaxTailFlips && op.target < nl &&
-                               local_of[op.target] >= 0;
                 bool dyn = false;
-                if (movable) {
-                    int n_in = 0, n_out = 0;
-                    for (int q = 0; q < 64; ++q)
-                        if ((op.cmask >> q) & 1) ((q < nl && local_of[q] >= 0) ? n_in : n_out)++;
-                    dyn = n_out > 0;
-                    movable = dyn ? (n_in == 0 && n_dyn < kMaxTailDyn) : (n_in <= 1);
-                }
+                bool movable = (int)tail.size() < kMaxTailFlips && affine_ok(op, n_dyn, &dyn);
                 if (movable)
                     for (int s2 : stay)
                         if (!commutes(op, out.lops[s2])) { movable = false; break; }
@@ -490,32 +531,62 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
             if (!tail.empty()) {
                 std::reverse(stay.begin(), stay.end());
                 std::reverse(tail.begin(), tail.end());
-                for (int idx : tail) {
-                    const LogicalOp& op = out.lops[idx];
-                    const uint16_t et = (uint16_t)(1u << local_of[op.target]);
-                    uint64_t cm_out = 0, cv_out = 0;
-                    int cb = -1, cv = 1;
-                    for (int q = 0; q < 64; ++q) {
-                        if (!((op.cmask >> q) & 1)) continue;
-                        const uint64_t v = (op.cval >> q) & 1;
-                        if (q < nl && local_of[q] >= 0) { cb = local_of[q]; cv = (int)v; }
-                        else { cm_out |= 1ULL << q; cv_out |= v << q; }
-                    }
-                    if (cm_out) {
-                        TailDyn& d = pd.dyn[pd.n_dyn++];
-                        d.cmask_out = cm_out; d.cval_out = cv_out; d.w = et;
-                    } else if (cb < 0) {
-                        pd.tail_const ^= et;
-                    } else {
-                        // l_t ^= l_cb (^ 1 for a control on zero), composed after everything folded so far
-                        for (int j = 0; j < kMaxTileBits; ++j) if ((pd.tail_lin[j] >> cb) & 1) pd.tail_lin[j] ^= et;
-                        for (int d = 0; d < pd.n_dyn; ++d) if ((pd.dyn[d].w >> cb) & 1) pd.dyn[d].w ^= et;
-                        if ((pd.tail_const >> cb) & 1) pd.tail_const ^= et;
-                        if (!cv) pd.tail_const ^= et;
-                    }
-                    ++pd.n_tail;
-                }
+                AffineMap M;
+                compose(tail, M);
+                std::memcpy(pd.tail_lin, M.lin, sizeof(M.lin));
+                pd.tail_const = M.cst;
+                pd.n_dyn = M.n_dyn;
+                for (int d = 0; d < M.n_dyn; ++d) pd.dyn[d] = M.dyn[d];
+                pd.n_tail = M.n;
                 plan.op_idx.swap(stay);
+            }
+            // leading flips (of what is left)
+            std::vector<int> keep, head;
+            n_dyn = 0;
+            for (int idx : plan.op_idx) {
+                const LogicalOp& op = out.lops[idx];
+                bool dyn = false;
+                bool movable = (int)head.size() < kMaxTailFlips && affine_ok(op, n_dyn, &dyn);
+                if (movable)
+                    for (int s2 : keep)
+                        if (!commutes(op, out.lops[s2])) { movable = false; break; }
+                if (movable && dyn) ++n_dyn;
+                (movable ? head : keep).push_back(idx);
+            }
+            if (!head.empty()) {
+                AffineMap M;
+                compose(head, M);
+                // invert the linear part over GF(2) (Gauss-Jordan on [A | I], columns as bit masks of rows)
+                uint32_t rows[kMaxTileBits];   // row i: bits 0..11 = A[i][*], bits 16..27 = I[i][*]
+                for (int i = 0; i < kMaxTileBits; ++i) {
+                    uint32_t r = 1u << (16 + i);
+                    for (int j = 0; j < kMaxTileBits; ++j) if ((M.lin[j] >> i) & 1) r |= 1u << j;   // A[i][j] = bit i of image of e_j
+                    rows[i] = r;
+                }
+                bool ok = true;
+                for (int c = 0; c < kMaxTileBits && ok; ++c) {
+                    int piv = -1;
+                    for (int i = c; i < kMaxTileBits; ++i) if ((rows[i] >> c) & 1) { piv = i; break; }
+                    if (piv < 0) { ok = false; break; }
+                    std::swap(rows[c], rows[piv]);
+                    for (int i = 0; i < kMaxTileBits; ++i) if (i != c && ((rows[i] >> c) & 1)) rows[i] ^= rows[c];
+                }
+                if (!ok) return fail("internal: folded flips are not invertible");
+                uint16_t inv[kMaxTileBits];   // image of e_j under A^-1: bit i = Ainv[i][j]
+                for (int j = 0; j < kMaxTileBits; ++j) {
+                    unsigned v = 0;
+                    for (int i = 0; i < kMaxTileBits; ++i) if ((rows[i] >> (16 + j)) & 1) v |= 1u << i;
+                    inv[j] = (uint16_t)v;
+                }
+                std::memcpy(pd.head_lin, inv, sizeof(inv));
+                pd.head_const = (uint16_t)apply_lin(pd.head_lin, M.cst);
+                pd.n_head_dyn = M.n_dyn;
+                for (int d = 0; d < M.n_dyn; ++d) {
+                    pd.head_dyn[d] = M.dyn[d];
+                    pd.head_dyn[d].w = (uint16_t)apply_lin(pd.head_lin, M.dyn[d].w);
+                }
+                pd.n_head = M.n;
+                plan.op_idx.swap(keep);
             }
         }
 
@@ -693,12 +764,17 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
             pd.sweep[pd.n_sweeps++] = sd;
             todo.swap(deferred);
         }
-        {   // the final store's slot offsets: the folded flips' linear part applied to the last sweep's
+        {   // the final store's (first load's) slot offsets: the folded flips' linear part applied to the last (first) sweep's
             const SweepDesc& last = pd.sweep[pd.n_sweeps - 1];
+            const SweepDesc& first = pd.sweep[0];
             for (int k = 0; k < 16; ++k) {
-                unsigned v = 0;
-                for (int j = 0; j < kMaxTileBits; ++j) if ((last.slot_off[k] >> j) & 1) v ^= pd.tail_lin[j];
+                unsigned v = 0, w = 0;
+                for (int j = 0; j < kMaxTileBits; ++j) {
+                    if ((last.slot_off[k] >> j) & 1) v ^= pd.tail_lin[j];
+                    if ((first.slot_off[k] >> j) & 1) w ^= pd.head_lin[j];
+                }
                 pd.store_slot_off[k] = (uint16_t)v;
+                pd.load_slot_off[k] = (uint16_t)w;
             }
         }
         out.passes.push_back(pd);

@@ -33,7 +33,7 @@ constexpr int kComputeWarps = 1 << (kMaxTileBits - kMaxRegBits - 5);      // a f
 constexpr int kComputeThreads = kComputeWarps * 32;
 constexpr int kMaxSweeps = 12;
 constexpr int kMaxSegments = 14;
-constexpr int kMaxOpsPerPass = 128;      // ops of one pass are staged in shared memory (with kMaxSweeps and kMaxPhaseOps this
+constexpr int kMaxOpsPerPass = 120;      // ops of one pass are staged in shared memory (with kMaxSweeps and kMaxPhaseOps this
                                          // keeps three 64 KiB stages + tables within the 227 KiB of shared memory)
 constexpr int kMaxPhaseOps = 24;         // fused diagonal runs per pass (13 complex factors each in shared memory)
 constexpr int kPhaseTableSize = 1 << kMaxTileBits;   // one complex factor per tile-local index
@@ -162,6 +162,16 @@ struct PassDesc {
     uint16_t pad3;
     uint16_t store_slot_off[16];       // A applied to the last sweep's slot_off
     TailDyn dyn[kMaxTailDyn];
+    // Leading flips, folded the same way into the FIRST sweep's load: with F(x) = A x ^ c (^ translations) their
+    // combined index map, the element that belongs at tile-local index l is read from F^-1(l).  The fields hold the
+    // inverse map: head_lin = A^-1, head_const = A^-1 c, head_dyn[].w = A^-1 w.
+    int32_t n_head;
+    int32_t n_head_dyn;
+    uint16_t head_lin[kMaxTileBits];
+    uint16_t head_const;
+    uint16_t pad4;
+    uint16_t load_slot_off[16];        // A^-1 applied to the first sweep's slot_off
+    TailDyn head_dyn[kMaxTailDyn];
     Segment seg[kMaxSegments];
     SweepDesc sweep[kMaxSweeps];
 };
@@ -181,7 +191,7 @@ struct CompileOptions {
     bool merge = true;           // merge runs of gates on the same (target, controls)
     bool reorder = true;         // commute ops across passes when legal (fewer passes)
     int n_global = 0;            // qubits >= n - n_global live in the rank id (sharded state)
-    bool fold_tail_flips = true; // bit flips that can slide to the end of a pass become store addressing
+    bool fold_tail_flips = true; // bit flips that can slide to the end (start) of a pass become store (load) addressing
     bool fuse_diagonals = true;  // runs of >= 3 diagonal gates become one OP_PHASE
     bool defer_x = true;         // carry uncontrolled X gates as an index-XOR frame, folded into the last pass's addressing
     uint64_t initial_xor = 0;    // X frame inherited from earlier segments (sharded driver: pending flips of global qubits)

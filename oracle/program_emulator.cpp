@@ -82,6 +82,19 @@ void run_pass(const Program& prog, const PassDesc& pd, uint64_t hi_bits, cplx* s
                     if (on) eu[op.tmask_out * 13 + e] *= cplx(t.fr, t.fi);
                 }
         }
+        if (pd.n_head > 0) {
+            // folded leading flips: the element that belongs at tile-local index l is read from F^-1(l)
+            std::vector<cplx> moved(tile_amps);
+            uint32_t shift = pd.head_const;
+            for (int f = 0; f < pd.n_head_dyn; ++f)
+                if ((gbase & pd.head_dyn[f].cmask_out) == pd.head_dyn[f].cval_out) shift ^= pd.head_dyn[f].w;
+            for (uint32_t l = 0; l < tile_amps; ++l) {
+                uint32_t src = shift;
+                for (int j = 0; j < pd.t; ++j) if ((l >> j) & 1) src ^= pd.head_lin[j];
+                moved[l] = tile[src];
+            }
+            tile.swap(moved);
+        }
         for (int sw = 0; sw < pd.n_sweeps; ++sw) {
             const SweepDesc& sd = pd.sweep[sw];
             const int slots = 1 << sd.r;

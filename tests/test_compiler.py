@@ -94,3 +94,8 @@ def test_trailing_flips_fold_into_the_store(seed):
         want = H.oracle_run(n, g, st0)
         got, _ = H.emu_run(n, g, st0, lmin=3, tmax=tmax)
         assert np.max(np.abs(got - want)) < 1e-12, (n, tmax, seed)
+        # the same gates reversed: the flips LEAD the pass and fold into the first sweep's load (inverse affine map)
+        gr = np.ascontiguousarray(g[::-1])
+        want = H.oracle_run(n, gr, st0)
+        got, _ = H.emu_run(n, gr, st0, lmin=3, tmax=tmax)
+        assert np.max(np.abs(got - want)) < 1e-12, ("leading", n, tmax, seed)

@@ -71,6 +71,10 @@ def test_trailing_flips_fold_into_the_store(n):
         got, _ = run_gpu(n, g, st0)
         want = H.oracle_run(n, g, st0)
         assert np.max(np.abs(got - want)) < 1e-12, (n, trial)
+        gr = np.ascontiguousarray(g[::-1])            # leading flips: folded into the first sweep's load
+        got, _ = run_gpu(n, gr, st0)
+        want = H.oracle_run(n, gr, st0)
+        assert np.max(np.abs(got - want)) < 1e-12, ("leading", n, trial)
 
 
 @pytest.mark.parametrize("n", [1, 4, 12, 13, 15, 18, 21])
