@@ -641,6 +641,12 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
                         if ((gbase & pd.head_dyn[f].cmask_out) == pd.head_dyn[f].cval_out) lb ^= pd.head_dyn[f].w;
 #pragma unroll
                     for (int k = 0; k < kSlots; ++k) la[k] = tile_u32 + (lb ^ (uint32_t)pd.load_slot_off[k]) * 16u;
+                } else if (sd.n_head > 0) {   // a later sweep with folded leading flips (no table row: mapped on the fly)
+                    uint32_t lb = sd.head_const;
+                    for (int j = 0; j < pd.t; ++j)
+                        if ((base_local >> j) & 1u) lb ^= sd.head_lin[j];
+#pragma unroll
+                    for (int k = 0; k < kSlots; ++k) la[k] = tile_u32 + (lb ^ (uint32_t)sd.load_slot_off[k]) * 16u;
                 } else {
 #pragma unroll
                     for (int k = 0; k < kSlots; ++k) la[k] = tile_u32 + (base_local + (uint32_t)sd.slot_off[k]) * 16u;

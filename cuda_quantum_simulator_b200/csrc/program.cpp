@@ -513,6 +513,28 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
             for (int j = 0; j < kMaxTileBits; ++j) if ((x >> j) & 1) v ^= lin[j];
             return v;
         };
+        // inverse of a linear map over GF(2)^12 given by the images of the unit vectors (Gauss-Jordan on [A | I])
+        auto invert_gf2 = [](const uint16_t (&lin)[kMaxTileBits], uint16_t (&inv)[kMaxTileBits]) {
+            uint32_t rows[kMaxTileBits];   // row i: bits 0..11 = A[i][*], bits 16..27 = I[i][*]
+            for (int i = 0; i < kMaxTileBits; ++i) {
+                uint32_t r = 1u << (16 + i);
+                for (int j = 0; j < kMaxTileBits; ++j) if ((lin[j] >> i) & 1) r |= 1u << j;   // A[i][j] = bit i of the image of e_j
+                rows[i] = r;
+            }
+            for (int c = 0; c < kMaxTileBits; ++c) {
+                int piv = -1;
+                for (int i = c; i < kMaxTileBits; ++i) if ((rows[i] >> c) & 1) { piv = i; break; }
+                if (piv < 0) return false;
+                std::swap(rows[c], rows[piv]);
+                for (int i = 0; i < kMaxTileBits; ++i) if (i != c && ((rows[i] >> c) & 1)) rows[i] ^= rows[c];
+            }
+            for (int j = 0; j < kMaxTileBits; ++j) {
+                unsigned v = 0;
+                for (int i = 0; i < kMaxTileBits; ++i) if ((rows[i] >> (16 + j)) & 1) v |= 1u << i;
+                inv[j] = (uint16_t)v;
+            }
+            return true;
+        };
         for (int j = 0; j < kMaxTileBits; ++j) pd.tail_lin[j] = pd.head_lin[j] = (uint16_t)(1u << j);
         if (opt.fold_tail_flips) {
             std::vector<int> stay, tail;   // both in reverse order
@@ -556,28 +578,8 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
             if (!head.empty()) {
                 AffineMap M;
                 compose(head, M);
-                // invert the linear part over GF(2) (Gauss-Jordan on [A | I], columns as bit masks of rows)
-                uint32_t rows[kMaxTileBits];   // row i: bits 0..11 = A[i][*], bits 16..27 = I[i][*]
-                for (int i = 0; i < kMaxTileBits; ++i) {
-                    uint32_t r = 1u << (16 + i);
-                    for (int j = 0; j < kMaxTileBits; ++j) if ((M.lin[j] >> i) & 1) r |= 1u << j;   // A[i][j] = bit i of image of e_j
-                    rows[i] = r;
-                }
-                bool ok = true;
-                for (int c = 0; c < kMaxTileBits && ok; ++c) {
-                    int piv = -1;
-                    for (int i = c; i < kMaxTileBits; ++i) if ((rows[i] >> c) & 1) { piv = i; break; }
-                    if (piv < 0) { ok = false; break; }
-                    std::swap(rows[c], rows[piv]);
-                    for (int i = 0; i < kMaxTileBits; ++i) if (i != c && ((rows[i] >> c) & 1)) rows[i] ^= rows[c];
-                }
-                if (!ok) return fail("internal: folded flips are not invertible");
-                uint16_t inv[kMaxTileBits];   // image of e_j under A^-1: bit i = Ainv[i][j]
-                for (int j = 0; j < kMaxTileBits; ++j) {
-                    unsigned v = 0;
-                    for (int i = 0; i < kMaxTileBits; ++i) if ((rows[i] >> (16 + j)) & 1) v |= 1u << i;
-                    inv[j] = (uint16_t)v;
-                }
+                uint16_t inv[kMaxTileBits];
+                if (!invert_gf2(M.lin, inv)) return fail("internal: folded flips are not invertible");
                 std::memcpy(pd.head_lin, inv, sizeof(inv));
                 pd.head_const = (uint16_t)apply_lin(pd.head_lin, M.cst);
                 pd.n_head_dyn = M.n_dyn;
@@ -712,6 +714,31 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
             for (int i = 0; i < nthr; ++i) role_tid[sd.thr_pos[i]] = i;
             for (int j = 0; j < r; ++j) role_reg[sd.reg_pos[j]] = j;
 
+            // flips that lead a later sweep fold into its load (the first sweep's were taken at pass level above)
+            for (int j = 0; j < kMaxTileBits; ++j) sd.head_lin[j] = (uint16_t)(1u << j);
+            if (opt.fold_tail_flips && pd.n_sweeps > 0) {
+                std::vector<int> keep, head;
+                for (int idx : chosen) {
+                    const LogicalOp& op = out.lops[idx];
+                    bool dyn = false;
+                    bool movable = (int)head.size() < kMaxTailFlips && affine_ok(op, 0, &dyn) && !dyn;
+                    if (movable)
+                        for (int s2 : keep)
+                            if (!commutes(op, out.lops[s2])) { movable = false; break; }
+                    (movable ? head : keep).push_back(idx);
+                }
+                if (!head.empty()) {
+                    AffineMap M;
+                    compose(head, M);
+                    uint16_t inv[kMaxTileBits];
+                    if (!invert_gf2(M.lin, inv)) return fail("internal: folded flips are not invertible");
+                    std::memcpy(sd.head_lin, inv, sizeof(inv));
+                    sd.head_const = (uint16_t)apply_lin(sd.head_lin, M.cst);
+                    sd.n_head = (uint16_t)M.n;
+                    chosen.swap(keep);
+                }
+            }
+            for (int k = 0; k < 16; ++k) sd.load_slot_off[k] = (uint16_t)apply_lin(sd.head_lin, sd.slot_off[k]);
             sd.op_begin = (uint16_t)pd.n_ops;
             for (int idx : chosen) {
                 const LogicalOp& op = out.lops[idx];

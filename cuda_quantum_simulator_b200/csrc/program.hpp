@@ -110,6 +110,12 @@ struct SweepDesc {
     uint8_t reg_pos[4];          // tile-local bit position held by register bit j
     uint16_t slot_off[16];       // tile-local index offset of register slot k
     uint16_t pad;
+    // Flips (without controls outside the tile) that lead a LATER sweep fold into that sweep's load like the pass's
+    // leading flips fold into the first one (PassDesc::head_lin): inverse map, slot offsets already mapped.
+    uint16_t n_head;
+    uint16_t head_const;
+    uint16_t head_lin[kMaxTileBits];
+    uint16_t load_slot_off[16];
 };
 
 struct Segment {                 // tile number -> global base index, one contiguous run of outer bits

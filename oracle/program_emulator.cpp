@@ -97,6 +97,15 @@ void run_pass(const Program& prog, const PassDesc& pd, uint64_t hi_bits, cplx* s
         }
         for (int sw = 0; sw < pd.n_sweeps; ++sw) {
             const SweepDesc& sd = pd.sweep[sw];
+            if (sd.n_head > 0) {   // flips folded into this sweep's load
+                std::vector<cplx> moved(tile_amps);
+                for (uint32_t l = 0; l < tile_amps; ++l) {
+                    uint32_t src = sd.head_const;
+                    for (int j = 0; j < pd.t; ++j) if ((l >> j) & 1) src ^= sd.head_lin[j];
+                    moved[l] = tile[src];
+                }
+                tile.swap(moved);
+            }
             const int slots = 1 << sd.r;
             const uint32_t n_active = 1u << sd.nthr;
             for (uint32_t warp0 = 0; warp0 < n_active; warp0 += 32) {
