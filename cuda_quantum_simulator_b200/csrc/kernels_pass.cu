@@ -631,35 +631,39 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
             const uint32_t base_local = base_tab[sw * kComputeThreads + (int)tid];
             const uint32_t tile_u32 = smem_u32(tile);
             const bool full_sweep = (sd.r == kMaxRegBits) && (sd.nthr == kMaxTileBits - kMaxRegBits);
-            {
-                // where each slot is read from: its own index, or (first sweep of a pass with folded leading flips)
-                // the pre-image of that index under the flips
-                uint32_t la[kSlots];
+            const bool mapped_load = (sw == 0 && pd.n_head > 0) || sd.n_head > 0;
+            if (mapped_load) {
+                // folded leading flips: every slot is read from the pre-image of its index under the flips
+                uint32_t lb;
+                const uint16_t* loff;
                 if (sw == 0 && pd.n_head > 0) {
-                    uint32_t lb = base_tab[(pd.n_sweeps + 1) * kComputeThreads + (int)tid];
+                    lb = base_tab[(pd.n_sweeps + 1) * kComputeThreads + (int)tid];
                     for (int f = 0; f < pd.n_head_dyn; ++f)
                         if ((gbase & pd.head_dyn[f].cmask_out) == pd.head_dyn[f].cval_out) lb ^= pd.head_dyn[f].w;
-#pragma unroll
-                    for (int k = 0; k < kSlots; ++k) la[k] = tile_u32 + (lb ^ (uint32_t)pd.load_slot_off[k]) * 16u;
-                } else if (sd.n_head > 0) {   // a later sweep with folded leading flips (no table row: mapped on the fly)
-                    uint32_t lb = sd.head_const;
+                    loff = pd.load_slot_off;
+                } else {   // a later sweep (no table row: mapped on the fly)
+                    lb = sd.head_const;
                     for (int j = 0; j < pd.t; ++j)
                         if ((base_local >> j) & 1u) lb ^= sd.head_lin[j];
-#pragma unroll
-                    for (int k = 0; k < kSlots; ++k) la[k] = tile_u32 + (lb ^ (uint32_t)sd.load_slot_off[k]) * 16u;
-                } else {
-#pragma unroll
-                    for (int k = 0; k < kSlots; ++k) la[k] = tile_u32 + (base_local + (uint32_t)sd.slot_off[k]) * 16u;
+                    loff = sd.load_slot_off;
                 }
+#pragma unroll
+                for (int k = 0; k < kSlots; ++k) {
+                    ar[k] = 0.0;
+                    ai[k] = 0.0;
+                    if (active && k < slots) lds128(tile_u32 + (lb ^ (uint32_t)loff[k]) * 16u, ar[k], ai[k]);
+                }
+            } else {
+                const uint32_t my_addr = tile_u32 + base_local * 16u;
                 if (full_sweep) {
 #pragma unroll
-                    for (int k = 0; k < kSlots; ++k) lds128(la[k], ar[k], ai[k]);
+                    for (int k = 0; k < kSlots; ++k) lds128(my_addr + (uint32_t)sd.slot_off[k] * 16u, ar[k], ai[k]);
                 } else {
 #pragma unroll
                     for (int k = 0; k < kSlots; ++k) {
                         ar[k] = 0.0;
                         ai[k] = 0.0;
-                        if (active && k < slots) lds128(la[k], ar[k], ai[k]);
+                        if (active && k < slots) lds128(my_addr + (uint32_t)sd.slot_off[k] * 16u, ar[k], ai[k]);
                     }
                 }
             }
