@@ -115,6 +115,9 @@ QSIM_API qsim_status_t qsim_sim_create(int num_qubits, qsim_sim_t** out);       
 QSIM_API qsim_status_t qsim_sim_create_external(int num_qubits, void* device_state, qsim_sim_t** out);
 QSIM_API void qsim_sim_destroy(qsim_sim_t* s);
 QSIM_API qsim_status_t qsim_sim_set_stream(qsim_sim_t* s, void* cuda_stream);
+/* On library-owned memory (and on shards) reset / init_basis only RECORD the basis state: the first pass of the next
+ * run generates it on chip, and any other access (device_ptr, get_state, probabilities, sample, measure) writes it out
+ * first.  Observable behaviour is the reference's; on caller-owned memory of a plain simulator the write is immediate. */
 QSIM_API qsim_status_t qsim_sim_reset(qsim_sim_t* s);                                /* Simulator::reset */
 QSIM_API qsim_status_t qsim_sim_init_basis(qsim_sim_t* s, uint64_t basis_index);     /* StateVector::initializeBasis */
 QSIM_API qsim_status_t qsim_sim_set_state(qsim_sim_t* s, const double* host_amplitudes);
