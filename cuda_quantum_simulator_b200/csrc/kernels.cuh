@@ -22,7 +22,7 @@ struct PassParams {
     uint64_t n_tiles;         // 2^(pd.n - pd.t)
     int32_t stages;           // depth of the shared-memory ring
     int32_t use_tensor_map;   // 1: cp.async.bulk.tensor boxes (default); 0: one 1-D bulk copy per contiguous run
-    int32_t init_basis;       // 1: the memory holds nothing yet, the input state is the basis state |init_index>:
+    int32_t init_basis;       // 1 / 2: the memory holds nothing yet / only zeros; the input state is the basis state |init_index>:
     int32_t pad;              //    tiles are generated on chip, all-zero tiles are stored without interpretation
     uint64_t init_index;
     // Fused qubit exchange (sharded states): this pass stores OUT OF PLACE.  Tiles whose index bit `redirect_bit`

@@ -435,7 +435,8 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
     // Global base index of a unit = its number deposited into the index bits that are neither tile bits nor the
     // pivot ("holes").  Stepping to the next unit is an add with the holes filled so carries pass through them.
     const uint64_t xdep = xor_tau ? tile_base(pd, xor_tau) : 0ULL;   // index XOR between the members of a pair
-    uint64_t holes = xor_tau ? tile_base(pd, 1ULL << pivot) : 0ULL;
+    const uint64_t pivot_dep = xor_tau ? tile_base(pd, 1ULL << pivot) : 0ULL;
+    uint64_t holes = pivot_dep;
     for (int j = 0; j < pd.t; ++j) holes |= 1ULL << pd.tile_bits[j];
     // Fused exchange: the tiles that leave drain at NVLink speed, the ones that stay at HBM speed; mixing them in one
     // CTA's three-stage ring makes every third stage wait for a slow drain.  So the grid is split: CTAs [0, send_ctas)
@@ -540,7 +541,7 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
     const uint64_t init_tile = P.init_index & ~tile_mask;
     uint32_t init_local = 0;
     for (int j = 0; j < pd.t; ++j) init_local |= (uint32_t)((P.init_index >> pd.tile_bits[j]) & 1ULL) << j;
-    if (P.init_basis) {
+    if (P.init_basis == 1) {   // (init_basis == 2: the caller has zero-filled the buffer, e.g. with cudaMemsetAsync)
         const uint64_t dest_tile = init_tile ^ xdep;   // where that tile is written (deferred X gates on outer bits)
         const uint64_t n_amps = 1ULL << pd.n;
         uint4* out = reinterpret_cast<uint4*>(P.state);
@@ -574,7 +575,25 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
     }
 
     double ar[kSlots], ai[kSlots], br[kSlots], bi[kSlots];
-    for (uint64_t i = 0; i < n_my; ++i) {
+    // Basis-state input: only the item that holds |init_index> has anything to do — go straight to it
+    uint64_t i_begin = 0, i_end = n_my;
+    if (P.init_basis) {
+        uint64_t ub = init_tile;   // its unit: the member of the pair whose pivot bit is clear
+        const bool odd = xor_tau && (ub & pivot_dep);
+        if (odd) ub ^= xdep;
+        uint64_t u = 0;            // unit number = the base with the holes squeezed out
+        int j = 0;
+        for (int b = 0; b < pd.n; ++b)
+            if ((keep >> b) & 1ULL) { u |= ((ub >> b) & 1ULL) << j; ++j; }
+        i_end = 0;
+        if (u < n_units && u >= first && (u - first) % stride == 0 && !((P.init_index >> pd.n) != 0)) {
+            const uint64_t iu = (u - first) / stride;
+            i_begin = xor_tau ? 2 * iu + (odd ? 1 : 0) : iu;
+            i_end = i_begin + 1;
+            cur_unit = ub;
+        }
+    }
+    for (uint64_t i = i_begin; i < i_end; ++i) {
         const int s = (int)(i % n_stages);
         const uint32_t parity = (uint32_t)((i / n_stages) & 1);
         const bool odd_item = xor_tau && (i & 1);
