@@ -345,8 +345,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(e2e_sec.item()) * 1e3,
                 "what": "reset + run(host gate records: compile, upload, launch) + sample(1024 host uniforms) + indices to host; "
-                        "reset is lazy: the first pass after it generates |0..0> on chip (zero-fill + one tile) instead of "
-                        "a memset sweep followed by a load sweep; `value` is measured on the dense evolved state"},
+                        "reset is lazy: the next run zero-fills once (memset) and its first pass generates and processes only the "
+                        "tile that holds |0..0>, instead of a memset sweep followed by a full load/compute/store sweep; "
+                        "`value` is measured on the dense evolved state"},
         "gpu_launches": launches,
         "clocks": clocks,
     }
