@@ -420,6 +420,11 @@ __global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, i
 #pragma unroll
         for (int cd = 0; cd < kCand; ++cd) ct_nxt[cd] = gl < n_groups ? g_cand[(uint64_t)cd * n_groups + gl] : 0.0;
         int my_choice = 0xff;
+        // a whole batch of all-zero groups (long stretches of a sparse state): the running sum does not move
+        if (__all_sync(0xffffffffu, k_cur == (int)G_ZERO)) {
+            if (g0 + lane < n_groups) { g_start[g0 + lane] = c; g_choice[g0 + lane] = 0xff; }
+            continue;
+        }
         const int cnt = (n_groups - g0) < 32 ? (int)(n_groups - g0) : 32;
         double my_start = 0.0;
         bool my_done = false;
