@@ -102,8 +102,9 @@ def plan_circuit(num_qubits: int, n_global: int, gates: np.ndarray, perm: Option
     """Split a circuit into local segments separated by global<->local qubit swaps.
 
     `perm[q]` is the physical bit position currently holding logical qubit q.  The swap partner is the
-    local position whose next use as a non-diagonal target lies farthest in the future (Belady), with a
-    preference for high positions (long contiguous runs in the exchange).
+    local position whose next use as a non-diagonal target lies farthest in the future (Belady); among equals, one
+    that is unlikely to be a tile qubit of the preceding pass (so the exchange can be fused into it), then the highest
+    position (long contiguous runs in the exchange).
     """
     n, nl = num_qubits, num_qubits - n_global
     perm = list(range(n)) if perm is None else list(perm)
@@ -122,6 +123,17 @@ def plan_circuit(num_qubits: int, n_global: int, gates: np.ndarray, perm: Option
             for slot in _target_positions(g):
                 lq = int(g[qcols[slot]])
                 if perm[lq] >= nl:
+                    # tile qubits of the segment's last pass, roughly: the low contiguous run plus the most recent
+                    # non-diagonal targets.  A victim outside them lets the exchange ride on that pass's store.
+                    recent = set(range(min(5, nl)))
+                    for rec in reversed(cur):
+                        if len(recent) >= 12:
+                            break
+                        if rec[0] == _X:
+                            continue
+                        rg = {"type": rec[0]}
+                        for slot in _target_positions(rg):
+                            recent.add(rec[1 + slot])
                     flush()
                     # choose the local position to evict
                     next_use = {p: 1 << 60 for p in range(nl)}
@@ -134,7 +146,7 @@ def plan_circuit(num_qubits: int, n_global: int, gates: np.ndarray, perm: Option
                             if p < nl and next_use[p] == 1 << 60:
                                 next_use[p] = j
                     cand = [p for p in range(nl) if p not in busy]
-                    victim = max(cand, key=lambda p: (next_use[p], p))
+                    victim = max(cand, key=lambda p: (next_use[p], p not in recent, p))
                     gpos = perm[lq]
                     plan.steps.append(Step("swap", global_qubit=gpos, local_qubit=victim))
                     other = inv[victim]
