@@ -640,7 +640,9 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
             const bool last_sweep = (sw + 1 == pd.n_sweeps);
             const uint32_t xl = last_sweep ? pd.xor_local : 0u;                 // deferred X gates, see the store
             const int n_tail = last_sweep ? pd.n_tail : 0;                      // trailing bit flips, see the store
-            const bool permuted_store = (xl != 0u) || (n_tail > 0);
+            const bool mapped_load = (sw == 0 && pd.n_head > 0) || sd.n_head > 0;   // folded leading flips, see the load
+            // a load or a store that reaches into other threads' slots: everybody must have loaded before anybody stores
+            const bool permuted_store = (xl != 0u) || (n_tail > 0) || mapped_load;
             if (!warp_active) {
                 if (permuted_store) __syncthreads();   // keep the barrier count equal across warps
                 continue;
@@ -650,7 +652,6 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
             const uint32_t base_local = base_tab[sw * kComputeThreads + (int)tid];
             const uint32_t tile_u32 = smem_u32(tile);
             const bool full_sweep = (sd.r == kMaxRegBits) && (sd.nthr == kMaxTileBits - kMaxRegBits);
-            const bool mapped_load = (sw == 0 && pd.n_head > 0) || sd.n_head > 0;
             if (mapped_load) {
                 // folded leading flips: every slot is read from the pre-image of its index under the flips
                 uint32_t lb;
@@ -716,7 +717,8 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
             }
             // The pass's index permutations ride on the last sweep's store: the folded trailing bit flips (an affine
             // map of the tile-local index, see TailDyn), then the deferred X gates (l ^= xor_local).  The targets are
-            // other threads' slots, hence the barrier: everybody has finished loading.
+            // other threads' slots — and with folded LEADING flips this sweep's load read other threads' slots — hence
+            // the barrier: everybody has finished loading before anybody stores.
             if (permuted_store) __syncthreads();
             {
                 uint32_t l[kSlots];
@@ -757,7 +759,15 @@ fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ 
             }
         }
     }
-    if (warp == 0) tma_store_wait_all();
+    if (warp == 0) {
+        tma_store_wait_all();
+        if (P.redirect) {
+            // half of the tiles went to the partner GPU's memory through the async proxy: order those writes before
+            // anything the partner is told after this kernel (the ranks' barrier follows in the stream)
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __threadfence_system();
+        }
+    }
 }
 
 // worst case with three full stages must fit (pick_stages never has to go below the three the partner-tile store needs)

@@ -270,6 +270,8 @@ class CudaShardEngine:
             return False
         peer = self.rank ^ (1 << (global_qubit - self.nl))
         alt = 1 - self._cur
+        if os.environ.get("QSIM_EXCHANGE_PREBARRIER"):
+            self.device_barrier()
         _lib.check(_lib.lib().qsim_shard_execute_exchange(self._h, handle, c_void_p(self._bufs[alt].data_ptr()),
                                                          c_void_p(self._peer_ptr[peer][alt]), global_qubit, local_qubit))
         self._cur = alt

@@ -108,6 +108,24 @@ def test_run_from_a_recorded_basis_state(n):
         assert np.array_equal(sim.sample(0, uniforms=u), H.oracle_sample(H.oracle_probs(want0), u)), (n, trial)
 
 
+@pytest.mark.parametrize("n", [13, 14, 16, 18])
+def test_leading_flips_with_a_plain_store(n):
+    """Flips folded into a sweep's LOAD read other threads' slots; when the same sweep then stores in place (no folded
+    trailing flips, no X frame) a barrier must separate the two.  Short passes make the window wide: a CNOT ladder that
+    cannot slide to the end because a Hadamard on its last target follows."""
+    rng = np.random.default_rng(8100 + n)
+    for trial in range(12):
+        qs = [int(x) for x in rng.permutation(n)[: int(rng.integers(3, min(n, 9)))]]
+        lst = [("CNOT", qs[i], qs[i + 1]) for i in range(len(qs) - 1)]
+        lst += [("H", qs[-1]), ("H", qs[0])]
+        g = H.gates(lst)
+        st0 = H.random_state(n, rng)
+        want = H.oracle_run(n, g, st0)
+        for rep in range(3):
+            got, _ = run_gpu(n, g, st0)
+            assert np.max(np.abs(got - want)) < 1e-12, (n, trial, rep)
+
+
 def test_every_gate_on_every_qubit_18q():
     """Each gate type with its target on every bit position class (lane, register, warp, outside-tile)."""
     n = 18
