@@ -63,6 +63,26 @@ class EmulatorShardEngine:
             r.wait()
         self.shard[leaving] = recv.numpy().view(np.complex128)
 
+    fused_exchanges = 0
+
+    def run_program_then_swap(self, handle, g, l):
+        """Stands in for the fused pass + exchange of the CUDA engine (same contract: refuse, having done nothing, or do
+        both): accepted for every other request so that both branches of ShardedSimulator.execute are exercised."""
+        self._asked = getattr(self, "_asked", 0) + 1
+        if self._asked % 2 == 0:
+            return False
+        self.run_program(handle)
+        self.swap(g, l)
+        self.fused_exchanges += 1
+        return True
+
+    def cdf_prepare(self):
+        """Staged sampling of the CUDA engine: this shard's approximate total (here simply its exact total)."""
+        return float(np.sum(H.oracle_probs(self.shard)))
+
+    def cdf_classify(self, approx_c_init):
+        self._approx_c_init = approx_c_init   # only used by the CUDA engine to pick tentative binades
+
     def synchronize(self): pass
     def local_state(self): return self.shard.copy()
     def partial_probability(self, bit=-1): return float(np.sum(np.abs(self.shard) ** 2))
