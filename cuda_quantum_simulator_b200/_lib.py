@@ -88,6 +88,7 @@ def _declare(L: ctypes.CDLL) -> None:
         "qsim_sim_get_probabilities": (c_int, [P, P]),
         "qsim_sim_get_probability_range": (c_int, [P, c_uint64, c_uint64, P]),
         "qsim_sim_total_probability": (c_int, [P, POINTER(c_double)]),
+        "qsim_sim_marginal": (c_int, [P, P, c_int, P]),
         "qsim_sim_sample_uniforms": (c_int, [P, P, c_int64, P]),
         "qsim_sim_sample_seeded": (c_int, [P, c_uint, c_int64, P]),
         "qsim_sim_measure": (c_int, [P, c_int, c_double, POINTER(c_int)]),

@@ -368,6 +368,16 @@ qsim_status_t qsim_sim_total_probability(const qsim_sim_t* s, double* out) {
     });
 }
 
+qsim_status_t qsim_sim_marginal(const qsim_sim_t* s, const int* qubits, int k, double* out) {
+    return guarded([&] {
+        require(s != nullptr && out != nullptr && (qubits != nullptr || k == 0), "null argument");
+        require(k >= 0 && k <= 12, "marginal over 0..12 qubits");
+        const std::vector<int> bits(qubits, qubits + k);
+        const std::vector<double> m = s->sim->state().marginalProbabilities(bits);
+        std::memcpy(out, m.data(), m.size() * sizeof(double));
+    });
+}
+
 qsim_status_t qsim_sim_sample_uniforms(qsim_sim_t* s, const double* u, int64_t shots, int64_t* out) {
     return guarded([&] {
         require(s != nullptr && u != nullptr && out != nullptr, "null argument");

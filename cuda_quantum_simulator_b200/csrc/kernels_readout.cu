@@ -593,6 +593,147 @@ void launch_collapse(cuDoubleComplex* state, uint64_t n, int bit, int outcome, d
     CUDA_CHECK_LAST_ERROR();
 }
 
+namespace {
+
+// Marginals.  Lanes always enumerate the five lowest index bits (coalesced 512-byte rows whatever the chosen qubits
+// are); the chosen bits among them ("low bin bits") split a warp's lanes into sub-bins, reduced with butterflies over
+// the other lane bits.  A block handles one value of the remaining chosen bits and one segment of the other indices;
+// sums are formed in a fixed order throughout.
+__global__ void marginal_partial_kernel(const cuDoubleComplex* __restrict__ state, uint64_t hole_mask, uint64_t keep,
+                                        unsigned low_bin_mask, const uint64_t* __restrict__ high_bits_of,
+                                        uint64_t others_per_seg, int n_seg, uint64_t step_dep,
+                                        const uint64_t* __restrict__ start_dep, int n_sub, double* __restrict__ partial) {
+    __shared__ double part[kBlock / 32][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int mh = blockIdx.x / n_seg, seg = blockIdx.x % n_seg;
+    // x runs over: (fixed high bin bits) | (other-index o deposited into the non-bin, non-lane bits) | lane
+    uint64_t x = start_dep[(size_t)seg * n_warps + warp];
+    const uint64_t fixed = high_bits_of[mh] | (uint64_t)lane;
+    double acc = 0.0;
+    for (uint64_t j = warp; j < others_per_seg; j += n_warps) {
+        acc = __dadd_rn(acc, prob_of(state[x | fixed]));
+        x = ((x | hole_mask) + step_dep) & keep;
+    }
+    // butterflies over the lane bits that are not bin bits: afterwards every lane holds its sub-bin's warp total
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const double other = __shfl_xor_sync(0xffffffffu, acc, 1 << b);
+        if (!((low_bin_mask >> b) & 1u)) acc = __dadd_rn(acc, other);
+    }
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        // lane l with no non-bin lane bits set represents sub-bin pattern (l & low_bin_mask); sum the warps in order
+        if ((lane & ~low_bin_mask & 31u) == 0) {
+            double t = 0.0;
+            for (int w = 0; w < n_warps; ++w) t = __dadd_rn(t, part[w][lane]);
+            // compact the pattern's bits into the sub-bin number
+            int sub = 0, jb = 0;
+            for (int b = 0; b < 5; ++b)
+                if ((low_bin_mask >> b) & 1u) { sub |= ((lane >> b) & 1) << jb; ++jb; }
+            partial[((size_t)mh * n_sub + sub) * n_seg + seg] = t;
+        }
+    }
+}
+
+// out[m] = sum over segments, m assembled from (high part, sub-bin) through the bin table
+__global__ void marginal_final_kernel(const double* __restrict__ partial, int n_seg, int n_rows, const int* __restrict__ row_to_bin,
+                                      double* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    double t = 0.0;
+    for (int s2 = 0; s2 < n_seg; ++s2) t = __dadd_rn(t, partial[(size_t)r * n_seg + s2]);
+    out[row_to_bin[r]] = t;
+}
+
+uint64_t deposit_bits(uint64_t v, uint64_t mask) {   // software pdep (host)
+    uint64_t r = 0;
+    int j = 0;
+    for (int b = 0; b < 64; ++b)
+        if ((mask >> b) & 1ULL) { r |= ((v >> j) & 1ULL) << b; ++j; }
+    return r;
+}
+
+}  // namespace
+
+void marginal_probabilities(const cuDoubleComplex* state, int n_bits, const int* bits, int k, double* host_out, Engine& eng) {
+    if (k < 0 || k > 12 || k > n_bits) throw std::invalid_argument("marginal over 0..12 qubits");
+    uint64_t bin_mask = 0;
+    for (int i = 0; i < k; ++i) {
+        if (bits[i] < 0 || bits[i] >= n_bits || ((bin_mask >> bits[i]) & 1ULL)) throw std::invalid_argument("Duplicate or invalid qubit in marginal");
+        bin_mask |= 1ULL << bits[i];
+    }
+    const int n_bins = 1 << k;
+    if (n_bits < 5) {   // tiny states: on the host from the probabilities
+        std::vector<double> p((size_t)1 << n_bits);
+        double* d = static_cast<double*>(eng.scratch(0, p.size() * sizeof(double)));
+        launch_probabilities(state, d, 0, p.size(), eng.numSMs(), eng.stream());
+        CUDA_CHECK(cudaMemcpyAsync(p.data(), d, p.size() * sizeof(double), cudaMemcpyDeviceToHost, eng.stream()));
+        CUDA_CHECK(cudaStreamSynchronize(eng.stream()));
+        for (int m = 0; m < n_bins; ++m) host_out[m] = 0.0;
+        for (size_t x = 0; x < p.size(); ++x) {
+            int m = 0;
+            for (int i = 0; i < k; ++i) m |= (int)((x >> bits[i]) & 1) << i;
+            host_out[m] += p[x];
+        }
+        eng.countLaunch(1);
+        return;
+    }
+    const uint64_t full_mask = (1ULL << n_bits) - 1ULL;
+    const unsigned low_bin_mask = (unsigned)(bin_mask & 31ULL);
+    const uint64_t high_bin_mask = bin_mask & ~31ULL;
+    const uint64_t hole_mask = high_bin_mask | 31ULL;             // bits the running index does not enumerate
+    const uint64_t keep = full_mask & ~hole_mask;
+    const int k_low = __builtin_popcount(low_bin_mask), k_high = k - k_low;
+    const int n_sub = 1 << k_low, n_high = 1 << k_high;
+    const uint64_t n_others = 1ULL << (n_bits - 5 - k_high);      // other-indices per high-bin value (lanes excluded)
+    const int n_warps = kBlock / 32;
+    int n_seg = 1;
+    while ((uint64_t)n_high * n_seg < (uint64_t)eng.numSMs() * 8 && (uint64_t)n_seg * 2 * n_warps <= n_others) n_seg *= 2;
+    const uint64_t others_per_seg = n_others / n_seg;
+    // host tables: index bits of every high-bin value; deposited start of every (segment, warp); row -> outcome
+    std::vector<uint64_t> h((size_t)n_high + (size_t)n_seg * n_warps);
+    std::vector<int> hb, lb;   // positions (within `bits`) of the high / low chosen bits, ascending by index bit
+    for (int b = 0; b < n_bits; ++b)
+        for (int i = 0; i < k; ++i)
+            if (bits[i] == b) (b < 5 ? lb : hb).push_back(i);
+    for (int mh = 0; mh < n_high; ++mh) {
+        uint64_t v = 0;
+        for (int j = 0; j < k_high; ++j) v |= (uint64_t)((mh >> j) & 1) << bits[hb[j]];
+        h[mh] = v;
+    }
+    for (int sg = 0; sg < n_seg; ++sg)
+        for (int w = 0; w < n_warps; ++w) h[(size_t)n_high + (size_t)sg * n_warps + w] = deposit_bits((uint64_t)sg * others_per_seg + w, keep);
+    std::vector<int> row_to_bin((size_t)n_high * n_sub);
+    for (int mh = 0; mh < n_high; ++mh)
+        for (int sub = 0; sub < n_sub; ++sub) {
+            int m = 0;
+            for (int j = 0; j < k_high; ++j) m |= ((mh >> j) & 1) << hb[j];
+            for (int j = 0; j < k_low; ++j) m |= ((sub >> j) & 1) << lb[j];
+            row_to_bin[(size_t)mh * n_sub + sub] = m;
+        }
+    const size_t tab_bytes = (h.size() * sizeof(uint64_t) + 63) & ~(size_t)63;
+    const size_t map_bytes = (row_to_bin.size() * sizeof(int) + 63) & ~(size_t)63;
+    const size_t part_bytes = ((size_t)n_bins * n_seg + n_bins) * sizeof(double);
+    unsigned char* arena = static_cast<unsigned char*>(eng.scratch(0, tab_bytes + map_bytes + part_bytes + 64));
+    uint64_t* d_tab = reinterpret_cast<uint64_t*>(arena);
+    int* d_map = reinterpret_cast<int*>(arena + tab_bytes);
+    double* d_part = reinterpret_cast<double*>(arena + tab_bytes + map_bytes);
+    double* d_out = d_part + (size_t)n_bins * n_seg;
+    cudaStream_t stream = eng.stream();
+    CUDA_CHECK(cudaMemcpyAsync(d_tab, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    CUDA_CHECK(cudaMemcpyAsync(d_map, row_to_bin.data(), row_to_bin.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));   // the host tables are pageable and go out of scope
+    marginal_partial_kernel<<<n_high * n_seg, kBlock, 0, stream>>>(state, hole_mask, keep, low_bin_mask, d_tab, others_per_seg, n_seg,
+                                                                  deposit_bits((uint64_t)n_warps, keep), d_tab + n_high, n_sub, d_part);
+    CUDA_CHECK_LAST_ERROR();
+    marginal_final_kernel<<<(n_bins + kBlock - 1) / kBlock, kBlock, 0, stream>>>(d_part, n_seg, n_bins, d_map, d_out);
+    CUDA_CHECK_LAST_ERROR();
+    CUDA_CHECK(cudaMemcpyAsync(host_out, d_out, (size_t)n_bins * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    eng.countLaunch(2);
+}
+
 SequentialCdf::SequentialCdf(const cuDoubleComplex* state, uint64_t n, int mask_bit, Engine& eng, double c_init)
     : state_(state), n_(n), mask_bit_(mask_bit), stream_(eng.stream()), eng_(eng) {
     setup();

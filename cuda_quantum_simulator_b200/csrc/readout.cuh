@@ -17,6 +17,9 @@ void launch_probabilities(const cuDoubleComplex* state, double* out, uint64_t fi
 void launch_init_basis(cuDoubleComplex* state, uint64_t n, uint64_t idx, cudaStream_t stream);
 // sum of |a_i|^2 over indices whose bit `mask_bit` is 0 (mask_bit < 0: all); deterministic tree order
 double reduce_probability(const cuDoubleComplex* state, uint64_t n, int mask_bit, Engine& eng);
+// Marginal distribution over k index bits (bits[i] -> bit i of the outcome), 2^k doubles to the host: every amplitude is
+// read once, sums are formed in a fixed tree order (deterministic), nothing of size 2^n is materialised.
+void marginal_probabilities(const cuDoubleComplex* state, int n_bits, const int* bits, int k, double* host_out, Engine& eng);
 void launch_collapse(cuDoubleComplex* state, uint64_t n, int bit, int outcome, double scale, int num_sms,
                      cudaStream_t stream);
 

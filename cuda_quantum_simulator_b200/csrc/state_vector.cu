@@ -248,6 +248,12 @@ std::vector<int64_t> StateVector::sampleWithUniforms(const double* uniforms, int
     return out;
 }
 
+std::vector<double> StateVector::marginalProbabilities(const std::vector<int>& bits) const {
+    std::vector<double> out(size_t(1) << bits.size());
+    b200::marginal_probabilities(devicePtr(), num_qubits_, bits.data(), (int)bits.size(), out.data(), *engine_);
+    return out;
+}
+
 double StateVector::sampleShardPrepare() {
     prepared_cdf_ = std::make_unique<b200::SequentialCdf>(devicePtr(), size_, -1, *engine_, b200::SequentialCdf::Deferred{});
     return prepared_cdf_->approxTotal();

@@ -88,6 +88,13 @@ class Simulator:
         _lib.check(_lib.lib().qsim_sim_get_probability_range(self._h, int(first), int(count), out.ctypes.data_as(c_void_p)))
         return out
 
+    def marginal(self, qubits) -> np.ndarray:
+        """Marginal distribution of up to 12 qubits (qubits[i] -> bit i of the outcome), computed on the device."""
+        qs = np.ascontiguousarray(qubits, dtype=np.int32)
+        out = np.empty(1 << len(qs), np.float64)
+        _lib.check(_lib.lib().qsim_sim_marginal(self._h, qs.ctypes.data_as(c_void_p), len(qs), out.ctypes.data_as(c_void_p)))
+        return out
+
     def get_total_probability(self) -> float:
         v = c_double()
         _lib.check(_lib.lib().qsim_sim_total_probability(self._h, byref(v)))

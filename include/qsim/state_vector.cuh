@@ -72,6 +72,8 @@ public:
     // then sampleShard(exact sum of the shards before, ...) finishes.  No other read-out in between.
     double sampleShardPrepare();
     void sampleShardClassify(double approx_c_init);
+    // marginal distribution over k index bits (bits[i] -> bit i of the outcome), k <= 12; nothing of size 2^n is built
+    std::vector<double> marginalProbabilities(const std::vector<int>& bits) const;
     double partialProbability(int bit) const;                            // sum |a|^2 with index bit == 0 (bit<0: all)
     void collapse(int bit, int outcome, double scale);
 

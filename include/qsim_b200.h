@@ -133,6 +133,9 @@ QSIM_API qsim_status_t qsim_sim_get_probabilities(const qsim_sim_t* s, double* h
 QSIM_API qsim_status_t qsim_sim_get_probability_range(const qsim_sim_t* s, uint64_t first, uint64_t count,
                                                       double* host_out);
 QSIM_API qsim_status_t qsim_sim_total_probability(const qsim_sim_t* s, double* out); /* getTotalProbability */
+/* Marginal distribution of k <= 12 qubits (qubits[i] -> bit i of the outcome), 2^k doubles: what the reference's callers
+ * get by summing getProbabilities() on the host (src/main.cpp:30-41), computed on the device without a 2^n vector. */
+QSIM_API qsim_status_t qsim_sim_marginal(const qsim_sim_t* s, const int* qubits, int k, double* host_out);
 /* Simulator::sample with caller-supplied uniforms in [0,1): out[i] = smallest index
  * whose sequential fp64 CDF value is >= uniforms[i] — bit-identical to std::partial_sum +
  * std::lower_bound (reference src/Simulator.cu:164-185).  64-bit indices. */

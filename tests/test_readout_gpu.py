@@ -145,3 +145,25 @@ def test_measure_edge_cases():
     a = sim.measure_qubit(0, 0.7)
     b = sim.measure_qubit(1, 0.2)
     assert a == b
+
+
+@pytest.mark.parametrize("n", [1, 3, 9, 14, 20])
+def test_marginal_probabilities(n):
+    """Device-side marginals (qsim_sim_marginal): what a caller of the reference computes from getProbabilities()."""
+    rng = np.random.default_rng(600 + n)
+    st = H.random_state(n, rng)
+    sim = prepared(n, [], st)
+    probs = H.oracle_probs(st)
+    idx = np.arange(1 << n)
+    for k in sorted({0, 1, min(n, 2), min(n, 5), min(n, 12)}):
+        qs = [int(x) for x in rng.permutation(n)[:k]]
+        outcome = np.zeros(1 << n, np.int64)
+        for i, qb in enumerate(qs):
+            outcome |= ((idx >> qb) & 1) << i
+        want = np.bincount(outcome, weights=probs, minlength=1 << k)
+        got = sim.marginal(qs)
+        assert got.shape == (1 << k,)
+        assert np.max(np.abs(got - want)) < 1e-13, (n, k, qs)
+        assert np.array_equal(got, sim.marginal(qs))          # fixed summation order: reproducible bit for bit
+    with pytest.raises(q.InvalidArgument):
+        sim.marginal([0, 0] if n > 1 else [5])
