@@ -327,6 +327,12 @@ class CudaShardEngine:
                                                 out.ctypes.data_as(c_void_p), byref(c_end)))
         return out, c_end.value
 
+    def marginal(self, local_bits) -> np.ndarray:
+        qs = np.ascontiguousarray(local_bits, dtype=np.int32)
+        out = np.empty(1 << len(qs), np.float64)
+        _lib.check(_lib.lib().qsim_sim_marginal(self._h, qs.ctypes.data_as(c_void_p), len(qs), out.ctypes.data_as(c_void_p)))
+        return out
+
     def cdf_prepare(self) -> float:
         v = c_double()
         _lib.check(_lib.lib().qsim_shard_cdf_prepare(self._h, byref(v)))
@@ -501,6 +507,42 @@ class ShardedSimulator:
 
     def get_total_probability(self) -> float:
         return float(sum(self._allgather(self.engine.partial_probability(-1))))
+
+    def marginal(self, qubits: Sequence[int]) -> np.ndarray:
+        """Marginal distribution of up to 12 logical qubits (qubits[i] -> bit i of the outcome), on every rank: each shard
+        reduces over its local index bits on the device, the rank bits place the shard's share in the outcome."""
+        phys = [self.perm[int(q_)] for q_ in qubits]
+        if len(set(phys)) != len(phys):
+            raise _lib.InvalidArgument("Duplicate qubit in marginal")
+        loc = [(i, p) for i, p in enumerate(phys) if p < self.nl]
+        glob = [(i, p) for i, p in enumerate(phys) if p >= self.nl]
+        mine = np.ascontiguousarray(self.engine.marginal([p for _, p in loc]), np.float64)
+        if self.world > 1:
+            if hasattr(self.engine, "allgather_array"):
+                shares = [np.asarray(a).view(np.float64) for a in self.engine.allgather_array(mine.view(np.complex128) if len(mine) % 2 == 0 else np.concatenate([mine, [0.0]]).view(np.complex128))]
+                shares = [a[:len(mine)] for a in shares]
+            else:
+                import torch
+                import torch.distributed as dist
+                t = torch.from_numpy(mine).cuda()
+                outs = [torch.empty_like(t) for _ in range(self.world)]
+                dist.all_gather(outs, t)
+                shares = [o.cpu().numpy() for o in outs]
+        else:
+            shares = [mine]
+        fx = self.frame >> self.nl
+        out = np.zeros(1 << len(phys), np.float64)
+        sub = np.arange(1 << len(loc))
+        spread = np.zeros(len(sub), np.int64)                   # local outcome bits moved to their places
+        for j, (i, _) in enumerate(loc):
+            spread |= ((sub >> j) & 1) << i
+        for r, share in enumerate(shares):
+            rank_bits = r ^ fx                                  # stored rank r holds frame-resolved rank r ^ fx
+            base = 0
+            for i, p in glob:
+                base |= ((rank_bits >> (p - self.nl)) & 1) << i
+            np.add.at(out, spread | base, share)
+        return out
 
     def sample(self, n_shots: int = 0, uniforms: Optional[np.ndarray] = None, seed: Optional[int] = None) -> np.ndarray:
         """Bit-exact distributed sampling: the sequential CDF runs through the shards in stored-index order (the

@@ -76,6 +76,14 @@ class EmulatorShardEngine:
         self.fused_exchanges += 1
         return True
 
+    def marginal(self, local_bits):
+        probs = H.oracle_probs(self.shard)
+        idx = np.arange(len(probs))
+        outcome = np.zeros(len(probs), np.int64)
+        for i, b in enumerate(local_bits):
+            outcome |= ((idx >> b) & 1) << i
+        return np.bincount(outcome, weights=probs, minlength=1 << len(local_bits))
+
     def cdf_prepare(self):
         """Staged sampling of the CUDA engine: this shard's approximate total (here simply its exact total)."""
         return float(np.sum(H.oracle_probs(self.shard)))
@@ -141,6 +149,14 @@ def _worker(rank, world, port, n, seeds, q):
             want2 = H.oracle_run(n, g, want)
             worst = max(worst, float(np.max(np.abs(got2 - want2))))
             assert abs(sim.get_total_probability() - 1) < 1e-10
+            # marginals of a few logical qubits (local and rank bits mixed, after swaps and with a pending X frame)
+            qs = [int(x) for x in np.random.default_rng(seed).permutation(n)[:4]]
+            idx = np.arange(1 << n)
+            outcome = np.zeros(1 << n, np.int64)
+            for i, qb in enumerate(qs):
+                outcome |= ((idx >> qb) & 1) << i
+            want_m = np.bincount(outcome, weights=np.abs(want2) ** 2, minlength=16)
+            assert np.max(np.abs(sim.marginal(qs) - want_m)) < 1e-12
             # sampling: identical on every rank, right distribution support
             u = np.random.default_rng(1).random(64)
             s = sim.sample(uniforms=u)

@@ -39,6 +39,13 @@ for seed, n in [(1, 12), (2, 16), (3, 18)]:
     s = sim.sample(uniforms=u)
     assert np.all(np.abs(want[s]) ** 2 > 0)
     assert abs(sim.get_total_probability() - 1) < 1e-10
+    qs = [int(x) for x in np.random.default_rng(seed).permutation(n)[:5]]
+    idx = np.arange(1 << n)
+    outcome = np.zeros(1 << n, np.int64)
+    for i, qb in enumerate(qs):
+        outcome |= ((idx >> qb) & 1) << i
+    want_m = np.bincount(outcome, weights=np.abs(want) ** 2, minlength=32)
+    assert np.max(np.abs(sim.marginal(qs) - want_m)) < 1e-12
     if rank == 0:
         print(f"n={n} seed={seed} exchange={sim.engine.exchange} swaps={sim.compile(c).n_swaps} "
               f"fused={sim.engine.fused_exchanges} max|err|={err:.2e}", flush=True)
