@@ -38,6 +38,8 @@ public:
     const StateVector& state() const { return state_; }
     void execute(const b200::DeviceProgram& program);   // pre-compiled circuit, no host work
     std::vector<int64_t> sampleSeeded(unsigned seed, int64_t n_shots) { return state_.sampleSeeded(seed, n_shots); }
+    // marginal distribution of up to 12 qubits (qubits[i] -> bit i of the outcome), reduced on the device
+    std::vector<double> getMarginalProbabilities(const std::vector<int>& qubits) const { return state_.marginalProbabilities(qubits); }
     int measureQubit(int qubit, double uniform_draw) { return state_.measure(qubit, uniform_draw); }
     void synchronize() const;
 
