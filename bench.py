@@ -46,9 +46,13 @@ def parse():
     ap.add_argument("--local-qubits", type=int, default=30, help="qubits per GPU shard (30 = BASELINE configs[1])")
     ap.add_argument("--depth", type=int, default=20)
     ap.add_argument("--seed", type=int, default=42)
-    ap.add_argument("--cpu-qubits", type=int, default=26, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-qubits", type=int, default=27, help="size of the bounded CPU-baseline sample of the GPU arm")
+    ap.add_argument("--ref-qubits", type=int, default=30, help="--impl reference: largest state the host runs for real")
+    ap.add_argument("--ref-runs", type=int, default=2, help="--impl reference: timed full-size runs (~50 s each at 30 qubits)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the depth-200 variant")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the oracle parity check before timing")
+    ap.add_argument("--no-c4", action="store_true", help="N = 8: skip the 36-qubit C4 leg (128 GiB shards)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"])
     return ap.parse_args()
 
@@ -124,34 +128,116 @@ def cpu_reference_run(n, depth, seed, repeats=1):
     return best, kind, len(g)
 
 
+def workload_name(n, depth, seed, n_local):
+    return (f"createRandomCircuit({n},{depth},{seed}) on a {n}-qubit fp64 state vector "
+            f"({16 * (1 << n_local) / 2**30:.0f} GiB per GPU)")
+
+
 def reference_arm(args):
-    """`--impl reference`: the reference's own CPU path (CPUSimulator) on the host cores; rank 0 only."""
+    """`--impl reference`: the reference's own CPU path (CPUSimulator::run, reference src/Simulator.cu:208-212) on the host
+    cores; rank 0 only.  At N = 1 it runs the REAL workload - createRandomCircuit(30, depth, seed) on a 16 GiB host state
+    vector - not an extrapolation: one circuit takes ~50 s on one core, so min(steps, 2) runs are timed and no warm-up run
+    is spent at full size (a CPU loop over a freshly allocated vector has nothing to warm up; the 26-qubit cross-check
+    below runs first and loads the code).  For N > 1 the 30 + log2(N)-qubit state (>= 32 GiB, up to 128 GiB) does not
+    fit the host, and the metric's unit is 30-qubit equivalents (gates * 2^(n-30) / s), so the same 30-qubit run is the
+    sample and the line says so."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     n_total = args.local_qubits + int(math.log2(args.gpus))
-    n_cpu = min(args.cpu_qubits, n_total)
+    n_run = min(n_total, args.ref_qubits)
+    # cross-check sample (the round-1 figure): same generator at a small size, scaled by 2^(n-30)
+    n_x = min(args.cpu_qubits, n_run)
+    t_x, kind, ng_x = cpu_reference_run(n_x, args.depth, args.seed)
+    runs = max(1, min(args.steps, args.ref_runs))
     times = []
-    kind, ng = "reference", args.depth
-    for i in range(args.warmup + args.steps):
-        t, kind, ng = cpu_reference_run(n_cpu, args.depth, args.seed)
-        if i >= args.warmup:
-            times.append(t)
+    ng = args.depth
+    for _ in range(runs):
+        t, kind, ng = cpu_reference_run(n_run, args.depth, args.seed)
+        times.append(t)
     sec = sum(times) / len(times)
-    # the bounded sample runs the same generator at n_cpu qubits; per-gate cost scales as 2^n (measured, BASELINE.md §2)
-    value = ng * 2.0 ** (n_cpu - 30) / sec
+    value = ng * 2.0 ** (n_run - 30) / sec
+    exact = (n_run == n_total)
+    sample = (f"CPUSimulator::run on createRandomCircuit({n_run},{args.depth},{args.seed}), the full workload, {runs} timed run(s) of "
+              f"{sec:.1f} s each, no warm-up run at this size" if exact else
+              f"CPUSimulator::run on createRandomCircuit({n_run},{args.depth},{args.seed}) ({runs} timed run(s) of {sec:.1f} s): the "
+              f"{n_total}-qubit state does not fit the host; the unit is 30-qubit equivalents so this is the per-GPU-share sample")
+    sample += f"; 1 of {os.cpu_count()} host cores (the reference CPU path is single-threaded)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"createRandomCircuit({n_total},{args.depth},{args.seed}) fp64 state vector",
-                   "sample": f"same generator at {n_cpu} qubits, scaled by 2^({n_cpu}-30)", "gates": ng},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
-                         "sample": f"CPUSimulator::run on createRandomCircuit({n_cpu},{args.depth},{args.seed}), "
-                                   f"{sec:.2f} s per run, 1 of {os.cpu_count()} host cores (reference path is single-threaded)"},
+        "config": {"workload": workload_name(n_total, args.depth, args.seed, args.local_qubits), "gates": ng, "qubits": n_total,
+                   "local_qubits": args.local_qubits, "reference_qubits_run": n_run, "reference_runs_timed": runs,
+                   "reference_warmup_runs_at_full_size": 0, "same_workload_as_gpu_arm": exact,
+                   "cross_check": {"qubits": n_x, "seconds": t_x, "value_scaled_by_2^(n-30)": ng_x * 2.0 ** (n_x - 30) / t_x}},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def sharded_parity_check(exchange, rank, world):
+    """N > 1 only, before anything is timed: the sharded engine against the CPU oracle on circuits that REALLY exchange
+    (24 and 22 qubits forced over `world` shards; identity layout so the gate on the top qubit needs a global<->local swap,
+    and a 300-gate circuit that targets every qubit), once with the exchange fused into the preceding pass and once as
+    a separate swap kernel; amplitudes <= 1e-10, sampling bit-identical to the reference's logical-order sequential CDF
+    after the exchanges, marginals, and one measurement.  Any mismatch ends the run with a non-zero exit code."""
+    import numpy as np
+    import cuda_quantum_simulator_b200 as q
+    import helpers as H
+    from cuda_quantum_simulator_b200.sharded import ShardedSimulator
+    out = {"max_abs_err": 0.0, "exchanges": 0, "fused": 0, "cases": [], "sampling_bit_identical": True,
+           "marginal_max_err": 0.0, "measure_ok": True, "tolerance": 1e-10}
+    cases = (("createRandomCircuit(24,40,7) identity layout", 24, 40, 7, False),
+             ("createRandomCircuit(22,300,11) free layout", 22, 300, 11, True))
+    for mode in ("fused", "separate"):
+        if mode == "separate":
+            os.environ["QSIM_NO_FUSED_EXCHANGE"] = "1"
+        try:
+            for label, n, depth, seed, free_layout in cases:
+                c = q.create_random_circuit(n, depth, seed)
+                sim = ShardedSimulator(n, exchange=exchange)
+                sim._pristine = free_layout
+                cp = sim.compile(c)
+                f0 = sim.engine.fused_exchanges
+                sim.execute(cp)
+                got = sim.get_state_vector()
+                want = H.oracle_run(n, c.gates)
+                err = float(np.max(np.abs(got - want)))
+                u = np.concatenate([np.random.default_rng(seed).random(256), [0.0, 0.5]])
+                samp_ok = bool(np.array_equal(sim.sample(uniforms=u), H.oracle_sample(H.oracle_probs(got), u)))
+                qs = [0, n // 2, n - 1, n - 2]
+                idx = np.arange(1 << n)
+                oc = np.zeros(1 << n, np.int64)
+                for i, qb in enumerate(qs):
+                    oc |= ((idx >> qb) & 1) << i
+                merr = float(np.max(np.abs(sim.marginal(qs) - np.bincount(oc, weights=np.abs(want) ** 2, minlength=16))))
+                # measurement of the top qubit's index bit (Simulator::measureQubit(0) addresses bit n-1, SURVEY 0.1)
+                pr = np.abs(got) ** 2
+                p0 = float(np.sum(pr[((idx >> (n - 1)) & 1) == 0]))
+                r = 0.25 if abs(p0 - 0.25) > 1e-6 else 0.6
+                meas_ok = True
+                if min(p0, 1 - p0) > 1e-9:
+                    res = sim.measure_qubit(0, r)
+                    keep = ((idx >> (n - 1)) & 1) == res
+                    want_c = np.where(keep, got, 0) / np.sqrt(p0 if res == 0 else 1 - p0)
+                    meas_ok = res == (0 if r < p0 else 1) and float(np.max(np.abs(sim.get_state_vector() - want_c))) < 1e-10
+                out["cases"].append({"circuit": label, "mode": mode, "exchange": sim.engine.exchange, "swaps": cp.n_swaps,
+                                     "fused_into_a_pass": sim.engine.fused_exchanges - f0, "max_abs_err": err})
+                out["max_abs_err"] = max(out["max_abs_err"], err)
+                out["exchanges"] += cp.n_swaps
+                out["fused"] += sim.engine.fused_exchanges - f0
+                out["sampling_bit_identical"] &= samp_ok
+                out["marginal_max_err"] = max(out["marginal_max_err"], merr)
+                out["measure_ok"] &= bool(meas_ok)
+                sim.release(cp)
+                sim.close()
+        finally:
+            os.environ.pop("QSIM_NO_FUSED_EXCHANGE", None)
+    out["passed"] = bool(out["max_abs_err"] < 1e-10 and out["sampling_bit_identical"] and out["marginal_max_err"] < 1e-12
+                         and out["measure_ok"] and out["exchanges"] > 0)
+    return out
 
 
 def main():
@@ -192,9 +278,26 @@ def main():
         runner = sim
     else:
         from cuda_quantum_simulator_b200.sharded import ShardedSimulator
+        parity = None
+        if not args.no_parity_check:
+            parity = sharded_parity_check(args.exchange, rank, world)
+            flag = torch.tensor([0.0 if parity["passed"] else 1.0], device="cuda")
+            dist.all_reduce(flag)
+            if flag.item() != 0:
+                if rank == 0:
+                    print(json.dumps({"parity_check": parity, "error": "sharded parity check failed"}), flush=True)
+                dist.destroy_process_group()
+                sys.exit(1)
         runner = ShardedSimulator(n, exchange=args.exchange)
-        plan = runner.compile(circuit)
-        step = lambda: runner.execute(plan)
+        # one plan per step: a run may leave a different qubit layout / X frame behind than it started from, and a plan is
+        # only valid for the layout it was compiled against (plans are shared when the layout repeats)
+        plans = runner.compile_sequence(circuit, 1 + args.warmup + args.steps)
+        plan = plans[0]
+        step_no = [0]
+
+        def step():
+            runner.execute(plans[step_no[0]])
+            step_no[0] += 1
 
         def sync_all():
             torch.cuda.synchronize()
@@ -276,14 +379,20 @@ def main():
             d_info = {"passes": dprog.n_passes, "global_qubit_swaps": 0}
         else:
             runner.reset()
-            dplan = runner.compile(dcirc)
+            dplans = runner.compile_sequence(dcirc, 4)
             f0 = runner.engine.fused_exchanges
-            dstep = lambda: runner.execute(dplan)
-            d_info = {"passes": dplan.n_passes, "global_qubit_swaps": dplan.n_swaps}
+            d_no = [0]
+
+            def dstep():
+                runner.execute(dplans[d_no[0]])
+                d_no[0] += 1
+            d_info = {"passes_per_step": [p_.n_passes for p_ in dplans[1:]],
+                      "global_qubit_swaps_per_step": [p_.n_swaps for p_ in dplans[1:]]}
         dstep()
+        f1 = runner.engine.fused_exchanges if world > 1 else 0
         d_ms = timed(dstep, 3) / 3
         if world > 1:
-            d_info["exchanges_fused_into_a_pass"] = (runner.engine.fused_exchanges - f0) // 4
+            d_info["exchanges_fused_into_a_pass_in_the_timed_steps"] = runner.engine.fused_exchanges - f1
         dense = dict(workload=f"createRandomCircuit({n},200,{args.seed})", gates=dcirc.get_gate_count(), ms_per_step=d_ms,
                      value=dcirc.get_gate_count() * 2.0 ** (n - 30) / (d_ms * 1e-3), **d_info)
 
@@ -308,6 +417,79 @@ def main():
                   "frac": half_bytes / float(sw_ms.item()) / 1e6 / 770.0,
                   "peak_source": "measured peer copy per direction per GPU (B200_PROFILING.md)"}
 
+    # ---- the same circuit with the IDENTITY layout: the gate on the top qubit forces a global<->local exchange -----------
+    forced = None
+    if world > 1:
+        def forced_run(circ, sim_, k):
+            """k timed steps of `circ` from the identity layout (no free initial layout): per-step plans, device time."""
+            sim_.reset()
+            sim_._pristine = False                       # keeps compile() from choosing a layout: identity
+            seq = sim_.compile_sequence(circ, 1 + k)
+            no = [0]
+
+            def st():
+                sim_.execute(seq[no[0]])
+                no[0] += 1
+            f_a = sim_.engine.fused_exchanges
+            st()                                         # from |0..0> (basis-state input), untimed
+            f_b = sim_.engine.fused_exchanges
+            ms = timed(st, k) / k
+            info = {"ms_per_step": ms, "passes_per_step": [p_.n_passes for p_ in seq[1:]],
+                    "swaps_per_step": [p_.n_swaps for p_ in seq[1:]],
+                    "swaps_first_step_from_zero_state": seq[0].n_swaps,
+                    "fused_into_a_pass": sim_.engine.fused_exchanges - f_b,
+                    "fused_first_step": f_b - f_a}
+            return info, seq
+        k_f = 4
+        f_info, seq = forced_run(circuit, runner, k_f)
+        pass_ms_1 = pass_ms / max(passes_timed, 1)
+        link_ms = nvlink["ms"]
+        ideal = sum(max(p_.n_passes * pass_ms_1, p_.n_swaps * link_ms) for p_ in seq[1:]) / k_f
+        forced = dict(workload=f"createRandomCircuit({n},{args.depth},{args.seed}), identity qubit layout (QSIM_NO_LAYOUT semantics)",
+                      exchange=runner.engine.exchange, pass_ms=pass_ms_1, link_ms=link_ms,
+                      ideal_ms_per_step=ideal, overlap_eff=ideal / f_info["ms_per_step"],
+                      value=n_gates * 2.0 ** (n - 30) / (f_info["ms_per_step"] * 1e-3),
+                      what="overlap_eff = mean over steps of max(passes * pass_ms, swaps * link_ms) / measured ms per step; pass_ms = "
+                           "the headline pass, link_ms = the nvlink leg above", **f_info)
+
+    # ---- BASELINE config C4 for real: createRandomCircuit(36,20,42) over 8 GPUs, 128 GiB shards --------------------------
+    c4 = None
+    if world == 8 and n_local == 30 and not args.no_c4:
+        sync_all()
+        runner.close()          # drops the 30-qubit shards (and their second buffers) on every rank
+        sync_all()
+        torch.cuda.empty_cache()
+        n4 = 36
+        c4circ = q.create_random_circuit(n4, 20, 42)
+        free_b, _tot = torch.cuda.mem_get_info()
+        fits = torch.tensor([1.0 if free_b > (128 << 30) + (6 << 30) else 0.0], device="cuda")
+        dist.all_reduce(fits, op=dist.ReduceOp.MIN)
+    if world == 8 and n_local == 30 and not args.no_c4 and fits.item() == 0:
+        c4 = {"skipped": f"a 128 GiB shard does not fit next to what is resident (free on rank 0: {free_b / 2**30:.0f} GiB)"}
+    elif world == 8 and n_local == 30 and not args.no_c4:
+        r4 = ShardedSimulator(n4, exchange=args.exchange)
+        c4 = {"workload": "createRandomCircuit(36,20,42), 2^33 amplitudes (128 GiB) per GPU", "gates": c4circ.get_gate_count(),
+              "second_buffer_for_fused_exchange": len(r4.engine._bufs) > 1, "exchange": r4.engine.exchange}
+        # (a) layout chosen from |0..0>
+        seq = r4.compile_sequence(c4circ, 3)
+        no = [0]
+
+        def st4():
+            r4.execute(seq[no[0]])
+            no[0] += 1
+        st4()
+        ms = timed(st4, 2) / 2
+        c4["chosen_layout"] = {"ms_per_circuit": ms, "passes": seq[1].n_passes, "swaps_per_step": [p_.n_swaps for p_ in seq[1:]],
+                               "gates_per_s": c4circ.get_gate_count() / (ms * 1e-3),
+                               "hbm_gbs_per_gpu": seq[1].n_passes * 2 * 16 * (1 << 33) / (ms * 1e-3) / 1e9}
+        tot = r4.get_total_probability()
+        c4["total_probability"] = tot
+        # (b) identity layout: H(35) needs the 64 GiB-each-way exchange
+        f_info, seq = forced_run(c4circ, r4, 2)
+        c4["identity_layout"] = f_info
+        c4["identity_layout"]["total_probability"] = r4.get_total_probability()
+        r4.close()
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -328,8 +510,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"createRandomCircuit({n},{args.depth},{args.seed}) on a {n}-qubit fp64 state vector "
-                               f"({16 * (1 << n_local) / 2**30:.0f} GiB per GPU)",
+        "config": {"workload": workload_name(n, args.depth, args.seed, n_local),
                    "gates": n_gates, "passes": n_passes, "global_qubit_swaps": n_swaps, "qubits": n,
                    "local_qubits": n_local,
                    "parallelism": f"shard {n_global} qubit(s) over {world} GPU(s); from |0..0> the layout puts qubits that are "
@@ -353,6 +534,11 @@ def main():
     }
     if nvlink:
         line["nvlink"] = nvlink
+    if world > 1:
+        line["parity_check"] = parity
+        line["forced_exchange"] = forced
+    if c4:
+        line["c4"] = c4
     if dense:
         line["dense_variant"] = dense
     if not args.no_cpu_baseline:

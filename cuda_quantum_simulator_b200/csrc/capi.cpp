@@ -297,6 +297,10 @@ qsim_status_t qsim_sim_run(qsim_sim_t* s, int circuit_qubits, const qsim_gate_t*
         b200::Program prog;
         b200::CompileOptions opt = b200::default_options();
         opt.n_global = s->n_global;
+        // no X frame on a shard through this entry point: an X on a rank qubit would be absorbed into the frame and left in
+        // Program::global_xor, which only a sharded driver (qsim_program_compile_ex) carries between calls; without the
+        // frame it is rejected by the compiler ("must be remapped") instead of being dropped
+        opt.defer_x = false;
         std::string err;
         if (!b200::compile(s->n_total, gates, ng, opt, prog, &err)) throw std::runtime_error(err);
         s->sim->state().engine().execute(prog, s->sim->state().devicePtr(), s->hi_bits());
@@ -312,6 +316,7 @@ qsim_status_t qsim_sim_apply_gate(qsim_sim_t* s, const qsim_gate_t* g) {
             b200::Program prog;
             b200::CompileOptions opt = b200::default_options();
             opt.n_global = s->n_global;
+            opt.defer_x = false;   // see qsim_sim_run
             std::string err;
             if (!b200::compile(s->n_total, g, 1, opt, prog, &err)) throw std::runtime_error(err);
             s->sim->state().engine().execute(prog, s->sim->state().devicePtr(), s->hi_bits());

@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace qsim {
 namespace b200 {
@@ -826,6 +827,20 @@ bool encode_tensor_map(const PassParams& prm, void* base, CUtensorMap* out) {
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// The dynamic shared-memory opt-in is a per-device (per-context) function attribute: set it once on every device this
+// process launches on.
+cudaError_t ensure_smem_optin() {
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev)) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(fused_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
+}
+
 }  // namespace
 
 cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t stream) {
@@ -843,13 +858,7 @@ cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t s
                                       !encode_tensor_map(params, params.dst_send, &tmap_send)))
             return cudaErrorInvalidValue;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e =
-            cudaFuncSetAttribute(fused_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = ensure_smem_optin()) return e;
     const size_t smem = pass_smem_bytes(params.pd, params.stages);
     if (params.stages < 1 || smem > (size_t)kMaxDynamicSmem) return cudaErrorInvalidValue;
     uint64_t grid = params.n_tiles < (uint64_t)num_sms ? params.n_tiles : (uint64_t)num_sms;

@@ -97,7 +97,7 @@ __global__ void collapse_kernel(cuDoubleComplex* __restrict__ state, uint64_t n,
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         cuDoubleComplex a = state[i];
-        if ((int)((i >> bit) & 1) != outcome) a = make_cuDoubleComplex(0.0, 0.0);
+        if (bit >= 0 && (int)((i >> bit) & 1) != outcome) a = make_cuDoubleComplex(0.0, 0.0);   // bit < 0: scale everything
         else a = make_cuDoubleComplex(__dmul_rn(a.x, scale), __dmul_rn(a.y, scale));
         state[i] = a;
     }

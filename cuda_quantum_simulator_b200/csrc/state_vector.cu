@@ -47,7 +47,8 @@ StateVector::~StateVector() { deallocate(); }
 
 StateVector::StateVector(StateVector&& o) noexcept
     : num_qubits_(o.num_qubits_), size_(o.size_), d_state_(o.d_state_), owns_(o.owns_), pending_basis_(o.pending_basis_),
-      pending_idx_(o.pending_idx_), engine_(std::move(o.engine_)) {
+      pending_idx_(o.pending_idx_), lazy_external_(o.lazy_external_), engine_(std::move(o.engine_)),
+      prepared_cdf_(std::move(o.prepared_cdf_)) {
     o.d_state_ = nullptr;
     o.pending_basis_ = false;
     o.size_ = 0;
@@ -56,6 +57,7 @@ StateVector::StateVector(StateVector&& o) noexcept
 
 StateVector& StateVector::operator=(StateVector&& o) noexcept {
     if (this != &o) {
+        prepared_cdf_.reset();   // it references the engine and the amplitudes that are about to go
         deallocate();
         num_qubits_ = o.num_qubits_;
         size_ = o.size_;
@@ -63,7 +65,9 @@ StateVector& StateVector::operator=(StateVector&& o) noexcept {
         owns_ = o.owns_;
         pending_basis_ = o.pending_basis_;
         pending_idx_ = o.pending_idx_;
+        lazy_external_ = o.lazy_external_;
         engine_ = std::move(o.engine_);
+        prepared_cdf_ = std::move(o.prepared_cdf_);
         o.d_state_ = nullptr;
         o.pending_basis_ = false;
         o.size_ = 0;

@@ -197,9 +197,13 @@ class CudaShardEngine:
                     self._bufs.append(torch.empty(1 << self.nl, dtype=torch.complex128, device="cuda"))
                 self._open_peers()
                 self.exchange = "p2p"
-            except Exception:
+            except Exception as exc:
                 if exchange == "p2p":
                     raise
+                import warnings
+                warnings.warn(f"qsim_b200 rank {rank}: CUDA-IPC peer memory unavailable ({type(exc).__name__}: {exc}); "
+                              "global-qubit swaps fall back to NCCL send/recv through bounce buffers (about a third of the "
+                              "peer-to-peer bandwidth)", RuntimeWarning)
                 self.exchange = "nccl"
                 self._bufs = [self.state]
         elif world > 1:
@@ -319,6 +323,10 @@ class CudaShardEngine:
         _lib.check(_lib.lib().qsim_shard_partial_probability(self._h, bit, byref(v)))
         return v.value
 
+    def collapse(self, bit: int, outcome: int, scale: float):
+        """Zero the amplitudes whose index bit `bit` != outcome and scale the rest (bit < 0: scale everything)."""
+        _lib.check(_lib.lib().qsim_shard_collapse(self._h, int(bit), int(outcome), c_double(scale)))
+
     def shard_sample(self, c_init: float, first: bool, uniforms: np.ndarray):
         u = np.ascontiguousarray(uniforms, np.float64)
         out = np.empty(len(u), np.int64)
@@ -359,6 +367,11 @@ class CudaShardEngine:
         for b in self._peer_base:
             _lib.lib().qsim_ipc_close_handle(b)
         self._peer_base = []
+        # drop the device buffers (peers have closed their mappings by the time they allocate again: close() is collective
+        # in practice, every rank calls it at the same point)
+        self.state = None
+        self._bufs = []
+        self._bounce = None
 
 
 @dataclass
@@ -369,6 +382,9 @@ class CompiledPlan:
     n_passes: int
     n_ops: int
     n_swaps: int
+    perm_before: List[int] = field(default_factory=list)   # the layout and frame the plan was compiled against
+    frame_before: int = 0
+    from_pristine: bool = False    # compiled for |0...0> with a freely chosen layout: valid on any pristine state
 
 
 class ShardedSimulator:
@@ -389,6 +405,7 @@ class ShardedSimulator:
         self.perm = list(range(self.n))      # logical qubit -> physical position
         self.frame = 0                       # pending X mask over physical positions (global bits only, between runs)
         self._pristine = True                # the state is |0...0>: the qubit layout is still free to choose
+        self._order_preserving = True        # stored index order == logical index order on the support (see sample)
 
     @property
     def local(self):
@@ -400,6 +417,7 @@ class ShardedSimulator:
         self.perm = list(range(self.n))
         self.frame = 0
         self._pristine = True
+        self._order_preserving = True
 
     def set_local_state(self, amps: np.ndarray):
         """Overwrite this rank's shard (stored layout); the qubit layout is fixed from here on."""
@@ -410,10 +428,14 @@ class ShardedSimulator:
         """Plan + compile against the CURRENT qubit permutation and X frame."""
         if circuit.get_num_qubits() != self.n:
             raise _lib.InvalidArgument("Circuit qubit count doesn't match simulator")
+        start_perm = list(self.perm)
+        chose = False
         if self._pristine and self.ng > 0 and os.environ.get("QSIM_NO_LAYOUT") is None:
-            self.perm = choose_initial_layout(self.n, self.ng, circuit.gates)
-        plan = plan_circuit(self.n, self.ng, circuit.gates, self.perm)
+            start_perm = choose_initial_layout(self.n, self.ng, circuit.gates)   # carried by the plan, applied by execute()
+            chose = True
+        plan = plan_circuit(self.n, self.ng, circuit.gates, start_perm)
         frame = self.frame
+        frame_before = frame
         programs, n_passes, n_ops = [], 0, 0
         for st in plan.steps:
             if st.kind == "gates":
@@ -427,9 +449,19 @@ class ShardedSimulator:
                 g, l = st.global_qubit, st.local_qubit      # the pending X (if any) travels with the qubit
                 bg, bl = (frame >> g) & 1, (frame >> l) & 1
                 frame = (frame & ~((1 << g) | (1 << l))) | (bl << g) | (bg << l)
-        return CompiledPlan(plan, programs, frame, n_passes, n_ops, plan.n_swaps)
+        return CompiledPlan(plan, programs, frame, n_passes, n_ops, plan.n_swaps, perm_before=start_perm,
+                            frame_before=frame_before, from_pristine=chose)
 
     def execute(self, cp: CompiledPlan):
+        """Runs a compiled plan.  A plan is only valid for the qubit layout and X frame it was compiled against: on the
+        state it was compiled for (same permutation and frame) or, for a plan compiled from |0...0> with its own layout,
+        on any pristine state.  Re-executing a plan that ends in a different layout than it starts from needs a reset()
+        (or a re-compile) in between and is refused here."""
+        same_layout = list(cp.perm_before) == list(self.perm) and cp.frame_before == self.frame
+        if not same_layout and not (cp.from_pristine and self._pristine and cp.frame_before == self.frame):
+            raise _lib.InvalidArgument("plan compiled against a different qubit layout / X frame than the state now has "
+                                       "(a plan that changes the layout cannot be executed twice in a row): reset(), or "
+                                       "compile it against the current state (compile / compile_sequence)")
         steps, progs = cp.plan.steps, cp.programs
         fuse = getattr(self.engine, "run_program_then_swap", None)
         i = 0
@@ -447,7 +479,27 @@ class ShardedSimulator:
             i += 1
         self.perm = list(cp.plan.perm)
         self.frame = cp.frame_after
+        # a layout chosen for |0...0> keeps the reference's index order on the support as long as no exchange has happened
+        # (the parked qubits have one value in every non-zero amplitude and the others keep their relative order)
+        self._order_preserving = (self._order_preserving if not self._pristine else True) and cp.n_swaps == 0
         self._pristine = False
+
+    def compile_sequence(self, circuit: Circuit, k: int) -> List[CompiledPlan]:
+        """Plans for k consecutive runs of `circuit` starting from the current state: run i is compiled against the layout
+        and X frame run i-1 leaves behind (plans are shared when the layout repeats).  Nothing is executed."""
+        saved = (list(self.perm), self.frame, self._pristine)
+        cache, out = {}, []
+        try:
+            for _ in range(k):
+                key = (tuple(self.perm), self.frame, self._pristine)
+                cp = cache.get(key)
+                if cp is None:
+                    cp = cache[key] = self.compile(circuit)
+                out.append(cp)
+                self.perm, self.frame, self._pristine = list(cp.plan.perm), cp.frame_after, False
+        finally:
+            self.perm, self.frame, self._pristine = saved
+        return out
 
     def release(self, cp: CompiledPlan):
         for h in cp.programs:
@@ -544,13 +596,103 @@ class ShardedSimulator:
             np.add.at(out, spread | base, share)
         return out
 
+    def restore_identity_layout(self):
+        """Moves the amplitudes back to the identity qubit layout (logical qubit q at index bit q): global<->local
+        exchanges for the rank bits, then ONE local pass of SWAP gates (pure index permutations: the compiler folds them
+        into the pass's load / store addressing).  The logical state does not change; an X frame on the rank bits may
+        remain (it only relabels which rank holds which shard, see _logical_rank_order).  Needed where the reference's
+        semantics depend on the index ORDER: the sequential CDF of sample() (reference src/Simulator.cu:164-185)."""
+        n, nl = self.n, self.nl
+        perm, frame = list(self.perm), self.frame
+
+        def swap(g, l):
+            nonlocal frame
+            self.engine.swap(g, l)
+            inv = {perm[q]: q for q in range(n)}
+            qg, ql = inv[g], inv[l]
+            perm[qg], perm[ql] = l, g
+            bg, bl = (frame >> g) & 1, (frame >> l) & 1
+            frame = (frame & ~((1 << g) | (1 << l))) | (bl << g) | (bg << l)
+
+        for g in range(nl, n):
+            if perm[g] == g:
+                continue
+            if perm[g] >= nl:              # sits in another rank bit: bring it down to a local position first
+                swap(perm[g], nl - 1)
+            swap(g, perm[g])
+        # local part: sort the positions with SWAP gates on PHYSICAL qubits (cycle sort), plus any X frame that the
+        # exchanges moved onto local bits — one program, applied by its addressing
+        inv = {perm[q]: q for q in range(n)}
+        recs = []
+        for pos in range(nl):
+            while inv[pos] != pos:
+                q = inv[pos]                                   # belongs at position q
+                recs.append((15, pos, q, -1, 0.0))             # SWAP(pos, q)
+                inv[pos], inv[q] = inv[q], q
+        if recs or (frame & ((1 << nl) - 1)):
+            h, info = self.engine.compile_gates(np.array(recs, dtype=GATE_DTYPE) if recs else np.zeros(0, GATE_DTYPE), frame)
+            try:
+                self.engine.run_program(h)
+            finally:
+                self.engine.free_program(h)
+            frame = info["global_xor"] << nl
+        self.perm = list(range(n))
+        self.frame = frame
+        self._order_preserving = True
+        self._pristine = False
+
+    def measure_bit(self, bit: int, uniform: float):
+        """Measures LOGICAL index bit `bit` with the caller's uniform draw r: outcome 0 iff r < P(bit = 0)
+        (reference src/StateVector.cu:284-313), then collapses and renormalises every shard.  Returns (outcome, p0).
+        P0 is the sum of the shards' partial sums in frame-resolved rank order."""
+        if not 0 <= bit < self.n:
+            raise _lib.InvalidArgument("Qubit index out of range")
+        pos = self.perm[bit]
+        fx = self.frame >> self.nl
+        if pos < self.nl:
+            part = self.engine.partial_probability(pos)
+            if (self.frame >> pos) & 1:        # pending X on that local bit (only between the steps of a plan; kept for safety)
+                part = self.engine.partial_probability(-1) - part
+        else:
+            mine = ((self.rank ^ fx) >> (pos - self.nl)) & 1
+            part = self.engine.partial_probability(-1) if mine == 0 else 0.0
+        parts = self._allgather(part)                          # indexed by physical rank
+        p0 = 0.0
+        for r in range(self.world):                            # frame-resolved order, fixed on every rank
+            p0 += parts[r ^ fx]
+        outcome = 0 if uniform < p0 else 1
+        prob = p0 if outcome == 0 else 1.0 - p0
+        if prob <= 0.0:
+            raise _lib.QsimError("Measurement outcome has zero probability")
+        scale = 1.0 / np.sqrt(prob)
+        if pos < self.nl:
+            self.engine.collapse(pos, outcome ^ ((self.frame >> pos) & 1), scale)
+        else:
+            mine = ((self.rank ^ fx) >> (pos - self.nl)) & 1
+            self.engine.collapse(-1, 0, scale if mine == outcome else 0.0)
+        self._pristine = False
+        return outcome, p0
+
+    def measure_qubit(self, qubit: int, uniform: Optional[float] = None) -> int:
+        """Simulator::measureQubit: measures index bit n-1-qubit (the reference's big-endian quirk, src/StateVector.cu:87-89)."""
+        if not 0 <= qubit < self.n:
+            raise _lib.InvalidArgument("Qubit index out of range")
+        r = float(np.random.random()) if uniform is None else float(uniform)
+        if self.world > 1 and uniform is None:                 # every rank must use the same draw
+            r = self._allgather(r)[0]
+        return self.measure_bit(self.n - 1 - qubit, r)[0]
+
     def sample(self, n_shots: int = 0, uniforms: Optional[np.ndarray] = None, seed: Optional[int] = None) -> np.ndarray:
-        """Bit-exact distributed sampling: the sequential CDF runs through the shards in stored-index order (the
-        order a single device holding the same stored layout would use); returns LOGICAL basis-state indices."""
+        """Bit-exact distributed sampling in the reference's LOGICAL index order (src/Simulator.cu:164-185: inclusive
+        sequential prefix sum over the basis states, lower_bound per shot): if exchanges have permuted the stored
+        layout, the identity layout is restored first (restore_identity_layout), then the sequential CDF is chained
+        through the shards in rank order.  Returns logical basis-state indices, identical on every rank."""
         if uniforms is None:
             rs = np.random.RandomState(seed)
             uniforms = rs.random_sample(n_shots)
         u = np.ascontiguousarray(uniforms, np.float64)
+        if not self._order_preserving and self.perm != list(range(self.n)):
+            self.restore_identity_layout()
         fx = self.frame >> self.nl
         my_pos = self.rank ^ fx                       # position of my shard in the frame-resolved order
         if self.world > 1 and hasattr(self.engine, "cdf_prepare"):

@@ -111,7 +111,9 @@ QSIM_API size_t qsim_program_describe(const qsim_program_t* p, char* buf, size_t
 
 /* ---- Simulator / StateVector (reference include/Simulator.hpp:53-85, include/StateVector.cuh:66-124) */
 QSIM_API qsim_status_t qsim_sim_create(int num_qubits, qsim_sim_t** out);            /* Simulator(int) */
-/* Same, on caller-owned device memory of 16 << num_qubits bytes (e.g. a torch tensor). */
+/* A simulator on caller-owned device memory of 16 << num_qubits bytes (e.g. a torch tensor).  Unlike Simulator(int)
+ * the memory is ADOPTED AS IS - its contents are the state, nothing is initialised (so an existing state vector can be
+ * handed over); call qsim_sim_reset for |0...0>. */
 QSIM_API qsim_status_t qsim_sim_create_external(int num_qubits, void* device_state, qsim_sim_t** out);
 QSIM_API void qsim_sim_destroy(qsim_sim_t* s);
 QSIM_API qsim_status_t qsim_sim_set_stream(qsim_sim_t* s, void* cuda_stream);
@@ -197,6 +199,9 @@ QSIM_API qsim_status_t qsim_ipc_close_handle(void* base_ptr);
 /* Partial sums for distributed read-out: this shard's sum of |a|^2 (optionally restricted to
  * index bit `bit` == 0; bit < 0 means no restriction). */
 QSIM_API qsim_status_t qsim_shard_partial_probability(const qsim_sim_t* s, int bit, double* out);
+/* Collapse after a distributed measurement: amplitudes whose index bit `bit` != outcome become 0, the others are
+ * multiplied by `scale` (1/sqrt(P(outcome)), reference src/StateVector.cu:110-124).  bit < 0: every amplitude is scaled
+ * (the measured qubit is a rank bit: scale = 1/sqrt(P) on the ranks that hold the outcome, 0 on the others). */
 QSIM_API qsim_status_t qsim_shard_collapse(qsim_sim_t* s, int bit, int outcome, double scale);
 /* Distributed bit-exact sampling: the sequential CDF of this shard continued from c_init (the exact
  * running sum at the end of the previous shard, in logical rank order).  out[i] = local index of the

@@ -186,6 +186,23 @@ def bench_c1_gates(n=20):
     return gates(lst)
 
 
+def qft_style_circuit(n, window=None):
+    """BASELINE config C3: createGHZCircuit(n) (reference src/Circuit.cpp:240-250) followed by QFT-style
+    layers h(q); crz(j, q, pi/2^(j-q)) for j > q (optionally windowed), then rz(q, theta_q) with theta_q drawn from
+    std::mt19937(42) / uniform_real_distribution(0, 2 pi).  Returns a package Circuit."""
+    import cuda_quantum_simulator_b200 as q
+    c = q.create_ghz_circuit(n)
+    for qb in range(n):
+        c.h(qb)
+        hi = n if window is None else min(n, qb + 1 + window)
+        for j in range(qb + 1, hi):
+            c.crz(j, qb, float(np.pi / 2 ** (j - qb)))
+    theta = mt19937_uniforms(42, n) * 2 * np.pi
+    for qb in range(n):
+        c.rz(qb, float(theta[qb]))
+    return c
+
+
 def load_known_answers():
     with open(os.path.join(GOLDEN, "known_answers.json")) as f:
         return json.load(f)

@@ -227,3 +227,58 @@ def test_30q_properties():
             inv._add(t, int(g["q0"]))
     sim.run(inv)
     assert abs(sim.get_probabilities(0, 1)[0] - 1.0) < 1e-10
+
+
+# ---- BASELINE config C3: GHZ + QFT-style H / CRZ / Rz layers -------------------------------------------
+
+@pytest.mark.parametrize("n,window", [(20, None), (22, None), (24, None), (22, 8)])
+def test_config_c3_qft_style_against_oracle(n, window):
+    """The C3 generator at sizes the oracle finishes in seconds; the CRZ ladders must take the fused-diagonal path
+    (OP_PHASE: one multiplicative phase polynomial per run) and still match the gate-by-gate oracle."""
+    c = H.qft_style_circuit(n, window)
+    prog = q.CompiledCircuit(c)
+    assert "PHASE" in prog.describe(), "the CRZ/Rz runs were expected to fuse into OP_PHASE ops"
+    assert prog.n_passes < c.get_gate_count() // 8
+    sim = q.Simulator(n)
+    sim.execute(prog)
+    got = sim.get_state_vector()
+    want = H.oracle_run(n, c.gates)
+    assert np.max(np.abs(got - want)) < TOL
+    # the uncompiled entry point (run from host gate records) takes the same path
+    sim2 = q.Simulator(n)
+    sim2.run(c)
+    assert np.max(np.abs(sim2.get_state_vector() - want)) < TOL
+    # and sampling on that state is bit-identical to the sequential CDF of the reference (src/Simulator.cu:164-185)
+    u = np.random.default_rng(n).random(512)
+    assert np.array_equal(sim.sample(0, uniforms=u), H.oracle_sample(H.oracle_probs(got), u))
+
+
+def test_config_c3_30q_properties():
+    """C3 at 30 qubits (16 GiB) through size-independent properties: analytic GHZ amplitudes, unit norm after the
+    QFT-style layers, and the inverse layers bring the GHZ state back."""
+    n = 30
+    sim = q.Simulator(n)
+    sim.run(q.create_ghz_circuit(n))
+    last = (1 << n) - 1
+    r = 1.0 / np.sqrt(2.0)
+    assert abs(sim.get_probabilities(0, 1)[0] - 0.5) < 1e-12 and abs(sim.get_probabilities(last, 1)[0] - 0.5) < 1e-12
+    assert abs(sim.get_total_probability() - 1.0) < 1e-12
+    full = H.qft_style_circuit(n)
+    layers = full.gates[n:]                                  # everything after the GHZ ladder
+    sim.run(q.Circuit(n).extend(layers))
+    assert abs(sim.get_total_probability() - 1.0) < 1e-10
+    inv = q.Circuit(n)
+    for g in layers[::-1]:
+        t = int(g["type"])
+        if t == 3:
+            inv.h(int(g["q0"]))
+        elif t == 10:
+            inv.rz(int(g["q0"]), -float(g["param"]))
+        else:
+            assert t == 14
+            inv.crz(int(g["q0"]), int(g["q1"]), -float(g["param"]))
+    sim.run(inv)
+    p0, p1 = sim.get_probabilities(0, 1)[0], sim.get_probabilities(last, 1)[0]
+    assert abs(p0 - 0.5) < 1e-10 and abs(p1 - 0.5) < 1e-10
+    m = sim.marginal([0, n - 1])                             # GHZ correlations: only 00 and 11
+    assert np.allclose(m, [0.5, 0, 0, 0.5], atol=1e-10)

@@ -95,6 +95,40 @@ def test_config_c5_average_matches_exact_channel():
     assert np.all(np.abs(hist / batch - exact) < 6 * sigma + 1e-3)
 
 
+def test_config_c5_full_size_against_exact_channel():
+    """BASELINE config 5 AT ITS STATED SIZE: BatchedSimulator(12, 65536), createGHZCircuit(12), depolarizing 0.005 +
+    amplitude damping 0.001 on every qubit after every gate, seed 42.  The exact distribution is the
+    committed fixture tests/golden/c5_exact_diag.npy (oracle Kraus evolution of the 4096 x 4096 density matrix,
+    generator tests/golden/make_c5_golden.py); tolerance 4 sigma of the 65 536-trajectory sampling error."""
+    n, batch = 12, 65536
+    exact = np.load(H.GOLDEN + "/c5_exact_diag.npy")
+    assert exact.shape == (1 << n,) and abs(exact.sum() - 1) < 1e-12
+    m = q.NoiseModel().add_depolarizing(0.005).add_amplitude_damping(0.001)
+    assert len(events_of(m, n)) == 2 * n
+    sim = q.BatchedSimulator(n, batch, m)
+    sim.set_seed(42)
+    sim.run(q.create_ghz_circuit(n))
+    avg = sim.get_average_probabilities()
+    assert abs(avg.sum() - 1) < 1e-10
+    # the average of |a|^2 over trajectories has per-entry variance <= p(1-p)/batch (it is a mean of values in [0,1] with mean p)
+    sigma = np.sqrt(np.maximum(exact * (1 - exact), 0) / batch)
+    assert np.all(np.abs(avg - exact) < 4 * sigma + 1e-5), float(np.max(np.abs(avg - exact) / (sigma + 1e-5)))
+    hist = sim.get_histogram(1)
+    assert hist.sum() == batch                                                    # tests/test_noise.cu:313-330
+    # one shot per trajectory is a multinomial draw of the exact distribution; the 4096 entries are tested jointly:
+    # chi-square over the cells with an expected count >= 5 (the rest pooled)
+    expct = exact * batch
+    big = expct >= 5
+    chi2 = float(np.sum((hist[big] - expct[big]) ** 2 / expct[big]))
+    rest_e, rest_o = expct[~big].sum(), hist[~big].sum()
+    if rest_e > 0:
+        chi2 += (rest_o - rest_e) ** 2 / rest_e
+    dof = int(big.sum())
+    assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, (chi2, dof)
+    assert abs(hist[0] / batch - exact[0]) < 4 * np.sqrt(exact[0] * (1 - exact[0]) / batch)
+    assert abs(hist[-1] / batch - exact[-1]) < 4 * np.sqrt(exact[-1] * (1 - exact[-1]) / batch)
+
+
 def test_batched_sampling_matches_sequential_cdf():
     n, batch, shots = 6, 16, 5
     rng = np.random.default_rng(2)

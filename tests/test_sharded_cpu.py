@@ -93,7 +93,16 @@ class EmulatorShardEngine:
 
     def synchronize(self): pass
     def local_state(self): return self.shard.copy()
-    def partial_probability(self, bit=-1): return float(np.sum(np.abs(self.shard) ** 2))
+    def partial_probability(self, bit=-1):
+        pr = np.abs(self.shard) ** 2
+        if bit >= 0:
+            pr = pr[((np.arange(len(pr)) >> bit) & 1) == 0]
+        return float(np.sum(pr))
+
+    def collapse(self, bit, outcome, scale):
+        if bit >= 0:
+            self.shard[((np.arange(len(self.shard)) >> bit) & 1) != outcome] = 0
+        self.shard *= scale
 
     def shard_sample(self, c_init, first, u):
         probs = H.oracle_probs(self.shard)
@@ -157,11 +166,37 @@ def _worker(rank, world, port, n, seeds, q):
                 outcome |= ((idx >> qb) & 1) << i
             want_m = np.bincount(outcome, weights=np.abs(want2) ** 2, minlength=16)
             assert np.max(np.abs(sim.marginal(qs) - want_m)) < 1e-12
-            # sampling: identical on every rank, right distribution support
-            u = np.random.default_rng(1).random(64)
+            # sampling after real exchanges: the reference's sequential CDF in LOGICAL index order, bit for bit
+            # (src/Simulator.cu:164-185) - the identity layout is restored first; the state itself is unchanged
+            u = np.concatenate([np.random.default_rng(1).random(64), [0.0, 0.5]])
             s = sim.sample(uniforms=u)
-            pr = np.abs(want2) ** 2
-            assert np.all(pr[s] > 0)
+            assert np.array_equal(s, H.oracle_sample(H.oracle_probs(got2), u))
+            assert sim.perm == list(range(n))
+            got3 = sim.get_state_vector()
+            assert np.array_equal(got3, got2)            # a pure data movement
+            # plans are tied to the layout they were compiled against
+            cp = sim.compile(c)
+            sim.execute(cp)
+            if cp.plan.perm != cp.perm_before or cp.frame_after != cp.frame_before:
+                with pytest.raises(ValueError):
+                    sim.execute(cp)
+            sim.release(cp)
+            want3 = H.oracle_run(n, g, want2)
+            worst = max(worst, float(np.max(np.abs(sim.get_state_vector() - want3))))
+            # measureQubit: outcome r < p0 ? 0 : 1 on index bit n-1-q (reference src/StateVector.cu:87-89, 284-313), collapse
+            for qb, r in ((0, 0.3), (n - 1, 0.8), (n // 2, 0.5)):
+                bit = n - 1 - qb
+                st = sim.get_state_vector()
+                pr = np.abs(st) ** 2
+                p0 = float(np.sum(pr[((np.arange(1 << n) >> bit) & 1) == 0]))
+                if min(p0, 1 - p0) < 1e-9 or abs(r - p0) < 1e-9:
+                    continue
+                res = sim.measure_qubit(qb, r)
+                assert res == (0 if r < p0 else 1)
+                keep = ((np.arange(1 << n) >> bit) & 1) == res
+                want_c = np.where(keep, st, 0) / np.sqrt(p0 if res == 0 else 1 - p0)
+                worst = max(worst, float(np.max(np.abs(sim.get_state_vector() - want_c))))
+                assert abs(sim.get_total_probability() - 1) < 1e-12
         # A circuit that leaves enough qubits without a non-diagonal target: from |0...0> the layout parks those in the
         # rank bits, no exchange happens, and — those bits being the same for every non-zero amplitude — sampling is
         # bit-identical to the single-device sequential CDF in LOGICAL index order.

@@ -143,3 +143,43 @@ def test_staged_shard_sampling_on_one_gpu():
     assert c == H.oracle().orc_total_probability(probs.ctypes.data_as(H.P), H.c_int64(len(probs)))
     for h in sims:
         L.qsim_sim_destroy(h)
+
+
+def test_shard_run_rejects_x_on_a_rank_qubit():
+    """qsim_sim_run / qsim_sim_apply_gate on a shard keep no X frame between calls: an uncontrolled X on a rank (global)
+    qubit must fail loudly ("must be remapped") instead of being absorbed into a frame nobody applies; the same gate on
+    a local qubit works, and a diagonal gate or a control on the rank qubit needs no remap."""
+    from ctypes import byref, c_void_p
+
+    import numpy as np
+
+    import cuda_quantum_simulator_b200 as q
+    from cuda_quantum_simulator_b200 import _lib
+
+    L = _lib.lib()
+    nl, n = 10, 11
+    rng = np.random.default_rng(5)
+    full = H.random_state(n, rng)
+    sims = []
+    for r in range(2):
+        h = c_void_p()
+        _lib.check(L.qsim_shard_create(n, 1, r, None, byref(h)))
+        _lib.check(L.qsim_sim_set_state(h, np.ascontiguousarray(full[r << nl:(r + 1) << nl]).ctypes.data_as(c_void_p)))
+        sims.append(h)
+    bad = H.gates([("X", n - 1)])
+    ok = H.gates([("X", 3), ("CNOT", n - 1, 2), ("Rz", n - 1, 0.3), ("H", 0), ("X", 0)])
+    for h in sims:
+        with pytest.raises(q.QsimError, match="remapped"):
+            _lib.check(L.qsim_sim_run(h, n, _lib.gates_ptr(bad), len(bad)))
+        with pytest.raises(q.QsimError, match="remapped"):
+            _lib.check(L.qsim_sim_apply_gate(h, _lib.gates_ptr(bad)))
+        _lib.check(L.qsim_sim_run(h, n, _lib.gates_ptr(ok), len(ok)))
+        _lib.check(L.qsim_sim_apply_gate(h, _lib.gates_ptr(H.gates([("X", 5)]))))
+    want = H.oracle_run(n, np.concatenate([ok, H.gates([("X", 5)])]), full)
+    got = []
+    for h in sims:
+        out = np.empty(1 << nl, np.complex128)
+        _lib.check(L.qsim_sim_get_state(h, out.ctypes.data_as(c_void_p)))
+        got.append(out)
+        L.qsim_sim_destroy(h)
+    assert np.max(np.abs(np.concatenate(got) - want)) < 1e-12

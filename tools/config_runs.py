@@ -24,18 +24,7 @@ def timed(sim, fn, reps):
     return (time.perf_counter() - t0) / reps
 
 
-def qft_style(n, window=None):
-    """GHZ followed by H / CRZ(j, q, pi/2^(j-q)) layers and a seeded Rz layer."""
-    c = q.create_ghz_circuit(n)
-    for qb in range(n):
-        c.h(qb)
-        hi = n if window is None else min(n, qb + 1 + window)
-        for j in range(qb + 1, hi):
-            c.crz(j, qb, float(np.pi / 2 ** (j - qb)))
-    theta = H.mt19937_uniforms(42, n) * 2 * np.pi
-    for qb in range(n):
-        c.rz(qb, float(theta[qb]))
-    return c
+qft_style = H.qft_style_circuit
 
 
 def c1():
