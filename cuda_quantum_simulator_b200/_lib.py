@@ -73,6 +73,10 @@ def _declare(L: ctypes.CDLL) -> None:
         "qsim_program_destroy": (None, [P]),
         "qsim_program_info": (c_int, [P, POINTER(c_int64)]),
         "qsim_program_describe": (c_size_t, [P, c_char_p, c_size_t]),
+        "qsim_jit_set_mode": (c_int, [c_int, c_int]),
+        "qsim_jit_stats": (c_int, [POINTER(c_int64)]),
+        "qsim_program_jit_source": (c_size_t, [P, c_int, c_int, c_char_p, c_size_t]),
+        "qsim_program_jit_compile": (c_int, [P, c_int, POINTER(c_int64), P, c_size_t]),
         "qsim_sim_create": (c_int, [c_int, PP]),
         "qsim_sim_create_external": (c_int, [c_int, P, PP]),
         "qsim_sim_destroy": (None, [P]),

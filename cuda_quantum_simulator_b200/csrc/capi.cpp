@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "engine.hpp"
+#include "jit.hpp"
 #include "program.hpp"
 #include "qsim/circuit.hpp"
 #include "qsim/constants.hpp"
@@ -181,7 +182,11 @@ qsim_status_t qsim_program_compile_ex(int n, int n_global, const qsim_gate_t* ga
         opt.initial_xor = initial_xor;
         std::string err;
         if (!b200::compile(n, gates, ng, opt, p->dev.host, &err)) throw std::runtime_error(err);
-        p->dev.upload();
+        // the device copy is made now when a GPU is there, else at the first execute (compiling, describing and
+        // inspecting the generated kernels need no device)
+        int n_dev = 0;
+        if (cudaGetDeviceCount(&n_dev) == cudaSuccess && n_dev > 0) p->dev.upload();
+        else cudaGetLastError();
         *out = p.release();
     });
 }
@@ -205,15 +210,58 @@ qsim_status_t qsim_program_info(const qsim_program_t* p, int64_t info[8]) {
     });
 }
 
-size_t qsim_program_describe(const qsim_program_t* p, char* buf, size_t cap) {
-    if (!p) return 0;
-    const std::string d = p->dev.host.describe();
+static size_t copy_out(const std::string& d, char* buf, size_t cap) {
     if (buf && cap) {
         const size_t k = d.size() < cap - 1 ? d.size() : cap - 1;
         std::memcpy(buf, d.data(), k);
         buf[k] = 0;
     }
     return d.size() + 1;
+}
+
+qsim_status_t qsim_jit_set_mode(int mode, int min_qubits) {
+    return guarded([&] {
+        require(mode >= 0 && mode <= 2, "mode must be 0 (off), 1 (auto) or 2 (always)");
+        b200::jit_set_mode(static_cast<b200::JitMode>(mode), min_qubits);
+    });
+}
+
+qsim_status_t qsim_jit_stats(int64_t out[8]) {
+    return guarded([&] {
+        require(out != nullptr, "null output");
+        const b200::JitStats st = b200::jit_stats();
+        out[0] = st.compiles; out[1] = st.cache_hits; out[2] = st.launches; out[3] = st.failures;
+        out[4] = (int64_t)(st.compile_seconds * 1e6); out[5] = st.last_cubin_bytes;
+        out[6] = (int64_t)b200::jit_mode(); out[7] = b200::jit_min_qubits();
+    });
+}
+
+size_t qsim_program_jit_source(const qsim_program_t* p, int pass, int whole_unit, char* buf, size_t cap) {
+    if (!p || pass < 0 || pass >= (int)p->dev.host.passes.size()) return 0;
+    const b200::PassDesc& pd = p->dev.host.passes[pass];
+    const b200::DevOp* ops = p->dev.host.ops.data() + pd.op_offset;
+    return copy_out(whole_unit ? b200::jit_translation_unit(pd, ops) : b200::jit_generate_compute(pd, ops), buf, cap);
+}
+
+qsim_status_t qsim_program_jit_compile(const qsim_program_t* p, int pass, int64_t* cubin_bytes, void* cubin_out, size_t cap) {
+    return guarded([&] {
+        require(p != nullptr && pass >= 0 && pass < (int)p->dev.host.passes.size(), "no such pass");
+        const b200::PassDesc& pd = p->dev.host.passes[pass];
+        const b200::JitMode saved = b200::jit_mode();
+        const int saved_min = b200::jit_min_qubits();
+        b200::jit_set_mode(b200::JitMode::Always, saved_min);   // a failure throws with the compiler's log
+        std::shared_ptr<b200::JitKernel> k;
+        try { k = b200::jit_get_kernel(pd, p->dev.host.ops.data() + pd.op_offset, /*needs_device=*/false); }
+        catch (...) { b200::jit_set_mode(saved, saved_min); throw; }
+        b200::jit_set_mode(saved, saved_min);
+        if (cubin_bytes) *cubin_bytes = k ? (int64_t)b200::jit_copy_cubin(*k, nullptr, 0) : 0;
+        if (cubin_out && k) b200::jit_copy_cubin(*k, cubin_out, cap);
+    });
+}
+
+size_t qsim_program_describe(const qsim_program_t* p, char* buf, size_t cap) {
+    if (!p) return 0;
+    return copy_out(p->dev.host.describe(), buf, cap);
 }
 
 // ---- simulator --------------------------------------------------------------------------------
@@ -329,6 +377,7 @@ qsim_status_t qsim_sim_execute(qsim_sim_t* s, const qsim_program_t* p) {
         require(s != nullptr && p != nullptr, "null argument");
         if (p->dev.host.n != s->n_total || p->n_global != s->n_global)
             throw std::invalid_argument("Circuit qubit count doesn't match simulator");
+        if (!p->dev.d_ops && !p->dev.host.ops.empty()) const_cast<qsim_program_t*>(p)->dev.upload();   // compiled without a device
         if (s->n_global == 0) s->sim->execute(p->dev);
         else {
             StateVector& sv = s->sim->state();

@@ -122,7 +122,7 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
         PassParams prm;
         prm.state = state;
         prm.ops = d_ops + pd.op_offset;
-        prm.phase_tables = d_tables ? reinterpret_cast<const double2*>(d_tables) + pd.phase_table_offset : nullptr;
+        prm.phase_tables = d_tables ? reinterpret_cast<const double2*>(d_tables) + pd.phase_table_offset : nullptr;   // (void*: pass_desc.h is plain data)
         prm.phase_terms = d_terms ? d_terms + pd.phase_term_offset : nullptr;
         prm.hi_bits = hi_bits;
         prm.n_tiles = 1ULL << (pd.n - pd.t);
@@ -158,7 +158,9 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
             e1 = getEvent();
             CUDA_CHECK(cudaEventRecord(e0, stream_));
         }
-        CUDA_CHECK(launch_pass(prm, num_sms_, stream_));
+        const size_t pass_i = (size_t)(&pd - p.passes.data());
+        if (p.jit.size() != p.passes.size()) { p.jit.assign(p.passes.size(), nullptr); p.jit_tried.assign(p.passes.size(), 0); }
+        CUDA_CHECK(launch_pass(prm, num_sms_, stream_, p.ops.data() + pd.op_offset, &p.jit[pass_i], &p.jit_tried[pass_i]));
         ++launches_;
         if (timing_) {
             CUDA_CHECK(cudaEventRecord(e1, stream_));

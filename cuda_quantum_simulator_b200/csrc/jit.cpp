@@ -1,0 +1,562 @@
+// Run-time specialised pass kernels: code generation, NVRTC, cache, launch.  See jit.hpp.
+#include "jit.hpp"
+
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <sstream>
+#include <stdexcept>
+#include <unordered_map>
+#include <vector>
+
+namespace qsim {
+namespace b200 {
+
+namespace {
+
+// the three sources the specialised kernel shares with the ahead-of-time one, embedded at build time (Makefile: *.embed)
+const char kSrcPassDesc[] =
+#include "_build/pass_desc.h.embed"
+    ;
+const char kSrcPassDevice[] =
+#include "_build/pass_device.cuh.embed"
+    ;
+const char kSrcKernelBody[] =
+#include "_build/pass_kernel_body.inc.embed"
+    ;
+
+// ---- code generation ------------------------------------------------------------------------------------------------
+
+struct Gen {
+    std::ostringstream os;
+    int indent = 1;
+    void line(const std::string& s) {
+        for (int i = 0; i < indent; ++i) os << "    ";
+        os << s << "\n";
+    }
+    void open(const std::string& s) { line(s + " {"); ++indent; }
+    void close() { --indent; line("}"); }
+};
+
+std::string hex(uint64_t v) {
+    char b[32];
+    std::snprintf(b, sizeof(b), "0x%llxULL", (unsigned long long)v);
+    return b;
+}
+std::string hex32(uint32_t v) {
+    char b[32];
+    std::snprintf(b, sizeof(b), "0x%xu", v);
+    return b;
+}
+std::string num(long long v) { return std::to_string(v); }
+
+// names of the register variables that hold slot k's amplitude
+struct Slots {
+    std::vector<int> var;   // slot -> variable index (bit flips on register bits are renamings)
+    std::string r(int k) const { return "xr" + num(var[k]); }
+    std::string i(int k) const { return "xi" + num(var[k]); }
+};
+
+bool is_one(const double* m) { return m[0] == 1.0 && m[1] == 0.0; }
+
+// value classes that change the generated code (they are part of the kernel's identity, the values themselves are not)
+struct DiagClass {
+    bool d0_one, real;
+};
+DiagClass diag_class(const DevOp& op) {
+    DiagClass c;
+    c.d0_one = is_one(&op.m[0]);
+    c.real = op.m[1] == 0.0 && op.m[7] == 0.0;
+    return c;
+}
+
+void emit_cmul(Gen& g, const Slots& s, int k, const std::string& pr, const std::string& pi, bool real) {
+    if (real) {
+        g.line(s.r(k) + " *= " + pr + "; " + s.i(k) + " *= " + pr + ";");
+    } else {
+        g.line("{ const double t_ = " + s.r(k) + " * " + pr + " - " + s.i(k) + " * " + pi + "; " + s.i(k) + " = " + s.r(k) +
+               " * " + pi + " + " + s.i(k) + " * " + pr + "; " + s.r(k) + " = t_; }");
+    }
+}
+
+void emit_op(Gen& g, Slots& s, const PassDesc& pd, const SweepDesc& sd, const DevOp& op, int o, int n_slots) {
+    static const char* kn[] = {"MAT", "MATREAL", "ADIAG", "FLIP", "DIAG", "PHASE"};
+    static const char* hn[] = {"lane", "reg", "thread", "outside"};
+    const std::string M = "reinterpret_cast<const double2*>(sops[" + num(o) + "].m)";
+    const uint32_t all = (n_slots >= 32) ? 0xffffffffu : ((1u << n_slots) - 1u);
+
+    if (op.kind == OP_PHASE) {
+        // amplitude(l) *= TABLE[l] * U * prod_{tile bits j of l} E_j   (see phase_op of the interpreter)
+        const uint32_t present = op.cmask_thr;
+        g.line("// op " + num(o) + ": PHASE present=" + hex32(present));
+        g.open("");
+        g.line("const double2* e_ = eu + " + num((long long)op.tmask_out * 13) + ";");
+        g.line("double pr_ = 1.0, pi_ = 0.0;");
+        if (present & (1u << 12)) g.line("pr_ = e_[12].x; pi_ = e_[12].y;");
+        for (int b = 0; b < sd.nthr; ++b) {
+            const int pos = sd.thr_pos[b];
+            if (!((present >> pos) & 1u)) continue;
+            g.line("if ((tid >> " + num(b) + ") & 1u) { const double2 v_ = e_[" + num(pos) + "]; const double t_ = pr_ * v_.x - pi_ * v_.y; "
+                   "pi_ = pr_ * v_.y + pi_ * v_.x; pr_ = t_; }");
+        }
+        if (!(present & (1u << 13)) && (present & (1u << 14)))
+            g.line("{ const double2 t2_ = __ldg(tables + " + num((long long)op.cmask_out) + "); const double t_ = t2_.x * pr_ - t2_.y * pi_; "
+                   "pi_ = t2_.x * pi_ + t2_.y * pr_; pr_ = t_; }");
+        for (int k = 0; k < n_slots; ++k) {
+            std::string fr = "fr" + num(k) + "_", fi = "fi" + num(k) + "_";
+            if (present & (1u << 13)) {
+                g.line("double " + fr + ", " + fi + "; { const double2 t2_ = __ldg(tables + " + num((long long)op.cmask_out) +
+                       " + (base_local ^ " + hex32(sd.slot_off[k]) + ")); " + fr + " = t2_.x * pr_ - t2_.y * pi_; " + fi +
+                       " = t2_.x * pi_ + t2_.y * pr_; }");
+            } else {
+                g.line("double " + fr + " = pr_, " + fi + " = pi_;");
+            }
+        }
+        for (int j = 0; j < sd.r; ++j) {
+            if (!((present >> sd.reg_pos[j]) & 1u)) continue;
+            g.line("{ const double2 v_ = e_[" + num(sd.reg_pos[j]) + "];");
+            for (int k = 0; k < n_slots; ++k) {
+                if (!((k >> j) & 1)) continue;
+                std::string fr = "fr" + num(k) + "_", fi = "fi" + num(k) + "_";
+                g.line("  { const double t_ = " + fr + " * v_.x - " + fi + " * v_.y; " + fi + " = " + fr + " * v_.y + " + fi +
+                       " * v_.x; " + fr + " = t_; }");
+            }
+            g.line("}");
+        }
+        for (int k = 0; k < n_slots; ++k) emit_cmul(g, s, k, "fr" + num(k) + "_", "fi" + num(k) + "_", false);
+        g.close();
+        return;
+    }
+
+    const bool has_out_ctrl = op.cmask_out != 0;
+    const bool has_thr_ctrl = op.cmask_thr != 0;
+    const uint32_t slotset = op.slotmask & all;
+    g.line("// op " + num(o) + ": " + kn[op.kind] + " target=" + hn[op.thome] + ":" + num(op.tbit) + " slots=" + hex32(slotset) +
+           (has_thr_ctrl ? " thr-ctrl" : "") + (has_out_ctrl ? " out-ctrl" : ""));
+    if (slotset == 0) return;
+
+    // FLIP on a register bit without thread / outside controls: a renaming of the slot variables, no code at all
+    if (op.kind == OP_FLIP && op.thome == T_REG && !has_out_ctrl && !has_thr_ctrl) {
+        const int J = 1 << op.tbit;
+        for (int k = 0; k < n_slots; ++k)
+            if (!(k & J) && ((slotset >> k) & 1)) std::swap(s.var[k], s.var[k | J]);
+        return;
+    }
+
+    int opened = 0;
+    if (has_out_ctrl) { g.open("if ((gbase & " + hex(op.cmask_out) + ") == " + hex(op.cval_out) + ")"); ++opened; }
+    else { g.open(""); ++opened; }
+    // Controls held in tid bits: a branch around in-thread work (warp-uniform for warp bits; for lane bits the idle lanes
+    // cost nothing extra).  Lane-target ops keep every lane in the shuffles (a partial-mask shuffle compiles to a
+    // WARPSYNC / collective sequence per instruction) and select afterwards, as the interpreter does.
+    const bool lane_sel = has_thr_ctrl && op.thome == T_LANE;
+    if (has_thr_ctrl) {
+        g.line("const bool pt_ = (tid & " + hex32(op.cmask_thr) + ") == " + hex32(op.cval_thr) + ";");
+        if (!lane_sel) { g.open("if (pt_)"); ++opened; }
+    }
+
+    if (op.kind == OP_DIAG) {
+        const DiagClass dc = diag_class(op);
+        g.line("const double2 d0_ = " + M + "[0], d1_ = " + M + "[3];");
+        if (op.thome == T_REG) {
+            for (int k = 0; k < n_slots; ++k) {
+                if (!((slotset >> k) & 1)) continue;
+                const bool b = (op.tslots >> k) & 1;
+                if (!b && dc.d0_one) continue;
+                emit_cmul(g, s, k, b ? "d1_.x" : "d0_.x", b ? "d1_.y" : "d0_.y", dc.real);
+            }
+        } else {
+            const std::string bt = (op.thome == T_THREAD) ? "(tid & " + hex32(op.tmask_thr) + ") != 0u"
+                                                          : "(gbase & " + hex(op.tmask_out) + ") != 0ULL";
+            if (dc.d0_one) {
+                g.open("if (" + bt + ")");
+                for (int k = 0; k < n_slots; ++k)
+                    if ((slotset >> k) & 1) emit_cmul(g, s, k, "d1_.x", "d1_.y", dc.real);
+                g.close();
+            } else {
+                g.line("const bool bt_ = " + bt + ";");
+                g.line("const double pr_ = bt_ ? d1_.x : d0_.x, pi_ = bt_ ? d1_.y : d0_.y;");
+                for (int k = 0; k < n_slots; ++k)
+                    if ((slotset >> k) & 1) emit_cmul(g, s, k, "pr_", "pi_", dc.real);
+            }
+        }
+    } else if (op.thome == T_REG) {
+        const int J = 1 << op.tbit;
+        if (op.kind != OP_FLIP) g.line("const double2 ma_ = " + M + "[0], mb_ = " + M + "[1], mc_ = " + M + "[2], md_ = " + M + "[3];");
+        for (int k = 0; k < n_slots; ++k) {
+            if ((k & J) || !((slotset >> k) & 1)) continue;
+            const int k1 = k | J;
+            const std::string ar = s.r(k), ai = s.i(k), br = s.r(k1), bi = s.i(k1);
+            g.line("{ const double ar_ = " + ar + ", ai_ = " + ai + ", br_ = " + br + ", bi_ = " + bi + ";");
+            if (op.kind == OP_FLIP) {
+                g.line("  " + ar + " = br_; " + ai + " = bi_; " + br + " = ar_; " + bi + " = ai_; }");
+            } else if (op.kind == OP_ADIAG) {
+                g.line("  " + ar + " = mb_.x * br_ - mb_.y * bi_; " + ai + " = mb_.x * bi_ + mb_.y * br_;");
+                g.line("  " + br + " = mc_.x * ar_ - mc_.y * ai_; " + bi + " = mc_.x * ai_ + mc_.y * ar_; }");
+            } else if (op.kind == OP_MATREAL) {
+                g.line("  " + ar + " = ma_.x * ar_ + mb_.x * br_; " + ai + " = ma_.x * ai_ + mb_.x * bi_;");
+                g.line("  " + br + " = mc_.x * ar_ + md_.x * br_; " + bi + " = mc_.x * ai_ + md_.x * bi_; }");
+            } else {
+                g.line("  " + ar + " = ma_.x * ar_ - ma_.y * ai_ + mb_.x * br_ - mb_.y * bi_;");
+                g.line("  " + ai + " = ma_.x * ai_ + ma_.y * ar_ + mb_.x * bi_ + mb_.y * br_;");
+                g.line("  " + br + " = mc_.x * ar_ - mc_.y * ai_ + md_.x * br_ - md_.y * bi_;");
+                g.line("  " + bi + " = mc_.x * ai_ + mc_.y * ar_ + md_.x * bi_ + md_.y * br_; }");
+            }
+        }
+    } else {   // T_LANE
+        const std::string lm = num(1 << op.tbit);
+        if (op.kind != OP_FLIP) {
+            g.line("const bool hb_ = (tid >> " + num(op.tbit) + ") & 1u;");
+            // coefficient of my own amplitude and of my partner's
+            g.line("const double2 ma_ = " + M + "[0], mb_ = " + M + "[1], mc_ = " + M + "[2], md_ = " + M + "[3];");
+            g.line("const double cor_ = hb_ ? md_.x : ma_.x, coi_ = hb_ ? md_.y : ma_.y, cpr_ = hb_ ? mc_.x : mb_.x, cpi_ = hb_ ? mc_.y : mb_.y;");
+        }
+        if (op.kind == OP_FLIP && lane_sel) g.line("const int src_ = pt_ ? (int)((tid & 31u) ^ " + lm + "u) : (int)(tid & 31u);");
+        for (int k = 0; k < n_slots; ++k) {
+            if (!((slotset >> k) & 1)) continue;
+            const std::string xr = s.r(k), xi = s.i(k);
+            if (op.kind == OP_FLIP) {
+                // pure data movement: the select is on the source lane, not on the data
+                if (lane_sel) g.line(xr + " = __shfl_sync(0xffffffffu, " + xr + ", src_); " + xi + " = __shfl_sync(0xffffffffu, " + xi + ", src_);");
+                else g.line(xr + " = __shfl_xor_sync(0xffffffffu, " + xr + ", " + lm + "); " + xi + " = __shfl_xor_sync(0xffffffffu, " + xi + ", " + lm + ");");
+                continue;
+            }
+            g.line("{ const double pr_ = __shfl_xor_sync(0xffffffffu, " + xr + ", " + lm + "), pi_ = __shfl_xor_sync(0xffffffffu, " + xi + ", " + lm + ");");
+            if (op.kind == OP_ADIAG)
+                g.line("  const double nr_ = cpr_ * pr_ - cpi_ * pi_, ni_ = cpr_ * pi_ + cpi_ * pr_;");
+            else if (op.kind == OP_MATREAL)
+                g.line("  const double nr_ = cor_ * " + xr + " + cpr_ * pr_, ni_ = cor_ * " + xi + " + cpr_ * pi_;");
+            else
+                g.line("  const double nr_ = cor_ * " + xr + " - coi_ * " + xi + " + cpr_ * pr_ - cpi_ * pi_, ni_ = cor_ * " + xi + " + coi_ * " + xr +
+                       " + cpr_ * pi_ + cpi_ * pr_;");
+            if (lane_sel) g.line("  " + xr + " = pt_ ? nr_ : " + xr + "; " + xi + " = pt_ ? ni_ : " + xi + "; }");
+            else g.line("  " + xr + " = nr_; " + xi + " = ni_; }");
+        }
+    }
+    while (opened-- > 0) g.close();
+}
+
+}  // namespace
+
+std::string jit_generate_compute(const PassDesc& pd, const DevOp* ops) {
+    Gen g;
+    g.indent = 0;
+    g.line("// generated by qsim_b200 jit.cpp: per-tile compute of one pass (n=" + num(pd.n) + ", t=" + num(pd.t) + ", " +
+           num(pd.n_sweeps) + " sweep(s), " + num(pd.n_ops) + " op(s))");
+    g.line("__device__ __forceinline__ void jit_compute_tile(const PassParams& P, unsigned char* tile, uint64_t gbase, uint32_t tid,");
+    g.line("                                                 const DevOp* sops, const double2* eu, const uint16_t* base_tab) {");
+    g.indent = 1;
+    g.line("const uint32_t tile_u32 = smem_u32(tile);");
+    g.line("const uint32_t warp = tid >> 5;");
+    g.line("const double2* tables = reinterpret_cast<const double2*>(P.phase_tables);");
+    g.line("(void)warp; (void)tables; (void)eu; (void)sops; (void)gbase;");
+    const int T = kComputeThreads;
+    for (int sw = 0; sw < pd.n_sweeps; ++sw) {
+        const SweepDesc& sd = pd.sweep[sw];
+        const int n_slots = 1 << sd.r;
+        const uint32_t n_active = 1u << sd.nthr;
+        const bool last = (sw + 1 == pd.n_sweeps);
+        const uint32_t xl = last ? pd.xor_local : 0u;
+        const int n_tail = last ? pd.n_tail : 0;
+        const bool pass_head = (sw == 0 && pd.n_head > 0);
+        const bool mapped_load = pass_head || sd.n_head > 0;
+        const bool permuted_store = (xl != 0u) || (n_tail > 0) || mapped_load;
+        const bool partial_warp = n_active < 32u;          // lanes beyond the tile inside the one active warp
+        const bool some_warps_idle = n_active < (uint32_t)T;
+        g.line("// ---- sweep " + num(sw) + ": r=" + num(sd.r) + " nthr=" + num(sd.nthr));
+        g.open("");
+        if (sw > 0) g.line("__syncthreads();");
+        if (some_warps_idle) g.open("if ((warp << 5) < " + num(n_active) + "u)");
+        else g.open("");
+        if (partial_warp) g.line("const bool active = tid < " + num(n_active) + "u;");
+        g.line("const uint32_t base_local = base_tab[" + num(sw * T) + " + (int)tid];");
+        g.line("const uint32_t a0_ = tile_u32 + base_local * 16u;");
+        Slots s;
+        s.var.resize(n_slots);
+        for (int k = 0; k < n_slots; ++k) s.var[k] = k;
+        {
+            std::string decl = "double ";
+            for (int k = 0; k < n_slots; ++k) decl += (k ? ", " : "") + ("xr" + num(k) + " = 0.0, xi" + num(k) + " = 0.0");
+            g.line(decl + ";");
+        }
+        const std::string guard = partial_warp ? "if (active) " : "";
+        if (mapped_load) {
+            const uint16_t* loff;
+            if (pass_head) {
+                g.line("uint32_t lb_ = base_tab[" + num((pd.n_sweeps + 1) * T) + " + (int)tid];");
+                for (int f = 0; f < pd.n_head_dyn; ++f)
+                    g.line("if ((gbase & " + hex(pd.head_dyn[f].cmask_out) + ") == " + hex(pd.head_dyn[f].cval_out) + ") lb_ ^= " +
+                           hex32(pd.head_dyn[f].w) + ";");
+                loff = pd.load_slot_off;
+            } else {
+                g.line("uint32_t lb_ = " + hex32(sd.head_const) + ";");
+                for (int j = 0; j < pd.t; ++j)
+                    if (sd.head_lin[j]) g.line("if ((base_local >> " + num(j) + ") & 1u) lb_ ^= " + hex32(sd.head_lin[j]) + ";");
+                loff = sd.load_slot_off;
+            }
+            for (int k = 0; k < n_slots; ++k)
+                g.line(guard + "lds128(tile_u32 + ((lb_ ^ " + hex32(loff[k]) + ") << 4), " + s.r(k) + ", " + s.i(k) + ");");
+        } else {
+            for (int k = 0; k < n_slots; ++k)
+                g.line(guard + "lds128(a0_ + " + num((long long)sd.slot_off[k] * 16) + "u, " + s.r(k) + ", " + s.i(k) + ");");
+        }
+        for (int o = sd.op_begin; o < sd.op_end; ++o) emit_op(g, s, pd, sd, ops[o], o, n_slots);
+        if (permuted_store) g.line("__syncthreads();");
+        const bool plain_store = !last || (pd.n_tail == 0 && pd.n_dyn == 0 && xl == 0u);
+        if (plain_store) {
+            for (int k = 0; k < n_slots; ++k)
+                g.line(guard + "sts128(a0_ + " + num((long long)sd.slot_off[k] * 16) + "u, " + s.r(k) + ", " + s.i(k) + ");");
+        } else {
+            g.line("uint32_t sb_ = (uint32_t)base_tab[" + num(pd.n_sweeps * T) + " + (int)tid] ^ " + hex32(xl) + ";");
+            for (int f = 0; f < pd.n_dyn; ++f)
+                g.line("if ((gbase & " + hex(pd.dyn[f].cmask_out) + ") == " + hex(pd.dyn[f].cval_out) + ") sb_ ^= " + hex32(pd.dyn[f].w) + ";");
+            for (int k = 0; k < n_slots; ++k)
+                g.line(guard + "sts128(tile_u32 + ((sb_ ^ " + hex32(pd.store_slot_off[k]) + ") << 4), " + s.r(k) + ", " + s.i(k) + ");");
+        }
+        g.close();
+        if (some_warps_idle && permuted_store) g.line("else { __syncthreads(); }   // keep the barrier count equal across warps");
+        g.close();
+    }
+    g.indent = 0;
+    g.line("}");
+    return g.os.str();
+}
+
+std::string jit_translation_unit(const PassDesc& pd, const DevOp* ops) {
+    std::string tu;
+    tu.reserve(1 << 16);
+    tu += "#define QSIM_REG_BITS " + std::to_string(QSIM_REG_BITS) + "\n";
+    tu += "#include \"pass_desc.h\"\n#include \"pass_device.cuh\"\n";
+    tu += "namespace qsim {\nnamespace b200 {\nnamespace {\n";
+    tu += jit_generate_compute(pd, ops);
+    tu += "}  // namespace\n";
+    tu += "#define QSIM_PASS_KERNEL qsim_jit_pass\n#define QSIM_COMPUTE_TILE jit_compute_tile\n#define QSIM_KERNEL_LINKAGE extern \"C\"\n";
+    tu += "#include \"pass_kernel_body.inc\"\n";
+    tu += "}  // namespace b200\n}  // namespace qsim\n";
+    return tu;
+}
+
+// ---- NVRTC (loaded on demand: the library itself does not link it) ----------------------------------------------------
+
+namespace {
+
+struct Nvrtc {
+    void* handle = nullptr;
+    decltype(&nvrtcCreateProgram) create = nullptr;
+    decltype(&nvrtcCompileProgram) compile = nullptr;
+    decltype(&nvrtcGetCUBINSize) cubin_size = nullptr;
+    decltype(&nvrtcGetCUBIN) cubin = nullptr;
+    decltype(&nvrtcGetProgramLogSize) log_size = nullptr;
+    decltype(&nvrtcGetProgramLog) log = nullptr;
+    decltype(&nvrtcDestroyProgram) destroy = nullptr;
+    decltype(&nvrtcGetErrorString) error_string = nullptr;
+    std::string why;   // why it is unavailable
+    bool ok() const { return handle != nullptr; }
+};
+
+const Nvrtc& nvrtc() {
+    static Nvrtc n = [] {
+        Nvrtc r;
+        std::vector<std::string> names;
+        if (const char* e = std::getenv("QSIM_NVRTC_LIB")) names.push_back(e);
+        // the toolkit's own NVRTC first (the build's CUDA version); a bare soname may resolve to an older copy that another
+        // library of the process bundles (PyTorch ships 12.8)
+        for (const char* s : {"/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so.12", "libnvrtc.so"})
+            names.push_back(s);
+        for (const std::string& nm : names) {
+            r.handle = dlopen(nm.c_str(), RTLD_NOW | RTLD_LOCAL);
+            if (r.handle) break;
+        }
+        if (!r.handle) { r.why = "libnvrtc.so.12 not found (set QSIM_NVRTC_LIB)"; return r; }
+        auto sym = [&](const char* s) { return dlsym(r.handle, s); };
+        r.create = reinterpret_cast<decltype(r.create)>(sym("nvrtcCreateProgram"));
+        r.compile = reinterpret_cast<decltype(r.compile)>(sym("nvrtcCompileProgram"));
+        r.cubin_size = reinterpret_cast<decltype(r.cubin_size)>(sym("nvrtcGetCUBINSize"));
+        r.cubin = reinterpret_cast<decltype(r.cubin)>(sym("nvrtcGetCUBIN"));
+        r.log_size = reinterpret_cast<decltype(r.log_size)>(sym("nvrtcGetProgramLogSize"));
+        r.log = reinterpret_cast<decltype(r.log)>(sym("nvrtcGetProgramLog"));
+        r.destroy = reinterpret_cast<decltype(r.destroy)>(sym("nvrtcDestroyProgram"));
+        r.error_string = reinterpret_cast<decltype(r.error_string)>(sym("nvrtcGetErrorString"));
+        if (!r.create || !r.compile || !r.cubin_size || !r.cubin || !r.log_size || !r.log || !r.destroy) {
+            r.why = "libnvrtc lacks a required entry point";
+            dlclose(r.handle);
+            r.handle = nullptr;
+        }
+        return r;
+    }();
+    return n;
+}
+
+std::mutex g_mu;
+JitMode g_mode = JitMode::Auto;
+int g_min_qubits = 26;
+bool g_mode_init = false;
+JitStats g_stats;
+std::string g_last_log;
+bool g_warned = false;
+
+void init_mode_locked() {
+    if (g_mode_init) return;
+    g_mode_init = true;
+    if (const char* e = std::getenv("QSIM_JIT")) {
+        const std::string v = e;
+        if (v == "off" || v == "0") g_mode = JitMode::Off;
+        else if (v == "always" || v == "2") g_mode = JitMode::Always;
+        else g_mode = JitMode::Auto;
+    }
+    if (const char* e = std::getenv("QSIM_JIT_MIN_QUBITS")) g_min_qubits = std::atoi(e);
+}
+
+uint64_t fnv1a(const std::string& s) {
+    uint64_t h = 1469598103934665603ULL;
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ULL; }
+    return h;
+}
+
+}  // namespace
+
+struct JitKernel {
+    std::vector<char> cubin;
+    cudaLibrary_t library = nullptr;
+    cudaKernel_t kernel = nullptr;
+    bool attr_set[64] = {};
+    std::string source;
+    ~JitKernel() {
+        if (library) cudaLibraryUnload(library);
+    }
+};
+
+namespace {
+std::unordered_map<uint64_t, std::shared_ptr<JitKernel>> g_cache;           // keyed by the hash of the generated compute
+std::unordered_map<uint64_t, bool> g_failed;
+}  // namespace
+
+JitMode jit_mode() {
+    std::lock_guard<std::mutex> lock(g_mu);
+    init_mode_locked();
+    return g_mode;
+}
+int jit_min_qubits() {
+    std::lock_guard<std::mutex> lock(g_mu);
+    init_mode_locked();
+    return g_min_qubits;
+}
+void jit_set_mode(JitMode mode, int min_qubits) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_mode_init = true;
+    g_mode = mode;
+    if (min_qubits > 0) g_min_qubits = min_qubits;
+}
+
+bool jit_wanted(const PassDesc& pd) {
+    const JitMode m = jit_mode();
+    if (m == JitMode::Off) return false;
+    if (m == JitMode::Always) return true;
+    return pd.n >= jit_min_qubits();
+}
+
+JitStats jit_stats() {
+    std::lock_guard<std::mutex> lock(g_mu);
+    return g_stats;
+}
+std::string jit_last_log() {
+    std::lock_guard<std::mutex> lock(g_mu);
+    return g_last_log;
+}
+
+std::shared_ptr<JitKernel> jit_get_kernel(const PassDesc& pd, const DevOp* ops, bool needs_device) {
+    const JitMode mode = jit_mode();
+    const std::string compute = jit_generate_compute(pd, ops);
+    const uint64_t key = fnv1a(compute) ^ ((uint64_t)QSIM_REG_BITS << 56);
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto fail = [&](const std::string& what) -> std::shared_ptr<JitKernel> {
+        ++g_stats.failures;
+        g_failed[key] = true;
+        if (mode == JitMode::Always) throw std::runtime_error("qsim_b200 jit: " + what);
+        if (!g_warned) {
+            g_warned = true;
+            std::fprintf(stderr, "qsim_b200: run-time specialisation unavailable (%s); using the interpreter kernel\n", what.c_str());
+        }
+        return nullptr;
+    };
+    auto it = g_cache.find(key);
+    if (it != g_cache.end() && it->second->source == compute && (!needs_device || it->second->kernel)) {
+        ++g_stats.cache_hits;
+        return it->second;
+    }
+    if (g_failed.count(key) && mode != JitMode::Always) return nullptr;
+    const Nvrtc& rt = nvrtc();
+    if (!rt.ok()) return fail(rt.why);
+
+    const auto t0 = std::chrono::steady_clock::now();
+    const std::string tu = jit_translation_unit(pd, ops);
+    nvrtcProgram prog = nullptr;
+    const char* headers[] = {kSrcPassDesc, kSrcPassDevice, kSrcKernelBody};
+    const char* names[] = {"pass_desc.h", "pass_device.cuh", "pass_kernel_body.inc"};
+    if (rt.create(&prog, tu.c_str(), "qsim_jit_pass.cu", 3, headers, names) != NVRTC_SUCCESS) return fail("nvrtcCreateProgram failed");
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+    const nvrtcResult rc = rt.compile(prog, 4, opts);
+    size_t log_n = 0;
+    rt.log_size(prog, &log_n);
+    std::string log(log_n, '\0');
+    if (log_n > 1) rt.log(prog, &log[0]);
+    g_last_log = log;
+    if (rc != NVRTC_SUCCESS) {
+        rt.destroy(&prog);
+        if (std::getenv("QSIM_JIT_DUMP")) std::fprintf(stderr, "%s\n", tu.c_str());
+        return fail(std::string("compile failed: ") + (rt.error_string ? rt.error_string(rc) : "?") + "\n" + log.substr(0, 4000));
+    }
+    auto k = std::make_shared<JitKernel>();
+    size_t cb = 0;
+    rt.cubin_size(prog, &cb);
+    k->cubin.resize(cb);
+    rt.cubin(prog, k->cubin.data());
+    rt.destroy(&prog);
+    k->source = compute;
+    if (needs_device) {
+        cudaError_t e = cudaLibraryLoadData(&k->library, k->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+        if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->kernel, k->library, "qsim_jit_pass");
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(std::string("loading the compiled kernel failed: ") + cudaGetErrorString(e));
+        }
+    }
+    ++g_stats.compiles;
+    g_stats.compile_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    g_stats.last_cubin_bytes = (int64_t)cb;
+    g_cache[key] = k;
+    return k;
+}
+
+size_t jit_copy_cubin(const JitKernel& k, void* out, size_t cap) {
+    if (out && cap) std::memcpy(out, k.cubin.data(), k.cubin.size() < cap ? k.cubin.size() : cap);
+    return k.cubin.size();
+}
+
+cudaError_t jit_launch(JitKernel& k, const PassParams& params, const void* tmap, const void* tmap_keep, const void* tmap_send,
+                       unsigned grid, size_t smem, cudaStream_t stream) {
+    if (!k.kernel) return cudaErrorInvalidDeviceFunction;
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev)) return e;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if (dev >= 0 && dev < 64 && !k.attr_set[dev]) {
+            if (cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k.kernel),
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem))
+                return e;
+            k.attr_set[dev] = true;
+        }
+        ++g_stats.launches;
+    }
+    void* args[] = {const_cast<PassParams*>(&params), const_cast<void*>(tmap), const_cast<void*>(tmap_keep),
+                    const_cast<void*>(tmap_send)};
+    return cudaLaunchKernel(reinterpret_cast<const void*>(k.kernel), dim3(grid), dim3(kComputeThreads), args, smem, stream);
+}
+
+}  // namespace b200
+}  // namespace qsim

@@ -1,0 +1,65 @@
+// Run-time specialisation of the pass kernel (internal header).
+//
+// The ahead-of-time kernel (kernels_pass.cu) INTERPRETS a pass's op list: per op and tile it fetches the record from
+// shared memory, decodes it, jumps through a table and selects on per-slot control masks — about half of the issued
+// instructions of a heavy pass are that bookkeeping (ncu, profiles/ncu_fused_pass_c2_30q_r01.json).  For large states a
+// pass is worth a kernel of its own: jit.cpp turns (PassDesc, op list) into straight-line CUDA C++ for the per-tile
+// compute — layouts, targets, control masks and slot sets are literals, bit flips on register bits are renamings,
+// controls become branches or static slot subsets — wraps it in the SAME skeleton (pass_kernel_body.inc: TMA ring, tile
+// stepping, basis-state input, fused exchange) and compiles it with NVRTC for sm_100a.  Matrix entries stay run-time data
+// (read from the staged op records), so the kernel depends only on the STRUCTURE of the pass: a variational loop that
+// re-runs a circuit with new angles hits the cache.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <string>
+
+#include "pass_desc.h"
+
+namespace qsim {
+namespace b200 {
+
+struct JitKernel;   // a loaded, specialised pass kernel
+
+enum class JitMode : int { Off = 0, Auto = 1, Always = 2 };
+
+// QSIM_JIT=off|auto|always (default auto), QSIM_JIT_MIN_QUBITS (default 26: a pass over 2^26 amplitudes takes ~0.4 ms,
+// a compile ~0.5 s and is cached per pass structure).  Always: every pass, and a compile failure throws (tests).
+JitMode jit_mode();
+int jit_min_qubits();
+void jit_set_mode(JitMode mode, int min_qubits);
+
+// Should this pass run specialised?  (mode, size of the state, NVRTC present)
+bool jit_wanted(const PassDesc& pd);
+
+// CUDA C++ of the specialised per-tile compute for this pass (the generated part only).
+std::string jit_generate_compute(const PassDesc& pd, const DevOp* host_ops);
+// The whole translation unit handed to NVRTC (generated part + the three embedded sources).
+std::string jit_translation_unit(const PassDesc& pd, const DevOp* host_ops);
+
+// Compile (or fetch from the process-wide cache) the kernel of this pass.  Returns nullptr when NVRTC is unavailable or
+// the compile failed in Auto mode (logged once; the caller uses the interpreter kernel); throws in Always mode.
+// needs_device = false only compiles to a cubin (used by the CPU-side build check); such a kernel cannot be launched.
+std::shared_ptr<JitKernel> jit_get_kernel(const PassDesc& pd, const DevOp* host_ops, bool needs_device = true);
+
+// Launch with the interpreter kernel's parameters.
+cudaError_t jit_launch(JitKernel& k, const PassParams& params, const void* tmap, const void* tmap_keep, const void* tmap_send,
+                       unsigned grid, size_t smem, cudaStream_t stream);
+
+// Copies the kernel's cubin (at most cap bytes); returns its size.
+size_t jit_copy_cubin(const JitKernel& k, void* out, size_t cap);
+
+struct JitStats {
+    int64_t compiles = 0, cache_hits = 0, launches = 0, failures = 0;
+    double compile_seconds = 0;
+    int64_t last_cubin_bytes = 0;
+    int last_registers = 0;
+};
+JitStats jit_stats();
+std::string jit_last_log();   // NVRTC log of the last compile (warnings / errors)
+
+}  // namespace b200
+}  // namespace qsim

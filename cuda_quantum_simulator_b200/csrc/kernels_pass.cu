@@ -28,130 +28,13 @@
 #include <cstring>
 #include <mutex>
 
+#include "jit.hpp"
+#include "pass_device.cuh"
+
 namespace qsim {
 namespace b200 {
 
 namespace {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-
-
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-
-// global -> shared bulk copy, completion counted in bytes on `bar`
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-
-// shared -> global bulk copy (bulk async-group completion)
-__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
-                 "r"(smem_u32(smem_src)), "r"(bytes)
-                 : "memory");
-}
-
-// tensor-map (tiled) variants: one instruction moves a whole 5-D box (SASS UTMALDG / UTMASTG)
-__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, const int (&c)[5], uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(smem_u32(smem_dst)),
-        "l"(map), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(smem_u32(bar))
-        : "memory");
-}
-
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const int (&c)[5], const void* smem_src) {
-    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(map),
-                 "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(smem_u32(smem_src))
-                 : "memory");
-}
-
-// coordinates of the box that starts at global amplitude index g
-__device__ __forceinline__ void tma_coords(const PassDesc& pd, uint64_t g, int (&c)[5]) {
-#pragma unroll
-    for (int d = 0; d < 5; ++d) {
-        const uint32_t rb = pd.tma_dim[d].range_bits;
-        const uint64_t v = rb ? ((g >> pd.tma_dim[d].start_bit) & ((1ULL << rb) - 1)) : 0ULL;
-        c[d] = (int)(d == 0 ? v * 2 : v);   // dimension 0 counts doubles
-    }
-}
-
-__device__ __forceinline__ uint64_t instr_offset(const PassDesc& pd, uint32_t q) {
-    uint64_t off = 0;
-    const int box_bits = pd.t - pd.tma_instr_bits;
-#pragma unroll 1
-    for (int b = 0; b < pd.tma_instr_bits; ++b)
-        if ((q >> b) & 1) off |= 1ULL << pd.tile_bits[box_bits + b];
-    return off;
-}
-
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void lds128(uint32_t addr, double& x, double& y) {
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr) : "memory");
-}
-__device__ __forceinline__ void sts128(uint32_t addr, double x, double y) {
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
-}
-__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ double shfl_xor_f64(double v, int lane_mask) {
-    return __shfl_xor_sync(0xffffffffu, v, lane_mask);
-}
-
-struct TileGeom {
-    uint64_t base;  // global amplitude index of the tile's element 0
-};
-
-__device__ __forceinline__ uint64_t tile_base(const PassDesc& pd, uint64_t tau) {
-    uint64_t b = 0;
-#pragma unroll 1
-    for (int s = 0; s < pd.n_segments; ++s) b |= ((tau >> pd.seg[s].src_shift) & pd.seg[s].mask) << pd.seg[s].dst_shift;
-    return b;
-}
-
-__device__ __forceinline__ uint64_t run_offset(const PassDesc& pd, uint32_t run) {
-    uint64_t off = 0;
-#pragma unroll 1
-    for (int b = 0; b < pd.n_high; ++b)
-        if ((run >> b) & 1) off |= 1ULL << pd.tile_bits[pd.L + b];
-    return off;
-}
 
 // ---- op application on the thread's register file -------------------------------------------------
 // Everything below is straight-line code over the kSlots register slots: no per-slot branches, so the
@@ -366,410 +249,139 @@ __device__ __forceinline__ void apply_op(const DevOp& op, uint32_t opcode, uint3
         default: __builtin_unreachable();
     }
 }
-
-}  // namespace
-
-__global__ void __launch_bounds__(kComputeThreads, 1)
-fused_pass_kernel(const __grid_constant__ PassParams P, const __grid_constant__ CUtensorMap tmap,
-                  const __grid_constant__ CUtensorMap tmap_keep, const __grid_constant__ CUtensorMap tmap_send) {
-    extern __shared__ __align__(1024) unsigned char smem[];
+// The interpreter: applies the pass's sweeps to one tile in shared memory (QSIM_COMPUTE_TILE of pass_kernel_body.inc).
+__device__ __forceinline__ void interp_compute_tile(const PassParams& P, unsigned char* tile, uint64_t gbase, uint32_t tid,
+                                                    const DevOp* sops, const double2* eu, const uint16_t* base_tab) {
     const PassDesc& pd = P.pd;
-    const uint32_t tile_bytes = 16u << pd.t;
-    unsigned char* tiles = smem;
-    const int n_stages = P.stages;
-    DevOp* sops = reinterpret_cast<DevOp*>(smem + (size_t)n_stages * tile_bytes);
-    double2* eu = reinterpret_cast<double2*>(sops + pd.n_ops + 1);       // (E_0..E_11, U) of every OP_PHASE, per tile
-    uint64_t* full = reinterpret_cast<uint64_t*>(eu + (size_t)pd.n_phase * 13);
-    // base_tab[sw][tid]: the tile-local index of the thread's slot 0 in sweep sw (tile-invariant)
-    uint16_t* base_tab = reinterpret_cast<uint16_t*>(full + 2 * n_stages);
-
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
-
-    // stage this pass's op list in shared memory (broadcast reads later)
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(P.ops);
-        uint4* dst = reinterpret_cast<uint4*>(sops);
-        const int n16 = pd.n_ops * (int)(sizeof(DevOp) / 16);
-        for (int i = tid; i < n16; i += kComputeThreads) dst[i] = src[i];
-        if (tid < (int)(sizeof(DevOp) / 16)) dst[n16 + tid] = make_uint4(0u, 0u, 0u, 0u);
-    }
+    const uint32_t warp = tid >> 5;
+    double ar[kSlots], ai[kSlots], br[kSlots], bi[kSlots];
+#pragma unroll 1
     for (int sw = 0; sw < pd.n_sweeps; ++sw) {
         const SweepDesc& sd = pd.sweep[sw];
-        uint32_t bl = 0;
-        for (int b = 0; b < sd.nthr; ++b)
-            if ((tid >> b) & 1) bl |= 1u << sd.thr_pos[b];
-        base_tab[sw * kComputeThreads + (int)tid] = (uint16_t)bl;
-        if (sw + 1 == pd.n_sweeps) {
-            // extra row: where the final store puts the thread's slot 0 (the folded flips' affine map, see TailDyn)
-            uint32_t sb = pd.tail_const;
-            for (int j = 0; j < pd.t; ++j)
-                if ((bl >> j) & 1) sb ^= pd.tail_lin[j];
-            base_tab[pd.n_sweeps * kComputeThreads + (int)tid] = (uint16_t)sb;
+        if (sw > 0) __syncthreads();
+        const uint32_t n_active = 1u << sd.nthr;
+        const bool warp_active = (warp << 5) < n_active;
+        const bool last_sweep = (sw + 1 == pd.n_sweeps);
+        const uint32_t xl = last_sweep ? pd.xor_local : 0u;                 // deferred X gates, see the store
+        const int n_tail = last_sweep ? pd.n_tail : 0;                      // trailing bit flips, see the store
+        const bool mapped_load = (sw == 0 && pd.n_head > 0) || sd.n_head > 0;   // folded leading flips, see the load
+        // a load or a store that reaches into other threads' slots: everybody must have loaded before anybody stores
+        const bool permuted_store = (xl != 0u) || (n_tail > 0) || mapped_load;
+        if (!warp_active) {
+            if (permuted_store) __syncthreads();   // keep the barrier count equal across warps
+            continue;
         }
-        if (sw == 0) {
-            // and where the first load finds it (leading flips, inverse map)
-            uint32_t lb = pd.head_const;
-            for (int j = 0; j < pd.t; ++j)
-                if ((bl >> j) & 1) lb ^= pd.head_lin[j];
-            base_tab[(pd.n_sweeps + 1) * kComputeThreads + (int)tid] = (uint16_t)lb;
-        }
-    }
-    if (tid == 0) {
-        if (P.use_tensor_map) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-        for (int s = 0; s < n_stages; ++s) {
-            mbar_init(&full[s], 1);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    const uint64_t n_tiles = P.n_tiles;
-    uint64_t first = blockIdx.x, stride = gridDim.x;
-    // Work items of this CTA.  Without a tile XOR item i is tile first + i*stride.  With one, tiles are
-    // handled in partner pairs (tau, tau ^ xor_tau): items 2j and 2j+1 are the two members of pair
-    // first + j*stride (the pair id is the tile number with the pivot bit of xor_tau squeezed out), each is
-    // written to the other's location, and a tile is only overwritten after its own contents have been loaded
-    // (see the wait before the store below).
-    const uint64_t xor_tau = pd.xor_tau;
-    const int pivot = xor_tau ? 63 - __clzll((long long)xor_tau) : 0;
-    uint64_t n_units = xor_tau ? n_tiles / 2 : n_tiles;
-    // Global base index of a unit = its number deposited into the index bits that are neither tile bits nor the
-    // pivot ("holes").  Stepping to the next unit is an add with the holes filled so carries pass through them.
-    const uint64_t xdep = xor_tau ? tile_base(pd, xor_tau) : 0ULL;   // index XOR between the members of a pair
-    const uint64_t pivot_dep = xor_tau ? tile_base(pd, 1ULL << pivot) : 0ULL;
-    uint64_t holes = pivot_dep;
-    for (int j = 0; j < pd.t; ++j) holes |= 1ULL << pd.tile_bits[j];
-    // Fused exchange: the tiles that leave drain at NVLink speed, the ones that stay at HBM speed; mixing them in one
-    // CTA's three-stage ring makes every third stage wait for a slow drain.  So the grid is split: CTAs [0, send_ctas)
-    // take the leaving tiles, the rest the staying ones (the exchanged bit becomes one more hole with a fixed value).
-    uint64_t class_bits = 0;
-    if (P.redirect && P.send_ctas > 0 && P.send_ctas < (int)gridDim.x && !((xdep >> P.redirect_bit) & 1ULL)) {
-        const bool sender = (int)blockIdx.x < P.send_ctas;
-        first = sender ? blockIdx.x : blockIdx.x - P.send_ctas;
-        stride = sender ? P.send_ctas : gridDim.x - P.send_ctas;
-        n_units /= 2;
-        holes |= 1ULL << P.redirect_bit;
-        class_bits = (uint64_t)(sender ? (P.redirect_keep ^ 1) : P.redirect_keep) << P.redirect_bit;
-    }
-    const uint64_t my_units = first < n_units ? (n_units - first + stride - 1) / stride : 0;
-    const uint64_t n_my = xor_tau ? 2 * my_units : my_units;
-    const uint64_t keep = ((1ULL << pd.n) - 1ULL) & ~holes;
-    auto deposit = [&](uint64_t x) -> uint64_t {
-        uint64_t r = 0;
-        int j = 0;
-        for (int b = 0; b < pd.n; ++b)
-            if ((keep >> b) & 1ULL) { r |= ((x >> j) & 1ULL) << b; ++j; }
-        return r;
-    };
-    const uint64_t ustride = deposit(stride), ufirst = deposit(first) | class_bits;
-    auto next_unit = [&](uint64_t ub) -> uint64_t { return (((ub | holes) + ustride) & keep) | class_bits; };
-    const uint32_t n_runs = 1u << pd.n_high;
-    const uint32_t run_bytes = 16u << pd.L;
-    const uint32_t n_instr = 1u << pd.tma_instr_bits;
-    const uint32_t box_bytes = tile_bytes >> pd.tma_instr_bits;
-    unsigned char* const gstate = reinterpret_cast<unsigned char*>(P.state);
-
-    // ---- TMA duties of the elected thread --------------------------------------------------------------
-    // (executed by every lane of warp 0: lane q issues instruction q, q+32, ...)
-    const uint32_t lane = tid & 31u;
-    auto issue_load = [&](uint64_t i, uint64_t base) {
-        const int s = (int)(i % n_stages);
-        if (lane == 0) mbar_expect_tx(&full[s], tile_bytes);
-        __syncwarp();
-        if (P.use_tensor_map) {
-            for (uint32_t q = lane; q < n_instr; q += 32) {
-                int c[5];
-                tma_coords(pd, base + instr_offset(pd, q), c);
-                tma_load_5d(tiles + (size_t)s * tile_bytes + (size_t)q * box_bytes, &tmap, c, &full[s]);
+        const bool active = tid < n_active;
+        const int slots = 1 << sd.r;
+        const uint32_t base_local = base_tab[sw * kComputeThreads + (int)tid];
+        const uint32_t tile_u32 = smem_u32(tile);
+        const bool full_sweep = (sd.r == kMaxRegBits) && (sd.nthr == kMaxTileBits - kMaxRegBits);
+        if (mapped_load) {
+            // folded leading flips: every slot is read from the pre-image of its index under the flips
+            uint32_t lb;
+            const uint16_t* loff;
+            if (sw == 0 && pd.n_head > 0) {
+                lb = base_tab[(pd.n_sweeps + 1) * kComputeThreads + (int)tid];
+                for (int f = 0; f < pd.n_head_dyn; ++f)
+                    if ((gbase & pd.head_dyn[f].cmask_out) == pd.head_dyn[f].cval_out) lb ^= pd.head_dyn[f].w;
+                loff = pd.load_slot_off;
+            } else {   // a later sweep (no table row: mapped on the fly)
+                lb = sd.head_const;
+                for (int j = 0; j < pd.t; ++j)
+                    if ((base_local >> j) & 1u) lb ^= sd.head_lin[j];
+                loff = sd.load_slot_off;
+            }
+#pragma unroll
+            for (int k = 0; k < kSlots; ++k) {
+                ar[k] = 0.0;
+                ai[k] = 0.0;
+                if (active && k < slots) lds128(tile_u32 + (lb ^ (uint32_t)loff[k]) * 16u, ar[k], ai[k]);
             }
         } else {
-            for (uint32_t run = lane; run < n_runs; run += 32) {
-                const uint64_t g = base + run_offset(pd, run);
-                tma_load_1d(tiles + (size_t)s * tile_bytes + (size_t)run * run_bytes, gstate + g * 16, run_bytes, &full[s]);
-            }
-        }
-    };
-    auto issue_store = [&](uint64_t i, uint64_t base) {
-        const int s = (int)(i % n_stages);
-        if (xor_tau && !(i & 1) && !P.init_basis) {
-            // this tile goes to its partner's location: the partner (item i+1) must have been read first
-            const uint64_t j = i + 1;
-            mbar_wait(&full[(int)(j % n_stages)], (uint32_t)((j / n_stages) & 1));
-        }
-        // fused qubit exchange: the whole tile stays (other buffer, same index) or leaves (partner GPU, bit flipped)
-        const CUtensorMap* smap = &tmap;
-        unsigned char* sdst = gstate;
-        if (P.redirect) {
-            const bool keep = (int)((base >> P.redirect_bit) & 1ULL) == P.redirect_keep;
-            smap = keep ? &tmap_keep : &tmap_send;
-            sdst = reinterpret_cast<unsigned char*>(keep ? P.dst_keep : P.dst_send);
-            if (!keep) base ^= 1ULL << P.redirect_bit;
-        }
-        if (P.use_tensor_map) {
-            for (uint32_t q = lane; q < n_instr; q += 32) {
-                int c[5];
-                tma_coords(pd, base + instr_offset(pd, q), c);
-                tma_store_5d(smap, c, tiles + (size_t)s * tile_bytes + (size_t)q * box_bytes);
-            }
-        } else {
-            for (uint32_t run = lane; run < n_runs; run += 32) {
-                const uint64_t g = base + run_offset(pd, run);
-                tma_store_1d(sdst + g * 16, tiles + (size_t)s * tile_bytes + (size_t)run * run_bytes, run_bytes);
-            }
-        }
-        tma_store_commit();   // every lane commits its own (possibly empty) bulk group
-    };
-
-    // bases of the next item to load (warp 0) and of the item being computed
-    uint64_t load_unit = ufirst, cur_unit = ufirst;
-    uint64_t n_loaded = 0;
-    auto load_next = [&]() {
-        const bool odd = xor_tau && (n_loaded & 1);
-        issue_load(n_loaded, odd ? (load_unit ^ xdep) : load_unit);
-        if (!xor_tau || odd) load_unit = next_unit(load_unit);
-        ++n_loaded;
-    };
-    if (warp == 0 && !P.init_basis) {
-        const uint64_t pre = n_my < (uint64_t)n_stages ? n_my : (uint64_t)n_stages;
-        for (uint64_t i = 0; i < pre; ++i) load_next();
-    }
-    // Basis-state input (P.init_basis): nothing is loaded.  A tile that does not contain |init_index> is all zero
-    // before and after any op: those locations are zero-filled linearly by the whole grid (the memset this pass
-    // replaces, minus the one tile below); the tile that does contain it is generated in shared memory and takes the
-    // normal path.
-    uint64_t tile_mask = 0;
-    for (int j = 0; j < pd.t; ++j) tile_mask |= 1ULL << pd.tile_bits[j];
-    const uint64_t init_tile = P.init_index & ~tile_mask;
-    uint32_t init_local = 0;
-    for (int j = 0; j < pd.t; ++j) init_local |= (uint32_t)((P.init_index >> pd.tile_bits[j]) & 1ULL) << j;
-    if (P.init_basis == 1) {   // (init_basis == 2: the caller has zero-filled the buffer, e.g. with cudaMemsetAsync)
-        const uint64_t dest_tile = init_tile ^ xdep;   // where that tile is written (deferred X gates on outer bits)
-        const uint64_t n_amps = 1ULL << pd.n;
-        uint4* out = reinterpret_cast<uint4*>(P.state);
-        if (n_amps >= 4096 && pd.t == kMaxTileBits) {
-            // 64 KiB at a time, as 1-D bulk copies from an all-zero stage (one instruction per chunk); the few chunks
-            // that contain rows of the special tile are written element by element around them
-            uint4* z = reinterpret_cast<uint4*>(tiles);
-            for (uint32_t e = tid; e < 65536 / 16; e += kComputeThreads) z[e] = make_uint4(0u, 0u, 0u, 0u);
-            fence_proxy_async();
-            __syncthreads();
-            const uint64_t n_chunks = n_amps >> 12;
-            for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-                const bool has_special = ((((c << 12) ^ dest_tile) & ~tile_mask) >> 12) == 0;   // (uniform)
-                if (has_special) {
-                    for (uint32_t e = tid; e < 4096; e += kComputeThreads) {
-                        const uint64_t idx = (c << 12) + e;
-                        if ((idx & ~tile_mask) != dest_tile) out[idx] = make_uint4(0u, 0u, 0u, 0u);
-                    }
-                } else if (tid == 0) {
-                    tma_store_1d(gstate + (c << 16), tiles, 65536);
-                    tma_store_commit();
-                }
-            }
-            if (tid == 0) tma_store_wait_all();   // the stage is reused below
-            __syncthreads();
-        } else {
-            const uint64_t step = (uint64_t)gridDim.x * kComputeThreads;
-            for (uint64_t idx = (uint64_t)blockIdx.x * kComputeThreads + tid; idx < n_amps; idx += step)
-                if ((idx & ~tile_mask) != dest_tile) out[idx] = make_uint4(0u, 0u, 0u, 0u);
-        }
-    }
-
-    double ar[kSlots], ai[kSlots], br[kSlots], bi[kSlots];
-    // Basis-state input: only the item that holds |init_index> has anything to do — go straight to it
-    uint64_t i_begin = 0, i_end = n_my;
-    if (P.init_basis) {
-        uint64_t ub = init_tile;   // its unit: the member of the pair whose pivot bit is clear
-        const bool odd = xor_tau && (ub & pivot_dep);
-        if (odd) ub ^= xdep;
-        uint64_t u = 0;            // unit number = the base with the holes squeezed out
-        int j = 0;
-        for (int b = 0; b < pd.n; ++b)
-            if ((keep >> b) & 1ULL) { u |= ((ub >> b) & 1ULL) << j; ++j; }
-        i_end = 0;
-        if (u < n_units && u >= first && (u - first) % stride == 0 && !((P.init_index >> pd.n) != 0)) {
-            const uint64_t iu = (u - first) / stride;
-            i_begin = xor_tau ? 2 * iu + (odd ? 1 : 0) : iu;
-            i_end = i_begin + 1;
-            cur_unit = ub;
-        }
-    }
-    for (uint64_t i = i_begin; i < i_end; ++i) {
-        const int s = (int)(i % n_stages);
-        const uint32_t parity = (uint32_t)((i / n_stages) & 1);
-        const bool odd_item = xor_tau && (i & 1);
-        const uint64_t tbase = odd_item ? (cur_unit ^ xdep) : cur_unit;
-        if (!xor_tau || odd_item) cur_unit = next_unit(cur_unit);
-        const uint64_t gbase = tbase | P.hi_bits;
-        unsigned char* tile = tiles + (size_t)s * tile_bytes;
-        if (P.init_basis) {
-            if (tbase != init_tile) continue;   // (uniform over the CTA) zero-filled above
-            uint4* z = reinterpret_cast<uint4*>(tile);
-            for (uint32_t e = tid; e < tile_bytes / 16; e += kComputeThreads) z[e] = make_uint4(0u, 0u, 0u, 0u);
-            __syncthreads();
-            if (tid == 0) reinterpret_cast<double2*>(z)[init_local] = make_double2(1.0, 0.0);
-            __syncthreads();
-        }
-        if (pd.n_phase > 0) {
-            // factors of the fused diagonal runs that depend on index bits outside the tile: one (op, factor) per thread
-            __syncthreads();   // the previous tile's readers of eu are done
-            for (int idx = (int)tid; idx < pd.n_ops * 13; idx += kComputeThreads) {
-                const int o = idx / 13, e = idx - o * 13;
-                const DevOp& op = sops[o];
-                if (op.kind != OP_PHASE) continue;
-                const uint16_t* starts = reinterpret_cast<const uint16_t*>(op.m);
-                const PhaseTerm* terms = P.phase_terms + op.cval_out;
-                double fr = 1.0, fi = 0.0;
-                for (int k = starts[e]; k < starts[e + 1]; ++k) {
-                    const PhaseTerm t = terms[k];
-                    bool on = (gbase >> t.o) & 1;
-                    if (t.kind == 2) on = on && ((gbase >> t.j) & 1);
-                    if (on) { const double r = fr * t.fr - fi * t.fi; fi = fr * t.fi + fi * t.fr; fr = r; }
-                }
-                eu[(size_t)op.tmask_out * 13 + e] = make_double2(fr, fi);
-            }
-            __syncthreads();
-        }
-        if (!P.init_basis) mbar_wait(&full[s], parity);
-
-#pragma unroll 1
-        for (int sw = 0; sw < pd.n_sweeps; ++sw) {
-            const SweepDesc& sd = pd.sweep[sw];
-            if (sw > 0) __syncthreads();
-            const uint32_t n_active = 1u << sd.nthr;
-            const bool warp_active = (warp << 5) < n_active;
-            const bool last_sweep = (sw + 1 == pd.n_sweeps);
-            const uint32_t xl = last_sweep ? pd.xor_local : 0u;                 // deferred X gates, see the store
-            const int n_tail = last_sweep ? pd.n_tail : 0;                      // trailing bit flips, see the store
-            const bool mapped_load = (sw == 0 && pd.n_head > 0) || sd.n_head > 0;   // folded leading flips, see the load
-            // a load or a store that reaches into other threads' slots: everybody must have loaded before anybody stores
-            const bool permuted_store = (xl != 0u) || (n_tail > 0) || mapped_load;
-            if (!warp_active) {
-                if (permuted_store) __syncthreads();   // keep the barrier count equal across warps
-                continue;
-            }
-            const bool active = tid < n_active;
-            const int slots = 1 << sd.r;
-            const uint32_t base_local = base_tab[sw * kComputeThreads + (int)tid];
-            const uint32_t tile_u32 = smem_u32(tile);
-            const bool full_sweep = (sd.r == kMaxRegBits) && (sd.nthr == kMaxTileBits - kMaxRegBits);
-            if (mapped_load) {
-                // folded leading flips: every slot is read from the pre-image of its index under the flips
-                uint32_t lb;
-                const uint16_t* loff;
-                if (sw == 0 && pd.n_head > 0) {
-                    lb = base_tab[(pd.n_sweeps + 1) * kComputeThreads + (int)tid];
-                    for (int f = 0; f < pd.n_head_dyn; ++f)
-                        if ((gbase & pd.head_dyn[f].cmask_out) == pd.head_dyn[f].cval_out) lb ^= pd.head_dyn[f].w;
-                    loff = pd.load_slot_off;
-                } else {   // a later sweep (no table row: mapped on the fly)
-                    lb = sd.head_const;
-                    for (int j = 0; j < pd.t; ++j)
-                        if ((base_local >> j) & 1u) lb ^= sd.head_lin[j];
-                    loff = sd.load_slot_off;
-                }
+            const uint32_t my_addr = tile_u32 + base_local * 16u;
+            if (full_sweep) {
+#pragma unroll
+                for (int k = 0; k < kSlots; ++k) lds128(my_addr + (uint32_t)sd.slot_off[k] * 16u, ar[k], ai[k]);
+            } else {
 #pragma unroll
                 for (int k = 0; k < kSlots; ++k) {
                     ar[k] = 0.0;
                     ai[k] = 0.0;
-                    if (active && k < slots) lds128(tile_u32 + (lb ^ (uint32_t)loff[k]) * 16u, ar[k], ai[k]);
+                    if (active && k < slots) lds128(my_addr + (uint32_t)sd.slot_off[k] * 16u, ar[k], ai[k]);
                 }
+            }
+        }
+        const uint32_t ops_u32 = smem_u32(sops);
+        // the interpreter: fetch() finds the next op that applies to this tile (ops whose controls outside the
+        // tile fail are skipped), apply_op() alternates between the two register files
+        int o = sd.op_begin;
+        const int o_end = sd.op_end;
+        uint32_t opcode = 0, sm = 0;
+        auto fetch = [&]() -> bool {
+            if (o >= o_end) return false;
+            // first 16 bytes of the record: kind|thome|tbit|opcode, slotmask|tslots, cmask_thr, cval_thr
+            const uint4 hdr = lds_u4(ops_u32 + (uint32_t)o * (uint32_t)sizeof(DevOp));
+            opcode = hdr.x >> 24;
+            // an op whose controls outside the tile fail becomes a register-file copy (no extra control-flow
+            // edge around apply_op: that edge is what made the compiler copy the file at every loop header)
+            const bool skip = (opcode & 0x80u) && (gbase & sops[o].cmask_out) != sops[o].cval_out;
+            opcode = skip ? kOpcodeCopy : (opcode & 0x7fu);
+            sm = ((tid & hdr.z) == hdr.w) ? (hdr.y & 0xffffu) : 0u;
+            return true;
+        };
+        bool in_b = false;
+#pragma unroll 1
+        for (;;) {
+            if (!fetch()) break;
+            apply_op(sops[o], opcode, sm, tid, gbase, reinterpret_cast<const double2*>(P.phase_tables), eu, sd, base_local, ar, ai, br, bi);
+            ++o;
+            if (!fetch()) { in_b = true; break; }
+            apply_op(sops[o], opcode, sm, tid, gbase, reinterpret_cast<const double2*>(P.phase_tables), eu, sd, base_local, br, bi, ar, ai);
+            ++o;
+        }
+        // The pass's index permutations ride on the last sweep's store: the folded trailing bit flips (an affine
+        // map of the tile-local index, see TailDyn), then the deferred X gates (l ^= xor_local).  The targets are
+        // other threads' slots — and with folded LEADING flips this sweep's load read other threads' slots — hence
+        // the barrier: everybody has finished loading before anybody stores.
+        if (permuted_store) __syncthreads();
+        {
+            uint32_t l[kSlots];
+            if (last_sweep) {
+                uint32_t sb = base_tab[pd.n_sweeps * kComputeThreads + (int)tid] ^ xl;
+                for (int f = 0; f < pd.n_dyn; ++f)   // flips controlled from outside the tile: the same for the whole tile
+                    if ((gbase & pd.dyn[f].cmask_out) == pd.dyn[f].cval_out) sb ^= pd.dyn[f].w;
+#pragma unroll
+                for (int k = 0; k < kSlots; ++k) l[k] = tile_u32 + (sb ^ (uint32_t)pd.store_slot_off[k]) * 16u;
             } else {
-                const uint32_t my_addr = tile_u32 + base_local * 16u;
+#pragma unroll
+                for (int k = 0; k < kSlots; ++k) l[k] = tile_u32 + (base_local ^ (uint32_t)sd.slot_off[k]) * 16u;
+            }
+            // (the result sits in whichever register file the last op wrote)
+            auto store = [&](const double (&sr)[kSlots], const double (&si)[kSlots]) {
                 if (full_sweep) {
 #pragma unroll
-                    for (int k = 0; k < kSlots; ++k) lds128(my_addr + (uint32_t)sd.slot_off[k] * 16u, ar[k], ai[k]);
+                    for (int k = 0; k < kSlots; ++k) sts128(l[k], sr[k], si[k]);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < kSlots; ++k) {
-                        ar[k] = 0.0;
-                        ai[k] = 0.0;
-                        if (active && k < slots) lds128(my_addr + (uint32_t)sd.slot_off[k] * 16u, ar[k], ai[k]);
-                    }
+                    for (int k = 0; k < kSlots; ++k)
+                        if (active && k < slots) sts128(l[k], sr[k], si[k]);
                 }
-            }
-            const uint32_t ops_u32 = smem_u32(sops);
-            // the interpreter: fetch() finds the next op that applies to this tile (ops whose controls outside the
-            // tile fail are skipped), apply_op() alternates between the two register files
-            int o = sd.op_begin;
-            const int o_end = sd.op_end;
-            uint32_t opcode = 0, sm = 0;
-            auto fetch = [&]() -> bool {
-                if (o >= o_end) return false;
-                // first 16 bytes of the record: kind|thome|tbit|opcode, slotmask|tslots, cmask_thr, cval_thr
-                const uint4 hdr = lds_u4(ops_u32 + (uint32_t)o * (uint32_t)sizeof(DevOp));
-                opcode = hdr.x >> 24;
-                // an op whose controls outside the tile fail becomes a register-file copy (no extra control-flow
-                // edge around apply_op: that edge is what made the compiler copy the file at every loop header)
-                const bool skip = (opcode & 0x80u) && (gbase & sops[o].cmask_out) != sops[o].cval_out;
-                opcode = skip ? kOpcodeCopy : (opcode & 0x7fu);
-                sm = ((tid & hdr.z) == hdr.w) ? (hdr.y & 0xffffu) : 0u;
-                return true;
             };
-            bool in_b = false;
-#pragma unroll 1
-            for (;;) {
-                if (!fetch()) break;
-                apply_op(sops[o], opcode, sm, tid, gbase, P.phase_tables, eu, sd, base_local, ar, ai, br, bi);
-                ++o;
-                if (!fetch()) { in_b = true; break; }
-                apply_op(sops[o], opcode, sm, tid, gbase, P.phase_tables, eu, sd, base_local, br, bi, ar, ai);
-                ++o;
-            }
-            // The pass's index permutations ride on the last sweep's store: the folded trailing bit flips (an affine
-            // map of the tile-local index, see TailDyn), then the deferred X gates (l ^= xor_local).  The targets are
-            // other threads' slots — and with folded LEADING flips this sweep's load read other threads' slots — hence
-            // the barrier: everybody has finished loading before anybody stores.
-            if (permuted_store) __syncthreads();
-            {
-                uint32_t l[kSlots];
-                if (last_sweep) {
-                    uint32_t sb = base_tab[pd.n_sweeps * kComputeThreads + (int)tid] ^ xl;
-                    for (int f = 0; f < pd.n_dyn; ++f)   // flips controlled from outside the tile: the same for the whole tile
-                        if ((gbase & pd.dyn[f].cmask_out) == pd.dyn[f].cval_out) sb ^= pd.dyn[f].w;
-#pragma unroll
-                    for (int k = 0; k < kSlots; ++k) l[k] = tile_u32 + (sb ^ (uint32_t)pd.store_slot_off[k]) * 16u;
-                } else {
-#pragma unroll
-                    for (int k = 0; k < kSlots; ++k) l[k] = tile_u32 + (base_local ^ (uint32_t)sd.slot_off[k]) * 16u;
-                }
-                // (the result sits in whichever register file the last op wrote)
-                auto store = [&](const double (&sr)[kSlots], const double (&si)[kSlots]) {
-                    if (full_sweep) {
-#pragma unroll
-                        for (int k = 0; k < kSlots; ++k) sts128(l[k], sr[k], si[k]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < kSlots; ++k)
-                            if (active && k < slots) sts128(l[k], sr[k], si[k]);
-                    }
-                };
-                if (in_b) store(br, bi); else store(ar, ai);
-            }
-        }
-        // make the generic-proxy writes visible to the bulk-copy engine; then the elected thread stores
-        // this tile and refills the stage whose store (tile i-1) has drained
-        fence_proxy_async();
-        __syncthreads();
-        if (warp == 0) {
-            issue_store(i, tbase ^ xdep);
-            if (!P.init_basis && i >= 1 && n_loaded < n_my) {
-                tma_store_wait_read_1();   // all but this lane's newest store group have finished reading shared memory
-                __syncwarp();              // ... for every lane: the stage of tile i-1 is free
-                load_next();               // item (i - 1) + n_stages
-            }
-        }
-    }
-    if (warp == 0) {
-        tma_store_wait_all();
-        if (P.redirect) {
-            // half of the tiles went to the partner GPU's memory through the async proxy: order those writes before
-            // anything the partner is told after this kernel (the ranks' barrier follows in the stream)
-            asm volatile("fence.proxy.async;" ::: "memory");
-            __threadfence_system();
+            if (in_b) store(br, bi); else store(ar, ai);
         }
     }
 }
+
+}  // namespace
+
+#define QSIM_PASS_KERNEL fused_pass_kernel
+#define QSIM_COMPUTE_TILE interp_compute_tile
+#define QSIM_KERNEL_LINKAGE
+#include "pass_kernel_body.inc"
+#undef QSIM_PASS_KERNEL
+#undef QSIM_COMPUTE_TILE
+#undef QSIM_KERNEL_LINKAGE
+
 
 // worst case with three full stages must fit (pick_stages never has to go below the three the partner-tile store needs)
 static_assert(3 * (16 << kMaxTileBits) + (kMaxOpsPerPass + 1) * sizeof(DevOp) + kMaxPhaseOps * 13 * sizeof(double2) +
@@ -843,7 +455,8 @@ cudaError_t ensure_smem_optin() {
 
 }  // namespace
 
-cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t stream) {
+cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t stream, const DevOp* host_ops,
+                        std::shared_ptr<JitKernel>* jit_slot, char* tried_slot) {
     PassParams params = params_in;
     alignas(64) CUtensorMap tmap, tmap_keep, tmap_send;
     std::memset(&tmap, 0, sizeof(tmap));
@@ -870,6 +483,15 @@ cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t s
         int send = (int)(grid / 3);
         if (const char* e = std::getenv("QSIM_SEND_CTAS")) send = std::atoi(e);
         if (send > 0 && send < (int)grid) params.send_ctas = send;
+    }
+    // a kernel specialised for this pass's structure (large states; compiled once per structure, see jit.hpp)
+    if (params.use_tensor_map && (host_ops || params.pd.n_ops == 0)) {
+        std::shared_ptr<JitKernel> local, *slot = jit_slot ? jit_slot : &local;
+        if (!*slot && !(tried_slot && *tried_slot) && jit_wanted(params.pd)) {
+            *slot = jit_get_kernel(params.pd, host_ops);
+            if (tried_slot) *tried_slot = 1;
+        }
+        if (*slot) return jit_launch(**slot, params, &tmap, &tmap_keep, &tmap_send, (unsigned)grid, smem, stream);
     }
     fused_pass_kernel<<<(unsigned)grid, kComputeThreads, smem, stream>>>(params, tmap, tmap_keep, tmap_send);
     return cudaGetLastError();

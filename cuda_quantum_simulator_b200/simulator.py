@@ -31,10 +31,41 @@ class CompiledCircuit:
         _lib.lib().qsim_program_describe(self._h, buf, need)
         return buf.value.decode()
 
+    def jit_source(self, pass_index: int = 0, whole_unit: bool = False) -> str:
+        """CUDA C++ generated for one pass (the run-time specialised kernel); needs no GPU."""
+        need = _lib.lib().qsim_program_jit_source(self._h, int(pass_index), int(whole_unit), None, 0)
+        buf = ctypes.create_string_buffer(need)
+        _lib.lib().qsim_program_jit_source(self._h, int(pass_index), int(whole_unit), buf, need)
+        return buf.value.decode()
+
+    def jit_compile(self, pass_index: int = 0, want_cubin: bool = False):
+        """NVRTC-compiles one pass's kernel to an sm_100a cubin without loading it (no GPU needed).  Returns the cubin
+        size, or the cubin bytes with want_cubin."""
+        nb = c_int64()
+        _lib.check(_lib.lib().qsim_program_jit_compile(self._h, int(pass_index), byref(nb), None, 0))
+        if not want_cubin:
+            return nb.value
+        buf = ctypes.create_string_buffer(nb.value)
+        _lib.check(_lib.lib().qsim_program_jit_compile(self._h, int(pass_index), byref(nb), buf, nb.value))
+        return buf.raw
+
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
             _lib.lib().qsim_program_destroy(self._h)
             self._h = c_void_p()
+
+
+def jit_set_mode(mode, min_qubits: int = 0):
+    """mode: "off" | "auto" | "always" (or 0 / 1 / 2); see qsim_jit_set_mode in include/qsim_b200.h."""
+    m = {"off": 0, "auto": 1, "always": 2}.get(mode, mode)
+    _lib.check(_lib.lib().qsim_jit_set_mode(int(m), int(min_qubits)))
+
+
+def jit_stats() -> dict:
+    out = (c_int64 * 8)()
+    _lib.check(_lib.lib().qsim_jit_stats(out))
+    return {"compiles": out[0], "cache_hits": out[1], "launches": out[2], "failures": out[3], "compile_seconds": out[4] / 1e6,
+            "last_cubin_bytes": out[5], "mode": ("off", "auto", "always")[out[6]], "min_qubits": out[7]}
 
 
 class Simulator:

@@ -106,6 +106,23 @@ QSIM_API void qsim_program_destroy(qsim_program_t* p);
 /* info[0]=passes, [1]=ops after merging, [2]=gates, [3]=sweeps (total), [4]=tile bits of pass 0,
  * [5]=local qubits, [6]=X frame left on the global qubits (bit q - n_local): the caller owns it */
 QSIM_API qsim_status_t qsim_program_info(const qsim_program_t* p, int64_t info[8]);
+/* ---- Run-time specialised pass kernels (additive; the reference launches one fixed kernel per gate,
+ * src/Simulator.cu:48-154).  For large states every pass gets a kernel generated from its op list and compiled with
+ * NVRTC for sm_100a, cached by the STRUCTURE of the pass (matrix entries stay run-time data).
+ * mode: 0 = never (always the interpreter kernel), 1 = passes over >= min_qubits local qubits (default, 26),
+ * 2 = every pass and a failed compile is an error.  min_qubits <= 0 keeps the current threshold.
+ * Environment: QSIM_JIT=off|auto|always, QSIM_JIT_MIN_QUBITS. */
+QSIM_API qsim_status_t qsim_jit_set_mode(int mode, int min_qubits);
+/* out[0]=kernels compiled, [1]=cache hits, [2]=specialised launches, [3]=failed compiles, [4]=compile time (us),
+ * [5]=size of the last cubin, [6]=mode, [7]=min_qubits */
+QSIM_API qsim_status_t qsim_jit_stats(int64_t out[8]);
+/* CUDA C++ generated for pass `pass` of a compiled program (whole_unit != 0: the full translation unit handed to
+ * NVRTC).  Returns bytes needed incl. NUL; needs no GPU. */
+QSIM_API size_t qsim_program_jit_source(const qsim_program_t* p, int pass, int whole_unit, char* buf, size_t cap);
+/* Compiles that pass's kernel to an sm_100a cubin without loading it (needs NVRTC, no GPU): the build check of the
+ * generated code.  cubin_out (optional, cap bytes) receives the image. */
+QSIM_API qsim_status_t qsim_program_jit_compile(const qsim_program_t* p, int pass, int64_t* cubin_bytes, void* cubin_out,
+                                                size_t cap);
 /* Human-readable plan (passes, tile qubits, sweeps).  Returns bytes needed incl. NUL. */
 QSIM_API size_t qsim_program_describe(const qsim_program_t* p, char* buf, size_t cap);
 

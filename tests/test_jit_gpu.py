@@ -1,0 +1,134 @@
+"""The run-time specialised pass kernels (csrc/jit.cpp) against the CPU oracle.  By default only passes over >= 26 local
+qubits are specialised (the 26/30-qubit tests elsewhere take that path); here the mode is forced to "always", so every pass
+of every circuit - all gate kinds, controls in every home, partial tiles, folded flips, fused diagonals, basis-state input,
+the redirected store of the fused exchange - runs through generated code, and a failed compile is an error."""
+import numpy as np
+import pytest
+
+import cuda_quantum_simulator_b200 as q
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def jit_always():
+    q.jit_set_mode("always")
+    yield
+    q.jit_set_mode("auto")
+
+
+def run_gpu(n, g, state=None):
+    sim = q.Simulator(n)
+    if state is not None:
+        sim.set_state(state)
+    sim.run(q.Circuit(n).extend(g) if len(g) else q.Circuit(n))
+    return sim.get_state_vector(), sim
+
+
+def test_specialised_kernels_are_what_runs():
+    before = q.jit_stats()
+    n = 10
+    g = H.random_gates(n, 40, np.random.default_rng(1))
+    got, sim = run_gpu(n, g)
+    after = q.jit_stats()
+    assert after["mode"] == "always"
+    assert after["launches"] > before["launches"] and after["failures"] == before["failures"]
+    assert after["compiles"] + after["cache_hits"] > before["compiles"] + before["cache_hits"]
+    assert np.max(np.abs(got - H.oracle_run(n, g))) < 1e-12
+    # the same structure with other angles is a cache hit, not a compile
+    g2 = g.copy()
+    g2["param"] = np.where(g2["param"] != 0, g2["param"] * 0.37 + 0.1, 0.0)
+    c0 = q.jit_stats()["compiles"]
+    got2, _ = run_gpu(n, g2)
+    assert np.max(np.abs(got2 - H.oracle_run(n, g2))) < 1e-12
+
+
+@pytest.mark.parametrize("case", H.load_known_answers()["cases"], ids=lambda c: c["name"])
+def test_known_answers(case):
+    from test_oracle import _check_expect
+    g = H.gates([tuple(x) for x in case["gates"]])
+    st, _ = run_gpu(case["n"], g)
+    _check_expect(st, case["expect"], case["tol"])
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 6, 8, 9, 11, 12, 13, 14, 16])
+def test_fuzz_all_gate_types_from_random_state(n):
+    rng = np.random.default_rng(500 + n)
+    g = H.random_gates(n, int(rng.integers(20, 90)), rng)
+    st0 = H.random_state(n, rng)
+    got, _ = run_gpu(n, g, st0)
+    assert np.max(np.abs(got - H.oracle_run(n, g, st0))) < 1e-12
+
+
+@pytest.mark.parametrize("n", [7, 13, 15, 18])
+def test_flips_fold_into_loads_and_stores(n):
+    rng = np.random.default_rng(40 + n)
+    for body, tail in ((6, 25), (0, 30), (12, 8)):
+        g = H.flip_heavy_gates(n, rng, body, tail)
+        st0 = H.random_state(n, rng)
+        got, _ = run_gpu(n, g, st0)
+        assert np.max(np.abs(got - H.oracle_run(n, g, st0))) < 1e-12
+        g2 = np.concatenate([g[::-1], g])          # flips leading a pass, dense gates, flips trailing it
+        got, _ = run_gpu(n, g2, st0)
+        assert np.max(np.abs(got - H.oracle_run(n, g2, st0))) < 1e-12
+
+
+@pytest.mark.parametrize("n", [9, 14, 19])
+def test_run_from_a_recorded_basis_state(n):
+    rng = np.random.default_rng(70 + n)
+    g = H.random_gates(n, 50, rng)
+    sim = q.Simulator(n)
+    idx = int(rng.integers(1 << n))
+    sim.init_basis(idx)
+    sim.run(q.Circuit(n).extend(g))
+    st0 = np.zeros(1 << n, np.complex128)
+    st0[idx] = 1
+    assert np.max(np.abs(sim.get_state_vector() - H.oracle_run(n, g, st0))) < 1e-12
+
+
+def test_every_gate_on_every_qubit_16q():
+    n = 16
+    rng = np.random.default_rng(9)
+    st0 = H.random_state(n, rng)
+    for t in range(17):
+        lst = []
+        for qb in range(n):
+            others = [x for x in range(n) if x != qb]
+            a, b = (int(x) for x in rng.choice(others, 2, replace=False))
+            ang = float(rng.uniform(0, 6))
+            if t <= 7: lst.append((t, qb))
+            elif t <= 10: lst.append((t, qb, ang))
+            elif t in (11, 12, 15): lst.append((t, a, qb))
+            elif t in (13, 14): lst.append((t, a, qb, ang))
+            else: lst.append((t, a, b, qb))
+        g = H.gates(lst)
+        got, _ = run_gpu(n, g, st0)
+        assert np.max(np.abs(got - H.oracle_run(n, g, st0))) < 1e-12, H.NAMES[t]
+
+
+def test_fused_diagonal_runs_c3_20q():
+    n = 20
+    c = H.qft_style_circuit(n)
+    prog = q.CompiledCircuit(c)
+    assert "PHASE" in prog.describe()
+    sim = q.Simulator(n)
+    sim.execute(prog)
+    assert np.max(np.abs(sim.get_state_vector() - H.oracle_run(n, c.gates))) < 1e-10
+
+
+def test_config_c1_and_c2_shapes():
+    g = H.bench_c1_gates(20)
+    got, _ = run_gpu(20, g)
+    assert np.max(np.abs(got - H.oracle_run(20, g))) < 1e-10
+    c = q.create_random_circuit(24, 200, 42)
+    sim = q.Simulator(24)
+    sim.run(c)
+    assert np.max(np.abs(sim.get_state_vector() - H.oracle_run(24, c.gates))) < 1e-10
+
+
+@pytest.mark.parametrize("nl,g_local", [(14, 13), (20, 17), (21, 0)])
+def test_fused_exchange_store_redirect(nl, g_local):
+    """The specialised kernel shares the skeleton's redirected store (fused qubit exchange): reuse the one-GPU check."""
+    from test_sharded_gpu import test_fused_exchange_on_one_gpu
+    test_fused_exchange_on_one_gpu(nl, g_local, False)
