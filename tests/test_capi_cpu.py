@@ -82,8 +82,13 @@ def test_no_gpu_means_error_not_fallback():
         pytest.skip("GPU present")
     with pytest.raises(q.QsimError, match="no CPU fallback"):
         q.Simulator(3)
-    with pytest.raises(q.QsimError):
-        q.CompiledCircuit(q.Circuit(3).h(0))
+    # compiling a circuit is host logic (passes, sweeps, generated kernel source) and needs no device; there is simply
+    # nothing to execute it on: every object that owns amplitudes refuses to exist
+    prog = q.CompiledCircuit(q.Circuit(3).h(0))
+    assert prog.n_passes == 1 and "jit_compute_tile" in prog.jit_source(0)
+    for make in (lambda: q.NoisySimulator(3), lambda: q.BatchedSimulator(3, 4), lambda: q.DensityMatrixSimulator(2)):
+        with pytest.raises(q.QsimError):
+            make()
 
 
 def test_product_never_touches_the_oracle():
