@@ -1,9 +1,12 @@
 #include "engine.hpp"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "kernels.cuh"
 #include "qsim/constants.hpp"
@@ -159,8 +162,16 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
             CUDA_CHECK(cudaEventRecord(e0, stream_));
         }
         const size_t pass_i = (size_t)(&pd - p.passes.data());
+        // NVTX range per pass (visible in Nsight Systems / ncu --nvtx; a no-op costing nanoseconds when no tool is attached)
+        char label[96];
+        std::snprintf(label, sizeof(label), "qsim pass %zu/%zu: %d ops, %d sweeps, t=%d%s", pass_i + 1, p.passes.size(), pd.n_ops,
+                      pd.n_sweeps, pd.t, prm.redirect ? ", fused exchange" : (prm.init_basis ? ", basis-state input" : ""));
+        struct NvtxScope { explicit NvtxScope(const char* l) { nvtxRangePushA(l); } ~NvtxScope() { nvtxRangePop(); } };
         if (p.jit.size() != p.passes.size()) { p.jit.assign(p.passes.size(), nullptr); p.jit_tried.assign(p.passes.size(), 0); }
-        CUDA_CHECK(launch_pass(prm, num_sms_, stream_, p.ops.data() + pd.op_offset, &p.jit[pass_i], &p.jit_tried[pass_i]));
+        {
+            NvtxScope range(label);
+            CUDA_CHECK(launch_pass(prm, num_sms_, stream_, p.ops.data() + pd.op_offset, &p.jit[pass_i], &p.jit_tried[pass_i]));
+        }
         ++launches_;
         if (timing_) {
             CUDA_CHECK(cudaEventRecord(e1, stream_));

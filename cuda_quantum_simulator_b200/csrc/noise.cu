@@ -86,14 +86,14 @@ void philox_uniforms(uint32_t seed, uint64_t traj, uint64_t event, double& u0, d
 
 void run_trajectories(cuDoubleComplex* states, int n, int64_t batch, const std::vector<b200::TrajItem>& items,
                       const std::vector<b200::TrajEvent>& events, uint32_t seed, uint64_t first_block, int num_sms,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, double* d_avg = nullptr) {
     if (items.empty()) return;
     CudaMemory<b200::TrajItem> d_items(items.size());
     d_items.copyFromHost(items.data(), items.size());
     CudaMemory<b200::TrajEvent> d_events(events.size() ? events.size() : 1);
     if (!events.empty()) d_events.copyFromHost(events.data(), events.size());
     b200::launch_trajectories(states, n, batch, d_items.get(), (int)items.size(), d_events.get(), (int)events.size(), seed, 0,
-                              first_block, num_sms, stream);
+                              first_block, num_sms, stream, d_avg);
     CUDA_CHECK(cudaStreamSynchronize(stream));   // the item / event buffers die with this scope
 }
 
@@ -183,7 +183,7 @@ void NoisySimulator::applyEvents(const std::vector<NoiseChannel>& channels) {
     (void)k;
     for (size_t e = 0; e < events.size(); ++e) {
         double u0, u1;
-        philox_uniforms(seed_, 0, noise_block_ * (uint64_t)events.size() + e, u0, u1);
+        philox_uniforms(seed_, 0, (noise_block_ << 16) | (uint64_t)e, u0, u1);
         const b200::TrajEvent& ev = events[e];
         b200::LogicalOp op{};
         op.target = ev.qubit;
@@ -279,6 +279,7 @@ BatchedSimulator::BatchedSimulator(int num_qubits, int batch_size)
     CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev));
     d_states_ = CudaMemory<cuDoubleComplex>(static_cast<size_t>(batch_size) * state_size_);
+    d_avg_ = CudaMemory<double>(state_size_);
     std::random_device rd;
     rng_.seed(rd());
     seed_ = rng_();
@@ -303,6 +304,7 @@ void BatchedSimulator::setSeed(unsigned int seed) {
 void BatchedSimulator::reset() {
     b200::launch_batched_init(d_states_.get(), num_qubits_, batch_size_, num_sms_, nullptr);
     CUDA_CHECK(cudaStreamSynchronize(nullptr));
+    avg_valid_ = false;
 }
 
 void BatchedSimulator::run(const Circuit& circuit) {
@@ -313,16 +315,20 @@ void BatchedSimulator::run(const Circuit& circuit) {
     const bool noisy = noise_model_.hasNoise();
     const auto events = noisy ? flatten(noise_model_.getChannels(), num_qubits_) : std::vector<b200::TrajEvent>{};
     const auto items = build_items(recs, noisy);
-    run_trajectories(d_states_.get(), num_qubits_, batch_size_, items, events, seed_, noise_block_, num_sms_, nullptr);
+    // the kernel's epilogue leaves the average probabilities of the final states in d_avg_ (no second pass over the batch)
+    run_trajectories(d_states_.get(), num_qubits_, batch_size_, items, events, seed_, noise_block_, num_sms_, nullptr, d_avg_.get());
+    avg_valid_ = true;
     if (noisy) noise_block_ += recs.size();
 }
 
 std::vector<double> BatchedSimulator::getAverageProbabilities() const {
-    CudaMemory<double> d_avg(state_size_);
-    b200::launch_batched_average(d_states_.get(), num_qubits_, batch_size_, d_avg.get(), num_sms_, nullptr);
+    if (!avg_valid_) {   // no run() since the states were last (re)set: one read of the batch
+        b200::launch_batched_average(d_states_.get(), num_qubits_, batch_size_, const_cast<double*>(d_avg_.get()), num_sms_, nullptr);
+        avg_valid_ = true;
+    }
     std::vector<double> avg(state_size_);
     CUDA_CHECK(cudaStreamSynchronize(nullptr));
-    d_avg.copyToHost(avg.data(), state_size_);
+    d_avg_.copyToHost(avg.data(), state_size_);
     return avg;
 }
 
@@ -350,21 +356,21 @@ std::vector<int32_t> BatchedSimulator::sampleFlat(int n_shots, bool histogram_on
     for (double& x : u) x = dist(rng_);
     CudaMemory<double> d_u(total);
     d_u.copyFromHost(u.data(), total);
-    CudaMemory<int32_t> d_out(total);
-    b200::launch_batched_sample(d_states_.get(), num_qubits_, batch_size_, d_u.get(), n_shots, d_out.get(), num_sms_, nullptr);
+    CudaMemory<int32_t> d_out(histogram_only ? 1 : total);
+    CudaMemory<int32_t> d_hist(hist ? state_size_ : 1);
+    if (hist) d_hist.zero();
+    // one kernel: per trajectory the CDF in shared memory, per shot the index and (optionally) the histogram count
+    b200::launch_batched_sample(d_states_.get(), num_qubits_, batch_size_, d_u.get(), n_shots, histogram_only ? nullptr : d_out.get(),
+                                hist ? d_hist.get() : nullptr, num_sms_, nullptr);
     std::vector<int32_t> out;
+    CUDA_CHECK(cudaStreamSynchronize(nullptr));
     if (hist) {
-        CudaMemory<int32_t> d_hist(state_size_);
-        d_hist.zero();
-        b200::launch_histogram(d_out.get(), (int64_t)total, num_qubits_, d_hist.get(), num_sms_, nullptr);
         std::vector<int32_t> h(state_size_);
-        CUDA_CHECK(cudaStreamSynchronize(nullptr));
         d_hist.copyToHost(h.data(), state_size_);
         hist->assign(h.begin(), h.end());
     }
     if (!histogram_only) {
         out.resize(total);
-        CUDA_CHECK(cudaStreamSynchronize(nullptr));
         d_out.copyToHost(out.data(), total);
     }
     return out;

@@ -148,13 +148,15 @@ public:
 
     // additive: trajectory amplitudes (tests), device pointer
     std::vector<std::complex<double>> getTrajectoryState(int trajectory_idx) const;
-    cuDoubleComplex* devicePtr() { return d_states_.get(); }
+    cuDoubleComplex* devicePtr() { avg_valid_ = false; return d_states_.get(); }   // the caller may change the states
 
 private:
     int num_qubits_;
     int batch_size_;
     size_t state_size_;
     CudaMemory<cuDoubleComplex> d_states_;
+    CudaMemory<double> d_avg_;        // average probabilities of the final states, accumulated by run()'s kernel epilogue
+    mutable bool avg_valid_ = false;
     NoiseModel noise_model_;
     std::mt19937 rng_;
     uint32_t seed_ = 0;

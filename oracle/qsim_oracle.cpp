@@ -496,7 +496,7 @@ static void traj_noise_event(cplx* a, int n, const orc_channel& ch, double u0, d
 
 // One trajectory: after every gate, every event in `ev[0..nev)` in order (Noisy/Batched schedule,
 // src/NoiseModel.cu:369-382, 815-831, with the empty-list-means-all fix D7 applied by the caller).
-// Event counter runs gate-major: event = gate_index * nev + event_index.
+// Event counter: event = (gate_index << 16) | event_index (independent of the number of events per gate).
 ORC_API int orc_traj_run(double* state, int n, const orc_gate* g, int64_t ng,
                          const orc_channel* ev, int64_t nev, uint32_t seed, uint64_t traj) {
     cplx* a = reinterpret_cast<cplx*>(state);
@@ -504,7 +504,7 @@ ORC_API int orc_traj_run(double* state, int n, const orc_gate* g, int64_t ng,
         if (orc_apply_gate(state, n, g + i)) return -1;
         for (int64_t e = 0; e < nev; ++e) {
             double u0, u1;
-            traj_uniforms(seed, traj, uint64_t(i) * uint64_t(nev) + uint64_t(e), u0, u1);
+            traj_uniforms(seed, traj, (uint64_t(i) << 16) | uint64_t(e), u0, u1);
             traj_noise_event(a, n, ev[e], u0, u1);
         }
     }

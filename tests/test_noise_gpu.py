@@ -110,9 +110,16 @@ def test_config_c5_full_size_against_exact_channel():
     sim.run(q.create_ghz_circuit(n))
     avg = sim.get_average_probabilities()
     assert abs(avg.sum() - 1) < 1e-10
-    # the average of |a|^2 over trajectories has per-entry variance <= p(1-p)/batch (it is a mean of values in [0,1] with mean p)
+    # the average of |a|^2 over trajectories has per-entry variance <= p(1-p)/batch (it is a mean of values in [0,1] with mean
+    # p): 4 sigma.  The 4096 cells are tested at once and the rare ones are Poisson, not Gaussian - a cell with p ~ 1e-6
+    # is hit by 0, 1, 2, ... whole trajectories of weight up to 1 - so the bound also allows 8 full-weight hits (8 / batch).
     sigma = np.sqrt(np.maximum(exact * (1 - exact), 0) / batch)
-    assert np.all(np.abs(avg - exact) < 4 * sigma + 1e-5), float(np.max(np.abs(avg - exact) / (sigma + 1e-5)))
+    assert np.all(np.abs(avg - exact) < 4 * sigma + 8.0 / batch), float(np.max(np.abs(avg - exact) / (sigma + 8.0 / batch)))
+    # the rare cells jointly: their total weight is one number with a Gaussian error
+    rare = exact < 1e-4
+    s_rare = np.sqrt(exact[rare].sum() / batch)
+    assert abs(avg[rare].sum() - exact[rare].sum()) < 4 * s_rare + 1e-6, (avg[rare].sum(), exact[rare].sum())
+    assert abs(avg[0] - exact[0]) < 4 * sigma[0] and abs(avg[-1] - exact[-1]) < 4 * sigma[-1]
     hist = sim.get_histogram(1)
     assert hist.sum() == batch                                                    # tests/test_noise.cu:313-330
     # one shot per trajectory is a multinomial draw of the exact distribution; the 4096 entries are tested jointly:
