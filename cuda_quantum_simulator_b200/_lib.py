@@ -116,6 +116,32 @@ def _declare(L: ctypes.CDLL) -> None:
         "qsim_ipc_close_handle": (c_int, [P]),
         "qsim_shard_partial_probability": (c_int, [P, c_int, POINTER(c_double)]),
         "qsim_shard_collapse": (c_int, [P, c_int, c_int, c_double]),
+        "qsim_sharded_unique_id": (c_int, [P]),
+        "qsim_sharded_create": (c_int, [c_int, c_int, c_int, P, c_int, PP]),
+        "qsim_sharded_destroy": (None, [P]),
+        "qsim_sharded_reset": (c_int, [P]),
+        "qsim_sharded_run": (c_int, [P, c_int, P, c_int64]),
+        "qsim_sharded_compile": (c_int, [P, c_int, P, c_int64, c_int, PP]),
+        "qsim_sharded_plan_destroy": (None, [P]),
+        "qsim_sharded_plan_info": (c_int, [P, POINTER(c_int64)]),
+        "qsim_sharded_execute": (c_int, [P, P]),
+        "qsim_sharded_sample": (c_int, [P, P, c_int64, P]),
+        "qsim_sharded_measure": (c_int, [P, c_int, c_double, POINTER(c_int)]),
+        "qsim_sharded_measure_bit": (c_int, [P, c_int, c_double, POINTER(c_int), POINTER(c_double)]),
+        "qsim_sharded_marginal": (c_int, [P, P, c_int, P]),
+        "qsim_sharded_total_probability": (c_int, [P, POINTER(c_double)]),
+        "qsim_sharded_get_local_state": (c_int, [P, P]),
+        "qsim_sharded_set_local_state": (c_int, [P, P]),
+        "qsim_sharded_restore_identity_layout": (c_int, [P]),
+        "qsim_sharded_layout": (c_int, [P, P, POINTER(c_uint64)]),
+        "qsim_sharded_set_identity_layout_only": (c_int, [P, c_int]),
+        "qsim_sharded_swap": (c_int, [P, c_int, c_int]),
+        "qsim_sharded_info": (c_int, [P, POINTER(c_int64)]),
+        "qsim_sharded_local": (c_void_p, [P]),
+        "qsim_sharded_set_stream": (c_int, [P, P]),
+        "qsim_sharded_synchronize": (c_int, [P]),
+        "qsim_sharded_barrier": (c_int, [P]),
+        "qsim_sharded_plan_circuit": (c_int, [c_int, c_int, P, c_int64, P, c_int, P, c_int64, P, P, P, POINTER(c_int64)]),
         "qsim_noisy_create": (c_int, [c_int, P, c_int, PP]),
         "qsim_noisy_destroy": (None, [P]),
         "qsim_noisy_set_noise": (c_int, [P, P, c_int]),

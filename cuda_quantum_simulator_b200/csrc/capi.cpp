@@ -18,8 +18,10 @@
 #include "qsim/constants.hpp"
 #include "qsim/density_matrix.cuh"
 #include "qsim/noise_model.cuh"
+#include "qsim/sharded_simulator.hpp"
 #include "qsim/simulator.hpp"
 #include "shard.cuh"
+#include "sharded_plan.hpp"
 
 using namespace qsim;
 
@@ -649,6 +651,185 @@ qsim_status_t qsim_shard_cdf_classify(qsim_sim_t* s, double approx_c_init) {
     return guarded([&] {
         require(s != nullptr, "null simulator");
         s->sim->state().sampleShardClassify(approx_c_init);
+    });
+}
+
+// ---- sharded simulator (C++ driver over NCCL, include/qsim/sharded_simulator.hpp) -----------------------------------------
+
+struct qsim_sharded { std::unique_ptr<ShardedSimulator> sim; };
+struct qsim_sharded_plan { std::shared_ptr<ShardedSimulator::CompiledPlan> plan; };
+
+qsim_status_t qsim_sharded_unique_id(unsigned char out[128]) {
+    return guarded([&] {
+        require(out != nullptr, "null output");
+        const auto id = ShardedSimulator::createUniqueId();
+        std::memcpy(out, id.data(), id.size());
+    });
+}
+
+qsim_status_t qsim_sharded_create(int n, int rank, int world, const unsigned char unique_id[128], int exchange, qsim_sharded_t** out) {
+    return guarded([&] {
+        require(out != nullptr, "null output");
+        require(isValidQubitCount(n), "Number of qubits out of range");
+        require(exchange >= 0 && exchange <= 2, "exchange must be 0 (auto), 1 (peer memory) or 2 (nccl)");
+        auto h = std::make_unique<qsim_sharded>();
+        h->sim = std::make_unique<ShardedSimulator>(n, rank, world, unique_id, static_cast<ShardedSimulator::Exchange>(exchange));
+        *out = h.release();
+    });
+}
+
+void qsim_sharded_destroy(qsim_sharded_t* h) { delete h; }
+
+qsim_status_t qsim_sharded_reset(qsim_sharded_t* h) {
+    return guarded([&] { require(h != nullptr, "null simulator"); h->sim->reset(); });
+}
+
+qsim_status_t qsim_sharded_run(qsim_sharded_t* h, int cq, const qsim_gate_t* gates, int64_t ng) {
+    return guarded([&] { require(h != nullptr, "null simulator"); h->sim->run(build(cq, gates, ng)); });
+}
+
+qsim_status_t qsim_sharded_compile(qsim_sharded_t* h, int cq, const qsim_gate_t* gates, int64_t ng, int k, qsim_sharded_plan_t** out) {
+    return guarded([&] {
+        require(h != nullptr && out != nullptr && k >= 1, "bad argument");
+        const Circuit c = build(cq, gates, ng);
+        const auto plans = k == 1 ? std::vector<std::shared_ptr<ShardedSimulator::CompiledPlan>>{h->sim->compile(c)}
+                                  : h->sim->compileSequence(c, k);
+        for (int i = 0; i < k; ++i) out[i] = new qsim_sharded_plan{plans[(size_t)i]};
+    });
+}
+
+void qsim_sharded_plan_destroy(qsim_sharded_plan_t* p) { delete p; }
+
+qsim_status_t qsim_sharded_plan_info(const qsim_sharded_plan_t* p, int64_t info[8]) {
+    return guarded([&] {
+        require(p != nullptr && info != nullptr, "null argument");
+        std::memset(info, 0, 8 * sizeof(int64_t));
+        info[0] = ShardedSimulator::planPasses(*p->plan);
+        info[1] = ShardedSimulator::planOps(*p->plan);
+        info[2] = ShardedSimulator::planSwaps(*p->plan);
+    });
+}
+
+qsim_status_t qsim_sharded_execute(qsim_sharded_t* h, const qsim_sharded_plan_t* p) {
+    return guarded([&] { require(h != nullptr && p != nullptr, "null argument"); h->sim->execute(*p->plan); });
+}
+
+qsim_status_t qsim_sharded_sample(qsim_sharded_t* h, const double* uniforms, int64_t n_shots, int64_t* out) {
+    return guarded([&] {
+        require(h != nullptr && (n_shots == 0 || (uniforms != nullptr && out != nullptr)) && n_shots >= 0, "bad argument");
+        const auto res = h->sim->sample(std::vector<double>(uniforms, uniforms + n_shots));
+        std::copy(res.begin(), res.end(), out);
+    });
+}
+
+qsim_status_t qsim_sharded_measure(qsim_sharded_t* h, int qubit, double uniform, int* result) {
+    return guarded([&] { require(h != nullptr && result != nullptr, "null argument"); *result = h->sim->measureQubit(qubit, uniform); });
+}
+
+qsim_status_t qsim_sharded_measure_bit(qsim_sharded_t* h, int bit, double uniform, int* result, double* p0) {
+    return guarded([&] { require(h != nullptr && result != nullptr, "null argument"); *result = h->sim->measureBit(bit, uniform, p0); });
+}
+
+qsim_status_t qsim_sharded_marginal(qsim_sharded_t* h, const int* qubits, int k, double* out) {
+    return guarded([&] {
+        require(h != nullptr && out != nullptr && k >= 0 && (k == 0 || qubits != nullptr), "bad argument");
+        const auto m = h->sim->getMarginalProbabilities(std::vector<int>(qubits, qubits + k));
+        std::copy(m.begin(), m.end(), out);
+    });
+}
+
+qsim_status_t qsim_sharded_total_probability(qsim_sharded_t* h, double* out) {
+    return guarded([&] { require(h != nullptr && out != nullptr, "null argument"); *out = h->sim->getTotalProbability(); });
+}
+
+qsim_status_t qsim_sharded_get_local_state(qsim_sharded_t* h, double* out) {
+    return guarded([&] {
+        require(h != nullptr && out != nullptr, "null argument");
+        const auto st = h->sim->getLocalState();
+        std::memcpy(out, st.data(), st.size() * sizeof(std::complex<double>));
+    });
+}
+
+qsim_status_t qsim_sharded_set_local_state(qsim_sharded_t* h, const double* amps) {
+    return guarded([&] {
+        require(h != nullptr && amps != nullptr, "null argument");
+        h->sim->setLocalState(reinterpret_cast<const std::complex<double>*>(amps));
+    });
+}
+
+qsim_status_t qsim_sharded_restore_identity_layout(qsim_sharded_t* h) {
+    return guarded([&] { require(h != nullptr, "null simulator"); h->sim->restoreIdentityLayout(); });
+}
+
+qsim_status_t qsim_sharded_layout(const qsim_sharded_t* h, int* perm_out, uint64_t* frame_out) {
+    return guarded([&] {
+        require(h != nullptr, "null simulator");
+        if (perm_out) std::copy(h->sim->permutation().begin(), h->sim->permutation().end(), perm_out);
+        if (frame_out) *frame_out = h->sim->frame();
+    });
+}
+
+qsim_status_t qsim_sharded_set_identity_layout_only(qsim_sharded_t* h, int on) {
+    return guarded([&] { require(h != nullptr, "null simulator"); h->sim->setIdentityLayoutOnly(on != 0); });
+}
+
+qsim_status_t qsim_sharded_swap(qsim_sharded_t* h, int global_position, int local_position) {
+    return guarded([&] { require(h != nullptr, "null simulator"); h->sim->swapQubits(global_position, local_position); });
+}
+
+qsim_status_t qsim_sharded_info(const qsim_sharded_t* h, int64_t info[8]) {
+    return guarded([&] {
+        require(h != nullptr && info != nullptr, "null argument");
+        std::memset(info, 0, 8 * sizeof(int64_t));
+        info[0] = h->sim->localQubits();
+        info[1] = h->sim->getNumQubits() - h->sim->localQubits();
+        info[2] = h->sim->fusedExchanges();
+        info[3] = h->sim->separateExchanges();
+        const std::string ex = h->sim->exchangeName();
+        info[4] = ex == "p2p" ? 1 : (ex == "nccl" ? 2 : 0);
+        info[5] = h->sim->rank();
+        info[6] = h->sim->worldSize();
+    });
+}
+
+qsim_sim_t* qsim_sharded_local(qsim_sharded_t* h) { return h ? static_cast<qsim_sim_t*>(h->sim->localHandle()) : nullptr; }
+
+qsim_status_t qsim_sharded_set_stream(qsim_sharded_t* h, void* stream) {
+    return guarded([&] { require(h != nullptr, "null simulator"); h->sim->setStream(static_cast<cudaStream_t>(stream)); });
+}
+
+qsim_status_t qsim_sharded_synchronize(qsim_sharded_t* h) {
+    return guarded([&] { require(h != nullptr, "null simulator"); h->sim->synchronize(); });
+}
+
+qsim_status_t qsim_sharded_barrier(qsim_sharded_t* h) {
+    return guarded([&] { require(h != nullptr, "null simulator"); h->sim->barrier(); });
+}
+
+qsim_status_t qsim_sharded_plan_circuit(int n, int n_global, const qsim_gate_t* gates, int64_t ng, const int* perm_in,
+                                        int choose_layout, int64_t* steps_out, int64_t cap_steps, qsim_gate_t* gates_out,
+                                        int* perm_start_out, int* perm_end_out, int64_t* n_steps_out) {
+    return guarded([&] {
+        require(n_steps_out != nullptr && n_global >= 0 && n_global < n, "bad argument");
+        build(n, gates, ng);   // validation only
+        std::vector<int> perm(n);
+        for (int q = 0; q < n; ++q) perm[q] = perm_in ? perm_in[q] : q;
+        if (choose_layout) perm = b200::shard_choose_initial_layout(n, n_global, gates, ng);
+        if (perm_start_out) std::copy(perm.begin(), perm.end(), perm_start_out);
+        const b200::ShardPlanRec plan = b200::shard_plan_circuit(n, n_global, gates, ng, perm);
+        *n_steps_out = (int64_t)plan.steps.size();
+        int64_t gi = 0;
+        for (size_t i = 0; i < plan.steps.size(); ++i) {
+            const auto& st = plan.steps[i];
+            if (steps_out && (int64_t)i < cap_steps) {
+                steps_out[3 * i] = st.is_swap ? 1 : 0;
+                steps_out[3 * i + 1] = st.is_swap ? st.global_qubit : (int64_t)st.gates.size();
+                steps_out[3 * i + 2] = st.is_swap ? st.local_qubit : 0;
+            }
+            if (gates_out)
+                for (const auto& r : st.gates) gates_out[gi++] = r;
+        }
+        if (perm_end_out) std::copy(plan.perm.begin(), plan.perm.end(), perm_end_out);
     });
 }
 

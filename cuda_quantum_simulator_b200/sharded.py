@@ -740,3 +740,185 @@ class ShardedSimulator:
 
     def close(self):
         self.engine.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The C++ driver (qsim::ShardedSimulator, include/qsim/sharded_simulator.hpp) behind the same Python surface
+# ---------------------------------------------------------------------------------------------------------------------
+
+def plan_circuit_native(num_qubits: int, n_global: int, gates: np.ndarray, perm: Optional[Sequence[int]] = None,
+                        choose_layout: bool = False):
+    """The C++ planner (csrc/sharded_plan.cpp) through the C ABI: returns (Plan, start permutation).  Host logic only."""
+    g = np.ascontiguousarray(gates, dtype=GATE_DTYPE)
+    cap = 2 * len(g) + 2
+    steps = np.zeros(3 * cap, np.int64)
+    gout = np.zeros(max(len(g), 1), GATE_DTYPE)
+    p_in = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+    p_start, p_end = np.zeros(num_qubits, np.int32), np.zeros(num_qubits, np.int32)
+    n_steps = c_int64()
+    _lib.check(_lib.lib().qsim_sharded_plan_circuit(
+        int(num_qubits), int(n_global), _lib.gates_ptr(g) if len(g) else None, len(g),
+        None if p_in is None else p_in.ctypes.data_as(c_void_p), int(choose_layout), steps.ctypes.data_as(c_void_p), cap,
+        gout.ctypes.data_as(c_void_p), p_start.ctypes.data_as(c_void_p), p_end.ctypes.data_as(c_void_p), byref(n_steps)))
+    plan = Plan(num_qubits, n_global, n_gates=len(g))
+    gi = 0
+    for i in range(n_steps.value):
+        kind, a, b = (int(x) for x in steps[3 * i:3 * i + 3])
+        if kind == 0:
+            plan.steps.append(Step("gates", gates=gout[gi:gi + a].copy()))
+            gi += a
+        else:
+            plan.steps.append(Step("swap", global_qubit=a, local_qubit=b))
+    plan.perm = [int(x) for x in p_end]
+    return plan, [int(x) for x in p_start]
+
+
+class _NativePlan:
+    def __init__(self, handle):
+        self._h = handle
+        info = (c_int64 * 8)()
+        _lib.check(_lib.lib().qsim_sharded_plan_info(handle, info))
+        self.n_passes, self.n_ops, self.n_swaps = int(info[0]), int(info[1]), int(info[2])
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _lib.lib().qsim_sharded_plan_destroy(self._h)
+            self._h = c_void_p()
+
+
+class NativeShardedSimulator:
+    """Python mirror of qsim::ShardedSimulator: planning, layout bookkeeping, CUDA-IPC / NCCL exchanges and the distributed
+    read-out all run in C++ (NCCL called directly); torch.distributed is used ONCE, to hand rank 0's NCCL unique id to the
+    other ranks.  Same surface as ShardedSimulator above (the pure-Python driver, kept for the gloo tests)."""
+
+    def __init__(self, num_qubits: int, exchange: str = "auto"):
+        import torch
+        import torch.distributed as dist
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.n = int(num_qubits)
+        ident = (ctypes.c_ubyte * 128)()
+        if self.world > 1:
+            if self.rank == 0:
+                _lib.check(_lib.lib().qsim_sharded_unique_id(ident))
+            box = [bytes(ident)]
+            dist.broadcast_object_list(box, src=0)
+            ident = (ctypes.c_ubyte * 128).from_buffer_copy(box[0])
+        self._h = c_void_p()
+        mode = {"auto": 0, "p2p": 1, "nccl": 2}[exchange]
+        _lib.check(_lib.lib().qsim_sharded_create(self.n, self.rank, self.world, ident, mode, byref(self._h)))
+        self.stream = torch.cuda.current_stream()
+        _lib.check(_lib.lib().qsim_sharded_set_stream(self._h, c_void_p(self.stream.cuda_stream)))
+        info = self._info()
+        self.nl, self.ng = int(info[0]), int(info[1])
+        from .simulator import Simulator
+
+        class _Borrowed(Simulator):          # the shard as a Simulator (timing, counters); owned by the C++ object
+            def __del__(self): pass
+            close = __del__
+        self.local = _Borrowed(self.nl, _handle=c_void_p(_lib.lib().qsim_sharded_local(self._h)))
+
+    def _info(self):
+        info = (c_int64 * 8)()
+        _lib.check(_lib.lib().qsim_sharded_info(self._h, info))
+        return info
+
+    @property
+    def fused_exchanges(self) -> int: return int(self._info()[2])
+    @property
+    def separate_exchanges(self) -> int: return int(self._info()[3])
+    @property
+    def exchange(self) -> str: return {0: "none", 1: "p2p", 2: "nccl"}[int(self._info()[4])]
+    @property
+    def perm(self) -> List[int]:
+        out = np.zeros(self.n, np.int32)
+        _lib.check(_lib.lib().qsim_sharded_layout(self._h, out.ctypes.data_as(c_void_p), None))
+        return [int(x) for x in out]
+    @property
+    def frame(self) -> int:
+        f = c_uint64()
+        _lib.check(_lib.lib().qsim_sharded_layout(self._h, None, byref(f)))
+        return int(f.value)
+
+    def reset(self): _lib.check(_lib.lib().qsim_sharded_reset(self._h))
+    def identity_layout_only(self, on: bool = True): _lib.check(_lib.lib().qsim_sharded_set_identity_layout_only(self._h, int(on)))
+    def synchronize(self): _lib.check(_lib.lib().qsim_sharded_synchronize(self._h))
+    def barrier(self): _lib.check(_lib.lib().qsim_sharded_barrier(self._h))
+    def swap(self, global_position: int, local_position: int): _lib.check(_lib.lib().qsim_sharded_swap(self._h, global_position, local_position))
+    def restore_identity_layout(self): _lib.check(_lib.lib().qsim_sharded_restore_identity_layout(self._h))
+
+    def run(self, circuit: Circuit):
+        g = circuit.gates
+        _lib.check(_lib.lib().qsim_sharded_run(self._h, circuit.get_num_qubits(), _lib.gates_ptr(g) if len(g) else None, len(g)))
+
+    def compile_sequence(self, circuit: Circuit, k: int) -> List[_NativePlan]:
+        g = circuit.gates
+        out = (c_void_p * k)()
+        _lib.check(_lib.lib().qsim_sharded_compile(self._h, circuit.get_num_qubits(), _lib.gates_ptr(g) if len(g) else None, len(g),
+                                                   int(k), out))
+        return [_NativePlan(c_void_p(out[i])) for i in range(k)]
+
+    def compile(self, circuit: Circuit) -> _NativePlan:
+        return self.compile_sequence(circuit, 1)[0]
+
+    def execute(self, plan: _NativePlan): _lib.check(_lib.lib().qsim_sharded_execute(self._h, plan._h))
+    def release(self, plan): pass
+
+    def sample(self, n_shots: int = 0, uniforms: Optional[np.ndarray] = None, seed: Optional[int] = None) -> np.ndarray:
+        if uniforms is None:
+            uniforms = np.random.RandomState(seed).random_sample(n_shots)
+        u = np.ascontiguousarray(uniforms, np.float64)
+        out = np.empty(len(u), np.int64)
+        _lib.check(_lib.lib().qsim_sharded_sample(self._h, u.ctypes.data_as(c_void_p), len(u), out.ctypes.data_as(c_void_p)))
+        return out
+
+    def measure_qubit(self, qubit: int, uniform: float) -> int:
+        res = ctypes.c_int()
+        _lib.check(_lib.lib().qsim_sharded_measure(self._h, int(qubit), float(uniform), byref(res)))
+        return res.value
+
+    def marginal(self, qubits) -> np.ndarray:
+        qs = np.ascontiguousarray(qubits, dtype=np.int32)
+        out = np.empty(1 << len(qs), np.float64)
+        _lib.check(_lib.lib().qsim_sharded_marginal(self._h, qs.ctypes.data_as(c_void_p), len(qs), out.ctypes.data_as(c_void_p)))
+        return out
+
+    def get_total_probability(self) -> float:
+        v = c_double()
+        _lib.check(_lib.lib().qsim_sharded_total_probability(self._h, byref(v)))
+        return v.value
+
+    def local_state(self) -> np.ndarray:
+        out = np.empty(1 << self.nl, np.complex128)
+        _lib.check(_lib.lib().qsim_sharded_get_local_state(self._h, out.ctypes.data_as(c_void_p)))
+        return out
+
+    def get_state_vector(self) -> np.ndarray:
+        """Full logical state on every rank (small states only: tests)."""
+        import torch
+        import torch.distributed as dist
+        local = self.local_state()
+        if self.world > 1:
+            t = torch.from_numpy(local).cuda()
+            outs = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(outs, t)
+            shards = [o.cpu().numpy() for o in outs]
+        else:
+            shards = [local]
+        perm, fx = self.perm, self.frame >> self.nl
+        stored = np.concatenate([shards[p ^ fx] for p in range(self.world)])
+        phys = np.arange(1 << self.n, dtype=np.uint64)
+        idx = np.zeros_like(phys)
+        for q in range(self.n):
+            idx |= ((phys >> np.uint64(perm[q])) & np.uint64(1)) << np.uint64(q)
+        out = np.empty(1 << self.n, np.complex128)
+        out[idx.astype(np.int64)] = stored
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.local._h = c_void_p()
+            _lib.lib().qsim_sharded_destroy(self._h)
+            self._h = c_void_p()
+
+    __del__ = close

@@ -77,6 +77,8 @@ typedef struct qsim_program qsim_program_t;   /* a compiled (fused) circuit   */
 typedef struct qsim_batched qsim_batched_t;   /* BatchedSimulator             */
 typedef struct qsim_noisy qsim_noisy_t;       /* NoisySimulator               */
 typedef struct qsim_dm qsim_dm_t;             /* DensityMatrixSimulator       */
+typedef struct qsim_sharded qsim_sharded_t;   /* ShardedSimulator (multi-GPU) */
+typedef struct qsim_sharded_plan qsim_sharded_plan_t;   /* a circuit planned + compiled for a sharded state */
 
 QSIM_API const char* qsim_last_error(void);
 QSIM_API const char* qsim_version(void);
@@ -233,6 +235,57 @@ QSIM_API qsim_status_t qsim_shard_sample(qsim_sim_t* s, double c_init, int first
  * only stitches the chunk starts from the exact c_init and samples.  No other read-out call in between. */
 QSIM_API qsim_status_t qsim_shard_cdf_prepare(qsim_sim_t* s, double* approx_total);
 QSIM_API qsim_status_t qsim_shard_cdf_classify(qsim_sim_t* s, double approx_c_init);
+
+/* ---- ShardedSimulator: the multi-GPU Simulator, driven from C++ over NCCL (include/qsim/sharded_simulator.hpp; additive,
+ * the reference is single-GPU: README.md:367; surface after include/Simulator.hpp:53-85).  One process per GPU; all ranks make
+ * the same calls in the same order (the calls contain collectives).  Bootstrap: rank 0 obtains a unique id and hands the 128
+ * bytes to every rank (any channel: MPI, a file, torch.distributed in the Python mirror), then every rank calls create on its
+ * current CUDA device.  exchange: 0 = auto (CUDA-IPC peer memory, else NCCL send/recv), 1 = peer memory, 2 = NCCL. */
+QSIM_API qsim_status_t qsim_sharded_unique_id(unsigned char out[128]);
+QSIM_API qsim_status_t qsim_sharded_create(int num_qubits, int rank, int world_size, const unsigned char unique_id[128],
+                                           int exchange, qsim_sharded_t** out);
+QSIM_API void qsim_sharded_destroy(qsim_sharded_t* h);
+QSIM_API qsim_status_t qsim_sharded_reset(qsim_sharded_t* h);                                           /* Simulator::reset */
+QSIM_API qsim_status_t qsim_sharded_run(qsim_sharded_t* h, int circuit_qubits, const qsim_gate_t* gates, int64_t n_gates);
+/* Plans + compiles the circuit against the current qubit layout: out[0..k) receive plans for k consecutive runs (run i is
+ * compiled against the layout run i-1 leaves; plans are shared when the layout repeats; destroy each handle). */
+QSIM_API qsim_status_t qsim_sharded_compile(qsim_sharded_t* h, int circuit_qubits, const qsim_gate_t* gates, int64_t n_gates,
+                                            int k, qsim_sharded_plan_t** out);
+QSIM_API void qsim_sharded_plan_destroy(qsim_sharded_plan_t* p);
+/* info[0]=passes, [1]=ops, [2]=global<->local swaps */
+QSIM_API qsim_status_t qsim_sharded_plan_info(const qsim_sharded_plan_t* p, int64_t info[8]);
+/* Fails with QSIM_ERR_INVALID_ARGUMENT when the state's layout is not the one the plan was compiled against. */
+QSIM_API qsim_status_t qsim_sharded_execute(qsim_sharded_t* h, const qsim_sharded_plan_t* p);
+/* LOGICAL basis-state indices in the reference's sequential-CDF order (src/Simulator.cu:164-185), identical on every rank. */
+QSIM_API qsim_status_t qsim_sharded_sample(qsim_sharded_t* h, const double* uniforms, int64_t n_shots, int64_t* out);
+/* Simulator::measureQubit: index bit n-1-qubit (src/StateVector.cu:87-89); outcome 0 iff uniform < P(bit = 0). */
+QSIM_API qsim_status_t qsim_sharded_measure(qsim_sharded_t* h, int qubit, double uniform, int* result);
+QSIM_API qsim_status_t qsim_sharded_measure_bit(qsim_sharded_t* h, int bit, double uniform, int* result, double* p0);
+QSIM_API qsim_status_t qsim_sharded_marginal(qsim_sharded_t* h, const int* qubits, int n_qubits, double* out);
+QSIM_API qsim_status_t qsim_sharded_total_probability(qsim_sharded_t* h, double* out);
+/* This rank's shard in the STORED layout (see qsim_sharded_layout), 2^(local qubits) amplitudes. */
+QSIM_API qsim_status_t qsim_sharded_get_local_state(qsim_sharded_t* h, double* out_amplitudes);
+QSIM_API qsim_status_t qsim_sharded_set_local_state(qsim_sharded_t* h, const double* amplitudes);
+/* Moves the amplitudes back to the identity qubit layout (exchanges + one local permutation pass). */
+QSIM_API qsim_status_t qsim_sharded_restore_identity_layout(qsim_sharded_t* h);
+/* perm_out[q] = physical index bit that holds logical qubit q; frame_out = pending X mask over physical bits (rank bits only). */
+QSIM_API qsim_status_t qsim_sharded_layout(const qsim_sharded_t* h, int* perm_out, uint64_t* frame_out);
+QSIM_API qsim_status_t qsim_sharded_set_identity_layout_only(qsim_sharded_t* h, int on);   /* never choose a layout for |0..0> */
+QSIM_API qsim_status_t qsim_sharded_swap(qsim_sharded_t* h, int global_position, int local_position);   /* one separate exchange */
+/* info[0]=local qubits, [1]=rank qubits, [2]=exchanges fused into a pass, [3]=separate exchanges, [4]=1 peer memory / 2 NCCL,
+ * [5]=rank, [6]=world size */
+QSIM_API qsim_status_t qsim_sharded_info(const qsim_sharded_t* h, int64_t info[8]);
+QSIM_API qsim_sim_t* qsim_sharded_local(qsim_sharded_t* h);   /* the shard as a qsim_sim_t (timing, launch counters); borrowed */
+QSIM_API qsim_status_t qsim_sharded_set_stream(qsim_sharded_t* h, void* cuda_stream);
+QSIM_API qsim_status_t qsim_sharded_synchronize(qsim_sharded_t* h);
+QSIM_API qsim_status_t qsim_sharded_barrier(qsim_sharded_t* h);   /* stream-ordered barrier across the ranks */
+/* The planner alone (host logic, no device, no NCCL): steps_out[3*i] = 0 (gates: [3*i+1] = how many, taken in order from
+ * gates_out, on PHYSICAL positions) or 1 (swap of global position [3*i+1] with local position [3*i+2]).  perm_in may be NULL
+ * (identity); choose_layout != 0 picks the layout for a run from |0...0> first (returned in perm_start_out). */
+QSIM_API qsim_status_t qsim_sharded_plan_circuit(int num_qubits, int n_global, const qsim_gate_t* gates, int64_t n_gates,
+                                                 const int* perm_in, int choose_layout, int64_t* steps_out, int64_t cap_steps,
+                                                 qsim_gate_t* gates_out, int* perm_start_out, int* perm_end_out,
+                                                 int64_t* n_steps_out);
 
 /* ---- NoisySimulator (reference include/NoiseModel.cuh:141-225) ---------------------------------- */
 QSIM_API qsim_status_t qsim_noisy_create(int num_qubits, const qsim_noise_channel_t* channels, int n_channels,

@@ -283,3 +283,34 @@ def test_planner_c4_needs_one_swap():
     c3 = qs.Circuit(6).h(5).h(5).cnot(0, 5).ry(4, 0.3)
     p3 = plan_circuit(6, 2, c3.gates)
     assert p3.n_swaps == 2 and sorted(p3.perm) == list(range(6))
+
+
+@pytest.mark.parametrize("n,ng,depth,seed", [(8, 1, 60, 1), (9, 2, 80, 2), (10, 3, 120, 3), (12, 2, 200, 4), (36, 3, 20, 42),
+                                             (33, 3, 200, 42)])
+def test_cpp_planner_equals_python_planner(n, ng, depth, seed):
+    """csrc/sharded_plan.cpp (the planner of qsim::ShardedSimulator) against plan_circuit / choose_initial_layout above:
+    same swaps at the same places, same gate records on physical positions, same final permutation."""
+    import cuda_quantum_simulator_b200 as qs
+    from cuda_quantum_simulator_b200.sharded import choose_initial_layout, plan_circuit_native
+    if n <= 12:
+        g = H.random_gates(n, depth, np.random.default_rng(seed))
+    else:
+        g = qs.create_random_circuit(n, depth, seed).gates
+    for choose in (False, True):
+        start = choose_initial_layout(n, ng, g) if choose else list(range(n))
+        want = plan_circuit(n, ng, g, start)
+        got, got_start = plan_circuit_native(n, ng, g, None, choose_layout=choose)
+        assert got_start == start
+        assert got.perm == want.perm and len(got.steps) == len(want.steps)
+        for a, b in zip(got.steps, want.steps):
+            assert a.kind == b.kind
+            if a.kind == "swap":
+                assert (a.global_qubit, a.local_qubit) == (b.global_qubit, b.local_qubit)
+            else:
+                assert np.array_equal(a.gates, b.gates)
+    # a start permutation handed in explicitly
+    rng = np.random.default_rng(seed)
+    perm = [int(x) for x in rng.permutation(n)]
+    want = plan_circuit(n, ng, g, perm)
+    got, _ = plan_circuit_native(n, ng, g, perm)
+    assert got.perm == want.perm and [s.kind for s in got.steps] == [s.kind for s in want.steps]

@@ -1,5 +1,6 @@
 """Multi-GPU parity (needs >= 2 GPUs; skipped on a single-GPU box).  Spawns torchrun on tools/sharded_check.py,
-which compares ShardedSimulator (CUDA IPC peer swaps and the NCCL fallback) with the CPU oracle."""
+which compares the sharded simulators - the Python driver and the C++ driver qsim::ShardedSimulator ("native"), each with CUDA
+IPC peer memory and with the NCCL fallback - with the CPU oracle."""
 import os
 import subprocess
 import sys
@@ -16,7 +17,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+@pytest.mark.parametrize("exchange", ["p2p", "nccl", "native", "native-nccl"])
 def test_two_gpu_parity(exchange):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
