@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -235,6 +236,15 @@ qsim_status_t qsim_jit_stats(int64_t out[8]) {
         out[0] = st.compiles; out[1] = st.cache_hits; out[2] = st.launches; out[3] = st.failures;
         out[4] = (int64_t)(st.compile_seconds * 1e6); out[5] = st.last_cubin_bytes;
         out[6] = (int64_t)b200::jit_mode(); out[7] = b200::jit_min_qubits();
+    });
+}
+
+qsim_status_t qsim_program_set_specialised(qsim_program_t* p, int on) {
+    return guarded([&] {
+        require(p != nullptr, "null program");
+        p->dev.host.force_jit = on != 0;
+        if (on) std::fill(p->dev.host.jit_tried.begin(), p->dev.host.jit_tried.end(), 0);
+        if (p->dev.graph.exec) { cudaGraphExecDestroy(p->dev.graph.exec); p->dev.graph = b200::DeviceProgram::Graph(); }
     });
 }
 

@@ -26,6 +26,7 @@ void require_device() {
 }
 
 DeviceProgram::~DeviceProgram() {
+    if (graph.exec) cudaGraphExecDestroy(graph.exec);
     if (d_ops) cudaFree(d_ops);
     if (d_tables) cudaFree(d_tables);
     if (d_terms) cudaFree(d_terms);
@@ -62,6 +63,8 @@ Engine::Engine() {
     CUDA_CHECK(cudaEventCreateWithFlags(&staged_, cudaEventDisableTiming));
     if (const char* e = std::getenv("QSIM_STAGES")) stages_wanted_ = std::atoi(e);
     if (std::getenv("QSIM_TMA_1D")) use_tensor_map_ = false;
+    if (const char* e = std::getenv("QSIM_GRAPH_MAX_QUBITS")) graph_max_qubits_ = std::atoi(e);
+    if (std::getenv("QSIM_NO_GRAPH")) graph_max_qubits_ = 0;
 }
 
 Engine::~Engine() {
@@ -70,6 +73,7 @@ Engine::~Engine() {
     if (d_ops_) cudaFree(d_ops_);
     if (h_ops_) cudaFreeHost(h_ops_);
     if (staged_) cudaEventDestroy(staged_);
+    if (capture_stream_) cudaStreamDestroy(capture_stream_);
     for (auto& e : events_) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto& e : pool_) cudaEventDestroy(e);
 }
@@ -170,7 +174,7 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
         if (p.jit.size() != p.passes.size()) { p.jit.assign(p.passes.size(), nullptr); p.jit_tried.assign(p.passes.size(), 0); }
         {
             NvtxScope range(label);
-            CUDA_CHECK(launch_pass(prm, num_sms_, stream_, p.ops.data() + pd.op_offset, &p.jit[pass_i], &p.jit_tried[pass_i]));
+            CUDA_CHECK(launch_pass(prm, num_sms_, stream_, p.ops.data() + pd.op_offset, &p.jit[pass_i], &p.jit_tried[pass_i], p.force_jit));
         }
         ++launches_;
         if (timing_) {
@@ -234,6 +238,64 @@ void Engine::execute(const DeviceProgram& p, cuDoubleComplex* state, uint64_t hi
                      const StoreRedirect* redirect) {
     if (p.host.passes.empty()) return;
     if (!p.d_ops && !p.host.ops.empty()) throw std::runtime_error("qsim_b200: program was not uploaded");
+    // Launch-bound regime: replay the pass sequence as one CUDA graph.  The first run on these amplitudes goes through the
+    // plain path (it also resolves the specialised kernels and sets their attributes), the second is captured, later ones
+    // replay.  A different state pointer, rank or device captures again.
+    const bool graphable = !timing_ && !redirect && init_basis < 0 && p.host.passes.size() >= 2 &&
+                           p.host.n_local <= graph_max_qubits_;
+    if (graphable) {
+        int dev = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        DeviceProgram::Graph& g = p.graph;
+        const bool same = g.state == state && g.hi_bits == hi_bits && g.device == dev;
+        if (same && g.exec) {
+            CUDA_CHECK(cudaGraphLaunch(g.exec, stream_));
+            launches_ += (int64_t)p.host.passes.size();
+            ++graph_launches_;
+            return;
+        }
+        if (same && g.plain_runs >= 1) {
+            if (!capture_stream_) CUDA_CHECK(cudaStreamCreateWithFlags(&capture_stream_, cudaStreamNonBlocking));
+            cudaStream_t user = stream_;
+            const int64_t launches_before = launches_;
+            cudaGraph_t graph = nullptr;
+            cudaError_t err = cudaStreamBeginCapture(capture_stream_, cudaStreamCaptureModeThreadLocal);
+            if (err == cudaSuccess) {
+                stream_ = capture_stream_;
+                try {
+                    launchAll(p.host, p.d_ops, p.d_tables, p.d_terms, state, hi_bits, init_basis, redirect);
+                } catch (...) {
+                    stream_ = user;
+                    cudaStreamEndCapture(capture_stream_, &graph);
+                    if (graph) cudaGraphDestroy(graph);
+                    cudaGetLastError();
+                    throw;
+                }
+                stream_ = user;
+                err = cudaStreamEndCapture(capture_stream_, &graph);
+            }
+            launches_ = launches_before;   // nothing ran yet
+            if (err == cudaSuccess && graph) {
+                if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+                err = cudaGraphInstantiate(&g.exec, graph, 0);
+                cudaGraphDestroy(graph);
+            }
+            if (err == cudaSuccess && g.exec) {
+                CUDA_CHECK(cudaGraphLaunch(g.exec, stream_));
+                launches_ += (int64_t)p.host.passes.size();
+                ++graph_launches_;
+                return;
+            }
+            cudaGetLastError();            // capture unavailable: stay on the plain path
+            g.exec = nullptr;
+            g.plain_runs = -(1 << 30);
+        }
+        if (!same) {
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            g.state = state; g.hi_bits = hi_bits; g.device = dev; g.plain_runs = 0;
+        }
+        ++g.plain_runs;
+    }
     launchAll(p.host, p.d_ops, p.d_tables, p.d_terms, state, hi_bits, init_basis, redirect);
 }
 

@@ -456,7 +456,7 @@ cudaError_t ensure_smem_optin() {
 }  // namespace
 
 cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t stream, const DevOp* host_ops,
-                        std::shared_ptr<JitKernel>* jit_slot, char* tried_slot) {
+                        std::shared_ptr<JitKernel>* jit_slot, char* tried_slot, bool force_jit) {
     PassParams params = params_in;
     alignas(64) CUtensorMap tmap, tmap_keep, tmap_send;
     std::memset(&tmap, 0, sizeof(tmap));
@@ -487,7 +487,7 @@ cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t s
     // a kernel specialised for this pass's structure (large states; compiled once per structure, see jit.hpp)
     if (params.use_tensor_map && (host_ops || params.pd.n_ops == 0)) {
         std::shared_ptr<JitKernel> local, *slot = jit_slot ? jit_slot : &local;
-        if (!*slot && !(tried_slot && *tried_slot) && jit_wanted(params.pd)) {
+        if (!*slot && !(tried_slot && *tried_slot) && (jit_wanted(params.pd) || (force_jit && jit_mode() != JitMode::Off))) {
             *slot = jit_get_kernel(params.pd, host_ops);
             if (tried_slot) *tried_slot = 1;
         }

@@ -62,6 +62,7 @@ struct Program {
     // jit_tried marks passes for which the interpreter was chosen)
     mutable std::vector<std::shared_ptr<JitKernel>> jit;
     mutable std::vector<char> jit_tried;
+    bool force_jit = false;      // specialise every pass whatever the state size (a pre-compiled circuit that will run many times)
     std::string describe() const;
 };
 

@@ -14,7 +14,9 @@ from .circuit import Circuit, gate_record
 class CompiledCircuit:
     """A circuit lowered to fused passes and resident on the device (qsim_program_t)."""
 
-    def __init__(self, circuit: Circuit, n_global: int = 0):
+    def __init__(self, circuit: Circuit, n_global: int = 0, specialise: Optional[bool] = None):
+        """specialise=True: every pass gets a run-time specialised kernel whatever the state size (worth it for a circuit
+        that runs many times); None: the library's policy (large states only)."""
         self._h = c_void_p()
         g = circuit.gates
         self.num_qubits = circuit.get_num_qubits()
@@ -24,6 +26,8 @@ class CompiledCircuit:
         info = (c_int64 * 8)()
         _lib.check(_lib.lib().qsim_program_info(self._h, info))
         self.n_passes, self.n_ops, _, self.n_sweeps = info[0], info[1], info[2], info[3]
+        if specialise:
+            _lib.check(_lib.lib().qsim_program_set_specialised(self._h, 1))
 
     def describe(self) -> str:
         need = _lib.lib().qsim_program_describe(self._h, None, 0)

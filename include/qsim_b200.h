@@ -118,6 +118,9 @@ QSIM_API qsim_status_t qsim_jit_set_mode(int mode, int min_qubits);
 /* out[0]=kernels compiled, [1]=cache hits, [2]=specialised launches, [3]=failed compiles, [4]=compile time (us),
  * [5]=size of the last cubin, [6]=mode, [7]=min_qubits */
 QSIM_API qsim_status_t qsim_jit_stats(int64_t out[8]);
+/* Marks a compiled program for specialisation whatever the state size: a pre-compiled circuit that will run many times is
+ * worth one NVRTC compile per pass even below min_qubits (ignored in mode 0).  Takes effect at the next execute. */
+QSIM_API qsim_status_t qsim_program_set_specialised(qsim_program_t* p, int on);
 /* CUDA C++ generated for pass `pass` of a compiled program (whole_unit != 0: the full translation unit handed to
  * NVRTC).  Returns bytes needed incl. NUL; needs no GPU. */
 QSIM_API size_t qsim_program_jit_source(const qsim_program_t* p, int pass, int whole_unit, char* buf, size_t cap);

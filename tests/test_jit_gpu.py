@@ -132,3 +132,34 @@ def test_fused_exchange_store_redirect(nl, g_local):
     """The specialised kernel shares the skeleton's redirected store (fused qubit exchange): reuse the one-GPU check."""
     from test_sharded_gpu import test_fused_exchange_on_one_gpu
     test_fused_exchange_on_one_gpu(nl, g_local, False)
+
+
+@pytest.mark.parametrize("mode", ["always", "off"])
+def test_multi_pass_program_replays_as_a_cuda_graph(mode):
+    """Small states are launch-bound: from the third run on the same amplitudes a multi-pass compiled circuit
+    is one CUDA-graph launch (specialised or interpreter kernels alike).  Five runs must equal five oracle applications."""
+    q.jit_set_mode(mode)
+    n = 15
+    rng = np.random.default_rng(77)
+    g = H.random_gates(n, 150, rng)
+    c = q.Circuit(n).extend(g)
+    prog = q.CompiledCircuit(c, specialise=(mode == "always"))
+    assert prog.n_passes >= 2
+    sim = q.Simulator(n)
+    st0 = H.random_state(n, rng)
+    sim.set_state(st0)
+    want = st0
+    for k in range(5):
+        sim.execute(prog)
+        want = H.oracle_run(n, g, want)
+        assert np.max(np.abs(sim.get_state_vector() - want)) < 1e-11, k
+    # another simulator, same program: captured again for the other amplitudes
+    sim2 = q.Simulator(n)
+    sim2.set_state(st0)
+    want = st0
+    for k in range(4):
+        sim2.execute(prog)
+        want = H.oracle_run(n, g, want)
+    assert np.max(np.abs(sim2.get_state_vector() - want)) < 1e-11
+    sim.execute(prog)      # and back on the first one
+    assert sim.launch_count() > 0

@@ -16,6 +16,7 @@ cases = {
     "z1": lambda: C(n).z(0),
     "x7high": lambda: (lambda c: [c.x(n - 1 - 2 * i) for i in range(7)] and c)(C(n)),
     "d200": lambda: q.create_random_circuit(n, 200, 1),
+    "dense": lambda: q.create_random_circuit(n, 200, 42),
 }
 sim = q.Simulator(n)
 prog = q.CompiledCircuit(cases[case]())
