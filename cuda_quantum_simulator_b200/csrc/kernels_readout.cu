@@ -20,6 +20,9 @@
 // (src/Simulator.cu:319-325) — with explicit __dmul_rn/__dadd_rn so nvcc cannot contract it.
 #include "readout.cuh"
 
+#include <cstdlib>
+#include <mutex>
+
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -872,6 +875,94 @@ void SequentialCdf::sample(const double* uniforms_host, int64_t n_shots, int64_t
     ++launches_;
     CUDA_CHECK(cudaMemcpyAsync(out_host, d_out, (size_t)n_shots * sizeof(int64_t), cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+
+// ---- small states (n <= 14): the whole CDF in one CTA's shared memory -------------------------------------------------
+// Below ~2^15 amplitudes the chunked machinery above is launch- and latency-bound (five kernels, two of them one warp
+// wide).  Here one CTA computes a TREE-order inclusive scan of the probabilities into shared memory and answers every shot
+// by binary search.  A sum of m non-negative terms differs from the exact sum by at most m * 2^-53 * total in ANY order, so
+// wherever the shot is farther than tau = 2^-37 * total (> 2 * 2^14 * 2^-53) from the neighbouring scan values the
+// reference's sequential sums C satisfy C[k-1] < u <= C[k] too; the (rare) shots inside that margin replay the sequential
+// sum from the amplitudes.  The result is the reference's index in every case (src/Simulator.cu:164-185).
+namespace {
+constexpr int kSmallThreads = 1024;
+
+__global__ void __launch_bounds__(kSmallThreads) small_cdf_sample_kernel(const cuDoubleComplex* __restrict__ state, uint32_t size,
+                                                                         const double* __restrict__ uniforms, int64_t n_shots,
+                                                                         int64_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    double* c = reinterpret_cast<double*>(small_smem);
+    __shared__ double warp_tot[kSmallThreads / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = size >= (uint32_t)kSmallThreads ? size / kSmallThreads : 1u;
+    const uint32_t i0 = tid * per;
+    double run = 0.0;
+    if (i0 < size)
+        for (uint32_t j = 0; j < per; ++j) { run = __dadd_rn(run, prob_of(state[i0 + j])); c[i0 + j] = run; }
+    double incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += up;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    double offset = incl - run, total = 0.0;
+    for (uint32_t w = 0; w < kSmallThreads / 32; ++w) {
+        if (w < warp) offset += warp_tot[w];
+        total += warp_tot[w];
+    }
+    if (i0 < size && offset != 0.0)
+        for (uint32_t j = 0; j < per; ++j) c[i0 + j] += offset;
+    __syncthreads();
+    const double tau = total * 0x1.0p-37;
+    for (int64_t shot = tid; shot < n_shots; shot += kSmallThreads) {
+        const double r = uniforms[shot];
+        uint32_t lo = 0, hi = size;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (c[mid] >= r) hi = mid; else lo = mid + 1; }
+        uint32_t k = lo;
+        bool sure;
+        if (k == 0) sure = (c[0] >= r);                               // C[0] = p[0] exactly
+        else if (k == size) sure = (r - c[size - 1] > tau);
+        else sure = (c[k] - r > tau) && (r - c[k - 1] > tau);
+        if (!sure) {                                                  // the reference's own loop
+            double C = 0.0;
+            k = size;
+            for (uint32_t i = 0; i < size; ++i) {
+                C = __dadd_rn(C, prob_of(state[i]));
+                if (C >= r) { k = i; break; }
+            }
+        }
+        out[shot] = (int64_t)k;
+    }
+}
+}  // namespace
+
+bool sample_small_state(const cuDoubleComplex* state, int n_qubits, const double* uniforms_host, int64_t n_shots,
+                        int64_t* out_host, Engine& eng) {
+    if (n_qubits > kSmallCdfMaxQubits || std::getenv("QSIM_NO_SMALL_CDF")) return false;
+    const uint32_t size = 1u << n_qubits;
+    const size_t smem = (size_t)size * sizeof(double);
+    static int configured_dev = -1;   // the shared-memory opt-in is a per-device attribute
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev != configured_dev) {
+        CUDA_CHECK(cudaFuncSetAttribute(small_cdf_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(sizeof(double) << kSmallCdfMaxQubits)));
+        configured_dev = dev;
+    }
+    cudaStream_t stream = eng.stream();
+    unsigned char* scratch = static_cast<unsigned char*>(eng.scratch(1, (size_t)n_shots * 16));
+    double* d_u = reinterpret_cast<double*>(scratch);
+    int64_t* d_out = reinterpret_cast<int64_t*>(scratch + (size_t)n_shots * 8);
+    CUDA_CHECK(cudaMemcpyAsync(d_u, uniforms_host, (size_t)n_shots * 8, cudaMemcpyHostToDevice, stream));
+    small_cdf_sample_kernel<<<1, kSmallThreads, smem, stream>>>(state, size, d_u, n_shots, d_out);
+    CUDA_CHECK_LAST_ERROR();
+    CUDA_CHECK(cudaMemcpyAsync(out_host, d_out, (size_t)n_shots * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    eng.countLaunch();
+    return true;
 }
 
 }  // namespace b200

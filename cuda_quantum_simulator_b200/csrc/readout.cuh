@@ -23,6 +23,12 @@ void marginal_probabilities(const cuDoubleComplex* state, int n_bits, const int*
 void launch_collapse(cuDoubleComplex* state, uint64_t n, int bit, int outcome, double scale, int num_sms,
                      cudaStream_t stream);
 
+// Small states: sampling in one launch of one CTA (tree-order scan in shared memory + exact replay inside the rounding
+// margin); false if the state is too large for it (the caller uses SequentialCdf).  Host in / host out.
+constexpr int kSmallCdfMaxQubits = 14;
+bool sample_small_state(const cuDoubleComplex* state, int n_qubits, const double* uniforms_host, int64_t n_shots,
+                        int64_t* out_host, Engine& eng);
+
 // Exact sequential-order fp64 prefix sums of the (optionally masked) probabilities, kept as the
 // running sum at every 4096-element chunk boundary.
 class SequentialCdf {

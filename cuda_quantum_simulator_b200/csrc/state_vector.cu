@@ -245,8 +245,9 @@ int StateVector::measure(int qubit) {
 
 std::vector<int64_t> StateVector::sampleWithUniforms(const double* uniforms, int64_t n_shots) {
     if (n_shots <= 0) throw std::invalid_argument("n_shots must be positive");
-    b200::SequentialCdf cdf(devicePtr(), size_, -1, *engine_);
     std::vector<int64_t> out((size_t)n_shots);
+    if (b200::sample_small_state(devicePtr(), num_qubits_, uniforms, n_shots, out.data(), *engine_)) return out;
+    b200::SequentialCdf cdf(devicePtr(), size_, -1, *engine_);
     cdf.sample(uniforms, n_shots, out.data());
     engine_->countLaunch(cdf.launches());
     return out;

@@ -72,13 +72,13 @@ def test_sampling_flat_and_sparse_states():
     assert set(out.tolist()) <= {0, (1 << n) - 1}
 
 
+@pytest.mark.parametrize("n", [14, 20])      # 14: the one-CTA small-state path (scan + exact replay inside the margin)
 @pytest.mark.parametrize("shape", ["plateau_half", "noise_tail", "ties", "tiny_head", "over_one"])
-def test_sampling_hard_cdf_shapes(shape):
+def test_sampling_hard_cdf_shapes(shape, n):
     """States that stress the exact parallel CDF (csrc/kernels_readout.cu): the running sum parked on a power of two
     over many chunks, a long tail of ~1e-34 probabilities after the sum has reached ~1, terms that round on exact ties,
     a head of tiny probabilities (many binades per chunk), and a sum that passes 1.0.  All must equal the host's
     sequential algorithm bit for bit — and stay fast (the replay path is sequential)."""
-    n = 20
     N = 1 << n
     rng = np.random.default_rng(77)
     amp = np.zeros(N, np.complex128)
