@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the oracle parity check before timing")
     ap.add_argument("--no-c4", action="store_true", help="N = 8: skip the 36-qubit C4 leg (128 GiB shards)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"])
+    ap.add_argument("--sharded-driver", default="native", choices=["native", "python"],
+                    help="N > 1: qsim::ShardedSimulator (C++ over NCCL, default) or the Python driver")
     return ap.parse_args()
 
 
@@ -177,7 +179,14 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def sharded_parity_check(exchange, rank, world):
+def make_sharded(n, exchange, driver):
+    """The sharded simulator: the C++ driver qsim::ShardedSimulator (NCCL called from C++; torch.distributed only hands
+    the NCCL unique id around) or the Python driver (same surface)."""
+    from cuda_quantum_simulator_b200 import sharded
+    return sharded.NativeShardedSimulator(n, exchange=exchange) if driver == "native" else sharded.ShardedSimulator(n, exchange=exchange)
+
+
+def sharded_parity_check(exchange, rank, world, drivers=("native", "python")):
     """N > 1 only, before anything is timed: the sharded engine against the CPU oracle on circuits that REALLY exchange
     (24 and 22 qubits forced over `world` shards; identity layout so the gate on the top qubit needs a global<->local swap,
     and a 300-gate circuit that targets every qubit), once with the exchange fused into the preceding pass and once as
@@ -186,21 +195,20 @@ def sharded_parity_check(exchange, rank, world):
     import numpy as np
     import cuda_quantum_simulator_b200 as q
     import helpers as H
-    from cuda_quantum_simulator_b200.sharded import ShardedSimulator
-    out = {"max_abs_err": 0.0, "exchanges": 0, "fused": 0, "cases": [], "sampling_bit_identical": True,
+    out = {"drivers": list(drivers), "max_abs_err": 0.0, "exchanges": 0, "fused": 0, "cases": [], "sampling_bit_identical": True,
            "marginal_max_err": 0.0, "measure_ok": True, "tolerance": 1e-10}
     cases = (("createRandomCircuit(24,40,7) identity layout", 24, 40, 7, False),
              ("createRandomCircuit(22,300,11) free layout", 22, 300, 11, True))
-    for mode in ("fused", "separate"):
+    for driver, mode in [(d, m) for d in drivers for m in ("fused", "separate")]:
         if mode == "separate":
             os.environ["QSIM_NO_FUSED_EXCHANGE"] = "1"
         try:
             for label, n, depth, seed, free_layout in cases:
                 c = q.create_random_circuit(n, depth, seed)
-                sim = ShardedSimulator(n, exchange=exchange)
-                sim._pristine = free_layout
+                sim = make_sharded(n, exchange, driver)
+                sim.identity_layout_only(not free_layout)
                 cp = sim.compile(c)
-                f0 = sim.engine.fused_exchanges
+                f0 = sim.fused_exchanges
                 sim.execute(cp)
                 got = sim.get_state_vector()
                 want = H.oracle_run(n, c.gates)
@@ -223,11 +231,11 @@ def sharded_parity_check(exchange, rank, world):
                     keep = ((idx >> (n - 1)) & 1) == res
                     want_c = np.where(keep, got, 0) / np.sqrt(p0 if res == 0 else 1 - p0)
                     meas_ok = res == (0 if r < p0 else 1) and float(np.max(np.abs(sim.get_state_vector() - want_c))) < 1e-10
-                out["cases"].append({"circuit": label, "mode": mode, "exchange": sim.engine.exchange, "swaps": cp.n_swaps,
-                                     "fused_into_a_pass": sim.engine.fused_exchanges - f0, "max_abs_err": err})
+                out["cases"].append({"circuit": label, "driver": driver, "mode": mode, "exchange": sim.exchange, "swaps": cp.n_swaps,
+                                     "fused_into_a_pass": sim.fused_exchanges - f0, "max_abs_err": err})
                 out["max_abs_err"] = max(out["max_abs_err"], err)
                 out["exchanges"] += cp.n_swaps
-                out["fused"] += sim.engine.fused_exchanges - f0
+                out["fused"] += sim.fused_exchanges - f0
                 out["sampling_bit_identical"] &= samp_ok
                 out["marginal_max_err"] = max(out["marginal_max_err"], merr)
                 out["measure_ok"] &= bool(meas_ok)
@@ -277,10 +285,9 @@ def main():
         n_passes, n_swaps = prog.n_passes, 0
         runner = sim
     else:
-        from cuda_quantum_simulator_b200.sharded import ShardedSimulator
         parity = None
         if not args.no_parity_check:
-            parity = sharded_parity_check(args.exchange, rank, world)
+            parity = sharded_parity_check(args.exchange, rank, world, ("native", "python") if args.sharded_driver == "native" else ("python",))
             flag = torch.tensor([0.0 if parity["passed"] else 1.0], device="cuda")
             dist.all_reduce(flag)
             if flag.item() != 0:
@@ -288,7 +295,7 @@ def main():
                     print(json.dumps({"parity_check": parity, "error": "sharded parity check failed"}), flush=True)
                 dist.destroy_process_group()
                 sys.exit(1)
-        runner = ShardedSimulator(n, exchange=args.exchange)
+        runner = make_sharded(n, args.exchange, args.sharded_driver)
         # one plan per step: a run may leave a different qubit layout / X frame behind than it started from, and a plan is
         # only valid for the layout it was compiled against (plans are shared when the layout repeats)
         plans = runner.compile_sequence(circuit, 1 + args.warmup + args.steps)
@@ -380,7 +387,7 @@ def main():
         else:
             runner.reset()
             dplans = runner.compile_sequence(dcirc, 4)
-            f0 = runner.engine.fused_exchanges
+            f0 = runner.fused_exchanges
             d_no = [0]
 
             def dstep():
@@ -389,17 +396,17 @@ def main():
             d_info = {"passes_per_step": [p_.n_passes for p_ in dplans[1:]],
                       "global_qubit_swaps_per_step": [p_.n_swaps for p_ in dplans[1:]]}
         dstep()
-        f1 = runner.engine.fused_exchanges if world > 1 else 0
+        f1 = runner.fused_exchanges if world > 1 else 0
         d_ms = timed(dstep, 3) / 3
         if world > 1:
-            d_info["exchanges_fused_into_a_pass_in_the_timed_steps"] = runner.engine.fused_exchanges - f1
+            d_info["exchanges_fused_into_a_pass_in_the_timed_steps"] = runner.fused_exchanges - f1
         dense = dict(workload=f"createRandomCircuit({n},200,{args.seed})", gates=dcirc.get_gate_count(), ms_per_step=d_ms,
                      value=dcirc.get_gate_count() * 2.0 ** (n - 30) / (d_ms * 1e-3), **d_info)
 
     # ---- NVLink leg of a global-qubit swap, timed on its own (two swaps = there and back) ---------------
     nvlink = None
     if world > 1:
-        eng = runner.engine
+        eng = runner
         g, l = n - 1, n_local - 1
         eng.swap(g, l); eng.swap(g, l)
         sync_all()
@@ -421,36 +428,41 @@ def main():
     forced = None
     if world > 1:
         def forced_run(circ, sim_, k):
-            """k timed steps of `circ` from the identity layout (no free initial layout): per-step plans, device time."""
+            """k timed steps of `circ`, every one from the IDENTITY qubit layout (no free initial layout), so that the gate
+            on the top qubit needs its global<->local exchange every time: between steps the stored layout is declared to be
+            the identity again (relabel_identity: bookkeeping only, no data moves; the state changes by a qubit permutation,
+            which a dense state does not care about).  Device time."""
+            sim_.identity_layout_only(True)
             sim_.reset()
-            sim_._pristine = False                       # keeps compile() from choosing a layout: identity
-            seq = sim_.compile_sequence(circ, 1 + k)
-            no = [0]
+            first = sim_.compile(circ)                   # from |0..0>, identity layout
+            f_a = sim_.fused_exchanges
+            sim_.execute(first)                          # untimed (basis-state input)
+            f_b = sim_.fused_exchanges
+            sim_.relabel_identity()
+            plan_ = sim_.compile(circ)                   # against a dense state in the identity layout
 
             def st():
-                sim_.execute(seq[no[0]])
-                no[0] += 1
-            f_a = sim_.engine.fused_exchanges
-            st()                                         # from |0..0> (basis-state input), untimed
-            f_b = sim_.engine.fused_exchanges
+                sim_.relabel_identity()
+                sim_.execute(plan_)
+            st()
+            f_c = sim_.fused_exchanges
             ms = timed(st, k) / k
-            info = {"ms_per_step": ms, "passes_per_step": [p_.n_passes for p_ in seq[1:]],
-                    "swaps_per_step": [p_.n_swaps for p_ in seq[1:]],
-                    "swaps_first_step_from_zero_state": seq[0].n_swaps,
-                    "fused_into_a_pass": sim_.engine.fused_exchanges - f_b,
-                    "fused_first_step": f_b - f_a}
-            return info, seq
+            info = {"ms_per_step": ms, "passes_per_step": plan_.n_passes, "swaps_per_step": plan_.n_swaps,
+                    "fused_into_a_pass_per_step": (sim_.fused_exchanges - f_c) / k, "fused_first_step_from_zero_state": f_b - f_a}
+            sim_.identity_layout_only(False)
+            return info, plan_
         k_f = 4
-        f_info, seq = forced_run(circuit, runner, k_f)
+        f_info, fplan = forced_run(circuit, runner, k_f)
         pass_ms_1 = pass_ms / max(passes_timed, 1)
         link_ms = nvlink["ms"]
-        ideal = sum(max(p_.n_passes * pass_ms_1, p_.n_swaps * link_ms) for p_ in seq[1:]) / k_f
+        ideal = max(fplan.n_passes * pass_ms_1, fplan.n_swaps * link_ms)
         forced = dict(workload=f"createRandomCircuit({n},{args.depth},{args.seed}), identity qubit layout (QSIM_NO_LAYOUT semantics)",
-                      exchange=runner.engine.exchange, pass_ms=pass_ms_1, link_ms=link_ms,
+                      exchange=runner.exchange, driver=args.sharded_driver, pass_ms=pass_ms_1, link_ms=link_ms,
                       ideal_ms_per_step=ideal, overlap_eff=ideal / f_info["ms_per_step"],
                       value=n_gates * 2.0 ** (n - 30) / (f_info["ms_per_step"] * 1e-3),
-                      what="overlap_eff = mean over steps of max(passes * pass_ms, swaps * link_ms) / measured ms per step; pass_ms = "
-                           "the headline pass, link_ms = the nvlink leg above", **f_info)
+                      what="every timed step runs 1 pass + 1 global<->local exchange (fused into the pass when the second buffer "
+                           "exists); overlap_eff = max(passes * pass_ms, swaps * link_ms) / measured ms per step; pass_ms = the "
+                           "headline pass, link_ms = the separate-swap nvlink leg above", **f_info)
 
     # ---- BASELINE config C4 for real: createRandomCircuit(36,20,42) over 8 GPUs, 128 GiB shards --------------------------
     c4 = None
@@ -467,9 +479,9 @@ def main():
     if world == 8 and n_local == 30 and not args.no_c4 and fits.item() == 0:
         c4 = {"skipped": f"a 128 GiB shard does not fit next to what is resident (free on rank 0: {free_b / 2**30:.0f} GiB)"}
     elif world == 8 and n_local == 30 and not args.no_c4:
-        r4 = ShardedSimulator(n4, exchange=args.exchange)
+        r4 = make_sharded(n4, args.exchange, args.sharded_driver)
         c4 = {"workload": "createRandomCircuit(36,20,42), 2^33 amplitudes (128 GiB) per GPU", "gates": c4circ.get_gate_count(),
-              "second_buffer_for_fused_exchange": len(r4.engine._bufs) > 1, "exchange": r4.engine.exchange}
+              "second_buffer_for_fused_exchange": r4.has_second_buffer, "exchange": r4.exchange, "driver": args.sharded_driver}
         # (a) layout chosen from |0..0>
         seq = r4.compile_sequence(c4circ, 3)
         no = [0]
@@ -485,7 +497,7 @@ def main():
         tot = r4.get_total_probability()
         c4["total_probability"] = tot
         # (b) identity layout: H(35) needs the 64 GiB-each-way exchange
-        f_info, seq = forced_run(c4circ, r4, 2)
+        f_info, _fp = forced_run(c4circ, r4, 2)
         c4["identity_layout"] = f_info
         c4["identity_layout"]["total_probability"] = r4.get_total_probability()
         r4.close()
@@ -513,6 +525,7 @@ def main():
         "config": {"workload": workload_name(n, args.depth, args.seed, n_local),
                    "gates": n_gates, "passes": n_passes, "global_qubit_swaps": n_swaps, "qubits": n,
                    "local_qubits": n_local,
+                   "sharded_driver": args.sharded_driver if world > 1 else None,
                    "parallelism": f"shard {n_global} qubit(s) over {world} GPU(s); from |0..0> the layout puts qubits that are "
                                   f"never a non-diagonal target in the rank bits (no exchange for this circuit)"
                                   if world > 1 else "one GPU",

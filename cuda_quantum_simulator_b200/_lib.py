@@ -137,6 +137,7 @@ def _declare(L: ctypes.CDLL) -> None:
         "qsim_sharded_layout": (c_int, [P, P, POINTER(c_uint64)]),
         "qsim_sharded_set_identity_layout_only": (c_int, [P, c_int]),
         "qsim_sharded_swap": (c_int, [P, c_int, c_int]),
+        "qsim_sharded_relabel_identity": (c_int, [P]),
         "qsim_sharded_info": (c_int, [P, POINTER(c_int64)]),
         "qsim_sharded_local": (c_void_p, [P]),
         "qsim_sharded_set_stream": (c_int, [P, P]),

@@ -783,6 +783,10 @@ qsim_status_t qsim_sharded_set_identity_layout_only(qsim_sharded_t* h, int on) {
     return guarded([&] { require(h != nullptr, "null simulator"); h->sim->setIdentityLayoutOnly(on != 0); });
 }
 
+qsim_status_t qsim_sharded_relabel_identity(qsim_sharded_t* h) {
+    return guarded([&] { require(h != nullptr, "null simulator"); h->sim->relabelIdentity(); });
+}
+
 qsim_status_t qsim_sharded_swap(qsim_sharded_t* h, int global_position, int local_position) {
     return guarded([&] { require(h != nullptr, "null simulator"); h->sim->swapQubits(global_position, local_position); });
 }
@@ -799,6 +803,7 @@ qsim_status_t qsim_sharded_info(const qsim_sharded_t* h, int64_t info[8]) {
         info[4] = ex == "p2p" ? 1 : (ex == "nccl" ? 2 : 0);
         info[5] = h->sim->rank();
         info[6] = h->sim->worldSize();
+        info[7] = h->sim->hasSecondBuffer() ? 1 : 0;
     });
 }
 

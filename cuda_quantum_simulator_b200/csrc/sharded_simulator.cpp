@@ -481,6 +481,13 @@ void ShardedSimulator::run(const Circuit& circuit) {
 
 // ---- layout ---------------------------------------------------------------------------------------------------------
 
+void ShardedSimulator::relabelIdentity() {
+    for (int q = 0; q < n_; ++q) perm_[q] = q;
+    frame_ = 0;
+    pristine_ = false;
+    order_preserving_ = true;
+}
+
 void ShardedSimulator::restoreIdentityLayout() {
     std::vector<int> perm = perm_;
     uint64_t frame = frame_;

@@ -430,7 +430,7 @@ class ShardedSimulator:
             raise _lib.InvalidArgument("Circuit qubit count doesn't match simulator")
         start_perm = list(self.perm)
         chose = False
-        if self._pristine and self.ng > 0 and os.environ.get("QSIM_NO_LAYOUT") is None:
+        if self._pristine and self.ng > 0 and os.environ.get("QSIM_NO_LAYOUT") is None and not getattr(self, "_identity_only", False):
             start_perm = choose_initial_layout(self.n, self.ng, circuit.gates)   # carried by the plan, applied by execute()
             chose = True
         plan = plan_circuit(self.n, self.ng, circuit.gates, start_perm)
@@ -483,6 +483,25 @@ class ShardedSimulator:
         # (the parked qubits have one value in every non-zero amplitude and the others keep their relative order)
         self._order_preserving = (self._order_preserving if not self._pristine else True) and cp.n_swaps == 0
         self._pristine = False
+
+    def identity_layout_only(self, on: bool = True):
+        """Never choose a layout for |0...0> (benchmarks of the exchange path)."""
+        self._identity_only = bool(on)
+
+    def relabel_identity(self):
+        """Declares the stored layout to be the identity WITHOUT moving data (a relabelling of the logical qubits)."""
+        self.perm = list(range(self.n))
+        self.frame = 0
+        self._pristine = False
+        self._order_preserving = True
+
+    @property
+    def has_second_buffer(self) -> bool: return len(getattr(self.engine, "_bufs", [])) > 1
+    @property
+    def fused_exchanges(self) -> int: return int(getattr(self.engine, "fused_exchanges", 0))
+    @property
+    def exchange(self) -> str: return getattr(self.engine, "exchange", "none")
+    def swap(self, g: int, l: int): self.engine.swap(g, l)
 
     def compile_sequence(self, circuit: Circuit, k: int) -> List[CompiledPlan]:
         """Plans for k consecutive runs of `circuit` starting from the current state: run i is compiled against the layout
@@ -846,6 +865,9 @@ class NativeShardedSimulator:
     def barrier(self): _lib.check(_lib.lib().qsim_sharded_barrier(self._h))
     def swap(self, global_position: int, local_position: int): _lib.check(_lib.lib().qsim_sharded_swap(self._h, global_position, local_position))
     def restore_identity_layout(self): _lib.check(_lib.lib().qsim_sharded_restore_identity_layout(self._h))
+    def relabel_identity(self): _lib.check(_lib.lib().qsim_sharded_relabel_identity(self._h))
+    @property
+    def has_second_buffer(self) -> bool: return bool(self._info()[7])
 
     def run(self, circuit: Circuit):
         g = circuit.gates

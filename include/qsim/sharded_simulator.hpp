@@ -89,6 +89,10 @@ public:
     const std::vector<int>& permutation() const { return perm_; }
     uint64_t frame() const { return frame_; }
     void setIdentityLayoutOnly(bool on) { identity_only_ = on; }   // never choose a layout for |0...0> (measurement tools)
+    // Declares the stored layout to be the identity WITHOUT moving data: the logical qubits are relabelled (the state changes
+    // by a qubit permutation).  For benchmarks that need every step to start from the same layout.
+    void relabelIdentity();
+    bool hasSecondBuffer() const { return bufs_[1] != nullptr; }
     std::vector<std::complex<double>> getLocalState();             // this rank's shard, stored layout
     void setLocalState(const std::complex<double>* amplitudes);
     cuDoubleComplex* devicePtr();

@@ -274,9 +274,12 @@ QSIM_API qsim_status_t qsim_sharded_restore_identity_layout(qsim_sharded_t* h);
 /* perm_out[q] = physical index bit that holds logical qubit q; frame_out = pending X mask over physical bits (rank bits only). */
 QSIM_API qsim_status_t qsim_sharded_layout(const qsim_sharded_t* h, int* perm_out, uint64_t* frame_out);
 QSIM_API qsim_status_t qsim_sharded_set_identity_layout_only(qsim_sharded_t* h, int on);   /* never choose a layout for |0..0> */
+/* Declares the stored layout to be the identity without moving data: a relabelling of the logical qubits (the state changes
+ * by a qubit permutation).  For benchmarks that need every step to start from the same layout. */
+QSIM_API qsim_status_t qsim_sharded_relabel_identity(qsim_sharded_t* h);
 QSIM_API qsim_status_t qsim_sharded_swap(qsim_sharded_t* h, int global_position, int local_position);   /* one separate exchange */
 /* info[0]=local qubits, [1]=rank qubits, [2]=exchanges fused into a pass, [3]=separate exchanges, [4]=1 peer memory / 2 NCCL,
- * [5]=rank, [6]=world size */
+ * [5]=rank, [6]=world size, [7]=1 if the second shard buffer of the fused exchange exists */
 QSIM_API qsim_status_t qsim_sharded_info(const qsim_sharded_t* h, int64_t info[8]);
 QSIM_API qsim_sim_t* qsim_sharded_local(qsim_sharded_t* h);   /* the shard as a qsim_sim_t (timing, launch counters); borrowed */
 QSIM_API qsim_status_t qsim_sharded_set_stream(qsim_sharded_t* h, void* cuda_stream);
