@@ -234,7 +234,7 @@ qsim_status_t qsim_jit_stats(int64_t out[8]) {
         require(out != nullptr, "null output");
         const b200::JitStats st = b200::jit_stats();
         out[0] = st.compiles; out[1] = st.cache_hits; out[2] = st.launches; out[3] = st.failures;
-        out[4] = (int64_t)(st.compile_seconds * 1e6); out[5] = st.last_cubin_bytes;
+        out[4] = (int64_t)(st.compile_seconds * 1e6); out[5] = st.disk_hits;
         out[6] = (int64_t)b200::jit_mode(); out[7] = b200::jit_min_qubits();
     });
 }

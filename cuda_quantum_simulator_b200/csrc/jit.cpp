@@ -3,6 +3,8 @@
 
 #include <dlfcn.h>
 #include <nvrtc.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <cstdio>
@@ -412,6 +414,68 @@ void init_mode_locked() {
     if (const char* e = std::getenv("QSIM_JIT_MIN_QUBITS")) g_min_qubits = std::atoi(e);
 }
 
+// ---- on-disk cache of compiled kernels: $QSIM_JIT_CACHE (default ~/.cache/qsim_b200/jit; "off" disables) ----
+// file = "QJ01" | u64 source length | generated source | cubin; the source is compared on load, so a hash collision or a
+// stale file from another library version (the embedded skeleton is part of the key) can only cost a recompile.
+std::string cache_dir() {
+    static std::string dir = [] {
+        std::string d;
+        if (const char* e = std::getenv("QSIM_JIT_CACHE")) d = e;
+        else if (const char* h = std::getenv("HOME")) d = std::string(h) + "/.cache/qsim_b200/jit";
+        if (d == "off" || d == "0") d.clear();
+        if (!d.empty()) {   // mkdir -p
+            for (size_t i = 1; i <= d.size(); ++i)
+                if (i == d.size() || d[i] == '/') ::mkdir(d.substr(0, i).c_str(), 0755);
+        }
+        return d;
+    }();
+    return dir;
+}
+
+std::string cache_path(uint64_t key) {
+    char name[64];
+    std::snprintf(name, sizeof(name), "/%016llx.qjit", (unsigned long long)key);
+    return cache_dir() + name;
+}
+
+bool cache_load(uint64_t key, const std::string& source, std::vector<char>& cubin) {
+    if (cache_dir().empty()) return false;
+    FILE* f = std::fopen(cache_path(key).c_str(), "rb");
+    if (!f) return false;
+    bool ok = false;
+    char magic[4];
+    uint64_t len = 0;
+    if (std::fread(magic, 1, 4, f) == 4 && std::memcmp(magic, "QJ01", 4) == 0 && std::fread(&len, 8, 1, f) == 1 && len == source.size()) {
+        std::string src(len, '\0');
+        if (std::fread(&src[0], 1, len, f) == len && src == source) {
+            const long pos = std::ftell(f);
+            std::fseek(f, 0, SEEK_END);
+            const long end = std::ftell(f);
+            std::fseek(f, pos, SEEK_SET);
+            if (end > pos) {
+                cubin.resize((size_t)(end - pos));
+                ok = std::fread(cubin.data(), 1, cubin.size(), f) == cubin.size();
+            }
+        }
+    }
+    std::fclose(f);
+    return ok;
+}
+
+void cache_store(uint64_t key, const std::string& source, const std::vector<char>& cubin) {
+    if (cache_dir().empty()) return;
+    const std::string path = cache_path(key), tmp = path + ".tmp" + std::to_string((long)::getpid());
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    const uint64_t len = source.size();
+    const bool ok = std::fwrite("QJ01", 1, 4, f) == 4 && std::fwrite(&len, 8, 1, f) == 1 &&
+                    std::fwrite(source.data(), 1, source.size(), f) == source.size() &&
+                    std::fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    std::fclose(f);
+    if (ok) std::rename(tmp.c_str(), path.c_str());
+    else std::remove(tmp.c_str());
+}
+
 uint64_t fnv1a(const std::string& s) {
     uint64_t h = 1469598103934665603ULL;
     for (unsigned char c : s) { h ^= c; h *= 1099511628211ULL; }
@@ -472,7 +536,8 @@ std::string jit_last_log() {
 std::shared_ptr<JitKernel> jit_get_kernel(const PassDesc& pd, const DevOp* ops, bool needs_device) {
     const JitMode mode = jit_mode();
     const std::string compute = jit_generate_compute(pd, ops);
-    const uint64_t key = fnv1a(compute) ^ ((uint64_t)QSIM_REG_BITS << 56);
+    static const uint64_t skeleton = fnv1a(kSrcPassDesc) * 31 + fnv1a(kSrcPassDevice) * 17 + fnv1a(kSrcKernelBody);
+    const uint64_t key = fnv1a(compute) ^ ((uint64_t)QSIM_REG_BITS << 56) ^ (skeleton * 0x9E3779B97F4A7C15ULL);
     std::lock_guard<std::mutex> lock(g_mu);
     auto fail = [&](const std::string& what) -> std::shared_ptr<JitKernel> {
         ++g_stats.failures;
@@ -490,6 +555,25 @@ std::shared_ptr<JitKernel> jit_get_kernel(const PassDesc& pd, const DevOp* ops, 
         return it->second;
     }
     if (g_failed.count(key) && mode != JitMode::Always) return nullptr;
+    // a kernel of this structure compiled by an earlier process?
+    {
+        auto k = std::make_shared<JitKernel>();
+        if (cache_load(key, compute, k->cubin)) {
+            k->source = compute;
+            bool ok = true;
+            if (needs_device) {
+                cudaError_t e = cudaLibraryLoadData(&k->library, k->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+                if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->kernel, k->library, "qsim_jit_pass");
+                if (e != cudaSuccess) { cudaGetLastError(); ok = false; }
+            }
+            if (ok) {
+                ++g_stats.disk_hits;
+                g_stats.last_cubin_bytes = (int64_t)k->cubin.size();
+                g_cache[key] = k;
+                return k;
+            }
+        }
+    }
     const Nvrtc& rt = nvrtc();
     if (!rt.ok()) return fail(rt.why);
 
@@ -526,6 +610,7 @@ std::shared_ptr<JitKernel> jit_get_kernel(const PassDesc& pd, const DevOp* ops, 
             return fail(std::string("loading the compiled kernel failed: ") + cudaGetErrorString(e));
         }
     }
+    cache_store(key, compute, k->cubin);
     ++g_stats.compiles;
     g_stats.compile_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     g_stats.last_cubin_bytes = (int64_t)cb;

@@ -8,7 +8,8 @@
 // controls become branches or static slot subsets — wraps it in the SAME skeleton (pass_kernel_body.inc: TMA ring, tile
 // stepping, basis-state input, fused exchange) and compiles it with NVRTC for sm_100a.  Matrix entries stay run-time data
 // (read from the staged op records), so the kernel depends only on the STRUCTURE of the pass: a variational loop that
-// re-runs a circuit with new angles hits the cache.
+// re-runs a circuit with new angles hits the cache.  Compiled kernels are also kept on disk ($QSIM_JIT_CACHE, default
+// ~/.cache/qsim_b200/jit, "off" disables), keyed by the generated source and the embedded skeleton.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -53,7 +54,7 @@ cudaError_t jit_launch(JitKernel& k, const PassParams& params, const void* tmap,
 size_t jit_copy_cubin(const JitKernel& k, void* out, size_t cap);
 
 struct JitStats {
-    int64_t compiles = 0, cache_hits = 0, launches = 0, failures = 0;
+    int64_t compiles = 0, cache_hits = 0, launches = 0, failures = 0, disk_hits = 0;
     double compile_seconds = 0;
     int64_t last_cubin_bytes = 0;
     int last_registers = 0;

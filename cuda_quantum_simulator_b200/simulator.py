@@ -69,7 +69,7 @@ def jit_stats() -> dict:
     out = (c_int64 * 8)()
     _lib.check(_lib.lib().qsim_jit_stats(out))
     return {"compiles": out[0], "cache_hits": out[1], "launches": out[2], "failures": out[3], "compile_seconds": out[4] / 1e6,
-            "last_cubin_bytes": out[5], "mode": ("off", "auto", "always")[out[6]], "min_qubits": out[7]}
+            "disk_hits": out[5], "mode": ("off", "auto", "always")[out[6]], "min_qubits": out[7]}
 
 
 class Simulator:

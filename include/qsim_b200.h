@@ -116,7 +116,8 @@ QSIM_API qsim_status_t qsim_program_info(const qsim_program_t* p, int64_t info[8
  * Environment: QSIM_JIT=off|auto|always, QSIM_JIT_MIN_QUBITS. */
 QSIM_API qsim_status_t qsim_jit_set_mode(int mode, int min_qubits);
 /* out[0]=kernels compiled, [1]=cache hits, [2]=specialised launches, [3]=failed compiles, [4]=compile time (us),
- * [5]=size of the last cubin, [6]=mode, [7]=min_qubits */
+ * [5]=kernels loaded from the on-disk cache ($QSIM_JIT_CACHE, default ~/.cache/qsim_b200/jit, "off" disables), [6]=mode,
+ * [7]=min_qubits */
 QSIM_API qsim_status_t qsim_jit_stats(int64_t out[8]);
 /* Marks a compiled program for specialisation whatever the state size: a pre-compiled circuit that will run many times is
  * worth one NVRTC compile per pass even below min_qubits (ignored in mode 0).  Takes effect at the next execute. */

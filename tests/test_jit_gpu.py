@@ -34,7 +34,8 @@ def test_specialised_kernels_are_what_runs():
     after = q.jit_stats()
     assert after["mode"] == "always"
     assert after["launches"] > before["launches"] and after["failures"] == before["failures"]
-    assert after["compiles"] + after["cache_hits"] > before["compiles"] + before["cache_hits"]
+    made = lambda st: st["compiles"] + st["cache_hits"] + st["disk_hits"]     # compiled now, or by an earlier run / process
+    assert made(after) > made(before)
     assert np.max(np.abs(got - H.oracle_run(n, g))) < 1e-12
     # the same structure with other angles is a cache hit, not a compile
     g2 = g.copy()
