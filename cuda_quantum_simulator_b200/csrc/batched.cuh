@@ -21,7 +21,21 @@ struct TrajEvent {       // one (channel, qubit) noise event; NoiseType order of
     int32_t type;
     int32_t qubit;
     double p;
+    double sqrt_keep;    // sqrt(1 - p): the no-jump scaling of the damping channels (filled by the host, see make_event)
+    double pad;
 };
+inline TrajEvent make_event(int type, int qubit, double p);
+
+}  // namespace b200
+}  // namespace qsim
+#include <cmath>
+namespace qsim {
+namespace b200 {
+inline TrajEvent make_event(int type, int qubit, double p) {
+    TrajEvent e{};
+    e.type = type; e.qubit = qubit; e.p = p; e.sqrt_keep = std::sqrt(1.0 - p); e.pad = 0.0;
+    return e;
+}
 
 constexpr int kTrajMaxQubits = 13;   // 2^13 amplitudes = 128 KiB of shared memory per trajectory
 

@@ -11,6 +11,7 @@
 #include "batched.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 
 #include "qsim/constants.hpp"
@@ -204,7 +205,7 @@ __device__ void damping_run(double2* s, int n, const TrajEvent* __restrict__ ev,
             for (int sl = 0; sl < NS; ++sl) R[sl] = 1.0;
             for (int j = 0; j < kk; ++j) {
                 const int q = ev[j].qubit;
-                const double r = sqrt(1.0 - ev[j].p);
+                const double r = ev[j].sqrt_keep;
                 if (q < 8) { if ((tid >> q) & 1u) fthr *= r; }
                 else {
                     const int b = q - 8;
@@ -235,8 +236,8 @@ __device__ __forceinline__ uint64_t event_id(uint64_t block, int e) { return (bl
 
 constexpr int kUniformChunk = kTrajThreads;   // uniforms are drawn kTrajThreads events at a time, one event per thread
 
-template <int NS>
-__global__ void __launch_bounds__(kTrajThreads) trajectory_kernel(cuDoubleComplex* __restrict__ states, int n, int64_t batch,
+template <int NS, int MINB>
+__global__ void __launch_bounds__(kTrajThreads, MINB) trajectory_kernel(cuDoubleComplex* __restrict__ states, int n, int64_t batch,
                                                                   const TrajItem* __restrict__ items, int n_items,
                                                                   const TrajEvent* __restrict__ events, int n_events,
                                                                   uint32_t seed, uint64_t traj_offset,
@@ -339,6 +340,8 @@ __global__ void batched_average_kernel(const cuDoubleComplex* __restrict__ state
     }
 }
 
+__device__ __forceinline__ uint32_t pad(uint32_t i) { return i + (i >> 4); }
+
 // Sampling: one CTA per trajectory.  The reference draws from the SEQUENTIAL fp64 prefix sums of the probabilities
 // (std::partial_sum + lower_bound, src/NoiseModel.cu:938-957).  A sum of m non-negative terms differs from the exact sum by
 // at most m * 2^-53 * total whatever the order, so a block-wide tree-order scan (approximate CDF c~) decides every shot whose
@@ -351,22 +354,24 @@ __global__ void __launch_bounds__(kTrajThreads) batched_sample_kernel(const cuDo
     extern __shared__ __align__(16) unsigned char samp_smem[];
     const uint32_t size = 1u << n, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    // (both arrays are indexed through pad(): one spare double per 16, so that the threads' contiguous 16-element segments
+    //  start in different banks - without it the segment scans are 32-way bank conflicts)
     double* p = reinterpret_cast<double*>(samp_smem);   // probabilities, rounded as std::norm
-    double* c = p + size;                               // tree-order inclusive prefix sums
+    double* c = p + pad(size);                          // tree-order inclusive prefix sums
     __shared__ double warp_tot[kTrajThreads / 32];
     const uint32_t per = size >= (uint32_t)kTrajThreads ? size / kTrajThreads : 1u;
     for (int64_t traj = blockIdx.x; traj < batch; traj += gridDim.x) {
         const cuDoubleComplex* a = states + (size_t)traj * size;
         for (uint32_t i = tid; i < size; i += kTrajThreads) {
             const cuDoubleComplex v = a[i];
-            p[i] = __dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y));
+            p[pad(i)] = __dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y));
         }
         __syncthreads();
         // thread t scans its contiguous segment, then the segment totals are scanned across the block
         const uint32_t i0 = tid * per;
         double run = 0.0;
         if (i0 < size)
-            for (uint32_t j = 0; j < per; ++j) { run = __dadd_rn(run, p[i0 + j]); c[i0 + j] = run; }
+            for (uint32_t j = 0; j < per; ++j) { run = __dadd_rn(run, p[pad(i0 + j)]); c[pad(i0 + j)] = run; }
         double incl = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -380,23 +385,23 @@ __global__ void __launch_bounds__(kTrajThreads) batched_sample_kernel(const cuDo
         double total = 0.0;
         for (int w = 0; w < kTrajThreads / 32; ++w) total += warp_tot[w];
         if (i0 < size && offset != 0.0)
-            for (uint32_t j = 0; j < per; ++j) c[i0 + j] += offset;
+            for (uint32_t j = 0; j < per; ++j) c[pad(i0 + j)] += offset;
         __syncthreads();
         const double tau = total * 0x1.0p-38;
         for (int shot = tid; shot < n_shots; shot += kTrajThreads) {
             const double r = uniforms[(size_t)traj * n_shots + shot];
             uint32_t lo = 0, hi = size;
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (c[mid] >= r) hi = mid; else lo = mid + 1; }
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (c[pad(mid)] >= r) hi = mid; else lo = mid + 1; }
             uint32_t k = lo;
             bool sure;
             if (k == 0) sure = (p[0] >= r);                               // C[0] = p[0] exactly
-            else if (k == size) sure = (r - c[size - 1] > tau);
-            else sure = (c[k] - r > tau) && (r - c[k - 1] > tau);
+            else if (k == size) sure = (r - c[pad(size - 1)] > tau);
+            else sure = (c[pad(k)] - r > tau) && (r - c[pad(k - 1)] > tau);
             if (!sure) {                                                  // the reference's own loop
                 double C = 0.0;
                 k = size;
                 for (uint32_t i = 0; i < size; ++i) {
-                    C = __dadd_rn(C, p[i]);
+                    C = __dadd_rn(C, p[pad(i)]);
                     if (C >= r) { k = i; break; }
                 }
             }
@@ -424,12 +429,24 @@ void launch_traj_ns(cuDoubleComplex* states, int n, int64_t batch, const TrajIte
                     cudaStream_t stream) {
     const size_t smem = ((size_t)16 << n) +
                         ((kTrajThreads / 32) * (kDampRun + 1) + (kDampRun + 2) + 2 * kUniformChunk) * sizeof(double);
-    CUDA_CHECK(cudaFuncSetAttribute(trajectory_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(224 * 1024) / (smem + 1024)));
+    // resident CTAs per SM: what shared memory allows (3 at 12 qubits), unless the register budget that goes with it costs more
+    // in spills than the occupancy brings (NS >= 16: 2 CTAs at 128 registers; QSIM_TRAJ_OCC=2|3 overrides, for measurements)
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(224 * 1024) / (smem + 1024)));
+    int minb = NS >= 16 ? 2 : 3;
+    if (const char* e = std::getenv("QSIM_TRAJ_OCC")) minb = std::atoi(e) >= 3 ? 3 : 2;
+    if (minb == 2) per_sm = std::min(per_sm, 2);
     const int64_t grid = std::min<int64_t>(batch, (int64_t)num_sms * per_sm);
-    trajectory_kernel<NS><<<(unsigned)grid, kTrajThreads, smem, stream>>>(states, n, batch, d_items, n_items, d_events, n_events, seed,
-                                                                         traj_offset, first_noise_block, d_avg,
-                                                                         1.0 / (double)batch);
+    if (minb == 3) {
+        CUDA_CHECK(cudaFuncSetAttribute(trajectory_kernel<NS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        trajectory_kernel<NS, 3><<<(unsigned)grid, kTrajThreads, smem, stream>>>(states, n, batch, d_items, n_items, d_events, n_events,
+                                                                                seed, traj_offset, first_noise_block, d_avg,
+                                                                                1.0 / (double)batch);
+    } else {
+        CUDA_CHECK(cudaFuncSetAttribute(trajectory_kernel<NS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        trajectory_kernel<NS, 2><<<(unsigned)grid, kTrajThreads, smem, stream>>>(states, n, batch, d_items, n_items, d_events, n_events,
+                                                                                seed, traj_offset, first_noise_block, d_avg,
+                                                                                1.0 / (double)batch);
+    }
     CUDA_CHECK_LAST_ERROR();
 }
 }  // namespace
@@ -468,7 +485,7 @@ void launch_batched_average(const cuDoubleComplex* states, int n, int64_t batch,
 
 void launch_batched_sample(const cuDoubleComplex* states, int n, int64_t batch, const double* d_uniforms, int n_shots,
                            int32_t* d_out, int32_t* d_hist, int num_sms, cudaStream_t stream) {
-    const size_t smem = (size_t)16 << n;
+    const size_t smem = 2 * sizeof(double) * (((size_t)1 << n) + ((size_t)1 << n) / 16 + 2);
     CUDA_CHECK(cudaFuncSetAttribute(batched_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(224 * 1024) / (smem + 1024)));
     const int64_t grid = std::min<int64_t>(batch, (int64_t)num_sms * per_sm);

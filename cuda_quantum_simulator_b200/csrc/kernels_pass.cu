@@ -384,13 +384,13 @@ __device__ __forceinline__ void interp_compute_tile(const PassParams& P, unsigne
 
 
 // worst case with three full stages must fit (pick_stages never has to go below the three the partner-tile store needs)
-static_assert(3 * (16 << kMaxTileBits) + (kMaxOpsPerPass + 1) * sizeof(DevOp) + kMaxPhaseOps * 13 * sizeof(double2) +
+static_assert(3 * (16 << kMaxTileBits) + (kMaxOpsPerPass + 1) * sizeof(DevOp) + 2 * kMaxPhaseOps * 13 * sizeof(double2) +
                       2 * 3 * sizeof(uint64_t) + (kMaxSweeps + 2) * kComputeThreads * sizeof(uint16_t) <=
                   (size_t)kMaxDynamicSmem,
               "shared-memory budget of a pass");
 
 size_t pass_smem_bytes(const PassDesc& pd, int stages) {
-    return (size_t)stages * ((size_t)16 << pd.t) + ((size_t)pd.n_ops + 1) * sizeof(DevOp) + (size_t)pd.n_phase * 13 * sizeof(double2) +
+    return (size_t)stages * ((size_t)16 << pd.t) + ((size_t)pd.n_ops + 1) * sizeof(DevOp) + 2 * (size_t)pd.n_phase * 13 * sizeof(double2) +
            2 * (size_t)stages * sizeof(uint64_t) + ((size_t)pd.n_sweeps + 2) * kComputeThreads * sizeof(uint16_t);
 }
 

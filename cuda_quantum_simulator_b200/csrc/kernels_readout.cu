@@ -892,14 +892,15 @@ __global__ void __launch_bounds__(kSmallThreads) small_cdf_sample_kernel(const c
                                                                          const double* __restrict__ uniforms, int64_t n_shots,
                                                                          int64_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char small_smem[];
-    double* c = reinterpret_cast<double*>(small_smem);
+    double* c = reinterpret_cast<double*>(small_smem);   // indexed through pad(): the threads' segments start in different banks
+    auto pad = [](uint32_t i) { return i + (i >> 4); };
     __shared__ double warp_tot[kSmallThreads / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t per = size >= (uint32_t)kSmallThreads ? size / kSmallThreads : 1u;
     const uint32_t i0 = tid * per;
     double run = 0.0;
     if (i0 < size)
-        for (uint32_t j = 0; j < per; ++j) { run = __dadd_rn(run, prob_of(state[i0 + j])); c[i0 + j] = run; }
+        for (uint32_t j = 0; j < per; ++j) { run = __dadd_rn(run, prob_of(state[i0 + j])); c[pad(i0 + j)] = run; }
     double incl = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -914,18 +915,18 @@ __global__ void __launch_bounds__(kSmallThreads) small_cdf_sample_kernel(const c
         total += warp_tot[w];
     }
     if (i0 < size && offset != 0.0)
-        for (uint32_t j = 0; j < per; ++j) c[i0 + j] += offset;
+        for (uint32_t j = 0; j < per; ++j) c[pad(i0 + j)] += offset;
     __syncthreads();
     const double tau = total * 0x1.0p-37;
     for (int64_t shot = tid; shot < n_shots; shot += kSmallThreads) {
         const double r = uniforms[shot];
         uint32_t lo = 0, hi = size;
-        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (c[mid] >= r) hi = mid; else lo = mid + 1; }
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (c[pad(mid)] >= r) hi = mid; else lo = mid + 1; }
         uint32_t k = lo;
         bool sure;
         if (k == 0) sure = (c[0] >= r);                               // C[0] = p[0] exactly
-        else if (k == size) sure = (r - c[size - 1] > tau);
-        else sure = (c[k] - r > tau) && (r - c[k - 1] > tau);
+        else if (k == size) sure = (r - c[pad(size - 1)] > tau);
+        else sure = (c[pad(k)] - r > tau) && (r - c[pad(k - 1)] > tau);
         if (!sure) {                                                  // the reference's own loop
             double C = 0.0;
             k = size;
@@ -943,13 +944,13 @@ bool sample_small_state(const cuDoubleComplex* state, int n_qubits, const double
                         int64_t* out_host, Engine& eng) {
     if (n_qubits > kSmallCdfMaxQubits || std::getenv("QSIM_NO_SMALL_CDF")) return false;
     const uint32_t size = 1u << n_qubits;
-    const size_t smem = (size_t)size * sizeof(double);
+    const size_t smem = ((size_t)size + size / 16 + 2) * sizeof(double);
     static int configured_dev = -1;   // the shared-memory opt-in is a per-device attribute
     int dev = 0;
     CUDA_CHECK(cudaGetDevice(&dev));
     if (dev != configured_dev) {
         CUDA_CHECK(cudaFuncSetAttribute(small_cdf_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sizeof(double) << kSmallCdfMaxQubits)));
+                                        (int)(sizeof(double) * ((1u << kSmallCdfMaxQubits) + (1u << kSmallCdfMaxQubits) / 16 + 2))));
         configured_dev = dev;
     }
     cudaStream_t stream = eng.stream();

@@ -34,11 +34,11 @@ std::vector<b200::TrajEvent> flatten(const std::vector<NoiseChannel>& channels, 
     std::vector<b200::TrajEvent> ev;
     for (const NoiseChannel& c : channels) {
         if (c.qubits.empty()) {
-            for (int q = 0; q < n; ++q) ev.push_back({static_cast<int32_t>(c.type), q, c.probability});
+            for (int q = 0; q < n; ++q) ev.push_back(b200::make_event(static_cast<int32_t>(c.type), q, c.probability));
         } else {
             for (int q : c.qubits) {
                 if (q < 0 || q >= n) throw std::out_of_range("Noise channel qubit out of range");
-                ev.push_back({static_cast<int32_t>(c.type), q, c.probability});
+                ev.push_back(b200::make_event(static_cast<int32_t>(c.type), q, c.probability));
             }
         }
     }

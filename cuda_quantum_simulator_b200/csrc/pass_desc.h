@@ -32,7 +32,8 @@ constexpr int kMaxSweeps = 12;
 constexpr int kMaxSegments = 14;
 constexpr int kMaxOpsPerPass = 120;      // ops of one pass are staged in shared memory (with kMaxSweeps and kMaxPhaseOps this
                                          // keeps three 64 KiB stages + tables within the 227 KiB of shared memory)
-constexpr int kMaxPhaseOps = 24;         // fused diagonal runs per pass (13 complex factors each in shared memory)
+constexpr int kMaxPhaseOps = 12;         // fused diagonal runs per pass (13 complex factors each in shared memory, two copies:
+                                         // the next tile's factors are computed while the current tile's are in use)
 constexpr int kPhaseTableSize = 1 << kMaxTileBits;   // one complex factor per tile-local index
 
 enum OpKind : uint8_t {
