@@ -184,3 +184,47 @@ def test_shard_run_rejects_x_on_a_rank_qubit():
         got.append(out)
         L.qsim_sim_destroy(h)
     assert np.max(np.abs(np.concatenate(got) - want)) < 1e-12
+
+
+def test_native_sharded_simulator_on_one_gpu():
+    """qsim::ShardedSimulator (the C++ driver) with a world of one rank: no exchange can happen, but planning, compiling,
+    plan validity, read-out (sampling in the reference's order, measurement on index bit n-1-q, marginals) all run through
+    the same C++ code the multi-GPU runs use, here against the oracle."""
+    import numpy as np
+
+    import cuda_quantum_simulator_b200 as q
+    from cuda_quantum_simulator_b200.sharded import NativeShardedSimulator
+
+    n = 13
+    rng = np.random.default_rng(31)
+    g = H.random_gates(n, 120, rng)
+    c = q.Circuit(n).extend(g)
+    sim = NativeShardedSimulator(n)
+    assert (sim.world, sim.nl, sim.ng, sim.exchange) == (1, n, 0, "none")
+    sim.run(c)
+    want = H.oracle_run(n, g)
+    assert np.max(np.abs(sim.get_state_vector() - want)) < 1e-12
+    plans = sim.compile_sequence(c, 2)
+    for p_ in plans:
+        sim.execute(p_)
+    want = H.oracle_run(n, g, H.oracle_run(n, g, want))
+    got = sim.get_state_vector()
+    assert np.max(np.abs(got - want)) < 1e-11
+    assert plans[0].n_swaps == 0 and plans[0].n_passes >= 1
+    u = np.concatenate([rng.random(300), [0.0, 0.5]])
+    assert np.array_equal(sim.sample(uniforms=u), H.oracle_sample(H.oracle_probs(got), u))
+    qs = [0, 7, n - 1]
+    idx = np.arange(1 << n)
+    oc = ((idx >> 0) & 1) | (((idx >> 7) & 1) << 1) | (((idx >> (n - 1)) & 1) << 2)
+    assert np.max(np.abs(sim.marginal(qs) - np.bincount(oc, weights=np.abs(got) ** 2, minlength=8))) < 1e-12
+    assert abs(sim.get_total_probability() - 1) < 1e-10
+    bit = n - 1 - 2
+    p0 = float(np.sum((np.abs(got) ** 2)[((idx >> bit) & 1) == 0]))
+    res = sim.measure_qubit(2, 0.5)
+    assert res == (0 if 0.5 < p0 else 1)
+    keep = ((idx >> bit) & 1) == res
+    want_c = np.where(keep, got, 0) / np.sqrt(p0 if res == 0 else 1 - p0)
+    assert np.max(np.abs(sim.get_state_vector() - want_c)) < 1e-11
+    with pytest.raises(q.InvalidArgument):
+        sim.run(q.Circuit(n - 1).h(0))
+    sim.close()
