@@ -4,20 +4,26 @@
 Workload (config.workload): `createRandomCircuit(n, 20, 42)` (reference src/Circuit.cpp:252-282) on an
 n-qubit fp64 state, n = 30 on one GPU (BASELINE configs[1], 16 GiB state) and n = 30 + log2(N) on N GPUs
 (weak scaling: every GPU keeps a 2^30-amplitude shard; non-diagonal gates on rank qubits go through NVLink exchanges,
-fused into the preceding pass — but from |0...0> the qubit layout is chosen so that this circuit needs none; the
-`dense_variant` object reports the depth-200 circuit of the same generator).
+fused into the preceding pass - but from |0...0> the qubit layout is chosen so that this circuit needs none).
 
 One "step" = one execution of the whole circuit on the resident state.
   value : gates * 2^(n-30) / s with the state and the compiled program already in HBM
           (= plain gates/s at 30 qubits; the 2^(n-30) factor makes the N-GPU number a whole-job aggregate).
   e2e   : the same through the public API from host inputs: reset -> run(circuit given as host gate records:
           compile + program upload) -> sample(1024 shots, host uniforms) -> indices back on the host.
-  roofline : fused_pass_kernel, algorithmic bytes 2*16*2^n_local per launch / its mean CUDA-event duration,
-          against MEASURED_PEAKS.json hbm_gbs.
+  roofline : the pass kernel (run-time specialised build at this size), algorithmic bytes 2*16*2^n_local per launch /
+          its mean CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline : the reference's own CPUSimulator (oracle/_ref, built from the unmodified reference) on the same
           generator at a bounded size, single thread (the reference CPU path has no threading).
+  dense_variant : createRandomCircuit(n, 200, seed), the depth-200 circuit of the same generator.
+  N > 1 only (the C++ driver qsim::ShardedSimulator unless --sharded-driver python):
+  parity_check : before anything is timed, the sharded engine against the CPU oracle on circuits that really exchange
+          (fused and separate exchanges, both drivers): amplitudes, logical-order sampling, marginals, measurement;
+          a mismatch ends the run with exit code 1.
+  nvlink : one separate global<->local swap, alone.   forced_exchange : the headline circuit from the identity layout,
+          1 pass + 1 exchange per step, and how well the two overlap.   c4 (N = 8) : the real 36-qubit circuit, 128 GiB shards.
 
-`--impl reference` times that CPU implementation alone (the reference arm).
+`--impl reference` times the reference CPU implementation alone (the reference arm): the REAL 30-qubit circuit.
 """
 import argparse
 import json
@@ -512,11 +518,17 @@ def main():
     bytes_per_pass = 2 * 16 * (1 << n_local)
     avg_pass_ms = pass_ms / max(passes_timed, 1)
     achieved = bytes_per_pass / (avg_pass_ms * 1e-3) / 1e9 if passes_timed else None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "pass_kernel_traffic.json")
-    if os.path.exists(tpath):
+    # DRAM traffic per launch: from the committed `ncu --set full` capture of this very kernel and workload (a number taken
+    # under a profiler is not re-measured inside a bench run); only meaningful for 30 local qubits
+    traffic, traffic_src = None, None
+    jit = q.jit_stats()
+    specialised = jit["launches"] > 0
+    tpath = os.path.join(ROOT, "profiles", "ncu_jit_pass_c2_30q_r02.json" if specialised else "pass_kernel_traffic.json")
+    if os.path.exists(tpath) and n_local == 30 and args.depth == 20 and args.seed == 42:
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic = tj["launches"][0]["dram_bytes_per_launch"] if "launches" in tj else tj.get("dram_bytes_per_launch")
+        traffic_src = f"committed ncu capture profiles/{os.path.basename(tpath)} (same kernel and workload; not measured in this run)"
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -531,8 +543,12 @@ def main():
                                   if world > 1 else "one GPU",
                    "l2": f"state ({16 * (1 << n_local) / 2**30:.0f} GiB/GPU) is far larger than the 126 MB L2: no flush needed",
                    "gates_per_s_raw": n_gates / (ms_per_step * 1e-3)},
-        "roofline": {"bound": "hbm", "kernel": "fused_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+        "roofline": {"bound": "hbm",
+                     "kernel": "qsim_jit_pass (the pass kernel specialised at run time for this pass, csrc/jit.cpp)" if specialised
+                               else "fused_pass_kernel (the pass kernel's ahead-of-time interpreter build)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_per_pass, "avg_launch_ms": avg_pass_ms,
                      "launches_timed": passes_timed,
                      "circuit_level_gbs": n_passes * bytes_per_pass / (ms_per_step * 1e-3) / 1e9},
@@ -544,6 +560,7 @@ def main():
                         "`value` is measured on the dense evolved state"},
         "gpu_launches": launches,
         "clocks": clocks,
+        "jit": jit,
     }
     if nvlink:
         line["nvlink"] = nvlink
