@@ -461,14 +461,24 @@ def main():
         f_info, fplan = forced_run(circuit, runner, k_f)
         pass_ms_1 = pass_ms / max(passes_timed, 1)
         link_ms = nvlink["ms"]
-        ideal = max(fplan.n_passes * pass_ms_1, fplan.n_swaps * link_ms)
+        # an exchange can only overlap the pass it is fused into (the next pass needs the exchanged data), so the ideal step is
+        # max(pass, link) per exchange plus the remaining passes
+        n_f = min(fplan.n_swaps, fplan.n_passes)
+        ideal = n_f * max(pass_ms_1, link_ms) + (fplan.n_passes - n_f) * pass_ms_1 + (fplan.n_swaps - n_f) * link_ms
+        fused_step_ms = (f_info["ms_per_step"] - (fplan.n_passes - n_f) * pass_ms_1) / max(n_f, 1)
+        half_bytes = 16 * (1 << (n_local - 1))
         forced = dict(workload=f"createRandomCircuit({n},{args.depth},{args.seed}), identity qubit layout (QSIM_NO_LAYOUT semantics)",
                       exchange=runner.exchange, driver=args.sharded_driver, pass_ms=pass_ms_1, link_ms=link_ms,
                       ideal_ms_per_step=ideal, overlap_eff=ideal / f_info["ms_per_step"],
                       value=n_gates * 2.0 ** (n - 30) / (f_info["ms_per_step"] * 1e-3),
-                      what="every timed step runs 1 pass + 1 global<->local exchange (fused into the pass when the second buffer "
-                           "exists); overlap_eff = max(passes * pass_ms, swaps * link_ms) / measured ms per step; pass_ms = the "
-                           "headline pass, link_ms = the separate-swap nvlink leg above", **f_info)
+                      fused_pass_plus_exchange_ms=fused_step_ms,
+                      nvlink_gbs_per_direction_in_the_fused_step=half_bytes / fused_step_ms / 1e6,
+                      nvlink_frac_of_770=half_bytes / fused_step_ms / 1e6 / 770.0,
+                      what="every timed step starts from the identity layout, so the gate on the top qubit needs its global<->local "
+                           "exchange every time; the exchange is fused into the pass before it when the second buffer exists. "
+                           "ideal = max(pass_ms, link_ms) per exchange + the remaining passes (an exchange can only overlap the pass "
+                           "it rides on); overlap_eff = ideal / measured; fused_pass_plus_exchange_ms = measured minus the unfused "
+                           "passes; pass_ms = the headline pass, link_ms = the separate-swap nvlink leg above", **f_info)
 
     # ---- BASELINE config C4 for real: createRandomCircuit(36,20,42) over 8 GPUs, 128 GiB shards --------------------------
     c4 = None
