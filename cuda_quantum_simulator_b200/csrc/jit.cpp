@@ -109,12 +109,35 @@ void emit_op(Gen& g, Slots& s, const PassDesc& pd, const SweepDesc& sd, const De
         if (!(present & (1u << 13)) && (present & (1u << 14)))
             g.line("{ const double2 t2_ = __ldg(tables + " + num((long long)op.cmask_out) + "); const double t_ = t2_.x * pr_ - t2_.y * pi_; "
                    "pi_ = t2_.x * pi_ + t2_.y * pr_; pr_ = t_; }");
+        // the table look-up goes to the COMPACT copy (indexed by the tile bits the run really depends on, op.tmask_thr):
+        // the thread's part of the index is gathered from base_local with literal shifts, the slot's part is a literal
+        const uint32_t dep = op.tmask_thr;
+        auto compact = [&](uint32_t l) {   // pext(l, dep)
+            uint32_t v = 0;
+            int c = 0;
+            for (int j = 0; j < kMaxTileBits; ++j)
+                if ((dep >> j) & 1u) { v |= ((l >> j) & 1u) << c; ++c; }
+            return v;
+        };
+        if (present & (1u << 13)) {
+            std::string expr;
+            int c = 0;
+            for (int j = 0; j < kMaxTileBits;) {
+                if (!((dep >> j) & 1u)) { ++j; continue; }
+                int len = 0;
+                while (j + len < kMaxTileBits && ((dep >> (j + len)) & 1u)) ++len;
+                const std::string term = "(((base_local >> " + num(j) + ") & " + hex32((1u << len) - 1u) + ") << " + num(c) + ")";
+                expr += (expr.empty() ? "" : " | ") + term;
+                c += len;
+                j += len;
+            }
+            g.line("const double2* tb_ = tables + " + num((long long)op.cval_thr) + " + (" + (expr.empty() ? std::string("0u") : expr) + ");");
+        }
         for (int k = 0; k < n_slots; ++k) {
             std::string fr = "fr" + num(k) + "_", fi = "fi" + num(k) + "_";
             if (present & (1u << 13)) {
-                g.line("double " + fr + ", " + fi + "; { const double2 t2_ = __ldg(tables + " + num((long long)op.cmask_out) +
-                       " + (base_local ^ " + hex32(sd.slot_off[k]) + ")); " + fr + " = t2_.x * pr_ - t2_.y * pi_; " + fi +
-                       " = t2_.x * pi_ + t2_.y * pr_; }");
+                g.line("double " + fr + ", " + fi + "; { const double2 t2_ = __ldg(tb_ + " + num((long long)compact(sd.slot_off[k])) +
+                       "); " + fr + " = t2_.x * pr_ - t2_.y * pi_; " + fi + " = t2_.x * pi_ + t2_.y * pr_; }");
             } else {
                 g.line("double " + fr + " = pr_, " + fi + " = pi_;");
             }

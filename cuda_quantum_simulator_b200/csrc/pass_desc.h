@@ -87,7 +87,8 @@ inline uint8_t op_code(uint8_t kind, uint8_t thome, uint8_t tbit, bool ctrl) {
     return (uint8_t)(kind * kOpcodesPerKind + home * 2 + (ctrl ? 1 : 0));
 }
 
-// OP_PHASE records reuse DevOp fields: cmask_out = first entry of the op's table in the pass's table blob,
+// OP_PHASE records reuse DevOp fields: cmask_out = first entry of the op's table in the pass's table blob (tmask_thr = the
+// tile bits that table really depends on, cval_thr = first entry of the COMPACT copy indexed by just those bits),
 // cval_out = first term in the pass's term array, tmask_out = slot of its (E_0..E_11, U) factors in shared
 // memory, tslots = number of terms; m[] viewed as uint16[14]: term range start of E_0..E_11, U, end.
 // A term multiplies one of those 13 factors when one (kind 0/1) or two (kind 2) index bits OUTSIDE the tile are set.

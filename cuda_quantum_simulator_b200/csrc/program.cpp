@@ -298,6 +298,30 @@ void encode_phase(Program& out, PassDesc& pd, const std::vector<int>& members, c
         out.phase_tables[base + 2 * l] = f.r;
         out.phase_tables[base + 2 * l + 1] = f.i;
     }
+    // The table only depends on the tile bits that carry an inside single or take part in an inside-inside pair - often a
+    // handful (a CRZ ladder inside a tile of which half the bits are idle low qubits).  A COMPACT copy indexed by just those
+    // bits (entry e = full entry at pdep(e, dep_mask)) follows the full one: a few hundred bytes to 2 KiB that stay in L1,
+    // where the full 64 KiB table is re-read from L2 for every tile (the specialised kernels index it with literals; the
+    // interpreter and the emulator keep the full table).
+    uint32_t dep_mask = 0;
+    for (int q = 0; q < 64; ++q)
+        if (inside(q) && (A[q].r != 1.0 || A[q].i != 0.0)) dep_mask |= 1u << local_of[q];
+    for (auto& e : B) {
+        const int p = e.first.first, q = e.first.second;
+        if (inside(p) && inside(q) && (e.second.r != 1.0 || e.second.i != 0.0)) dep_mask |= (1u << local_of[p]) | (1u << local_of[q]);
+    }
+    const int dep_bits = __builtin_popcount(dep_mask);
+    const size_t cbase = out.phase_tables.size();
+    out.phase_tables.resize(cbase + 2 * ((size_t)1 << dep_bits));
+    for (uint32_t e = 0; e < (1u << dep_bits); ++e) {
+        uint32_t l = 0, rest = e;
+        for (int j = 0; j < kMaxTileBits; ++j)
+            if ((dep_mask >> j) & 1u) { l |= (rest & 1u) << j; rest >>= 1; }
+        out.phase_tables[cbase + 2 * e] = out.phase_tables[base + 2 * (size_t)l];
+        out.phase_tables[cbase + 2 * e + 1] = out.phase_tables[base + 2 * (size_t)l + 1];
+    }
+    d.tmask_thr = dep_mask;                                                          // tile bits the table depends on
+    d.cval_thr = (uint32_t)((cbase / 2) - (size_t)pd.phase_table_offset);            // compact table, entry offset within the pass
     // terms with outside bits, grouped by the factor they feed: E_0..E_11, then U
     std::vector<std::vector<PhaseTerm>> groups(13);
     auto term = [&](int kind, int o, int j, Cx f) {
