@@ -304,7 +304,7 @@ def main():
         runner = make_sharded(n, args.exchange, args.sharded_driver)
         # one plan per step: a run may leave a different qubit layout / X frame behind than it started from, and a plan is
         # only valid for the layout it was compiled against (plans are shared when the layout repeats)
-        plans = runner.compile_sequence(circuit, 1 + args.warmup + args.steps)
+        plans = runner.compile_sequence(circuit, 1 + args.warmup + args.steps)   # (the first step is the untimed one from |0..0>)
         plan = plans[0]
         step_no = [0]
 
@@ -335,6 +335,8 @@ def main():
     # ---- kernel-resident throughput -------------------------------------------------------------
     step()   # untimed and not a warm-up step: the first pass after reset() generates |0..0> on chip; everything timed
              # below runs on the dense evolved state, loaded from and stored to HBM in full
+    q.jit_wait()   # the pass kernels specialised for this circuit are compiled in the background (a one-off cost per pass
+                   # structure, cached on disk; jit.compile_seconds in the line): the timed steps run the steady state
     for _ in range(args.warmup):
         step()
     sync_all()
@@ -371,6 +373,8 @@ def main():
         d2h = SHOTS * 8 + 8 * world
     for _ in range(2):
         e2e_step()
+    q.jit_wait()
+    e2e_step()
     sync_all()
     t0 = time.perf_counter()
     k_e2e = max(3, min(args.steps, 10))
@@ -392,15 +396,17 @@ def main():
             d_info = {"passes": dprog.n_passes, "global_qubit_swaps": 0}
         else:
             runner.reset()
-            dplans = runner.compile_sequence(dcirc, 4)
+            dplans = runner.compile_sequence(dcirc, 5)
             f0 = runner.fused_exchanges
             d_no = [0]
 
             def dstep():
                 runner.execute(dplans[d_no[0]])
                 d_no[0] += 1
-            d_info = {"passes_per_step": [p_.n_passes for p_ in dplans[1:]],
-                      "global_qubit_swaps_per_step": [p_.n_swaps for p_ in dplans[1:]]}
+            d_info = {"passes_per_step": [p_.n_passes for p_ in dplans[2:]],
+                      "global_qubit_swaps_per_step": [p_.n_swaps for p_ in dplans[2:]]}
+        dstep()
+        q.jit_wait()
         dstep()
         f1 = runner.fused_exchanges if world > 1 else 0
         d_ms = timed(dstep, 3) / 3
@@ -451,6 +457,8 @@ def main():
                 sim_.relabel_identity()
                 sim_.execute(plan_)
             st()
+            q.jit_wait()
+            st()
             f_c = sim_.fused_exchanges
             ms = timed(st, k) / k
             info = {"ms_per_step": ms, "passes_per_step": plan_.n_passes, "swaps_per_step": plan_.n_swaps,
@@ -499,17 +507,19 @@ def main():
         c4 = {"workload": "createRandomCircuit(36,20,42), 2^33 amplitudes (128 GiB) per GPU", "gates": c4circ.get_gate_count(),
               "second_buffer_for_fused_exchange": r4.has_second_buffer, "exchange": r4.exchange, "driver": args.sharded_driver}
         # (a) layout chosen from |0..0>
-        seq = r4.compile_sequence(c4circ, 3)
+        seq = r4.compile_sequence(c4circ, 4)
         no = [0]
 
         def st4():
             r4.execute(seq[no[0]])
             no[0] += 1
         st4()
+        q.jit_wait()
+        st4()
         ms = timed(st4, 2) / 2
-        c4["chosen_layout"] = {"ms_per_circuit": ms, "passes": seq[1].n_passes, "swaps_per_step": [p_.n_swaps for p_ in seq[1:]],
+        c4["chosen_layout"] = {"ms_per_circuit": ms, "passes": seq[2].n_passes, "swaps_per_step": [p_.n_swaps for p_ in seq[2:]],
                                "gates_per_s": c4circ.get_gate_count() / (ms * 1e-3),
-                               "hbm_gbs_per_gpu": seq[1].n_passes * 2 * 16 * (1 << 33) / (ms * 1e-3) / 1e9}
+                               "hbm_gbs_per_gpu": seq[2].n_passes * 2 * 16 * (1 << 33) / (ms * 1e-3) / 1e9}
         tot = r4.get_total_probability()
         c4["total_probability"] = tot
         # (b) identity layout: H(35) needs the 64 GiB-each-way exchange

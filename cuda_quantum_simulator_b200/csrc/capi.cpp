@@ -229,6 +229,10 @@ qsim_status_t qsim_jit_set_mode(int mode, int min_qubits) {
     });
 }
 
+qsim_status_t qsim_jit_wait(void) {
+    return guarded([&] { b200::jit_wait_all(); });
+}
+
 qsim_status_t qsim_jit_stats(int64_t out[8]) {
     return guarded([&] {
         require(out != nullptr, "null output");

@@ -171,10 +171,19 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
         std::snprintf(label, sizeof(label), "qsim pass %zu/%zu: %d ops, %d sweeps, t=%d%s", pass_i + 1, p.passes.size(), pd.n_ops,
                       pd.n_sweeps, pd.t, prm.redirect ? ", fused exchange" : (prm.init_basis ? ", basis-state input" : ""));
         struct NvtxScope { explicit NvtxScope(const char* l) { nvtxRangePushA(l); } ~NvtxScope() { nvtxRangePop(); } };
-        if (p.jit.size() != p.passes.size()) { p.jit.assign(p.passes.size(), nullptr); p.jit_tried.assign(p.passes.size(), 0); }
+        if (p.jit.size() != p.passes.size()) {
+            p.jit.assign(p.passes.size(), nullptr);
+            p.jit_req.assign(p.passes.size(), nullptr);
+            p.jit_tried.assign(p.passes.size(), 0);
+        }
+        JitSlots slots;
+        slots.kernel = &p.jit[pass_i];
+        slots.request = &p.jit_req[pass_i];
+        slots.tried = &p.jit_tried[pass_i];
+        slots.force = p.force_jit;
         {
             NvtxScope range(label);
-            CUDA_CHECK(launch_pass(prm, num_sms_, stream_, p.ops.data() + pd.op_offset, &p.jit[pass_i], &p.jit_tried[pass_i], p.force_jit));
+            CUDA_CHECK(launch_pass(prm, num_sms_, stream_, p.ops.data() + pd.op_offset, slots));
         }
         ++launches_;
         if (timing_) {

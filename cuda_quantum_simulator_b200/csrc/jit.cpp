@@ -7,6 +7,9 @@
 #include <unistd.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -352,19 +355,7 @@ std::string jit_generate_compute(const PassDesc& pd, const DevOp* ops) {
     return g.os.str();
 }
 
-std::string jit_translation_unit(const PassDesc& pd, const DevOp* ops) {
-    std::string tu;
-    tu.reserve(1 << 16);
-    tu += "#define QSIM_REG_BITS " + std::to_string(QSIM_REG_BITS) + "\n";
-    tu += "#include \"pass_desc.h\"\n#include \"pass_device.cuh\"\n";
-    tu += "namespace qsim {\nnamespace b200 {\nnamespace {\n";
-    tu += jit_generate_compute(pd, ops);
-    tu += "}  // namespace\n";
-    tu += "#define QSIM_PASS_KERNEL qsim_jit_pass\n#define QSIM_COMPUTE_TILE jit_compute_tile\n#define QSIM_KERNEL_LINKAGE extern \"C\"\n";
-    tu += "#include \"pass_kernel_body.inc\"\n";
-    tu += "}  // namespace b200\n}  // namespace qsim\n";
-    return tu;
-}
+std::string jit_translation_unit(const PassDesc& pd, const DevOp* ops);   // defined below (needs tu_from_compute)
 
 // ---- NVRTC (loaded on demand: the library itself does not link it) ----------------------------------------------------
 
@@ -556,15 +547,149 @@ std::string jit_last_log() {
     return g_last_log;
 }
 
-std::shared_ptr<JitKernel> jit_get_kernel(const PassDesc& pd, const DevOp* ops, bool needs_device) {
-    const JitMode mode = jit_mode();
-    const std::string compute = jit_generate_compute(pd, ops);
+namespace {
+
+std::string tu_from_compute(const std::string& compute) {
+    std::string tu;
+    tu.reserve(compute.size() + 1024);
+    tu += "#define QSIM_REG_BITS " + std::to_string(QSIM_REG_BITS) + "\n";
+    tu += "#include \"pass_desc.h\"\n#include \"pass_device.cuh\"\n";
+    tu += "namespace qsim {\nnamespace b200 {\nnamespace {\n";
+    tu += compute;
+    tu += "}  // namespace\n";
+    tu += "#define QSIM_PASS_KERNEL qsim_jit_pass\n#define QSIM_COMPUTE_TILE jit_compute_tile\n#define QSIM_KERNEL_LINKAGE extern \"C\"\n";
+    tu += "#include \"pass_kernel_body.inc\"\n";
+    tu += "}  // namespace b200\n}  // namespace qsim\n";
+    return tu;
+}
+
+// NVRTC, no locks held: generated compute -> sm_100a cubin.  Returns an empty string on success, else what went wrong.
+std::string compile_cubin(const std::string& compute, std::vector<char>& cubin, std::string& log) {
+    const Nvrtc& rt = nvrtc();
+    if (!rt.ok()) return rt.why;
+    const std::string tu = tu_from_compute(compute);
+    nvrtcProgram prog = nullptr;
+    const char* headers[] = {kSrcPassDesc, kSrcPassDevice, kSrcKernelBody};
+    const char* names[] = {"pass_desc.h", "pass_device.cuh", "pass_kernel_body.inc"};
+    if (rt.create(&prog, tu.c_str(), "qsim_jit_pass.cu", 3, headers, names) != NVRTC_SUCCESS) return "nvrtcCreateProgram failed";
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+    const nvrtcResult rc = rt.compile(prog, 4, opts);
+    size_t log_n = 0;
+    rt.log_size(prog, &log_n);
+    log.assign(log_n, '\0');
+    if (log_n > 1) rt.log(prog, &log[0]);
+    if (rc != NVRTC_SUCCESS) {
+        rt.destroy(&prog);
+        if (std::getenv("QSIM_JIT_DUMP")) std::fprintf(stderr, "%s\n", tu.c_str());
+        return std::string("compile failed: ") + (rt.error_string ? rt.error_string(rc) : "?") + "\n" + log.substr(0, 4000);
+    }
+    size_t cb = 0;
+    rt.cubin_size(prog, &cb);
+    cubin.resize(cb);
+    rt.cubin(prog, cubin.data());
+    rt.destroy(&prog);
+    return "";
+}
+
+// (g_mu held) make the kernel launchable in this process: cubin -> library -> kernel handle
+bool ensure_loaded_locked(JitKernel& k) {
+    if (k.kernel) return true;
+    cudaError_t e = cudaLibraryLoadData(&k.library, k.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&k.kernel, k.library, "qsim_jit_pass");
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (k.library) { cudaLibraryUnload(k.library); k.library = nullptr; }
+        k.kernel = nullptr;
+        return false;
+    }
+    return true;
+}
+
+// ---- background compiles: run() never waits for NVRTC ----
+// One worker thread compiles queued requests (CPU work only: the cubin is loaded into the CUDA context by the thread that
+// launches, so the worker never touches a device).  State lives in a leaked heap object: no destructor races at exit.
+struct Worker {
+    std::mutex mu;                       // guards queue / inflight (g_mu guards the caches; never hold both)
+    std::condition_variable cv_work, cv_done;
+    std::deque<std::pair<uint64_t, std::string>> queue;
+    std::unordered_map<uint64_t, bool> inflight;
+    bool started = false;
+};
+Worker& worker() {
+    static Worker* w = new Worker();
+    return *w;
+}
+
+void worker_main() {
+    Worker& w = worker();
+    for (;;) {
+        std::pair<uint64_t, std::string> job;
+        {
+            std::unique_lock<std::mutex> lk(w.mu);
+            w.cv_work.wait(lk, [&] { return !w.queue.empty(); });
+            job = std::move(w.queue.front());
+            w.queue.pop_front();
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        auto k = std::make_shared<JitKernel>();
+        std::string log;
+        const std::string err = compile_cubin(job.second, k->cubin, log);
+        {
+            std::lock_guard<std::mutex> lock(g_mu);
+            g_last_log = log;
+            if (err.empty()) {
+                k->source = job.second;
+                cache_store(job.first, job.second, k->cubin);
+                ++g_stats.compiles;
+                g_stats.compile_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                g_stats.last_cubin_bytes = (int64_t)k->cubin.size();
+                g_cache[job.first] = k;
+            } else {
+                ++g_stats.failures;
+                g_failed[job.first] = true;
+                if (!g_warned) {
+                    g_warned = true;
+                    std::fprintf(stderr, "qsim_b200: run-time specialisation unavailable (%s); using the interpreter kernel\n", err.c_str());
+                }
+            }
+        }
+        {
+            std::lock_guard<std::mutex> lk(w.mu);
+            w.inflight.erase(job.first);
+        }
+        w.cv_done.notify_all();
+    }
+}
+
+}  // namespace
+
+struct JitRequest {
+    uint64_t key = 0;
+    std::string compute;
+};
+
+std::shared_ptr<JitRequest> jit_make_request(const PassDesc& pd, const DevOp* ops) {
+    auto rq = std::make_shared<JitRequest>();
+    rq->compute = jit_generate_compute(pd, ops);
     static const uint64_t skeleton = fnv1a(kSrcPassDesc) * 31 + fnv1a(kSrcPassDevice) * 17 + fnv1a(kSrcKernelBody);
-    const uint64_t key = fnv1a(compute) ^ ((uint64_t)QSIM_REG_BITS << 56) ^ (skeleton * 0x9E3779B97F4A7C15ULL);
-    std::lock_guard<std::mutex> lock(g_mu);
-    auto fail = [&](const std::string& what) -> std::shared_ptr<JitKernel> {
+    rq->key = fnv1a(rq->compute) ^ ((uint64_t)QSIM_REG_BITS << 56) ^ (skeleton * 0x9E3779B97F4A7C15ULL);
+    return rq;
+}
+
+bool jit_async_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("QSIM_JIT_ASYNC");
+        return !(e && (std::string(e) == "0" || std::string(e) == "off"));
+    }();
+    return on;
+}
+
+std::shared_ptr<JitKernel> jit_lookup(const JitRequest& rq, bool needs_device, bool async, bool* pending) {
+    if (pending) *pending = false;
+    const JitMode mode = jit_mode();
+    auto fail_locked = [&](const std::string& what) -> std::shared_ptr<JitKernel> {
         ++g_stats.failures;
-        g_failed[key] = true;
+        g_failed[rq.key] = true;
         if (mode == JitMode::Always) throw std::runtime_error("qsim_b200 jit: " + what);
         if (!g_warned) {
             g_warned = true;
@@ -572,74 +697,76 @@ std::shared_ptr<JitKernel> jit_get_kernel(const PassDesc& pd, const DevOp* ops, 
         }
         return nullptr;
     };
-    auto it = g_cache.find(key);
-    if (it != g_cache.end() && it->second->source == compute && (!needs_device || it->second->kernel)) {
-        ++g_stats.cache_hits;
-        return it->second;
-    }
-    if (g_failed.count(key) && mode != JitMode::Always) return nullptr;
-    // a kernel of this structure compiled by an earlier process?
     {
+        std::lock_guard<std::mutex> lock(g_mu);
+        auto it = g_cache.find(rq.key);
+        if (it != g_cache.end() && it->second->source == rq.compute) {
+            if (needs_device && !ensure_loaded_locked(*it->second)) return fail_locked("loading the compiled kernel failed");
+            ++g_stats.cache_hits;
+            return it->second;
+        }
+        if (g_failed.count(rq.key) && mode != JitMode::Always) return nullptr;
+        // a kernel of this structure compiled by an earlier process?
         auto k = std::make_shared<JitKernel>();
-        if (cache_load(key, compute, k->cubin)) {
-            k->source = compute;
-            bool ok = true;
-            if (needs_device) {
-                cudaError_t e = cudaLibraryLoadData(&k->library, k->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-                if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->kernel, k->library, "qsim_jit_pass");
-                if (e != cudaSuccess) { cudaGetLastError(); ok = false; }
-            }
-            if (ok) {
+        if (cache_load(rq.key, rq.compute, k->cubin)) {
+            k->source = rq.compute;
+            if (!needs_device || ensure_loaded_locked(*k)) {
                 ++g_stats.disk_hits;
                 g_stats.last_cubin_bytes = (int64_t)k->cubin.size();
-                g_cache[key] = k;
+                g_cache[rq.key] = k;
                 return k;
             }
         }
     }
-    const Nvrtc& rt = nvrtc();
-    if (!rt.ok()) return fail(rt.why);
-
-    const auto t0 = std::chrono::steady_clock::now();
-    const std::string tu = jit_translation_unit(pd, ops);
-    nvrtcProgram prog = nullptr;
-    const char* headers[] = {kSrcPassDesc, kSrcPassDevice, kSrcKernelBody};
-    const char* names[] = {"pass_desc.h", "pass_device.cuh", "pass_kernel_body.inc"};
-    if (rt.create(&prog, tu.c_str(), "qsim_jit_pass.cu", 3, headers, names) != NVRTC_SUCCESS) return fail("nvrtcCreateProgram failed");
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
-    const nvrtcResult rc = rt.compile(prog, 4, opts);
-    size_t log_n = 0;
-    rt.log_size(prog, &log_n);
-    std::string log(log_n, '\0');
-    if (log_n > 1) rt.log(prog, &log[0]);
-    g_last_log = log;
-    if (rc != NVRTC_SUCCESS) {
-        rt.destroy(&prog);
-        if (std::getenv("QSIM_JIT_DUMP")) std::fprintf(stderr, "%s\n", tu.c_str());
-        return fail(std::string("compile failed: ") + (rt.error_string ? rt.error_string(rc) : "?") + "\n" + log.substr(0, 4000));
-    }
-    auto k = std::make_shared<JitKernel>();
-    size_t cb = 0;
-    rt.cubin_size(prog, &cb);
-    k->cubin.resize(cb);
-    rt.cubin(prog, k->cubin.data());
-    rt.destroy(&prog);
-    k->source = compute;
-    if (needs_device) {
-        cudaError_t e = cudaLibraryLoadData(&k->library, k->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-        if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->kernel, k->library, "qsim_jit_pass");
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return fail(std::string("loading the compiled kernel failed: ") + cudaGetErrorString(e));
+    if (async && mode != JitMode::Always) {
+        if (!nvrtc().ok()) {
+            std::lock_guard<std::mutex> lock(g_mu);
+            return fail_locked(nvrtc().why);
         }
+        Worker& w = worker();
+        std::lock_guard<std::mutex> lk(w.mu);
+        if (!w.started) {
+            w.started = true;
+            std::thread(worker_main).detach();
+        }
+        if (!w.inflight.count(rq.key)) {
+            w.inflight[rq.key] = true;
+            w.queue.emplace_back(rq.key, rq.compute);
+            w.cv_work.notify_one();
+        }
+        if (pending) *pending = true;
+        return nullptr;
     }
-    cache_store(key, compute, k->cubin);
+    // synchronous compile (pre-compiled circuits with `specialise`, mode always, the GPU-less build check)
+    const auto t0 = std::chrono::steady_clock::now();
+    auto k = std::make_shared<JitKernel>();
+    std::string log;
+    const std::string err = compile_cubin(rq.compute, k->cubin, log);
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_last_log = log;
+    if (!err.empty()) return fail_locked(err);
+    k->source = rq.compute;
+    if (needs_device && !ensure_loaded_locked(*k)) return fail_locked("loading the compiled kernel failed");
+    cache_store(rq.key, rq.compute, k->cubin);
     ++g_stats.compiles;
     g_stats.compile_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    g_stats.last_cubin_bytes = (int64_t)cb;
-    g_cache[key] = k;
+    g_stats.last_cubin_bytes = (int64_t)k->cubin.size();
+    g_cache[rq.key] = k;
     return k;
 }
+
+void jit_wait_all() {
+    Worker& w = worker();
+    std::unique_lock<std::mutex> lk(w.mu);
+    w.cv_done.wait(lk, [&] { return w.inflight.empty(); });
+}
+
+std::shared_ptr<JitKernel> jit_get_kernel(const PassDesc& pd, const DevOp* ops, bool needs_device) {
+    const auto rq = jit_make_request(pd, ops);
+    return jit_lookup(*rq, needs_device, /*async=*/false, nullptr);
+}
+
+std::string jit_translation_unit(const PassDesc& pd, const DevOp* ops) { return tu_from_compute(jit_generate_compute(pd, ops)); }
 
 size_t jit_copy_cubin(const JitKernel& k, void* out, size_t cap) {
     if (out && cap) std::memcpy(out, k.cubin.data(), k.cubin.size() < cap ? k.cubin.size() : cap);

@@ -41,6 +41,17 @@ std::string jit_generate_compute(const PassDesc& pd, const DevOp* host_ops);
 // The whole translation unit handed to NVRTC (generated part + the three embedded sources).
 std::string jit_translation_unit(const PassDesc& pd, const DevOp* host_ops);
 
+// The generated source of a pass and its cache key (the expensive part of a lookup; kept per program and pass).
+struct JitRequest;
+std::shared_ptr<JitRequest> jit_make_request(const PassDesc& pd, const DevOp* host_ops);
+// The kernel if it is ready (process cache, on-disk cache).  Otherwise: async = false compiles now; async = true queues the
+// compile on a background thread and returns nullptr with *pending = true - the caller launches the interpreter kernel this
+// time and asks again at the next launch, so run() never waits for NVRTC (QSIM_JIT_ASYNC=0 turns this off).  nullptr with
+// *pending = false: unavailable (NVRTC missing or the compile failed; logged once).  Mode always: synchronous, failures throw.
+std::shared_ptr<JitKernel> jit_lookup(const JitRequest& rq, bool needs_device, bool async, bool* pending);
+bool jit_async_enabled();
+void jit_wait_all();   // blocks until every queued compile has finished
+
 // Compile (or fetch from the process-wide cache) the kernel of this pass.  Returns nullptr when NVRTC is unavailable or
 // the compile failed in Auto mode (logged once; the caller uses the interpreter kernel); throws in Always mode.
 // needs_device = false only compiles to a cubin (used by the CPU-side build check); such a kernel cannot be launched.

@@ -13,10 +13,17 @@ namespace b200 {
 
 size_t pass_smem_bytes(const PassDesc& pd, int stages);
 int pick_stages(const PassDesc& pd, int wanted);
-// host_ops: the pass's op records on the host (the key of the run-time specialised kernel); jit_slot / tried_slot: where
-// the looked-up kernel is remembered between launches of the same program (all three may be null: interpreter only).
+// Where the engine remembers, per program and pass, what the run-time specialisation has come to (all may be null:
+// interpreter only).
+struct JitSlots {
+    std::shared_ptr<JitKernel>* kernel = nullptr;    // the looked-up kernel
+    std::shared_ptr<JitRequest>* request = nullptr;  // generated source + key, kept while a background compile is pending
+    char* tried = nullptr;                           // 1: decided (kernel found, or the interpreter it is)
+    bool force = false;                              // specialise whatever the state size, synchronously (pre-compiled circuits)
+};
+// host_ops: the pass's op records on the host (the key of the run-time specialised kernel).
 cudaError_t launch_pass(const PassParams& params, int num_sms, cudaStream_t stream, const DevOp* host_ops = nullptr,
-                        std::shared_ptr<JitKernel>* jit_slot = nullptr, char* tried_slot = nullptr, bool force_jit = false);
+                        const JitSlots& jit = JitSlots());
 
 }  // namespace b200
 }  // namespace qsim

@@ -455,8 +455,7 @@ cudaError_t ensure_smem_optin() {
 
 }  // namespace
 
-cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t stream, const DevOp* host_ops,
-                        std::shared_ptr<JitKernel>* jit_slot, char* tried_slot, bool force_jit) {
+cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t stream, const DevOp* host_ops, const JitSlots& jit) {
     PassParams params = params_in;
     alignas(64) CUtensorMap tmap, tmap_keep, tmap_send;
     std::memset(&tmap, 0, sizeof(tmap));
@@ -484,12 +483,25 @@ cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t s
         if (const char* e = std::getenv("QSIM_SEND_CTAS")) send = std::atoi(e);
         if (send > 0 && send < (int)grid) params.send_ctas = send;
     }
-    // a kernel specialised for this pass's structure (large states; compiled once per structure, see jit.hpp)
+    // A kernel specialised for this pass's structure (large states, pre-compiled circuits; see jit.hpp).  In the default
+    // mode the compile runs on a background thread: until it is ready the interpreter kernel below does the pass.
     if (params.use_tensor_map && (host_ops || params.pd.n_ops == 0)) {
-        std::shared_ptr<JitKernel> local, *slot = jit_slot ? jit_slot : &local;
-        if (!*slot && !(tried_slot && *tried_slot) && (jit_wanted(params.pd) || (force_jit && jit_mode() != JitMode::Off))) {
-            *slot = jit_get_kernel(params.pd, host_ops);
-            if (tried_slot) *tried_slot = 1;
+        std::shared_ptr<JitKernel> local_k;
+        std::shared_ptr<JitRequest> local_r;
+        std::shared_ptr<JitKernel>* slot = jit.kernel ? jit.kernel : &local_k;
+        std::shared_ptr<JitRequest>* req = jit.request ? jit.request : &local_r;
+        if (!*slot && !(jit.tried && *jit.tried)) {
+            const JitMode mode = jit_mode();
+            bool pending = false;
+            if (mode != JitMode::Off && (jit.force || jit_wanted(params.pd))) {
+                if (!*req) *req = jit_make_request(params.pd, host_ops);
+                const bool async = !jit.force && mode == JitMode::Auto && jit_async_enabled() && jit.kernel != nullptr;
+                *slot = jit_lookup(**req, /*needs_device=*/true, async, &pending);
+            }
+            if (!pending) {
+                if (jit.tried) *jit.tried = 1;
+                req->reset();
+            }
         }
         if (*slot) return jit_launch(**slot, params, &tmap, &tmap_keep, &tmap_send, (unsigned)grid, smem, stream);
     }

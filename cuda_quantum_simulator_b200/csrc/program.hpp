@@ -47,6 +47,7 @@ struct CompileOptions {
 };
 
 struct JitKernel;                // a run-time specialised pass kernel (jit.hpp)
+struct JitRequest;               // its generated source + cache key
 
 struct Program {
     int n = 0;                   // total qubits (local + global)
@@ -61,6 +62,7 @@ struct Program {
     // per pass: the specialised kernel once it has been looked up (filled lazily by the engine; empty slot = not yet,
     // jit_tried marks passes for which the interpreter was chosen)
     mutable std::vector<std::shared_ptr<JitKernel>> jit;
+    mutable std::vector<std::shared_ptr<JitRequest>> jit_req;   // kept while the kernel is being compiled in the background
     mutable std::vector<char> jit_tried;
     bool force_jit = false;      // specialise every pass whatever the state size (a pre-compiled circuit that will run many times)
     std::string describe() const;

@@ -65,6 +65,11 @@ def jit_set_mode(mode, min_qubits: int = 0):
     _lib.check(_lib.lib().qsim_jit_set_mode(int(m), int(min_qubits)))
 
 
+def jit_wait():
+    """Blocks until every specialised kernel queued for background compilation is ready (see qsim_jit_wait)."""
+    _lib.check(_lib.lib().qsim_jit_wait())
+
+
 def jit_stats() -> dict:
     out = (c_int64 * 8)()
     _lib.check(_lib.lib().qsim_jit_stats(out))

@@ -115,6 +115,10 @@ QSIM_API qsim_status_t qsim_program_info(const qsim_program_t* p, int64_t info[8
  * 2 = every pass and a failed compile is an error.  min_qubits <= 0 keeps the current threshold.
  * Environment: QSIM_JIT=off|auto|always, QSIM_JIT_MIN_QUBITS. */
 QSIM_API qsim_status_t qsim_jit_set_mode(int mode, int min_qubits);
+/* In mode 1 a run never waits for the compiler: the first launches of a new pass structure use the ahead-of-time kernel
+ * while a background thread compiles (QSIM_JIT_ASYNC=0: compile in the calling thread instead).  qsim_jit_wait blocks until
+ * every queued compile has finished (benchmarks, or before a long run). */
+QSIM_API qsim_status_t qsim_jit_wait(void);
 /* out[0]=kernels compiled, [1]=cache hits, [2]=specialised launches, [3]=failed compiles, [4]=compile time (us),
  * [5]=kernels loaded from the on-disk cache ($QSIM_JIT_CACHE, default ~/.cache/qsim_b200/jit, "off" disables), [6]=mode,
  * [7]=min_qubits */

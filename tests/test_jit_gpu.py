@@ -164,3 +164,33 @@ def test_multi_pass_program_replays_as_a_cuda_graph(mode):
     assert np.max(np.abs(sim2.get_state_vector() - want)) < 1e-11
     sim.execute(prog)      # and back on the first one
     assert sim.launch_count() > 0
+
+
+def test_background_compilation_never_blocks_a_run():
+    """Default mode: a run of a new pass structure launches the ahead-of-time kernel at once while a background thread
+    compiles the specialised one; once it is ready (jit_wait) the next run uses it.  Both give the oracle's state."""
+    q.jit_set_mode("auto", 10)                       # specialise from 10 qubits on (default 26), asynchronously
+    try:
+        n = 12
+        rng = np.random.default_rng(4242)
+        g = H.random_gates(n, 70, rng)
+        g["param"] = np.where(g["param"] != 0, g["param"] + 0.123, 0.0)
+        c = q.Circuit(n).extend(g)
+        want = H.oracle_run(n, g)
+        sim = q.Simulator(n)
+        before = q.jit_stats()
+        sim.run(c)                                   # interpreter kernels (unless an earlier process left the cubins on disk)
+        first = q.jit_stats()
+        assert np.max(np.abs(sim.get_state_vector() - want)) < 1e-12
+        q.jit_wait()
+        ready = q.jit_stats()
+        assert ready["failures"] == before["failures"]
+        sim.reset()
+        sim.run(c)                                   # specialised kernels now
+        after = q.jit_stats()
+        assert after["launches"] > first["launches"]
+        assert np.max(np.abs(sim.get_state_vector() - want)) < 1e-12
+        made = lambda st: st["compiles"] + st["disk_hits"] + st["cache_hits"]
+        assert made(after) > made(before)
+    finally:
+        q.jit_set_mode("auto", 26)

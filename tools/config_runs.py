@@ -17,6 +17,8 @@ import helpers as H
 
 def timed(sim, fn, reps):
     fn(); sim.synchronize()
+    q.jit_wait()               # specialised kernels are compiled in the background: time the steady state
+    fn(); sim.synchronize()
     t0 = time.perf_counter()
     for _ in range(reps):
         fn()

@@ -16,7 +16,8 @@ circ = {"c2": lambda: q.create_random_circuit(n, 20, 42), "dense": lambda: q.cre
         "c3": lambda: H.qft_style_circuit(n), "c3w": lambda: H.qft_style_circuit(n, 8)}[name]()
 prog = q.CompiledCircuit(circ)
 sim = q.Simulator(n)
-sim.execute(prog)          # from |0..0> (and compiles the specialised kernels)
+sim.execute(prog)          # from |0..0> (queues the specialised kernels for compilation)
+q.jit_wait()
 sim.execute(prog)
 sim.synchronize()
 sim.set_timing(True)

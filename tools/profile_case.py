@@ -21,6 +21,8 @@ cases = {
 sim = q.Simulator(n)
 prog = q.CompiledCircuit(cases[case]())
 print(prog.describe())
+sim.execute(prog)
+q.jit_wait()                   # the specialised kernels are ready before the profiled launches
 for _ in range(reps):
     sim.execute(prog)
 sim.synchronize()
