@@ -76,6 +76,7 @@ def _declare(L: ctypes.CDLL) -> None:
         "qsim_jit_set_mode": (c_int, [c_int, c_int]),
         "qsim_jit_stats": (c_int, [POINTER(c_int64)]),
         "qsim_jit_wait": (c_int, []),
+        "qsim_program_jit_request": (c_int, [P, c_int, POINTER(c_int)]),
         "qsim_program_set_specialised": (c_int, [P, c_int]),
         "qsim_program_jit_source": (c_size_t, [P, c_int, c_int, c_char_p, c_size_t]),
         "qsim_program_jit_compile": (c_int, [P, c_int, POINTER(c_int64), P, c_size_t]),

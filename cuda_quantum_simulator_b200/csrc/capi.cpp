@@ -229,6 +229,19 @@ qsim_status_t qsim_jit_set_mode(int mode, int min_qubits) {
     });
 }
 
+// Queues the background compile of one pass (or finds its kernel ready) without a device: *state = 0 ready, 1 pending,
+// 2 unavailable.  The GPU-less check of the background-compilation machinery (tests/test_jit_cpu.py).
+qsim_status_t qsim_program_jit_request(const qsim_program_t* p, int pass, int* state) {
+    return guarded([&] {
+        require(p != nullptr && state != nullptr && pass >= 0 && pass < (int)p->dev.host.passes.size(), "bad argument");
+        const b200::PassDesc& pd = p->dev.host.passes[pass];
+        const auto rq = b200::jit_make_request(pd, p->dev.host.ops.data() + pd.op_offset);
+        bool pending = false;
+        const auto k = b200::jit_lookup(*rq, /*needs_device=*/false, /*async=*/true, &pending);
+        *state = k ? 0 : (pending ? 1 : 2);
+    });
+}
+
 qsim_status_t qsim_jit_wait(void) {
     return guarded([&] { b200::jit_wait_all(); });
 }

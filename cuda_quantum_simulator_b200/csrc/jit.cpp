@@ -6,6 +6,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
@@ -606,7 +607,7 @@ bool ensure_loaded_locked(JitKernel& k) {
 }
 
 // ---- background compiles: run() never waits for NVRTC ----
-// One worker thread compiles queued requests (CPU work only: the cubin is loaded into the CUDA context by the thread that
+// A few worker threads compile queued requests (CPU work only: the cubin is loaded into the CUDA context by the thread that
 // launches, so the worker never touches a device).  State lives in a leaked heap object: no destructor races at exit.
 struct Worker {
     std::mutex mu;                       // guards queue / inflight (g_mu guards the caches; never hold both)
@@ -727,7 +728,10 @@ std::shared_ptr<JitKernel> jit_lookup(const JitRequest& rq, bool needs_device, b
         std::lock_guard<std::mutex> lk(w.mu);
         if (!w.started) {
             w.started = true;
-            std::thread(worker_main).detach();
+            unsigned n_workers = std::thread::hardware_concurrency() / 2;   // the passes of a circuit compile side by side
+            n_workers = n_workers < 1 ? 1 : (n_workers > 4 ? 4 : n_workers);
+            if (const char* e = std::getenv("QSIM_JIT_THREADS")) n_workers = (unsigned)std::max(1, std::atoi(e));
+            for (unsigned i = 0; i < n_workers; ++i) std::thread(worker_main).detach();
         }
         if (!w.inflight.count(rq.key)) {
             w.inflight[rq.key] = true;

@@ -42,6 +42,12 @@ class CompiledCircuit:
         _lib.lib().qsim_program_jit_source(self._h, int(pass_index), int(whole_unit), buf, need)
         return buf.value.decode()
 
+    def jit_request(self, pass_index: int = 0) -> str:
+        """Queues the background compile of one pass: "ready" | "compiling" | "unavailable" (no GPU needed)."""
+        st = ctypes.c_int()
+        _lib.check(_lib.lib().qsim_program_jit_request(self._h, int(pass_index), byref(st)))
+        return ("ready", "compiling", "unavailable")[st.value]
+
     def jit_compile(self, pass_index: int = 0, want_cubin: bool = False):
         """NVRTC-compiles one pass's kernel to an sm_100a cubin without loading it (no GPU needed).  Returns the cubin
         size, or the cubin bytes with want_cubin."""

@@ -119,6 +119,9 @@ QSIM_API qsim_status_t qsim_jit_set_mode(int mode, int min_qubits);
  * while a background thread compiles (QSIM_JIT_ASYNC=0: compile in the calling thread instead).  qsim_jit_wait blocks until
  * every queued compile has finished (benchmarks, or before a long run). */
 QSIM_API qsim_status_t qsim_jit_wait(void);
+/* Queues the background compile of one pass of a compiled program, or finds its kernel ready: *state = 0 ready, 1 compiling,
+ * 2 unavailable.  Needs no GPU (pre-warming the on-disk cache; the GPU-less test of the background machinery). */
+QSIM_API qsim_status_t qsim_program_jit_request(const qsim_program_t* p, int pass, int* state);
 /* out[0]=kernels compiled, [1]=cache hits, [2]=specialised launches, [3]=failed compiles, [4]=compile time (us),
  * [5]=kernels loaded from the on-disk cache ($QSIM_JIT_CACHE, default ~/.cache/qsim_b200/jit, "off" disables), [6]=mode,
  * [7]=min_qubits */

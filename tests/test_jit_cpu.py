@@ -52,3 +52,17 @@ def test_c2_c3_kernels_and_their_sass(tmp_path):
         assert "UTMALDG" in sass and "UTMASTG" in sass and "DFMA" in sass
         res = subprocess.run(["cuobjdump", "--dump-resource-usage", str(path)], capture_output=True, text=True).stdout
         assert "STACK:0" in res and "LOCAL:0" in res, res   # the 9-op C2 pass fits the register file: no spills
+
+
+def test_background_compilation_machinery(monkeypatch):
+    """The default mode queues compiles on background threads (a run never waits for NVRTC).  Without a GPU: queue every pass
+    of a circuit, wait, find them ready."""
+    g = H.random_gates(15, 120, np.random.default_rng(99))
+    g["param"] = np.where(g["param"] != 0, g["param"] + 0.5, 0.0)
+    prog = q.CompiledCircuit(q.Circuit(15).extend(g))
+    states = [prog.jit_request(i) for i in range(prog.n_passes)]
+    assert set(states) <= {"ready", "compiling"}
+    q.jit_wait()
+    assert [prog.jit_request(i) for i in range(prog.n_passes)] == ["ready"] * prog.n_passes
+    q.jit_wait()      # nothing queued: returns at once
+    assert q.jit_stats()["failures"] == 0
