@@ -409,12 +409,14 @@ const Nvrtc& nvrtc() {
     return n;
 }
 
-std::mutex g_mu;
+// Process-wide state.  It lives in heap objects that are never destroyed: background threads may still be compiling when the
+// process exits, and a loaded kernel must not be unloaded while the CUDA runtime is being torn down.
+std::mutex& g_mu = *new std::mutex();
 JitMode g_mode = JitMode::Auto;
 int g_min_qubits = 26;
 bool g_mode_init = false;
-JitStats g_stats;
-std::string g_last_log;
+JitStats& g_stats = *new JitStats();
+std::string& g_last_log = *new std::string();
 bool g_warned = false;
 
 void init_mode_locked() {
@@ -511,8 +513,9 @@ struct JitKernel {
 };
 
 namespace {
-std::unordered_map<uint64_t, std::shared_ptr<JitKernel>> g_cache;           // keyed by the hash of the generated compute
-std::unordered_map<uint64_t, bool> g_failed;
+// keyed by the hash of the generated compute (never destroyed, see above)
+std::unordered_map<uint64_t, std::shared_ptr<JitKernel>>& g_cache = *new std::unordered_map<uint64_t, std::shared_ptr<JitKernel>>();
+std::unordered_map<uint64_t, bool>& g_failed = *new std::unordered_map<uint64_t, bool>();
 }  // namespace
 
 JitMode jit_mode() {
