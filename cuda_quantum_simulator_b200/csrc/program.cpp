@@ -374,16 +374,15 @@ void encode_phase(Program& out, PassDesc& pd, const std::vector<int>& members, c
 
 }  // namespace
 
-bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& opt, Program& out, std::string* error) {
-    auto fail = [&](const std::string& s) { if (error) *error = s; return false; };
-    out = Program();
-    out.n = n;
-    out.n_local = n - opt.n_global;
-    const int nl = out.n_local;
-    if (nl < 1) return fail("no local qubits");
-    const int t = std::min(opt.max_tile_bits, nl);
-    const int lmin = std::min(std::max(opt.min_low_bits, 3), t);
+namespace {
 
+using Fail = bool (*)(std::string*, const std::string&);
+inline bool set_error(std::string* error, const std::string& s) { if (error) *error = s; return false; }
+
+// Step 1 of compile_ops: the X frame and the merge of gate runs on the same (target, controls).
+bool merge_with_x_frame(const std::vector<LogicalOp>& lops_in, const CompileOptions& opt, int nl, Program& out, uint64_t* xf_local_out,
+                        std::string* error) {
+    auto fail = [&](const std::string& s) { return set_error(error, s); };
     // 0. X frame: an uncontrolled X is not executed; it toggles a pending index-XOR mask through which
     //    later ops are conjugated (X on their target: swap the matrix's rows and columns; X on a control:
     //    the control fires on 0).  What is left at the end is applied by the last pass's addressing.
@@ -413,11 +412,18 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
         out.lops.swap(kept);
     }
 
+    *xf_local_out = xf_local;
+    return true;
+}
+
+// Step 2: list scheduling of the merged ops into passes.
+bool schedule_passes(const CompileOptions& opt, int nl, int t, int lmin, uint64_t xf_local, const Program& out, std::vector<PassPlan>& plans,
+                     std::string* error) {
+    auto fail = [&](const std::string& s) { return set_error(error, s); };
     // 2. passes: list scheduling — an op joins the open pass if its target fits the tile and it
     //    commutes with every op already deferred to a later pass.
     std::vector<int> pending(out.lops.size());
     for (size_t i = 0; i < pending.size(); ++i) pending[i] = (int)i;
-    std::vector<PassPlan> plans;
     while (!pending.empty()) {
         PassPlan plan;
         std::vector<int> deferred;
@@ -454,149 +460,305 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
 
     if (plans.empty() && xf_local) plans.emplace_back();   // nothing but a deferred X: one pure permutation pass
 
-    // 3. per pass: tile bits, sweeps, device records
-    for (size_t plan_i = 0; plan_i < plans.size(); ++plan_i) {
-        PassPlan& plan = plans[plan_i];
-        PassDesc pd{};
-        pd.n = nl;
-        choose_tile_bits(plan.need, nl, t, lmin, pd);
-        int local_of[64];
-        for (int q = 0; q < 64; ++q) local_of[q] = -1;
-        for (int i = 0; i < pd.t; ++i) local_of[pd.tile_bits[i]] = i;
+    return true;
+}
 
-        const int r = pd.t > 5 + kMaxRegBits ? kMaxRegBits : std::max(0, pd.t - 5);
-        const int nthr = pd.t - r;
-        const int n_lane = std::min(5, nthr);
-        const int cap = n_lane + r;  // targetable positions per sweep
+// Step 3, once per pass: tile bits, folded flips, fused diagonal runs, sweeps, device records.
+bool build_pass(PassPlan& plan, bool last_pass, const CompileOptions& opt, int nl, int t, int lmin, uint64_t xf_local, Program& out,
+                std::string* error) {
+    auto fail = [&](const std::string& s) { return set_error(error, s); };
+    PassDesc pd{};
+    pd.n = nl;
+    choose_tile_bits(plan.need, nl, t, lmin, pd);
+    int local_of[64];
+    for (int q = 0; q < 64; ++q) local_of[q] = -1;
+    for (int i = 0; i < pd.t; ++i) local_of[pd.tile_bits[i]] = i;
 
-        pd.op_offset = (int)out.ops.size();
-        pd.n_ops = 0;
-        pd.n_sweeps = 0;
+    const int r = pd.t > 5 + kMaxRegBits ? kMaxRegBits : std::max(0, pd.t - 5);
+    const int nthr = pd.t - r;
+    const int n_lane = std::min(5, nthr);
+    const int cap = n_lane + r;  // targetable positions per sweep
 
-        if (plan_i + 1 == plans.size() && xf_local) {
-            // the deferred X frame rides on the last pass: tile bits -> XOR of the tile-local store index,
-            // other bits -> the tile is written to the partner tile's location
-            uint64_t tau_bit = 0;
-            int src = 0;
-            for (int q = 0; q < nl; ++q) {
-                if (local_of[q] >= 0) { if ((xf_local >> q) & 1) pd.xor_local |= 1u << local_of[q]; }
-                else { if ((xf_local >> q) & 1) tau_bit |= 1ULL << src; ++src; }
-            }
-            pd.xor_tau = tau_bit;
+    pd.op_offset = (int)out.ops.size();
+    pd.n_ops = 0;
+    pd.n_sweeps = 0;
+
+    if (last_pass && xf_local) {
+        // the deferred X frame rides on the last pass: tile bits -> XOR of the tile-local store index,
+        // other bits -> the tile is written to the partner tile's location
+        uint64_t tau_bit = 0;
+        int src = 0;
+        for (int q = 0; q < nl; ++q) {
+            if (local_of[q] >= 0) { if ((xf_local >> q) & 1) pd.xor_local |= 1u << local_of[q]; }
+            else { if ((xf_local >> q) & 1) tau_bit |= 1ULL << src; ++src; }
         }
+        pd.xor_tau = tau_bit;
+    }
 
-        // Trailing / leading bit flips.  Walking backwards, a FLIP that commutes with every op that stays behind it can
-        // be moved to the end of the pass, where it costs only index arithmetic in the final store; walking forwards,
-        // one that commutes with every op that stays in front of it can be moved to the start, into the first sweep's
-        // load.  Only flips that are affine in the tile-local index qualify (see TailDyn).
-        struct AffineMap {
-            uint16_t lin[kMaxTileBits];
-            uint16_t cst = 0;
-            TailDyn dyn[kMaxTailDyn];
-            int n_dyn = 0, n = 0;
-        };
-        auto affine_ok = [&](const LogicalOp& op, int n_dyn_so_far, bool* is_dyn) {
-            if (op.kind != OP_FLIP || op.target >= nl || local_of[op.target] < 0) return false;
-            int n_in = 0, n_out = 0;
-            for (int q = 0; q < 64; ++q)
-                if ((op.cmask >> q) & 1) ((q < nl && local_of[q] >= 0) ? n_in : n_out)++;
-            *is_dyn = n_out > 0;
-            return *is_dyn ? (n_in == 0 && n_dyn_so_far < kMaxTailDyn) : (n_in <= 1);
-        };
-        // F = f_m o ... o f_1 for the flips in execution order: F(x) = lin x ^ cst ^ (fired translations)
-        auto compose = [&](const std::vector<int>& flips, AffineMap& M) {
-            for (int j = 0; j < kMaxTileBits; ++j) M.lin[j] = (uint16_t)(1u << j);
-            for (int idx : flips) {
-                const LogicalOp& op = out.lops[idx];
-                const uint16_t et = (uint16_t)(1u << local_of[op.target]);
-                uint64_t cm_out = 0, cv_out = 0;
-                int cb = -1, cv = 1;
-                for (int q = 0; q < 64; ++q) {
-                    if (!((op.cmask >> q) & 1)) continue;
-                    const uint64_t v = (op.cval >> q) & 1;
-                    if (q < nl && local_of[q] >= 0) { cb = local_of[q]; cv = (int)v; }
-                    else { cm_out |= 1ULL << q; cv_out |= v << q; }
-                }
-                if (cm_out) {
-                    TailDyn& d = M.dyn[M.n_dyn++];
-                    d.cmask_out = cm_out; d.cval_out = cv_out; d.w = et;
-                } else if (cb < 0) {
-                    M.cst ^= et;
-                } else {
-                    // l_t ^= l_cb (^ 1 for a control on zero), composed after everything folded so far
-                    for (int j = 0; j < kMaxTileBits; ++j) if ((M.lin[j] >> cb) & 1) M.lin[j] ^= et;
-                    for (int d = 0; d < M.n_dyn; ++d) if ((M.dyn[d].w >> cb) & 1) M.dyn[d].w ^= et;
-                    if ((M.cst >> cb) & 1) M.cst ^= et;
-                    if (!cv) M.cst ^= et;
-                }
-                ++M.n;
+    // Trailing / leading bit flips.  Walking backwards, a FLIP that commutes with every op that stays behind it can
+    // be moved to the end of the pass, where it costs only index arithmetic in the final store; walking forwards,
+    // one that commutes with every op that stays in front of it can be moved to the start, into the first sweep's
+    // load.  Only flips that are affine in the tile-local index qualify (see TailDyn).
+    struct AffineMap {
+        uint16_t lin[kMaxTileBits];
+        uint16_t cst = 0;
+        TailDyn dyn[kMaxTailDyn];
+        int n_dyn = 0, n = 0;
+    };
+    auto affine_ok = [&](const LogicalOp& op, int n_dyn_so_far, bool* is_dyn) {
+        if (op.kind != OP_FLIP || op.target >= nl || local_of[op.target] < 0) return false;
+        int n_in = 0, n_out = 0;
+        for (int q = 0; q < 64; ++q)
+            if ((op.cmask >> q) & 1) ((q < nl && local_of[q] >= 0) ? n_in : n_out)++;
+        *is_dyn = n_out > 0;
+        return *is_dyn ? (n_in == 0 && n_dyn_so_far < kMaxTailDyn) : (n_in <= 1);
+    };
+    // F = f_m o ... o f_1 for the flips in execution order: F(x) = lin x ^ cst ^ (fired translations)
+    auto compose = [&](const std::vector<int>& flips, AffineMap& M) {
+        for (int j = 0; j < kMaxTileBits; ++j) M.lin[j] = (uint16_t)(1u << j);
+        for (int idx : flips) {
+            const LogicalOp& op = out.lops[idx];
+            const uint16_t et = (uint16_t)(1u << local_of[op.target]);
+            uint64_t cm_out = 0, cv_out = 0;
+            int cb = -1, cv = 1;
+            for (int q = 0; q < 64; ++q) {
+                if (!((op.cmask >> q) & 1)) continue;
+                const uint64_t v = (op.cval >> q) & 1;
+                if (q < nl && local_of[q] >= 0) { cb = local_of[q]; cv = (int)v; }
+                else { cm_out |= 1ULL << q; cv_out |= v << q; }
             }
-        };
-        auto apply_lin = [](const uint16_t (&lin)[kMaxTileBits], unsigned x) {
+            if (cm_out) {
+                TailDyn& d = M.dyn[M.n_dyn++];
+                d.cmask_out = cm_out; d.cval_out = cv_out; d.w = et;
+            } else if (cb < 0) {
+                M.cst ^= et;
+            } else {
+                // l_t ^= l_cb (^ 1 for a control on zero), composed after everything folded so far
+                for (int j = 0; j < kMaxTileBits; ++j) if ((M.lin[j] >> cb) & 1) M.lin[j] ^= et;
+                for (int d = 0; d < M.n_dyn; ++d) if ((M.dyn[d].w >> cb) & 1) M.dyn[d].w ^= et;
+                if ((M.cst >> cb) & 1) M.cst ^= et;
+                if (!cv) M.cst ^= et;
+            }
+            ++M.n;
+        }
+    };
+    auto apply_lin = [](const uint16_t (&lin)[kMaxTileBits], unsigned x) {
+        unsigned v = 0;
+        for (int j = 0; j < kMaxTileBits; ++j) if ((x >> j) & 1) v ^= lin[j];
+        return v;
+    };
+    // inverse of a linear map over GF(2)^12 given by the images of the unit vectors (Gauss-Jordan on [A | I])
+    auto invert_gf2 = [](const uint16_t (&lin)[kMaxTileBits], uint16_t (&inv)[kMaxTileBits]) {
+        uint32_t rows[kMaxTileBits];   // row i: bits 0..11 = A[i][*], bits 16..27 = I[i][*]
+        for (int i = 0; i < kMaxTileBits; ++i) {
+            uint32_t r = 1u << (16 + i);
+            for (int j = 0; j < kMaxTileBits; ++j) if ((lin[j] >> i) & 1) r |= 1u << j;   // A[i][j] = bit i of the image of e_j
+            rows[i] = r;
+        }
+        for (int c = 0; c < kMaxTileBits; ++c) {
+            int piv = -1;
+            for (int i = c; i < kMaxTileBits; ++i) if ((rows[i] >> c) & 1) { piv = i; break; }
+            if (piv < 0) return false;
+            std::swap(rows[c], rows[piv]);
+            for (int i = 0; i < kMaxTileBits; ++i) if (i != c && ((rows[i] >> c) & 1)) rows[i] ^= rows[c];
+        }
+        for (int j = 0; j < kMaxTileBits; ++j) {
             unsigned v = 0;
-            for (int j = 0; j < kMaxTileBits; ++j) if ((x >> j) & 1) v ^= lin[j];
-            return v;
+            for (int i = 0; i < kMaxTileBits; ++i) if ((rows[i] >> (16 + j)) & 1) v |= 1u << i;
+            inv[j] = (uint16_t)v;
+        }
+        return true;
+    };
+    for (int j = 0; j < kMaxTileBits; ++j) pd.tail_lin[j] = pd.head_lin[j] = (uint16_t)(1u << j);
+    if (opt.fold_tail_flips) {
+        std::vector<int> stay, tail;   // both in reverse order
+        int n_dyn = 0;
+        for (size_t k = plan.op_idx.size(); k-- > 0;) {
+            const int idx = plan.op_idx[k];
+            const LogicalOp& op = out.lops[idx];
+            bool dyn = false;
+            bool movable = (int)tail.size() < kMaxTailFlips && affine_ok(op, n_dyn, &dyn);
+            if (movable)
+                for (int s2 : stay)
+                    if (!commutes(op, out.lops[s2])) { movable = false; break; }
+            if (movable && dyn) ++n_dyn;
+            (movable ? tail : stay).push_back(idx);
+        }
+        if (!tail.empty()) {
+            std::reverse(stay.begin(), stay.end());
+            std::reverse(tail.begin(), tail.end());
+            AffineMap M;
+            compose(tail, M);
+            std::memcpy(pd.tail_lin, M.lin, sizeof(M.lin));
+            pd.tail_const = M.cst;
+            pd.n_dyn = M.n_dyn;
+            for (int d = 0; d < M.n_dyn; ++d) pd.dyn[d] = M.dyn[d];
+            pd.n_tail = M.n;
+            plan.op_idx.swap(stay);
+        }
+        // leading flips (of what is left)
+        std::vector<int> keep, head;
+        n_dyn = 0;
+        for (int idx : plan.op_idx) {
+            const LogicalOp& op = out.lops[idx];
+            bool dyn = false;
+            bool movable = (int)head.size() < kMaxTailFlips && affine_ok(op, n_dyn, &dyn);
+            if (movable)
+                for (int s2 : keep)
+                    if (!commutes(op, out.lops[s2])) { movable = false; break; }
+            if (movable && dyn) ++n_dyn;
+            (movable ? head : keep).push_back(idx);
+        }
+        if (!head.empty()) {
+            AffineMap M;
+            compose(head, M);
+            uint16_t inv[kMaxTileBits];
+            if (!invert_gf2(M.lin, inv)) return fail("internal: folded flips are not invertible");
+            std::memcpy(pd.head_lin, inv, sizeof(inv));
+            pd.head_const = (uint16_t)apply_lin(pd.head_lin, M.cst);
+            pd.n_head_dyn = M.n_dyn;
+            for (int d = 0; d < M.n_dyn; ++d) {
+                pd.head_dyn[d] = M.dyn[d];
+                pd.head_dyn[d].w = (uint16_t)apply_lin(pd.head_lin, M.dyn[d].w);
+            }
+            pd.n_head = M.n;
+            plan.op_idx.swap(keep);
+        }
+    }
+
+    // Fuse runs of diagonal gates (each with at most one control and no zero entry) into OP_PHASE ops:
+    // a diagonal op may slide back to the open run as long as nothing emitted since the run started has its
+    // non-diagonal target among the op's qubits.
+    std::vector<std::vector<int>> clusters;   // members (indices into out.lops) of each fused run
+    if (opt.fuse_diagonals) {
+        auto eligible = [&](const LogicalOp& op) {
+            if (op.kind != OP_DIAG || __builtin_popcountll(op.cmask) > 1) return false;
+            return (op.m[0] != 0.0 || op.m[1] != 0.0) && (op.m[6] != 0.0 || op.m[7] != 0.0);
         };
-        // inverse of a linear map over GF(2)^12 given by the images of the unit vectors (Gauss-Jordan on [A | I])
-        auto invert_gf2 = [](const uint16_t (&lin)[kMaxTileBits], uint16_t (&inv)[kMaxTileBits]) {
-            uint32_t rows[kMaxTileBits];   // row i: bits 0..11 = A[i][*], bits 16..27 = I[i][*]
-            for (int i = 0; i < kMaxTileBits; ++i) {
-                uint32_t r = 1u << (16 + i);
-                for (int j = 0; j < kMaxTileBits; ++j) if ((lin[j] >> i) & 1) r |= 1u << j;   // A[i][j] = bit i of the image of e_j
-                rows[i] = r;
+        std::vector<int> order;               // >= 0: op index, < 0: -(cluster id) - 1
+        int open = -1;
+        uint64_t blocked = 0;                 // non-diagonal targets emitted since the open run started
+        for (int idx : plan.op_idx) {
+            const LogicalOp& op = out.lops[idx];
+            if (eligible(op)) {
+                if (open >= 0 && (qubits_of(op) & blocked) == 0) { clusters[open].push_back(idx); continue; }
+                if ((int)clusters.size() < kMaxPhaseOps) {
+                    open = (int)clusters.size();
+                    clusters.push_back({idx});
+                    blocked = 0;
+                    order.push_back(-open - 1);
+                    continue;
+                }
             }
-            for (int c = 0; c < kMaxTileBits; ++c) {
-                int piv = -1;
-                for (int i = c; i < kMaxTileBits; ++i) if ((rows[i] >> c) & 1) { piv = i; break; }
-                if (piv < 0) return false;
-                std::swap(rows[c], rows[piv]);
-                for (int i = 0; i < kMaxTileBits; ++i) if (i != c && ((rows[i] >> c) & 1)) rows[i] ^= rows[c];
+            order.push_back(idx);
+            if (!is_diag_kind(op.kind)) blocked |= 1ULL << op.target;
+        }
+        std::vector<int> rebuilt;
+        for (int item : order) {
+            if (item >= 0) { rebuilt.push_back(item); continue; }
+            const std::vector<int>& mem = clusters[-item - 1];
+            if (mem.size() < 3) { for (int m : mem) rebuilt.push_back(m); continue; }   // not worth a table
+            LogicalOp ph{};
+            ph.kind = OP_PHASE;
+            uint64_t qs = 0;
+            for (int m : mem) qs |= qubits_of(out.lops[m]);
+            ph.target = __builtin_ctzll(qs);
+            ph.cmask = qs & ~(1ULL << ph.target);   // qubits_of(ph) == every qubit of the run
+            ph.cval = ph.cmask;
+            ph.first_gate = -item - 1;              // cluster id
+            ph.n_gates = (int)mem.size();
+            out.lops.push_back(ph);
+            rebuilt.push_back((int)out.lops.size() - 1);
+        }
+        plan.op_idx.swap(rebuilt);
+    }
+    pd.phase_table_offset = (int)(out.phase_tables.size() / 2);
+    pd.phase_term_offset = (int)out.phase_terms.size();
+
+    std::vector<int> todo = plan.op_idx;
+    bool need_empty_sweep = todo.empty();
+    while (!todo.empty() || need_empty_sweep) {
+        need_empty_sweep = false;
+        if (pd.n_sweeps >= kMaxSweeps) return fail("too many sweeps in one pass");
+        // choose the targetable set greedily in order (commutation-aware deferral as above)
+        uint32_t S = 0;
+        for (int p = 0; p < std::min(3, pd.t); ++p) S |= 1u << p;
+        std::vector<int> chosen, deferred;
+        std::vector<int> uses(pd.t, 0);
+        for (int idx : todo) {
+            const LogicalOp& op = out.lops[idx];
+            bool ok = true;
+            uint32_t S2 = S;
+            if (!is_diag_kind(op.kind)) {
+                S2 |= 1u << local_of[op.target];
+                ok = __builtin_popcount(S2) <= cap;
             }
-            for (int j = 0; j < kMaxTileBits; ++j) {
-                unsigned v = 0;
-                for (int i = 0; i < kMaxTileBits; ++i) if ((rows[i] >> (16 + j)) & 1) v |= 1u << i;
-                inv[j] = (uint16_t)v;
+            if (ok && !deferred.empty()) {
+                if (!opt.reorder) ok = false;
+                else
+                    for (int d : deferred)
+                        if (!commutes(out.lops[d], op)) { ok = false; break; }
             }
-            return true;
-        };
-        for (int j = 0; j < kMaxTileBits; ++j) pd.tail_lin[j] = pd.head_lin[j] = (uint16_t)(1u << j);
-        if (opt.fold_tail_flips) {
-            std::vector<int> stay, tail;   // both in reverse order
-            int n_dyn = 0;
-            for (size_t k = plan.op_idx.size(); k-- > 0;) {
-                const int idx = plan.op_idx[k];
-                const LogicalOp& op = out.lops[idx];
-                bool dyn = false;
-                bool movable = (int)tail.size() < kMaxTailFlips && affine_ok(op, n_dyn, &dyn);
-                if (movable)
-                    for (int s2 : stay)
-                        if (!commutes(op, out.lops[s2])) { movable = false; break; }
-                if (movable && dyn) ++n_dyn;
-                (movable ? tail : stay).push_back(idx);
-            }
-            if (!tail.empty()) {
-                std::reverse(stay.begin(), stay.end());
-                std::reverse(tail.begin(), tail.end());
-                AffineMap M;
-                compose(tail, M);
-                std::memcpy(pd.tail_lin, M.lin, sizeof(M.lin));
-                pd.tail_const = M.cst;
-                pd.n_dyn = M.n_dyn;
-                for (int d = 0; d < M.n_dyn; ++d) pd.dyn[d] = M.dyn[d];
-                pd.n_tail = M.n;
-                plan.op_idx.swap(stay);
-            }
-            // leading flips (of what is left)
+            if (ok) {
+                S = S2;
+                chosen.push_back(idx);
+                if (!is_diag_kind(op.kind)) uses[local_of[op.target]]++;
+            } else deferred.push_back(idx);
+        }
+        if (chosen.empty() && !plan.op_idx.empty()) return fail("sweep scheduler made no progress");
+
+        // role assignment: tid bits 0..2 = tile bits 0..2; busiest other targets -> registers;
+        // remaining targets -> lane bits 3,4; everything else -> leftover lane/warp bits.
+        SweepDesc sd{};
+        sd.r = (uint8_t)r;
+        sd.nthr = (uint8_t)nthr;
+        std::vector<int> cand;  // targetable positions beyond the fixed low lanes
+        for (int p = std::min(3, pd.t); p < pd.t; ++p)
+            if ((S >> p) & 1) cand.push_back(p);
+        std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return uses[a] > uses[b]; });
+        std::vector<int> regs, lanes_extra, rest;
+        for (int p : cand) {
+            if ((int)regs.size() < r) regs.push_back(p);
+            else lanes_extra.push_back(p);
+        }
+        std::vector<char> taken(pd.t, 0);
+        for (int p = 0; p < std::min(3, pd.t); ++p) taken[p] = 1;
+        for (int p : regs) taken[p] = 1;
+        for (int p : lanes_extra) taken[p] = 1;
+        // registers prefer high tile bits when free (keeps lane bits low => coalesced smem rows)
+        for (int p = pd.t - 1; p >= 0 && (int)regs.size() < r; --p)
+            if (!taken[p]) { regs.push_back(p); taken[p] = 1; }
+        std::sort(regs.begin(), regs.end());
+        for (int p = 0; p < pd.t; ++p)
+            if (!taken[p]) rest.push_back(p);
+        int ti = 0;
+        for (int p = 0; p < std::min(3, pd.t); ++p) sd.thr_pos[ti++] = (uint8_t)p;
+        for (int p : lanes_extra) sd.thr_pos[ti++] = (uint8_t)p;
+        for (int p : rest) sd.thr_pos[ti++] = (uint8_t)p;
+        if (ti != nthr) return fail("internal: thread-bit assignment");
+        for (int j = 0; j < r; ++j) sd.reg_pos[j] = (uint8_t)regs[j];
+        for (int k = 0; k < 16; ++k) {
+            unsigned off = 0;
+            for (int j = 0; j < r; ++j)
+                if ((k >> j) & 1) off |= 1u << regs[j];
+            sd.slot_off[k] = (uint16_t)off;
+        }
+        int role_tid[kMaxTileBits], role_reg[kMaxTileBits];
+        for (int p = 0; p < pd.t; ++p) role_tid[p] = role_reg[p] = -1;
+        for (int i = 0; i < nthr; ++i) role_tid[sd.thr_pos[i]] = i;
+        for (int j = 0; j < r; ++j) role_reg[sd.reg_pos[j]] = j;
+
+        // flips that lead a later sweep fold into its load (the first sweep's were taken at pass level above)
+        for (int j = 0; j < kMaxTileBits; ++j) sd.head_lin[j] = (uint16_t)(1u << j);
+        if (opt.fold_tail_flips && pd.n_sweeps > 0) {
             std::vector<int> keep, head;
-            n_dyn = 0;
-            for (int idx : plan.op_idx) {
+            for (int idx : chosen) {
                 const LogicalOp& op = out.lops[idx];
                 bool dyn = false;
-                bool movable = (int)head.size() < kMaxTailFlips && affine_ok(op, n_dyn, &dyn);
+                bool movable = (int)head.size() < kMaxTailFlips && affine_ok(op, 0, &dyn) && !dyn;
                 if (movable)
                     for (int s2 : keep)
                         if (!commutes(op, out.lops[s2])) { movable = false; break; }
-                if (movable && dyn) ++n_dyn;
                 (movable ? head : keep).push_back(idx);
             }
             if (!head.empty()) {
@@ -604,232 +766,100 @@ bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& op
                 compose(head, M);
                 uint16_t inv[kMaxTileBits];
                 if (!invert_gf2(M.lin, inv)) return fail("internal: folded flips are not invertible");
-                std::memcpy(pd.head_lin, inv, sizeof(inv));
-                pd.head_const = (uint16_t)apply_lin(pd.head_lin, M.cst);
-                pd.n_head_dyn = M.n_dyn;
-                for (int d = 0; d < M.n_dyn; ++d) {
-                    pd.head_dyn[d] = M.dyn[d];
-                    pd.head_dyn[d].w = (uint16_t)apply_lin(pd.head_lin, M.dyn[d].w);
-                }
-                pd.n_head = M.n;
-                plan.op_idx.swap(keep);
+                std::memcpy(sd.head_lin, inv, sizeof(inv));
+                sd.head_const = (uint16_t)apply_lin(sd.head_lin, M.cst);
+                sd.n_head = (uint16_t)M.n;
+                chosen.swap(keep);
             }
         }
-
-        // Fuse runs of diagonal gates (each with at most one control and no zero entry) into OP_PHASE ops:
-        // a diagonal op may slide back to the open run as long as nothing emitted since the run started has its
-        // non-diagonal target among the op's qubits.
-        std::vector<std::vector<int>> clusters;   // members (indices into out.lops) of each fused run
-        if (opt.fuse_diagonals) {
-            auto eligible = [&](const LogicalOp& op) {
-                if (op.kind != OP_DIAG || __builtin_popcountll(op.cmask) > 1) return false;
-                return (op.m[0] != 0.0 || op.m[1] != 0.0) && (op.m[6] != 0.0 || op.m[7] != 0.0);
-            };
-            std::vector<int> order;               // >= 0: op index, < 0: -(cluster id) - 1
-            int open = -1;
-            uint64_t blocked = 0;                 // non-diagonal targets emitted since the open run started
-            for (int idx : plan.op_idx) {
-                const LogicalOp& op = out.lops[idx];
-                if (eligible(op)) {
-                    if (open >= 0 && (qubits_of(op) & blocked) == 0) { clusters[open].push_back(idx); continue; }
-                    if ((int)clusters.size() < kMaxPhaseOps) {
-                        open = (int)clusters.size();
-                        clusters.push_back({idx});
-                        blocked = 0;
-                        order.push_back(-open - 1);
-                        continue;
-                    }
-                }
-                order.push_back(idx);
-                if (!is_diag_kind(op.kind)) blocked |= 1ULL << op.target;
-            }
-            std::vector<int> rebuilt;
-            for (int item : order) {
-                if (item >= 0) { rebuilt.push_back(item); continue; }
-                const std::vector<int>& mem = clusters[-item - 1];
-                if (mem.size() < 3) { for (int m : mem) rebuilt.push_back(m); continue; }   // not worth a table
-                LogicalOp ph{};
-                ph.kind = OP_PHASE;
-                uint64_t qs = 0;
-                for (int m : mem) qs |= qubits_of(out.lops[m]);
-                ph.target = __builtin_ctzll(qs);
-                ph.cmask = qs & ~(1ULL << ph.target);   // qubits_of(ph) == every qubit of the run
-                ph.cval = ph.cmask;
-                ph.first_gate = -item - 1;              // cluster id
-                ph.n_gates = (int)mem.size();
-                out.lops.push_back(ph);
-                rebuilt.push_back((int)out.lops.size() - 1);
-            }
-            plan.op_idx.swap(rebuilt);
-        }
-        pd.phase_table_offset = (int)(out.phase_tables.size() / 2);
-        pd.phase_term_offset = (int)out.phase_terms.size();
-
-        std::vector<int> todo = plan.op_idx;
-        bool need_empty_sweep = todo.empty();
-        while (!todo.empty() || need_empty_sweep) {
-            need_empty_sweep = false;
-            if (pd.n_sweeps >= kMaxSweeps) return fail("too many sweeps in one pass");
-            // choose the targetable set greedily in order (commutation-aware deferral as above)
-            uint32_t S = 0;
-            for (int p = 0; p < std::min(3, pd.t); ++p) S |= 1u << p;
-            std::vector<int> chosen, deferred;
-            std::vector<int> uses(pd.t, 0);
-            for (int idx : todo) {
-                const LogicalOp& op = out.lops[idx];
-                bool ok = true;
-                uint32_t S2 = S;
-                if (!is_diag_kind(op.kind)) {
-                    S2 |= 1u << local_of[op.target];
-                    ok = __builtin_popcount(S2) <= cap;
-                }
-                if (ok && !deferred.empty()) {
-                    if (!opt.reorder) ok = false;
-                    else
-                        for (int d : deferred)
-                            if (!commutes(out.lops[d], op)) { ok = false; break; }
-                }
-                if (ok) {
-                    S = S2;
-                    chosen.push_back(idx);
-                    if (!is_diag_kind(op.kind)) uses[local_of[op.target]]++;
-                } else deferred.push_back(idx);
-            }
-            if (chosen.empty() && !plan.op_idx.empty()) return fail("sweep scheduler made no progress");
-
-            // role assignment: tid bits 0..2 = tile bits 0..2; busiest other targets -> registers;
-            // remaining targets -> lane bits 3,4; everything else -> leftover lane/warp bits.
-            SweepDesc sd{};
-            sd.r = (uint8_t)r;
-            sd.nthr = (uint8_t)nthr;
-            std::vector<int> cand;  // targetable positions beyond the fixed low lanes
-            for (int p = std::min(3, pd.t); p < pd.t; ++p)
-                if ((S >> p) & 1) cand.push_back(p);
-            std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return uses[a] > uses[b]; });
-            std::vector<int> regs, lanes_extra, rest;
-            for (int p : cand) {
-                if ((int)regs.size() < r) regs.push_back(p);
-                else lanes_extra.push_back(p);
-            }
-            std::vector<char> taken(pd.t, 0);
-            for (int p = 0; p < std::min(3, pd.t); ++p) taken[p] = 1;
-            for (int p : regs) taken[p] = 1;
-            for (int p : lanes_extra) taken[p] = 1;
-            // registers prefer high tile bits when free (keeps lane bits low => coalesced smem rows)
-            for (int p = pd.t - 1; p >= 0 && (int)regs.size() < r; --p)
-                if (!taken[p]) { regs.push_back(p); taken[p] = 1; }
-            std::sort(regs.begin(), regs.end());
-            for (int p = 0; p < pd.t; ++p)
-                if (!taken[p]) rest.push_back(p);
-            int ti = 0;
-            for (int p = 0; p < std::min(3, pd.t); ++p) sd.thr_pos[ti++] = (uint8_t)p;
-            for (int p : lanes_extra) sd.thr_pos[ti++] = (uint8_t)p;
-            for (int p : rest) sd.thr_pos[ti++] = (uint8_t)p;
-            if (ti != nthr) return fail("internal: thread-bit assignment");
-            for (int j = 0; j < r; ++j) sd.reg_pos[j] = (uint8_t)regs[j];
-            for (int k = 0; k < 16; ++k) {
-                unsigned off = 0;
-                for (int j = 0; j < r; ++j)
-                    if ((k >> j) & 1) off |= 1u << regs[j];
-                sd.slot_off[k] = (uint16_t)off;
-            }
-            int role_tid[kMaxTileBits], role_reg[kMaxTileBits];
-            for (int p = 0; p < pd.t; ++p) role_tid[p] = role_reg[p] = -1;
-            for (int i = 0; i < nthr; ++i) role_tid[sd.thr_pos[i]] = i;
-            for (int j = 0; j < r; ++j) role_reg[sd.reg_pos[j]] = j;
-
-            // flips that lead a later sweep fold into its load (the first sweep's were taken at pass level above)
-            for (int j = 0; j < kMaxTileBits; ++j) sd.head_lin[j] = (uint16_t)(1u << j);
-            if (opt.fold_tail_flips && pd.n_sweeps > 0) {
-                std::vector<int> keep, head;
-                for (int idx : chosen) {
-                    const LogicalOp& op = out.lops[idx];
-                    bool dyn = false;
-                    bool movable = (int)head.size() < kMaxTailFlips && affine_ok(op, 0, &dyn) && !dyn;
-                    if (movable)
-                        for (int s2 : keep)
-                            if (!commutes(op, out.lops[s2])) { movable = false; break; }
-                    (movable ? head : keep).push_back(idx);
-                }
-                if (!head.empty()) {
-                    AffineMap M;
-                    compose(head, M);
-                    uint16_t inv[kMaxTileBits];
-                    if (!invert_gf2(M.lin, inv)) return fail("internal: folded flips are not invertible");
-                    std::memcpy(sd.head_lin, inv, sizeof(inv));
-                    sd.head_const = (uint16_t)apply_lin(sd.head_lin, M.cst);
-                    sd.n_head = (uint16_t)M.n;
-                    chosen.swap(keep);
-                }
-            }
-            for (int k = 0; k < 16; ++k) sd.load_slot_off[k] = (uint16_t)apply_lin(sd.head_lin, sd.slot_off[k]);
-            sd.op_begin = (uint16_t)pd.n_ops;
-            for (int idx : chosen) {
-                const LogicalOp& op = out.lops[idx];
-                DevOp d{};
-                d.kind = op.kind;
-                if (op.kind == OP_PHASE) {
-                    encode_phase(out, pd, clusters[op.first_gate], local_of, nl, d);
-                    out.ops.push_back(d);
-                    pd.n_ops++;
-                    continue;
-                }
-                std::memcpy(d.m, op.m, sizeof(op.m));
-                uint32_t reg_cmask = 0, reg_cval = 0;
-                for (int q = 0; q < 64; ++q) {
-                    if (!((op.cmask >> q) & 1)) continue;
-                    uint64_t v = (op.cval >> q) & 1;
-                    int p = q < nl ? local_of[q] : -1;
-                    if (p < 0) { d.cmask_out |= 1ULL << q; d.cval_out |= v << q; }
-                    else if (role_reg[p] >= 0) { reg_cmask |= 1u << role_reg[p]; reg_cval |= (uint32_t)v << role_reg[p]; }
-                    else { d.cmask_thr |= 1u << role_tid[p]; d.cval_thr |= (uint32_t)v << role_tid[p]; }
-                }
-                for (int k = 0; k < 16; ++k)
-                    if (((uint32_t)k & reg_cmask) == reg_cval) d.slotmask |= (uint16_t)(1u << k);
-                int p = op.target < nl ? local_of[op.target] : -1;
-                if (p < 0) {
-                    if (!is_diag_kind(op.kind)) return fail("internal: non-diagonal target outside tile");
-                    d.thome = T_OUTSIDE;
-                    d.tmask_out = 1ULL << op.target;
-                } else if (role_reg[p] >= 0) {
-                    d.thome = T_REG;
-                    d.tbit = (uint8_t)role_reg[p];
-                    for (int k = 0; k < 16; ++k)
-                        if ((k >> role_reg[p]) & 1) d.tslots |= (uint16_t)(1u << k);
-                } else {
-                    int tb = role_tid[p];
-                    if (is_diag_kind(op.kind)) { d.thome = T_THREAD; d.tbit = (uint8_t)tb; d.tmask_thr = 1u << tb; }
-                    else {
-                        if (tb >= 5) return fail("internal: non-diagonal target on a warp bit");
-                        d.thome = T_LANE;
-                        d.tbit = (uint8_t)tb;
-                    }
-                }
-                d.has_out = (d.cmask_out != 0 || d.tmask_out != 0) ? 1u : 0u;
-                d.opcode = (uint8_t)(op_code(d.kind, d.thome, d.tbit, d.cmask_thr != 0 || d.slotmask != 0xffffu) |
-                                     (d.has_out ? 0x80u : 0u));   // bit 7: depends on index bits outside the tile
+        for (int k = 0; k < 16; ++k) sd.load_slot_off[k] = (uint16_t)apply_lin(sd.head_lin, sd.slot_off[k]);
+        sd.op_begin = (uint16_t)pd.n_ops;
+        for (int idx : chosen) {
+            const LogicalOp& op = out.lops[idx];
+            DevOp d{};
+            d.kind = op.kind;
+            if (op.kind == OP_PHASE) {
+                encode_phase(out, pd, clusters[op.first_gate], local_of, nl, d);
                 out.ops.push_back(d);
                 pd.n_ops++;
+                continue;
             }
-            sd.op_end = (uint16_t)pd.n_ops;
-            pd.sweep[pd.n_sweeps++] = sd;
-            todo.swap(deferred);
-        }
-        {   // the final store's (first load's) slot offsets: the folded flips' linear part applied to the last (first) sweep's
-            const SweepDesc& last = pd.sweep[pd.n_sweeps - 1];
-            const SweepDesc& first = pd.sweep[0];
-            for (int k = 0; k < 16; ++k) {
-                unsigned v = 0, w = 0;
-                for (int j = 0; j < kMaxTileBits; ++j) {
-                    if ((last.slot_off[k] >> j) & 1) v ^= pd.tail_lin[j];
-                    if ((first.slot_off[k] >> j) & 1) w ^= pd.head_lin[j];
+            std::memcpy(d.m, op.m, sizeof(op.m));
+            uint32_t reg_cmask = 0, reg_cval = 0;
+            for (int q = 0; q < 64; ++q) {
+                if (!((op.cmask >> q) & 1)) continue;
+                uint64_t v = (op.cval >> q) & 1;
+                int p = q < nl ? local_of[q] : -1;
+                if (p < 0) { d.cmask_out |= 1ULL << q; d.cval_out |= v << q; }
+                else if (role_reg[p] >= 0) { reg_cmask |= 1u << role_reg[p]; reg_cval |= (uint32_t)v << role_reg[p]; }
+                else { d.cmask_thr |= 1u << role_tid[p]; d.cval_thr |= (uint32_t)v << role_tid[p]; }
+            }
+            for (int k = 0; k < 16; ++k)
+                if (((uint32_t)k & reg_cmask) == reg_cval) d.slotmask |= (uint16_t)(1u << k);
+            int p = op.target < nl ? local_of[op.target] : -1;
+            if (p < 0) {
+                if (!is_diag_kind(op.kind)) return fail("internal: non-diagonal target outside tile");
+                d.thome = T_OUTSIDE;
+                d.tmask_out = 1ULL << op.target;
+            } else if (role_reg[p] >= 0) {
+                d.thome = T_REG;
+                d.tbit = (uint8_t)role_reg[p];
+                for (int k = 0; k < 16; ++k)
+                    if ((k >> role_reg[p]) & 1) d.tslots |= (uint16_t)(1u << k);
+            } else {
+                int tb = role_tid[p];
+                if (is_diag_kind(op.kind)) { d.thome = T_THREAD; d.tbit = (uint8_t)tb; d.tmask_thr = 1u << tb; }
+                else {
+                    if (tb >= 5) return fail("internal: non-diagonal target on a warp bit");
+                    d.thome = T_LANE;
+                    d.tbit = (uint8_t)tb;
                 }
-                pd.store_slot_off[k] = (uint16_t)v;
-                pd.load_slot_off[k] = (uint16_t)w;
             }
+            d.has_out = (d.cmask_out != 0 || d.tmask_out != 0) ? 1u : 0u;
+            d.opcode = (uint8_t)(op_code(d.kind, d.thome, d.tbit, d.cmask_thr != 0 || d.slotmask != 0xffffu) |
+                                 (d.has_out ? 0x80u : 0u));   // bit 7: depends on index bits outside the tile
+            out.ops.push_back(d);
+            pd.n_ops++;
         }
-        out.passes.push_back(pd);
+        sd.op_end = (uint16_t)pd.n_ops;
+        pd.sweep[pd.n_sweeps++] = sd;
+        todo.swap(deferred);
     }
+    {   // the final store's (first load's) slot offsets: the folded flips' linear part applied to the last (first) sweep's
+        const SweepDesc& last = pd.sweep[pd.n_sweeps - 1];
+        const SweepDesc& first = pd.sweep[0];
+        for (int k = 0; k < 16; ++k) {
+            unsigned v = 0, w = 0;
+            for (int j = 0; j < kMaxTileBits; ++j) {
+                if ((last.slot_off[k] >> j) & 1) v ^= pd.tail_lin[j];
+                if ((first.slot_off[k] >> j) & 1) w ^= pd.head_lin[j];
+            }
+            pd.store_slot_off[k] = (uint16_t)v;
+            pd.load_slot_off[k] = (uint16_t)w;
+        }
+    }
+    out.passes.push_back(pd);
+    return true;
+}
+
+}  // namespace
+
+bool compile_ops(int n, std::vector<LogicalOp> lops_in, const CompileOptions& opt, Program& out, std::string* error) {
+    auto fail = [&](const std::string& s) { if (error) *error = s; return false; };
+    out = Program();
+    out.n = n;
+    out.n_local = n - opt.n_global;
+    const int nl = out.n_local;
+    if (nl < 1) return fail("no local qubits");
+    const int t = std::min(opt.max_tile_bits, nl);
+    const int lmin = std::min(std::max(opt.min_low_bits, 3), t);
+
+    uint64_t xf_local = 0;
+    if (!merge_with_x_frame(lops_in, opt, nl, out, &xf_local, error)) return false;
+    std::vector<PassPlan> plans;
+    if (!schedule_passes(opt, nl, t, lmin, xf_local, out, plans, error)) return false;
+    for (size_t plan_i = 0; plan_i < plans.size(); ++plan_i)
+        if (!build_pass(plans[plan_i], plan_i + 1 == plans.size(), opt, nl, t, lmin, xf_local, out, error)) return false;
     return true;
 }
 
