@@ -737,6 +737,9 @@ std::shared_ptr<JitKernel> jit_lookup(const JitRequest& rq, bool needs_device, b
             for (unsigned i = 0; i < n_workers; ++i) std::thread(worker_main).detach();
         }
         if (!w.inflight.count(rq.key)) {
+            // a caller that streams many one-off programs (gate-by-gate application on a large state) must not pile up
+            // compiles nobody will wait for: beyond a backlog the pass simply stays on the interpreter
+            if (w.queue.size() >= 64) return nullptr;
             w.inflight[rq.key] = true;
             w.queue.emplace_back(rq.key, rq.compute);
             w.cv_work.notify_one();
