@@ -431,23 +431,36 @@ __global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, i
         const int cnt = (n_groups - g0) < 32 ? (int)(n_groups - g0) : 32;
         double my_start = 0.0;
         bool my_done = false;
+        // The loop below is ONE warp walking the groups in order: its speed is the latency of the chain through c.  Group
+        // i + 1's summary is broadcast (shuffles, independent of c) while group i's addition is in flight, and the binade of
+        // c is read from its exponent bits instead of frexp / ldexp (3.3 ms -> see DESIGN 5.2 for a dense 30-qubit state).
+        struct Summary { int kind, tie; double t, bb, ct[kCand]; };
+        auto fetch = [&](int i) {
+            Summary sm;
+            sm.kind = __shfl_sync(0xffffffffu, k_cur, i & 31);
+            sm.tie = __shfl_sync(0xffffffffu, tie_cur, i & 31);
+            sm.t = __shfl_sync(0xffffffffu, t_cur, i & 31);
+            sm.bb = __shfl_sync(0xffffffffu, b_cur, i & 31);
+#pragma unroll
+            for (int q = 0; q < kCand; ++q) sm.ct[q] = __shfl_sync(0xffffffffu, ct_cur[q], i & 31);
+            return sm;
+        };
+        Summary nxt = fetch(0);
         for (int i = 0; i < cnt; ++i) {
-            const int kind = __shfl_sync(0xffffffffu, k_cur, i);
+            const Summary cur = nxt;
+            nxt = fetch(i + 1);   // (i + 1 == 32 wraps to lane 0: fetched, never used)
+            const int kind = cur.kind;
             if (kind == G_ZERO) { if (lane == i) my_start = c; continue; }
             // the whole group under the candidate binade the EXACT running sum is in
             if (c > 0.0) {
-                int ex;
-                frexp(c, &ex);
-                const int cd = 1 - ex;   // c in [2^-cd, 2^(1-cd))
-                if (cd >= 0 && cd < kCand && !((__shfl_sync(0xffffffffu, tie_cur, i) >> cd) & 1)) {
-                    double tot = 0.0;
+                const int E = (__double2hiint(c) >> 20) & 0x7ff;   // c = m * 2^(E - 1022), m in [0.5, 1)
+                const int cd = 1023 - E;                             // c in [2^-cd, 2^(1-cd))
+                if (cd >= 0 && cd < kCand && !((cur.tie >> cd) & 1)) {
+                    double tot = cur.ct[0];
 #pragma unroll
-                    for (int q = 0; q < kCand; ++q) {
-                        const double v = __shfl_sync(0xffffffffu, ct_cur[q], i);
-                        if (q == cd) tot = v;
-                    }
+                    for (int q = 1; q < kCand; ++q) tot = (q == cd) ? cur.ct[q] : tot;
                     const double c_end = __dadd_rn(c, tot);
-                    if (c_end < ldexp(1.0, ex)) {
+                    if (c_end < __hiloint2double((E + 1) << 20, 0)) {   // still below 2^(1-cd)
                         if (lane == i) { my_start = c; my_choice = cd; }
                         c = c_end;
                         continue;
@@ -455,8 +468,8 @@ __global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, i
                 }
             }
             if (kind == G_SIMPLE) {
-                const double bb = __shfl_sync(0xffffffffu, b_cur, i);
-                const double c_end = __dadd_rn(c, __shfl_sync(0xffffffffu, t_cur, i));
+                const double bb = cur.bb;
+                const double c_end = __dadd_rn(c, cur.t);
                 if (c >= bb && c_end < 2.0 * bb) { if (lane == i) my_start = c; c = c_end; continue; }   // exact binade check
             }
             // chunk by chunk
