@@ -3,9 +3,14 @@ import sys
 
 import pytest
 
+import tempfile
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+
+# the specialised kernels the tests compile (hundreds, with specialisation forced) go to a scratch cache, not to ~/.cache
+os.environ.setdefault("QSIM_JIT_CACHE", os.path.join(tempfile.gettempdir(), "qsim_b200_jit_test_cache"))
 
 
 def pytest_configure(config):
