@@ -205,11 +205,16 @@ def sharded_parity_check(exchange, rank, world, drivers=("native", "python")):
            "marginal_max_err": 0.0, "measure_ok": True, "tolerance": 1e-10}
     cases = (("createRandomCircuit(24,40,7) identity layout", 24, 40, 7, False),
              ("createRandomCircuit(22,300,11) free layout", 22, 300, 11, True))
-    for driver, mode in [(d, m) for d in drivers for m in ("fused", "separate")]:
+    # third variant (first driver only): the fused exchange carried by run-time SPECIALISED pass kernels (forced here: these
+    # shards are below the size at which they are used by default) - the 40-gate case only, a handful of compiles
+    variants = [(d, m) for d in drivers for m in ("fused", "separate")] + [(drivers[0], "fused+specialised")]
+    for driver, mode in variants:
         if mode == "separate":
             os.environ["QSIM_NO_FUSED_EXCHANGE"] = "1"
+        if mode == "fused+specialised":
+            q.jit_set_mode("always")
         try:
-            for label, n, depth, seed, free_layout in cases:
+            for label, n, depth, seed, free_layout in (cases[:1] if mode == "fused+specialised" else cases):
                 c = q.create_random_circuit(n, depth, seed)
                 sim = make_sharded(n, exchange, driver)
                 sim.identity_layout_only(not free_layout)
@@ -249,6 +254,7 @@ def sharded_parity_check(exchange, rank, world, drivers=("native", "python")):
                 sim.close()
         finally:
             os.environ.pop("QSIM_NO_FUSED_EXCHANGE", None)
+            q.jit_set_mode("auto")
     out["passed"] = bool(out["max_abs_err"] < 1e-10 and out["sampling_bit_identical"] and out["marginal_max_err"] < 1e-12
                          and out["measure_ok"] and out["exchanges"] > 0)
     return out
