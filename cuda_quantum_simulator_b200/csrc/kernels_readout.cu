@@ -401,6 +401,7 @@ __global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, i
     const int lane = threadIdx.x & 31;
     double c = c_init;
     unsigned long long slow = 0;
+    unsigned int n_cand = 0, n_simple = 0, n_chunkwise = 0;   // groups by the path they took (diagnostics, QSIM_DEBUG_CDF)
     // lane l holds the summary of group g0 + l; the next 32 are fetched while these are stitched
     uint64_t gl = lane;
     double t_nxt = gl < n_groups ? g_total[gl] : 0.0, b_nxt = gl < n_groups ? g_bb[gl] : 0.0;
@@ -463,6 +464,7 @@ __global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, i
                     if (c_end < __hiloint2double((E + 1) << 20, 0)) {   // still below 2^(1-cd)
                         if (lane == i) { my_start = c; my_choice = cd; }
                         c = c_end;
+                        ++n_cand;
                         continue;
                     }
                 }
@@ -470,8 +472,9 @@ __global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, i
             if (kind == G_SIMPLE) {
                 const double bb = cur.bb;
                 const double c_end = __dadd_rn(c, cur.t);
-                if (c >= bb && c_end < 2.0 * bb) { if (lane == i) my_start = c; c = c_end; continue; }   // exact binade check
+                if (c >= bb && c_end < 2.0 * bb) { if (lane == i) my_start = c; c = c_end; ++n_simple; continue; }   // exact binade check
             }
+            ++n_chunkwise;
             // chunk by chunk
             const uint64_t k0 = (g0 + i) * 32, kk = k0 + lane;
             const double d = kk < m ? delta[kk] : 0.0;
@@ -507,7 +510,13 @@ __global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, i
             if (my_done) g_kind[g0 + lane] = G_DONE;
         }
     }
-    if (lane == 0) { start[m] = c; *n_slow = slow; }
+    if (lane == 0) {
+        start[m] = c;
+        // chunks replayed sequentially in the low 24 bits; above them the number of groups stitched chunk by chunk
+        // (20 bits) and through a candidate binade (20 bits)
+        *n_slow = (slow & 0xffffffULL) | ((unsigned long long)(n_chunkwise & 0xfffffu) << 24) | ((unsigned long long)(n_cand & 0xfffffu) << 44);
+        (void)n_simple;
+    }
 }
 
 __global__ void group_write_kernel(const double* __restrict__ delta, const double* __restrict__ bin_base,
@@ -870,12 +879,18 @@ uint64_t SequentialCdf::slowChunks() const {
     unsigned long long s = 0;
     CUDA_CHECK(cudaMemcpyAsync(&s, slow_, sizeof(s), cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
-    return s;
+    return s & 0xffffffULL;
 }
 
 void SequentialCdf::sample(const double* uniforms_host, int64_t n_shots, int64_t* out_host) {
     if (n_shots <= 0) return;
-    if (std::getenv("QSIM_DEBUG_CDF")) fprintf(stderr, "[cdf] chunks %llu, replayed sequentially %llu\n", (unsigned long long)m_, (unsigned long long)slowChunks());
+    if (std::getenv("QSIM_DEBUG_CDF")) {
+        unsigned long long raw = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&raw, slow_, sizeof(raw), cudaMemcpyDeviceToHost, stream_));
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        fprintf(stderr, "[cdf] chunks %llu (groups %llu): replayed sequentially %llu; groups stitched chunk by chunk %llu, through a candidate binade %llu\n",
+                (unsigned long long)m_, (unsigned long long)n_groups_, raw & 0xffffffULL, (raw >> 24) & 0xfffffULL, (raw >> 44) & 0xfffffULL);
+    }
     unsigned char* arena = static_cast<unsigned char*>(eng_.scratch(1, (size_t)n_shots * 16));
     double* d_u = reinterpret_cast<double*>(arena);
     int64_t* d_out = reinterpret_cast<int64_t*>(arena + (size_t)n_shots * 8);
