@@ -289,6 +289,8 @@ __global__ void chunk_surrogate_kernel(const cuDoubleComplex* __restrict__ state
     }
 }
 
+constexpr bool kSequentialReplayOnly = false;   // (true: every replay walks the whole chunk; for A/B measurements)
+
 // Sequential replay of one chunk by a full warp (all lanes carry the same running sum).  Only the additions form a
 // dependent chain: the next 32 probabilities are loaded and the 32 broadcasts issued ahead of it.
 __device__ __forceinline__ double replay_chunk(const cuDoubleComplex* __restrict__ state, int mask_bit, uint64_t g0,
@@ -308,6 +310,66 @@ __device__ __forceinline__ double replay_chunk(const cuDoubleComplex* __restrict
         } else {
             for (int j = 0; j < chunk - g; ++j) c = __dadd_rn(c, __shfl_sync(0xffffffffu, p, j));
         }
+    }
+    return c;
+}
+
+// The same result much faster when the chunk is the usual 4096 amplitudes: while the running sum stays inside one binade
+// [2^e, 2^(e+1)), fl(c + p) = c + rn_u(p) with u = 2^(e-52), whatever c is - so the increments of whole BLOCKS of the chunk
+// (32 blocks of 128 elements, one per lane) add exactly and in parallel, a warp scan finds the first block in which the sum
+// would reach 2^(e+1), the sum jumps to that block's start, ONLY that block is walked sequentially (it handles the crossing,
+// and any tie inside it, exactly), and the walk continues behind it in the new binade.  A tie in a block that would have been
+// skipped (a term exactly half an ulp: its rounding depends on the parity of the running sum) sends everything from that
+// point on down the sequential path.  Typical replay (one binade crossing): two block sweeps and 128 dependent additions
+// instead of 4096.
+__device__ __noinline__ double replay_chunk_blocks(const cuDoubleComplex* __restrict__ state, int mask_bit, uint64_t g0, double c) {
+    constexpr int kPer = 128;                      // elements per block, 32 blocks = 4096
+    const int lane = threadIdx.x & 31;
+    int b = 0;                                     // first block not yet accounted for
+    while (b < 32) {
+        const int E = (__double2hiint(c) >> 20) & 0x7ff;
+        if (!(c > 0.0) || E == 0 || E >= 0x7fe) {  // nothing summed yet (or out of the normal range): walk this block
+            c = replay_chunk(state, mask_bit, g0 + (uint64_t)b * kPer, kPer, c);
+            ++b;
+            continue;
+        }
+        const double B = __hiloint2double(E << 20, 0);        // 2^e <= c < 2^(e+1)
+        const double lim = __hiloint2double((E + 1) << 20, 0);
+        const double half_u = __hiloint2double((E - 53) > 0 ? (E - 53) << 20 : 0, 0);   // 2^(e-53)
+        double L = 0.0;
+        bool tie = (E - 53) <= 0;                  // (ulp not representable as a normal number: do not trust the model)
+        if (lane >= b) {
+            const uint64_t i0 = g0 + (uint64_t)lane * kPer;
+            for (int j = 0; j < kPer; ++j) {
+                const double x = masked_prob(state, i0 + j, mask_bit);
+                if (x != 0.0) {
+                    const double t = __dadd_rn(B, x);
+                    const double r = __dsub_rn(t, B);                 // rn_u(x): exact
+                    const double err = __dsub_rn(x, r);               // exact while B >= x; larger x cross anyway
+                    if (fabs(err) == half_u || x >= B) tie = true;
+                    L = __dadd_rn(L, r);                              // exact while the block stays below 2^(e+1)
+                }
+            }
+        }
+        double incl = L;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl = __dadd_rn(incl, up);
+        }
+        const double excl = __dsub_rn(incl, L);
+        const unsigned crossing = __ballot_sync(0xffffffffu, lane >= b && !(__dadd_rn(__dadd_rn(c, excl), L) < lim));
+        const int x_blk = crossing ? (__ffs(crossing) - 1) : 32;                      // first block that reaches 2^(e+1)
+        const unsigned ties = __ballot_sync(0xffffffffu, tie && lane >= b && lane < x_blk);
+        if (ties) {                                // a skipped block holds a tie: the rest goes the sequential way
+            const int first = __ffs(ties) - 1;
+            c = __dadd_rn(c, __shfl_sync(0xffffffffu, excl, first));                  // the blocks before it are exact
+            return replay_chunk(state, mask_bit, g0 + (uint64_t)first * kPer, (32 - first) * kPer, c);
+        }
+        if (x_blk == 32) return __dadd_rn(c, __shfl_sync(0xffffffffu, incl, 31));     // never left the binade: exact
+        c = __dadd_rn(c, __shfl_sync(0xffffffffu, excl, x_blk));                      // exact: still below 2^(e+1)
+        c = replay_chunk(state, mask_bit, g0 + (uint64_t)x_blk * kPer, kPer, c);     // the block with the crossing
+        b = x_blk + 1;
     }
     return c;
 }
@@ -499,7 +561,8 @@ __global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, i
                         if (c2 < ldexp(1.0, ex)) { c = c2; continue; }
                     }
                 }
-                c = replay_chunk(state, mask_bit, (k0 + j) * (uint64_t)chunk, chunk, c);
+                c = (chunk == 4096 && !kSequentialReplayOnly) ? replay_chunk_blocks(state, mask_bit, (k0 + j) * (uint64_t)chunk, c)
+                                                              : replay_chunk(state, mask_bit, (k0 + j) * (uint64_t)chunk, chunk, c);
                 ++slow;
             }
             if (lane == i) my_done = true;
