@@ -464,32 +464,38 @@ __global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, i
     double c = c_init;
     unsigned long long slow = 0;
     unsigned int n_cand = 0, n_simple = 0, n_chunkwise = 0;   // groups by the path they took (diagnostics, QSIM_DEBUG_CDF)
-    // lane l holds the summary of group g0 + l; the next 32 are fetched while these are stitched
-    uint64_t gl = lane;
-    double t_nxt = gl < n_groups ? g_total[gl] : 0.0, b_nxt = gl < n_groups ? g_bb[gl] : 0.0;
-    int k_nxt = gl < n_groups ? (int)g_kind[gl] : (int)G_ZERO;
-    double ct_nxt[kCand];
-    int tie_nxt = gl < n_groups ? (int)g_tie[gl] : 0xff;
+    // lane l holds the summary of group g0 + l.  The summaries of the next kAhead batches of 32 groups are in flight
+    // while a batch is stitched (a batch of all-zero or candidate-path groups is shorter than one trip to L2, so a single
+    // batch of look-ahead left the warp waiting for memory most of the time).
+    constexpr int kAhead = 4;
+    struct Batch {
+        double t, b, ct[kCand];
+        int k, tie;
+    };
+    auto load_batch = [&](uint64_t g_first, Batch& bt) {
+        const uint64_t gl = g_first + lane;
+        const bool in = gl < n_groups;
+        bt.t = in ? g_total[gl] : 0.0;
+        bt.b = in ? g_bb[gl] : 0.0;
+        bt.k = in ? (int)g_kind[gl] : (int)G_ZERO;
+        bt.tie = in ? (int)g_tie[gl] : 0xff;
 #pragma unroll
-    for (int cd = 0; cd < kCand; ++cd) ct_nxt[cd] = gl < n_groups ? g_cand[(uint64_t)cd * n_groups + gl] : 0.0;
-    for (uint64_t g0 = 0; g0 < n_groups; g0 += 32) {
-        const double t_cur = t_nxt, b_cur = b_nxt;
-        const int k_cur = k_nxt, tie_cur = tie_nxt;
+        for (int cd = 0; cd < kCand; ++cd) bt.ct[cd] = in ? g_cand[(uint64_t)cd * n_groups + gl] : 0.0;
+    };
+    Batch ring[kAhead];
+#pragma unroll
+    for (int a = 0; a < kAhead; ++a) load_batch((uint64_t)a * 32, ring[a]);
+    auto stitch_batch = [&](uint64_t g0, const Batch& cur_batch) {
+        const double t_cur = cur_batch.t, b_cur = cur_batch.b;
+        const int k_cur = cur_batch.k, tie_cur = cur_batch.tie;
         double ct_cur[kCand];
 #pragma unroll
-        for (int cd = 0; cd < kCand; ++cd) ct_cur[cd] = ct_nxt[cd];
-        gl = g0 + 32 + lane;
-        t_nxt = gl < n_groups ? g_total[gl] : 0.0;
-        b_nxt = gl < n_groups ? g_bb[gl] : 0.0;
-        k_nxt = gl < n_groups ? (int)g_kind[gl] : (int)G_ZERO;
-        tie_nxt = gl < n_groups ? (int)g_tie[gl] : 0xff;
-#pragma unroll
-        for (int cd = 0; cd < kCand; ++cd) ct_nxt[cd] = gl < n_groups ? g_cand[(uint64_t)cd * n_groups + gl] : 0.0;
+        for (int cd = 0; cd < kCand; ++cd) ct_cur[cd] = cur_batch.ct[cd];
         int my_choice = 0xff;
         // a whole batch of all-zero groups (long stretches of a sparse state): the running sum does not move
         if (__all_sync(0xffffffffu, k_cur == (int)G_ZERO)) {
             if (g0 + lane < n_groups) { g_start[g0 + lane] = c; g_choice[g0 + lane] = 0xff; }
-            continue;
+            return;
         }
         const int cnt = (n_groups - g0) < 32 ? (int)(n_groups - g0) : 32;
         double my_start = 0.0;
@@ -571,6 +577,16 @@ __global__ void group_stitch_kernel(const cuDoubleComplex* __restrict__ state, i
             g_start[g0 + lane] = my_start;
             g_choice[g0 + lane] = (uint8_t)my_choice;
             if (my_done) g_kind[g0 + lane] = G_DONE;
+        }
+    };
+    for (uint64_t g0 = 0; g0 < n_groups; g0 += 32 * kAhead) {
+#pragma unroll
+        for (int a = 0; a < kAhead; ++a) {   // (static ring slots: the look-ahead lives in registers)
+            const uint64_t ga = g0 + (uint64_t)a * 32;
+            if (ga < n_groups) {
+                stitch_batch(ga, ring[a]);
+                load_batch(ga + 32 * kAhead, ring[a]);
+            }
         }
     }
     if (lane == 0) {
