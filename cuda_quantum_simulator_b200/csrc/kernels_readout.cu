@@ -340,11 +340,16 @@ __device__ __noinline__ double replay_chunk_blocks(const cuDoubleComplex* __rest
         bool tie = (E - 53) <= 0;                  // (ulp not representable as a normal number: do not trust the model)
         if (lane >= b) {
             const uint64_t i0 = g0 + (uint64_t)lane * kPer;
-            for (int j = 0; j < kPer; ++j) {
-                const double x = masked_prob(state, i0 + j, mask_bit);
-                if (x != 0.0) {
+            constexpr int kBatch = 16;               // loads in flight per lane (the block is read from HBM, not from a cache)
+            for (int j0 = 0; j0 < kPer; j0 += kBatch) {
+                double xs[kBatch];
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) xs[j] = masked_prob(state, i0 + j0 + j, mask_bit);
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) {
+                    const double x = xs[j];
                     const double t = __dadd_rn(B, x);
-                    const double r = __dsub_rn(t, B);                 // rn_u(x): exact
+                    const double r = __dsub_rn(t, B);                 // rn_u(x): exact (0 for x = 0)
                     const double err = __dsub_rn(x, r);               // exact while B >= x; larger x cross anyway
                     if (fabs(err) == half_u || x >= B) tie = true;
                     L = __dadd_rn(L, r);                              // exact while the block stays below 2^(e+1)
