@@ -379,6 +379,89 @@ __device__ __noinline__ double replay_chunk_blocks(const cuDoubleComplex* __rest
     return c;
 }
 
+// The shot lookup inside a chunk with the same trick: index (0..4095) of the first element at which the sequential running
+// sum, started at c, reaches r; 4096 if it never does.  Blocks that neither reach r nor leave the binade are skipped with
+// their exact increments; only the block that does one or the other is walked.
+__device__ __noinline__ int locate_in_chunk_blocks(const cuDoubleComplex* __restrict__ state, int mask_bit, uint64_t g0, double c,
+                                                   double r) {
+    constexpr int kPer = 128;
+    const int lane = threadIdx.x & 31;
+    // sequential walk over blocks [blk, blk + nblk): first index whose running sum is >= r, else -1 (cc carries on)
+    auto walk = [&](int blk, int nblk, double& cc) -> int {
+        const uint64_t e0 = (uint64_t)blk * kPer;
+        const int cnt = nblk * kPer;
+        double p_next = masked_prob(state, g0 + e0 + lane, mask_bit);
+        for (int g = 0; g < cnt; g += 32) {
+            const double p = p_next;
+            if (g + 32 < cnt) p_next = masked_prob(state, g0 + e0 + g + 32 + lane, mask_bit);
+            for (int j = 0; j < 32; ++j) {
+                cc = __dadd_rn(cc, __shfl_sync(0xffffffffu, p, j));
+                if (cc >= r) return (int)(e0 + g + j);
+            }
+        }
+        return -1;
+    };
+    int b = 0;
+    while (b < 32) {
+        const int E = (__double2hiint(c) >> 20) & 0x7ff;
+        if (!(c > 0.0) || E == 0 || E >= 0x7fe) {
+            const int idx = walk(b, 1, c);
+            if (idx >= 0) return idx;
+            ++b;
+            continue;
+        }
+        const double B = __hiloint2double(E << 20, 0);
+        const double lim = __hiloint2double((E + 1) << 20, 0);
+        const double half_u = __hiloint2double((E - 53) > 0 ? (E - 53) << 20 : 0, 0);
+        double L = 0.0;
+        bool tie = (E - 53) <= 0;
+        if (lane >= b) {
+            const uint64_t i0 = g0 + (uint64_t)lane * kPer;
+            constexpr int kBatch = 16;
+            for (int j0 = 0; j0 < kPer; j0 += kBatch) {
+                double xs[kBatch];
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) xs[j] = masked_prob(state, i0 + j0 + j, mask_bit);
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) {
+                    const double x = xs[j];
+                    const double t = __dadd_rn(B, x);
+                    const double rr = __dsub_rn(t, B);
+                    const double err = __dsub_rn(x, rr);
+                    if (fabs(err) == half_u || x >= B) tie = true;
+                    L = __dadd_rn(L, rr);
+                }
+            }
+        }
+        double incl = L;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl = __dadd_rn(incl, up);
+        }
+        const double excl = __dsub_rn(incl, L);
+        const double end = __dadd_rn(__dadd_rn(c, excl), L);          // exact for every block before the first crossing
+        const unsigned crossing = __ballot_sync(0xffffffffu, lane >= b && !(end < lim));
+        const unsigned reaching = __ballot_sync(0xffffffffu, lane >= b && end >= r);
+        const int x_blk = crossing ? (__ffs(crossing) - 1) : 32;
+        const int y_blk = reaching ? (__ffs(reaching) - 1) : 32;
+        const int stop = x_blk < y_blk ? x_blk : y_blk;                // first block that reaches r or leaves the binade
+        const unsigned ties = __ballot_sync(0xffffffffu, tie && lane >= b && lane < stop);
+        if (ties) {
+            const int first = __ffs(ties) - 1;
+            c = __dadd_rn(c, __shfl_sync(0xffffffffu, excl, first));
+            const int idx = walk(first, 32 - first, c);
+            return idx >= 0 ? idx : 4096;
+        }
+        if (stop == 32) return 4096;
+        c = __dadd_rn(c, __shfl_sync(0xffffffffu, excl, stop));
+        const int idx = walk(stop, 1, c);
+        if (idx >= 0) return idx;
+        b = stop + 1;
+    }
+    return 4096;
+}
+
 // K4: the exact running sum at every chunk start, in three launches.  The chunks are taken in groups of 32.
 //  (a) one warp per group, whole grid: a group whose non-zero chunks are all FAST in one binade has increments that are
 //      multiples of one ulp — they add exactly in any order, so a warp scan gives the group's total;
@@ -646,6 +729,11 @@ __global__ void sample_kernel(const cuDoubleComplex* __restrict__ state, int mas
             double c = start[lo_k];
             const uint64_t g0 = lo_k * (uint64_t)chunk;
             bool found = false;
+            if (chunk == 4096 && !kSequentialReplayOnly) {   // block-wise: two parallel sweeps of the chunk + one 128-element walk
+                const int idx = locate_in_chunk_blocks(state, mask_bit, g0, c, r);
+                if (idx < 4096) result = (int64_t)(g0 + (uint64_t)idx);
+                found = true;
+            }
             for (int g = 0; g < chunk && !found; g += 32) {
                 const double p = (g + lane < chunk) ? masked_prob(state, g0 + g + lane, mask_bit) : 0.0;
                 const int lim = (chunk - g) < 32 ? (chunk - g) : 32;
