@@ -201,16 +201,21 @@ def sharded_parity_check(exchange, rank, world, drivers=("native", "python")):
     import numpy as np
     import cuda_quantum_simulator_b200 as q
     import helpers as H
-    out = {"drivers": list(drivers), "max_abs_err": 0.0, "exchanges": 0, "fused": 0, "cases": [], "sampling_bit_identical": True,
+    out = {"drivers": list(drivers), "max_abs_err": 0.0, "exchanges": 0, "fused": 0, "in_place": 0, "cases": [], "sampling_bit_identical": True,
            "marginal_max_err": 0.0, "measure_ok": True, "tolerance": 1e-10}
     cases = (("createRandomCircuit(24,40,7) identity layout", 24, 40, 7, False),
              ("createRandomCircuit(22,300,11) free layout", 22, 300, 11, True))
     # third variant (first driver only): the fused exchange carried by run-time SPECIALISED pass kernels (forced here: these
     # shards are below the size at which they are used by default) - the 40-gate case only, a handful of compiles
+    # fourth (C++ driver): the fused exchange IN PLACE - what shards too large for a second buffer get (C4's 128 GiB) - forced
     variants = [(d, m) for d in drivers for m in ("fused", "separate")] + [(drivers[0], "fused+specialised")]
+    if "native" in drivers:
+        variants.append(("native", "fused in place"))
     for driver, mode in variants:
         if mode == "separate":
             os.environ["QSIM_NO_FUSED_EXCHANGE"] = "1"
+        if mode == "fused in place":
+            os.environ["QSIM_FORCE_INPLACE_EXCHANGE"] = "1"
         if mode == "fused+specialised":
             q.jit_set_mode("always")
         try:
@@ -247,6 +252,7 @@ def sharded_parity_check(exchange, rank, world, drivers=("native", "python")):
                 out["max_abs_err"] = max(out["max_abs_err"], err)
                 out["exchanges"] += cp.n_swaps
                 out["fused"] += sim.fused_exchanges - f0
+                out["in_place"] += getattr(sim, "inplace_exchanges", 0)
                 out["sampling_bit_identical"] &= samp_ok
                 out["marginal_max_err"] = max(out["marginal_max_err"], merr)
                 out["measure_ok"] &= bool(meas_ok)
@@ -254,9 +260,10 @@ def sharded_parity_check(exchange, rank, world, drivers=("native", "python")):
                 sim.close()
         finally:
             os.environ.pop("QSIM_NO_FUSED_EXCHANGE", None)
+            os.environ.pop("QSIM_FORCE_INPLACE_EXCHANGE", None)
             q.jit_set_mode("auto")
     out["passed"] = bool(out["max_abs_err"] < 1e-10 and out["sampling_bit_identical"] and out["marginal_max_err"] < 1e-12
-                         and out["measure_ok"] and out["exchanges"] > 0)
+                         and out["measure_ok"] and out["exchanges"] > 0 and ("native" not in drivers or out["in_place"] > 0))
     return out
 
 
@@ -466,9 +473,12 @@ def main():
             q.jit_wait()
             st()
             f_c = sim_.fused_exchanges
+            i_c = getattr(sim_, "inplace_exchanges", 0)
             ms = timed(st, k) / k
             info = {"ms_per_step": ms, "passes_per_step": plan_.n_passes, "swaps_per_step": plan_.n_swaps,
-                    "fused_into_a_pass_per_step": (sim_.fused_exchanges - f_c) / k, "fused_first_step_from_zero_state": f_b - f_a}
+                    "fused_into_a_pass_per_step": (sim_.fused_exchanges - f_c) / k,
+                    "of_which_in_place_per_step": (getattr(sim_, "inplace_exchanges", 0) - i_c) / k,
+                    "fused_first_step_from_zero_state": f_b - f_a}
             sim_.identity_layout_only(False)
             return info, plan_
         k_f = 4
@@ -493,6 +503,18 @@ def main():
                            "ideal = max(pass_ms, link_ms) per exchange + the remaining passes (an exchange can only overlap the pass "
                            "it rides on); overlap_eff = ideal / measured; fused_pass_plus_exchange_ms = measured minus the unfused "
                            "passes; pass_ms = the headline pass, link_ms = the separate-swap nvlink leg above", **f_info)
+        if args.sharded_driver == "native" and runner.exchange == "p2p":
+            # the same steps with the fused exchange IN PLACE (what shards without room for a second buffer get: C4)
+            os.environ["QSIM_FORCE_INPLACE_EXCHANGE"] = "1"
+            try:
+                ip_info, _ip = forced_run(circuit, runner, k_f)
+                runner.synchronize()
+            finally:
+                os.environ.pop("QSIM_FORCE_INPLACE_EXCHANGE", None)
+            ip_step = (ip_info["ms_per_step"] - (fplan.n_passes - n_f) * pass_ms_1) / max(n_f, 1)
+            forced["in_place"] = dict(overlap_eff=ideal / ip_info["ms_per_step"], fused_pass_plus_exchange_ms=ip_step,
+                                      nvlink_gbs_per_direction_in_the_fused_step=half_bytes / ip_step / 1e6,
+                                      nvlink_frac_of_770=half_bytes / ip_step / 1e6 / 770.0, **ip_info)
 
     # ---- BASELINE config C4 for real: createRandomCircuit(36,20,42) over 8 GPUs, 128 GiB shards --------------------------
     c4 = None
@@ -529,9 +551,21 @@ def main():
         tot = r4.get_total_probability()
         c4["total_probability"] = tot
         # (b) identity layout: H(35) needs the 64 GiB-each-way exchange
-        f_info, _fp = forced_run(c4circ, r4, 2)
-        c4["identity_layout"] = f_info
-        c4["identity_layout"]["total_probability"] = r4.get_total_probability()
+        # fused into the pass before it IN PLACE (no room for a second buffer); if that fails, and for comparison, the
+        # separate swap kernel
+        try:
+            f_info, _fp = forced_run(c4circ, r4, 2)
+            f_info["total_probability"] = r4.get_total_probability()   # (also where a failed handshake would surface, on every rank)
+            c4["identity_layout"] = f_info
+        except Exception as exc:   # noqa: BLE001 - reported in the line
+            c4["identity_layout_error"] = str(exc)[:300]
+        os.environ["QSIM_NO_INPLACE_EXCHANGE"] = "1"
+        try:
+            s_info, _sp = forced_run(c4circ, r4, 2)
+            s_info["total_probability"] = r4.get_total_probability()
+            c4["identity_layout_separate_swap"] = s_info
+        finally:
+            os.environ.pop("QSIM_NO_INPLACE_EXCHANGE", None)
         r4.close()
 
     if rank != 0:

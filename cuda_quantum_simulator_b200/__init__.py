@@ -4,10 +4,10 @@ libqsim_b200.so (hand-written CUDA).  There is no CPU fallback."""
 from ._lib import GATE_DTYPE, InvalidArgument, OutOfRange, QsimError, LIB_PATH
 from .circuit import Circuit, GateType, create_bell_circuit, create_ghz_circuit, create_random_circuit
 from .noise import (BatchedSimulator, DensityMatrixSimulator, NoiseChannel, NoiseModel, NoiseType, NoisySimulator)
-from .simulator import CompiledCircuit, Simulator, jit_set_mode, jit_stats, jit_wait
+from .simulator import CompiledCircuit, Simulator, jit_set_dual, jit_set_mode, jit_stats, jit_wait
 
 __all__ = [
     "GATE_DTYPE", "InvalidArgument", "OutOfRange", "QsimError", "LIB_PATH", "Circuit", "GateType",
-    "create_bell_circuit", "create_ghz_circuit", "create_random_circuit", "CompiledCircuit", "Simulator", "jit_set_mode", "jit_stats", "jit_wait",
+    "create_bell_circuit", "create_ghz_circuit", "create_random_circuit", "CompiledCircuit", "Simulator", "jit_set_dual", "jit_set_mode", "jit_stats", "jit_wait",
     "BatchedSimulator", "DensityMatrixSimulator", "NoiseChannel", "NoiseModel", "NoiseType", "NoisySimulator",
 ]

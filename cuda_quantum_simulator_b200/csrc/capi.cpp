@@ -229,6 +229,13 @@ qsim_status_t qsim_jit_set_mode(int mode, int min_qubits) {
     });
 }
 
+qsim_status_t qsim_jit_set_dual(int mode, int min_fp64) {
+    return guarded([&] {
+        require(mode >= -1 && mode <= 2, "mode must be -1 (keep), 0 (off), 1 (auto) or 2 (always)");
+        b200::jit_set_dual(mode, min_fp64);
+    });
+}
+
 // Queues the background compile of one pass (or finds its kernel ready) without a device: *state = 0 ready, 1 pending,
 // 2 unavailable.  The GPU-less check of the background-compilation machinery (tests/test_jit_cpu.py).
 qsim_status_t qsim_program_jit_request(const qsim_program_t* p, int pass, int* state) {
@@ -269,7 +276,8 @@ size_t qsim_program_jit_source(const qsim_program_t* p, int pass, int whole_unit
     if (!p || pass < 0 || pass >= (int)p->dev.host.passes.size()) return 0;
     const b200::PassDesc& pd = p->dev.host.passes[pass];
     const b200::DevOp* ops = p->dev.host.ops.data() + pd.op_offset;
-    return copy_out(whole_unit ? b200::jit_translation_unit(pd, ops) : b200::jit_generate_compute(pd, ops), buf, cap);
+    const bool dual = b200::jit_dual_wanted(pd, ops);   // (QSIM_DUAL=always / off to look at either build)
+    return copy_out(whole_unit ? b200::jit_translation_unit(pd, ops, dual) : b200::jit_generate_compute(pd, ops, dual), buf, cap);
 }
 
 qsim_status_t qsim_program_jit_compile(const qsim_program_t* p, int pass, int64_t* cubin_bytes, void* cubin_out, size_t cap) {
@@ -280,7 +288,8 @@ qsim_status_t qsim_program_jit_compile(const qsim_program_t* p, int pass, int64_
         const int saved_min = b200::jit_min_qubits();
         b200::jit_set_mode(b200::JitMode::Always, saved_min);   // a failure throws with the compiler's log
         std::shared_ptr<b200::JitKernel> k;
-        try { k = b200::jit_get_kernel(pd, p->dev.host.ops.data() + pd.op_offset, /*needs_device=*/false); }
+        const b200::DevOp* ops = p->dev.host.ops.data() + pd.op_offset;
+        try { k = b200::jit_get_kernel(pd, ops, /*needs_device=*/false, b200::jit_dual_wanted(pd, ops)); }
         catch (...) { b200::jit_set_mode(saved, saved_min); throw; }
         b200::jit_set_mode(saved, saved_min);
         if (cubin_bytes) *cubin_bytes = k ? (int64_t)b200::jit_copy_cubin(*k, nullptr, 0) : 0;
@@ -568,6 +577,56 @@ qsim_status_t qsim_shard_execute_exchange(qsim_sim_t* s, const qsim_program_t* p
     });
 }
 
+// Can the last pass of `p` carry the exchange of `local_qubit` IN PLACE?  (the launch-time conditions of launch_pass)
+static bool inplace_exchange_possible(const qsim_program_t* p, int local_qubit, int num_sms) {
+    if (p->dev.host.passes.empty()) return false;
+    const b200::PassDesc& pd = p->dev.host.passes.back();
+    for (int j = 0; j < pd.t; ++j)
+        if (pd.tile_bits[j] == local_qubit) return false;
+    const uint64_t n_tiles = 1ULL << (pd.n - pd.t);
+    const uint64_t grid = n_tiles < (uint64_t)num_sms ? n_tiles : (uint64_t)num_sms;
+    if (grid < 16) return false;
+    uint64_t xdep = 0;   // index XOR of the tile pairs of deferred X gates on outer bits
+    for (int sg = 0; sg < pd.n_segments; ++sg) xdep |= ((pd.xor_tau >> pd.seg[sg].src_shift) & pd.seg[sg].mask) << pd.seg[sg].dst_shift;
+    return !((xdep >> local_qubit) & 1ULL);
+}
+
+qsim_status_t qsim_shard_inplace_exchange_possible(qsim_sim_t* s, const qsim_program_t* p, int local_qubit, int* possible_out) {
+    return guarded([&] {
+        require(s != nullptr && p != nullptr && possible_out != nullptr, "null argument");
+        *possible_out = inplace_exchange_possible(p, local_qubit, s->sim->state().engine().numSMs()) ? 1 : 0;
+    });
+}
+
+qsim_status_t qsim_shard_execute_exchange_inplace(qsim_sim_t* s, const qsim_program_t* p, void* peer_state, int global_qubit,
+                                                  int local_qubit, void* hs_local, void* hs_peer, uint64_t hs_base,
+                                                  uint64_t timeout_ns, int* hs_error_dev) {
+    return guarded([&] {
+        require(s != nullptr && p != nullptr && peer_state != nullptr && hs_local != nullptr && hs_peer != nullptr &&
+                hs_error_dev != nullptr, "null argument");
+        if (p->dev.host.n != s->n_total || p->n_global != s->n_global)
+            throw std::invalid_argument("Circuit qubit count doesn't match simulator");
+        const int nl = s->n_total - s->n_global;
+        require(global_qubit >= nl && global_qubit < s->n_total, "global_qubit is not a global qubit");
+        require(local_qubit >= 0 && local_qubit < nl, "local_qubit is not a local qubit");
+        StateVector& sv = s->sim->state();
+        require(inplace_exchange_possible(p, local_qubit, sv.engine().numSMs()),
+                "the program's last pass cannot carry this exchange in place (qsim_shard_inplace_exchange_possible)");
+        b200::StoreRedirect rd;
+        rd.keep = sv.devicePtr();   // (a lazily reset shard is written out here)
+        rd.send = static_cast<cuDoubleComplex*>(peer_state);
+        rd.bit = local_qubit;
+        rd.keep_value = (s->rank >> (global_qubit - nl)) & 1;
+        rd.in_place = true;
+        rd.hs_local = static_cast<unsigned long long*>(hs_local);
+        rd.hs_peer = static_cast<unsigned long long*>(hs_peer);
+        rd.hs_base = hs_base;
+        rd.hs_timeout_ns = timeout_ns ? timeout_ns : 10000000000ULL;
+        rd.hs_error = hs_error_dev;
+        sv.engine().execute(p->dev, rd.keep, s->hi_bits(), -1, &rd);
+    });
+}
+
 static void chunk_range(int nl, int64_t chunk, int64_t n_chunks, uint64_t* jb, uint64_t* cnt) {
     const uint64_t pairs = 1ULL << (nl - 1);
     const uint64_t per = (pairs + (uint64_t)n_chunks - 1) / (uint64_t)n_chunks;
@@ -821,6 +880,13 @@ qsim_status_t qsim_sharded_info(const qsim_sharded_t* h, int64_t info[8]) {
         info[5] = h->sim->rank();
         info[6] = h->sim->worldSize();
         info[7] = h->sim->hasSecondBuffer() ? 1 : 0;
+    });
+}
+
+qsim_status_t qsim_sharded_inplace_exchanges(const qsim_sharded_t* h, int64_t* count_out) {
+    return guarded([&] {
+        require(h != nullptr && count_out != nullptr, "null argument");
+        *count_out = h->sim->inPlaceExchanges();
     });
 }
 

@@ -153,7 +153,12 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
             }
         }
         first = false;
-        prm.redirect = (last && redirect) ? 1 : 0;
+        prm.redirect = (last && redirect) ? (redirect->in_place ? 2 : 1) : 0;
+        prm.hs_local = (last && redirect) ? redirect->hs_local : nullptr;
+        prm.hs_peer = (last && redirect) ? redirect->hs_peer : nullptr;
+        prm.hs_base = redirect ? redirect->hs_base : 0;
+        prm.hs_timeout_ns = redirect ? redirect->hs_timeout_ns : 0;
+        prm.hs_error = (last && redirect) ? redirect->hs_error : nullptr;
         prm.redirect_bit = redirect ? redirect->bit : 0;
         prm.redirect_keep = redirect ? redirect->keep_value : 0;
         prm.send_ctas = 0;   // chosen by launch_pass
@@ -169,17 +174,17 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
         // NVTX range per pass (visible in Nsight Systems / ncu --nvtx; a no-op costing nanoseconds when no tool is attached)
         char label[96];
         std::snprintf(label, sizeof(label), "qsim pass %zu/%zu: %d ops, %d sweeps, t=%d%s", pass_i + 1, p.passes.size(), pd.n_ops,
-                      pd.n_sweeps, pd.t, prm.redirect ? ", fused exchange" : (prm.init_basis ? ", basis-state input" : ""));
+                      pd.n_sweeps, pd.t, prm.redirect ? (prm.redirect == 2 ? ", fused exchange in place" : ", fused exchange") : (prm.init_basis ? ", basis-state input" : ""));
         struct NvtxScope { explicit NvtxScope(const char* l) { nvtxRangePushA(l); } ~NvtxScope() { nvtxRangePop(); } };
-        if (p.jit.size() != p.passes.size()) {
-            p.jit.assign(p.passes.size(), nullptr);
-            p.jit_req.assign(p.passes.size(), nullptr);
-            p.jit_tried.assign(p.passes.size(), 0);
+        if (p.jit.size() != 2 * p.passes.size()) {   // two builds per pass: one warp group / two (JitSlots)
+            p.jit.assign(2 * p.passes.size(), nullptr);
+            p.jit_req.assign(2 * p.passes.size(), nullptr);
+            p.jit_tried.assign(2 * p.passes.size(), 0);
         }
         JitSlots slots;
-        slots.kernel = &p.jit[pass_i];
-        slots.request = &p.jit_req[pass_i];
-        slots.tried = &p.jit_tried[pass_i];
+        slots.kernel = &p.jit[2 * pass_i];
+        slots.request = &p.jit_req[2 * pass_i];
+        slots.tried = &p.jit_tried[2 * pass_i];
         slots.force = p.force_jit;
         {
             NvtxScope range(label);

@@ -7,6 +7,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
@@ -64,8 +65,9 @@ std::string num(long long v) { return std::to_string(v); }
 // names of the register variables that hold slot k's amplitude
 struct Slots {
     std::vector<int> var;   // slot -> variable index (bit flips on register bits are renamings)
-    std::string r(int k) const { return "xr" + num(var[k]); }
-    std::string i(int k) const { return "xi" + num(var[k]); }
+    std::string pfx;        // (two-group kernels: the first half's variables outlive its block)
+    std::string r(int k) const { return pfx + "xr" + num(var[k]); }
+    std::string i(int k) const { return pfx + "xi" + num(var[k]); }
 };
 
 bool is_one(const double* m) { return m[0] == 1.0 && m[1] == 0.0; }
@@ -272,18 +274,55 @@ void emit_op(Gen& g, Slots& s, const PassDesc& pd, const SweepDesc& sd, const De
 
 }  // namespace
 
-std::string jit_generate_compute(const PassDesc& pd, const DevOp* ops) {
+// Can this pass run as TWO WARP GROUPS (pass_kernel_body.inc, QSIM_DUAL_GROUPS)?  Full tiles swept by all 512 (virtual)
+// threads only.
+bool jit_dual_possible(const PassDesc& pd) {
+    if (pd.t != kMaxTileBits || kMaxRegBits != 3 || pd.n_sweeps < 1) return false;
+    for (int sw = 0; sw < pd.n_sweeps; ++sw)
+        if (pd.sweep[sw].r != 3 || pd.sweep[sw].nthr != 9) return false;
+    return true;
+}
+
+// Rough count of FP64 instructions per tile and thread (8 amplitudes), to tell compute-heavy passes from HBM-bound ones.
+int jit_fp64_estimate(const PassDesc& pd, const DevOp* ops) {
+    int total = 0;
+    for (int o = 0; o < pd.n_ops; ++o) {
+        const DevOp& op = ops[o];
+        int w = 0;
+        switch (op.kind) {
+            case OP_MAT: w = 64; break;
+            case OP_MATREAL: w = 32; break;
+            case OP_ADIAG: w = 32; break;
+            case OP_DIAG: w = 24; break;
+            case OP_PHASE: w = 80; break;
+            default: w = 0;
+        }
+        if (op.kind != OP_PHASE && op.kind != OP_DIAG && op.thome == T_REG && op.slotmask != 0 &&
+            (op.slotmask & 0xff) != 0xff) w /= 2;   // a control on a register bit: half the slots
+        total += w;
+    }
+    return total;
+}
+
+std::string jit_generate_compute(const PassDesc& pd, const DevOp* ops, bool dual) {
     Gen g;
     g.indent = 0;
     g.line("// generated by qsim_b200 jit.cpp: per-tile compute of one pass (n=" + num(pd.n) + ", t=" + num(pd.t) + ", " +
-           num(pd.n_sweeps) + " sweep(s), " + num(pd.n_ops) + " op(s))");
-    g.line("__device__ __forceinline__ void jit_compute_tile(const PassParams& P, unsigned char* tile, uint64_t gbase, uint32_t tid,");
-    g.line("                                                 const DevOp* sops, const double2* eu, const uint16_t* base_tab) {");
+           num(pd.n_sweeps) + " sweep(s), " + num(pd.n_ops) + " op(s))" + (dual ? ", two warp groups" : ""));
+    if (dual) {
+        g.line("#define QSIM_DUAL_GROUPS 1");
+        g.line("__device__ __forceinline__ void jit_compute_tile(const PassParams& P, unsigned char* tile, uint64_t gbase, uint32_t tid0,");
+        g.line("                                                 const DevOp* sops, const double2* eu, const uint16_t* base_tab, uint32_t bar_id) {");
+    } else {
+        g.line("__device__ __forceinline__ void jit_compute_tile(const PassParams& P, unsigned char* tile, uint64_t gbase, uint32_t tid,");
+        g.line("                                                 const DevOp* sops, const double2* eu, const uint16_t* base_tab) {");
+    }
     g.indent = 1;
     g.line("const uint32_t tile_u32 = smem_u32(tile);");
-    g.line("const uint32_t warp = tid >> 5;");
+    if (!dual) g.line("const uint32_t warp = tid >> 5;");
     g.line("const double2* tables = reinterpret_cast<const double2*>(P.phase_tables);");
-    g.line("(void)warp; (void)tables; (void)eu; (void)sops; (void)gbase;");
+    g.line(std::string(dual ? "" : "(void)warp; ") + "(void)tables; (void)eu; (void)sops; (void)gbase;");
+    const std::string BAR = dual ? "asm volatile(\"bar.sync %0, 256;\" ::\"r\"(bar_id) : \"memory\");" : "__syncthreads();";
     const int T = kComputeThreads;
     for (int sw = 0; sw < pd.n_sweeps; ++sw) {
         const SweepDesc& sd = pd.sweep[sw];
@@ -297,58 +336,107 @@ std::string jit_generate_compute(const PassDesc& pd, const DevOp* ops) {
         const bool permuted_store = (xl != 0u) || (n_tail > 0) || mapped_load;
         const bool partial_warp = n_active < 32u;          // lanes beyond the tile inside the one active warp
         const bool some_warps_idle = n_active < (uint32_t)T;
-        g.line("// ---- sweep " + num(sw) + ": r=" + num(sd.r) + " nthr=" + num(sd.nthr));
-        g.open("");
-        if (sw > 0) g.line("__syncthreads();");
-        if (some_warps_idle) g.open("if ((warp << 5) < " + num(n_active) + "u)");
-        else g.open("");
-        if (partial_warp) g.line("const bool active = tid < " + num(n_active) + "u;");
-        g.line("const uint32_t base_local = base_tab[" + num(sw * T) + " + (int)tid];");
-        g.line("const uint32_t a0_ = tile_u32 + base_local * 16u;");
-        Slots s;
-        s.var.resize(n_slots);
-        for (int k = 0; k < n_slots; ++k) s.var[k] = k;
-        {
-            std::string decl = "double ";
-            for (int k = 0; k < n_slots; ++k) decl += (k ? ", " : "") + ("xr" + num(k) + " = 0.0, xi" + num(k) + " = 0.0");
-            g.line(decl + ";");
-        }
-        const std::string guard = partial_warp ? "if (active) " : "";
-        if (mapped_load) {
-            const uint16_t* loff;
-            if (pass_head) {
-                g.line("uint32_t lb_ = base_tab[" + num((pd.n_sweeps + 1) * T) + " + (int)tid];");
-                for (int f = 0; f < pd.n_head_dyn; ++f)
-                    g.line("if ((gbase & " + hex(pd.head_dyn[f].cmask_out) + ") == " + hex(pd.head_dyn[f].cval_out) + ") lb_ ^= " +
-                           hex32(pd.head_dyn[f].w) + ";");
-                loff = pd.load_slot_off;
-            } else {
-                g.line("uint32_t lb_ = " + hex32(sd.head_const) + ";");
-                for (int j = 0; j < pd.t; ++j)
-                    if (sd.head_lin[j]) g.line("if ((base_local >> " + num(j) + ") & 1u) lb_ ^= " + hex32(sd.head_lin[j]) + ";");
-                loff = sd.load_slot_off;
-            }
-            for (int k = 0; k < n_slots; ++k)
-                g.line(guard + "lds128(tile_u32 + ((lb_ ^ " + hex32(loff[k]) + ") << 4), " + s.r(k) + ", " + s.i(k) + ");");
-        } else {
-            for (int k = 0; k < n_slots; ++k)
-                g.line(guard + "lds128(a0_ + " + num((long long)sd.slot_off[k] * 16) + "u, " + s.r(k) + ", " + s.i(k) + ");");
-        }
-        for (int o = sd.op_begin; o < sd.op_end; ++o) emit_op(g, s, pd, sd, ops[o], o, n_slots);
-        if (permuted_store) g.line("__syncthreads();");
         const bool plain_store = !last || (pd.n_tail == 0 && pd.n_dyn == 0 && xl == 0u);
-        if (plain_store) {
-            for (int k = 0; k < n_slots; ++k)
-                g.line(guard + "sts128(a0_ + " + num((long long)sd.slot_off[k] * 16) + "u, " + s.r(k) + ", " + s.i(k) + ");");
-        } else {
+        const std::string guard = partial_warp ? "if (active) " : "";
+        // the three parts of a sweep for one (virtual) thread: addresses + loads, ops, stores; `px` prefixes the names that
+        // must outlive the block they are set in (two-group kernels, first half of a sweep that permutes the tile)
+        auto emit_decl = [&](Slots& s, const std::string& px) {
+            s.var.resize(n_slots);
+            s.pfx = px;
+            for (int k = 0; k < n_slots; ++k) s.var[k] = k;
+            std::string decl = "double ";
+            for (int k = 0; k < n_slots; ++k) decl += (k ? ", " : "") + (px + "xr" + num(k) + " = 0.0, " + px + "xi" + num(k) + " = 0.0");
+            g.line(decl + ";");
+        };
+        auto emit_load = [&](Slots& s) {
+            if (partial_warp) g.line("const bool active = tid < " + num(n_active) + "u;");
+            g.line("const uint32_t base_local = base_tab[" + num(sw * T) + " + (int)tid];");
+            g.line("const uint32_t a0_ = tile_u32 + base_local * 16u;");
+            if (mapped_load) {
+                const uint16_t* loff;
+                if (pass_head) {
+                    g.line("uint32_t lb_ = base_tab[" + num((pd.n_sweeps + 1) * T) + " + (int)tid];");
+                    for (int f = 0; f < pd.n_head_dyn; ++f)
+                        g.line("if ((gbase & " + hex(pd.head_dyn[f].cmask_out) + ") == " + hex(pd.head_dyn[f].cval_out) + ") lb_ ^= " +
+                               hex32(pd.head_dyn[f].w) + ";");
+                    loff = pd.load_slot_off;
+                } else {
+                    g.line("uint32_t lb_ = " + hex32(sd.head_const) + ";");
+                    for (int j = 0; j < pd.t; ++j)
+                        if (sd.head_lin[j]) g.line("if ((base_local >> " + num(j) + ") & 1u) lb_ ^= " + hex32(sd.head_lin[j]) + ";");
+                    loff = sd.load_slot_off;
+                }
+                for (int k = 0; k < n_slots; ++k)
+                    g.line(guard + "lds128(tile_u32 + ((lb_ ^ " + hex32(loff[k]) + ") << 4), " + s.r(k) + ", " + s.i(k) + ");");
+            } else {
+                for (int k = 0; k < n_slots; ++k)
+                    g.line(guard + "lds128(a0_ + " + num((long long)sd.slot_off[k] * 16) + "u, " + s.r(k) + ", " + s.i(k) + ");");
+            }
+        };
+        // where the stores go: `dst` names a variable holding a0_ (plain) or sb_ (mapped)
+        auto emit_store_base = [&](const std::string& dst, bool declare) {
+            const std::string lhs = (declare ? "const uint32_t " : "") + dst + " = ";
+            if (plain_store) { g.line(lhs + "a0_;"); return; }
             g.line("uint32_t sb_ = (uint32_t)base_tab[" + num(pd.n_sweeps * T) + " + (int)tid] ^ " + hex32(xl) + ";");
             for (int f = 0; f < pd.n_dyn; ++f)
                 g.line("if ((gbase & " + hex(pd.dyn[f].cmask_out) + ") == " + hex(pd.dyn[f].cval_out) + ") sb_ ^= " + hex32(pd.dyn[f].w) + ";");
-            for (int k = 0; k < n_slots; ++k)
-                g.line(guard + "sts128(tile_u32 + ((sb_ ^ " + hex32(pd.store_slot_off[k]) + ") << 4), " + s.r(k) + ", " + s.i(k) + ");");
+            g.line(lhs + "sb_;");
+        };
+        auto emit_store = [&](const Slots& s, const std::string& base) {
+            for (int k = 0; k < n_slots; ++k) {
+                if (plain_store) g.line(guard + "sts128(" + base + " + " + num((long long)sd.slot_off[k] * 16) + "u, " + s.r(k) + ", " + s.i(k) + ");");
+                else g.line(guard + "sts128(tile_u32 + ((" + base + " ^ " + hex32(pd.store_slot_off[k]) + ") << 4), " + s.r(k) + ", " + s.i(k) + ");");
+            }
+        };
+        g.line("// ---- sweep " + num(sw) + ": r=" + num(sd.r) + " nthr=" + num(sd.nthr));
+        g.open("");
+        if (sw > 0) g.line(BAR);
+        if (!dual) {
+            if (some_warps_idle) g.open("if ((warp << 5) < " + num(n_active) + "u)");
+            else g.open("");
+            Slots s;
+            emit_decl(s, "");
+            emit_load(s);
+            for (int o = sd.op_begin; o < sd.op_end; ++o) emit_op(g, s, pd, sd, ops[o], o, n_slots);
+            if (permuted_store) g.line(BAR);
+            if (plain_store) emit_store(s, "a0_");
+            else { emit_store_base("sbx_", true); emit_store(s, "sbx_"); }
+            g.close();
+            if (some_warps_idle && permuted_store) g.line("else { " + BAR + " }   // keep the barrier count equal across warps");
+        } else if (!permuted_store) {
+            // each thread does the work of virtual threads tid0 and tid0 + 256, one after the other
+            for (int h = 0; h < 2; ++h) {
+                g.open("");
+                g.line("const uint32_t tid = tid0 + " + num(256 * h) + "u;");
+                Slots s;
+                emit_decl(s, "");
+                emit_load(s);
+                for (int o = sd.op_begin; o < sd.op_end; ++o) emit_op(g, s, pd, sd, ops[o], o, n_slots);
+                emit_store(s, "a0_");
+                g.close();
+            }
+        } else {
+            // the sweep permutes the tile: both halves are loaded before anything is stored (the first half stays in registers)
+            Slots s0, s1;
+            emit_decl(s0, "h0");
+            g.line("uint32_t h0sb_;");
+            g.open("");
+            g.line("const uint32_t tid = tid0;");
+            emit_load(s0);
+            for (int o = sd.op_begin; o < sd.op_end; ++o) emit_op(g, s0, pd, sd, ops[o], o, n_slots);
+            emit_store_base("h0sb_", false);
+            g.close();
+            g.open("");
+            g.line("const uint32_t tid = tid0 + 256u;");
+            emit_decl(s1, "");
+            emit_load(s1);
+            for (int o = sd.op_begin; o < sd.op_end; ++o) emit_op(g, s1, pd, sd, ops[o], o, n_slots);
+            g.line(BAR);
+            if (plain_store) emit_store(s1, "a0_");
+            else { emit_store_base("sbx_", true); emit_store(s1, "sbx_"); }
+            g.close();
+            emit_store(s0, "h0sb_");
         }
-        g.close();
-        if (some_warps_idle && permuted_store) g.line("else { __syncthreads(); }   // keep the barrier count equal across warps");
         g.close();
     }
     g.indent = 0;
@@ -356,7 +444,7 @@ std::string jit_generate_compute(const PassDesc& pd, const DevOp* ops) {
     return g.os.str();
 }
 
-std::string jit_translation_unit(const PassDesc& pd, const DevOp* ops);   // defined below (needs tu_from_compute)
+std::string jit_translation_unit(const PassDesc& pd, const DevOp* ops, bool dual);   // defined below (needs tu_from_compute)
 
 // ---- NVRTC (loaded on demand: the library itself does not link it) ----------------------------------------------------
 
@@ -672,9 +760,38 @@ struct JitRequest {
     std::string compute;
 };
 
-std::shared_ptr<JitRequest> jit_make_request(const PassDesc& pd, const DevOp* ops) {
+namespace {
+struct DualPolicy {
+    std::atomic<int> mode{1};        // 0 off, 1 auto, 2 always (whenever possible)
+    std::atomic<int> min_fp64{400};
+    DualPolicy() {
+        if (const char* e = std::getenv("QSIM_DUAL")) {
+            const std::string v(e);
+            mode = (v == "off" || v == "0") ? 0 : ((v == "always" || v == "2") ? 2 : 1);
+        }
+        if (const char* e = std::getenv("QSIM_DUAL_MIN_FP64")) min_fp64 = std::atoi(e);
+    }
+};
+DualPolicy& dual_policy() {
+    static DualPolicy p;
+    return p;
+}
+}  // namespace
+
+void jit_set_dual(int mode, int min_fp64) {
+    if (mode >= 0 && mode <= 2) dual_policy().mode = mode;
+    if (min_fp64 >= 0) dual_policy().min_fp64 = min_fp64;
+}
+
+bool jit_dual_wanted(const PassDesc& pd, const DevOp* ops) {
+    const int mode = dual_policy().mode;
+    if (mode == 0 || !ops || !jit_dual_possible(pd)) return false;
+    return mode == 2 || jit_fp64_estimate(pd, ops) >= dual_policy().min_fp64;
+}
+
+std::shared_ptr<JitRequest> jit_make_request(const PassDesc& pd, const DevOp* ops, bool dual) {
     auto rq = std::make_shared<JitRequest>();
-    rq->compute = jit_generate_compute(pd, ops);
+    rq->compute = jit_generate_compute(pd, ops, dual);
     static const uint64_t skeleton = fnv1a(kSrcPassDesc) * 31 + fnv1a(kSrcPassDevice) * 17 + fnv1a(kSrcKernelBody);
     rq->key = fnv1a(rq->compute) ^ ((uint64_t)QSIM_REG_BITS << 56) ^ (skeleton * 0x9E3779B97F4A7C15ULL);
     return rq;
@@ -771,12 +888,12 @@ void jit_wait_all() {
     w.cv_done.wait(lk, [&] { return w.inflight.empty(); });
 }
 
-std::shared_ptr<JitKernel> jit_get_kernel(const PassDesc& pd, const DevOp* ops, bool needs_device) {
-    const auto rq = jit_make_request(pd, ops);
+std::shared_ptr<JitKernel> jit_get_kernel(const PassDesc& pd, const DevOp* ops, bool needs_device, bool dual) {
+    const auto rq = jit_make_request(pd, ops, dual);
     return jit_lookup(*rq, needs_device, /*async=*/false, nullptr);
 }
 
-std::string jit_translation_unit(const PassDesc& pd, const DevOp* ops) { return tu_from_compute(jit_generate_compute(pd, ops)); }
+std::string jit_translation_unit(const PassDesc& pd, const DevOp* ops, bool dual) { return tu_from_compute(jit_generate_compute(pd, ops, dual)); }
 
 size_t jit_copy_cubin(const JitKernel& k, void* out, size_t cap) {
     if (out && cap) std::memcpy(out, k.cubin.data(), k.cubin.size() < cap ? k.cubin.size() : cap);

@@ -37,13 +37,23 @@ void jit_set_mode(JitMode mode, int min_qubits);
 bool jit_wanted(const PassDesc& pd);
 
 // CUDA C++ of the specialised per-tile compute for this pass (the generated part only).
-std::string jit_generate_compute(const PassDesc& pd, const DevOp* host_ops);
+// dual = true: the TWO-WARP-GROUP build of the kernel (pass_kernel_body.inc, QSIM_DUAL_GROUPS): the 16 warps work as two
+// groups of 8 on two tiles at once, so that one group's shared-memory / shuffle / barrier phases overlap the other's FP64
+// phases.  For compute-heavy passes (jit_dual_wanted); HBM-bound passes keep the one-group build, whose ring keeps two
+// tiles in flight instead of one.
+std::string jit_generate_compute(const PassDesc& pd, const DevOp* host_ops, bool dual = false);
 // The whole translation unit handed to NVRTC (generated part + the three embedded sources).
-std::string jit_translation_unit(const PassDesc& pd, const DevOp* host_ops);
+std::string jit_translation_unit(const PassDesc& pd, const DevOp* host_ops, bool dual = false);
+// Full 12-bit tiles swept by all threads in every sweep, and enough FP64 work per tile that the pass is bound by the SM, not
+// by HBM (QSIM_DUAL=off|auto|always, QSIM_DUAL_MIN_FP64: FP64 instructions per tile and thread, default 400).
+bool jit_dual_possible(const PassDesc& pd);
+bool jit_dual_wanted(const PassDesc& pd, const DevOp* host_ops);
+void jit_set_dual(int mode, int min_fp64);   // mode 0 off / 1 auto / 2 always, -1 keeps; min_fp64 < 0 keeps
+int jit_fp64_estimate(const PassDesc& pd, const DevOp* host_ops);
 
 // The generated source of a pass and its cache key (the expensive part of a lookup; kept per program and pass).
 struct JitRequest;
-std::shared_ptr<JitRequest> jit_make_request(const PassDesc& pd, const DevOp* host_ops);
+std::shared_ptr<JitRequest> jit_make_request(const PassDesc& pd, const DevOp* host_ops, bool dual = false);
 // The kernel if it is ready (process cache, on-disk cache).  Otherwise: async = false compiles now; async = true queues the
 // compile on a background thread and returns nullptr with *pending = true - the caller launches the interpreter kernel this
 // time and asks again at the next launch, so run() never waits for NVRTC (QSIM_JIT_ASYNC=0 turns this off).  nullptr with
@@ -55,7 +65,7 @@ void jit_wait_all();   // blocks until every queued compile has finished
 // Compile (or fetch from the process-wide cache) the kernel of this pass.  Returns nullptr when NVRTC is unavailable or
 // the compile failed in Auto mode (logged once; the caller uses the interpreter kernel); throws in Always mode.
 // needs_device = false only compiles to a cubin (used by the CPU-side build check); such a kernel cannot be launched.
-std::shared_ptr<JitKernel> jit_get_kernel(const PassDesc& pd, const DevOp* host_ops, bool needs_device = true);
+std::shared_ptr<JitKernel> jit_get_kernel(const PassDesc& pd, const DevOp* host_ops, bool needs_device = true, bool dual = false);
 
 // Launch with the interpreter kernel's parameters.
 cudaError_t jit_launch(JitKernel& k, const PassParams& params, const void* tmap, const void* tmap_keep, const void* tmap_send,

@@ -16,6 +16,7 @@ int pick_stages(const PassDesc& pd, int wanted);
 // Where the engine remembers, per program and pass, what the run-time specialisation has come to (all may be null:
 // interpreter only).
 struct JitSlots {
+    // each points at TWO entries: [0] the one-group build of the pass kernel, [1] the two-warp-group build (jit.hpp)
     std::shared_ptr<JitKernel>* kernel = nullptr;    // the looked-up kernel
     std::shared_ptr<JitRequest>* request = nullptr;  // generated source + key, kept while a background compile is pending
     char* tried = nullptr;                           // 1: decided (kernel found, or the interpreter it is)

@@ -483,27 +483,45 @@ cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t s
         if (const char* e = std::getenv("QSIM_SEND_CTAS")) send = std::atoi(e);
         if (send > 0 && send < (int)grid) params.send_ctas = send;
     }
+    if (params.redirect == 2) {
+        // the in-place exchange counts items per CTA across the two GPUs: it needs the sender / keeper split, the
+        // handshake words, and a tile XOR (deferred X gates) that does not cross the exchanged bit
+        uint64_t xdep = 0;
+        for (int sg = 0; sg < params.pd.n_segments; ++sg)
+            xdep |= ((params.pd.xor_tau >> params.pd.seg[sg].src_shift) & params.pd.seg[sg].mask) << params.pd.seg[sg].dst_shift;
+        if (!params.send_ctas || ((xdep >> params.redirect_bit) & 1ULL) || !params.hs_local || !params.hs_peer || !params.hs_error ||
+            params.dst_keep != params.state)
+            return cudaErrorInvalidValue;
+    }
     // A kernel specialised for this pass's structure (large states, pre-compiled circuits; see jit.hpp).  In the default
     // mode the compile runs on a background thread: until it is ready the interpreter kernel below does the pass.
     if (params.use_tensor_map && (host_ops || params.pd.n_ops == 0)) {
+        // compute-heavy passes take the two-warp-group build (not for basis-state input or the in-place exchange, which
+        // only the one-group skeleton implements); its factor tables of fused diagonal runs exist in four copies
+        const size_t smem_dual = smem + 2 * (size_t)params.pd.n_phase * 13 * sizeof(double2);
+        const int dual = (!params.init_basis && params.redirect != 2 && params.stages == 3 && smem_dual <= (size_t)kMaxDynamicSmem &&
+                          params.n_tiles >= (uint64_t)num_sms && jit_dual_wanted(params.pd, host_ops)) ? 1 : 0;
+        // both groups of a CTA need a tile: a state of fewer than two tiles per SM runs on half as many CTAs as it has tiles
+        if (dual && grid * 2 > params.n_tiles) grid = params.n_tiles / 2;
         std::shared_ptr<JitKernel> local_k;
         std::shared_ptr<JitRequest> local_r;
-        std::shared_ptr<JitKernel>* slot = jit.kernel ? jit.kernel : &local_k;
-        std::shared_ptr<JitRequest>* req = jit.request ? jit.request : &local_r;
-        if (!*slot && !(jit.tried && *jit.tried)) {
+        std::shared_ptr<JitKernel>* slot = jit.kernel ? jit.kernel + dual : &local_k;
+        std::shared_ptr<JitRequest>* req = jit.request ? jit.request + dual : &local_r;
+        char* tried = jit.tried ? jit.tried + dual : nullptr;
+        if (!*slot && !(tried && *tried)) {
             const JitMode mode = jit_mode();
             bool pending = false;
             if (mode != JitMode::Off && (jit.force || jit_wanted(params.pd))) {
-                if (!*req) *req = jit_make_request(params.pd, host_ops);
+                if (!*req) *req = jit_make_request(params.pd, host_ops, dual != 0);
                 const bool async = !jit.force && mode == JitMode::Auto && jit_async_enabled() && jit.kernel != nullptr;
                 *slot = jit_lookup(**req, /*needs_device=*/true, async, &pending);
             }
             if (!pending) {
-                if (jit.tried) *jit.tried = 1;
+                if (tried) *tried = 1;
                 req->reset();
             }
         }
-        if (*slot) return jit_launch(**slot, params, &tmap, &tmap_keep, &tmap_send, (unsigned)grid, smem, stream);
+        if (*slot) return jit_launch(**slot, params, &tmap, &tmap_keep, &tmap_send, (unsigned)grid, dual ? smem_dual : smem, stream);
     }
     fused_pass_kernel<<<(unsigned)grid, kComputeThreads, smem, stream>>>(params, tmap, tmap_keep, tmap_send);
     return cudaGetLastError();

@@ -207,6 +207,17 @@ struct PassParams {
     int32_t send_ctas;        // > 0: CTAs [0, send_ctas) take the tiles that leave, the others the tiles that stay
     void* dst_keep;
     void* dst_send;
+    // redirect == 2: the fused exchange IN PLACE (no second buffer: dst_keep is `state` itself, dst_send the partner's live
+    // buffer).  A leaving tile lands on the partner's own leaving tile of the same item number (both ranks run the same
+    // grid over the same item order), so CTA c may store its item i only after the partner's CTA c has LOADED its item i:
+    // every sender CTA publishes hs_base + (items loaded) in the partner's hs array (hs_peer[c], a relaxed system-scope
+    // store over NVLink) and polls its own (hs_local[c]).  hs_base grows from exchange to exchange, so the words never need a reset.
+    // A poll that sees nothing for hs_timeout_ns sets *hs_error and goes on (wrong data, reported by the host: no hang).
+    unsigned long long* hs_local;
+    unsigned long long* hs_peer;
+    unsigned long long hs_base;
+    unsigned long long hs_timeout_ns;
+    int32_t* hs_error;
     PassDesc pd;
 };
 static_assert(sizeof(PassParams) <= 4000, "kernel parameter space");

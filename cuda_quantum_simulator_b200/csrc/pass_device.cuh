@@ -94,6 +94,7 @@ __device__ __forceinline__ uint64_t instr_offset(const PassDesc& pd, uint32_t q)
 
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -111,6 +112,24 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
 
 __device__ __forceinline__ double shfl_xor_f64(double v, int lane_mask) {
     return __shfl_xor_sync(0xffffffffu, v, lane_mask);
+}
+
+// cross-GPU handshake words of the in-place fused exchange (PassParams::hs_*).  RELAXED system-scope accesses on purpose: the
+// word only says "my copy of that tile has arrived in my shared memory" (the mbarrier has been observed), nothing the writer
+// stored has to become visible with it, and a release store (MEMBAR.SYS) would first wait for every TMA store this SM has in
+// flight over NVLink - one tile per round trip (measured: 280 GB/s instead of 700).
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
 struct TileGeom {

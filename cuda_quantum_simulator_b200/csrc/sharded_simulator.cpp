@@ -189,6 +189,11 @@ std::array<unsigned char, ShardedSimulator::kUniqueIdBytes> ShardedSimulator::cr
 
 // ---- construction ---------------------------------------------------------------------------------------------------
 
+namespace {
+constexpr size_t kHsWords = 1024;                       // one per CTA of a pass launch (grid <= number of SMs)
+constexpr size_t kHsBytes = kHsWords * 8 + 64;          // + the error word
+}  // namespace
+
 struct ShardedSimulator::CompiledPlan {
     b200::ShardPlanRec plan;
     std::vector<qsim_program_t*> programs;   // per step: program or nullptr (swap)
@@ -239,6 +244,8 @@ ShardedSimulator::ShardedSimulator(int num_qubits, int rank, int world_size, con
         const auto all = allGather(want);
         if (std::all_of(all.begin(), all.end(), [](double v) { return v != 0.0; }))
             cuda_chk(cudaMalloc(reinterpret_cast<void**>(&bufs_[1]), shard_bytes), "cudaMalloc(second shard buffer)");
+        cuda_chk(cudaMalloc(reinterpret_cast<void**>(&hs_), kHsBytes), "cudaMalloc(handshake words)");
+        cuda_chk(cudaMemset(hs_, 0, kHsBytes), "memset(handshake words)");
         try {
             openPeers();
             exchange_ = Exchange::PeerMemory;
@@ -262,6 +269,7 @@ ShardedSimulator::~ShardedSimulator() {
     for (void* b : peer_base_) cudaIpcCloseMemHandle(b);
     for (auto*& b : bounce_) if (b) cudaFree(b);
     for (auto*& b : bufs_) if (b) cudaFree(b);
+    if (hs_) cudaFree(hs_);
 }
 
 const char* ShardedSimulator::exchangeName() const {
@@ -273,7 +281,26 @@ void ShardedSimulator::setStream(cudaStream_t s) {
     chk(qsim_sim_set_stream(static_cast<qsim_sim_t*>(shard_), s));
 }
 
-void ShardedSimulator::synchronize() { chk(qsim_sim_synchronize(static_cast<qsim_sim_t*>(shard_))); }
+void ShardedSimulator::synchronize() {
+    chk(qsim_sim_synchronize(static_cast<qsim_sim_t*>(shard_)));
+    checkExchanges(false);
+}
+
+void ShardedSimulator::checkExchanges(bool collective) {
+    if (!hs_unchecked_) return;
+    int err = 0;
+    cuda_chk(cudaMemcpyAsync(&err, reinterpret_cast<unsigned char*>(hs_) + kHsWords * 8, sizeof(int), cudaMemcpyDeviceToHost, stream_),
+             "read handshake status");
+    cuda_chk(cudaStreamSynchronize(stream_), "sync");
+    if (collective) {   // every rank learns of any rank's failure, so that all of them leave the collective call sequence together
+        for (double v : allGather((double)err))
+            if (v != 0.0 && err == 0) err = (int)v;
+        hs_unchecked_ = false;
+    }
+    if (err != 0)
+        throw std::runtime_error(err == 1 ? "qsim_b200: an in-place qubit exchange timed out waiting for the partner GPU (the state is invalid)"
+                                          : "qsim_b200: an in-place qubit exchange could not split its grid (the state is invalid)");
+}
 
 void ShardedSimulator::barrier() {
     if (world_ > 1)
@@ -289,19 +316,27 @@ std::vector<double> ShardedSimulator::allGather(double v) {
 
 void ShardedSimulator::openPeers() {
     struct Info {
-        unsigned char handle[2][64];
-        uint64_t offset[2];
+        unsigned char handle[3][64];   // the shard's buffer(s), then the handshake words
+        uint64_t offset[3];
         int32_t n_bufs;
         int32_t pad;
     } mine{};
     mine.n_bufs = bufs_[1] ? 2 : 1;
     for (int b = 0; b < mine.n_bufs; ++b) chk(qsim_ipc_get_handle(bufs_[b], mine.handle[b], &mine.offset[b]));
+    chk(qsim_ipc_get_handle(hs_, mine.handle[2], &mine.offset[2]));
     const auto all = comm_->allGatherBytes(&mine, sizeof(Info), stream_);
     peer_ptr_.assign(ng_, {nullptr, nullptr});
+    peer_hs_.assign(ng_, nullptr);
     for (int b = 0; b < ng_; ++b) {
         const int peer = rank_ ^ (1 << b);
         Info pi;
         std::memcpy(&pi, all.data() + sizeof(Info) * (size_t)peer, sizeof(Info));
+        {
+            void* base = nullptr;
+            chk(qsim_ipc_open_handle(pi.handle[2], &base));
+            peer_base_.push_back(base);
+            peer_hs_[b] = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(base) + pi.offset[2]);
+        }
         for (int k = 0; k < pi.n_bufs && k < mine.n_bufs; ++k) {
             void* base = nullptr;
             chk(qsim_ipc_open_handle(pi.handle[k], &base));
@@ -326,6 +361,7 @@ cuDoubleComplex* ShardedSimulator::devicePtr() {
 }
 
 std::vector<std::complex<double>> ShardedSimulator::getLocalState() {
+    checkExchanges(false);
     std::vector<std::complex<double>> out(size_t(1) << nl_);
     chk(qsim_sim_get_state(static_cast<qsim_sim_t*>(shard_), reinterpret_cast<double*>(out.data())));
     return out;
@@ -436,8 +472,26 @@ void ShardedSimulator::swapNccl(int peer, int g, int l) {
 }
 
 bool ShardedSimulator::runThenSwap(void* program, int g, int l) {
-    if (exchange_ != Exchange::PeerMemory || !bufs_[1]) return false;
+    if (exchange_ != Exchange::PeerMemory || std::getenv("QSIM_NO_FUSED_EXCHANGE") != nullptr) return false;
     qsim_program_t* prog = static_cast<qsim_program_t*>(program);
+    if (!bufs_[1] || std::getenv("QSIM_FORCE_INPLACE_EXCHANGE") != nullptr) {
+        // no room for a second buffer (36 qubits on 8 GPUs: 128 GiB shards): the same fusion IN PLACE, the stores over the
+        // partner's live shard ordered tile by tile by the kernels' own handshake.  No barrier before: the partner's kernel
+        // only publishes a tile as loaded from inside THIS step's pass, which its stream runs after everything earlier.
+        if (std::getenv("QSIM_NO_INPLACE_EXCHANGE") != nullptr || !hs_) return false;
+        int ok = 0;
+        chk(qsim_shard_inplace_exchange_possible(static_cast<qsim_sim_t*>(shard_), prog, l, &ok));
+        if (!ok) return false;   // (a property of the compiled pass: the same answer on every rank)
+        const int b = g - nl_;
+        ++hs_epoch_;
+        chk(qsim_shard_execute_exchange_inplace(static_cast<qsim_sim_t*>(shard_), prog, peer_ptr_[b][cur_], g, l, hs_, peer_hs_[b],
+                                                hs_epoch_ << 32, 0, reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(hs_) + kHsWords * 8)));
+        hs_unchecked_ = true;
+        ++fused_exchanges_;
+        ++inplace_exchanges_;
+        barrier();
+        return true;
+    }
     uint64_t mask = 0;
     chk(qsim_program_last_tile_mask(prog, &mask));
     if (mask == 0 || ((mask >> l) & 1)) return false;   // no pass to ride on, or the swapped qubit is one of its tile qubits
@@ -539,6 +593,7 @@ void ShardedSimulator::restoreIdentityLayout() {
 // ---- read-out -------------------------------------------------------------------------------------------------------
 
 double ShardedSimulator::getTotalProbability() {
+    checkExchanges(true);
     double part = 0.0;
     chk(qsim_shard_partial_probability(static_cast<qsim_sim_t*>(shard_), -1, &part));
     double tot = 0.0;
@@ -547,6 +602,7 @@ double ShardedSimulator::getTotalProbability() {
 }
 
 int ShardedSimulator::measureBit(int bit, double uniform, double* p0_out) {
+    checkExchanges(true);
     if (bit < 0 || bit >= n_) throw std::invalid_argument("Qubit index out of range");
     qsim_sim_t* h = static_cast<qsim_sim_t*>(shard_);
     const int pos = perm_[bit];
@@ -580,6 +636,7 @@ int ShardedSimulator::measureQubit(int qubit, double uniform) {
 }
 
 std::vector<double> ShardedSimulator::getMarginalProbabilities(const std::vector<int>& qubits) {
+    checkExchanges(true);
     const int k = (int)qubits.size();
     if (k > 12) throw std::invalid_argument("at most 12 qubits");
     std::vector<int> phys(k);
@@ -611,6 +668,7 @@ std::vector<double> ShardedSimulator::getMarginalProbabilities(const std::vector
 }
 
 std::vector<int64_t> ShardedSimulator::sample(const std::vector<double>& uniforms) {
+    checkExchanges(true);
     qsim_sim_t* h = static_cast<qsim_sim_t*>(shard_);
     bool identity = true;
     for (int q = 0; q < n_; ++q) identity = identity && perm_[q] == q;

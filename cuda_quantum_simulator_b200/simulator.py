@@ -65,6 +65,13 @@ class CompiledCircuit:
             self._h = c_void_p()
 
 
+def jit_set_dual(mode, min_fp64: int = -1):
+    """Two-warp-group build of the specialised kernels: mode "off" | "auto" | "always" (or 0 / 1 / 2); see qsim_jit_set_dual in
+    include/qsim_b200.h."""
+    m = {"off": 0, "auto": 1, "always": 2}.get(mode, mode)
+    _lib.check(_lib.lib().qsim_jit_set_dual(int(m), int(min_fp64)))
+
+
 def jit_set_mode(mode, min_qubits: int = 0):
     """mode: "off" | "auto" | "always" (or 0 / 1 / 2); see qsim_jit_set_mode in include/qsim_b200.h."""
     m = {"off": 0, "auto": 1, "always": 2}.get(mode, mode)

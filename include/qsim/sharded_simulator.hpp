@@ -102,6 +102,9 @@ public:
     int localQubits() const { return nl_; }
     int64_t fusedExchanges() const { return fused_exchanges_; }
     int64_t separateExchanges() const { return separate_exchanges_; }
+    // of fusedExchanges(): those that ran IN PLACE (no second buffer; stores over the partner's live shard under the
+    // cross-GPU handshake of qsim_shard_execute_exchange_inplace)
+    int64_t inPlaceExchanges() const { return inplace_exchanges_; }
     const char* exchangeName() const;
     void setStream(cudaStream_t s);
     void synchronize();
@@ -125,6 +128,13 @@ private:
     bool pristine_ = true, order_preserving_ = true, identity_only_ = false;
     int64_t fused_exchanges_ = 0, separate_exchanges_ = 0;
     cudaStream_t stream_ = nullptr;
+    // in-place fused exchange: 1024 handshake words + the error word, one small allocation every partner maps
+    unsigned long long* hs_ = nullptr;
+    std::vector<unsigned long long*> peer_hs_;      // per rank bit
+    uint64_t hs_epoch_ = 0;
+    int64_t inplace_exchanges_ = 0;
+    bool hs_unchecked_ = false;
+    void checkExchanges(bool collective);           // throws if a handshake of an in-place exchange timed out
 
     void openPeers();
     void swapSeparate(int g, int l);

@@ -115,6 +115,13 @@ QSIM_API qsim_status_t qsim_program_info(const qsim_program_t* p, int64_t info[8
  * 2 = every pass and a failed compile is an error.  min_qubits <= 0 keeps the current threshold.
  * Environment: QSIM_JIT=off|auto|always, QSIM_JIT_MIN_QUBITS. */
 QSIM_API qsim_status_t qsim_jit_set_mode(int mode, int min_qubits);
+/* Specialised kernels come in two builds.  One warp group: all 16 warps sweep one tile together, two tiles in flight (HBM-bound
+ * passes).  TWO warp groups: 8 + 8 warps on two tiles at once, each thread doing two threads' work in turn, so that one
+ * group's shared-memory / shuffle / barrier phases overlap the other's FP64 phases (compute-heavy passes: many ops per tile).
+ * mode: 0 = never, 1 = passes whose estimated FP64 instructions per tile and thread reach min_fp64 (default, 400),
+ * 2 = every pass that can (full 12-qubit tiles, >= 148 tiles); -1 / min_fp64 < 0 keep the current value.
+ * Environment: QSIM_DUAL=off|auto|always, QSIM_DUAL_MIN_FP64. */
+QSIM_API qsim_status_t qsim_jit_set_dual(int mode, int min_fp64);
 /* In mode 1 a run never waits for the compiler: the first launches of a new pass structure use the ahead-of-time kernel
  * while a background thread compiles (QSIM_JIT_ASYNC=0: compile in the calling thread instead).  qsim_jit_wait blocks until
  * every queued compile has finished (benchmarks, or before a long run). */
@@ -211,6 +218,23 @@ QSIM_API qsim_status_t qsim_shard_swap_p2p(qsim_sim_t* s, void* peer_state, int 
  * its last pass (qsim_program_last_tile_mask): run qsim_sim_execute + qsim_shard_swap_p2p instead. */
 QSIM_API qsim_status_t qsim_shard_execute_exchange(qsim_sim_t* s, const qsim_program_t* p, void* alt_state,
                                                    void* peer_alt_state, int global_qubit, int local_qubit);
+/* The fused exchange IN PLACE, for shards that leave no room for a second buffer (36 qubits on 8 x 180 GB): amplitudes
+ * that stay are stored where they were, amplitudes that leave go straight over the partner's own leaving amplitudes in
+ * `peer_state` (the partner's LIVE buffer, peer-mapped).  Both GPUs run the same grid over the same tile order, and a
+ * tile is stored over the partner's tile only after the partner's kernel has loaded that tile: each sender CTA publishes
+ * `hs_base` + its count of loaded tiles in the partner's handshake words (`hs_peer`, 1024 x u64, peer-mapped) and polls
+ * its own (`hs_local`).  `hs_base` must grow by at least 2^32 from one exchange to the next on both ranks (the words are
+ * never reset).  Ranks must be synchronised BEFORE the call (the partner's previous kernels have finished) and after it.
+ * A poll that sees no progress for `timeout_ns` (0: 10 s) sets *hs_error_dev (device int, caller-zeroed) and the kernel
+ * runs to its end without waiting any more: the state is then invalid, nothing hangs.  Needs
+ * qsim_shard_inplace_exchange_possible; a program whose first pass would start from a lazily reset shard is written out first. */
+QSIM_API qsim_status_t qsim_shard_execute_exchange_inplace(qsim_sim_t* s, const qsim_program_t* p, void* peer_state,
+                                                           int global_qubit, int local_qubit, void* hs_local, void* hs_peer,
+                                                           uint64_t hs_base, uint64_t timeout_ns, int* hs_error_dev);
+/* *possible_out = 1 when the last pass of `p` can carry the exchange of `local_qubit` in place: the qubit is not one of its
+ * tile qubits, the shard has at least 16 tiles, and no deferred X gate pairs tiles across that qubit. */
+QSIM_API qsim_status_t qsim_shard_inplace_exchange_possible(qsim_sim_t* s, const qsim_program_t* p, int local_qubit,
+                                                            int* possible_out);
 /* Bit q set: local qubit q is a tile qubit of the program's last pass (0 when the program has no pass). */
 QSIM_API qsim_status_t qsim_program_last_tile_mask(const qsim_program_t* p, uint64_t* mask_out);
 /* Bounce-buffer variant for NCCL send/recv: pack the half shard that must leave into `buf`
@@ -289,6 +313,8 @@ QSIM_API qsim_status_t qsim_sharded_swap(qsim_sharded_t* h, int global_position,
 /* info[0]=local qubits, [1]=rank qubits, [2]=exchanges fused into a pass, [3]=separate exchanges, [4]=1 peer memory / 2 NCCL,
  * [5]=rank, [6]=world size, [7]=1 if the second shard buffer of the fused exchange exists */
 QSIM_API qsim_status_t qsim_sharded_info(const qsim_sharded_t* h, int64_t info[8]);
+/* Of info[2]: the exchanges that ran in place (no second buffer; qsim_shard_execute_exchange_inplace). */
+QSIM_API qsim_status_t qsim_sharded_inplace_exchanges(const qsim_sharded_t* h, int64_t* count_out);
 QSIM_API qsim_sim_t* qsim_sharded_local(qsim_sharded_t* h);   /* the shard as a qsim_sim_t (timing, launch counters); borrowed */
 QSIM_API qsim_status_t qsim_sharded_set_stream(qsim_sharded_t* h, void* cuda_stream);
 QSIM_API qsim_status_t qsim_sharded_synchronize(qsim_sharded_t* h);

@@ -194,3 +194,51 @@ def test_background_compilation_never_blocks_a_run():
         assert made(after) > made(before)
     finally:
         q.jit_set_mode("auto", 26)
+
+
+@pytest.mark.parametrize("n,depth,seed,from_state", [(20, 150, 1, True), (20, 60, 2, False), (21, 200, 3, True), (22, 120, 4, True)])
+def test_two_warp_group_kernels(n, depth, seed, from_state):
+    """The TWO-WARP-GROUP build of the specialised kernels (pass_kernel_body.inc QSIM_DUAL_GROUPS; what compute-heavy passes of
+    large states get), forced for every pass that can take it: all gate kinds, folded flips (sweeps that permute the tile keep
+    the first half in registers), fused diagonals (four factor copies), deferred X on outer bits (tile pairs across the two
+    groups), several tiles per CTA.  Against the oracle, and bit-identical run to run (the groups' interleaving must not matter)."""
+    q.jit_set_dual("always")
+    try:
+        rng = np.random.default_rng(7000 + seed)
+        g = H.random_gates(n, depth, rng)
+        if seed % 2 == 1:
+            g = np.concatenate([g, H.gates([("X", n - 1), ("X", n - 2), ("X", 3)])])   # deferred X: partner tiles, local XOR
+        st0 = H.random_state(n, rng) if from_state else None
+        before = q.jit_stats()["launches"]
+        got, sim = run_gpu(n, g, st0)
+        assert q.jit_stats()["launches"] > before
+        want = H.oracle_run(n, g, st0)
+        assert np.max(np.abs(got - want)) < 1e-12
+        prog = q.CompiledCircuit(q.Circuit(n).extend(g), specialise=True)
+        outs = []
+        for _ in range(3):
+            s2 = q.Simulator(n)
+            if st0 is not None:
+                s2.set_state(st0)
+            else:
+                s2.set_state(H.zero_state(n))
+            s2.execute(prog)
+            outs.append(s2.get_state_vector())
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], outs[2])
+        assert np.max(np.abs(outs[0] - want)) < 1e-12
+    finally:
+        q.jit_set_dual("auto")
+
+
+def test_two_warp_group_kernels_c3_shape():
+    """C3-style layers (fused diagonal runs with factors that depend on bits outside the tile) through the two-group build."""
+    q.jit_set_dual("always")
+    try:
+        n = 21
+        c = H.qft_style_circuit(n)
+        sim = q.Simulator(n)
+        sim.run(c)
+        want = H.oracle_run(n, c.gates)
+        assert np.max(np.abs(sim.get_state_vector() - want)) < 1e-12
+    finally:
+        q.jit_set_dual("auto")

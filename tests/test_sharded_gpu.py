@@ -17,7 +17,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("exchange", ["p2p", "nccl", "native", "native-nccl"])
+@pytest.mark.parametrize("exchange", ["p2p", "nccl", "native", "native-nccl", "native-inplace"])
 def test_two_gpu_parity(exchange):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
@@ -92,6 +92,85 @@ def test_fused_exchange_on_one_gpu(nl, g_local, tail_x):
         out = np.empty(1 << nl, np.complex128)
         _lib.check(L.qsim_sim_get_state(sims[1], out.ctypes.data_as(c_void_p)))
         assert np.array_equal(out, got[1 << nl:])
+    L.qsim_program_destroy(prog)
+    for h in sims:
+        L.qsim_sim_destroy(h)
+
+
+@pytest.mark.parametrize("nl,g_local,tail_x", [(18, 17, False), (18, 3, False), (18, 14, False), (18, 15, True), (19, 18, True), (18, 16, "victim"),
+                                               (15, 14, False)])
+def test_inplace_fused_exchange_on_one_gpu(nl, g_local, tail_x):
+    """qsim_shard_execute_exchange_inplace with both 'ranks' of a 2-shard state on this one GPU, their kernels running
+    concurrently on two streams: no second buffer - the staying half is stored in place, the leaving half straight over the
+    other rank's leaving half, ordered tile by tile by the kernels' handshake words.  Two epochs back to back (the words are
+    never reset).  Oracle: gates on the full state, then the qubit swap as an index permutation."""
+    from ctypes import byref, c_int, c_uint64, c_void_p
+
+    import numpy as np
+    import torch
+
+    from cuda_quantum_simulator_b200 import _lib
+
+    L = _lib.lib()
+    n = nl + 1
+    rng = np.random.default_rng(1900 + nl + g_local)
+    others = [q for q in range(nl) if q != g_local]
+    lst = []
+    for _ in range(30):
+        k = str(rng.choice(["H", "T", "CNOT", "Rz", "X"]))
+        a, b = (int(x) for x in rng.choice(others, 2, replace=False))
+        lst.append((k, a, b) if k == "CNOT" else (k, a, float(rng.uniform(-3, 3))) if k == "Rz" else (k, a))
+    if tail_x == "victim":
+        lst.append(("X", g_local))
+        lst.append(("X", others[-2]))
+    elif tail_x:
+        lst.append(("X", others[-1]))   # a deferred X on a high local qubit: tiles are stored to their pair partner's place
+    g = H.gates(lst)
+    full = H.random_state(n, rng)
+    idx = np.arange(1 << n, dtype=np.uint64)
+    bg, bl = (idx >> np.uint64(nl)) & np.uint64(1), (idx >> np.uint64(g_local)) & np.uint64(1)
+    src = ((idx & ~((np.uint64(1) << np.uint64(nl)) | (np.uint64(1) << np.uint64(g_local)))) | (bl << np.uint64(nl)) | (bg << np.uint64(g_local))).astype(np.int64)
+
+    bufs = [torch.empty(1 << nl, dtype=torch.complex128, device="cuda") for _ in range(2)]
+    hs = [torch.zeros(1024 + 8, dtype=torch.int64, device="cuda") for _ in range(2)]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    sims = []
+    for r in range(2):
+        h = c_void_p()
+        _lib.check(L.qsim_shard_create(n, 1, r, c_void_p(bufs[r].data_ptr()), byref(h)))
+        shard = np.ascontiguousarray(full[r << nl:(r + 1) << nl])
+        _lib.check(L.qsim_sim_set_state(h, shard.ctypes.data_as(c_void_p)))
+        _lib.check(L.qsim_sim_set_stream(h, c_void_p(streams[r].cuda_stream)))
+        sims.append(h)
+    torch.cuda.synchronize()
+    prog = c_void_p()
+    _lib.check(L.qsim_program_compile_ex(n, 1, _lib.gates_ptr(g), len(g), c_uint64(0), byref(prog)))
+    ok = c_int()
+    _lib.check(L.qsim_shard_inplace_exchange_possible(sims[0], prog, g_local, byref(ok)))
+
+    def call(r, epoch):
+        return L.qsim_shard_execute_exchange_inplace(sims[r], prog, c_void_p(bufs[1 - r].data_ptr()), nl, g_local,
+                                                     c_void_p(hs[r].data_ptr()), c_void_p(hs[1 - r].data_ptr()), c_uint64(epoch << 32),
+                                                     c_uint64(3_000_000_000), c_void_p(hs[r].data_ptr() + 1024 * 8))
+
+    mask = c_uint64()
+    _lib.check(L.qsim_program_last_tile_mask(prog, byref(mask)))
+    if tail_x == "victim" or nl < 16 or ((mask.value >> g_local) & 1):
+        # a deferred X pairs tiles across the exchanged qubit / fewer than 16 tiles / the qubit is a tile qubit of the last
+        # pass: refused, nothing touched
+        assert ok.value == 0
+        assert call(0, 1) != 0
+    else:
+        assert ok.value == 1
+        want = full
+        for epoch in (1, 2):
+            want = H.oracle_run(n, g, want)[src]
+            for r in range(2):
+                _lib.check(call(r, epoch))
+            torch.cuda.synchronize()
+            assert int(hs[0][1024].item()) == 0 and int(hs[1][1024].item()) == 0, "handshake timed out"
+            got = np.concatenate([bufs[r].cpu().numpy() for r in range(2)])
+            assert np.max(np.abs(got - want)) < 1e-12
     L.qsim_program_destroy(prog)
     for h in sims:
         L.qsim_sim_destroy(h)

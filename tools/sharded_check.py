@@ -19,6 +19,9 @@ import helpers as H
 exchange = sys.argv[1] if len(sys.argv) > 1 else "auto"
 big = int(sys.argv[2]) if len(sys.argv) > 2 else 28
 NATIVE = exchange.startswith("native")          # "native" / "native-nccl": the C++ driver (qsim::ShardedSimulator) over NCCL
+INPLACE = exchange == "native-inplace"          # the fused exchange in place (no second buffer), forced for shards of any size
+if INPLACE:
+    os.environ["QSIM_FORCE_INPLACE_EXCHANGE"] = "1"
 if NATIVE:
     exchange = "nccl" if exchange.endswith("nccl") else "auto"
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -68,7 +71,8 @@ if NATIVE:
             assert res == (0 if r < p0 else 1) and np.max(np.abs(sim.get_state_vector() - want_c)) < 1e-10
         if rank == 0:
             print(f"native n={n} seed={seed} exchange={sim.exchange} swaps/run={plans[1].n_swaps} fused={sim.fused_exchanges} "
-                  f"separate={sim.separate_exchanges} max|err|={err:.2e}", flush=True)
+                  f"separate={sim.separate_exchanges} in-place={sim.inplace_exchanges} max|err|={err:.2e}", flush=True)
+        assert not (INPLACE and n >= 22) or sim.inplace_exchanges > 0
         sim.close()
     assert worst < 1e-10, worst
     dist.barrier()
