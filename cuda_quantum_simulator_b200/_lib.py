@@ -106,6 +106,7 @@ def _declare(L: ctypes.CDLL) -> None:
         "qsim_sim_launch_count": (c_int64, [P]),
         "qsim_sim_set_timing": (c_int, [P, c_int]),
         "qsim_sim_pass_time_ms": (c_int, [P, POINTER(c_double), POINTER(c_int64)]),
+        "qsim_sim_pass_timeline": (c_int, [P, P, c_int64, P]),
         "qsim_sim_pass_times": (c_int, [P, P, c_int64, POINTER(c_int64)]),
         "qsim_shard_create": (c_int, [c_int, c_int, c_int, P, PP]),
         "qsim_shard_swap_p2p": (c_int, [P, P, c_int, c_int]),

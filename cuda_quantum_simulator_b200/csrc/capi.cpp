@@ -525,6 +525,15 @@ qsim_status_t qsim_sim_pass_times(qsim_sim_t* s, double* out_ms, int64_t cap, in
     });
 }
 
+qsim_status_t qsim_sim_pass_timeline(qsim_sim_t* s, uint64_t* out, int64_t cap, int64_t* n_out) {
+    return guarded([&] {
+        require(s != nullptr && n_out != nullptr, "null argument");
+        const auto t = s->sim->state().engine().passTimeline();
+        *n_out = (int64_t)t.size();
+        for (int64_t i = 0; i < (int64_t)t.size() && i < cap; ++i) out[i] = t[i];
+    });
+}
+
 // ---- shards -----------------------------------------------------------------------------------
 
 qsim_status_t qsim_shard_swap_p2p(qsim_sim_t* s, void* peer_state, int global_qubit, int local_qubit) {

@@ -65,11 +65,31 @@ Engine::Engine() {
     if (std::getenv("QSIM_TMA_1D")) use_tensor_map_ = false;
     if (const char* e = std::getenv("QSIM_GRAPH_MAX_QUBITS")) graph_max_qubits_ = std::atoi(e);
     if (std::getenv("QSIM_NO_GRAPH")) graph_max_qubits_ = 0;
+    if (std::getenv("QSIM_PASS_TIMELINE")) {
+        // pinned host memory the kernels write directly (system-scope stores): still readable after a kernel has faulted
+        CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&d_timeline_), (64 * 8 + 1024) * sizeof(unsigned long long), cudaHostAllocMapped));
+        std::memset(d_timeline_, 0, (64 * 8 + 1024) * sizeof(unsigned long long));
+        graph_max_qubits_ = 0;   // (a replayed graph would stamp the slots it was captured with)
+    }
+}
+
+std::vector<unsigned long long> Engine::passTimeline() {
+    std::vector<unsigned long long> out;
+    if (!d_timeline_) return out;
+    cudaStreamSynchronize(stream_);   // (no check: the point is to see how far a faulting kernel got)
+    const int64_t n = timeline_n_ < 64 ? timeline_n_ : 64;
+    std::vector<unsigned long long> all(d_timeline_, d_timeline_ + 64 * 8);
+    for (int64_t k = timeline_n_ - n; k < timeline_n_; ++k)
+        for (int j = 0; j < 8; ++j) out.push_back(all[(size_t)(k % 64) * 8 + j]);
+    if (std::getenv("QSIM_PASS_PROGRESS"))   // per-CTA progress words of the last two-group launch (development aid)
+        out.insert(out.end(), d_timeline_ + 64 * 8, d_timeline_ + 64 * 8 + 1024);
+    return out;
 }
 
 Engine::~Engine() {
     for (void* p : scratch_) if (p) cudaFree(p);
     if (d_aux_) cudaFree(d_aux_);
+    if (d_timeline_) cudaFreeHost(d_timeline_);
     if (d_ops_) cudaFree(d_ops_);
     if (h_ops_) cudaFreeHost(h_ops_);
     if (staged_) cudaEventDestroy(staged_);
@@ -138,6 +158,7 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
         prm.use_tensor_map = use_tensor_map_ ? 1 : 0;
         prm.init_basis = 0;
         prm.pad = 0;
+        if (const char* e = std::getenv("QSIM_DBG_FLAGS")) prm.pad = std::atoi(e);   // (development aid)
         prm.init_index = init_basis >= 0 ? (uint64_t)init_basis : 0;
         if (first && init_basis >= 0) {
             // Basis-state input: the driver's memset is the fastest zero fill (7.4 TB/s against 5.7 TB/s from the pass
@@ -159,6 +180,8 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
         prm.hs_base = redirect ? redirect->hs_base : 0;
         prm.hs_timeout_ns = redirect ? redirect->hs_timeout_ns : 0;
         prm.hs_error = (last && redirect) ? redirect->hs_error : nullptr;
+        prm.timeline = d_timeline_ ? d_timeline_ + (size_t)((timeline_n_++) % 64) * 8 : nullptr;
+        prm.progress = d_timeline_ ? d_timeline_ + 64 * 8 : nullptr;
         prm.redirect_bit = redirect ? redirect->bit : 0;
         prm.redirect_keep = redirect ? redirect->keep_value : 0;
         prm.send_ctas = 0;   // chosen by launch_pass

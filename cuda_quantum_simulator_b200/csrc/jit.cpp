@@ -308,7 +308,8 @@ std::string jit_generate_compute(const PassDesc& pd, const DevOp* ops, bool dual
     Gen g;
     g.indent = 0;
     g.line("// generated by qsim_b200 jit.cpp: per-tile compute of one pass (n=" + num(pd.n) + ", t=" + num(pd.t) + ", " +
-           num(pd.n_sweeps) + " sweep(s), " + num(pd.n_ops) + " op(s))" + (dual ? ", two warp groups" : ""));
+           num(pd.n_sweeps) + " sweep(s), " + num(pd.n_ops) + " op(s), ~" + num(jit_fp64_estimate(pd, ops)) + " FP64 instructions per thread)" +
+           (dual ? ", two warp groups" : ""));
     if (dual) {
         g.line("#define QSIM_DUAL_GROUPS 1");
         g.line("__device__ __forceinline__ void jit_compute_tile(const PassParams& P, unsigned char* tile, uint64_t gbase, uint32_t tid0,");
@@ -763,7 +764,7 @@ struct JitRequest {
 namespace {
 struct DualPolicy {
     std::atomic<int> mode{1};        // 0 off, 1 auto, 2 always (whenever possible)
-    std::atomic<int> min_fp64{400};
+    std::atomic<int> min_fp64{450};
     DualPolicy() {
         if (const char* e = std::getenv("QSIM_DUAL")) {
             const std::string v(e);

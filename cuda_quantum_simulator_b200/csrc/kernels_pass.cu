@@ -435,8 +435,14 @@ bool encode_tensor_map(const PassParams& prm, void* base, CUtensorMap* out) {
         if (d == 0) { gdim[d] *= 2; box[d] *= 2; }
         else gstride[d - 1] = (cuuint64_t)16 << td.start_bit;
     }
+    static const CUtensorMapL2promotion promo = [] {
+        const char* e = std::getenv("QSIM_TMA_L2PROMO");   // (development aid) 0 / 64 / 128 / 256
+        const int v = e ? std::atoi(e) : 256;
+        return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                      : (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+    }();
     return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // The dynamic shared-memory opt-in is a per-device (per-context) function attribute: set it once on every device this

@@ -218,6 +218,9 @@ struct PassParams {
     unsigned long long hs_base;
     unsigned long long hs_timeout_ns;
     int32_t* hs_error;
+    // development aid (QSIM_PASS_TIMELINE=1): CTA 0's %globaltimer at eight points of the kernel, null otherwise
+    unsigned long long* timeline;
+    unsigned long long* progress;   // (1024 words: per CTA and warp group, the item it has reached)
     PassDesc pd;
 };
 static_assert(sizeof(PassParams) <= 4000, "kernel parameter space");

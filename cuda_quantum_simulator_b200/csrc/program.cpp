@@ -888,7 +888,13 @@ std::string Program::describe() const {
         const PassDesc& p = passes[i];
         os << "  pass " << i << ": t=" << p.t << " L=" << p.L << " tile_bits=[";
         for (int b = 0; b < p.t; ++b) os << (b ? "," : "") << (int)p.tile_bits[b];
-        os << "] ops=" << p.n_ops << " sweeps=" << p.n_sweeps << "\n";
+        os << "] ops=" << p.n_ops << " sweeps=" << p.n_sweeps;
+        if (p.n_head) os << " head_flips=" << p.n_head << "(" << p.n_head_dyn << " per-tile)";
+        if (p.n_tail) os << " tail_flips=" << p.n_tail << "(" << p.n_dyn << " per-tile)";
+        if (p.xor_local) os << " xor_local=0x" << std::hex << p.xor_local << std::dec;
+        if (p.xor_tau) os << " xor_tau=0x" << std::hex << p.xor_tau << std::dec;
+        if (p.tma_instr_bits) os << " tma_instrs=" << (1 << p.tma_instr_bits);
+        os << "\n";
         for (int s = 0; s < p.n_sweeps; ++s) {
             const SweepDesc& sd = p.sweep[s];
             os << "    sweep " << s << ": regs=[";

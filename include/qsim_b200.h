@@ -118,7 +118,7 @@ QSIM_API qsim_status_t qsim_jit_set_mode(int mode, int min_qubits);
 /* Specialised kernels come in two builds.  One warp group: all 16 warps sweep one tile together, two tiles in flight (HBM-bound
  * passes).  TWO warp groups: 8 + 8 warps on two tiles at once, each thread doing two threads' work in turn, so that one
  * group's shared-memory / shuffle / barrier phases overlap the other's FP64 phases (compute-heavy passes: many ops per tile).
- * mode: 0 = never, 1 = passes whose estimated FP64 instructions per tile and thread reach min_fp64 (default, 400),
+ * mode: 0 = never, 1 = passes whose estimated FP64 instructions per tile and thread reach min_fp64 (default, 450),
  * 2 = every pass that can (full 12-qubit tiles, >= 148 tiles); -1 / min_fp64 < 0 keep the current value.
  * Environment: QSIM_DUAL=off|auto|always, QSIM_DUAL_MIN_FP64. */
 QSIM_API qsim_status_t qsim_jit_set_dual(int mode, int min_fp64);
@@ -198,6 +198,10 @@ QSIM_API qsim_status_t qsim_sim_set_timing(qsim_sim_t* s, int enabled);
 QSIM_API qsim_status_t qsim_sim_pass_time_ms(qsim_sim_t* s, double* total_ms, int64_t* n_passes);
 /* Same, one duration per timed pass in launch order (at most `cap` written; *n_out = how many there were). */
 QSIM_API qsim_status_t qsim_sim_pass_times(qsim_sim_t* s, double* out_ms, int64_t cap, int64_t* n_out);
+/* Development aid, only with QSIM_PASS_TIMELINE=1 in the environment when the simulator is created: eight %globaltimer
+ * stamps (ns) of CTA 0 for each of the last <= 64 pass launches - kernel entry, set-up done, first loads issued, first tile
+ * arrived, first tile computed, its store issued, all tiles computed, all stores complete.  *n_out = values available. */
+QSIM_API qsim_status_t qsim_sim_pass_timeline(qsim_sim_t* s, uint64_t* out, int64_t cap, int64_t* n_out);
 
 /* ---- Sharded state: one process per GPU, top n_global qubits = rank -------------- */
 /* The shard holds 2^(num_qubits - n_global) amplitudes; `rank` supplies the values of the global

@@ -66,3 +66,27 @@ def test_background_compilation_machinery(monkeypatch):
     assert [prog.jit_request(i) for i in range(prog.n_passes)] == ["ready"] * prog.n_passes
     q.jit_wait()      # nothing queued: returns at once
     assert q.jit_stats()["failures"] == 0
+
+
+def test_two_warp_group_build_compiles(tmp_path):
+    """The two-warp-group build (QSIM_DUAL_GROUPS: 8 + 8 warps on two tiles at once) of heavy 30-qubit passes: generated,
+    compiled for sm_100a, named barriers of 256 threads in the SASS; the policy picks it for the heavy passes only."""
+    prog = q.CompiledCircuit(q.create_random_circuit(30, 200, 42))
+    c2 = q.CompiledCircuit(q.create_random_circuit(30, 20, 42))
+    assert "two warp groups" not in c2.jit_source(0)          # 9 ops: HBM-bound, one group
+    assert "two warp groups" in prog.jit_source(0)             # 21 executed ops: compute-bound
+    q.jit_set_dual("always")
+    try:
+        src = prog.jit_source(0)
+        assert "QSIM_DUAL_GROUPS" in src and "bar.sync %0, 256" in src and "tid0 + 256u" in src
+        cub = prog.jit_compile(0, want_cubin=True)
+        assert len(cub) > 10000
+        if shutil.which("cuobjdump"):
+            path = tmp_path / "dual.cubin"
+            path.write_bytes(cub)
+            sass = subprocess.run(["cuobjdump", "-sass", str(path)], capture_output=True, text=True).stdout
+            assert "UTMALDG" in sass and "UTMASTG" in sass and "BAR.SYNC" in sass
+        q.jit_set_dual("off")
+        assert "QSIM_DUAL_GROUPS" not in prog.jit_source(0)
+    finally:
+        q.jit_set_dual("auto")
