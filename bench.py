@@ -317,7 +317,7 @@ def main():
         runner = make_sharded(n, args.exchange, args.sharded_driver)
         # one plan per step: a run may leave a different qubit layout / X frame behind than it started from, and a plan is
         # only valid for the layout it was compiled against (plans are shared when the layout repeats)
-        plans = runner.compile_sequence(circuit, 1 + args.warmup + args.steps)   # (the first step is the untimed one from |0..0>)
+        plans = runner.compile_sequence(circuit, 2 + args.warmup + args.steps)   # (the first two steps are untimed: from |0..0>, and the one that lets late kernel builds finish)
         plan = plans[0]
         step_no = [0]
 
@@ -350,6 +350,8 @@ def main():
              # below runs on the dense evolved state, loaded from and stored to HBM in full
     q.jit_wait()   # the pass kernels specialised for this circuit are compiled in the background (a one-off cost per pass
                    # structure, cached on disk; jit.compile_seconds in the line): the timed steps run the steady state
+    step()         # (a first pass that no longer starts from a basis state, and a compute-heavy pass that has two builds to
+    q.jit_wait()   #  choose from, ask for another kernel at their second launch)
     for _ in range(args.warmup):
         step()
     sync_all()
@@ -409,18 +411,20 @@ def main():
             d_info = {"passes": dprog.n_passes, "global_qubit_swaps": 0}
         else:
             runner.reset()
-            dplans = runner.compile_sequence(dcirc, 5)
+            dplans = runner.compile_sequence(dcirc, 10)
             f0 = runner.fused_exchanges
             d_no = [0]
 
             def dstep():
                 runner.execute(dplans[d_no[0]])
                 d_no[0] += 1
-            d_info = {"passes_per_step": [p_.n_passes for p_ in dplans[2:]],
-                      "global_qubit_swaps_per_step": [p_.n_swaps for p_ in dplans[2:]]}
-        dstep()
-        q.jit_wait()
-        dstep()
+            d_info = {"passes_per_step": [p_.n_passes for p_ in dplans[7:]],
+                      "global_qubit_swaps_per_step": [p_.n_swaps for p_ in dplans[7:]]}
+        for _ in range(3):     # untimed: from |0..0>; kernel builds asked for at the second launch of a pass; ...
+            dstep()
+            q.jit_wait()
+        for _ in range(4):     # ... and the two builds of a compute-heavy pass timed against each other in passing (the faster stays)
+            dstep()
         f1 = runner.fused_exchanges if world > 1 else 0
         d_ms = timed(dstep, 3) / 3
         if world > 1:

@@ -203,12 +203,17 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
             p.jit.assign(2 * p.passes.size(), nullptr);
             p.jit_req.assign(2 * p.passes.size(), nullptr);
             p.jit_tried.assign(2 * p.passes.size(), 0);
+            p.jit_tune.assign(p.passes.size(), nullptr);
         }
         JitSlots slots;
         slots.kernel = &p.jit[2 * pass_i];
         slots.request = &p.jit_req[2 * pass_i];
         slots.tried = &p.jit_tried[2 * pass_i];
         slots.force = p.force_jit;
+        if (stream_ != capture_stream_ || !capture_stream_) {   // (never inside a graph capture: events would become nodes)
+            if (!p.jit_tune[pass_i]) p.jit_tune[pass_i] = std::make_shared<DualTune>();
+            slots.tune = p.jit_tune[pass_i].get();
+        }
         {
             NvtxScope range(label);
             CUDA_CHECK(launch_pass(prm, num_sms_, stream_, p.ops.data() + pd.op_offset, slots));

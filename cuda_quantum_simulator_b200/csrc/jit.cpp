@@ -310,6 +310,26 @@ std::string jit_generate_compute(const PassDesc& pd, const DevOp* ops, bool dual
     g.line("// generated by qsim_b200 jit.cpp: per-tile compute of one pass (n=" + num(pd.n) + ", t=" + num(pd.t) + ", " +
            num(pd.n_sweeps) + " sweep(s), " + num(pd.n_ops) + " op(s), ~" + num(jit_fp64_estimate(pd, ops)) + " FP64 instructions per thread)" +
            (dual ? ", two warp groups" : ""));
+    // the pass's tensor-map geometry as literals: box coordinates of a tile and the offsets of its TMA instructions (the
+    // elected warp computes these for every load and store, on the tile's critical path)
+    g.line("#define QSIM_JIT_GEOMETRY 1");
+    g.line("__device__ __forceinline__ void jit_tma_coords(uint64_t g, int (&c)[5]) {");
+    for (int d = 0; d < 5; ++d) {
+        const TmaDim& td = pd.tma_dim[d];
+        if (td.range_bits == 0) { g.line("    c[" + num(d) + "] = 0;"); continue; }
+        const std::string v = "((g >> " + num(td.start_bit) + ") & " + hex((td.range_bits >= 64 ? ~0ULL : ((1ULL << td.range_bits) - 1ULL))) + ")";
+        g.line("    c[" + num(d) + "] = (int)(" + v + (d == 0 ? " * 2ULL" : "") + ");");
+    }
+    g.line("}");
+    g.line("__device__ __forceinline__ uint64_t jit_instr_offset(uint32_t q) {");
+    {
+        std::string e = "0ULL";
+        const int box_bits = pd.t - pd.tma_instr_bits;
+        for (int b = 0; b < pd.tma_instr_bits; ++b)
+            e += " | ((uint64_t)((q >> " + num(b) + ") & 1u) << " + num(pd.tile_bits[box_bits + b]) + ")";
+        g.line("    return " + e + ";");
+    }
+    g.line("}");
     if (dual) {
         g.line("#define QSIM_DUAL_GROUPS 1");
         g.line("__device__ __forceinline__ void jit_compute_tile(const PassParams& P, unsigned char* tile, uint64_t gbase, uint32_t tid0,");
@@ -764,7 +784,7 @@ struct JitRequest {
 namespace {
 struct DualPolicy {
     std::atomic<int> mode{1};        // 0 off, 1 auto, 2 always (whenever possible)
-    std::atomic<int> min_fp64{450};
+    std::atomic<int> min_fp64{350};
     DualPolicy() {
         if (const char* e = std::getenv("QSIM_DUAL")) {
             const std::string v(e);
@@ -778,6 +798,14 @@ DualPolicy& dual_policy() {
     return p;
 }
 }  // namespace
+
+bool jit_dual_autotune() {
+    static const bool on = [] {
+        const char* e = std::getenv("QSIM_DUAL_AUTOTUNE");
+        return !(e && (std::string(e) == "0" || std::string(e) == "off"));
+    }();
+    return on && dual_policy().mode == 1;   // (mode always: every eligible pass takes the two-group build, the tests rely on it)
+}
 
 void jit_set_dual(int mode, int min_fp64) {
     if (mode >= 0 && mode <= 2) dual_policy().mode = mode;

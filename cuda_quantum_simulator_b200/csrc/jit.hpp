@@ -45,9 +45,10 @@ std::string jit_generate_compute(const PassDesc& pd, const DevOp* host_ops, bool
 // The whole translation unit handed to NVRTC (generated part + the three embedded sources).
 std::string jit_translation_unit(const PassDesc& pd, const DevOp* host_ops, bool dual = false);
 // Full 12-bit tiles swept by all threads in every sweep, and enough FP64 work per tile that the pass is bound by the SM, not
-// by HBM (QSIM_DUAL=off|auto|always, QSIM_DUAL_MIN_FP64: FP64 instructions per tile and thread, default 450).
+// by HBM (QSIM_DUAL=off|auto|always, QSIM_DUAL_MIN_FP64: FP64 instructions per tile and thread, default 350).
 bool jit_dual_possible(const PassDesc& pd);
 bool jit_dual_wanted(const PassDesc& pd, const DevOp* host_ops);
+bool jit_dual_autotune();   // QSIM_DUAL_AUTOTUNE=0 turns the measured choice off (the estimate alone decides)
 void jit_set_dual(int mode, int min_fp64);   // mode 0 off / 1 auto / 2 always, -1 keeps; min_fp64 < 0 keeps
 int jit_fp64_estimate(const PassDesc& pd, const DevOp* host_ops);
 

@@ -21,6 +21,16 @@ struct JitSlots {
     std::shared_ptr<JitRequest>* request = nullptr;  // generated source + key, kept while a background compile is pending
     char* tried = nullptr;                           // 1: decided (kernel found, or the interpreter it is)
     bool force = false;                              // specialise whatever the state size, synchronously (pre-compiled circuits)
+    struct DualTune* tune = nullptr;                 // which of the two builds is faster for this pass, measured (may be null)
+};
+// One-group or two-group build?  The FP64 estimate only says "worth trying": when both kernels are ready each is timed once
+// in passing (CUDA events around one ordinary launch, read back later without blocking) and the faster one stays.
+struct DualTune {
+    cudaEvent_t ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int state[2] = {0, 0};     // 0 not timed, 1 events recorded, 2 measured
+    float ms[2] = {0.f, 0.f};
+    int choice = -1;           // -1 undecided, 0 one group, 1 two groups
+    ~DualTune();
 };
 // host_ops: the pass's op records on the host (the key of the run-time specialised kernel).
 cudaError_t launch_pass(const PassParams& params, int num_sms, cudaStream_t stream, const DevOp* host_ops = nullptr,

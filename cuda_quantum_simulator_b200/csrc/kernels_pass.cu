@@ -461,6 +461,12 @@ cudaError_t ensure_smem_optin() {
 
 }  // namespace
 
+DualTune::~DualTune() {
+    for (auto& pair : ev)
+        for (cudaEvent_t e : pair)
+            if (e) cudaEventDestroy(e);
+}
+
 cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t stream, const DevOp* host_ops, const JitSlots& jit) {
     PassParams params = params_in;
     alignas(64) CUtensorMap tmap, tmap_keep, tmap_send;
@@ -505,8 +511,38 @@ cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t s
         // compute-heavy passes take the two-warp-group build (not for basis-state input or the in-place exchange, which
         // only the one-group skeleton implements); its factor tables of fused diagonal runs exist in four copies
         const size_t smem_dual = smem + 2 * (size_t)params.pd.n_phase * 13 * sizeof(double2);
-        const int dual = (!params.init_basis && params.redirect != 2 && params.stages == 3 && smem_dual <= (size_t)kMaxDynamicSmem &&
-                          params.n_tiles >= (uint64_t)num_sms && jit_dual_wanted(params.pd, host_ops)) ? 1 : 0;
+        const bool dual_ok = !params.init_basis && params.redirect != 2 && params.stages == 3 && smem_dual <= (size_t)kMaxDynamicSmem &&
+                             params.n_tiles >= (uint64_t)num_sms && jit_dual_wanted(params.pd, host_ops);
+        int dual = dual_ok ? 1 : 0;
+        // measured choice: once both builds of this pass are loaded, one ordinary launch of each is bracketed by events; the
+        // times are collected at a later launch (cudaEventQuery: never blocks) and the faster build stays
+        // (states of >= 26 qubits: a pass takes >= 0.4 ms there and one measurement is meaningful; below, the estimate decides)
+        DualTune* tune = (dual_ok && !params.redirect && params.pd.n >= 26 && jit.tune && jit.kernel && jit_dual_autotune()) ? jit.tune : nullptr;
+        const uint64_t grid_one = grid;
+        int timing = -1;
+        if (tune) {
+            for (int v = 0; v < 2; ++v)
+                if (tune->state[v] == 1 && cudaEventQuery(tune->ev[v][1]) == cudaSuccess) {
+                    if (cudaEventElapsedTime(&tune->ms[v], tune->ev[v][0], tune->ev[v][1]) == cudaSuccess) tune->state[v] = 2;
+                    else tune->state[v] = 0;
+                }
+            if (tune->choice < 0 && tune->state[0] == 2 && tune->state[1] == 2) {
+                tune->choice = tune->ms[1] < 0.98f * tune->ms[0] ? 1 : 0;
+                static const bool verbose = std::getenv("QSIM_DUAL_VERBOSE") != nullptr;
+                if (verbose)
+                    std::fprintf(stderr, "qsim_b200: pass over %d qubits, %d ops in %d sweeps (~%d FP64 instructions per thread): one warp "
+                                 "group %.3f ms, two %.3f ms -> %s\n", params.pd.n, params.pd.n_ops, params.pd.n_sweeps,
+                                 jit_fp64_estimate(params.pd, host_ops), tune->ms[0], tune->ms[1], tune->choice ? "two" : "one");
+            }
+            if (tune->choice >= 0) dual = tune->choice;
+            else if (jit.kernel[0] && jit.kernel[1]) {   // both ready: time the one that has not been timed yet
+                const int v = tune->state[1] == 0 ? 1 : (tune->state[0] == 0 ? 0 : -1);
+                if (v >= 0) { dual = v; timing = v; }
+            } else if (jit.kernel[1] && !jit.kernel[0] && !(jit.tried && jit.tried[0])) {
+                dual = 0;   // the two-group build is there, the one-group build has not been asked for yet: ask (below)
+            }
+        }
+        (void)cudaGetLastError();   // (cudaEventQuery's cudaErrorNotReady is not an error)
         // both groups of a CTA need a tile: a state of fewer than two tiles per SM runs on half as many CTAs as it has tiles
         if (dual && grid * 2 > params.n_tiles) grid = params.n_tiles / 2;
         std::shared_ptr<JitKernel> local_k;
@@ -527,7 +563,29 @@ cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t s
                 req->reset();
             }
         }
-        if (*slot) return jit_launch(**slot, params, &tmap, &tmap_keep, &tmap_send, (unsigned)grid, dual ? smem_dual : smem, stream);
+        // the build asked for is still being compiled, the other one is loaded: use that rather than the interpreter
+        if (!*slot && jit.kernel && jit.kernel[1 - dual] && (dual == 0 ? dual_ok : true)) {
+            dual = 1 - dual;
+            slot = jit.kernel + dual;
+            timing = -1;
+            grid = grid_one;
+            if (dual && grid * 2 > params.n_tiles) grid = params.n_tiles / 2;
+        }
+        if (!*slot) grid = grid_one;   // (the interpreter: one group)
+        if (*slot) {
+            const bool timed = tune && timing == dual;
+            if (timed) {
+                for (cudaEvent_t& e : tune->ev[dual])
+                    if (!e && cudaEventCreate(&e) != cudaSuccess) return cudaGetLastError();
+                if (cudaError_t e = cudaEventRecord(tune->ev[dual][0], stream)) return e;
+            }
+            const cudaError_t rc = jit_launch(**slot, params, &tmap, &tmap_keep, &tmap_send, (unsigned)grid, dual ? smem_dual : smem, stream);
+            if (timed && rc == cudaSuccess) {
+                if (cudaError_t e = cudaEventRecord(tune->ev[dual][1], stream)) return e;
+                tune->state[dual] = 1;
+            }
+            return rc;
+        }
     }
     fused_pass_kernel<<<(unsigned)grid, kComputeThreads, smem, stream>>>(params, tmap, tmap_keep, tmap_send);
     return cudaGetLastError();

@@ -179,6 +179,10 @@ struct PassDesc {
     TailDyn head_dyn[kMaxTailDyn];
     Segment seg[kMaxSegments];
     SweepDesc sweep[kMaxSweeps];
+    // derived by the compiler so that the kernel's set-up does not walk the arrays above bit by bit
+    uint64_t tile_mask;          // OR of 1 << tile_bits[j]
+    uint64_t xdep;               // tile_base(xor_tau): index XOR between the two tiles of a pair
+    uint64_t pivot_dep;          // tile_base(highest bit of xor_tau)
 };
 
 

@@ -838,6 +838,17 @@ bool build_pass(PassPlan& plan, bool last_pass, const CompileOptions& opt, int n
             pd.load_slot_off[k] = (uint16_t)w;
         }
     }
+    {   // derived fields (see PassDesc)
+        auto base_of = [&](uint64_t tau) {
+            uint64_t b = 0;
+            for (int sg = 0; sg < pd.n_segments; ++sg) b |= ((tau >> pd.seg[sg].src_shift) & pd.seg[sg].mask) << pd.seg[sg].dst_shift;
+            return b;
+        };
+        pd.tile_mask = 0;
+        for (int j = 0; j < pd.t; ++j) pd.tile_mask |= 1ULL << pd.tile_bits[j];
+        pd.xdep = base_of(pd.xor_tau);
+        pd.pivot_dep = pd.xor_tau ? base_of(1ULL << (63 - __builtin_clzll(pd.xor_tau))) : 0ULL;
+    }
     out.passes.push_back(pd);
     return true;
 }

@@ -64,6 +64,7 @@ struct Program {
     mutable std::vector<std::shared_ptr<JitKernel>> jit;
     mutable std::vector<std::shared_ptr<JitRequest>> jit_req;   // kept while the kernel is being compiled in the background
     mutable std::vector<char> jit_tried;
+    mutable std::vector<std::shared_ptr<struct DualTune>> jit_tune;   // per pass: measured choice between the two builds (kernels.cuh)
     bool force_jit = false;      // specialise every pass whatever the state size (a pre-compiled circuit that will run many times)
     std::string describe() const;
 };

@@ -118,7 +118,7 @@ QSIM_API qsim_status_t qsim_jit_set_mode(int mode, int min_qubits);
 /* Specialised kernels come in two builds.  One warp group: all 16 warps sweep one tile together, two tiles in flight (HBM-bound
  * passes).  TWO warp groups: 8 + 8 warps on two tiles at once, each thread doing two threads' work in turn, so that one
  * group's shared-memory / shuffle / barrier phases overlap the other's FP64 phases (compute-heavy passes: many ops per tile).
- * mode: 0 = never, 1 = passes whose estimated FP64 instructions per tile and thread reach min_fp64 (default, 450),
+ * mode: 0 = never, 1 = passes whose estimated FP64 instructions per tile and thread reach min_fp64 (default, 350),
  * 2 = every pass that can (full 12-qubit tiles, >= 148 tiles); -1 / min_fp64 < 0 keep the current value.
  * Environment: QSIM_DUAL=off|auto|always, QSIM_DUAL_MIN_FP64. */
 QSIM_API qsim_status_t qsim_jit_set_dual(int mode, int min_fp64);

@@ -16,9 +16,12 @@ import helpers as H
 
 
 def timed(sim, fn, reps):
-    fn(); sim.synchronize()
-    q.jit_wait()               # specialised kernels are compiled in the background: time the steady state
-    fn(); sim.synchronize()
+    for _ in range(3):
+        fn(); sim.synchronize()
+        q.jit_wait()           # specialised kernels are compiled in the background: time the steady state
+    for _ in range(4):         # (heavy passes: the two builds are timed against each other in passing, the faster one stays)
+        fn()
+    sim.synchronize()
     t0 = time.perf_counter()
     for _ in range(reps):
         fn()
