@@ -800,7 +800,7 @@ class _NativePlan:
         self.n_passes, self.n_ops, self.n_swaps = int(info[0]), int(info[1]), int(info[2])
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:   # (_lib is None while the interpreter shuts down)
             _lib.lib().qsim_sharded_plan_destroy(self._h)
             self._h = c_void_p()
 
