@@ -43,6 +43,10 @@ def lib() -> ctypes.CDLL:
                 "(there is no CPU fallback)")
         _lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_LOCAL)
         _declare(_lib)
+        # specialised kernels are compiled on background threads: the interpreter must not start tearing the process down
+        # (NVRTC's own exit handlers) while one of them is still inside the compiler
+        import atexit
+        atexit.register(_lib.qsim_jit_shutdown)
     return _lib
 
 
@@ -75,6 +79,7 @@ def _declare(L: ctypes.CDLL) -> None:
         "qsim_program_describe": (c_size_t, [P, c_char_p, c_size_t]),
         "qsim_jit_set_mode": (c_int, [c_int, c_int]),
         "qsim_jit_set_dual": (c_int, [c_int, c_int]),
+        "qsim_jit_shutdown": (c_int, []),
         "qsim_jit_stats": (c_int, [POINTER(c_int64)]),
         "qsim_jit_wait": (c_int, []),
         "qsim_program_jit_request": (c_int, [P, c_int, POINTER(c_int)]),

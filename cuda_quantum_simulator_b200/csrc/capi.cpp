@@ -249,6 +249,10 @@ qsim_status_t qsim_program_jit_request(const qsim_program_t* p, int pass, int* s
     });
 }
 
+qsim_status_t qsim_jit_shutdown(void) {
+    return guarded([&] { b200::jit_shutdown(); });
+}
+
 qsim_status_t qsim_jit_wait(void) {
     return guarded([&] { b200::jit_wait_all(); });
 }

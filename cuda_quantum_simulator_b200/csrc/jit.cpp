@@ -92,8 +92,75 @@ void emit_cmul(Gen& g, const Slots& s, int k, const std::string& pr, const std::
     }
 }
 
-void emit_op(Gen& g, Slots& s, const PassDesc& pd, const SweepDesc& sd, const DevOp& op, int o, int n_slots) {
+// Conditional bit flips on a register bit (X / CNOT whose controls sit in thread bits or outside the tile) are not executed
+// as 32 predicated register moves: the thread carries them as an XOR mask over its slot index (`fx_`), applied by the sweep's
+// store addressing (a register bit only permutes the thread's OWN slots, so no barrier is involved).  Ops in between that
+// do not look at the flipped bit are unaffected; a 2x2 on that very bit takes the X-conjugated matrix, a diagonal on it the
+// swapped pair of factors (selects); anything else (controls on register bits, fused diagonal runs) first materialises the
+// pending flips the old way.
+struct Defer {
+    bool enabled = false;
+    bool dirty[4] = {false, false, false, false};
+    uint32_t dep_thr[4] = {0, 0, 0, 0};   // thread bits the pending flips of that register bit were conditioned on
+    bool any() const { return dirty[0] || dirty[1] || dirty[2] || dirty[3]; }
+};
+
+bool jit_defer_flips() {
+    static const bool on = [] {
+        const char* e = std::getenv("QSIM_JIT_DEFER_FLIPS");
+        return !(e && (std::string(e) == "0" || std::string(e) == "off"));
+    }();
+    return on;
+}
+
+bool flip_deferrable(const DevOp& op, int n_slots) {
+    const uint32_t all = (n_slots >= 32) ? 0xffffffffu : ((1u << n_slots) - 1u);
+    return op.kind == OP_FLIP && op.thome == T_REG && (op.cmask_out != 0 || op.cmask_thr != 0) && (op.slotmask & all) == all;
+}
+
+void emit_materialise(Gen& g, Slots& s, Defer& df, int n_slots, int only_bit = -1) {
+    for (int b = 0; b < 4; ++b) {
+        if (!df.dirty[b] || (only_bit >= 0 && b != only_bit)) continue;
+        const int J = 1 << b;
+        g.open("if ((fx_ >> " + num(b) + ") & 1u)");
+        for (int k = 0; k < n_slots; ++k) {
+            if (k & J) continue;
+            const std::string ar = s.r(k), ai = s.i(k), br = s.r(k | J), bi = s.i(k | J);
+            g.line("{ const double ar_ = " + ar + ", ai_ = " + ai + "; " + ar + " = " + br + "; " + ai + " = " + bi + "; " + br + " = ar_; " + bi + " = ai_; }");
+        }
+        g.line("fx_ &= ~" + hex32((uint32_t)J) + ";");
+        g.close();
+        df.dirty[b] = false;
+        df.dep_thr[b] = 0;
+    }
+}
+
+void emit_op(Gen& g, Slots& s, const PassDesc& pd, const SweepDesc& sd, const DevOp& op, int o, int n_slots, Defer* df = nullptr) {
     static const char* kn[] = {"MAT", "MATREAL", "ADIAG", "FLIP", "DIAG", "PHASE"};
+    bool dirty_target = false;   // this op's register target bit carries a pending conditional flip
+    if (df && df->enabled) {
+        const uint32_t all_ = (n_slots >= 32) ? 0xffffffffu : ((1u << n_slots) - 1u);
+        if (flip_deferrable(op, n_slots)) {
+            g.line("// op " + num(o) + ": FLIP target=reg:" + num(op.tbit) + " (conditional: carried as a slot-index XOR to the store)");
+            std::string cond;
+            if (op.cmask_out) cond = "(gbase & " + hex(op.cmask_out) + ") == " + hex(op.cval_out);
+            if (op.cmask_thr) cond += std::string(cond.empty() ? "" : " && ") + "(tid & " + hex32(op.cmask_thr) + ") == " + hex32(op.cval_thr);
+            g.line("if (" + cond + ") fx_ ^= " + hex32(1u << op.tbit) + ";");
+            df->dirty[op.tbit] = true;
+            df->dep_thr[op.tbit] |= op.cmask_thr;
+            return;
+        }
+        if (df->any()) {
+            const bool full = (op.slotmask & all_) == all_;
+            if (op.kind == OP_PHASE || !full) emit_materialise(g, s, *df, n_slots);
+            else if (op.thome == T_LANE) {
+                // the two lanes of a pair must agree on where their slots are: a pending flip conditioned on this very lane
+                // bit differs between them
+                for (int b = 0; b < 4; ++b)
+                    if (df->dirty[b] && ((df->dep_thr[b] >> op.tbit) & 1u)) emit_materialise(g, s, *df, n_slots, b);
+            } else if (op.thome == T_REG && op.kind != OP_FLIP && df->dirty[op.tbit]) dirty_target = true;
+        }
+    }
     static const char* hn[] = {"lane", "reg", "thread", "outside"};
     const std::string M = "reinterpret_cast<const double2*>(sops[" + num(o) + "].m)";
     const uint32_t all = (n_slots >= 32) ? 0xffffffffu : ((1u << n_slots) - 1u);
@@ -194,7 +261,16 @@ void emit_op(Gen& g, Slots& s, const PassDesc& pd, const SweepDesc& sd, const De
     if (op.kind == OP_DIAG) {
         const DiagClass dc = diag_class(op);
         g.line("const double2 d0_ = " + M + "[0], d1_ = " + M + "[3];");
-        if (op.thome == T_REG) {
+        if (op.thome == T_REG && dirty_target) {
+            // the target bit carries a pending flip: the two factors trade places when it is set
+            g.line("const bool sw_ = (fx_ >> " + num(op.tbit) + ") & 1u;");
+            g.line("const double e0r_ = sw_ ? d1_.x : d0_.x, e0i_ = sw_ ? d1_.y : d0_.y, e1r_ = sw_ ? d0_.x : d1_.x, e1i_ = sw_ ? d0_.y : d1_.y;");
+            for (int k = 0; k < n_slots; ++k) {
+                if (!((slotset >> k) & 1)) continue;
+                const bool b = (op.tslots >> k) & 1;
+                emit_cmul(g, s, k, b ? "e1r_" : "e0r_", b ? "e1i_" : "e0i_", dc.real);
+            }
+        } else if (op.thome == T_REG) {
             for (int k = 0; k < n_slots; ++k) {
                 if (!((slotset >> k) & 1)) continue;
                 const bool b = (op.tslots >> k) & 1;
@@ -218,7 +294,12 @@ void emit_op(Gen& g, Slots& s, const PassDesc& pd, const SweepDesc& sd, const De
         }
     } else if (op.thome == T_REG) {
         const int J = 1 << op.tbit;
-        if (op.kind != OP_FLIP) g.line("const double2 ma_ = " + M + "[0], mb_ = " + M + "[1], mc_ = " + M + "[2], md_ = " + M + "[3];");
+        if (op.kind != OP_FLIP && dirty_target) {
+            // the target bit carries a pending flip: X-conjugated matrix [[d, c], [b, a]] when it is set
+            g.line("const bool sw_ = (fx_ >> " + num(op.tbit) + ") & 1u;");
+            g.line("const double2 m0_ = " + M + "[0], m1_ = " + M + "[1], m2_ = " + M + "[2], m3_ = " + M + "[3];");
+            g.line("const double2 ma_ = sw_ ? m3_ : m0_, mb_ = sw_ ? m2_ : m1_, mc_ = sw_ ? m1_ : m2_, md_ = sw_ ? m0_ : m3_;");
+        } else if (op.kind != OP_FLIP) g.line("const double2 ma_ = " + M + "[0], mb_ = " + M + "[1], mc_ = " + M + "[2], md_ = " + M + "[3];");
         for (int k = 0; k < n_slots; ++k) {
             if ((k & J) || !((slotset >> k) & 1)) continue;
             const int k1 = k | J;
@@ -395,19 +476,35 @@ std::string jit_generate_compute(const PassDesc& pd, const DevOp* ops, bool dual
             }
         };
         // where the stores go: `dst` names a variable holding a0_ (plain) or sb_ (mapped)
-        auto emit_store_base = [&](const std::string& dst, bool declare) {
+        // does this sweep carry conditional register-bit flips to its store (Defer)?
+        bool sweep_defers = false;
+        for (int o = sd.op_begin; o < sd.op_end && jit_defer_flips(); ++o) sweep_defers = sweep_defers || flip_deferrable(ops[o], n_slots);
+        const bool index_store = !plain_store || sweep_defers;   // stores address by tile-local index XOR instead of base + literal
+        auto emit_store_base = [&](const std::string& dst, bool declare, const Defer& df) {
             const std::string lhs = (declare ? "const uint32_t " : "") + dst + " = ";
-            if (plain_store) { g.line(lhs + "a0_;"); return; }
-            g.line("uint32_t sb_ = (uint32_t)base_tab[" + num(pd.n_sweeps * T) + " + (int)tid] ^ " + hex32(xl) + ";");
-            for (int f = 0; f < pd.n_dyn; ++f)
-                g.line("if ((gbase & " + hex(pd.dyn[f].cmask_out) + ") == " + hex(pd.dyn[f].cval_out) + ") sb_ ^= " + hex32(pd.dyn[f].w) + ";");
+            if (!index_store) { g.line(lhs + "a0_;"); return; }
+            if (plain_store) g.line("uint32_t sb_ = base_local;");
+            else {
+                g.line("uint32_t sb_ = (uint32_t)base_tab[" + num(pd.n_sweeps * T) + " + (int)tid] ^ " + hex32(xl) + ";");
+                for (int f = 0; f < pd.n_dyn; ++f)
+                    g.line("if ((gbase & " + hex(pd.dyn[f].cmask_out) + ") == " + hex(pd.dyn[f].cval_out) + ") sb_ ^= " + hex32(pd.dyn[f].w) + ";");
+            }
+            // pending conditional flips: slot k's amplitude goes where slot k ^ fx_ lives (the slot offsets are XOR-linear)
+            for (int b = 0; b < sd.r; ++b)
+                if (df.dirty[b])
+                    g.line("if ((fx_ >> " + num(b) + ") & 1u) sb_ ^= " + hex32(plain_store ? sd.slot_off[1 << b] : pd.store_slot_off[1 << b]) + ";");
             g.line(lhs + "sb_;");
         };
         auto emit_store = [&](const Slots& s, const std::string& base) {
             for (int k = 0; k < n_slots; ++k) {
-                if (plain_store) g.line(guard + "sts128(" + base + " + " + num((long long)sd.slot_off[k] * 16) + "u, " + s.r(k) + ", " + s.i(k) + ");");
-                else g.line(guard + "sts128(tile_u32 + ((" + base + " ^ " + hex32(pd.store_slot_off[k]) + ") << 4), " + s.r(k) + ", " + s.i(k) + ");");
+                if (!index_store) g.line(guard + "sts128(" + base + " + " + num((long long)sd.slot_off[k] * 16) + "u, " + s.r(k) + ", " + s.i(k) + ");");
+                else g.line(guard + "sts128(tile_u32 + ((" + base + " ^ " + hex32(plain_store ? sd.slot_off[k] : pd.store_slot_off[k]) + ") << 4), " + s.r(k) + ", " + s.i(k) + ");");
             }
+        };
+        auto emit_ops = [&](Slots& s, Defer& df) {
+            df.enabled = sweep_defers;
+            if (sweep_defers) g.line("uint32_t fx_ = 0u;   // pending conditional flips of register bits (see Defer)");
+            for (int o = sd.op_begin; o < sd.op_end; ++o) emit_op(g, s, pd, sd, ops[o], o, n_slots, &df);
         };
         g.line("// ---- sweep " + num(sw) + ": r=" + num(sd.r) + " nthr=" + num(sd.nthr));
         g.open("");
@@ -416,12 +513,13 @@ std::string jit_generate_compute(const PassDesc& pd, const DevOp* ops, bool dual
             if (some_warps_idle) g.open("if ((warp << 5) < " + num(n_active) + "u)");
             else g.open("");
             Slots s;
+            Defer df;
             emit_decl(s, "");
             emit_load(s);
-            for (int o = sd.op_begin; o < sd.op_end; ++o) emit_op(g, s, pd, sd, ops[o], o, n_slots);
+            emit_ops(s, df);
             if (permuted_store) g.line(BAR);
-            if (plain_store) emit_store(s, "a0_");
-            else { emit_store_base("sbx_", true); emit_store(s, "sbx_"); }
+            if (!index_store) emit_store(s, "a0_");
+            else { emit_store_base("sbx_", true, df); emit_store(s, "sbx_"); }
             g.close();
             if (some_warps_idle && permuted_store) g.line("else { " + BAR + " }   // keep the barrier count equal across warps");
         } else if (!permuted_store) {
@@ -430,10 +528,12 @@ std::string jit_generate_compute(const PassDesc& pd, const DevOp* ops, bool dual
                 g.open("");
                 g.line("const uint32_t tid = tid0 + " + num(256 * h) + "u;");
                 Slots s;
+                Defer df;
                 emit_decl(s, "");
                 emit_load(s);
-                for (int o = sd.op_begin; o < sd.op_end; ++o) emit_op(g, s, pd, sd, ops[o], o, n_slots);
-                emit_store(s, "a0_");
+                emit_ops(s, df);
+                if (!index_store) emit_store(s, "a0_");
+                else { emit_store_base("sbx_", true, df); emit_store(s, "sbx_"); }
                 g.close();
             }
         } else {
@@ -443,18 +543,19 @@ std::string jit_generate_compute(const PassDesc& pd, const DevOp* ops, bool dual
             g.line("uint32_t h0sb_;");
             g.open("");
             g.line("const uint32_t tid = tid0;");
+            Defer df0, df1;
             emit_load(s0);
-            for (int o = sd.op_begin; o < sd.op_end; ++o) emit_op(g, s0, pd, sd, ops[o], o, n_slots);
-            emit_store_base("h0sb_", false);
+            emit_ops(s0, df0);
+            emit_store_base("h0sb_", false, df0);
             g.close();
             g.open("");
             g.line("const uint32_t tid = tid0 + 256u;");
             emit_decl(s1, "");
             emit_load(s1);
-            for (int o = sd.op_begin; o < sd.op_end; ++o) emit_op(g, s1, pd, sd, ops[o], o, n_slots);
+            emit_ops(s1, df1);
             g.line(BAR);
-            if (plain_store) emit_store(s1, "a0_");
-            else { emit_store_base("sbx_", true); emit_store(s1, "sbx_"); }
+            if (!index_store) emit_store(s1, "a0_");
+            else { emit_store_base("sbx_", true, df1); emit_store(s1, "sbx_"); }
             g.close();
             emit_store(s0, "h0sb_");
         }
@@ -727,11 +828,16 @@ struct Worker {
     std::deque<std::pair<uint64_t, std::string>> queue;
     std::unordered_map<uint64_t, bool> inflight;
     bool started = false;
+    bool stopping = false;               // the process is exiting: no new compiles
+    int running = 0;                     // compiles in progress
+    int reregistered = 0;
 };
 Worker& worker() {
     static Worker* w = new Worker();
     return *w;
 }
+
+void worker_atexit();
 
 void worker_main() {
     Worker& w = worker();
@@ -739,9 +845,10 @@ void worker_main() {
         std::pair<uint64_t, std::string> job;
         {
             std::unique_lock<std::mutex> lk(w.mu);
-            w.cv_work.wait(lk, [&] { return !w.queue.empty(); });
+            w.cv_work.wait(lk, [&] { return !w.queue.empty() && !w.stopping; });
             job = std::move(w.queue.front());
             w.queue.pop_front();
+            ++w.running;
         }
         const auto t0 = std::chrono::steady_clock::now();
         auto k = std::make_shared<JitKernel>();
@@ -769,9 +876,25 @@ void worker_main() {
         {
             std::lock_guard<std::mutex> lk(w.mu);
             w.inflight.erase(job.first);
+            --w.running;
+            // (NVRTC registers exit handlers of its own lazily, inside its first compiles: ours has to be registered after
+            // them to run before them)
+            if (w.reregistered < 8) { ++w.reregistered; std::atexit(worker_atexit); }
         }
         w.cv_done.notify_all();
     }
+}
+
+// Registered with atexit when the first worker starts (after NVRTC and the CUDA runtime have been initialised, so it runs
+// BEFORE their own exit handlers): a process must not run into the static destructors of those libraries while a detached
+// worker is still inside nvrtcCompileProgram (seen as a segmentation fault at exit of a test process whose last circuits had
+// queued compiles nobody waited for).  Queued jobs are dropped, compiles in progress get to finish.
+void worker_atexit() {
+    Worker& w = worker();
+    std::unique_lock<std::mutex> lk(w.mu);
+    w.stopping = true;
+    w.queue.clear();
+    w.cv_done.wait_for(lk, std::chrono::seconds(30), [&] { return w.running == 0; });
 }
 
 }  // namespace
@@ -881,6 +1004,7 @@ std::shared_ptr<JitKernel> jit_lookup(const JitRequest& rq, bool needs_device, b
             n_workers = n_workers < 1 ? 1 : (n_workers > 4 ? 4 : n_workers);
             if (const char* e = std::getenv("QSIM_JIT_THREADS")) n_workers = (unsigned)std::max(1, std::atoi(e));
             for (unsigned i = 0; i < n_workers; ++i) std::thread(worker_main).detach();
+            std::atexit(worker_atexit);
         }
         if (!w.inflight.count(rq.key)) {
             // a caller that streams many one-off programs (gate-by-gate application on a large state) must not pile up
@@ -911,10 +1035,14 @@ std::shared_ptr<JitKernel> jit_lookup(const JitRequest& rq, bool needs_device, b
     return k;
 }
 
+void jit_shutdown() {
+    if (worker().started) worker_atexit();
+}
+
 void jit_wait_all() {
     Worker& w = worker();
     std::unique_lock<std::mutex> lk(w.mu);
-    w.cv_done.wait(lk, [&] { return w.inflight.empty(); });
+    w.cv_done.wait(lk, [&] { return w.inflight.empty() || w.stopping; });
 }
 
 std::shared_ptr<JitKernel> jit_get_kernel(const PassDesc& pd, const DevOp* ops, bool needs_device, bool dual) {

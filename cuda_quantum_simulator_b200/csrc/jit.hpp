@@ -62,6 +62,9 @@ std::shared_ptr<JitRequest> jit_make_request(const PassDesc& pd, const DevOp* ho
 std::shared_ptr<JitKernel> jit_lookup(const JitRequest& rq, bool needs_device, bool async, bool* pending);
 bool jit_async_enabled();
 void jit_wait_all();   // blocks until every queued compile has finished
+// Before the process exits: queued compiles are dropped, compiles in progress get to finish, no new ones start (a process
+// must not reach the exit handlers of NVRTC while a background thread is still compiling).  Idempotent.
+void jit_shutdown();
 
 // Compile (or fetch from the process-wide cache) the kernel of this pass.  Returns nullptr when NVRTC is unavailable or
 // the compile failed in Auto mode (logged once; the caller uses the interpreter kernel); throws in Always mode.

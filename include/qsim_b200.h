@@ -126,6 +126,11 @@ QSIM_API qsim_status_t qsim_jit_set_dual(int mode, int min_fp64);
  * while a background thread compiles (QSIM_JIT_ASYNC=0: compile in the calling thread instead).  qsim_jit_wait blocks until
  * every queued compile has finished (benchmarks, or before a long run). */
 QSIM_API qsim_status_t qsim_jit_wait(void);
+/* Call before the process exits if background compiles may still be running (the Python mirror registers it with atexit): queued
+ * compiles are dropped, compiles in progress get to finish, none start after it.  A process must not run into NVRTC's own exit
+ * handlers while a background thread is inside the compiler.  The library also registers it with atexit() itself (best effort:
+ * handlers NVRTC registers later still run first). */
+QSIM_API qsim_status_t qsim_jit_shutdown(void);
 /* Queues the background compile of one pass of a compiled program, or finds its kernel ready: *state = 0 ready, 1 compiling,
  * 2 unavailable.  Needs no GPU (pre-warming the on-disk cache; the GPU-less test of the background machinery). */
 QSIM_API qsim_status_t qsim_program_jit_request(const qsim_program_t* p, int pass, int* state);
