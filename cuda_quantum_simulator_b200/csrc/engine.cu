@@ -158,7 +158,6 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
         prm.use_tensor_map = use_tensor_map_ ? 1 : 0;
         prm.init_basis = 0;
         prm.pad = 0;
-        if (const char* e = std::getenv("QSIM_DBG_FLAGS")) prm.pad = std::atoi(e);   // (development aid)
         prm.init_index = init_basis >= 0 ? (uint64_t)init_basis : 0;
         if (first && init_basis >= 0) {
             // Basis-state input: the driver's memset is the fastest zero fill (7.4 TB/s against 5.7 TB/s from the pass

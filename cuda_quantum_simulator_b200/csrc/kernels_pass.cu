@@ -514,6 +514,9 @@ cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t s
         const bool dual_ok = !params.init_basis && params.redirect != 2 && params.stages == 3 && smem_dual <= (size_t)kMaxDynamicSmem &&
                              params.n_tiles >= (uint64_t)num_sms && jit_dual_wanted(params.pd, host_ops);
         int dual = dual_ok ? 1 : 0;
+        // a pass that carries a fused exchange is bound by NVLink, not by the SM: one group (two tiles in flight), unless this
+        // pass has been measured without the exchange and the two-group build won
+        if (params.redirect && !(jit.tune && jit.tune->choice == 1)) dual = 0;
         // measured choice: once both builds of this pass are loaded, one ordinary launch of each is bracketed by events; the
         // times are collected at a later launch (cudaEventQuery: never blocks) and the faster build stays
         // (states of >= 26 qubits: a pass takes >= 0.4 ms there and one measurement is meaningful; below, the estimate decides)
