@@ -242,3 +242,29 @@ def test_two_warp_group_kernels_c3_shape():
         assert np.max(np.abs(sim.get_state_vector() - want)) < 1e-12
     finally:
         q.jit_set_dual("auto")
+
+
+@pytest.mark.parametrize("n,seed", [(14, 0), (16, 1), (17, 2), (20, 3), (21, 4)])
+def test_conditional_flips_carried_to_the_store(n, seed):
+    """CNOT / X-type flips whose controls sit in thread bits or outside the tile and whose target is a register bit are not
+    executed as register moves by the specialised kernels: the thread carries an XOR mask over its slot index to the sweep's
+    store, later 2x2 ops on the same bit take the X-conjugated matrix, diagonals the swapped factors, and ops that cannot live
+    with a pending flip (register-bit controls, fused diagonal runs, a lane op on a lane bit that conditioned it) materialise it
+    first.  CNOT-heavy random circuits over every gate kind, from a random state, both builds of the kernel."""
+    rng = np.random.default_rng(8100 + seed)
+    kinds = [0, 3, 3, 8, 9, 11, 11, 11, 11, 12, 13, 14, 15, 16, 5, 6]     # H, Rz..., many CNOTs, CZ, SWAP, CRY, CRZ, Toffoli
+    g = H.random_gates(n, 160, rng, kinds=kinds)
+    c = q.Circuit(n).extend(g)
+    prog = q.CompiledCircuit(c)
+    assert any("carried as a slot-index XOR" in prog.jit_source(i) for i in range(prog.n_passes)), "no deferred flip in this circuit"
+    st0 = H.random_state(n, rng)
+    want = H.oracle_run(n, g, st0)
+    got, _ = run_gpu(n, g, st0)
+    assert np.max(np.abs(got - want)) < 1e-12
+    if n >= 20:
+        q.jit_set_dual("always")
+        try:
+            got2, _ = run_gpu(n, g, st0)
+            assert np.max(np.abs(got2 - want)) < 1e-12
+        finally:
+            q.jit_set_dual("auto")
