@@ -201,7 +201,7 @@ def sharded_parity_check(exchange, rank, world, drivers=("native", "python")):
     import numpy as np
     import cuda_quantum_simulator_b200 as q
     import helpers as H
-    out = {"drivers": list(drivers), "max_abs_err": 0.0, "exchanges": 0, "fused": 0, "in_place": 0, "cases": [], "sampling_bit_identical": True,
+    out = {"drivers": list(drivers), "max_abs_err": 0.0, "exchanges": 0, "fused": 0, "in_place": 0, "split": 0, "cases": [], "sampling_bit_identical": True,
            "marginal_max_err": 0.0, "measure_ok": True, "tolerance": 1e-10}
     cases = (("createRandomCircuit(24,40,7) identity layout", 24, 40, 7, False),
              ("createRandomCircuit(22,300,11) free layout", 22, 300, 11, True))
@@ -210,12 +210,15 @@ def sharded_parity_check(exchange, rank, world, drivers=("native", "python")):
     # fourth (C++ driver): the fused exchange IN PLACE - what shards too large for a second buffer get (C4's 128 GiB) - forced
     variants = [(d, m) for d in drivers for m in ("fused", "separate")] + [(drivers[0], "fused+specialised")]
     if "native" in drivers:
-        variants.append(("native", "fused in place"))
+        variants.append(("native", "fused in place"))            # (split over the two passes around the exchange where it can be)
+        variants.append(("native", "fused in place, unsplit"))
     for driver, mode in variants:
         if mode == "separate":
             os.environ["QSIM_NO_FUSED_EXCHANGE"] = "1"
-        if mode == "fused in place":
+        if mode.startswith("fused in place"):
             os.environ["QSIM_FORCE_INPLACE_EXCHANGE"] = "1"
+        if mode.endswith("unsplit"):
+            os.environ["QSIM_NO_SPLIT_EXCHANGE"] = "1"
         if mode == "fused+specialised":
             q.jit_set_mode("always")
         try:
@@ -253,6 +256,7 @@ def sharded_parity_check(exchange, rank, world, drivers=("native", "python")):
                 out["exchanges"] += cp.n_swaps
                 out["fused"] += sim.fused_exchanges - f0
                 out["in_place"] += getattr(sim, "inplace_exchanges", 0)
+                out["split"] += getattr(sim, "split_exchanges", 0)
                 out["sampling_bit_identical"] &= samp_ok
                 out["marginal_max_err"] = max(out["marginal_max_err"], merr)
                 out["measure_ok"] &= bool(meas_ok)
@@ -261,6 +265,7 @@ def sharded_parity_check(exchange, rank, world, drivers=("native", "python")):
         finally:
             os.environ.pop("QSIM_NO_FUSED_EXCHANGE", None)
             os.environ.pop("QSIM_FORCE_INPLACE_EXCHANGE", None)
+            os.environ.pop("QSIM_NO_SPLIT_EXCHANGE", None)
             q.jit_set_mode("auto")
     out["passed"] = bool(out["max_abs_err"] < 1e-10 and out["sampling_bit_identical"] and out["marginal_max_err"] < 1e-12
                          and out["measure_ok"] and out["exchanges"] > 0 and ("native" not in drivers or out["in_place"] > 0))
@@ -478,10 +483,12 @@ def main():
             st()
             f_c = sim_.fused_exchanges
             i_c = getattr(sim_, "inplace_exchanges", 0)
+            p_c = getattr(sim_, "split_exchanges", 0)
             ms = timed(st, k) / k
             info = {"ms_per_step": ms, "passes_per_step": plan_.n_passes, "swaps_per_step": plan_.n_swaps,
                     "fused_into_a_pass_per_step": (sim_.fused_exchanges - f_c) / k,
                     "of_which_in_place_per_step": (getattr(sim_, "inplace_exchanges", 0) - i_c) / k,
+                    "of_which_split_over_two_passes_per_step": (getattr(sim_, "split_exchanges", 0) - p_c) / k,
                     "fused_first_step_from_zero_state": f_b - f_a}
             sim_.identity_layout_only(False)
             return info, plan_
@@ -508,17 +515,24 @@ def main():
                            "it rides on); overlap_eff = ideal / measured; fused_pass_plus_exchange_ms = measured minus the unfused "
                            "passes; pass_ms = the headline pass, link_ms = the separate-swap nvlink leg above", **f_info)
         if args.sharded_driver == "native" and runner.exchange == "p2p":
-            # the same steps with the fused exchange IN PLACE (what shards without room for a second buffer get: C4)
-            os.environ["QSIM_FORCE_INPLACE_EXCHANGE"] = "1"
-            try:
-                ip_info, _ip = forced_run(circuit, runner, k_f)
-                runner.synchronize()
-            finally:
-                os.environ.pop("QSIM_FORCE_INPLACE_EXCHANGE", None)
-            ip_step = (ip_info["ms_per_step"] - (fplan.n_passes - n_f) * pass_ms_1) / max(n_f, 1)
-            forced["in_place"] = dict(overlap_eff=ideal / ip_info["ms_per_step"], fused_pass_plus_exchange_ms=ip_step,
-                                      nvlink_gbs_per_direction_in_the_fused_step=half_bytes / ip_step / 1e6,
-                                      nvlink_frac_of_770=half_bytes / ip_step / 1e6 / 770.0, **ip_info)
+            # the same steps without a second buffer (what shards that fill the GPU get: C4): the exchange fused IN PLACE into
+            # the pass before it, and SPLIT over the pass before (scatters half) and the pass after (gathers half)
+            for leg, env in (("in_place", {"QSIM_FORCE_INPLACE_EXCHANGE": "1", "QSIM_NO_SPLIT_EXCHANGE": "1"}),
+                             ("split", {"QSIM_FORCE_INPLACE_EXCHANGE": "1"})):
+                os.environ.update(env)
+                try:
+                    ip_info, _ip = forced_run(circuit, runner, k_f)
+                    runner.synchronize()
+                finally:
+                    for k_ in env:
+                        os.environ.pop(k_, None)
+                ip_step = (ip_info["ms_per_step"] - (fplan.n_passes - n_f) * pass_ms_1) / max(n_f, 1)
+                forced[leg] = dict(overlap_eff=ideal / ip_info["ms_per_step"], fused_pass_plus_exchange_ms=ip_step,
+                                   nvlink_gbs_per_direction_in_the_fused_step=half_bytes / ip_step / 1e6,
+                                   nvlink_frac_of_770=half_bytes / ip_step / 1e6 / 770.0, **ip_info)
+            forced["split"]["what"] = ("both passes carry half of the exchange, so the step can beat `ideal` (which lets an exchange "
+                                       "overlap one pass only): ideal for the split is max(2 passes, link) = "
+                                       f"{max(2 * pass_ms_1, link_ms):.2f} ms")
 
     # ---- BASELINE config C4 for real: createRandomCircuit(36,20,42) over 8 GPUs, 128 GiB shards --------------------------
     c4 = None

@@ -121,6 +121,8 @@ def _declare(L: ctypes.CDLL) -> None:
         "qsim_program_last_tile_mask": (c_int, [P, P]),
         "qsim_shard_execute_exchange_inplace": (c_int, [P, P, P, c_int, c_int, P, P, c_uint64, c_uint64, P]),
         "qsim_shard_inplace_exchange_possible": (c_int, [P, P, c_int, P]),
+        "qsim_shard_execute_exchange_half": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, c_uint64, c_uint64, P]),
+        "qsim_shard_split_exchange_possible": (c_int, [P, P, P, c_int, P]),
         "qsim_shard_pack_half": (c_int, [P, c_int, c_int, c_int64, c_int64, P]),
         "qsim_shard_unpack_half": (c_int, [P, c_int, c_int, c_int64, c_int64, P]),
         "qsim_ipc_get_handle": (c_int, [P, P, POINTER(c_uint64)]),
@@ -151,6 +153,7 @@ def _declare(L: ctypes.CDLL) -> None:
         "qsim_sharded_relabel_identity": (c_int, [P]),
         "qsim_sharded_info": (c_int, [P, POINTER(c_int64)]),
         "qsim_sharded_inplace_exchanges": (c_int, [P, P]),
+        "qsim_sharded_split_exchanges": (c_int, [P, P]),
         "qsim_sharded_local": (c_void_p, [P]),
         "qsim_sharded_set_stream": (c_int, [P, P]),
         "qsim_sharded_synchronize": (c_int, [P]),

@@ -590,18 +590,23 @@ qsim_status_t qsim_shard_execute_exchange(qsim_sim_t* s, const qsim_program_t* p
     });
 }
 
-// Can the last pass of `p` carry the exchange of `local_qubit` IN PLACE?  (the launch-time conditions of launch_pass)
-static bool inplace_exchange_possible(const qsim_program_t* p, int local_qubit, int num_sms) {
-    if (p->dev.host.passes.empty()) return false;
-    const b200::PassDesc& pd = p->dev.host.passes.back();
-    for (int j = 0; j < pd.t; ++j)
-        if (pd.tile_bits[j] == local_qubit) return false;
+// Can this pass carry the exchange of local qubit v in place (w < 0), or one half of it split by index bit w?  (the launch-time
+// conditions of launch_pass)
+static bool pass_can_exchange_in_place(const b200::PassDesc& pd, int v, int w, int num_sms) {
+    uint64_t vw = 1ULL << v;
+    if (w >= 0) {
+        if (w == v || w >= pd.n) return false;
+        vw |= 1ULL << w;
+    }
+    if ((pd.tile_mask | pd.xdep) & vw) return false;   // a tile qubit, or deferred X gates pair tiles across it
     const uint64_t n_tiles = 1ULL << (pd.n - pd.t);
     const uint64_t grid = n_tiles < (uint64_t)num_sms ? n_tiles : (uint64_t)num_sms;
-    if (grid < 16) return false;
-    uint64_t xdep = 0;   // index XOR of the tile pairs of deferred X gates on outer bits
-    for (int sg = 0; sg < pd.n_segments; ++sg) xdep |= ((pd.xor_tau >> pd.seg[sg].src_shift) & pd.seg[sg].mask) << pd.seg[sg].dst_shift;
-    return !((xdep >> local_qubit) & 1ULL);
+    return w >= 0 ? (grid >= 32 && n_tiles >= 64) : grid >= 16;
+}
+
+static bool inplace_exchange_possible(const qsim_program_t* p, int local_qubit, int num_sms) {
+    if (p->dev.host.passes.empty()) return false;
+    return pass_can_exchange_in_place(p->dev.host.passes.back(), local_qubit, -1, num_sms);
 }
 
 qsim_status_t qsim_shard_inplace_exchange_possible(qsim_sim_t* s, const qsim_program_t* p, int local_qubit, int* possible_out) {
@@ -631,6 +636,57 @@ qsim_status_t qsim_shard_execute_exchange_inplace(qsim_sim_t* s, const qsim_prog
         rd.bit = local_qubit;
         rd.keep_value = (s->rank >> (global_qubit - nl)) & 1;
         rd.in_place = true;
+        rd.hs_local = static_cast<unsigned long long*>(hs_local);
+        rd.hs_peer = static_cast<unsigned long long*>(hs_peer);
+        rd.hs_base = hs_base;
+        rd.hs_timeout_ns = timeout_ns ? timeout_ns : 10000000000ULL;
+        rd.hs_error = hs_error_dev;
+        sv.engine().execute(p->dev, rd.keep, s->hi_bits(), -1, &rd);
+    });
+}
+
+qsim_status_t qsim_shard_split_exchange_possible(qsim_sim_t* s, const qsim_program_t* before, const qsim_program_t* after,
+                                                 int local_qubit, int* split_bit_out) {
+    return guarded([&] {
+        require(s != nullptr && before != nullptr && after != nullptr && split_bit_out != nullptr, "null argument");
+        *split_bit_out = -1;
+        if (before->dev.host.passes.empty() || after->dev.host.passes.empty()) return;
+        const int num_sms = s->sim->state().engine().numSMs();
+        const b200::PassDesc& pa = before->dev.host.passes.back();
+        const b200::PassDesc& pb = after->dev.host.passes.front();
+        for (int w = pa.n - 1; w >= 0; --w)
+            if (pass_can_exchange_in_place(pa, local_qubit, w, num_sms) && pass_can_exchange_in_place(pb, local_qubit, w, num_sms)) {
+                *split_bit_out = w;
+                return;
+            }
+    });
+}
+
+qsim_status_t qsim_shard_execute_exchange_half(qsim_sim_t* s, const qsim_program_t* p, void* peer_state, int global_qubit,
+                                               int local_qubit, int split_bit, int which, void* hs_local, void* hs_peer,
+                                               uint64_t hs_base, uint64_t timeout_ns, int* hs_error_dev) {
+    return guarded([&] {
+        require(s != nullptr && p != nullptr && peer_state != nullptr && hs_local != nullptr && hs_peer != nullptr &&
+                hs_error_dev != nullptr, "null argument");
+        require(which == 1 || which == 2, "which must be 1 (scatter: the program's last pass) or 2 (gather: its first pass)");
+        if (p->dev.host.n != s->n_total || p->n_global != s->n_global)
+            throw std::invalid_argument("Circuit qubit count doesn't match simulator");
+        const int nl = s->n_total - s->n_global;
+        require(global_qubit >= nl && global_qubit < s->n_total, "global_qubit is not a global qubit");
+        require(local_qubit >= 0 && local_qubit < nl, "local_qubit is not a local qubit");
+        require(!p->dev.host.passes.empty(), "the program has no pass");
+        StateVector& sv = s->sim->state();
+        const b200::PassDesc& pd = which == 1 ? p->dev.host.passes.back() : p->dev.host.passes.front();
+        require(pass_can_exchange_in_place(pd, local_qubit, split_bit, sv.engine().numSMs()),
+                "that pass cannot carry half of this exchange (qsim_shard_split_exchange_possible)");
+        b200::StoreRedirect rd;
+        rd.keep = sv.devicePtr();   // (a lazily reset shard is written out here)
+        rd.send = static_cast<cuDoubleComplex*>(peer_state);
+        rd.bit = local_qubit;
+        rd.keep_value = (s->rank >> (global_qubit - nl)) & 1;
+        rd.in_place = true;
+        rd.split = which;
+        rd.split_bit = split_bit;
         rd.hs_local = static_cast<unsigned long long*>(hs_local);
         rd.hs_peer = static_cast<unsigned long long*>(hs_peer);
         rd.hs_base = hs_base;
@@ -900,6 +956,13 @@ qsim_status_t qsim_sharded_inplace_exchanges(const qsim_sharded_t* h, int64_t* c
     return guarded([&] {
         require(h != nullptr && count_out != nullptr, "null argument");
         *count_out = h->sim->inPlaceExchanges();
+    });
+}
+
+qsim_status_t qsim_sharded_split_exchanges(const qsim_sharded_t* h, int64_t* count_out) {
+    return guarded([&] {
+        require(h != nullptr && count_out != nullptr, "null argument");
+        *count_out = h->sim->splitExchanges();
     });
 }
 

@@ -164,7 +164,7 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
             // kernel's own stores); the pass then only generates and processes the one tile that is not zero — and a
             // shard that holds no part of the basis state has nothing to process at all.
             first = false;
-            if (redirect && last) throw std::runtime_error("qsim_b200: basis-state input cannot be combined with a redirected store");
+            if (redirect && (last || redirect->split == 2)) throw std::runtime_error("qsim_b200: basis-state input cannot be combined with a redirected store");
             if (std::getenv("QSIM_INIT_FILL_IN_KERNEL")) prm.init_basis = 1;
             else {
                 CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(cuDoubleComplex) << pd.n, stream_));
@@ -173,19 +173,23 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
             }
         }
         first = false;
-        prm.redirect = (last && redirect) ? (redirect->in_place ? 2 : 1) : 0;
-        prm.hs_local = (last && redirect) ? redirect->hs_local : nullptr;
-        prm.hs_peer = (last && redirect) ? redirect->hs_peer : nullptr;
+        // the pass that carries the exchange: the program's last one, or (second half of a split exchange) its first
+        const bool carries = redirect && (redirect->split == 2 ? (&pd == &p.passes.front()) : last);
+        prm.redirect = carries ? (redirect->split == 2 ? 4 : (redirect->split == 1 ? 3 : (redirect->in_place ? 2 : 1))) : 0;
+        prm.split_bit = redirect ? redirect->split_bit : -1;
+        prm.mid_ctas = 0;
+        prm.hs_local = carries ? redirect->hs_local : nullptr;
+        prm.hs_peer = carries ? redirect->hs_peer : nullptr;
         prm.hs_base = redirect ? redirect->hs_base : 0;
         prm.hs_timeout_ns = redirect ? redirect->hs_timeout_ns : 0;
-        prm.hs_error = (last && redirect) ? redirect->hs_error : nullptr;
+        prm.hs_error = carries ? redirect->hs_error : nullptr;
         prm.timeline = d_timeline_ ? d_timeline_ + (size_t)((timeline_n_++) % 64) * 8 : nullptr;
         prm.progress = d_timeline_ ? d_timeline_ + 64 * 8 : nullptr;
         prm.redirect_bit = redirect ? redirect->bit : 0;
         prm.redirect_keep = redirect ? redirect->keep_value : 0;
         prm.send_ctas = 0;   // chosen by launch_pass
-        prm.dst_keep = (last && redirect) ? redirect->keep : nullptr;
-        prm.dst_send = (last && redirect) ? redirect->send : nullptr;
+        prm.dst_keep = carries ? redirect->keep : nullptr;
+        prm.dst_send = carries ? redirect->send : nullptr;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (timing_) {
             e0 = getEvent();
@@ -196,7 +200,7 @@ void Engine::launchAll(const Program& p, const DevOp* d_ops, const double* d_tab
         // NVTX range per pass (visible in Nsight Systems / ncu --nvtx; a no-op costing nanoseconds when no tool is attached)
         char label[96];
         std::snprintf(label, sizeof(label), "qsim pass %zu/%zu: %d ops, %d sweeps, t=%d%s", pass_i + 1, p.passes.size(), pd.n_ops,
-                      pd.n_sweeps, pd.t, prm.redirect ? (prm.redirect == 2 ? ", fused exchange in place" : ", fused exchange") : (prm.init_basis ? ", basis-state input" : ""));
+                      pd.n_sweeps, pd.t, prm.redirect ? (prm.redirect == 4 ? ", exchange gathered in place" : (prm.redirect >= 2 ? ", fused exchange in place" : ", fused exchange")) : (prm.init_basis ? ", basis-state input" : ""));
         struct NvtxScope { explicit NvtxScope(const char* l) { nvtxRangePushA(l); } ~NvtxScope() { nvtxRangePop(); } };
         if (p.jit.size() != 2 * p.passes.size()) {   // two builds per pass: one warp group / two (JitSlots)
             p.jit.assign(2 * p.passes.size(), nullptr);

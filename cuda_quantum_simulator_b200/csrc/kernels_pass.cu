@@ -495,15 +495,24 @@ cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t s
         if (const char* e = std::getenv("QSIM_SEND_CTAS")) send = std::atoi(e);
         if (send > 0 && send < (int)grid) params.send_ctas = send;
     }
-    if (params.redirect == 2) {
+    params.mid_ctas = 0;
+    if (params.redirect >= 2) {
         // the in-place exchange counts items per CTA across the two GPUs: it needs the sender / keeper split, the
         // handshake words, and a tile XOR (deferred X gates) that does not cross the exchanged bit
-        uint64_t xdep = 0;
-        for (int sg = 0; sg < params.pd.n_segments; ++sg)
-            xdep |= ((params.pd.xor_tau >> params.pd.seg[sg].src_shift) & params.pd.seg[sg].mask) << params.pd.seg[sg].dst_shift;
-        if (!params.send_ctas || ((xdep >> params.redirect_bit) & 1ULL) || !params.hs_local || !params.hs_peer || !params.hs_error ||
-            params.dst_keep != params.state)
+        if (!params.send_ctas || ((params.pd.xdep >> params.redirect_bit) & 1ULL) || !params.hs_local || !params.hs_peer ||
+            !params.hs_error || params.dst_keep != params.state)
             return cudaErrorInvalidValue;
+    }
+    if (params.redirect >= 3) {
+        // split exchange: three CTA classes - the exchanged quarter of the tiles (NVLink-bound), the staying half and the
+        // leaving quarter this pass does not move (both HBM-bound, 2 : 1 tiles)
+        const uint64_t vw = (1ULL << params.redirect_bit) | (1ULL << params.split_bit);
+        if (!params.use_tensor_map || grid < 32 || params.n_tiles < 64 || params.split_bit < 0 || params.split_bit >= params.pd.n ||
+            params.split_bit == params.redirect_bit || ((params.pd.xdep | params.pd.tile_mask) & vw))
+            return cudaErrorInvalidValue;
+        const int rest = (int)grid - params.send_ctas;
+        params.mid_ctas = rest * 2 / 3;
+        if (params.mid_ctas < 1 || params.send_ctas + params.mid_ctas >= (int)grid) return cudaErrorInvalidValue;
     }
     // A kernel specialised for this pass's structure (large states, pre-compiled circuits; see jit.hpp).  In the default
     // mode the compile runs on a background thread: until it is ready the interpreter kernel below does the pass.
@@ -511,7 +520,7 @@ cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t s
         // compute-heavy passes take the two-warp-group build (not for basis-state input or the in-place exchange, which
         // only the one-group skeleton implements); its factor tables of fused diagonal runs exist in four copies
         const size_t smem_dual = smem + 2 * (size_t)params.pd.n_phase * 13 * sizeof(double2);
-        const bool dual_ok = !params.init_basis && params.redirect != 2 && params.stages == 3 && smem_dual <= (size_t)kMaxDynamicSmem &&
+        const bool dual_ok = !params.init_basis && params.redirect < 2 && params.stages == 3 && smem_dual <= (size_t)kMaxDynamicSmem &&
                              params.n_tiles >= (uint64_t)num_sms && jit_dual_wanted(params.pd, host_ops);
         int dual = dual_ok ? 1 : 0;
         // a pass that carries a fused exchange is bound by NVLink, not by the SM: one group (two tiles in flight), unless this

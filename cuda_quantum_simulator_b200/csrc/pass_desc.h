@@ -211,6 +211,15 @@ struct PassParams {
     int32_t send_ctas;        // > 0: CTAs [0, send_ctas) take the tiles that leave, the others the tiles that stay
     void* dst_keep;
     void* dst_send;
+    // redirect == 3 / 4: the in-place exchange SPLIT over the two passes around it.  `split_bit` (another index bit that is a
+    // tile bit of neither pass) halves the leaving tiles: the pass before the exchange scatters the half with that bit clear
+    // (3: as redirect == 2, restricted to those tiles; the other leaving tiles are stored in place), the pass after it GATHERS
+    // the half with the bit set (4: those tiles are LOADED from the partner's live shard at index ^ (1 << redirect_bit) and
+    // stored in place, under the same handshake: my store over a tile waits until the partner has loaded it).  Three CTA
+    // classes: [0, send_ctas) the exchanged quarter, [send_ctas, send_ctas + mid_ctas) the staying half, the rest the
+    // leaving quarter this pass does not move.
+    int32_t split_bit;
+    int32_t mid_ctas;
     // redirect == 2: the fused exchange IN PLACE (no second buffer: dst_keep is `state` itself, dst_send the partner's live
     // buffer).  A leaving tile lands on the partner's own leaving tile of the same item number (both ranks run the same
     // grid over the same item order), so CTA c may store its item i only after the partner's CTA c has LOADED its item i:

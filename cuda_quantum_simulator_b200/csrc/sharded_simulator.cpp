@@ -503,6 +503,36 @@ bool ShardedSimulator::runThenSwap(void* program, int g, int l) {
     return true;
 }
 
+// A forced exchange between two programs, when there is no room for a second buffer: split over the last pass of the program
+// before it (scatters half of the leaving tiles into the partner's shard) and the first pass of the program after it (gathers
+// the other half from the partner's shard), so that each pass hides half of the NVLink time instead of one pass hiding what it
+// can of all of it.  Both under the kernels' own handshake; a barrier after each half.
+bool ShardedSimulator::runSwapSplit(void* before, void* after, int g, int l) {
+    if (exchange_ != Exchange::PeerMemory || !hs_ || std::getenv("QSIM_NO_FUSED_EXCHANGE") != nullptr ||
+        std::getenv("QSIM_NO_INPLACE_EXCHANGE") != nullptr || std::getenv("QSIM_NO_SPLIT_EXCHANGE") != nullptr)
+        return false;
+    if (bufs_[1] && std::getenv("QSIM_FORCE_INPLACE_EXCHANGE") == nullptr) return false;   // (room for the second buffer: that path)
+    qsim_sim_t* h = static_cast<qsim_sim_t*>(shard_);
+    qsim_program_t* pa = static_cast<qsim_program_t*>(before);
+    qsim_program_t* pb = static_cast<qsim_program_t*>(after);
+    int w = -1;
+    chk(qsim_shard_split_exchange_possible(h, pa, pb, l, &w));
+    if (w < 0) return false;   // (a property of the two compiled passes: the same answer on every rank)
+    const int b = g - nl_;
+    int* err = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(hs_) + kHsWords * 8);
+    ++hs_epoch_;
+    chk(qsim_shard_execute_exchange_half(h, pa, peer_ptr_[b][cur_], g, l, w, 1, hs_, peer_hs_[b], hs_epoch_ << 32, 0, err));
+    barrier();   // the partner's half-finished shard is complete before anything is gathered from it
+    ++hs_epoch_;
+    chk(qsim_shard_execute_exchange_half(h, pb, peer_ptr_[b][cur_], g, l, w, 2, hs_, peer_hs_[b], hs_epoch_ << 32, 0, err));
+    barrier();
+    hs_unchecked_ = true;
+    ++fused_exchanges_;
+    ++inplace_exchanges_;
+    ++split_exchanges_;
+    return true;
+}
+
 void ShardedSimulator::execute(const CompiledPlan& cp) {
     const bool same = (cp.perm_before == perm_) && cp.frame_before == frame_;
     if (!same && !(cp.from_pristine && pristine_ && cp.frame_before == frame_))
@@ -512,6 +542,13 @@ void ShardedSimulator::execute(const CompiledPlan& cp) {
     const auto& steps = cp.plan.steps;
     for (size_t i = 0; i < steps.size(); ++i) {
         if (!steps[i].is_swap) {
+            // program, swap, program (and no further swap riding on that second program): the exchange split over both
+            if (i + 2 < steps.size() && steps[i + 1].is_swap && !steps[i + 2].is_swap &&
+                !(i + 3 < steps.size() && steps[i + 3].is_swap) &&
+                runSwapSplit(cp.programs[i], cp.programs[i + 2], steps[i + 1].global_qubit, steps[i + 1].local_qubit)) {
+                i += 2;
+                continue;
+            }
             if (i + 1 < steps.size() && steps[i + 1].is_swap &&
                 runThenSwap(cp.programs[i], steps[i + 1].global_qubit, steps[i + 1].local_qubit)) {
                 ++i;   // the program's last pass carried the exchange

@@ -852,6 +852,11 @@ class NativeShardedSimulator:
         _lib.check(_lib.lib().qsim_sharded_inplace_exchanges(self._h, byref(c)))
         return int(c.value)
     @property
+    def split_exchanges(self) -> int:
+        c = c_int64()
+        _lib.check(_lib.lib().qsim_sharded_split_exchanges(self._h, byref(c)))
+        return int(c.value)
+    @property
     def exchange(self) -> str: return {0: "none", 1: "p2p", 2: "nccl"}[int(self._info()[4])]
     @property
     def perm(self) -> List[int]:

@@ -105,6 +105,8 @@ public:
     // of fusedExchanges(): those that ran IN PLACE (no second buffer; stores over the partner's live shard under the
     // cross-GPU handshake of qsim_shard_execute_exchange_inplace)
     int64_t inPlaceExchanges() const { return inplace_exchanges_; }
+    // of inPlaceExchanges(): those split over the pass before and the pass after the exchange (scatter half, gather half)
+    int64_t splitExchanges() const { return split_exchanges_; }
     const char* exchangeName() const;
     void setStream(cudaStream_t s);
     void synchronize();
@@ -132,13 +134,14 @@ private:
     unsigned long long* hs_ = nullptr;
     std::vector<unsigned long long*> peer_hs_;      // per rank bit
     uint64_t hs_epoch_ = 0;
-    int64_t inplace_exchanges_ = 0;
+    int64_t inplace_exchanges_ = 0, split_exchanges_ = 0;
     bool hs_unchecked_ = false;
     void checkExchanges(bool collective);           // throws if a handshake of an in-place exchange timed out
 
     void openPeers();
     void swapSeparate(int g, int l);
     bool runThenSwap(void* program, int g, int l);
+    bool runSwapSplit(void* before, void* after, int g, int l);
     void swapNccl(int peer, int g, int l);
     std::vector<double> allGather(double v);
 };

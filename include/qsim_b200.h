@@ -240,6 +240,18 @@ QSIM_API qsim_status_t qsim_shard_execute_exchange(qsim_sim_t* s, const qsim_pro
 QSIM_API qsim_status_t qsim_shard_execute_exchange_inplace(qsim_sim_t* s, const qsim_program_t* p, void* peer_state,
                                                            int global_qubit, int local_qubit, void* hs_local, void* hs_peer,
                                                            uint64_t hs_base, uint64_t timeout_ns, int* hs_error_dev);
+/* The in-place exchange SPLIT over the two passes around it, so that each pass hides half of the NVLink time: another index
+ * bit w that is a tile qubit of neither pass halves the leaving amplitudes.  which = 1: the LAST pass of `p` (the program before
+ * the exchange) scatters the half with bit w clear into the partner's shard, like qsim_shard_execute_exchange_inplace;
+ * synchronise ranks; which = 2: the FIRST pass of `p` (the program after the exchange) loads the half with bit w set from
+ * `peer_state` (at index ^ (1 << local_qubit)) instead of from its own shard and stores it in place, a store over a tile
+ * waiting until the partner has loaded that tile (same handshake words, a later epoch); synchronise ranks again.
+ * qsim_shard_split_exchange_possible: *split_bit_out = a usable w, or -1 (then use the unsplit call). */
+QSIM_API qsim_status_t qsim_shard_execute_exchange_half(qsim_sim_t* s, const qsim_program_t* p, void* peer_state, int global_qubit,
+                                                        int local_qubit, int split_bit, int which, void* hs_local, void* hs_peer,
+                                                        uint64_t hs_base, uint64_t timeout_ns, int* hs_error_dev);
+QSIM_API qsim_status_t qsim_shard_split_exchange_possible(qsim_sim_t* s, const qsim_program_t* before, const qsim_program_t* after,
+                                                          int local_qubit, int* split_bit_out);
 /* *possible_out = 1 when the last pass of `p` can carry the exchange of `local_qubit` in place: the qubit is not one of its
  * tile qubits, the shard has at least 16 tiles, and no deferred X gate pairs tiles across that qubit. */
 QSIM_API qsim_status_t qsim_shard_inplace_exchange_possible(qsim_sim_t* s, const qsim_program_t* p, int local_qubit,
@@ -324,6 +336,8 @@ QSIM_API qsim_status_t qsim_sharded_swap(qsim_sharded_t* h, int global_position,
 QSIM_API qsim_status_t qsim_sharded_info(const qsim_sharded_t* h, int64_t info[8]);
 /* Of info[2]: the exchanges that ran in place (no second buffer; qsim_shard_execute_exchange_inplace). */
 QSIM_API qsim_status_t qsim_sharded_inplace_exchanges(const qsim_sharded_t* h, int64_t* count_out);
+/* Of those: the exchanges split over the pass before and the pass after (qsim_shard_execute_exchange_half). */
+QSIM_API qsim_status_t qsim_sharded_split_exchanges(const qsim_sharded_t* h, int64_t* count_out);
 QSIM_API qsim_sim_t* qsim_sharded_local(qsim_sharded_t* h);   /* the shard as a qsim_sim_t (timing, launch counters); borrowed */
 QSIM_API qsim_status_t qsim_sharded_set_stream(qsim_sharded_t* h, void* cuda_stream);
 QSIM_API qsim_status_t qsim_sharded_synchronize(qsim_sharded_t* h);

@@ -176,6 +176,82 @@ def test_inplace_fused_exchange_on_one_gpu(nl, g_local, tail_x):
         L.qsim_sim_destroy(h)
 
 
+@pytest.mark.parametrize("nl,g_local,tail_x", [(18, 17, False), (19, 16, False), (18, 14, True), (20, 19, False)])
+def test_split_exchange_on_one_gpu(nl, g_local, tail_x):
+    """qsim_shard_execute_exchange_half with both 'ranks' of a 2-shard state on this one GPU (kernels concurrent on two streams):
+    the LAST pass of the program before the exchange scatters the half of the leaving tiles whose split bit is clear into the
+    other rank's shard, the FIRST pass of the program after it gathers the other half from there - no second buffer, no separate
+    swap.  Oracle: gates A on the full state, the qubit swap as an index permutation, gates B."""
+    from ctypes import byref, c_int, c_uint64, c_void_p
+
+    import numpy as np
+    import torch
+
+    from cuda_quantum_simulator_b200 import _lib
+
+    L = _lib.lib()
+    n = nl + 1
+    rng = np.random.default_rng(2900 + nl + g_local)
+    # few distinct targets per program, so that enough qubits stay outside both tiles to split on
+    pool = [q for q in range(nl) if q != g_local]
+    targets = [int(x) for x in rng.choice(pool[:12], 7, replace=False)]
+
+    def program_gates(k):
+        lst = []
+        for _ in range(k):
+            kind = str(rng.choice(["H", "T", "CNOT", "Rz", "X"]))
+            a, b = (int(x) for x in rng.choice(targets, 2, replace=False))
+            lst.append((kind, a, b) if kind == "CNOT" else (kind, a, float(rng.uniform(-3, 3))) if kind == "Rz" else (kind, a))
+        return lst
+    la, lb = program_gates(24), program_gates(24)
+    if tail_x:
+        la.append(("X", targets[0]))
+    ga, gb = H.gates(la), H.gates(lb)
+    full = H.random_state(n, rng)
+    idx = np.arange(1 << n, dtype=np.uint64)
+    bg, bl = (idx >> np.uint64(nl)) & np.uint64(1), (idx >> np.uint64(g_local)) & np.uint64(1)
+    src = ((idx & ~((np.uint64(1) << np.uint64(nl)) | (np.uint64(1) << np.uint64(g_local)))) | (bl << np.uint64(nl)) | (bg << np.uint64(g_local))).astype(np.int64)
+    want = H.oracle_run(n, gb, H.oracle_run(n, ga, full)[src])
+
+    bufs = [torch.empty(1 << nl, dtype=torch.complex128, device="cuda") for _ in range(2)]
+    hs = [torch.zeros(1024 + 8, dtype=torch.int64, device="cuda") for _ in range(2)]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    sims = []
+    for r in range(2):
+        h = c_void_p()
+        _lib.check(L.qsim_shard_create(n, 1, r, c_void_p(bufs[r].data_ptr()), byref(h)))
+        shard = np.ascontiguousarray(full[r << nl:(r + 1) << nl])
+        _lib.check(L.qsim_sim_set_state(h, shard.ctypes.data_as(c_void_p)))
+        _lib.check(L.qsim_sim_set_stream(h, c_void_p(streams[r].cuda_stream)))
+        sims.append(h)
+    torch.cuda.synchronize()
+    pa, pb = c_void_p(), c_void_p()
+    _lib.check(L.qsim_program_compile_ex(n, 1, _lib.gates_ptr(ga), len(ga), c_uint64(0), byref(pa)))
+    _lib.check(L.qsim_program_compile_ex(n, 1, _lib.gates_ptr(gb), len(gb), c_uint64(0), byref(pb)))
+    w = c_int(-2)
+    _lib.check(L.qsim_shard_split_exchange_possible(sims[0], pa, pb, g_local, byref(w)))
+    assert w.value >= 0 and w.value != g_local, "no split bit for this case"
+
+    def half(r, prog, which, epoch):
+        return L.qsim_shard_execute_exchange_half(sims[r], prog, c_void_p(bufs[1 - r].data_ptr()), nl, g_local, w.value, which,
+                                                  c_void_p(hs[r].data_ptr()), c_void_p(hs[1 - r].data_ptr()), c_uint64(epoch << 32),
+                                                  c_uint64(3_000_000_000), c_void_p(hs[r].data_ptr() + 1024 * 8))
+    for which, prog, epoch in ((1, pa, 1), (2, pb, 2)):
+        for r in range(2):
+            _lib.check(half(r, prog, which, epoch))
+        torch.cuda.synchronize()          # (the ranks' barrier between the two halves)
+        assert int(hs[0][1024].item()) == 0 and int(hs[1][1024].item()) == 0, "handshake failed"
+    got = np.concatenate([bufs[r].cpu().numpy() for r in range(2)])
+    assert np.max(np.abs(got - want)) < 1e-12
+    # a split bit that is a tile qubit / the exchanged qubit itself is refused
+    assert L.qsim_shard_execute_exchange_half(sims[0], pa, c_void_p(bufs[1].data_ptr()), nl, g_local, g_local, 1, c_void_p(hs[0].data_ptr()),
+                                              c_void_p(hs[1].data_ptr()), c_uint64(9 << 32), c_uint64(0), c_void_p(hs[0].data_ptr() + 8192)) != 0
+    for p_ in (pa, pb):
+        L.qsim_program_destroy(p_)
+    for h in sims:
+        L.qsim_sim_destroy(h)
+
+
 def test_staged_shard_sampling_on_one_gpu():
     """qsim_shard_cdf_prepare / _classify / qsim_shard_sample with both shards of a 2-shard state on this GPU: the chained
     result must equal the host's sequential CDF over the whole state, bit for bit."""

@@ -63,10 +63,10 @@ def variant(sim, env):
         st()
         q.jit_wait()
         st()
-        f0, i0, s0 = sim.fused_exchanges, sim.inplace_exchanges, sim.separate_exchanges
+        f0, i0, s0, p0 = sim.fused_exchanges, sim.inplace_exchanges, sim.separate_exchanges, sim.split_exchanges
         ms = timed(st, steps)
         info = {"ms_per_step": ms, "passes": plan.n_passes, "swaps": plan.n_swaps, "fused_per_step": (sim.fused_exchanges - f0) / steps,
-                "in_place_per_step": (sim.inplace_exchanges - i0) / steps, "separate_per_step": (sim.separate_exchanges - s0) / steps,
+                "in_place_per_step": (sim.inplace_exchanges - i0) / steps, "split_per_step": (sim.split_exchanges - p0) / steps, "separate_per_step": (sim.separate_exchanges - s0) / steps,
                 "total_probability": sim.get_total_probability(),
                 "marginal_top_and_low": [float(x) for x in sim.marginal([n - 1, 0, nl - 1, 5])]}
         return info
@@ -77,13 +77,15 @@ def variant(sim, env):
 
 sim = NativeShardedSimulator(n)
 out = {"qubits": n, "local_qubits": nl, "world": world, "second_buffer": sim.has_second_buffer, "exchange": sim.exchange}
-out["in_place"] = variant(sim, {"QSIM_FORCE_INPLACE_EXCHANGE": "1"})
+out["split"] = variant(sim, {"QSIM_FORCE_INPLACE_EXCHANGE": "1"})     # scatter half in the pass before, gather half in the pass after
+out["in_place"] = variant(sim, {"QSIM_FORCE_INPLACE_EXCHANGE": "1", "QSIM_NO_SPLIT_EXCHANGE": "1"})
 out["separate"] = variant(sim, {"QSIM_NO_INPLACE_EXCHANGE": "1", "QSIM_NO_FUSED_EXCHANGE": "1"})
 # both variants ran the same number of steps from the same start: same state, so the same marginals (1e-12)
-a, b = np.array(out["in_place"]["marginal_top_and_low"]), np.array(out["separate"]["marginal_top_and_low"])
-out["marginals_agree"] = bool(np.max(np.abs(a - b)) < 1e-12)
+a, b, c = (np.array(out[k]["marginal_top_and_low"]) for k in ("in_place", "separate", "split"))
+out["marginals_agree"] = bool(np.max(np.abs(a - b)) < 1e-12 and np.max(np.abs(c - b)) < 1e-12)
 out["half_shard_bytes"] = 16 * (1 << (nl - 1))
 out["in_place"]["speedup_vs_separate"] = out["separate"]["ms_per_step"] / out["in_place"]["ms_per_step"]
+out["split"]["speedup_vs_separate"] = out["separate"]["ms_per_step"] / out["split"]["ms_per_step"]
 sim.close()
 if rank == 0:
     print(json.dumps(out), flush=True)
