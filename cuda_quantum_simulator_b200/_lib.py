@@ -74,6 +74,7 @@ def _declare(L: ctypes.CDLL) -> None:
         "qsim_circuit_depth": (c_int, [c_int, P, c_int64, POINTER(c_int64)]),
         "qsim_program_compile": (c_int, [c_int, c_int, P, c_int64, PP]),
         "qsim_program_compile_ex": (c_int, [c_int, c_int, P, c_int64, c_uint64, PP]),
+        "qsim_program_compile_ex2": (c_int, [c_int, c_int, P, c_int64, c_uint64, c_int, PP]),
         "qsim_program_destroy": (None, [P]),
         "qsim_program_info": (c_int, [P, POINTER(c_int64)]),
         "qsim_program_describe": (c_size_t, [P, c_char_p, c_size_t]),

@@ -174,6 +174,11 @@ qsim_status_t qsim_program_compile(int n, int n_global, const qsim_gate_t* gates
 
 qsim_status_t qsim_program_compile_ex(int n, int n_global, const qsim_gate_t* gates, int64_t ng, uint64_t initial_xor,
                                       qsim_program_t** out) {
+    return qsim_program_compile_ex2(n, n_global, gates, ng, initial_xor, -1, out);
+}
+
+qsim_status_t qsim_program_compile_ex2(int n, int n_global, const qsim_gate_t* gates, int64_t ng, uint64_t initial_xor,
+                                       int isolate_qubit, qsim_program_t** out) {
     return guarded([&] {
         require(out != nullptr, "null output");
         require(n_global >= 0 && n_global < n, "n_global out of range");
@@ -183,6 +188,7 @@ qsim_status_t qsim_program_compile_ex(int n, int n_global, const qsim_gate_t* ga
         b200::CompileOptions opt = b200::default_options();
         opt.n_global = n_global;
         opt.initial_xor = initial_xor;
+        opt.isolate_bit = isolate_qubit;
         std::string err;
         if (!b200::compile(n, gates, ng, opt, p->dev.host, &err)) throw std::runtime_error(err);
         // the device copy is made now when a GPU is there, else at the first execute (compiling, describing and
@@ -604,6 +610,17 @@ static bool pass_can_exchange_in_place(const b200::PassDesc& pd, int v, int w, i
     return w >= 0 ? (grid >= 32 && n_tiles >= 64) : grid >= 16;
 }
 
+// Can this pass GATHER half of the exchange of local qubit v (split by index bit w)?  v must be its highest tile qubit, moved
+// by TMA instructions of its own (qsim_program_compile_ex2's isolate hint); w a qubit outside the tile.
+static bool pass_can_gather_half(const b200::PassDesc& pd, int v, int w, int num_sms) {
+    if (w < 0 || w >= pd.n || w == v) return false;
+    if (pd.t < 2 || pd.tma_instr_bits < 1 || (int)pd.tile_bits[pd.t - 1] != v) return false;
+    if ((pd.tile_mask | pd.xdep) & (1ULL << w)) return false;
+    const uint64_t n_tiles = 1ULL << (pd.n - pd.t);
+    const uint64_t grid = n_tiles < (uint64_t)num_sms ? n_tiles : (uint64_t)num_sms;
+    return grid >= 32 && n_tiles >= 64;
+}
+
 static bool inplace_exchange_possible(const qsim_program_t* p, int local_qubit, int num_sms) {
     if (p->dev.host.passes.empty()) return false;
     return pass_can_exchange_in_place(p->dev.host.passes.back(), local_qubit, -1, num_sms);
@@ -655,7 +672,7 @@ qsim_status_t qsim_shard_split_exchange_possible(qsim_sim_t* s, const qsim_progr
         const b200::PassDesc& pa = before->dev.host.passes.back();
         const b200::PassDesc& pb = after->dev.host.passes.front();
         for (int w = pa.n - 1; w >= 0; --w)
-            if (pass_can_exchange_in_place(pa, local_qubit, w, num_sms) && pass_can_exchange_in_place(pb, local_qubit, w, num_sms)) {
+            if (pass_can_exchange_in_place(pa, local_qubit, w, num_sms) && pass_can_gather_half(pb, local_qubit, w, num_sms)) {
                 *split_bit_out = w;
                 return;
             }
@@ -677,7 +694,8 @@ qsim_status_t qsim_shard_execute_exchange_half(qsim_sim_t* s, const qsim_program
         require(!p->dev.host.passes.empty(), "the program has no pass");
         StateVector& sv = s->sim->state();
         const b200::PassDesc& pd = which == 1 ? p->dev.host.passes.back() : p->dev.host.passes.front();
-        require(pass_can_exchange_in_place(pd, local_qubit, split_bit, sv.engine().numSMs()),
+        require(which == 1 ? pass_can_exchange_in_place(pd, local_qubit, split_bit, sv.engine().numSMs())
+                           : pass_can_gather_half(pd, local_qubit, split_bit, sv.engine().numSMs()),
                 "that pass cannot carry half of this exchange (qsim_shard_split_exchange_possible)");
         b200::StoreRedirect rd;
         rd.keep = sv.devicePtr();   // (a lazily reset shard is written out here)

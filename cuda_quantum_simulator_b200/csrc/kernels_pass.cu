@@ -476,7 +476,7 @@ cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t s
     tmap_send = tmap;
     if (params.redirect) {
         if (!params.dst_keep || !params.dst_send || params.init_basis) return cudaErrorInvalidValue;
-        for (int j = 0; j < params.pd.t; ++j)
+        for (int j = 0; j < params.pd.t && params.redirect != 4; ++j)   // (4: the gathering pass has it as its highest tile qubit)
             if (params.pd.tile_bits[j] == params.redirect_bit) return cudaErrorInvalidValue;
         if (params.use_tensor_map && (!encode_tensor_map(params, params.dst_keep, &tmap_keep) ||
                                       !encode_tensor_map(params, params.dst_send, &tmap_send)))
@@ -504,15 +504,28 @@ cudaError_t launch_pass(const PassParams& params_in, int num_sms, cudaStream_t s
             return cudaErrorInvalidValue;
     }
     if (params.redirect >= 3) {
-        // split exchange: three CTA classes - the exchanged quarter of the tiles (NVLink-bound), the staying half and the
-        // leaving quarter this pass does not move (both HBM-bound, 2 : 1 tiles)
-        const uint64_t vw = (1ULL << params.redirect_bit) | (1ULL << params.split_bit);
         if (!params.use_tensor_map || grid < 32 || params.n_tiles < 64 || params.split_bit < 0 || params.split_bit >= params.pd.n ||
-            params.split_bit == params.redirect_bit || ((params.pd.xdep | params.pd.tile_mask) & vw))
+            params.split_bit == params.redirect_bit)
             return cudaErrorInvalidValue;
-        const int rest = (int)grid - params.send_ctas;
-        params.mid_ctas = rest * 2 / 3;
-        if (params.mid_ctas < 1 || params.send_ctas + params.mid_ctas >= (int)grid) return cudaErrorInvalidValue;
+        const uint64_t vbit = 1ULL << params.redirect_bit, wbit = 1ULL << params.split_bit;
+        if (params.redirect == 3) {
+            // first half of a split exchange: three CTA classes - the exchanged quarter of the tiles (NVLink-bound), the staying
+            // half and the leaving quarter this pass does not move (both HBM-bound, 2 : 1 tiles)
+            if ((params.pd.xdep | params.pd.tile_mask) & (vbit | wbit)) return cudaErrorInvalidValue;
+            const int rest = (int)grid - params.send_ctas;
+            params.mid_ctas = rest * 2 / 3;
+            if (params.mid_ctas < 1 || params.send_ctas + params.mid_ctas >= (int)grid) return cudaErrorInvalidValue;
+        } else {
+            // second half: the exchanged qubit is this pass's highest tile qubit, moved by TMA instructions of its own; the tiles
+            // with the split bit set load half of their boxes over NVLink (so twice the CTAs of a full-tile sender class)
+            if (params.pd.tma_instr_bits < 1 || params.pd.tile_bits[params.pd.t - 1] != params.redirect_bit ||
+                ((params.pd.xdep | params.pd.tile_mask) & wbit))
+                return cudaErrorInvalidValue;
+            int gath = (int)grid * 3 / 5;
+            if (const char* e = std::getenv("QSIM_GATHER_CTAS")) gath = std::atoi(e);
+            if (gath < 1 || gath >= (int)grid) return cudaErrorInvalidValue;
+            params.send_ctas = gath;
+        }
     }
     // A kernel specialised for this pass's structure (large states, pre-compiled circuits; see jit.hpp).  In the default
     // mode the compile runs on a background thread: until it is ready the interpreter kernel below does the pass.

@@ -162,7 +162,7 @@ bool tile_feasible(uint64_t need, int n_local, int t, int lmin) {
     return lmin + high <= t;
 }
 
-void choose_tile_bits(uint64_t need, int n_local, int t, int lmin, PassDesc& pd) {
+void choose_tile_bits(uint64_t need, int n_local, int t, int lmin, PassDesc& pd, int isolate_bit = -1) {
     // Largest L with L + |need ∩ [L, n)| <= t (f is non-decreasing in L).
     int L = std::min(t, n_local);
     if (t < n_local) {
@@ -195,7 +195,16 @@ void choose_tile_bits(uint64_t need, int n_local, int t, int lmin, PassDesc& pd)
             chunks.emplace_back(bits[i], (int)(j - i + 1));
             i = j + 1;
         }
-        const int nd = std::min<int>(5, (int)chunks.size());
+        // the highest tile bit on request in a chunk of its own that separate instructions enumerate (CompileOptions::isolate_bit)
+        bool isolated = false;
+        if (isolate_bit >= 0 && !bits.empty() && bits.back() == isolate_bit && chunks.size() >= 1 && bits.size() >= 2) {
+            if (chunks.back().second > 1) {
+                --chunks.back().second;
+                chunks.emplace_back(isolate_bit, 1);
+            }
+            isolated = chunks.size() >= 2;
+        }
+        const int nd = std::min<int>(5, (int)chunks.size() - (isolated ? 1 : 0));
         int instr_bits = 0;
         for (size_t c = nd; c < chunks.size(); ++c) instr_bits += chunks[c].second;
         pd.tma_instr_bits = (uint8_t)instr_bits;
@@ -469,7 +478,7 @@ bool build_pass(PassPlan& plan, bool last_pass, const CompileOptions& opt, int n
     auto fail = [&](const std::string& s) { return set_error(error, s); };
     PassDesc pd{};
     pd.n = nl;
-    choose_tile_bits(plan.need, nl, t, lmin, pd);
+    choose_tile_bits(plan.need, nl, t, lmin, pd, opt.isolate_bit);
     int local_of[64];
     for (int q = 0; q < 64; ++q) local_of[q] = -1;
     for (int i = 0; i < pd.t; ++i) local_of[pd.tile_bits[i]] = i;

@@ -44,6 +44,9 @@ struct CompileOptions {
     bool fuse_diagonals = true;  // runs of >= 3 diagonal gates become one OP_PHASE
     bool defer_x = true;         // carry uncontrolled X gates as an index-XOR frame, folded into the last pass's addressing
     uint64_t initial_xor = 0;    // X frame inherited from earlier segments (sharded driver: pending flips of global qubits)
+    int isolate_bit = -1;        // (sharded driver) a pass whose HIGHEST tile qubit this is moves it with TMA instructions of its
+                                 // own, so that the half of every tile with that bit set / clear can come from another GPU
+                                 // (second half of a split qubit exchange, PassParams::redirect == 4)
 };
 
 struct JitKernel;                // a run-time specialised pass kernel (jit.hpp)

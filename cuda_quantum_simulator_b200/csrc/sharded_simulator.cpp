@@ -385,10 +385,12 @@ std::shared_ptr<ShardedSimulator::CompiledPlan> ShardedSimulator::compile(const 
     cp->perm_before = start;
     cp->frame_before = frame_;
     uint64_t frame = frame_;
+    int after_swap_of = -1;   // the local position of the exchange right before this segment (the gathering half of a split exchange)
     for (const auto& st : cp->plan.steps) {
         if (!st.is_swap) {
             qsim_program_t* prog = nullptr;
-            chk(qsim_program_compile_ex(n_, ng_, st.gates.data(), (int64_t)st.gates.size(), frame, &prog));
+            chk(qsim_program_compile_ex2(n_, ng_, st.gates.data(), (int64_t)st.gates.size(), frame, after_swap_of, &prog));
+            after_swap_of = -1;
             cp->programs.push_back(prog);
             int64_t info[8];
             chk(qsim_program_info(prog, info));
@@ -397,6 +399,7 @@ std::shared_ptr<ShardedSimulator::CompiledPlan> ShardedSimulator::compile(const 
             frame = (uint64_t)info[6] << nl_;          // the local part was applied by the program itself
         } else {
             cp->programs.push_back(nullptr);
+            after_swap_of = st.local_qubit;
             const int g = st.global_qubit, l = st.local_qubit;   // a pending X travels with its qubit
             const uint64_t bg = (frame >> g) & 1, bl = (frame >> l) & 1;
             frame = (frame & ~((1ULL << g) | (1ULL << l))) | (bl << g) | (bg << l);

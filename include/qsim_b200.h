@@ -104,6 +104,11 @@ QSIM_API qsim_status_t qsim_program_compile(int num_qubits, int n_global, const 
  * pending" (the sharded driver threads the frame of the global qubits from one segment to the next). */
 QSIM_API qsim_status_t qsim_program_compile_ex(int num_qubits, int n_global, const qsim_gate_t* gates,
                                                int64_t n_gates, uint64_t initial_xor, qsim_program_t** out);
+/* The same with one more hint for a sharded driver: a pass whose HIGHEST tile qubit is local qubit `isolate_qubit` moves that
+ * qubit's two halves of every tile with TMA instructions of their own, so that one half can be loaded from another GPU (the
+ * program after a qubit exchange, second half of a split exchange: qsim_shard_execute_exchange_half).  -1: no hint. */
+QSIM_API qsim_status_t qsim_program_compile_ex2(int n, int n_global, const qsim_gate_t* gates, int64_t n_gates, uint64_t initial_xor,
+                                                int isolate_qubit, qsim_program_t** out);
 QSIM_API void qsim_program_destroy(qsim_program_t* p);
 /* info[0]=passes, [1]=ops after merging, [2]=gates, [3]=sweeps (total), [4]=tile bits of pass 0,
  * [5]=local qubits, [6]=X frame left on the global qubits (bit q - n_local): the caller owns it */

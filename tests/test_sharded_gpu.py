@@ -180,8 +180,9 @@ def test_inplace_fused_exchange_on_one_gpu(nl, g_local, tail_x):
 def test_split_exchange_on_one_gpu(nl, g_local, tail_x):
     """qsim_shard_execute_exchange_half with both 'ranks' of a 2-shard state on this one GPU (kernels concurrent on two streams):
     the LAST pass of the program before the exchange scatters the half of the leaving tiles whose split bit is clear into the
-    other rank's shard, the FIRST pass of the program after it gathers the other half from there - no second buffer, no separate
-    swap.  Oracle: gates A on the full state, the qubit swap as an index permutation, gates B."""
+    other rank's shard, the FIRST pass of the program after it - which has the exchanged qubit as its highest tile qubit - loads
+    the leaving half of every tile whose split bit is set from there (TMA boxes from two GPUs into one tile) - no second buffer,
+    no separate swap.  Oracle: gates A on the full state, the qubit swap as an index permutation, gates B."""
     from ctypes import byref, c_int, c_uint64, c_void_p
 
     import numpy as np
@@ -203,9 +204,13 @@ def test_split_exchange_on_one_gpu(nl, g_local, tail_x):
             a, b = (int(x) for x in rng.choice(targets, 2, replace=False))
             lst.append((kind, a, b) if kind == "CNOT" else (kind, a, float(rng.uniform(-3, 3))) if kind == "Rz" else (kind, a))
         return lst
-    la, lb = program_gates(24), program_gates(24)
+    la, lb = program_gates(24), program_gates(16)
+    # the program after the exchange works on the exchanged qubit (that is why it was exchanged): it becomes the highest tile
+    # qubit of its first pass, which the compile hint makes TMA instructions of its own enumerate
+    lb = [("H", g_local)] + lb[:8] + [("CNOT", targets[1], g_local), ("Rz", g_local, 0.37)] + lb[8:] + [("H", g_local)]
     if tail_x:
         la.append(("X", targets[0]))
+        lb.append(("X", targets[2]))
     ga, gb = H.gates(la), H.gates(lb)
     full = H.random_state(n, rng)
     idx = np.arange(1 << n, dtype=np.uint64)
@@ -227,7 +232,7 @@ def test_split_exchange_on_one_gpu(nl, g_local, tail_x):
     torch.cuda.synchronize()
     pa, pb = c_void_p(), c_void_p()
     _lib.check(L.qsim_program_compile_ex(n, 1, _lib.gates_ptr(ga), len(ga), c_uint64(0), byref(pa)))
-    _lib.check(L.qsim_program_compile_ex(n, 1, _lib.gates_ptr(gb), len(gb), c_uint64(0), byref(pb)))
+    _lib.check(L.qsim_program_compile_ex2(n, 1, _lib.gates_ptr(gb), len(gb), c_uint64(0), g_local, byref(pb)))
     w = c_int(-2)
     _lib.check(L.qsim_shard_split_exchange_possible(sims[0], pa, pb, g_local, byref(w)))
     assert w.value >= 0 and w.value != g_local, "no split bit for this case"
