@@ -71,7 +71,7 @@ if NATIVE:
             assert res == (0 if r < p0 else 1) and np.max(np.abs(sim.get_state_vector() - want_c)) < 1e-10
         if rank == 0:
             print(f"native n={n} seed={seed} exchange={sim.exchange} swaps/run={plans[1].n_swaps} fused={sim.fused_exchanges} "
-                  f"separate={sim.separate_exchanges} in-place={sim.inplace_exchanges} max|err|={err:.2e}", flush=True)
+                  f"separate={sim.separate_exchanges} in-place={sim.inplace_exchanges} split={sim.split_exchanges} max|err|={err:.2e}", flush=True)
         assert not (INPLACE and n >= 22) or sim.inplace_exchanges > 0
         sim.close()
     assert worst < 1e-10, worst

@@ -55,6 +55,7 @@ while True:
             sim.execute(cp)
         fused += sim.fused_exchanges
         inplace = globals().get("inplace", 0) + sim.inplace_exchanges
+        split = globals().get("split", 0) + sim.split_exchanges
     else:
         sim = ShardedSimulator(n)
         sim._pristine = pristine
@@ -81,5 +82,5 @@ while True:
     cases += 1
 if rank == 0:
     print(f"sharded stress ok on {world} GPUs ({'C++ driver' if NATIVE else 'Python driver'}): {cases} cases, {swaps} exchanges ({fused} fused into a pass, "
-          f"{globals().get('inplace', 0)} of them in place), worst max|err| {worst:.2e}")
+          f"{globals().get('inplace', 0)} of them in place, {globals().get('split', 0)} split over two passes), worst max|err| {worst:.2e}")
 dist.destroy_process_group()
