@@ -99,3 +99,26 @@ def test_trailing_flips_fold_into_the_store(seed):
         want = H.oracle_run(n, gr, st0)
         got, _ = H.emu_run(n, gr, st0, lmin=3, tmax=tmax)
         assert np.max(np.abs(got - want)) < 1e-12, ("leading", n, tmax, seed)
+
+
+def test_isolate_hint_makes_the_top_tile_qubit_a_tma_instruction_bit():
+    """qsim_program_compile_ex2's hint (the program after a qubit exchange, second half of a split exchange): a pass whose highest
+    tile qubit is the hinted one moves it with TMA instructions of its own - same tile, same ops, one more instruction bit."""
+    import ctypes
+    from ctypes import byref, c_uint64, c_void_p
+
+    from cuda_quantum_simulator_b200 import _lib
+    L = _lib.lib()
+    n, v = 19, 17
+    g = H.gates([("H", v), ("H", 3), ("CNOT", 5, v), ("Rz", v, 0.3), ("H", 7)])
+    lines = {}
+    for iso in (-1, v, 9):
+        p = c_void_p()
+        _lib.check(L.qsim_program_compile_ex2(n, 1, _lib.gates_ptr(g), len(g), c_uint64(0), iso, byref(p)))
+        buf = ctypes.create_string_buffer(8000)
+        L.qsim_program_describe(p, buf, 8000)
+        lines[iso] = [l for l in buf.value.decode().split("\n") if l.startswith("  pass")]
+        L.qsim_program_destroy(p)
+    assert len(lines[-1]) == 1 and "tile_bits=[0,1,2,3,4,5,6,7,8,9,10,17]" in lines[-1][0] and "tma_instrs" not in lines[-1][0]
+    assert "tma_instrs=2" in lines[v][0] and lines[v][0].replace(" tma_instrs=2", "") == lines[-1][0]
+    assert lines[9] == lines[-1]          # a hint that is not the highest tile qubit changes nothing

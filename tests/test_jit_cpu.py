@@ -90,3 +90,18 @@ def test_two_warp_group_build_compiles(tmp_path):
         assert "QSIM_DUAL_GROUPS" not in prog.jit_source(0)
     finally:
         q.jit_set_dual("auto")
+
+
+def test_conditional_flips_are_carried_to_the_store_in_generated_code():
+    """A CNOT-heavy circuit: controlled flips on register bits become `fx_ ^= ...` (an XOR mask over the thread's slot index that
+    the sweep's store addressing applies) instead of predicated register moves; later ops on the flipped bit select the
+    X-conjugated matrix; the generated kernels still compile for sm_100a."""
+    rng = np.random.default_rng(8103)
+    g = H.random_gates(20, 160, rng, kinds=[0, 3, 3, 8, 9, 11, 11, 11, 11, 12, 13, 14, 15, 16, 5, 6])
+    prog = q.CompiledCircuit(q.Circuit(20).extend(g))
+    srcs = [prog.jit_source(i) for i in range(prog.n_passes)]
+    assert any("carried as a slot-index XOR" in s and "fx_ ^=" in s for s in srcs)
+    assert any("sw_ ? m3_ : m0_" in s for s in srcs)                       # a 2x2 on a bit with a pending flip
+    assert any("if ((fx_ >>" in s and "sb_ ^=" in s for s in srcs)          # applied by the store addressing
+    i = next(k for k, s in enumerate(srcs) if "fx_ ^=" in s)
+    assert prog.jit_compile(i) > 10000
